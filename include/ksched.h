@@ -1,0 +1,259 @@
+/*
+ * ksched — B200-native drop-in for Karpenter's provisioning scheduler hot path.
+ *
+ * C-ABI boundary: plain pointers and sizes only. A cgo shim in the reference would marshal the
+ * arguments of scheduling.NewScheduler (pkg/controllers/provisioning/scheduling/scheduler.go:42-45)
+ * into ksched_catalog + ksched_problem, call ksched_solve in place of (*Scheduler).Solve
+ * (scheduler.go:96), and rebuild []*Node / []*ExistingNode from ksched_result (INTEGRATION.md shows
+ * the stub). Every buffer is caller-allocated and caller-owned; the library keeps no pointer to caller
+ * memory after a call returns (cgo pointer rules). Unschedulable pods are data (assign = -1), never
+ * errors — Solve itself never fails in the reference (scheduler.go:132).
+ *
+ * Encoding (done by the caller; karpenter-core_b200/host/encoder.cc is the C++ version):
+ *  - label keys are dictionary ids; up to KSCHED_MAX_KEYS "mask keys", each with <= 63 distinct values,
+ *    one bit per value. kubernetes.io/hostname and node.kubernetes.io/instance-type are NOT mask keys:
+ *    a node's hostname is its slot index, an instance-type requirement is a bitset over types.
+ *  - a requirement mirrors pkg/scheduling/requirement.go:36-42 exactly: {complement, values, >gt, <lt};
+ *    `values` are the members (complement=0) or the excluded members (complement=1).
+ *  - resource quantities are int64 milli-units (k8s resource.Quantity, exact for whole milli values).
+ *  - instance types ("columns") are supplied in ascending (cheapest available offering price, input
+ *    index) order; type_input_index maps back to the caller's slice order (lo.Filter keeps input order,
+ *    node.go:138).
+ */
+#ifndef KSCHED_H
+#define KSCHED_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSCHED_ABI_VERSION 1
+#define KSCHED_MAX_KEYS 16
+#define KSCHED_MAX_RES 8
+#define KSCHED_MAX_TEMPLATES 16
+#define KSCHED_ROW_WORDS 32 /* canonical 256-byte rows (B_pod = B_col = 256 B) */
+#define KSCHED_KEY_HOSTNAME 255
+#define KSCHED_NONE 0xFFFFFFFFu
+
+/* error codes (negative) */
+#define KSCHED_OK 0
+#define KSCHED_ERR_INVALID -1     /* bad argument / inconsistent sizes */
+#define KSCHED_ERR_UNSUPPORTED -2 /* problem uses a feature the encoding cannot express (fail loudly) */
+#define KSCHED_ERR_CUDA -3
+#define KSCHED_ERR_NCCL -4
+#define KSCHED_ERR_NO_DEVICE -5
+#define KSCHED_ERR_OVERFLOW -6 /* a capacity bound (max new nodes, queue) was exceeded */
+
+/* meta word of a requirement set (16 keys): bit k of each 16-bit field */
+#define KSCHED_META_PRESENT_SHIFT 0
+#define KSCHED_META_COMPLEMENT_SHIFT 16
+#define KSCHED_META_HASGT_SHIFT 32
+#define KSCHED_META_HASLT_SHIFT 48
+
+/* A set of requirements over the mask keys: replaces scheduling.Requirements (requirements.go:33). */
+typedef struct ksched_reqset {
+  uint64_t values[KSCHED_MAX_KEYS];
+  uint64_t meta;
+} ksched_reqset; /* 136 bytes */
+
+/* Optional integer bounds (Gt/Lt, requirement.go:58-66) for one reqset; only read where meta has HASGT/HASLT. */
+typedef struct ksched_bounds {
+  int64_t gt[KSCHED_MAX_KEYS];
+  int64_t lt[KSCHED_MAX_KEYS];
+} ksched_bounds;
+
+/*
+ * 256-byte pod-class row. One row per class of pods that are indistinguishable to the scheduler
+ * (same requests, requirements, tolerations, host ports, topology terms); every relaxation level
+ * (preferences.go:36-56) of a pod is its own class, chained by relax_next.
+ * Replaces: resources.RequestsForPods (utils/resources/resources.go:25), NewPodRequirements
+ * (requirements.go:61), Taints.Tolerates (taints.go:28), HostPortUsage entries (hostportusage.go:118).
+ */
+typedef struct ksched_pod_row {
+  int64_t requests[KSCHED_MAX_RES]; /* includes pods: 1000 */
+  uint64_t values[KSCHED_MAX_KEYS]; /* NewPodRequirements on the mask keys */
+  uint64_t meta;
+  uint64_t tolerated_taintsets; /* bit s: pod tolerates every taint of taint set s */
+  uint64_t hostport_conflicts;  /* host-port entries this pod's ports clash with (hostportusage.go:45-57) */
+  uint64_t hostport_entries;    /* host-port entries this pod reserves */
+  uint32_t res_present;         /* bit r: resource r is a key of the pod's request map */
+  uint32_t relax_next;          /* class after one successful Relax, or KSCHED_NONE */
+  uint32_t itype_req;           /* index into problem.itype_req_sets (instance-type key), or KSCHED_NONE */
+  uint32_t hostname_req;        /* index into problem.hostname_reqs, or KSCHED_NONE */
+  uint32_t topo_begin, topo_end; /* range in problem.class_topo (groups that constrain / record this class) */
+  uint64_t reserved;
+} ksched_pod_row; /* 256 bytes */
+
+/* 256-byte instance-type column. Replaces cloudprovider.InstanceType (cloudprovider/types.go:72-85). */
+typedef struct ksched_type_row {
+  int64_t allocatable[KSCHED_MAX_RES]; /* Capacity - Overhead.Total(), types.go:87-89; 0 where absent */
+  uint64_t values[KSCHED_MAX_KEYS];
+  uint64_t meta;
+  uint64_t offerings;        /* bit (ct*16 + zone): an AVAILABLE offering exists (node.go:151-159) */
+  uint64_t template_members; /* bit v: type is in template v's GetInstanceTypes list */
+  double min_price;          /* cheapest available offering */
+  uint32_t res_present;      /* resources present in Capacity */
+  uint32_t input_index;      /* position in the caller's instance-type slice */
+  uint64_t reserved[3];
+} ksched_type_row; /* 256 bytes */
+
+typedef struct ksched_template {
+  ksched_reqset reqs;               /* NewMachineTemplate requirements (machinetemplate.go:46-62) */
+  int64_t daemon_requests[KSCHED_MAX_RES]; /* getDaemonOverhead (scheduler.go:250-267); includes pods */
+  uint32_t daemon_res_present;
+  uint32_t taintset;                /* index of this template's taint set */
+  int32_t has_limits;               /* provisioner.Spec.Limits != nil */
+  uint32_t limit_present;           /* resources that are keys of the limits map */
+  int64_t remaining[KSCHED_MAX_RES]; /* remainingResources after calculateExistingMachines */
+} ksched_template;
+
+/* dictionary facts the kernels need */
+typedef struct ksched_keyinfo {
+  uint64_t dict_mask;   /* bits of the values that exist for this key */
+  uint64_t int_mask;    /* values that parse as integers (strconv.Atoi), for Gt/Lt */
+  int32_t well_known;   /* key is in v1alpha5.WellKnownLabels (requirements.go:125) */
+  int32_t is_zone;      /* topology.kubernetes.io/zone */
+  int32_t is_capacity_type; /* karpenter.sh/capacity-type */
+  int32_t pad;
+} ksched_keyinfo;
+
+typedef struct ksched_catalog {
+  int32_t n_keys, n_res, n_types, n_templates;
+  const ksched_keyinfo* keys;      /* [n_keys] */
+  const int64_t* key_int_values;   /* [n_keys][64] integer value of dictionary entry, where int_mask set; may be NULL */
+  const ksched_type_row* types;    /* [n_types], price order */
+  const ksched_bounds* type_bounds; /* [n_types] or NULL */
+  const int64_t* type_capacity;    /* [n_types][KSCHED_MAX_RES] Capacity (limits bookkeeping, scheduler.go:273-309) */
+  const ksched_template* templates; /* [n_templates], weight order (v1alpha5/provisioner.go:132) */
+  const ksched_bounds* template_bounds; /* [n_templates] or NULL */
+} ksched_catalog;
+
+/* Existing (real / in-flight) node: NewExistingNode, existingnode.go:41-75. */
+typedef struct ksched_existing_node {
+  ksched_reqset reqs;                 /* NewLabelRequirements(node.Labels) on the mask keys */
+  int64_t available[KSCHED_MAX_RES];  /* state.Node.Available(), state/node.go:113 */
+  int64_t requests[KSCHED_MAX_RES];   /* remaining daemonset overhead, clamped >= 0 */
+  uint32_t available_present, requests_present;
+  uint32_t taintset;
+  uint32_t itype;                     /* node's instance-type label as a type column, or KSCHED_NONE */
+  uint64_t hostport_entries;          /* entries already reserved by bound pods */
+  uint64_t label_keys_other;          /* reserved */
+} ksched_existing_node;
+
+/* topology group: TopologyGroup, topologygroup.go:53-64 */
+typedef struct ksched_topo_group {
+  uint8_t type;      /* 0 spread, 1 pod affinity, 2 pod anti-affinity */
+  uint8_t key;       /* mask key index or KSCHED_KEY_HOSTNAME */
+  uint8_t inverse;   /* lives in Topology.inverseTopologies (topology.go:47) */
+  uint8_t pad;
+  int32_t max_skew;
+  uint32_t filter_begin, filter_end; /* TopologyNodeFilter terms in problem.filter_terms; empty = always matches */
+  uint64_t registered;               /* mask-key groups: domains the group knows (universe + recorded) */
+  int32_t extra_nonzero_domains;     /* hostname groups: counted domains that are not schedulable node slots */
+  int32_t pad2;
+} ksched_topo_group;
+
+/* one (class, group) relation */
+#define KSCHED_TOPO_CONSTRAINS 1 /* group is owned by the class, or is an inverse group selecting it (topology.go:351-364) */
+#define KSCHED_TOPO_SELECTS 2    /* TopologyGroup.selects(pod), topologygroup.go:246 */
+#define KSCHED_TOPO_RECORDS 4    /* group in Topology.topologies and selects the class (topology.go:122-135) */
+#define KSCHED_TOPO_RECORDS_INVERSE 8 /* inverse group owned by the class (topology.go:138-142) */
+typedef struct ksched_class_topo {
+  uint32_t group;
+  uint32_t flags;
+} ksched_class_topo;
+
+typedef struct ksched_problem {
+  int32_t n_pods, n_classes, n_existing, n_groups;
+  const ksched_pod_row* classes;     /* [n_classes] */
+  const ksched_bounds* class_bounds; /* [n_classes] or NULL */
+  const uint32_t* pod_class;         /* [n_pods] initial class of every pod, caller order */
+  const int64_t* pod_timestamp;      /* [n_pods] creationTimestamp seconds (queue.go:100) */
+  const uint32_t* pod_uid_rank;      /* [n_pods] rank of the pod's UID in ascending string order (queue.go:108) */
+  const ksched_existing_node* existing; /* [n_existing], caller order */
+  const ksched_bounds* existing_bounds; /* or NULL */
+  const ksched_topo_group* groups;   /* [n_groups] */
+  const int32_t* group_domain_counts; /* [n_groups][64] initial per-domain counts of mask-key groups (countDomains) */
+  const int32_t* group_existing_counts; /* [n_groups][n_existing] initial counts of hostname groups per existing node */
+  const ksched_class_topo* class_topo; /* ranges referenced by pod rows */
+  int32_t n_class_topo;
+  const ksched_reqset* filter_terms;  /* TopologyNodeFilter requirement sets */
+  int32_t n_filter_terms;
+  const uint64_t* itype_req_sets;     /* [n_itype_reqs][type_words]: allowed types per instance-type requirement */
+  const uint8_t* itype_req_complement; /* [n_itype_reqs] 1 = NotIn/Exists form (allows types outside the catalog) */
+  int32_t n_itype_reqs;
+  const int32_t* hostname_reqs;       /* [n_hostname_reqs][2]: {complement, existing node slot or -1 (= none of ours)} */
+  int32_t n_hostname_reqs;
+  int32_t max_new_nodes;              /* capacity for new nodes (<= n_pods) */
+  int32_t write_feasibility;          /* also copy the dense feasibility bitmask back (result.feasibility) */
+} ksched_problem;
+
+typedef struct ksched_new_node {
+  int32_t template_index;
+  int32_t pod_count;
+  int64_t requests[KSCHED_MAX_RES];
+  uint32_t requests_present;
+  uint32_t pad;
+  ksched_reqset reqs; /* final requirements on the mask keys (hostname removed, node.go:111-115) */
+} ksched_new_node;
+
+typedef struct ksched_result {
+  int32_t* assign;       /* [n_pods] -1 | existing slot | n_existing + new node index (creation order) */
+  int32_t* relax_level;  /* [n_pods] successful Relax calls */
+  int32_t* place_seq;    /* [n_pods] order in which the pod was committed (-1 if never) */
+  ksched_new_node* new_nodes; /* [max_new_nodes] */
+  uint64_t* new_node_types;   /* [max_new_nodes][type_words] surviving InstanceTypeOptions bitset (price order) */
+  ksched_reqset* existing_reqs; /* [n_existing] final requirements, or NULL */
+  uint64_t* feasibility; /* [n_pods][n_templates][type_words] dense pods x columns bitmask, or NULL */
+  uint64_t* best_column; /* [n_pods] min over feasible columns of (f32 price bits << 32 | template << 24 | type), or NULL */
+  int32_t n_new_nodes;
+  int32_t n_unscheduled;
+  int64_t nodes_visited; /* candidate nodes examined, reference scan order (SURVEY.md 8d K2 bytes) */
+  int64_t add_calls;     /* queue pops = Scheduler.add calls */
+} ksched_result;
+
+typedef struct ksched_timings {
+  double upload_us, sort_us, feasibility_us, pack_us, download_us, total_us, allreduce_us;
+  int64_t feasibility_bytes; /* P*256 + C*256 + P*C/8 for the last solve */
+  int64_t pack_steps;
+  int32_t feasibility_launches, pack_launches, sort_launches;
+  int32_t pad;
+} ksched_timings;
+
+typedef struct ksched_handle ksched_handle;
+
+int ksched_abi_version(void);
+/* number of CUDA devices visible, or a negative error */
+int ksched_device_count(void);
+/* Bind a handle to one CUDA device. One handle = one stream, single-threaded; handles are independent. */
+int ksched_create(int device_ordinal, ksched_handle** out);
+void ksched_destroy(ksched_handle* h);
+const char* ksched_last_error(const ksched_handle* h);
+/* words (uint64) per instance-type bitset for n_types types */
+int ksched_type_words(int n_types);
+
+/* Upload the instance-type catalog + templates and build the bit-sliced type tables (amortised across solves). */
+int ksched_load_catalog(ksched_handle* h, const ksched_catalog* catalog);
+/* Column sharding for multi-GPU feasibility: this handle owns types [begin, end). Default: all. */
+int ksched_set_shard(ksched_handle* h, int rank, int world);
+/* NCCL: rank 0 calls ksched_nccl_unique_id, the host distributes the 128 bytes, every rank calls ksched_nccl_init. */
+int ksched_nccl_unique_id(void* out128);
+int ksched_nccl_init(ksched_handle* h, const void* id128, int rank, int world);
+
+/* Scheduler.Solve: host buffers in, host buffers out; stream-synchronised before returning. */
+int ksched_solve(ksched_handle* h, const ksched_problem* problem, ksched_result* result);
+
+/* Device-resident benchmarking of the same path: upload once, then time kernels only. */
+int ksched_upload(ksched_handle* h, const ksched_problem* problem);
+int ksched_run_resident(ksched_handle* h, int flush_l2);
+int ksched_download(ksched_handle* h, const ksched_problem* problem, ksched_result* result);
+int ksched_run_feasibility_only(ksched_handle* h, int flush_l2, float* elapsed_us);
+
+int ksched_get_timings(const ksched_handle* h, ksched_timings* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSCHED_H */

@@ -1,0 +1,59 @@
+"""In-tree build of the native pieces (no JIT cache: the built .so files travel to the GPU box).
+
+  csrc/ksched.cu + host/*.cc  ->  karpenter-core_b200/libksched.so   (C-ABI of include/ksched.h + host layer)
+  oracle/                     ->  oracle/_build/liboracle.so          (test infrastructure; `make -C oracle`)
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+HOST_SRCS = ["loader.cc", "synth.cc", "result_io.cc", "encoder.cc", "scheduler.cc"]
+CUDA_SRCS = ["ksched.cu"]
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(s).stat().st_mtime > t for s in sources)
+
+
+def _run(cmd):
+    print("+", " ".join(str(c) for c in cmd), flush=True)
+    subprocess.check_call([str(c) for c in cmd])
+
+
+def build_product(force=False, verbose_ptxas=False):
+    out = PKG / "libksched.so"
+    srcs = [PKG / "host" / s for s in HOST_SRCS] + [PKG / "csrc" / s for s in CUDA_SRCS]
+    deps = srcs + list((PKG / "host").glob("*.h")) + list((PKG / "csrc").glob("*.cuh")) + list((ROOT / "include").glob("*.h"))
+    if not force and not _newer(out, deps):
+        return out
+    cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-Wall",
+           "-I", ROOT / "include", "-I", PKG / "host", "-I", PKG / "csrc", "-o", out, *srcs, "-lnccl"]
+    if verbose_ptxas:
+        cmd.insert(1, "-Xptxas=-v")
+    _run(cmd)
+    return out
+
+
+def build_oracle(force=False):
+    if force:
+        _run(["make", "-C", ROOT / "oracle", "clean"])
+    _run(["make", "-C", ROOT / "oracle"])
+    return ROOT / "oracle" / "_build" / "liboracle.so"
+
+
+def build_all(force=False):
+    build_product(force)
+    build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)

@@ -1,0 +1,124 @@
+// Result accessors shared by every producer of a kmodel::Result (the GPU scheduler facade and,
+// in tests, the oracle): flat copies for numpy, a canonical JSON dump, and a 64-bit digest.
+#include <cstring>
+#include <sstream>
+
+#include "loader.h"
+#include "model.h"
+#include "synth.h"
+
+using namespace kmodel;
+
+static uint64_t fnv(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+  return h;
+}
+static uint64_t fnv_str(uint64_t h, const std::string& s) { h = fnv(h, s.data(), s.size()); return fnv(h, "\0", 1); }
+static void json_str(std::ostringstream& o, const std::string& s) {
+  o << '"';
+  for (char c : s) { if (c == '"' || c == '\\') o << '\\'; o << c; }
+  o << '"';
+}
+static thread_local std::string g_err;
+
+extern "C" {
+const char* kh_last_error() { return g_err.c_str(); }
+
+Problem* kh_problem_from_json(const char* text) {
+  try { return problem_from_json(text); } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+Problem* kh_problem_synth(int config, long long n_pods, long long n_types, unsigned long long seed, long long n_nodes) {
+  try { return synth_problem(config, n_pods, n_types, seed, n_nodes); } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void kh_problem_free(Problem* p) { delete p; }
+// counts: [pods, instance types, provisioners, nodes, daemonset pods, bound pods]
+void kh_problem_counts(const Problem* p, long long* out) {
+  out[0] = (long long)p->pods.size();
+  out[1] = (long long)p->instance_types.size();
+  out[2] = (long long)p->provisioners.size();
+  out[3] = (long long)p->nodes.size();
+  out[4] = (long long)p->daemonset_pods.size();
+  long long b = 0;
+  for (auto& n : p->nodes) b += (long long)n.pods.size();
+  out[5] = b;
+}
+long long kh_parse_quantity(const char* s) {
+  try { return parse_quantity_milli(s); } catch (const std::exception& e) { g_err = e.what(); return INT64_MIN; }
+}
+
+Result* kh_result_new() { return new Result(); }
+void kh_result_free(Result* r) { delete r; }
+const char* kh_result_error(const Result* r) { return r->error.c_str(); }
+long long kh_result_num_pods(const Result* r) { return (long long)r->assign.size(); }
+long long kh_result_num_new_nodes(const Result* r) { return (long long)r->new_nodes.size(); }
+long long kh_result_num_existing(const Result* r) { return (long long)r->existing_node_index.size(); }
+long long kh_result_nodes_visited(const Result* r) { return r->nodes_visited; }
+long long kh_result_add_calls(const Result* r) { return r->add_calls; }
+void kh_result_assign(const Result* r, int* out) { std::memcpy(out, r->assign.data(), r->assign.size() * sizeof(int32_t)); }
+void kh_result_relax(const Result* r, int* out) { std::memcpy(out, r->relax_level.data(), r->relax_level.size() * sizeof(int32_t)); }
+// per new node: [provisioner, n_pods, n_options]
+void kh_result_new_node_info(const Result* r, int* out) {
+  for (size_t i = 0; i < r->new_nodes.size(); ++i) {
+    out[3 * i] = r->new_nodes[i].provisioner;
+    out[3 * i + 1] = (int)r->new_nodes[i].pods.size();
+    out[3 * i + 2] = (int)r->new_nodes[i].instance_type_options.size();
+  }
+}
+long long kh_result_new_node_options(const Result* r, long long i, int* out, long long cap) {
+  auto& v = r->new_nodes.at(i).instance_type_options;
+  for (size_t k = 0; k < v.size() && (long long)k < cap; ++k) out[k] = v[k];
+  return (long long)v.size();
+}
+// Order-sensitive digest of everything parity is judged on: assignment, relax levels, and for every new node
+// its provisioner, pods, surviving instance-type options, requests and final requirements.
+unsigned long long kh_result_digest(const Result* r) {
+  uint64_t h = 1469598103934665603ULL;
+  h = fnv(h, r->assign.data(), r->assign.size() * 4);
+  h = fnv(h, r->relax_level.data(), r->relax_level.size() * 4);
+  for (auto& n : r->new_nodes) {
+    h = fnv(h, &n.provisioner, 4);
+    h = fnv(h, n.pods.data(), n.pods.size() * 4);
+    h = fnv(h, n.instance_type_options.data(), n.instance_type_options.size() * 4);
+    for (auto& kv : n.requests) { h = fnv_str(h, kv.first); h = fnv(h, &kv.second, 8); }
+    for (auto& kv : n.requirements) { h = fnv_str(h, kv.first); h = fnv_str(h, kv.second); }
+  }
+  for (auto& e : r->existing_pods) h = fnv(h, e.data(), e.size() * 4);
+  return h;
+}
+// Canonical JSON dump (small problems). Returns the required size; writes only if it fits.
+long long kh_result_to_json(const Result* r, char* buf, long long cap) {
+  std::ostringstream o;
+  o << "{\"error\":";
+  json_str(o, r->error);
+  o << ",\"assign\":[";
+  for (size_t i = 0; i < r->assign.size(); ++i) o << (i ? "," : "") << r->assign[i];
+  o << "],\"relax\":[";
+  for (size_t i = 0; i < r->relax_level.size(); ++i) o << (i ? "," : "") << r->relax_level[i];
+  o << "],\"existing\":[";
+  for (size_t e = 0; e < r->existing_pods.size(); ++e) {
+    o << (e ? "," : "") << "{\"node\":" << r->existing_node_index[e] << ",\"pods\":[";
+    for (size_t i = 0; i < r->existing_pods[e].size(); ++i) o << (i ? "," : "") << r->existing_pods[e][i];
+    o << "]}";
+  }
+  o << "],\"newNodes\":[";
+  for (size_t n = 0; n < r->new_nodes.size(); ++n) {
+    auto& nn = r->new_nodes[n];
+    o << (n ? "," : "") << "{\"provisioner\":" << nn.provisioner << ",\"pods\":[";
+    for (size_t i = 0; i < nn.pods.size(); ++i) o << (i ? "," : "") << nn.pods[i];
+    o << "],\"options\":[";
+    for (size_t i = 0; i < nn.instance_type_options.size(); ++i) o << (i ? "," : "") << nn.instance_type_options[i];
+    o << "],\"requests\":{";
+    bool first = true;
+    for (auto& kv : nn.requests) { o << (first ? "" : ","); json_str(o, kv.first); o << ":" << kv.second; first = false; }
+    o << "},\"requirements\":{";
+    first = true;
+    for (auto& kv : nn.requirements) { o << (first ? "" : ","); json_str(o, kv.first); o << ":"; json_str(o, kv.second); first = false; }
+    o << "}}";
+  }
+  o << "],\"nodesVisited\":" << r->nodes_visited << ",\"addCalls\":" << r->add_calls << "}";
+  std::string s = o.str();
+  if ((long long)s.size() + 1 <= cap) std::memcpy(buf, s.c_str(), s.size() + 1);
+  return (long long)s.size() + 1;
+}
+}

@@ -1,0 +1,32 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see requirements.h header).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../karpenter-core_b200/host/model.h"
+#include "requirements.h"
+
+namespace oracle {
+
+// pkg/utils/resources/resources.go:25-33
+kmodel::ResourceList requests_for_pods(const std::vector<const kmodel::Pod*>& pods);
+
+// One Scheduler.Solve (scheduler.go:96) over the pods/nodes a reconcile would hand it:
+// candidates == {}  -> Provisioner.Reconcile's view (provisioner.go:119-144)
+// candidates != {}  -> simulateScheduling's view (deprovisioning/helpers.go:42-93); Result.assign
+// is indexed over [P.pods..., candidates' pods in order..., deleting nodes' pods].
+void solve(const kmodel::Problem& P, const std::vector<int>& candidates, kmodel::Result& out);
+
+struct ConsolidationResult {
+  int action = 0;         // 0 do nothing, 1 delete, 2 replace (consolidation.go actions)
+  int nodes_removed = 0;  // largest feasible prefix of the cost-ordered candidates
+  std::vector<int> replacement_options;  // instance type indices after price filters
+  std::vector<int> candidate_order;      // node indices in disruption-cost order
+  std::vector<int> probes, probe_actions;  // binary-search trace (prefix length, action)
+  int simulations = 0;
+  std::string error;
+};
+// MultiNodeConsolidation.firstNNodeConsolidationOption (multinodeconsolidation.go:74-114)
+void consolidate(const kmodel::Problem& P, ConsolidationResult& out);
+
+}  // namespace oracle
