@@ -220,6 +220,7 @@ typedef struct ksched_timings {
   int64_t pack_steps;
   int32_t feasibility_launches, pack_launches, sort_launches;
   int32_t pad;
+  int64_t h2d_bytes, d2h_bytes; /* host<->device bytes moved by the last ksched_solve (upload + download) */
 } ksched_timings;
 
 typedef struct ksched_handle ksched_handle;

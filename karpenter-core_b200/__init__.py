@@ -1,0 +1,321 @@
+"""karpenter-core_b200 — B200-native drop-in for Karpenter's provisioning scheduler hot path.
+
+Python is only the test / bench harness here: every call goes through the C-ABI library
+`libksched.so` (include/ksched.h + the C++ host layer in host/). There is no Python or CPU
+implementation of the solver in this package; without the CUDA extension the calls raise.
+
+Names mirror the reference: `Scheduler.solve` <-> scheduling.Scheduler.Solve (scheduler.go:96),
+`simulate_scheduling` <-> deprovisioning.simulateScheduling (helpers.go:42),
+`MultiNodeConsolidation.first_n_node_consolidation_option` <-> multinodeconsolidation.go:74.
+"""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libksched.so"
+
+KSCHED_OK = 0
+KSCHED_ERR_INVALID = -1
+KSCHED_ERR_UNSUPPORTED = -2
+KSCHED_ERR_CUDA = -3
+KSCHED_ERR_NCCL = -4
+KSCHED_ERR_NO_DEVICE = -5
+KSCHED_ERR_OVERFLOW = -6
+
+# every symbol include/ksched.h declares
+ABI_SYMBOLS = [
+    "ksched_abi_version", "ksched_device_count", "ksched_create", "ksched_destroy", "ksched_last_error",
+    "ksched_type_words", "ksched_load_catalog", "ksched_set_shard", "ksched_nccl_unique_id", "ksched_nccl_init",
+    "ksched_solve", "ksched_upload", "ksched_run_resident", "ksched_download", "ksched_run_feasibility_only",
+    "ksched_get_timings",
+]
+
+
+class KschedError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"ksched error {code}: {message}")
+        self.code = code
+
+
+class Timings(C.Structure):
+    _fields_ = [("upload_us", C.c_double), ("sort_us", C.c_double), ("feasibility_us", C.c_double), ("pack_us", C.c_double),
+                ("download_us", C.c_double), ("total_us", C.c_double), ("allreduce_us", C.c_double),
+                ("feasibility_bytes", C.c_int64), ("pack_steps", C.c_int64),
+                ("feasibility_launches", C.c_int32), ("pack_launches", C.c_int32), ("sort_launches", C.c_int32), ("pad", C.c_int32),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}
+
+
+_lib = None
+
+
+def lib():
+    """Load libksched.so (fails loudly when the extension was not built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the solver)")
+    L = C.CDLL(str(LIB_PATH))
+    L.kh_last_error.restype = C.c_char_p
+    L.kh_scheduler_error.restype = C.c_char_p
+    L.kh_problem_from_json.restype = C.c_void_p
+    L.kh_problem_from_json.argtypes = [C.c_char_p]
+    L.kh_problem_synth.restype = C.c_void_p
+    L.kh_problem_synth.argtypes = [C.c_int, C.c_longlong, C.c_longlong, C.c_ulonglong, C.c_longlong]
+    L.kh_problem_free.argtypes = [C.c_void_p]
+    L.kh_problem_counts.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    L.kh_parse_quantity.restype = C.c_longlong
+    L.kh_parse_quantity.argtypes = [C.c_char_p]
+    L.kh_result_new.restype = C.c_void_p
+    L.kh_result_free.argtypes = [C.c_void_p]
+    L.kh_result_error.restype = C.c_char_p
+    L.kh_result_error.argtypes = [C.c_void_p]
+    for name in ("kh_result_num_pods", "kh_result_num_new_nodes", "kh_result_num_existing", "kh_result_nodes_visited", "kh_result_add_calls"):
+        getattr(L, name).restype = C.c_longlong
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.kh_result_assign.argtypes = [C.c_void_p, C.c_void_p]
+    L.kh_result_relax.argtypes = [C.c_void_p, C.c_void_p]
+    L.kh_result_new_node_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.kh_result_new_node_options.restype = C.c_longlong
+    L.kh_result_new_node_options.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong]
+    L.kh_result_digest.restype = C.c_ulonglong
+    L.kh_result_digest.argtypes = [C.c_void_p]
+    L.kh_result_to_json.restype = C.c_longlong
+    L.kh_result_to_json.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+    L.kh_set_device.argtypes = [C.c_int]
+    L.kh_handle.restype = C.c_void_p
+    L.kh_scheduler_solve.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+    L.kh_encode.restype = C.c_void_p
+    L.kh_encode.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    L.kh_encoded_free.argtypes = [C.c_void_p]
+    L.kh_encoded_dims.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    L.kh_gpu_load.argtypes = [C.c_void_p]
+    L.kh_gpu_run.argtypes = [C.c_int]
+    L.kh_gpu_run_feasibility.argtypes = [C.c_int, C.POINTER(C.c_float)]
+    L.kh_gpu_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.kh_gpu_timings.argtypes = [C.POINTER(Timings)]
+    L.kh_gpu_solve_e2e.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    L.kh_gpu_load_catalog.argtypes = [C.c_void_p]
+    L.kh_consolidate.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                 C.POINTER(C.c_int)]
+    L.kh_mask_intersection.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_longlong)]
+    L.kh_mask_allowed.restype = C.c_longlong
+    L.kh_mask_allowed.argtypes = [C.c_char_p, C.c_char_p]
+    L.kh_mask_compatible.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    L.ksched_device_count.restype = C.c_int
+    L.ksched_abi_version.restype = C.c_int
+    L.ksched_nccl_unique_id.argtypes = [C.c_void_p]
+    L.ksched_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ksched_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    _lib = L
+    return L
+
+
+def device_count():
+    n = lib().ksched_device_count()
+    return max(n, 0)
+
+
+def _check(rc):
+    if rc != KSCHED_OK:
+        raise KschedError(rc, lib().kh_scheduler_error().decode())
+
+
+class Problem:
+    """The inputs of NewScheduler + Solve (see host/model.h for the fields)."""
+
+    def __init__(self, ptr):
+        if not ptr:
+            raise ValueError(lib().kh_last_error().decode())
+        self.ptr = ptr
+
+    @classmethod
+    def from_dict(cls, d):
+        return cls(lib().kh_problem_from_json(json.dumps(d).encode()))
+
+    @classmethod
+    def synth(cls, config, n_pods, n_types, seed=42, n_nodes=0):
+        """BASELINE.json configurations C1..C5."""
+        return cls(lib().kh_problem_synth(config, n_pods, n_types, seed, n_nodes))
+
+    def counts(self):
+        out = (C.c_longlong * 6)()
+        lib().kh_problem_counts(self.ptr, out)
+        return dict(zip(["pods", "instance_types", "provisioners", "nodes", "daemonset_pods", "bound_pods"], list(out)))
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.kh_problem_free(self.ptr)
+            self.ptr = None
+
+
+class Result:
+    """([]*Node, []*ExistingNode) of Scheduler.Solve as flat data."""
+
+    def __init__(self):
+        self.ptr = lib().kh_result_new()
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.kh_result_free(self.ptr)
+            self.ptr = None
+
+    @property
+    def error(self):
+        return lib().kh_result_error(self.ptr).decode()
+
+    @property
+    def assign(self):
+        n = lib().kh_result_num_pods(self.ptr)
+        out = np.empty(n, dtype=np.int32)
+        lib().kh_result_assign(self.ptr, out.ctypes.data)
+        return out
+
+    @property
+    def relax_level(self):
+        n = lib().kh_result_num_pods(self.ptr)
+        out = np.empty(n, dtype=np.int32)
+        lib().kh_result_relax(self.ptr, out.ctypes.data)
+        return out
+
+    @property
+    def num_new_nodes(self):
+        return lib().kh_result_num_new_nodes(self.ptr)
+
+    @property
+    def num_existing(self):
+        return lib().kh_result_num_existing(self.ptr)
+
+    @property
+    def nodes_visited(self):
+        return lib().kh_result_nodes_visited(self.ptr)
+
+    @property
+    def add_calls(self):
+        return lib().kh_result_add_calls(self.ptr)
+
+    def new_node_info(self):
+        """[n_new, 3] = (provisioner index in weight order, pod count, surviving instance-type options)"""
+        n = self.num_new_nodes
+        out = np.empty((n, 3), dtype=np.int32)
+        lib().kh_result_new_node_info(self.ptr, out.ctypes.data)
+        return out
+
+    def new_node_options(self, i):
+        cap = 1 << 16
+        out = np.empty(cap, dtype=np.int32)
+        n = lib().kh_result_new_node_options(self.ptr, i, out.ctypes.data, cap)
+        return out[:n].copy()
+
+    def digest(self):
+        return lib().kh_result_digest(self.ptr)
+
+    def to_dict(self):
+        need = lib().kh_result_to_json(self.ptr, None, 0)
+        buf = C.create_string_buffer(need)
+        lib().kh_result_to_json(self.ptr, buf, need)
+        return json.loads(buf.value.decode())
+
+
+def _cand_array(candidates):
+    arr = (C.c_int * max(1, len(candidates)))(*candidates)
+    return arr, len(candidates)
+
+
+class Scheduler:
+    """scheduling.Scheduler: NewScheduler(...) then Solve(pods). GPU only."""
+
+    def __init__(self, problem: Problem):
+        self.problem = problem
+
+    def solve(self, candidates=()):
+        res = Result()
+        arr, n = _cand_array(list(candidates))
+        rc = lib().kh_scheduler_solve(self.problem.ptr, arr, n, res.ptr)
+        _check(rc)
+        return res
+
+
+def simulate_scheduling(problem: Problem, nodes_to_delete):
+    """deprovisioning.simulateScheduling (helpers.go:42): re-run Solve with the candidates' pods added."""
+    return Scheduler(problem).solve(candidates=nodes_to_delete)
+
+
+class MultiNodeConsolidation:
+    def __init__(self, problem: Problem):
+        self.problem = problem
+
+    def first_n_node_consolidation_option(self):
+        out4 = (C.c_int * 4)()
+        opts = (C.c_int * 8192)()
+        probes = (C.c_int * 256)()
+        acts = (C.c_int * 256)()
+        npr = C.c_int()
+        rc = lib().kh_consolidate(self.problem.ptr, out4, opts, 8192, probes, acts, 256, C.byref(npr))
+        _check(rc)
+        return {"action": out4[0], "nodes_removed": out4[1], "simulations": out4[2], "options": list(opts[:out4[3]]),
+                "probes": list(probes[:npr.value]), "probe_actions": list(acts[:npr.value])}
+
+
+class ResidentSolve:
+    """Encode once, keep the problem in HBM, run the kernels repeatedly (bench / kernel tests)."""
+
+    def __init__(self, problem: Problem, candidates=()):
+        self.problem = problem
+        arr, n = _cand_array(list(candidates))
+        self.enc = lib().kh_encode(problem.ptr, arr, n)
+        if not self.enc:
+            raise KschedError(KSCHED_ERR_INVALID, lib().kh_scheduler_error().decode())
+        d = (C.c_longlong * 10)()
+        lib().kh_encoded_dims(self.enc, d)
+        self.dims = dict(zip(["pods", "classes", "existing", "groups", "types", "templates", "keys", "resources", "type_words", "class_topo"], list(d)))
+
+    def load(self):
+        _check(lib().kh_gpu_load(self.enc))
+
+    def load_catalog(self):
+        _check(lib().kh_gpu_load_catalog(self.enc))
+
+    def solve_e2e(self, want_result=False):
+        """ksched_solve with host buffers: upload + kernels + download. Returns (wall microseconds, Result|None)."""
+        us = C.c_double()
+        res = Result() if want_result else None
+        _check(lib().kh_gpu_solve_e2e(self.enc, res.ptr if res else None, C.byref(us)))
+        return us.value, res
+
+    def run(self, flush_l2=False):
+        _check(lib().kh_gpu_run(int(flush_l2)))
+
+    def run_feasibility(self, flush_l2=False):
+        us = C.c_float()
+        _check(lib().kh_gpu_run_feasibility(int(flush_l2), C.byref(us)))
+        return us.value
+
+    def download(self, want_feasibility=False):
+        res = Result()
+        feas = best = None
+        fptr = bptr = None
+        if want_feasibility:
+            d = self.dims
+            feas = np.zeros((d["pods"], d["templates"], d["type_words"]), dtype=np.uint64)
+            best = np.zeros(d["pods"], dtype=np.uint64)
+            fptr, bptr = feas.ctypes.data, best.ctypes.data
+        _check(lib().kh_gpu_download(self.enc, res.ptr, fptr, bptr))
+        return (res, feas, best) if want_feasibility else res
+
+    def timings(self):
+        t = Timings()
+        lib().kh_gpu_timings(C.byref(t))
+        return t.as_dict()
+
+    def __del__(self):
+        if getattr(self, "enc", None) and _lib is not None:
+            _lib.kh_encoded_free(self.enc)
+            self.enc = None

@@ -1,0 +1,1811 @@
+// ksched.cu — sm_100a kernels and the C-ABI of include/ksched.h.
+//
+//  K0  sort_keys / gather_rows   FFD order of the queue (queue.go:35-110) and the dense, FFD-ordered
+//                                P x 256 B pod-row matrix the feasibility kernel streams.
+//  K1  feasibility_kernel        dense pods x (template, instance type) bitmask F, bit-sliced over columns:
+//                                Requirements.Compatible/Intersects (requirements.go:123-206), fits /
+//                                hasOffering (node.go:143-159), Taints.Tolerates (taints.go:28) as AND/OR of
+//                                precomputed column bitsets; warp ballot/ffs gives the per-pod best column.
+//  K2  pack_kernel               the sequential first-fit of Scheduler.add (scheduler.go:174-219) with
+//                                Node.Add / ExistingNode.Add (node.go:62-107, existingnode.go:77-130),
+//                                topology domains (topology.go:120-167, topologygroup.go:88-243), queue
+//                                requeue / relaxation (scheduler.go:104-124, queue.go:44-68) in ONE persistent
+//                                CTA: candidate nodes are examined in parallel, the reference's scan order is
+//                                recovered with a block-wide argmin on (pod count, stable tie-break).
+// Integer / bitmask work only — no tensor cores by design (BASELINE.json north_star).
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+
+#include "ksched.h"
+#include "reqmask.cuh"
+
+using ksched::KeyMeta;
+using ksched::Req;
+
+#define CUDA_TRY(h, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                              \
+      return KSCHED_ERR_CUDA;                                                                     \
+    }                                                                                             \
+  } while (0)
+
+namespace {
+
+constexpr int kMaxCG = 8;        // topology groups that may constrain one pod class
+constexpr int kMaxTouched = 8;   // requirement keys one Add may touch (pod keys + topology keys)
+constexpr int kPackThreads = 1024;
+constexpr uint64_t kNoBest = ~0ull;
+
+// ------------------------------------------------------------------------------------------------
+// Device-side catalog: instance-type columns as bit-sliced tables (one bit per column, u32 words).
+// ------------------------------------------------------------------------------------------------
+struct DevCatalog {
+  int n_keys, n_res, n_types, n_templates, W32;
+  const ksched_keyinfo* keys;        // [n_keys]
+  const int64_t* key_int_values;     // [n_keys][64]
+  const ksched_template* templates;  // [n_templates]
+  const ksched_type_row* types;      // [n_types]
+  const int64_t* capacity;           // [n_types][8]
+  const float* price32;              // [n_types]
+  const int16_t* valrow;             // [n_keys*64] row in valset or -1
+  const uint32_t* valset;            // [rows][W32] type has a positive requirement on key containing value
+  const uint32_t* absent;            // [n_keys][W32] type has no requirement on key
+  const uint32_t* negempty;          // [n_keys][W32] type requirement on key is DoesNotExist
+  uint32_t type_relevant;            // bit k: some type defines key k
+  const int16_t* offrow;             // [64] row in offset table or -1
+  const uint32_t* offset;            // [rows][W32] type has an available offering (ct*16+zone)
+  const uint32_t* anyoffer;          // [W32]
+  const uint32_t* member;            // [n_templates][W32]
+  const int64_t* alloc_sorted;       // [n_res][n_types] ascending
+  const uint32_t* fitset;            // [n_res][n_types+1][W32]  rank -> types with alloc >= alloc_sorted[rank]
+  int zone_key, ct_key;
+};
+
+__device__ __forceinline__ KeyMeta key_meta(const DevCatalog& c, int k) {
+  return KeyMeta{c.keys[k].int_mask, c.key_int_values ? c.key_int_values + (size_t)k * 64 : nullptr};
+}
+
+// number of types with alloc_r < q  (lower bound)
+__device__ __forceinline__ int fit_rank(const DevCatalog& c, int r, int64_t q) {
+  const int64_t* a = c.alloc_sorted + (size_t)r * c.n_types;
+  int lo = 0, hi = c.n_types;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < q) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Column set {t : instanceType.Requirements.Intersects(node) holds on key k} for one u32 word
+// (requirements.go:189-206 with the type as receiver). `allowed` = dictionary values the node requirement
+// admits, `neg` = its operator is NotIn/DoesNotExist.
+__device__ __forceinline__ uint32_t key_typeset_word(const DevCatalog& c, int k, uint64_t allowed, bool neg, int w) {
+  uint32_t s = c.absent[(size_t)k * c.W32 + w];
+  if (neg) s |= c.negempty[(size_t)k * c.W32 + w];
+  uint64_t m = allowed;
+  while (m) {
+    int b = __ffsll((long long)m) - 1;
+    m &= m - 1;
+    int row = c.valrow[k * 64 + b];
+    if (row >= 0) s |= c.valset[(size_t)row * c.W32 + w];
+  }
+  return s;
+}
+// hasOffering (node.go:151-159) for one word: zmask / cmask = admitted zone / capacity-type value bits
+__device__ __forceinline__ uint32_t offer_word(const DevCatalog& c, uint32_t zmask, uint32_t cmask, bool unconstrained, int w) {
+  if (unconstrained) return c.anyoffer[w];
+  uint32_t s = 0;
+  uint32_t cm = cmask & 0xF;
+  while (cm) {
+    int ct = __ffs(cm) - 1;
+    cm &= cm - 1;
+    uint32_t zm = zmask & 0xFFFF;
+    while (zm) {
+      int z = __ffs(zm) - 1;
+      zm &= zm - 1;
+      int row = c.offrow[ct * 16 + z];
+      if (row >= 0) s |= c.offset[(size_t)row * c.W32 + w];
+    }
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: queue order
+// ------------------------------------------------------------------------------------------------
+__global__ void sort_keys_kernel(int n, const ksched_pod_row* __restrict__ classes, const uint32_t* __restrict__ pod_class,
+                                 const int64_t* __restrict__ ts, const uint32_t* __restrict__ uid_rank,
+                                 uint64_t* k_cpu, uint64_t* k_mem, uint64_t* k_tie, uint32_t* idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ksched_pod_row& row = classes[pod_class[i]];
+  // descending cpu / memory -> ascending on the complemented value (milli-units are < 2^62)
+  k_cpu[i] = ~(uint64_t)(row.requests[0] + (1ll << 62));
+  k_mem[i] = ~(uint64_t)(row.requests[1] + (1ll << 62));
+  k_tie[i] = ((uint64_t)(ts[i] + (1ll << 32)) << 30) | (uint64_t)uid_rank[i];
+  idx[i] = (uint32_t)i;
+}
+__global__ void gather_u64_kernel(int n, const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t* dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+// FFD-ordered dense pod-row matrix: row j = class row of the j-th pod of the queue. One warp per row,
+// 256-byte coalesced loads and stores.
+__global__ void gather_rows_kernel(int n, const ksched_pod_row* __restrict__ classes, const uint32_t* __restrict__ pod_class,
+                                   const uint32_t* __restrict__ order, uint64_t* __restrict__ rows) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int j = warp; j < n; j += nwarps) {
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(&classes[pod_class[order[j]]]);
+    rows[(size_t)j * KSCHED_ROW_WORDS + lane] = src[lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: feasibility. One warp per pod row; lane l owns column words l, l+32, ...
+// ------------------------------------------------------------------------------------------------
+struct K1Params {
+  DevCatalog cat;
+  const uint64_t* rows;  // [n_pods][32] FFD order
+  int n_pods;
+  const uint32_t* itype_sets;  // [n][W32]
+  uint32_t* F;                 // [n_pods][n_templates][W32]
+  unsigned long long* best;    // [n_pods]
+  int word_begin, word_end;    // column shard (u32 words) this device computes
+};
+
+__global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
+  const DevCatalog& c = p.cat;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int V = c.n_templates, W32 = c.W32;
+  uint64_t next_word = 0;
+  if (warp < p.n_pods) next_word = __ldg(p.rows + (size_t)warp * KSCHED_ROW_WORDS + lane);
+  for (int j = warp; j < p.n_pods; j += nwarps) {
+    const uint64_t word = next_word;  // lane l holds u64 word l of the 256-byte row
+    if (j + nwarps < p.n_pods) next_word = __ldg(p.rows + (size_t)(j + nwarps) * KSCHED_ROW_WORDS + lane);
+    const uint64_t meta = __shfl_sync(0xffffffffu, word, 24);
+    const uint64_t tolerated = __shfl_sync(0xffffffffu, word, 25);
+    const uint64_t w28 = __shfl_sync(0xffffffffu, word, 28);
+    const uint64_t w29 = __shfl_sync(0xffffffffu, word, 29);
+    const uint32_t pod_res_present = (uint32_t)w28;
+    const uint32_t itype_req = (uint32_t)w29;
+    unsigned long long best = kNoBest;
+    for (int v = 0; v < V; ++v) {
+      const ksched_template& tm = c.templates[v];
+      uint32_t* out = p.F + ((size_t)j * V + v) * W32;
+      bool ok = (tolerated >> tm.taintset) & 1;  // Taints.Tolerates
+      // lanes 8..23 own one requirement key each: Compatible + merge (node.go:73-81 on a fresh node)
+      uint64_t allowed = 0;
+      bool neg = false, present = false, compat = true;
+      const int k = lane - 8;
+      if (k >= 0 && k < c.n_keys) {
+        Req pod;
+        pod.present = (meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
+        pod.complement = (meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1;
+        pod.has_gt = pod.has_lt = false; pod.gt = pod.lt = 0;
+        pod.values = word;
+        Req node = ksched::req_load(tm.reqs, nullptr, k);
+        KeyMeta km = key_meta(c, k);
+        compat = ksched::key_compatible(node, pod, c.keys[k].well_known != 0, km);
+        Req merged = ksched::key_add(node, pod, km);
+        present = merged.present;
+        if (present) {
+          allowed = ksched::req_allowed(merged, c.keys[k].dict_mask, km);
+          neg = ksched::req_op_negative(merged);
+        }
+      }
+      ok = ok && (__ballot_sync(0xffffffffu, !compat) == 0);
+      const uint32_t present_keys = (__ballot_sync(0xffffffffu, present) >> 8) & c.type_relevant;
+      // resources: lanes 0..7 own one resource each (Fits, resources.go:138-145)
+      int rank = 0;
+      bool res_used = false;
+      if (lane < c.n_res) {
+        uint32_t pres = pod_res_present | tm.daemon_res_present;
+        res_used = (pres >> lane) & 1;
+        if (res_used) rank = fit_rank(c, lane, (int64_t)word + tm.daemon_requests[lane]);
+      }
+      const uint32_t res_mask = __ballot_sync(0xffffffffu, res_used);
+      uint64_t zallowed = 0xFFFF, callowed = 0xF;
+      bool zc_unconstrained = true;
+      if (c.zone_key >= 0) {
+        bool zp = __shfl_sync(0xffffffffu, (int)present, 8 + c.zone_key);
+        uint64_t za = __shfl_sync(0xffffffffu, allowed, 8 + c.zone_key);
+        if (zp) { zallowed = za; zc_unconstrained = false; }
+      }
+      if (c.ct_key >= 0) {
+        bool cp = __shfl_sync(0xffffffffu, (int)present, 8 + c.ct_key);
+        uint64_t ca = __shfl_sync(0xffffffffu, allowed, 8 + c.ct_key);
+        if (cp) { callowed = ca; zc_unconstrained = false; }
+      }
+      bool any = false;
+      int first_word = -1;
+      uint32_t first_bits = 0;
+      for (int w0 = 0; w0 < W32; w0 += 32) {
+        const int w = w0 + lane;
+        const bool mine = w < W32 && w >= p.word_begin && w < p.word_end;
+        uint32_t s = 0;
+        if (ok && mine) s = c.member[(size_t)v * W32 + w];
+        uint32_t pk = present_keys;
+        while (pk) {  // uniform loop: every lane walks the same keys
+          int kk = __ffs(pk) - 1;
+          pk &= pk - 1;
+          uint64_t a = __shfl_sync(0xffffffffu, allowed, 8 + kk);
+          bool ng = __shfl_sync(0xffffffffu, (int)neg, 8 + kk);
+          if (s) s &= key_typeset_word(c, kk, a, ng, w);
+        }
+        if (s) s &= offer_word(c, (uint32_t)zallowed, (uint32_t)callowed, zc_unconstrained, w);
+        uint32_t rm = res_mask;
+        while (rm) {
+          int r = __ffs(rm) - 1;
+          rm &= rm - 1;
+          int rk = __shfl_sync(0xffffffffu, rank, r);
+          if (s) s &= c.fitset[((size_t)r * (c.n_types + 1) + rk) * W32 + w];
+        }
+        if (s && itype_req != KSCHED_NONE) s &= p.itype_sets[(size_t)itype_req * W32 + w];
+        if (mine) out[w] = s;
+        uint32_t nz = __ballot_sync(0xffffffffu, s != 0);
+        if (nz && !any) {
+          any = true;
+          int src = __ffs(nz) - 1;
+          first_word = w0 + src;
+          first_bits = __shfl_sync(0xffffffffu, s, src);
+        }
+      }
+      if (any) {
+        int t = first_word * 32 + __ffs(first_bits) - 1;  // columns are in price order: first set bit = cheapest
+        unsigned long long key = ((unsigned long long)__float_as_uint(c.price32[t]) << 32) | ((unsigned long long)v << 24) | (unsigned)t;
+        best = key < best ? key : best;
+      }
+    }
+    if (lane == 0) p.best[j] = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: pack
+// ------------------------------------------------------------------------------------------------
+struct PackState {
+  // problem (read-only)
+  const ksched_pod_row* classes;
+  const ksched_topo_group* groups;
+  const ksched_class_topo* class_topo;
+  const ksched_reqset* filter_terms;
+  const uint32_t* itype_sets;        // [n][W32]
+  const uint8_t* itype_complement;
+  const int32_t* hostname_reqs;      // [n][2]
+  const uint32_t* order;             // FFD order: queue position -> pod
+  uint32_t* pod_pos;                 // pod -> FFD position (row of F / best)
+  int use_F;                         // F / best cover every column on this device (not column-sharded)
+  const uint32_t* F;                 // [n_pods][V][W32] in FFD order (nullptr: compute fresh-node types dynamically)
+  const unsigned long long* best;    // [n_pods] FFD order (after allreduce when sharded) or nullptr
+  int n_pods, n_classes, n_existing, n_groups, max_new;
+  int64_t min_req[KSCHED_MAX_RES];   // min over all classes of requests[r] (0 if some class lacks r)
+  // mutable
+  uint32_t* pod_class;               // [n_pods] current class
+  int32_t* relax_level;              // [n_pods]
+  int32_t* assign;                   // [n_pods]
+  int32_t* place_seq;                // [n_pods]
+  uint32_t* queue;                   // [n_pods+1] circular
+  int32_t* last_len;                 // [n_pods]
+  uint32_t* last_epoch;              // [n_pods]
+  // existing nodes (SoA)
+  int64_t* ex_req;                   // [8][n_existing]
+  const int64_t* ex_avail;           // [8][n_existing]
+  uint32_t* ex_req_present;
+  const uint32_t* ex_avail_present;
+  uint64_t* ex_vals;                 // [16][n_existing]
+  uint64_t* ex_meta;
+  const uint32_t* ex_taintset;
+  const uint32_t* ex_itype;
+  uint64_t* ex_hp;
+  uint8_t* ex_closed;
+  // new nodes (SoA, capacity max_new)
+  uint8_t* nn_tmpl;
+  int32_t* nn_count;
+  int32_t* nn_tb;
+  int64_t* nn_req;                   // [8][max_new]
+  uint32_t* nn_req_present;
+  int64_t* nn_maxalloc;              // [8][max_new] upper bound of allocatable over surviving options
+  int32_t* nn_argmax;                // [8][max_new] a type attaining it
+  uint64_t* nn_vals;                 // [16][max_new]
+  uint64_t* nn_meta;
+  uint32_t* nn_opts;                 // [W32][max_new]
+  uint64_t* nn_hp;
+  int32_t* active;                   // open new nodes
+  // topology counters
+  int32_t* grp_cnt;                  // [n_groups][64]
+  uint64_t* grp_registered;          // [n_groups]
+  uint16_t* grp_host;                // [n_hostgroups][n_existing+max_new]
+  const int32_t* grp_host_row;       // [n_groups] row in grp_host or -1
+  int32_t* grp_host_total;           // [n_groups] schedulable-slot domains with count > 0 (+ extra_nonzero_domains)
+  int64_t* remaining;                // [V][8] provisioner limits
+  // outputs / counters: [0]=n_new [1]=n_unscheduled [2]=nodes_visited [3]=add_calls [4]=error [5]=steps
+  long long* counters;
+};
+
+struct K2Params {
+  DevCatalog cat;
+  PackState st;
+};
+
+struct Touched {
+  int n;
+  int8_t key[kMaxTouched];
+  Req merged[kMaxTouched];  // node ∩ pod          (node.go:81)
+  Req fin[kMaxTouched];     // ... ∩ topology      (node.go:90)
+  bool changed[kMaxTouched];
+};
+
+struct PodTopo {  // per (pod step, constraining group): node-independent part of TopologyGroup.Get
+  int n;
+  int32_t group[kMaxCG];
+  uint32_t flags[kMaxCG];
+  int32_t min_count[kMaxCG];   // spread: domainMinCount over the pod's domains
+  uint64_t options[kMaxCG];    // affinity / anti-affinity: admissible domains (mask keys)
+  uint8_t bootstrap[kMaxCG];   // affinity: no domain has a matching pod and the pod selects itself
+  uint64_t pod_allowed[kMaxCG]; // pod's own admissible domains for the key
+  int overflow;
+};
+
+__device__ __forceinline__ Req load_soa(const uint64_t* vals, uint64_t meta, int stride, int idx, int k) {
+  Req r;
+  r.present = (meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
+  r.complement = (meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1;
+  r.has_gt = r.has_lt = false;
+  r.gt = r.lt = 0;
+  r.values = r.present ? vals[(size_t)k * stride + idx] : 0;
+  return r;
+}
+__device__ __forceinline__ Req pod_req(const ksched_pod_row& row, int k) {
+  Req r;
+  r.present = (row.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
+  r.complement = (row.meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1;
+  r.has_gt = r.has_lt = false;
+  r.gt = r.lt = 0;
+  r.values = row.values[k];
+  return r;
+}
+__device__ __forceinline__ bool req_equal(const Req& a, const Req& b) {
+  return a.present == b.present && a.complement == b.complement && a.values == b.values;
+}
+
+// TopologyGroup.Get for a mask-key group (topologygroup.go:88-243). node_dom = the node's requirement for the
+// key after the pod's own requirements were merged (topology.go:156-159). Returns false when Len()==0.
+__device__ bool topo_domains_mask(const DevCatalog& c, const PackState& s, const PodTopo& pt, int j, const Req& node_dom, uint64_t* out) {
+  const ksched_topo_group& g = s.groups[pt.group[j]];
+  const int gi = pt.group[j];
+  const int k = g.key;
+  KeyMeta km = key_meta(c, k);
+  const uint64_t registered = s.grp_registered[gi];
+  const uint64_t node_allowed = node_dom.present ? ksched::req_allowed(node_dom, c.keys[k].dict_mask, km) : c.keys[k].dict_mask;
+  if (g.type == 0) {  // nextDomainTopologySpread
+    const bool self = pt.flags[j] & KSCHED_TOPO_SELECTS;
+    const int32_t mn = pt.min_count[j];
+    int best = -1;
+    int32_t best_count = INT32_MAX;
+    uint64_t m = registered & node_allowed;
+    while (m) {  // ascending domain id = ascending string order (canonical rule R3)
+      int d = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      int64_t cnt = (int64_t)s.grp_cnt[(size_t)gi * 64 + d] + (self ? 1 : 0);
+      if (cnt - (int64_t)mn <= (int64_t)g.max_skew && cnt < best_count) { best = d; best_count = (int32_t)cnt; }
+    }
+    if (best < 0) return false;
+    *out = 1ull << best;
+    return true;
+  }
+  if (g.type == 1) {  // nextDomainAffinity
+    uint64_t opts = pt.options[j];
+    if (pt.bootstrap[j]) {
+      uint64_t inter = registered & pt.pod_allowed[j] & node_allowed;  // podDomains.Intersection(nodeDomains).Has
+      if (inter) opts |= inter & (~inter + 1);
+      uint64_t pm = registered & pt.pod_allowed[j];
+      if (pm) opts |= pm & (~pm + 1);
+    }
+    if (!opts) return false;
+    *out = opts;
+    return true;
+  }
+  uint64_t opts = pt.options[j];  // nextDomainAntiAffinity
+  if (!opts) return false;
+  *out = opts;
+  return true;
+}
+
+// hostname-key groups: the node's hostname domain is its slot.
+__device__ bool topo_hostname_ok(const PackState& s, const PodTopo& pt, int j, int slot, bool pod_allows_slot) {
+  const int gi = pt.group[j];
+  const ksched_topo_group& g = s.groups[gi];
+  const int row = s.grp_host_row[gi];
+  const int stride = s.n_existing + s.max_new;
+  const int32_t cnt = s.grp_host[(size_t)row * stride + slot];
+  if (g.type == 0) {  // spread, min is 0 for hostname (topologygroup.go:186-188); candidate = the node's own hostname
+    int64_t c2 = (int64_t)cnt + ((pt.flags[j] & KSCHED_TOPO_SELECTS) ? 1 : 0);
+    return c2 <= (int64_t)g.max_skew;
+  }
+  if (g.type == 1) {  // affinity
+    if (cnt > 0 && pod_allows_slot) return true;
+    if (pt.bootstrap[j]) return pod_allows_slot;  // first loop picks the node's own (registered) hostname
+    return false;
+  }
+  return cnt == 0 && pod_allows_slot;  // anti-affinity
+}
+
+// Does the pod's hostname requirement admit this slot? (requirement on kubernetes.io/hostname, never well-known)
+__device__ __forceinline__ bool hostname_allows(const PackState& s, const ksched_pod_row& row, int slot, bool is_existing) {
+  if (row.hostname_req == KSCHED_NONE) return true;
+  const int32_t comp = s.hostname_reqs[row.hostname_req * 2], target = s.hostname_reqs[row.hostname_req * 2 + 1];
+  const bool same = is_existing && target == slot;
+  return comp ? !same : same;
+}
+
+// Requirement phase of Node.Add / ExistingNode.Add: Compatible(pod) + merge, topology tighten + Compatible + merge.
+// vals/meta/stride/idx describe the node's requirement set. Returns false on reject.
+__device__ bool requirements_phase(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const PodTopo& pt,
+                                   const uint64_t* vals, uint64_t meta, int stride, int idx, int slot, bool is_existing, Touched& t) {
+  t.n = 0;
+  if (!hostname_allows(s, row, slot, is_existing)) return false;
+  uint32_t podkeys = (uint32_t)(row.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF;
+  while (podkeys) {
+    int k = __ffs(podkeys) - 1;
+    podkeys &= podkeys - 1;
+    Req node = load_soa(vals, meta, stride, idx, k);
+    Req pod = pod_req(row, k);
+    KeyMeta km = key_meta(c, k);
+    if (!ksched::key_compatible(node, pod, c.keys[k].well_known != 0, km)) return false;
+    if (t.n >= kMaxTouched) return false;
+    Req merged = ksched::key_add(node, pod, km);
+    t.key[t.n] = (int8_t)k;
+    t.merged[t.n] = merged;
+    t.fin[t.n] = merged;
+    t.changed[t.n] = !req_equal(merged, node);
+    ++t.n;
+  }
+  for (int j = 0; j < pt.n; ++j) {
+    if (!(pt.flags[j] & KSCHED_TOPO_CONSTRAINS)) continue;
+    const ksched_topo_group& g = s.groups[pt.group[j]];
+    if (g.key == KSCHED_KEY_HOSTNAME) {
+      if (!topo_hostname_ok(s, pt, j, slot, hostname_allows(s, row, slot, is_existing))) return false;
+      continue;
+    }
+    const int k = g.key;
+    int ti = -1;
+    for (int i = 0; i < t.n; ++i) if (t.key[i] == k) ti = i;
+    if (ti < 0) {
+      if (t.n >= kMaxTouched) return false;
+      ti = t.n++;
+      Req node = load_soa(vals, meta, stride, idx, k);
+      t.key[ti] = (int8_t)k;
+      t.merged[ti] = node;
+      t.fin[ti] = node;
+      t.changed[ti] = false;
+    }
+    uint64_t dom;
+    if (!topo_domains_mask(c, s, pt, j, t.merged[ti], &dom)) return false;
+    Req d{dom, 0, 0, true, false, false, false};
+    KeyMeta km = key_meta(c, k);
+    t.fin[ti] = ksched::key_add(t.fin[ti], d, km);  // requirements.Add(domains) topology.go:164
+  }
+  // nodeRequirements.Compatible(topologyRequirements) node.go:87 — only topology keys can differ
+  for (int i = 0; i < t.n; ++i) {
+    if (req_equal(t.fin[i], t.merged[i])) continue;
+    const int k = t.key[i];
+    if (!ksched::key_compatible(t.merged[i], t.fin[i], c.keys[k].well_known != 0, key_meta(c, k))) return false;
+    t.fin[i] = ksched::key_add(t.merged[i], t.fin[i], key_meta(c, k));
+    t.changed[i] = true;
+  }
+  return true;
+}
+
+// Surviving instance types of a node for one word (filterInstanceTypesByRequirements node.go:137-141):
+// previous options ∧ Fits ∧ (keys whose requirement changed) ∧ hasOffering (if zone / capacity-type changed).
+struct TypeCtx {
+  int rank[KSCHED_MAX_RES];
+  uint32_t res_mask;
+  int nkeys;
+  int8_t key[KSCHED_MAX_KEYS];
+  uint64_t allowed[KSCHED_MAX_KEYS];
+  bool neg[KSCHED_MAX_KEYS];
+  bool offer_needed, offer_unconstrained;
+  uint32_t zmask, cmask;
+  uint32_t itype_req;
+};
+__device__ void build_type_ctx(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const Touched& t, const int64_t* q,
+                               uint32_t q_present, const uint64_t* vals, uint64_t meta, int stride, int idx, bool fresh, TypeCtx& x) {
+  x.res_mask = q_present;
+  for (int r = 0; r < c.n_res; ++r) x.rank[r] = ((q_present >> r) & 1) ? fit_rank(c, r, q[r]) : 0;
+  x.nkeys = 0;
+  x.offer_needed = fresh;
+  auto add_key = [&](int k, const Req& f) {
+    if (!((c.type_relevant >> k) & 1) || !f.present) return;
+    KeyMeta km = key_meta(c, k);
+    x.key[x.nkeys] = (int8_t)k;
+    x.allowed[x.nkeys] = ksched::req_allowed(f, c.keys[k].dict_mask, km);
+    x.neg[x.nkeys] = ksched::req_op_negative(f);
+    ++x.nkeys;
+  };
+  if (fresh) {
+    // every key of the new node's requirement set is evaluated from scratch
+    uint32_t done = 0;
+    for (int i = 0; i < t.n; ++i) { add_key(t.key[i], t.fin[i]); done |= 1u << t.key[i]; }
+    uint32_t rest = ((uint32_t)(meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) & ~done;
+    while (rest) {
+      int k = __ffs(rest) - 1;
+      rest &= rest - 1;
+      add_key(k, load_soa(vals, meta, stride, idx, k));
+    }
+  } else {
+    for (int i = 0; i < t.n; ++i) {
+      if (!t.changed[i]) continue;
+      add_key(t.key[i], t.fin[i]);
+      if (t.key[i] == c.zone_key || t.key[i] == c.ct_key) x.offer_needed = true;
+    }
+  }
+  x.zmask = 0xFFFF; x.cmask = 0xF; x.offer_unconstrained = true;
+  if (x.offer_needed) {
+    auto final_req = [&](int k) -> Req {
+      for (int i = 0; i < t.n; ++i) if (t.key[i] == k) return t.fin[i];
+      return load_soa(vals, meta, stride, idx, k);
+    };
+    if (c.zone_key >= 0) {
+      Req z = final_req(c.zone_key);
+      if (z.present) { x.zmask = (uint32_t)ksched::req_allowed(z, c.keys[c.zone_key].dict_mask, key_meta(c, c.zone_key)); x.offer_unconstrained = false; }
+    }
+    if (c.ct_key >= 0) {
+      Req ct = final_req(c.ct_key);
+      if (ct.present) { x.cmask = (uint32_t)ksched::req_allowed(ct, c.keys[c.ct_key].dict_mask, key_meta(c, c.ct_key)); x.offer_unconstrained = false; }
+    }
+  }
+  x.itype_req = row.itype_req;
+}
+__device__ __forceinline__ uint32_t type_word(const DevCatalog& c, const PackState& s, const TypeCtx& x, uint32_t base, int w) {
+  uint32_t sw = base;
+  uint32_t rm = x.res_mask;
+  while (sw && rm) {
+    int r = __ffs(rm) - 1;
+    rm &= rm - 1;
+    sw &= c.fitset[((size_t)r * (c.n_types + 1) + x.rank[r]) * c.W32 + w];
+  }
+  for (int i = 0; i < x.nkeys && sw; ++i) sw &= key_typeset_word(c, x.key[i], x.allowed[i], x.neg[i], w);
+  if (sw && x.offer_needed) sw &= offer_word(c, x.zmask, x.cmask, x.offer_unconstrained, w);
+  if (sw && x.itype_req != KSCHED_NONE) sw &= s.itype_sets[(size_t)x.itype_req * c.W32 + w];
+  return sw;
+}
+
+// Node-independent part of the pod's topology constraints for this step.
+__device__ void build_pod_topo(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt) {
+  pt.n = 0;
+  pt.overflow = 0;
+  for (uint32_t e = row.topo_begin; e < row.topo_end; ++e) {
+    const ksched_class_topo ct = s.class_topo[e];
+    if (!(ct.flags & KSCHED_TOPO_CONSTRAINS)) continue;
+    if (pt.n >= kMaxCG) { pt.overflow = 1; return; }
+    const int j = pt.n++;
+    const int gi = (int)ct.group;
+    const ksched_topo_group& g = s.groups[gi];
+    pt.group[j] = gi;
+    pt.flags[j] = ct.flags;
+    pt.min_count[j] = 0;
+    pt.options[j] = 0;
+    pt.bootstrap[j] = 0;
+    pt.pod_allowed[j] = 0;
+    if (g.key == KSCHED_KEY_HOSTNAME) {
+      if (g.type == 1) {
+        // options.Len()==0 <=> no admissible hostname has a matching pod (hostname requirements on the pod are
+        // restricted to a single existing slot, handled in topo_hostname_ok)
+        pt.bootstrap[j] = (s.grp_host_total[gi] == 0) && (ct.flags & KSCHED_TOPO_SELECTS);
+      }
+      continue;
+    }
+    const int k = g.key;
+    KeyMeta km = key_meta(c, k);
+    Req pd = pod_req(row, k);
+    const uint64_t pod_allowed = pd.present ? ksched::req_allowed(pd, c.keys[k].dict_mask, km) : c.keys[k].dict_mask;
+    pt.pod_allowed[j] = pod_allowed;
+    const uint64_t registered = s.grp_registered[gi];
+    uint64_t m = registered & pod_allowed;
+    if (g.type == 0) {
+      int32_t mn = INT32_MAX;
+      while (m) {
+        int d = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        int32_t cnt = s.grp_cnt[(size_t)gi * 64 + d];
+        mn = cnt < mn ? cnt : mn;
+      }
+      pt.min_count[j] = mn;
+    } else if (g.type == 1) {
+      uint64_t opts = 0;
+      while (m) {
+        int d = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (s.grp_cnt[(size_t)gi * 64 + d] > 0) opts |= 1ull << d;
+      }
+      pt.options[j] = opts;
+      pt.bootstrap[j] = (opts == 0) && (ct.flags & KSCHED_TOPO_SELECTS);
+    } else {
+      uint64_t opts = 0;
+      while (m) {
+        int d = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (s.grp_cnt[(size_t)gi * 64 + d] == 0) opts |= 1ull << d;
+      }
+      pt.options[j] = opts;
+    }
+  }
+}
+
+// TopologyNodeFilter.MatchesRequirements (topologynodefilter.go:57-70): any term Compatible with the node requirements
+__device__ bool filter_matches(const DevCatalog& c, const PackState& s, const ksched_topo_group& g, const uint64_t* vals, uint64_t meta,
+                               int stride, int idx) {
+  if (g.filter_begin == g.filter_end) return true;
+  for (uint32_t f = g.filter_begin; f < g.filter_end; ++f) {
+    const ksched_reqset& term = s.filter_terms[f];
+    bool ok = true;
+    uint32_t keys = (uint32_t)(term.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF;
+    while (keys && ok) {
+      int k = __ffs(keys) - 1;
+      keys &= keys - 1;
+      Req node = load_soa(vals, meta, stride, idx, k);
+      Req inc = ksched::req_load(term, nullptr, k);
+      ok = ksched::key_compatible(node, inc, c.keys[k].well_known != 0, key_meta(c, k));
+    }
+    if (ok) return true;
+  }
+  return false;
+}
+
+// Topology.Record (topology.go:120-143) after the node's requirements were committed. Single thread.
+__device__ void topo_record(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const uint64_t* vals, uint64_t meta, int stride,
+                            int idx, int slot) {
+  const int hstride = s.n_existing + s.max_new;
+  for (uint32_t e = row.topo_begin; e < row.topo_end; ++e) {
+    const ksched_class_topo ct = s.class_topo[e];
+    const int gi = (int)ct.group;
+    const ksched_topo_group& g = s.groups[gi];
+    bool rec = false, all_values = false;
+    if (ct.flags & KSCHED_TOPO_RECORDS) {
+      if (filter_matches(c, s, g, vals, meta, stride, idx)) { rec = true; all_values = (g.type == 2); }
+    }
+    bool rec_inv = (ct.flags & KSCHED_TOPO_RECORDS_INVERSE) != 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool doit = pass == 0 ? rec : rec_inv;
+      const bool allv = pass == 0 ? all_values : true;
+      if (!doit) continue;
+      if (g.key == KSCHED_KEY_HOSTNAME) {  // the node's hostname requirement is always In [its own hostname]
+        uint16_t* cell = &s.grp_host[(size_t)s.grp_host_row[gi] * hstride + slot];
+        if (*cell == 0) s.grp_host_total[gi]++;
+        if (*cell < 0xFFFF) (*cell)++;
+      } else {
+        Req r = load_soa(vals, meta, stride, idx, g.key);
+        uint64_t v = 0;
+        if (allv) v = r.present ? r.values : 0;  // domains.Values(): members, or the excluded set of a complement
+        else if (r.present && ksched::req_len_one(r)) v = r.values;
+        while (v) {
+          int d = __ffsll((long long)v) - 1;
+          v &= v - 1;
+          s.grp_cnt[(size_t)gi * 64 + d]++;
+          s.grp_registered[gi] |= 1ull << d;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long* smem) {
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o);
+    v = x < v ? x : v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  unsigned long long r = smem[lane < (blockDim.x >> 5) ? lane : 0];
+  if (lane >= (blockDim.x >> 5)) r = ~0ull;
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long x = __shfl_xor_sync(0xffffffffu, r, o);
+    r = x < r ? x : r;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(K2Params p) {
+  const DevCatalog& c = p.cat;
+  const PackState& s = p.st;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W32 = c.W32, V = c.n_templates, NE = s.n_existing, MAXN = s.max_new;
+
+  __shared__ ksched_pod_row row;
+  __shared__ PodTopo pt;
+  __shared__ Touched win_t;
+  __shared__ TypeCtx win_x;
+  __shared__ unsigned long long red[32];
+  __shared__ int sh_flag, sh_useF;
+  __shared__ uint32_t sh_any;
+  __shared__ int64_t sh_q[KSCHED_MAX_RES];
+  __shared__ uint32_t sh_qp;
+
+  int head = 0, qlen = s.n_pods;  // queue[head .. head+qlen) circular, capacity n_pods+1
+  const int qcap = s.n_pods + 1;
+  int n_new = 0, n_active = 0, tick = 0, seq = 0;
+  uint32_t epoch = 1;
+  int node_id = 0;  // hostname placeholders handed out (one per NewNode attempt, node.go:46)
+  long long nodes_visited = 0, add_calls = 0, steps = 0;
+  int fatal = 0;
+
+  for (int i = tid; i < s.n_pods; i += blockDim.x) {
+    s.queue[i] = s.order[i];
+    s.pod_pos[s.order[i]] = (uint32_t)i;
+    s.assign[i] = -1;
+    s.place_seq[i] = -1;
+    s.last_epoch[i] = 0;
+  }
+  __syncthreads();
+
+  while (qlen > 0) {
+    const uint32_t pod = s.queue[head];
+    // Pop(): stop when the pod comes round again with an unchanged queue length (queue.go:52)
+    if (s.last_epoch[pod] == epoch && s.last_len[pod] == qlen) break;
+    head = (head + 1) % qcap;
+    --qlen;
+    ++add_calls;
+    ++steps;
+    const uint32_t cls = s.pod_class[pod];
+    __syncthreads();
+    if (warp == 0) reinterpret_cast<uint64_t*>(&row)[lane] = reinterpret_cast<const uint64_t*>(&s.classes[cls])[lane];
+    __syncthreads();
+    if (tid == 0) build_pod_topo(c, s, row, pt);
+    __syncthreads();
+    if (pt.overflow) { fatal = KSCHED_ERR_UNSUPPORTED; break; }
+
+    bool placed = false;
+    // ---------------------------------------------------------------- 1) existing nodes, caller order (scheduler.go:176-180)
+    if (NE > 0) {
+      unsigned long long mine = ~0ull;
+      for (int e = tid; e < NE; e += blockDim.x) {
+        if (s.ex_closed[e]) continue;
+        if (!((row.tolerated_taintsets >> s.ex_taintset[e]) & 1)) continue;
+        if (s.ex_hp[e] & row.hostport_conflicts) continue;
+        bool ok = true;  // Fits(requests, available) first (existingnode.go:98-102)
+        const uint32_t qp = s.ex_req_present[e] | row.res_present;
+        for (int r = 0; r < c.n_res && ok; ++r) {
+          if (!((qp >> r) & 1)) continue;
+          int64_t q = s.ex_req[(size_t)r * NE + e] + row.requests[r];
+          int64_t a = ((s.ex_avail_present[e] >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
+          ok = q <= a;
+        }
+        if (!ok) continue;
+        if (row.itype_req != KSCHED_NONE) {
+          const uint32_t it = s.ex_itype[e];
+          bool allowed = it == KSCHED_NONE ? (s.itype_complement[row.itype_req] != 0)
+                                           : ((s.itype_sets[(size_t)row.itype_req * W32 + (it >> 5)] >> (it & 31)) & 1);
+          if (!allowed) continue;
+        }
+        Touched t;
+        if (!requirements_phase(c, s, row, pt, s.ex_vals, s.ex_meta[e], NE, e, e, true, t)) continue;
+        mine = (unsigned long long)e;
+        break;  // this thread's later nodes have larger indices
+      }
+      unsigned long long w = block_min_u64(mine, red);
+      if (w != ~0ull) {
+        const int e = (int)w;
+        nodes_visited += e + 1;
+        if (tid == 0) {
+          Touched t;
+          requirements_phase(c, s, row, pt, s.ex_vals, s.ex_meta[e], NE, e, e, true, t);
+          uint64_t meta = s.ex_meta[e];
+          for (int i = 0; i < t.n; ++i) {
+            const int k = t.key[i];
+            const Req& f = t.fin[i];
+            uint64_t bit = 1ull << k;
+            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+            s.ex_vals[(size_t)k * NE + e] = f.values;
+          }
+          s.ex_meta[e] = meta;
+          bool closed = false;
+          for (int r = 0; r < c.n_res; ++r) {
+            if ((row.res_present >> r) & 1) s.ex_req[(size_t)r * NE + e] += row.requests[r];
+            int64_t a = ((s.ex_avail_present[e] >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
+            if (s.min_req[r] > 0 && s.ex_req[(size_t)r * NE + e] + s.min_req[r] > a) closed = true;
+          }
+          s.ex_req_present[e] |= row.res_present;
+          s.ex_hp[e] |= row.hostport_entries;
+          s.ex_closed[e] = closed;
+          topo_record(c, s, row, s.ex_vals, meta, NE, e, e);
+          s.assign[pod] = e;
+          s.place_seq[pod] = seq;
+        }
+        ++seq;
+        placed = true;
+      } else {
+        nodes_visited += NE;
+      }
+    }
+    // ---------------------------------------------------------------- 2) in-flight nodes, fewest pods first (scheduler.go:183-190)
+    if (!placed && n_active > 0) {
+      unsigned long long mine = ~0ull;
+      for (int a = tid; a < n_active; a += blockDim.x) {
+        const int n = s.active[a];
+        const int v = s.nn_tmpl[n];
+        if (!((row.tolerated_taintsets >> c.templates[v].taintset) & 1)) continue;
+        if (s.nn_hp[n] & row.hostport_conflicts) continue;
+        int64_t q[KSCHED_MAX_RES];
+        const uint32_t qp = s.nn_req_present[n] | row.res_present;
+        bool ok = true;
+        for (int r = 0; r < c.n_res && ok; ++r) {
+          q[r] = s.nn_req[(size_t)r * MAXN + n] + (((row.res_present >> r) & 1) ? row.requests[r] : 0);
+          if ((qp >> r) & 1) ok = q[r] <= s.nn_maxalloc[(size_t)r * MAXN + n];
+        }
+        if (!ok) continue;
+        Touched t;
+        if (!requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, t)) continue;
+        TypeCtx x;
+        build_type_ctx(c, s, row, t, q, qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, x);
+        bool any = false;
+        for (int w = 0; w < W32 && !any; ++w) {
+          uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
+          if (base) any = type_word(c, s, x, base, w) != 0;
+        }
+        if (!any) continue;
+        // order key: (pod count, tie-break) — the stable-sorted position of the node in s.newNodes
+        unsigned long long key = ((unsigned long long)(uint32_t)s.nn_count[n] << 32) | (uint32_t)(s.nn_tb[n] ^ 0x80000000);
+        if (key < mine) mine = key;
+      }
+      unsigned long long wkey = block_min_u64(mine, red);
+      if (wkey != ~0ull) {
+        // find the winner: (count, tb) is unique per node
+        __syncthreads();
+        if (tid == 0) sh_flag = -1;
+        __syncthreads();
+        for (int a = tid; a < n_active; a += blockDim.x) {
+          const int n = s.active[a];
+          unsigned long long key = ((unsigned long long)(uint32_t)s.nn_count[n] << 32) | (uint32_t)(s.nn_tb[n] ^ 0x80000000);
+          if (key == wkey) sh_flag = a;
+        }
+        __syncthreads();
+        const int a_win = sh_flag;
+        const int n = s.active[a_win];
+        // nodes_visited: rank of the winner in scan order = number of in-flight nodes with a smaller key + 1
+        // (closed nodes are also scanned by the reference; count all created nodes with smaller key)
+        {
+          int cntless = 0;
+          for (int i = tid; i < n_new; i += blockDim.x) {
+            unsigned long long key = ((unsigned long long)(uint32_t)s.nn_count[i] << 32) | (uint32_t)(s.nn_tb[i] ^ 0x80000000);
+            if (key < wkey) ++cntless;
+          }
+          for (int o = 16; o; o >>= 1) cntless += __shfl_xor_sync(0xffffffffu, cntless, o);
+          __syncthreads();
+          if (lane == 0) red[warp] = cntless;
+          __syncthreads();
+          long long tot = 0;
+          for (int i = 0; i < (blockDim.x >> 5); ++i) tot += (long long)red[i];
+          nodes_visited += tot + 1;
+        }
+        // commit by warp 0
+        if (tid == 0) {
+          requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, win_t);
+          uint32_t qp = s.nn_req_present[n] | row.res_present;
+          for (int r = 0; r < c.n_res; ++r) sh_q[r] = s.nn_req[(size_t)r * MAXN + n] + (((row.res_present >> r) & 1) ? row.requests[r] : 0);
+          sh_qp = qp;
+          build_type_ctx(c, s, row, win_t, sh_q, qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, win_x);
+        }
+        __syncthreads();
+        if (warp == 0) {
+          for (int w = lane; w < W32; w += 32) {
+            uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
+            uint32_t sw = base ? type_word(c, s, win_x, base, w) : 0;
+            s.nn_opts[(size_t)w * MAXN + n] = sw;
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          uint64_t meta = s.nn_meta[n];
+          for (int i = 0; i < win_t.n; ++i) {
+            const int k = win_t.key[i];
+            const Req& f = win_t.fin[i];
+            uint64_t bit = 1ull << k;
+            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+            s.nn_vals[(size_t)k * MAXN + n] = f.values;
+          }
+          s.nn_meta[n] = meta;
+          for (int r = 0; r < c.n_res; ++r) s.nn_req[(size_t)r * MAXN + n] = sh_q[r];
+          s.nn_req_present[n] = sh_qp;
+          s.nn_hp[n] |= row.hostport_entries;
+          s.nn_count[n] += 1;
+          s.nn_tb[n] = -(tick + 1);  // moves to the front of the next pod-count block under a stable sort
+          topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
+          s.assign[pod] = NE + n;
+          s.place_seq[pod] = seq;
+        }
+        ++tick;
+        ++seq;
+        placed = true;
+        __syncthreads();
+        // refresh maxalloc bounds where the arg-max type dropped out, and close the node when nothing can fit
+        if (warp == 0) {
+          bool closed = false;
+          for (int r = 0; r < c.n_res; ++r) {
+            int am = s.nn_argmax[(size_t)r * MAXN + n];
+            bool still = (s.nn_opts[(size_t)(am >> 5) * MAXN + n] >> (am & 31)) & 1;
+            if (!still) {
+              long long best = INT64_MIN;
+              int bt = 0;
+              for (int w = lane; w < W32; w += 32) {
+                uint32_t m = s.nn_opts[(size_t)w * MAXN + n];
+                while (m) {
+                  int b = __ffs(m) - 1;
+                  m &= m - 1;
+                  int t = w * 32 + b;
+                  long long al = c.types[t].allocatable[r];
+                  if (al > best) { best = al; bt = t; }
+                }
+              }
+              for (int o = 16; o; o >>= 1) {
+                long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                if (ob > best || (ob == best && ot < bt)) { best = ob; bt = ot; }
+              }
+              if (lane == 0) { s.nn_maxalloc[(size_t)r * MAXN + n] = best; s.nn_argmax[(size_t)r * MAXN + n] = bt; }
+            }
+            __syncwarp();
+            int64_t mx = s.nn_maxalloc[(size_t)r * MAXN + n];
+            if (s.min_req[r] > 0 && s.nn_req[(size_t)r * MAXN + n] + s.min_req[r] > mx) closed = true;
+          }
+          if (closed && lane == 0) s.active[a_win] = s.active[n_active - 1];
+          if (lane == 0) sh_flag = closed ? 1 : 0;
+        }
+        __syncthreads();
+        if (sh_flag) --n_active;
+      } else {
+        nodes_visited += n_new;
+      }
+    } else if (!placed) {
+      nodes_visited += n_new;  // every in-flight node is full: the reference still walks them
+    }
+    // ---------------------------------------------------------------- 3) open a new node, templates in weight order (scheduler.go:194-217)
+    if (!placed) {
+      // K1's row of this pod is valid while the pod still has its original class (relaxation changes the row)
+      const bool f_valid = s.use_F && s.relax_level[pod] == 0;
+      const uint32_t fpos = s.pod_pos[pod];
+      const bool no_column = f_valid && s.best[fpos] == kNoBest;  // no feasible (template, type) column at all
+      if (no_column) { nodes_visited += V; node_id += V; }
+      for (int v = 0; v < V && !placed && !no_column; ++v) {
+        const ksched_template& tm = c.templates[v];
+        __syncthreads();
+        // filterByRemainingResources (scheduler.go:293-309) folded into the base set below
+        ++nodes_visited;
+        ++node_id;
+        if (n_new >= MAXN) { fatal = KSCHED_ERR_OVERFLOW; break; }
+        const int n = n_new;  // tentative slot: the hostname placeholder of this attempt
+        if (tid == 0) {
+          sh_flag = 0;
+          sh_any = 0;
+          bool ok = (row.tolerated_taintsets >> tm.taintset) & 1;
+          // template requirements become the node requirements (NewNode node.go:44-60)
+          for (int k = 0; k < c.n_keys; ++k) s.nn_vals[(size_t)k * MAXN + n] = tm.reqs.values[k];
+          s.nn_meta[n] = tm.reqs.meta & 0xFFFFFFFFull;
+          if (ok) ok = requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, win_t);
+          if (ok) {
+            uint32_t qp = tm.daemon_res_present | row.res_present;
+            for (int r = 0; r < c.n_res; ++r) sh_q[r] = tm.daemon_requests[r] + (((row.res_present >> r) & 1) ? row.requests[r] : 0);
+            sh_qp = qp;
+            build_type_ctx(c, s, row, win_t, sh_q, qp, s.nn_vals, s.nn_meta[n], MAXN, n, true, win_x);
+            // topology left every requirement as K1 saw it -> the precomputed row is the exact answer
+            bool same = f_valid;
+            for (int i = 0; i < win_t.n && same; ++i) same = req_equal(win_t.fin[i], win_t.merged[i]);
+            sh_useF = same ? 1 : 0;
+          }
+          sh_flag = ok ? 1 : 0;
+        }
+        __syncthreads();
+        if (!sh_flag) continue;
+        // surviving types: template members ∧ limits ∧ full predicate
+        bool local_any = false;
+        for (int w = tid; w < W32; w += blockDim.x) {
+          uint32_t base = c.member[(size_t)v * W32 + w];
+          if (base && tm.has_limits && tm.limit_present) {
+            uint32_t m = base;
+            while (m) {
+              int b = __ffs(m) - 1;
+              m &= m - 1;
+              int t = w * 32 + b;
+              bool viable = true;
+              for (int r = 0; r < c.n_res; ++r)
+                if (((tm.limit_present >> r) & 1) && c.capacity[(size_t)t * KSCHED_MAX_RES + r] > s.remaining[(size_t)v * KSCHED_MAX_RES + r]) viable = false;
+              if (!viable) base &= ~(1u << b);
+            }
+          }
+          uint32_t sw = 0;
+          if (base) sw = sh_useF ? (base & s.F[((size_t)fpos * V + v) * W32 + w]) : type_word(c, s, win_x, base, w);
+          s.nn_opts[(size_t)w * MAXN + n] = sw;
+          if (sw) local_any = true;
+        }
+        if (local_any) atomicOr(&sh_any, 1u);
+        __syncthreads();
+        // "all available instance types exceed provisioner limits" -> continue without NewNode in the reference;
+        // here the attempt is made and fails identically (no types), only the placeholder counter differs.
+        if (!sh_any) continue;
+        // commit the new node
+        if (tid == 0) {
+          uint64_t meta = s.nn_meta[n];
+          for (int i = 0; i < win_t.n; ++i) {
+            const int k = win_t.key[i];
+            const Req& f = win_t.fin[i];
+            uint64_t bit = 1ull << k;
+            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+            s.nn_vals[(size_t)k * MAXN + n] = f.values;
+          }
+          s.nn_meta[n] = meta;
+          s.nn_tmpl[n] = (uint8_t)v;
+          for (int r = 0; r < KSCHED_MAX_RES; ++r) s.nn_req[(size_t)r * MAXN + n] = r < c.n_res ? sh_q[r] : 0;
+          s.nn_req_present[n] = sh_qp;
+          s.nn_hp[n] = row.hostport_entries;
+          s.nn_count[n] = 1;
+          s.nn_tb[n] = tick + 1;  // appended: last of the one-pod block
+          topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
+          s.assign[pod] = NE + n;
+          s.place_seq[pod] = seq;
+          s.active[n_active] = n;
+        }
+        ++tick;
+        ++seq;
+        __syncthreads();
+        // maxalloc bounds + limits bookkeeping (subtractMax scheduler.go:273-290) by warp 0
+        if (warp == 0) {
+          bool closed = false;
+          for (int r = 0; r < c.n_res; ++r) {
+            long long best = INT64_MIN, bestcap = INT64_MIN;
+            int bt = 0;
+            for (int w = lane; w < W32; w += 32) {
+              uint32_t m = s.nn_opts[(size_t)w * MAXN + n];
+              while (m) {
+                int b = __ffs(m) - 1;
+                m &= m - 1;
+                int t = w * 32 + b;
+                long long al = c.types[t].allocatable[r];
+                if (al > best) { best = al; bt = t; }
+                long long cp = c.capacity[(size_t)t * KSCHED_MAX_RES + r];
+                if (cp > bestcap) bestcap = cp;
+              }
+            }
+            for (int o = 16; o; o >>= 1) {
+              long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+              int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+              long long oc = __shfl_xor_sync(0xffffffffu, bestcap, o);
+              if (ob > best || (ob == best && ot < bt)) { best = ob; bt = ot; }
+              if (oc > bestcap) bestcap = oc;
+            }
+            if (lane == 0) {
+              s.nn_maxalloc[(size_t)r * MAXN + n] = best;
+              s.nn_argmax[(size_t)r * MAXN + n] = bt;
+              if (tm.has_limits && ((tm.limit_present >> r) & 1)) s.remaining[(size_t)v * KSCHED_MAX_RES + r] -= bestcap;
+            }
+            if (s.min_req[r] > 0 && sh_q[r] + s.min_req[r] > best) closed = true;
+          }
+          if (lane == 0) sh_flag = closed ? 1 : 0;
+        }
+        __syncthreads();
+        ++n_new;
+        if (!sh_flag) ++n_active;
+        placed = true;
+      }
+      if (fatal) break;
+    }
+    // ---------------------------------------------------------------- failure: relax + requeue (scheduler.go:117-123, queue.go:61-68)
+    if (!placed) {
+      const uint32_t nx = row.relax_next;
+      const int tail = (head + qlen) % qcap;
+      __syncthreads();
+      if (tid == 0) {
+        s.queue[tail] = pod;
+        if (nx != KSCHED_NONE) {
+          s.pod_class[pod] = nx;
+          s.relax_level[pod] += 1;
+        } else {
+          s.last_len[pod] = qlen + 1;
+          s.last_epoch[pod] = epoch;
+        }
+      }
+      ++qlen;
+      if (nx != KSCHED_NONE) ++epoch;  // relaxed: lastLen map is reset
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    s.counters[0] = n_new;
+    s.counters[1] = qlen;
+    s.counters[2] = nodes_visited;
+    s.counters[3] = add_calls;
+    s.counters[4] = fatal;
+    s.counters[5] = steps;
+  }
+}
+
+// L2 flush helper: write a buffer larger than L2 between timed iterations
+__global__ void flush_kernel(uint32_t* buf, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) buf[i] = (uint32_t)i;
+}
+
+template <class T>
+struct DevBuf {
+  T* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap && ptr) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = n ? n : 1;
+    cudaError_t e = cudaMalloc(&ptr, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct ksched_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // catalog
+  bool have_catalog = false;
+  DevCatalog cat{};
+  int W64 = 0;
+  DevBuf<ksched_keyinfo> d_keys;
+  DevBuf<int64_t> d_key_int, d_capacity, d_alloc_sorted;
+  DevBuf<ksched_template> d_templates;
+  DevBuf<ksched_type_row> d_types;
+  DevBuf<float> d_price32;
+  DevBuf<int16_t> d_valrow, d_offrow;
+  DevBuf<uint32_t> d_valset, d_absent, d_negempty, d_offset, d_anyoffer, d_member, d_fitset;
+  std::vector<ksched_template> h_templates;
+  // problem
+  bool uploaded = false;
+  int n_pods = 0, n_classes = 0, n_existing = 0, n_groups = 0, max_new = 0, n_hostgroups = 0;
+  DevBuf<ksched_pod_row> d_classes;
+  DevBuf<uint32_t> d_pod_pos, d_pod_class0, d_pod_class, d_uid_rank, d_order, d_idx_tmp, d_itype_sets, d_queue, d_last_epoch;
+  DevBuf<int64_t> d_ts;
+  DevBuf<uint64_t> d_k_cpu, d_k_mem, d_k_tie, d_k_tmp, d_rows;
+  DevBuf<uint8_t> d_cub_tmp, d_itype_comp, d_ex_closed, d_nn_tmpl;
+  DevBuf<ksched_topo_group> d_groups;
+  DevBuf<ksched_class_topo> d_class_topo;
+  DevBuf<ksched_reqset> d_filter_terms;
+  DevBuf<int32_t> d_hostname_reqs, d_relax, d_assign, d_place_seq, d_last_len, d_nn_count, d_nn_tb, d_nn_argmax, d_active, d_grp_cnt,
+      d_grp_cnt0, d_grp_host_row, d_grp_host_total, d_grp_host_total0;
+  DevBuf<uint32_t> d_F;
+  DevBuf<unsigned long long> d_best;
+  DevBuf<int64_t> d_ex_req, d_ex_req0, d_ex_avail, d_nn_req, d_nn_maxalloc, d_remaining;
+  DevBuf<uint32_t> d_ex_req_present, d_ex_req_present0, d_ex_avail_present, d_ex_taintset, d_ex_itype, d_nn_req_present, d_nn_opts;
+  DevBuf<uint64_t> d_ex_vals, d_ex_vals0, d_ex_meta, d_ex_meta0, d_ex_hp, d_ex_hp0, d_nn_vals, d_nn_meta, d_nn_hp, d_grp_registered,
+      d_grp_registered0;
+  DevBuf<uint16_t> d_grp_host, d_grp_host0;
+  DevBuf<long long> d_counters;
+  DevBuf<uint32_t> d_flush;
+  size_t cub_tmp_bytes = 0;
+  int64_t min_req[KSCHED_MAX_RES] = {0};
+  // sharding / nccl
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  // timings
+  ksched_timings tm{};
+  cudaEvent_t ev[8] = {nullptr};
+};
+
+template <class T>
+static cudaError_t upload(ksched_handle* h, DevBuf<T>& buf, const T* src, size_t n) {
+  cudaError_t e = buf.ensure(n);
+  if (e != cudaSuccess) return e;
+  if (n == 0) return cudaSuccess;
+  h->tm.h2d_bytes += (int64_t)(n * sizeof(T));
+  return cudaMemcpyAsync(buf.ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+}
+template <class T>
+static cudaError_t upload_vec(ksched_handle* h, DevBuf<T>& buf, const std::vector<T>& v) { return upload(h, buf, v.data(), v.size()); }
+
+static int type_words64(int n_types) { int w = (n_types + 63) / 64; return w ? w : 1; }
+
+extern "C" {
+
+int ksched_abi_version(void) { return KSCHED_ABI_VERSION; }
+int ksched_type_words(int n_types) { return type_words64(n_types); }
+
+int ksched_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return KSCHED_ERR_NO_DEVICE;
+  return n;
+}
+
+int ksched_create(int device_ordinal, ksched_handle** out) {
+  if (!out) return KSCHED_ERR_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device_ordinal >= n) return KSCHED_ERR_NO_DEVICE;
+  ksched_handle* h = new ksched_handle();
+  h->device = device_ordinal;
+  if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return KSCHED_ERR_CUDA;
+  }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return KSCHED_OK;
+}
+
+void ksched_destroy(ksched_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->comm) ncclCommDestroy(h->comm);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  // device buffers are released with the context at process exit; free the big ones eagerly
+  h->d_F.release(); h->d_rows.release(); h->d_grp_host.release(); h->d_grp_host0.release(); h->d_fitset.release(); h->d_flush.release();
+  h->d_nn_opts.release(); h->d_nn_vals.release(); h->d_nn_req.release(); h->d_nn_maxalloc.release();
+  delete h;
+}
+
+const char* ksched_last_error(const ksched_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+
+int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
+  if (!h || !cat) return KSCHED_ERR_INVALID;
+  if (cat->n_keys > KSCHED_MAX_KEYS || cat->n_res > KSCHED_MAX_RES || cat->n_templates > KSCHED_MAX_TEMPLATES || cat->n_templates < 1 ||
+      cat->n_types < 0) { h->err = "catalog dimensions out of range"; return KSCHED_ERR_INVALID; }
+  if (cat->type_bounds) { h->err = "instance types with Gt/Lt requirements are not supported"; return KSCHED_ERR_UNSUPPORTED; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int T = cat->n_types, NK = cat->n_keys, V = cat->n_templates, R = cat->n_res;
+  const int W64 = type_words64(T), W32 = W64 * 2;
+  h->W64 = W64;
+  // ---- bit-sliced tables, built on the host (amortised: instance types change rarely)
+  std::vector<int16_t> valrow((size_t)NK * 64, -1), offrow(64, -1);
+  std::vector<uint32_t> valset, absent((size_t)std::max(NK, 1) * W32, 0), negempty((size_t)std::max(NK, 1) * W32, 0), offset, anyoffer(W32, 0),
+      member((size_t)V * W32, 0);
+  uint32_t type_relevant = 0;
+  int zone_key = -1, ct_key = -1;
+  for (int k = 0; k < NK; ++k) {
+    if (cat->keys[k].is_zone) zone_key = k;
+    if (cat->keys[k].is_capacity_type) ct_key = k;
+  }
+  std::vector<float> price32(std::max(T, 1), 0.f);
+  for (int t = 0; t < T; ++t) {
+    const ksched_type_row& row = cat->types[t];
+    if (t > 0 && row.min_price < cat->types[t - 1].min_price) { h->err = "instance types must be in ascending price order"; return KSCHED_ERR_INVALID; }
+    price32[t] = (float)row.min_price;
+    const int w = t >> 5;
+    const uint32_t bit = 1u << (t & 31);
+    if ((row.meta >> KSCHED_META_COMPLEMENT_SHIFT) & 0xFFFF || (row.meta >> KSCHED_META_HASGT_SHIFT)) {
+      h->err = "instance types with complement / bounded requirements are not supported";
+      return KSCHED_ERR_UNSUPPORTED;
+    }
+    for (int k = 0; k < NK; ++k) {
+      bool present = (row.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
+      if (!present) { absent[(size_t)k * W32 + w] |= bit; continue; }
+      type_relevant |= 1u << k;
+      uint64_t v = row.values[k];
+      if (!v) { negempty[(size_t)k * W32 + w] |= bit; continue; }
+      while (v) {
+        int b = __builtin_ctzll(v);
+        v &= v - 1;
+        int16_t& r = valrow[(size_t)k * 64 + b];
+        if (r < 0) { r = (int16_t)(valset.size() / W32); valset.resize(valset.size() + W32, 0); }
+        valset[(size_t)r * W32 + w] |= bit;
+      }
+    }
+    uint64_t o = row.offerings;
+    if (o) anyoffer[w] |= bit;
+    while (o) {
+      int b = __builtin_ctzll(o);
+      o &= o - 1;
+      int16_t& r = offrow[b];
+      if (r < 0) { r = (int16_t)(offset.size() / W32); offset.resize(offset.size() + W32, 0); }
+      offset[(size_t)r * W32 + w] |= bit;
+    }
+    for (int v = 0; v < V; ++v) if ((row.template_members >> v) & 1) member[(size_t)v * W32 + w] |= bit;
+  }
+  if (valset.empty()) valset.resize(W32, 0);
+  if (offset.empty()) offset.resize(W32, 0);
+  std::vector<int64_t> alloc_sorted((size_t)std::max(R, 1) * std::max(T, 1), 0);
+  std::vector<uint32_t> fitset((size_t)std::max(R, 1) * (T + 1) * W32, 0);
+  {
+    std::vector<int> perm(T);
+    for (int r = 0; r < R; ++r) {
+      for (int t = 0; t < T; ++t) perm[t] = t;
+      std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cat->types[a].allocatable[r] < cat->types[b].allocatable[r]; });
+      for (int i = 0; i < T; ++i) alloc_sorted[(size_t)r * T + i] = cat->types[perm[i]].allocatable[r];
+      uint32_t* base = &fitset[(size_t)r * (T + 1) * W32];
+      for (int i = T - 1; i >= 0; --i) {
+        uint32_t* cur = base + (size_t)i * W32;
+        std::memcpy(cur, base + (size_t)(i + 1) * W32, W32 * sizeof(uint32_t));
+        cur[perm[i] >> 5] |= 1u << (perm[i] & 31);
+      }
+    }
+  }
+  CUDA_TRY(h, upload(h, h->d_keys, cat->keys, (size_t)NK));
+  if (cat->key_int_values) CUDA_TRY(h, upload(h, h->d_key_int, cat->key_int_values, (size_t)NK * 64));
+  CUDA_TRY(h, upload(h, h->d_templates, cat->templates, (size_t)V));
+  CUDA_TRY(h, upload(h, h->d_types, cat->types, (size_t)T));
+  CUDA_TRY(h, upload(h, h->d_capacity, cat->type_capacity, (size_t)T * KSCHED_MAX_RES));
+  CUDA_TRY(h, upload_vec(h, h->d_price32, price32));
+  CUDA_TRY(h, upload_vec(h, h->d_valrow, valrow));
+  CUDA_TRY(h, upload_vec(h, h->d_offrow, offrow));
+  CUDA_TRY(h, upload_vec(h, h->d_valset, valset));
+  CUDA_TRY(h, upload_vec(h, h->d_absent, absent));
+  CUDA_TRY(h, upload_vec(h, h->d_negempty, negempty));
+  CUDA_TRY(h, upload_vec(h, h->d_offset, offset));
+  CUDA_TRY(h, upload_vec(h, h->d_anyoffer, anyoffer));
+  CUDA_TRY(h, upload_vec(h, h->d_member, member));
+  CUDA_TRY(h, upload_vec(h, h->d_alloc_sorted, alloc_sorted));
+  CUDA_TRY(h, upload_vec(h, h->d_fitset, fitset));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->h_templates.assign(cat->templates, cat->templates + V);
+  DevCatalog& c = h->cat;
+  c.n_keys = NK; c.n_res = R; c.n_types = T; c.n_templates = V; c.W32 = W32;
+  c.keys = h->d_keys.ptr;
+  c.key_int_values = cat->key_int_values ? h->d_key_int.ptr : nullptr;
+  c.templates = h->d_templates.ptr;
+  c.types = h->d_types.ptr;
+  c.capacity = h->d_capacity.ptr;
+  c.price32 = h->d_price32.ptr;
+  c.valrow = h->d_valrow.ptr; c.valset = h->d_valset.ptr; c.absent = h->d_absent.ptr; c.negempty = h->d_negempty.ptr;
+  c.type_relevant = type_relevant;
+  c.offrow = h->d_offrow.ptr; c.offset = h->d_offset.ptr; c.anyoffer = h->d_anyoffer.ptr; c.member = h->d_member.ptr;
+  c.alloc_sorted = h->d_alloc_sorted.ptr; c.fitset = h->d_fitset.ptr;
+  c.zone_key = zone_key; c.ct_key = ct_key;
+  h->have_catalog = true;
+  h->uploaded = false;
+  return KSCHED_OK;
+}
+
+int ksched_set_shard(ksched_handle* h, int rank, int world) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return KSCHED_ERR_INVALID;
+  h->rank = rank;
+  h->world = world;
+  return KSCHED_OK;
+}
+
+int ksched_nccl_unique_id(void* out128) {
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return KSCHED_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  std::memcpy(out128, &id, 128);
+  return KSCHED_OK;
+}
+int ksched_nccl_init(ksched_handle* h, const void* id128, int rank, int world) {
+  if (!h || !id128) return KSCHED_ERR_INVALID;
+  if (cudaSetDevice(h->device) != cudaSuccess) return KSCHED_ERR_CUDA;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclResult_t r = ncclCommInitRank(&h->comm, world, id, rank);
+  if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); return KSCHED_ERR_NCCL; }
+  h->rank = rank;
+  h->world = world;
+  return KSCHED_OK;
+}
+
+// ---- upload one problem (pods / nodes / topology) and keep pristine copies of everything the pack kernel mutates
+int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
+  if (!h || !pb) return KSCHED_ERR_INVALID;
+  if (!h->have_catalog) { h->err = "ksched_load_catalog must be called first"; return KSCHED_ERR_INVALID; }
+  if (pb->class_bounds || pb->existing_bounds) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  h->tm.h2d_bytes = 0;
+  const DevCatalog& c = h->cat;
+  const int P = pb->n_pods, NC = pb->n_classes, NE = pb->n_existing, NG = pb->n_groups, W32 = c.W32, V = c.n_templates;
+  const int MAXN = std::max(1, std::min(pb->max_new_nodes > 0 ? pb->max_new_nodes : P, std::max(P, 1)));
+  h->n_pods = P; h->n_classes = NC; h->n_existing = NE; h->n_groups = NG; h->max_new = MAXN;
+  for (int c2 = 0; c2 < NC; ++c2) {
+    const ksched_pod_row& row = pb->classes[c2];
+    if (row.relax_next != KSCHED_NONE && row.relax_next >= (uint32_t)NC) { h->err = "relax_next out of range"; return KSCHED_ERR_INVALID; }
+    if (row.topo_end < row.topo_begin || row.topo_end > (uint32_t)pb->n_class_topo) { h->err = "class_topo range out of bounds"; return KSCHED_ERR_INVALID; }
+    int ncg = 0, touched = __builtin_popcountll((row.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF);
+    for (uint32_t e = row.topo_begin; e < row.topo_end; ++e) {
+      if (pb->class_topo[e].group >= (uint32_t)NG) { h->err = "class_topo group out of range"; return KSCHED_ERR_INVALID; }
+      if (pb->class_topo[e].flags & KSCHED_TOPO_CONSTRAINS) { ++ncg; if (pb->groups[pb->class_topo[e].group].key != KSCHED_KEY_HOSTNAME) ++touched; }
+    }
+    if (ncg > kMaxCG || touched > kMaxTouched) { h->err = "a pod class is constrained by more topology groups / label keys than the pack kernel carries"; return KSCHED_ERR_UNSUPPORTED; }
+  }
+  // min request per resource over all classes (node closing rule)
+  for (int r = 0; r < KSCHED_MAX_RES; ++r) {
+    int64_t mn = INT64_MAX;
+    for (int c2 = 0; c2 < NC; ++c2) {
+      const ksched_pod_row& row = pb->classes[c2];
+      int64_t v = ((row.res_present >> r) & 1) ? row.requests[r] : 0;
+      mn = std::min(mn, v);
+    }
+    h->min_req[r] = (NC == 0 || mn == INT64_MAX || mn < 0) ? 0 : mn;
+  }
+  CUDA_TRY(h, upload(h, h->d_classes, pb->classes, (size_t)NC));
+  CUDA_TRY(h, upload(h, h->d_pod_class0, pb->pod_class, (size_t)P));
+  CUDA_TRY(h, h->d_pod_class.ensure(P));
+  CUDA_TRY(h, upload(h, h->d_ts, pb->pod_timestamp, (size_t)P));
+  CUDA_TRY(h, upload(h, h->d_uid_rank, pb->pod_uid_rank, (size_t)P));
+  CUDA_TRY(h, upload(h, h->d_groups, pb->groups, (size_t)NG));
+  CUDA_TRY(h, upload(h, h->d_class_topo, pb->class_topo, (size_t)pb->n_class_topo));
+  CUDA_TRY(h, upload(h, h->d_filter_terms, pb->filter_terms, (size_t)pb->n_filter_terms));
+  CUDA_TRY(h, upload(h, h->d_hostname_reqs, pb->hostname_reqs, (size_t)pb->n_hostname_reqs * 2));
+  CUDA_TRY(h, upload(h, h->d_itype_comp, pb->itype_req_complement, (size_t)pb->n_itype_reqs));
+  CUDA_TRY(h, upload(h, h->d_itype_sets, reinterpret_cast<const uint32_t*>(pb->itype_req_sets), (size_t)pb->n_itype_reqs * W32));
+  // existing nodes -> SoA
+  {
+    std::vector<int64_t> req((size_t)8 * std::max(NE, 1), 0), avail((size_t)8 * std::max(NE, 1), 0);
+    std::vector<uint32_t> reqp(std::max(NE, 1), 0), availp(std::max(NE, 1), 0), ts(std::max(NE, 1), 0), it(std::max(NE, 1), 0);
+    std::vector<uint64_t> vals((size_t)16 * std::max(NE, 1), 0), meta(std::max(NE, 1), 0), hp(std::max(NE, 1), 0);
+    for (int e = 0; e < NE; ++e) {
+      const ksched_existing_node& n = pb->existing[e];
+      for (int r = 0; r < 8; ++r) { req[(size_t)r * NE + e] = n.requests[r]; avail[(size_t)r * NE + e] = n.available[r]; }
+      for (int k = 0; k < 16; ++k) vals[(size_t)k * NE + e] = n.reqs.values[k];
+      meta[e] = n.reqs.meta & 0xFFFFFFFFull;
+      reqp[e] = n.requests_present; availp[e] = n.available_present; ts[e] = n.taintset; it[e] = n.itype; hp[e] = n.hostport_entries;
+    }
+    CUDA_TRY(h, upload_vec(h, h->d_ex_req0, req));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_avail, avail));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_req_present0, reqp));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_avail_present, availp));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_taintset, ts));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_itype, it));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_vals0, vals));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_meta0, meta));
+    CUDA_TRY(h, upload_vec(h, h->d_ex_hp0, hp));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host vectors go out of scope
+    size_t ne = (size_t)std::max(NE, 1);
+    CUDA_TRY(h, h->d_ex_req.ensure(8 * ne));
+    CUDA_TRY(h, h->d_ex_req_present.ensure(ne));
+    CUDA_TRY(h, h->d_ex_vals.ensure(16 * ne));
+    CUDA_TRY(h, h->d_ex_meta.ensure(ne));
+    CUDA_TRY(h, h->d_ex_hp.ensure(ne));
+    CUDA_TRY(h, h->d_ex_closed.ensure(ne));
+  }
+  // topology counters
+  {
+    std::vector<int32_t> host_row(std::max(NG, 1), -1), host_total(std::max(NG, 1), 0), cnt((size_t)std::max(NG, 1) * 64, 0);
+    std::vector<uint64_t> registered(std::max(NG, 1), 0);
+    int nh = 0;
+    for (int g = 0; g < NG; ++g) {
+      if (pb->groups[g].key == KSCHED_KEY_HOSTNAME) host_row[g] = nh++;
+      else if (pb->groups[g].key >= c.n_keys) { h->err = "topology group key out of range"; return KSCHED_ERR_INVALID; }
+      registered[g] = pb->groups[g].registered;
+      for (int d = 0; d < 64; ++d) cnt[(size_t)g * 64 + d] = pb->group_domain_counts[(size_t)g * 64 + d];
+    }
+    h->n_hostgroups = nh;
+    const size_t stride = (size_t)NE + MAXN;
+    std::vector<uint16_t> host((size_t)std::max(nh, 1) * stride, 0);
+    for (int g = 0; g < NG; ++g) {
+      if (host_row[g] < 0) continue;
+      int total = pb->groups[g].extra_nonzero_domains;
+      for (int e = 0; e < NE; ++e) {
+        int32_t v = pb->group_existing_counts[(size_t)g * std::max(NE, 1) + e];
+        host[(size_t)host_row[g] * stride + e] = (uint16_t)std::min(v, 0xFFFF);
+        if (v > 0) ++total;
+      }
+      host_total[g] = total;
+    }
+    CUDA_TRY(h, upload_vec(h, h->d_grp_host_row, host_row));
+    CUDA_TRY(h, upload_vec(h, h->d_grp_host_total0, host_total));
+    CUDA_TRY(h, upload_vec(h, h->d_grp_cnt0, cnt));
+    CUDA_TRY(h, upload_vec(h, h->d_grp_registered0, registered));
+    CUDA_TRY(h, upload_vec(h, h->d_grp_host0, host));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, h->d_grp_host_total.ensure(std::max(NG, 1)));
+    CUDA_TRY(h, h->d_grp_cnt.ensure((size_t)std::max(NG, 1) * 64));
+    CUDA_TRY(h, h->d_grp_registered.ensure(std::max(NG, 1)));
+    CUDA_TRY(h, h->d_grp_host.ensure((size_t)std::max(nh, 1) * stride));
+  }
+  // scratch / state
+  const size_t p1 = (size_t)std::max(P, 1);
+  CUDA_TRY(h, h->d_order.ensure(p1)); CUDA_TRY(h, h->d_idx_tmp.ensure(p1)); CUDA_TRY(h, h->d_pod_pos.ensure(p1));
+  CUDA_TRY(h, h->d_k_cpu.ensure(p1)); CUDA_TRY(h, h->d_k_mem.ensure(p1)); CUDA_TRY(h, h->d_k_tie.ensure(p1)); CUDA_TRY(h, h->d_k_tmp.ensure(p1));
+  CUDA_TRY(h, h->d_rows.ensure(p1 * KSCHED_ROW_WORDS));
+  CUDA_TRY(h, h->d_F.ensure(p1 * V * W32));
+  CUDA_TRY(h, h->d_best.ensure(p1));
+  CUDA_TRY(h, h->d_relax.ensure(p1)); CUDA_TRY(h, h->d_assign.ensure(p1)); CUDA_TRY(h, h->d_place_seq.ensure(p1));
+  CUDA_TRY(h, h->d_queue.ensure(p1 + 1)); CUDA_TRY(h, h->d_last_len.ensure(p1)); CUDA_TRY(h, h->d_last_epoch.ensure(p1));
+  const size_t mn = (size_t)MAXN;
+  CUDA_TRY(h, h->d_nn_tmpl.ensure(mn)); CUDA_TRY(h, h->d_nn_count.ensure(mn)); CUDA_TRY(h, h->d_nn_tb.ensure(mn));
+  CUDA_TRY(h, h->d_nn_req.ensure(8 * mn)); CUDA_TRY(h, h->d_nn_req_present.ensure(mn)); CUDA_TRY(h, h->d_nn_maxalloc.ensure(8 * mn));
+  CUDA_TRY(h, h->d_nn_argmax.ensure(8 * mn)); CUDA_TRY(h, h->d_nn_vals.ensure(16 * mn)); CUDA_TRY(h, h->d_nn_meta.ensure(mn));
+  CUDA_TRY(h, h->d_nn_opts.ensure((size_t)W32 * mn)); CUDA_TRY(h, h->d_nn_hp.ensure(mn)); CUDA_TRY(h, h->d_active.ensure(mn));
+  CUDA_TRY(h, h->d_remaining.ensure((size_t)V * KSCHED_MAX_RES));
+  CUDA_TRY(h, h->d_counters.ensure(8));
+  {
+    size_t need = 0, n2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)p1, 0, 64, h->stream);
+    n2 = need;
+    CUDA_TRY(h, h->d_cub_tmp.ensure(n2 + 256));
+    h->cub_tmp_bytes = n2 + 256;
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->uploaded = true;
+  return KSCHED_OK;
+}
+
+static int run_sort(ksched_handle* h) {
+  const int P = h->n_pods;
+  if (P == 0) return KSCHED_OK;
+  const int threads = 256, blocks = (P + threads - 1) / threads;
+  sort_keys_kernel<<<blocks, threads, 0, h->stream>>>(P, h->d_classes.ptr, h->d_pod_class.ptr, h->d_ts.ptr, h->d_uid_rank.ptr, h->d_k_cpu.ptr,
+                                                      h->d_k_mem.ptr, h->d_k_tie.ptr, h->d_order.ptr);
+  // LSD over three 64-bit keys with a stable radix sort: tie-break key first, cpu last
+  size_t tmp = h->cub_tmp_bytes;
+  uint32_t *ia = h->d_order.ptr, *ib = h->d_idx_tmp.ptr;
+  CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.ptr, tmp, h->d_k_tie.ptr, h->d_k_tmp.ptr, ia, ib, P, 0, 64, h->stream));
+  gather_u64_kernel<<<blocks, threads, 0, h->stream>>>(P, h->d_k_mem.ptr, ib, h->d_k_tie.ptr);
+  tmp = h->cub_tmp_bytes;
+  CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.ptr, tmp, h->d_k_tie.ptr, h->d_k_tmp.ptr, ib, ia, P, 0, 64, h->stream));
+  gather_u64_kernel<<<blocks, threads, 0, h->stream>>>(P, h->d_k_cpu.ptr, ia, h->d_k_tie.ptr);
+  tmp = h->cub_tmp_bytes;
+  CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.ptr, tmp, h->d_k_tie.ptr, h->d_k_tmp.ptr, ia, ib, P, 0, 64, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_order.ptr, ib, (size_t)P * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+  const int gblocks = std::min((P + 7) / 8, 148 * 8);
+  gather_rows_kernel<<<gblocks, 256, 0, h->stream>>>(P, h->d_classes.ptr, h->d_pod_class.ptr, h->d_order.ptr, h->d_rows.ptr);
+  h->tm.sort_launches = 7;
+  return KSCHED_OK;
+}
+
+static void fill_k1(ksched_handle* h, K1Params& k1) {
+  k1.cat = h->cat;
+  k1.rows = h->d_rows.ptr;
+  k1.n_pods = h->n_pods;
+  k1.itype_sets = h->d_itype_sets.ptr;
+  k1.F = h->d_F.ptr;
+  k1.best = h->d_best.ptr;
+  const int W32 = h->cat.W32;
+  if (h->world > 1) {
+    int per = (W32 + h->world - 1) / h->world;
+    k1.word_begin = std::min(W32, h->rank * per);
+    k1.word_end = std::min(W32, k1.word_begin + per);
+  } else {
+    k1.word_begin = 0;
+    k1.word_end = W32;
+  }
+}
+
+static int run_feasibility(ksched_handle* h) {
+  if (h->n_pods == 0) return KSCHED_OK;
+  K1Params k1;
+  fill_k1(h, k1);
+  const int warps_per_block = 8;
+  int blocks = std::min((h->n_pods + warps_per_block - 1) / warps_per_block, 148 * 8);
+  feasibility_kernel<<<blocks, 256, 0, h->stream>>>(k1);
+  h->tm.feasibility_launches = 1;
+  const long long C = (long long)h->cat.n_templates * h->cat.n_types;
+  h->tm.feasibility_bytes = (long long)h->n_pods * 256 + C * 256 + (long long)h->n_pods * C / 8;
+  return KSCHED_OK;
+}
+
+static int reset_state(ksched_handle* h) {
+  const int P = h->n_pods, NE = std::max(h->n_existing, 1), NG = std::max(h->n_groups, 1);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)P * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_relax.ptr, 0, (size_t)std::max(P, 1) * 4, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_req.ptr, h->d_ex_req0.ptr, (size_t)8 * NE * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_req_present.ptr, h->d_ex_req_present0.ptr, (size_t)NE * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_vals.ptr, h->d_ex_vals0.ptr, (size_t)16 * NE * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_meta.ptr, h->d_ex_meta0.ptr, (size_t)NE * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_hp.ptr, h->d_ex_hp0.ptr, (size_t)NE * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_ex_closed.ptr, 0, (size_t)NE, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_cnt.ptr, h->d_grp_cnt0.ptr, (size_t)NG * 64 * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_registered.ptr, h->d_grp_registered0.ptr, (size_t)NG * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host_total.ptr, h->d_grp_host_total0.ptr, (size_t)NG * 4, cudaMemcpyDeviceToDevice, h->stream));
+  const size_t hs = (size_t)std::max(h->n_hostgroups, 1) * ((size_t)h->n_existing + h->max_new);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host.ptr, h->d_grp_host0.ptr, hs * 2, cudaMemcpyDeviceToDevice, h->stream));
+  std::vector<int64_t> rem((size_t)h->cat.n_templates * KSCHED_MAX_RES);
+  for (int v = 0; v < h->cat.n_templates; ++v)
+    for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[(size_t)v * KSCHED_MAX_RES + r] = h->h_templates[v].remaining[r];
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, rem.data(), rem.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rem is a stack vector
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 8 * sizeof(long long), h->stream));
+  return KSCHED_OK;
+}
+
+static int run_pack(ksched_handle* h) {
+  K2Params k2;
+  k2.cat = h->cat;
+  PackState& s = k2.st;
+  s.classes = h->d_classes.ptr; s.groups = h->d_groups.ptr; s.class_topo = h->d_class_topo.ptr; s.filter_terms = h->d_filter_terms.ptr;
+  s.itype_sets = h->d_itype_sets.ptr; s.itype_complement = h->d_itype_comp.ptr; s.hostname_reqs = h->d_hostname_reqs.ptr;
+  s.order = h->d_order.ptr; s.F = h->d_F.ptr; s.best = h->d_best.ptr;
+  s.pod_pos = h->d_pod_pos.ptr; s.use_F = h->world == 1 ? 1 : 0;
+  s.n_pods = h->n_pods; s.n_classes = h->n_classes; s.n_existing = h->n_existing; s.n_groups = h->n_groups; s.max_new = h->max_new;
+  for (int r = 0; r < KSCHED_MAX_RES; ++r) s.min_req[r] = h->min_req[r];
+  s.pod_class = h->d_pod_class.ptr; s.relax_level = h->d_relax.ptr; s.assign = h->d_assign.ptr; s.place_seq = h->d_place_seq.ptr;
+  s.queue = h->d_queue.ptr; s.last_len = h->d_last_len.ptr; s.last_epoch = h->d_last_epoch.ptr;
+  s.ex_req = h->d_ex_req.ptr; s.ex_avail = h->d_ex_avail.ptr; s.ex_req_present = h->d_ex_req_present.ptr; s.ex_avail_present = h->d_ex_avail_present.ptr;
+  s.ex_vals = h->d_ex_vals.ptr; s.ex_meta = h->d_ex_meta.ptr; s.ex_taintset = h->d_ex_taintset.ptr; s.ex_itype = h->d_ex_itype.ptr;
+  s.ex_hp = h->d_ex_hp.ptr; s.ex_closed = h->d_ex_closed.ptr;
+  s.nn_tmpl = h->d_nn_tmpl.ptr; s.nn_count = h->d_nn_count.ptr; s.nn_tb = h->d_nn_tb.ptr; s.nn_req = h->d_nn_req.ptr;
+  s.nn_req_present = h->d_nn_req_present.ptr; s.nn_maxalloc = h->d_nn_maxalloc.ptr; s.nn_argmax = h->d_nn_argmax.ptr;
+  s.nn_vals = h->d_nn_vals.ptr; s.nn_meta = h->d_nn_meta.ptr; s.nn_opts = h->d_nn_opts.ptr; s.nn_hp = h->d_nn_hp.ptr; s.active = h->d_active.ptr;
+  s.grp_cnt = h->d_grp_cnt.ptr; s.grp_registered = h->d_grp_registered.ptr; s.grp_host = h->d_grp_host.ptr;
+  s.grp_host_row = h->d_grp_host_row.ptr; s.grp_host_total = h->d_grp_host_total.ptr; s.remaining = h->d_remaining.ptr;
+  s.counters = h->d_counters.ptr;
+  pack_kernel<<<1, kPackThreads, 0, h->stream>>>(k2);
+  h->tm.pack_launches = 1;
+  return KSCHED_OK;
+}
+
+static int flush_l2(ksched_handle* h) {
+  const size_t n = (size_t)64 << 20;  // 256 MiB of u32 > 126 MB L2
+  CUDA_TRY(h, h->d_flush.ensure(n));
+  flush_kernel<<<148 * 4, 512, 0, h->stream>>>(h->d_flush.ptr, n);
+  return KSCHED_OK;
+}
+
+static float ev_us(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms * 1000.f;
+}
+
+int ksched_run_resident(ksched_handle* h, int do_flush) {
+  if (!h || !h->uploaded) return KSCHED_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc;
+  if ((rc = reset_state(h)) != KSCHED_OK) return rc;
+  if (do_flush && (rc = flush_l2(h)) != KSCHED_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+  if ((rc = run_sort(h)) != KSCHED_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  if ((rc = run_feasibility(h)) != KSCHED_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
+  h->tm.allreduce_us = 0;
+  if (h->world > 1 && h->comm) {
+    ncclResult_t r = ncclAllReduce(h->d_best.ptr, h->d_best.ptr, (size_t)h->n_pods, ncclUint64, ncclMin, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + ncclGetErrorString(r); return KSCHED_ERR_NCCL; }
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev[3], h->stream));
+  if ((rc = run_pack(h)) != KSCHED_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  h->tm.sort_us = ev_us(h->ev[0], h->ev[1]);
+  h->tm.feasibility_us = ev_us(h->ev[1], h->ev[2]);
+  h->tm.allreduce_us = ev_us(h->ev[2], h->ev[3]);
+  h->tm.pack_us = ev_us(h->ev[3], h->ev[4]);
+  h->tm.total_us = ev_us(h->ev[0], h->ev[4]);
+  return KSCHED_OK;
+}
+
+int ksched_run_feasibility_only(ksched_handle* h, int do_flush, float* elapsed_us) {
+  if (!h || !h->uploaded) return KSCHED_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc;
+  if (do_flush && (rc = flush_l2(h)) != KSCHED_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[5], h->stream));
+  if ((rc = run_feasibility(h)) != KSCHED_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[6], h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  if (elapsed_us) *elapsed_us = ev_us(h->ev[5], h->ev[6]);
+  h->tm.feasibility_us = ev_us(h->ev[5], h->ev[6]);
+  return KSCHED_OK;
+}
+
+int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* res) {
+  if (!h || !pb || !res || !h->uploaded) return KSCHED_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int P = h->n_pods, NE = h->n_existing, MAXN = h->max_new, W32 = h->cat.W32, W64 = h->W64, V = h->cat.n_templates;
+  long long counters[8];
+  CUDA_TRY(h, cudaMemcpyAsync(counters, h->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (counters[4] != 0) {
+    h->err = counters[4] == KSCHED_ERR_OVERFLOW ? "new-node capacity exceeded" : "a pod is constrained by more topology groups than the kernel supports";
+    return (int)counters[4];
+  }
+  const int n_new = (int)counters[0];
+  h->tm.d2h_bytes = (int64_t)sizeof counters + (int64_t)P * 4 * ((res->assign != nullptr) + (res->relax_level != nullptr) + (res->place_seq != nullptr)) +
+                    (int64_t)n_new * (1 + 4 + 4 + 8 + 64 + 128 + (int64_t)W32 * 4) + (res->existing_reqs ? (int64_t)NE * 136 : 0) +
+                    (res->feasibility ? (int64_t)P * V * W32 * 4 + (int64_t)P * 4 : 0) + (res->best_column ? (int64_t)P * 12 : 0);
+  res->n_new_nodes = n_new;
+  res->n_unscheduled = (int)counters[1];
+  res->nodes_visited = counters[2];
+  res->add_calls = counters[3];
+  h->tm.pack_steps = counters[5];
+  if (res->assign) CUDA_TRY(h, cudaMemcpyAsync(res->assign, h->d_assign.ptr, (size_t)P * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (res->relax_level) CUDA_TRY(h, cudaMemcpyAsync(res->relax_level, h->d_relax.ptr, (size_t)P * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (res->place_seq) CUDA_TRY(h, cudaMemcpyAsync(res->place_seq, h->d_place_seq.ptr, (size_t)P * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (n_new > 0 && res->new_nodes && res->new_node_types) {
+    std::vector<uint8_t> tmpl(n_new);
+    std::vector<int32_t> count(n_new);
+    std::vector<int64_t> req((size_t)8 * n_new);
+    std::vector<uint32_t> reqp(n_new), opts((size_t)W32 * n_new);
+    std::vector<uint64_t> vals((size_t)16 * n_new), meta(n_new);
+    CUDA_TRY(h, cudaMemcpyAsync(tmpl.data(), h->d_nn_tmpl.ptr, n_new, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(count.data(), h->d_nn_count.ptr, (size_t)n_new * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(reqp.data(), h->d_nn_req_present.ptr, (size_t)n_new * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(meta.data(), h->d_nn_meta.ptr, (size_t)n_new * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(req.data(), (size_t)n_new * 8, h->d_nn_req.ptr, (size_t)MAXN * 8, (size_t)n_new * 8, 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(vals.data(), (size_t)n_new * 8, h->d_nn_vals.ptr, (size_t)MAXN * 8, (size_t)n_new * 8, 16, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(opts.data(), (size_t)n_new * 4, h->d_nn_opts.ptr, (size_t)MAXN * 4, (size_t)n_new * 4, W32, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int n = 0; n < n_new; ++n) {
+      ksched_new_node& o = res->new_nodes[n];
+      std::memset(&o, 0, sizeof o);
+      o.template_index = tmpl[n];
+      o.pod_count = count[n];
+      o.requests_present = reqp[n];
+      for (int r = 0; r < 8; ++r) o.requests[r] = req[(size_t)r * n_new + n];
+      for (int k = 0; k < 16; ++k) o.reqs.values[k] = vals[(size_t)k * n_new + n];
+      o.reqs.meta = meta[n];
+      uint32_t* dst = reinterpret_cast<uint32_t*>(res->new_node_types + (size_t)n * W64);
+      for (int w = 0; w < W32; ++w) dst[w] = opts[(size_t)w * n_new + n];
+    }
+  }
+  if (res->existing_reqs && NE > 0) {
+    std::vector<uint64_t> vals((size_t)16 * NE), meta(NE);
+    CUDA_TRY(h, cudaMemcpyAsync(vals.data(), h->d_ex_vals.ptr, vals.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(meta.data(), h->d_ex_meta.ptr, meta.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int e = 0; e < NE; ++e) {
+      for (int k = 0; k < 16; ++k) res->existing_reqs[e].values[k] = vals[(size_t)k * NE + e];
+      res->existing_reqs[e].meta = meta[e];
+    }
+  }
+  if (res->feasibility) {
+    // device rows are in FFD (queue) order; the caller gets them in its own pod order
+    std::vector<uint32_t> order(P), F((size_t)P * V * W32);
+    CUDA_TRY(h, cudaMemcpyAsync(order.data(), h->d_order.ptr, (size_t)P * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(F.data(), h->d_F.ptr, F.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t rowb = (size_t)V * W32;
+    for (int j = 0; j < P; ++j) std::memcpy(reinterpret_cast<uint32_t*>(res->feasibility) + (size_t)order[j] * rowb, &F[(size_t)j * rowb], rowb * 4);
+  }
+  if (res->best_column) {
+    std::vector<uint32_t> order(P);
+    std::vector<unsigned long long> best(P);
+    CUDA_TRY(h, cudaMemcpyAsync(order.data(), h->d_order.ptr, (size_t)P * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(best.data(), h->d_best.ptr, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < P; ++j) res->best_column[order[j]] = best[j];
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return KSCHED_OK;
+}
+
+int ksched_solve(ksched_handle* h, const ksched_problem* pb, ksched_result* res) {
+  if (!h || !pb || !res) return KSCHED_ERR_INVALID;
+  cudaEvent_t e0 = h->ev[7];
+  (void)e0;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = ksched_upload(h, pb);
+  if (rc != KSCHED_OK) return rc;
+  auto t1 = std::chrono::steady_clock::now();
+  rc = ksched_run_resident(h, 0);
+  if (rc != KSCHED_OK) return rc;
+  auto t2 = std::chrono::steady_clock::now();
+  rc = ksched_download(h, pb, res);
+  auto t3 = std::chrono::steady_clock::now();
+  h->tm.upload_us = std::chrono::duration<double, std::micro>(t1 - t0).count();
+  h->tm.download_us = std::chrono::duration<double, std::micro>(t3 - t2).count();
+  (void)t2;
+  return rc;
+}
+
+int ksched_get_timings(const ksched_handle* h, ksched_timings* out) {
+  if (!h || !out) return KSCHED_ERR_INVALID;
+  *out = h->tm;
+  return KSCHED_OK;
+}
+
+}  // extern "C"

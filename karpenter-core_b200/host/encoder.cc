@@ -1,0 +1,1112 @@
+// Problem -> flat C-ABI encoder (see encoder.h). Product code: it must not use anything under oracle/.
+//
+// Reference steps restated here because they happen before Solve, on the host, in the reference too:
+//   provisioner.go:237-296   template order, instance types per provisioner, domain universe
+//   scheduler.go:221-267     daemonset overhead, existing nodes, remaining provisioner limits
+//   topology.go:56-117,183-322  topology groups, owners, inverse anti-affinity groups, countDomains
+//   preferences.go:36-145    the relaxation chain of every pod (pre-computed as classes)
+#include "encoder.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <tuple>
+#include <set>
+#include <stdexcept>
+
+#include "reqmask.cuh"
+
+namespace khost {
+using namespace kmodel;
+using ksched::KeyMeta;
+using ksched::Req;
+
+namespace {
+
+[[noreturn]] void unsupported(const std::string& what) { throw std::runtime_error("unsupported: " + what); }
+
+const char* kHostname = "kubernetes.io/hostname";
+const char* kZone = "topology.kubernetes.io/zone";
+const char* kCapacityType = "karpenter.sh/capacity-type";
+const char* kProvisionerName = "karpenter.sh/provisioner-name";
+const char* kInitialized = "karpenter.sh/initialized";
+const char* kInstanceType = "node.kubernetes.io/instance-type";
+
+std::string normalize_key(const std::string& k) {  // v1alpha5.NormalizedLabels, labels.go:103-109
+  if (k == "failure-domain.beta.kubernetes.io/zone") return kZone;
+  if (k == "beta.kubernetes.io/arch") return "kubernetes.io/arch";
+  if (k == "beta.kubernetes.io/os") return "kubernetes.io/os";
+  if (k == "beta.kubernetes.io/instance-type") return kInstanceType;
+  if (k == "failure-domain.beta.kubernetes.io/region") return "topology.kubernetes.io/region";
+  return k;
+}
+
+bool parse_int(const std::string& s, int64_t* out) {  // strconv.Atoi
+  if (s.empty()) return false;
+  size_t i = 0;
+  bool neg = false;
+  if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
+  if (i >= s.size() || s.size() - i > 18) return false;
+  int64_t v = 0;
+  for (; i < s.size(); ++i) {
+    if (s[i] < '0' || s[i] > '9') return false;
+    v = v * 10 + (s[i] - '0');
+  }
+  *out = neg ? -v : v;
+  return true;
+}
+
+// ---- resources (utils/resources/resources.go)
+ResourceList merge(const ResourceList& a, const ResourceList& b) {
+  ResourceList r = a;
+  for (auto& kv : b) r[kv.first] += kv.second;
+  return r;
+}
+ResourceList pod_requests(const Pod& p) {  // RequestsForPods(pod): Ceiling + pods:1
+  ResourceList r;
+  auto eff = [](const Container& c) {
+    ResourceList x = c.requests;
+    for (auto& kv : c.limits) if (!x.count(kv.first)) x[kv.first] = kv.second;
+    return x;
+  };
+  for (auto& c : p.containers) r = merge(r, eff(c));
+  for (auto& c : p.init_containers) {
+    ResourceList x = eff(c);
+    for (auto& kv : x) {
+      auto it = r.find(kv.first);
+      if (it == r.end() || kv.second > it->second) r[kv.first] = kv.second;
+    }
+  }
+  r["pods"] = 1000;
+  return r;
+}
+
+// ---- tolerations (k8s.io/api core/v1 Toleration.ToleratesTaint)
+bool tolerates_taint(const Toleration& t, const Taint& taint) {
+  if (!t.effect.empty() && t.effect != taint.effect) return false;
+  if (!t.key.empty() && t.key != taint.key) return false;
+  if (t.op.empty() || t.op == "Equal") return t.value == taint.value;
+  return t.op == "Exists";
+}
+bool tolerates_all(const std::vector<Taint>& taints, const std::vector<Toleration>& tols) {  // taints.go:28-40
+  for (auto& taint : taints) {
+    bool ok = false;
+    for (auto& t : tols) ok = ok || tolerates_taint(t, taint);
+    if (!ok) return false;
+  }
+  return true;
+}
+std::string taints_key(const std::vector<Taint>& ts) {
+  std::string s;
+  for (auto& t : ts) s += t.key + "=" + t.value + ":" + t.effect + ";";
+  return s;
+}
+
+// ---- label selectors (apimachinery): nil -> nothing, invalid -> nothing
+bool selector_valid(const LabelSelector& s) {
+  for (auto& e : s.match_expressions) {
+    if ((e.op == Op::In || e.op == Op::NotIn) && e.values.empty()) return false;
+    if ((e.op == Op::Exists || e.op == Op::DoesNotExist) && !e.values.empty()) return false;
+    if (e.op == Op::Gt || e.op == Op::Lt) return false;
+  }
+  return true;
+}
+bool selector_matches(const LabelSelector& s, const Labels& labels) {  // s non-nil
+  if (!selector_valid(s)) return false;
+  for (auto& kv : s.match_labels) {
+    auto it = labels.find(kv.first);
+    if (it == labels.end() || it->second != kv.second) return false;
+  }
+  for (auto& e : s.match_expressions) {
+    auto it = labels.find(e.key);
+    bool has = it != labels.end();
+    bool in = has && std::find(e.values.begin(), e.values.end(), it->second) != e.values.end();
+    if (e.op == Op::In && !in) return false;
+    if (e.op == Op::NotIn && has && in) return false;
+    if (e.op == Op::Exists && !has) return false;
+    if (e.op == Op::DoesNotExist && has) return false;
+  }
+  return true;
+}
+std::string selector_key(const LabelSelector& s) {
+  if (s.is_nil) return "<nil>";
+  std::string out = "{";
+  for (auto& kv : s.match_labels) out += kv.first + "=" + kv.second + ",";
+  out += "|";
+  std::vector<std::string> ex;
+  for (auto& e : s.match_expressions) {
+    std::string x = e.key + ":" + std::to_string((int)e.op) + ":";
+    std::vector<std::string> v = e.values;
+    std::sort(v.begin(), v.end());
+    for (auto& y : v) x += y + ",";
+    ex.push_back(x);
+  }
+  std::sort(ex.begin(), ex.end());
+  for (auto& x : ex) out += x + ";";
+  return out + "}";
+}
+
+std::string reqs_key(const std::vector<NodeSelectorRequirement>& rs) {
+  std::string s;
+  for (auto& r : rs) {
+    s += normalize_key(r.key) + ":" + std::to_string((int)r.op) + ":";
+    for (auto& v : r.values) s += v + ",";
+    s += ";";
+  }
+  return s;
+}
+std::string labels_key(const Labels& l) {
+  std::string s;
+  for (auto& kv : l) s += kv.first + "=" + kv.second + ",";
+  return s;
+}
+std::string term_key(const PodAffinityTerm& t) {
+  std::string s = t.topology_key + "|" + selector_key(t.selector) + "|";
+  for (auto& n : t.namespaces) s += n + ",";
+  return s;
+}
+
+// Everything the scheduler can observe about a pod except its identity (uid / name / timestamp).
+std::string class_key(const Pod& p, const ResourceList& req) {
+  std::string s = "ns=" + p.ns + "|L=" + labels_key(p.labels) + "|R=";
+  for (auto& kv : req) s += kv.first + ":" + std::to_string(kv.second) + ",";
+  s += "|S=" + labels_key(p.node_selector) + "|NA=" + std::to_string(p.has_node_affinity) + std::to_string(p.has_required_node_affinity);
+  for (auto& t : p.required_node_terms) s += "[" + reqs_key(t) + "]";
+  s += "|NP=";
+  for (auto& t : p.preferred_node_terms) s += std::to_string(t.weight) + "[" + reqs_key(t.preference) + "]";
+  s += "|PA=";
+  for (auto& t : p.pod_affinity_required) s += "(" + term_key(t) + ")";
+  s += "|PAP=";
+  for (auto& t : p.pod_affinity_preferred) s += std::to_string(t.weight) + "(" + term_key(t.term) + ")";
+  s += "|PAA=";
+  for (auto& t : p.pod_anti_affinity_required) s += "(" + term_key(t) + ")";
+  s += "|PAAP=";
+  for (auto& t : p.pod_anti_affinity_preferred) s += std::to_string(t.weight) + "(" + term_key(t.term) + ")";
+  s += "|TS=";
+  for (auto& t : p.topology_spread)
+    s += std::to_string(t.max_skew) + ":" + t.topology_key + ":" + std::to_string(t.schedule_anyway) + ":" + selector_key(t.selector) + ";";
+  s += "|T=";
+  for (auto& t : p.tolerations) s += t.key + ":" + t.op + ":" + t.value + ":" + t.effect + ";";
+  s += "|HP=";
+  for (auto& c : p.containers)
+    for (auto& hp : c.ports) s += hp.ip + ":" + std::to_string(hp.port) + ":" + hp.protocol + ";";
+  return s;
+}
+
+// ---- Preferences.Relax restated (preferences.go:36-145); sorts are stable (tie order is unpinned in Go)
+template <class T>
+bool remove_heaviest(std::vector<T>& terms) {
+  if (terms.empty()) return false;
+  std::stable_sort(terms.begin(), terms.end(), [](const T& a, const T& b) { return a.weight > b.weight; });
+  terms.erase(terms.begin());
+  return true;
+}
+bool relax(Pod& p, bool tolerate_prefer_no_schedule) {
+  if (p.has_node_affinity && p.has_required_node_affinity && p.required_node_terms.size() > 1) {
+    p.required_node_terms.erase(p.required_node_terms.begin());
+    return true;
+  }
+  if (remove_heaviest(p.pod_affinity_preferred)) return true;
+  if (remove_heaviest(p.pod_anti_affinity_preferred)) return true;
+  if (p.has_node_affinity && remove_heaviest(p.preferred_node_terms)) return true;
+  for (size_t i = 0; i < p.topology_spread.size(); ++i)
+    if (p.topology_spread[i].schedule_anyway) {
+      p.topology_spread[i] = p.topology_spread.back();
+      p.topology_spread.pop_back();
+      return true;
+    }
+  if (tolerate_prefer_no_schedule) {
+    for (auto& x : p.tolerations)
+      if (x.key.empty() && x.effect == "PreferNoSchedule" && x.op == "Exists" && x.value.empty()) return false;
+    p.tolerations.push_back({"", "Exists", "", "PreferNoSchedule"});
+    return true;
+  }
+  return false;
+}
+
+struct HostPortEntry {
+  std::string ip;
+  int32_t port;
+  std::string protocol;
+  bool operator<(const HostPortEntry& o) const { return std::tie(ip, port, protocol) < std::tie(o.ip, o.port, o.protocol); }
+};
+bool ip_unspecified(const std::string& ip) { return ip == "0.0.0.0" || ip == "::"; }
+bool hp_matches(const HostPortEntry& a, const HostPortEntry& b) {  // hostportusage.go:45-57
+  if (a.protocol != b.protocol || a.port != b.port) return false;
+  return a.ip == b.ip || ip_unspecified(a.ip) || ip_unspecified(b.ip);
+}
+std::vector<HostPortEntry> host_ports(const Pod& p) {  // hostportusage.go:118-144
+  std::vector<HostPortEntry> out;
+  for (auto& c : p.containers)
+    for (auto& hp : c.ports)
+      if (hp.port != 0) out.push_back({hp.ip.empty() ? "0.0.0.0" : hp.ip, hp.port, hp.protocol});
+  return out;
+}
+
+struct Builder {
+  const Problem& P;
+  Encoded& E;
+  std::set<std::string> well_known;
+  std::map<std::string, int> key_id;                       // mask key -> id
+  std::vector<std::map<std::string, int>> value_id;        // per key
+  std::map<std::string, int> res_id;
+  std::vector<KeyMeta> key_meta;
+  std::map<std::string, int> taintset_id;
+  std::vector<std::vector<Taint>> taintsets;
+  std::vector<HostPortEntry> hp_entries;
+  std::map<std::string, int> type_col;                     // instance type name -> column
+
+  Builder(const Problem& p, Encoded& e) : P(p), E(e) {}
+
+  // ------------------------------------------------------------ requirement encoding
+  int key_of(const std::string& k) const {
+    auto it = key_id.find(normalize_key(k));
+    return it == key_id.end() ? -1 : it->second;
+  }
+  Req encode_req(int k, Op op, const std::vector<std::string>& values) const {  // NewRequirement requirement.go:44-68
+    Req r{0, 0, 0, true, true, false, false};
+    r.complement = !(op == Op::In || op == Op::DoesNotExist);
+    if (op == Op::In || op == Op::NotIn)
+      for (auto& v : values) r.values |= 1ull << value_id[k].at(v);
+    if (op == Op::Gt) { r.has_gt = true; parse_int(values.at(0), &r.gt); }
+    if (op == Op::Lt) { r.has_lt = true; parse_int(values.at(0), &r.lt); }
+    return r;
+  }
+  void add_req(ksched_reqset& rs, ksched_bounds& b, int k, const Req& r) const {  // Requirements.Add
+    Req cur = ksched::req_load(rs, &b, k);
+    ksched::req_store(rs, &b, k, ksched::key_add(cur, r, key_meta[k]));
+  }
+  // requirements on mask keys only; hostname / instance-type requirements are returned separately
+  struct Special {
+    std::vector<NodeSelectorRequirement> hostname, itype;
+  };
+  void add_selector_reqs(ksched_reqset& rs, ksched_bounds& b, const std::vector<NodeSelectorRequirement>& list, Special* sp) const {
+    for (auto& r : list) {
+      std::string key = normalize_key(r.key);
+      if (key == kHostname) { if (sp) sp->hostname.push_back(r); else unsupported("hostname requirement here"); continue; }
+      if (key == kInstanceType) { if (sp) sp->itype.push_back(r); else unsupported("instance-type requirement here"); continue; }
+      int k = key_of(key);
+      if (k < 0) continue;  // key inactive: cannot influence any decision
+      add_req(rs, b, k, encode_req(k, r.op, r.values));
+    }
+  }
+  static std::vector<NodeSelectorRequirement> label_reqs(const Labels& l) {  // NewLabelRequirements requirements.go:54-59
+    std::vector<NodeSelectorRequirement> out;
+    for (auto& kv : l) out.push_back({kv.first, Op::In, {kv.second}});
+    return out;
+  }
+  // NewPodRequirements requirements.go:61-78 (the preferred-term sort is stable here)
+  void pod_requirements(const Pod& pod, ksched_reqset& rs, ksched_bounds& b, Special* sp) const {
+    add_selector_reqs(rs, b, label_reqs(pod.node_selector), sp);
+    if (!pod.has_node_affinity) return;
+    if (!pod.preferred_node_terms.empty()) {
+      auto terms = pod.preferred_node_terms;
+      std::stable_sort(terms.begin(), terms.end(), [](auto& x, auto& y) { return x.weight > y.weight; });
+      add_selector_reqs(rs, b, terms[0].preference, sp);
+    }
+    if (pod.has_required_node_affinity && !pod.required_node_terms.empty())
+      add_selector_reqs(rs, b, pod.required_node_terms[0], sp);
+  }
+  bool compatible(const ksched_reqset& node, const ksched_bounds& nb, const ksched_reqset& inc, const ksched_bounds& ib) const {
+    for (int k = 0; k < (int)E.key_names.size(); ++k) {
+      Req n = ksched::req_load(node, &nb, k), i = ksched::req_load(inc, &ib, k);
+      if (!ksched::key_compatible(n, i, E.keys[k].well_known != 0, key_meta[k])) return false;
+    }
+    return true;
+  }
+
+  int taintset(const std::vector<Taint>& ts) {
+    std::string k = taints_key(ts);
+    auto it = taintset_id.find(k);
+    if (it != taintset_id.end()) return it->second;
+    int id = (int)taintsets.size();
+    if (id >= 64) unsupported("more than 64 distinct taint sets");
+    taintset_id[k] = id;
+    taintsets.push_back(ts);
+    return id;
+  }
+  int hp_entry(const HostPortEntry& e) {
+    for (size_t i = 0; i < hp_entries.size(); ++i)
+      if (hp_entries[i].ip == e.ip && hp_entries[i].port == e.port && hp_entries[i].protocol == e.protocol) return (int)i;
+    if (hp_entries.size() >= 64) unsupported("more than 64 distinct host-port entries");
+    hp_entries.push_back(e);
+    return (int)hp_entries.size() - 1;
+  }
+  int resource(const std::string& name) const {
+    auto it = res_id.find(name);
+    if (it == res_id.end()) throw std::runtime_error("internal: unknown resource " + name);
+    return it->second;
+  }
+  uint32_t fill_resources(const ResourceList& r, int64_t* out) const {
+    uint32_t present = 0;
+    for (int i = 0; i < KSCHED_MAX_RES; ++i) out[i] = 0;
+    for (auto& kv : r) {
+      int id = resource(kv.first);
+      out[id] = kv.second;
+      present |= 1u << id;
+    }
+    return present;
+  }
+};
+
+std::vector<Taint> state_node_taints(const StateNode& n) {  // state/node.go:61-78
+  auto lab = [&](const char* k) { auto it = n.labels.find(k); return it == n.labels.end() ? std::string() : it->second; };
+  bool initialized = lab(kInitialized) == "true", owned = !lab(kProvisionerName).empty();
+  std::vector<Taint> eph = {{"node.kubernetes.io/not-ready", "", "NoSchedule"}, {"node.kubernetes.io/unreachable", "", "NoSchedule"}};
+  if (!initialized && owned) eph.insert(eph.end(), n.startup_taints.begin(), n.startup_taints.end());
+  std::vector<Taint> out;
+  for (auto& t : n.taints) {
+    bool rej = false;
+    for (auto& e : eph) rej = rej || (e.key == t.key && e.value == t.value && e.effect == t.effect);
+    if (!rej) out.push_back(t);
+  }
+  return out;
+}
+
+// topology group under construction (topologygroup.go:53-86)
+struct Group {
+  int type;  // 0 spread, 1 affinity, 2 anti-affinity
+  std::string key;
+  int32_t max_skew;
+  std::set<std::string> namespaces;
+  LabelSelector selector;
+  bool filter_nil = true;
+  std::vector<std::pair<ksched_reqset, ksched_bounds>> filter;  // TopologyNodeFilter terms
+  std::string filter_key;
+  bool inverse = false;
+  std::map<std::string, int32_t> counts;  // domain string -> count (countDomains / inverse Record)
+  std::set<size_t> owner_specs;           // indices into the spec table (classes)
+  bool selects(const Pod& p) const {      // topologygroup.go:246-252
+    if (selector.is_nil) return false;
+    return namespaces.count(p.ns) && selector_matches(selector, p.labels);
+  }
+  std::string hash() const {
+    std::string h = key + "|" + std::to_string(type) + "|" + std::to_string(max_skew) + "|";
+    for (auto& n : namespaces) h += n + ",";
+    return h + "|" + selector_key(selector) + "|" + filter_key;
+  }
+};
+
+}  // namespace
+
+std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candidates) {
+  auto enc = std::make_unique<Encoded>();
+  Encoded& E = *enc;
+  Builder B(P, E);
+
+  // ------------------------------------------------------------------ who takes part
+  std::vector<int> state_nodes;
+  {
+    std::set<int> cand(candidates.begin(), candidates.end());
+    auto reschedulable = [](const Pod& p) { return !p.is_daemonset && !p.terminal && !p.terminating; };  // utils/node/node.go:30-50
+    for (size_t i = 0; i < P.nodes.size(); ++i)
+      if (!cand.count((int)i) && !P.nodes[i].marked_for_deletion) state_nodes.push_back((int)i);
+    for (auto& p : P.pods) E.pods.push_back(&p);
+    for (int c : candidates)
+      for (auto& p : P.nodes.at(c).pods) if (reschedulable(p)) E.pods.push_back(&p);
+    for (size_t i = 0; i < P.nodes.size(); ++i)
+      if (!cand.count((int)i) && P.nodes[i].marked_for_deletion)
+        for (auto& p : P.nodes[i].pods) if (reschedulable(p)) E.pods.push_back(&p);
+  }
+  const size_t NP = E.pods.size();
+  {
+    std::set<std::string> uids;
+    for (auto* p : E.pods)
+      if (!uids.insert(p->uid).second) throw std::runtime_error("pods must have unique UIDs: " + p->uid);
+  }
+  if (P.provisioners.empty()) throw std::runtime_error("no provisioners found");
+  if (P.provisioners.size() > KSCHED_MAX_TEMPLATES) unsupported("more than 16 provisioners");
+
+  B.well_known = {kProvisionerName, kZone, "topology.kubernetes.io/region", kInstanceType, "kubernetes.io/arch", "kubernetes.io/os", kCapacityType};
+  B.well_known.insert(P.extra_well_known_labels.begin(), P.extra_well_known_labels.end());
+
+  // template order: OrderByWeight (v1alpha5/provisioner.go:132-136), stable
+  for (size_t i = 0; i < P.provisioners.size(); ++i) E.template_provisioner.push_back((int)i);
+  std::stable_sort(E.template_provisioner.begin(), E.template_provisioner.end(),
+                   [&](int a, int b) { return P.provisioners[a].weight > P.provisioners[b].weight; });
+  bool tolerate_pns = false;  // scheduler.go:49-56
+  for (auto& pr : P.provisioners)
+    for (auto& t : pr.taints) if (t.effect == "PreferNoSchedule") tolerate_pns = true;
+
+  // ------------------------------------------------------------------ pod specs: classes and relaxation chains
+  struct Spec { Pod pod; ResourceList req; uint32_t next = KSCHED_NONE; };
+  std::vector<Spec> specs;
+  std::map<std::string, uint32_t> spec_id;
+  std::function<uint32_t(const Pod&)> intern = [&](const Pod& p) -> uint32_t {
+    ResourceList req = pod_requests(p);
+    std::string k = class_key(p, req);
+    auto it = spec_id.find(k);
+    if (it != spec_id.end()) return it->second;
+    uint32_t id = (uint32_t)specs.size();
+    spec_id[k] = id;
+    specs.push_back({p, req, KSCHED_NONE});
+    Pod relaxed = p;
+    // NewPodRequirements sorts the preferred terms in place before Relax ever runs (requirements.go:69)
+    std::stable_sort(relaxed.preferred_node_terms.begin(), relaxed.preferred_node_terms.end(),
+                     [](auto& a, auto& b) { return a.weight > b.weight; });
+    if (relax(relaxed, tolerate_pns)) {
+      uint32_t nx = intern(relaxed);
+      specs[id].next = nx;
+    }
+    return id;
+  };
+  E.pod_class.resize(NP);
+  for (size_t i = 0; i < NP; ++i) E.pod_class[i] = intern(*E.pods[i]);
+  std::vector<Pod> daemons = P.daemonset_pods;
+
+  // ------------------------------------------------------------------ active keys + dictionary
+  // pod-side keys: anything a pod / daemonset / topology group / node filter can put into a node's requirements
+  std::set<std::string> pod_side;
+  auto note_reqs = [&](const std::vector<NodeSelectorRequirement>& rs) { for (auto& r : rs) pod_side.insert(normalize_key(r.key)); };
+  auto note_pod = [&](const Pod& p) {
+    for (auto& kv : p.node_selector) pod_side.insert(normalize_key(kv.first));
+    for (auto& t : p.required_node_terms) note_reqs(t);
+    for (auto& t : p.preferred_node_terms) note_reqs(t.preference);
+    for (auto& t : p.pod_affinity_required) pod_side.insert(t.topology_key);
+    for (auto& t : p.pod_affinity_preferred) pod_side.insert(t.term.topology_key);
+    for (auto& t : p.pod_anti_affinity_required) pod_side.insert(t.topology_key);
+    for (auto& t : p.pod_anti_affinity_preferred) pod_side.insert(t.term.topology_key);
+    for (auto& t : p.topology_spread) pod_side.insert(t.topology_key);
+  };
+  for (auto& s : specs) note_pod(s.pod);
+  for (auto& d : daemons) note_pod(d);
+  if (!P.empty_topology)
+    for (auto& n : P.nodes)
+      for (auto& p : n.pods)
+        for (auto& t : p.pod_anti_affinity_required) pod_side.insert(t.topology_key);
+  std::set<std::string> type_keys, template_keys;
+  for (auto& it : P.instance_types) for (auto& r : it.requirements) type_keys.insert(normalize_key(r.key));
+  for (auto& pr : P.provisioners) {
+    for (auto& r : pr.requirements) template_keys.insert(normalize_key(r.key));
+    for (auto& kv : pr.labels) template_keys.insert(normalize_key(kv.first));
+    template_keys.insert(kProvisionerName);
+  }
+  // Active keys: everything that can appear in a node's requirements (template or pod side). Keys that only
+  // instance types define can never meet a node requirement (Intersects walks keys present on BOTH sides,
+  // requirements.go:189-190) and are dropped.
+  std::set<std::string> active = pod_side;
+  active.insert(template_keys.begin(), template_keys.end());
+  (void)type_keys;
+  active.erase(kHostname);
+  active.erase(kInstanceType);
+  if (active.size() > KSCHED_MAX_KEYS) unsupported("more than 16 active label keys");
+  for (auto& k : active) {
+    B.key_id[k] = (int)E.key_names.size();
+    E.key_names.push_back(k);
+  }
+  const int NK = (int)E.key_names.size();
+  std::vector<std::set<std::string>> vals(NK);
+  auto note_vals = [&](const std::vector<NodeSelectorRequirement>& rs) {
+    for (auto& r : rs) {
+      int k = B.key_of(r.key);
+      if (k < 0) continue;
+      if (r.op == Op::In || r.op == Op::NotIn) vals[k].insert(r.values.begin(), r.values.end());
+    }
+  };
+  auto note_label_vals = [&](const Labels& l) {
+    for (auto& kv : l) { int k = B.key_of(kv.first); if (k >= 0) vals[k].insert(kv.second); }
+  };
+  auto note_pod_vals = [&](const Pod& p) {
+    note_label_vals(p.node_selector);
+    for (auto& t : p.required_node_terms) note_vals(t);
+    for (auto& t : p.preferred_node_terms) note_vals(t.preference);
+  };
+  for (auto& s : specs) note_pod_vals(s.pod);
+  for (auto& d : daemons) note_pod_vals(d);
+  for (auto& it : P.instance_types) note_vals(it.requirements);
+  for (auto& pr : P.provisioners) {
+    note_vals(pr.requirements);
+    Labels l = pr.labels;
+    l[kProvisionerName] = pr.name;
+    note_label_vals(l);
+  }
+  for (auto& n : P.nodes) note_label_vals(n.labels);
+  B.value_id.resize(NK);
+  E.key_values.resize(NK);
+  E.keys.resize(NK);
+  E.key_int_values.assign((size_t)NK * 64, 0);
+  B.key_meta.resize(NK);
+  for (int k = 0; k < NK; ++k) {
+    if (vals[k].size() > 63) unsupported("label key " + E.key_names[k] + " has more than 63 distinct values");
+    ksched_keyinfo& ki = E.keys[k];
+    std::memset(&ki, 0, sizeof ki);
+    int b = 0;
+    for (auto& v : vals[k]) {
+      B.value_id[k][v] = b;
+      E.key_values[k].push_back(v);
+      ki.dict_mask |= 1ull << b;
+      int64_t iv;
+      if (parse_int(v, &iv)) { ki.int_mask |= 1ull << b; E.key_int_values[(size_t)k * 64 + b] = iv; }
+      ++b;
+    }
+    ki.well_known = B.well_known.count(E.key_names[k]) ? 1 : 0;
+    ki.is_zone = E.key_names[k] == kZone;
+    ki.is_capacity_type = E.key_names[k] == kCapacityType;
+  }
+  for (int k = 0; k < NK; ++k) B.key_meta[k] = KeyMeta{E.keys[k].int_mask, &E.key_int_values[(size_t)k * 64]};
+  const int zone_key = B.key_of(kZone), ct_key = B.key_of(kCapacityType);
+
+  // ------------------------------------------------------------------ resources
+  {
+    std::set<std::string> names;
+    auto note = [&](const ResourceList& r) { for (auto& kv : r) names.insert(kv.first); };
+    for (auto& s : specs) note(s.req);
+    for (auto& d : daemons) note(pod_requests(d));
+    for (auto& it : P.instance_types) { note(it.capacity); }
+    for (auto& pr : P.provisioners) note(pr.limits);
+    for (auto& n : P.nodes) { note(n.allocatable); note(n.capacity); for (auto& p : n.pods) note(pod_requests(p)); }
+    E.res_names = {"cpu", "memory", "pods"};
+    for (auto& n : names) if (n != "cpu" && n != "memory" && n != "pods") E.res_names.push_back(n);
+    if (E.res_names.size() > KSCHED_MAX_RES) unsupported("more than 8 distinct resources");
+    for (size_t i = 0; i < E.res_names.size(); ++i) B.res_id[E.res_names[i]] = (int)i;
+  }
+
+  // ------------------------------------------------------------------ instance types (columns, price order)
+  const int NT = (int)P.instance_types.size();
+  E.type_words = (NT + 63) / 64;
+  if (E.type_words == 0) E.type_words = 1;
+  {
+    std::vector<double> min_price(NT, std::numeric_limits<double>::infinity());
+    for (int i = 0; i < NT; ++i)
+      for (auto& o : P.instance_types[i].offerings)
+        if (o.available && o.price < min_price[i]) min_price[i] = o.price;
+    E.type_input_index.resize(NT);
+    for (int i = 0; i < NT; ++i) E.type_input_index[i] = i;
+    std::stable_sort(E.type_input_index.begin(), E.type_input_index.end(), [&](int a, int b) { return min_price[a] < min_price[b]; });
+    E.types.resize(NT);
+    E.type_capacity.assign((size_t)NT * KSCHED_MAX_RES, 0);
+    for (int c = 0; c < NT; ++c) {
+      const InstanceType& it = P.instance_types[E.type_input_index[c]];
+      if (B.type_col.count(it.name)) unsupported("duplicate instance type name " + it.name);
+      B.type_col[it.name] = c;
+      ksched_type_row& row = E.types[c];
+      std::memset(&row, 0, sizeof row);
+      ksched_reqset rs{};
+      ksched_bounds bd{};
+      for (auto& r : it.requirements) {
+        std::string key = normalize_key(r.key);
+        if (key == kHostname) unsupported("instance type with a hostname requirement");
+        if (key == kInstanceType) {
+          if (!(r.op == Op::In && r.values.size() == 1 && r.values[0] == it.name)) unsupported("instance-type requirement of a type must be In [its own name]");
+          continue;
+        }
+        int k = B.key_of(key);
+        if (k < 0) continue;
+        if (r.op == Op::Gt || r.op == Op::Lt || r.op == Op::NotIn || r.op == Op::Exists)
+          unsupported("instance type " + it.name + " has a complement / bounded requirement on " + key);
+        B.add_req(rs, bd, k, B.encode_req(k, r.op, r.values));
+      }
+      std::memcpy(row.values, rs.values, sizeof row.values);
+      row.meta = rs.meta;
+      ResourceList overhead = merge(merge(it.kube_reserved, it.system_reserved), it.eviction_threshold);
+      ResourceList alloc = it.capacity;  // resources.Subtract only over keys of capacity
+      for (auto& kv : alloc) { auto o = overhead.find(kv.first); if (o != overhead.end()) kv.second -= o->second; }
+      row.res_present = B.fill_resources(alloc, row.allocatable);
+      B.fill_resources(it.capacity, &E.type_capacity[(size_t)c * KSCHED_MAX_RES]);
+      for (auto& o : it.offerings) {
+        if (!o.available) continue;
+        int z = 0, ct = 0;
+        if (zone_key >= 0) { auto f = B.value_id[zone_key].find(o.zone); if (f == B.value_id[zone_key].end()) continue; z = f->second; }
+        if (ct_key >= 0) { auto f = B.value_id[ct_key].find(o.capacity_type); if (f == B.value_id[ct_key].end()) continue; ct = f->second; }
+        if (z >= 16 || ct >= 4) unsupported("more than 16 zones or 4 capacity types");
+        row.offerings |= 1ull << (ct * 16 + z);
+      }
+      row.min_price = min_price[E.type_input_index[c]];
+      row.input_index = (uint32_t)E.type_input_index[c];
+    }
+  }
+  // offerings whose zone / capacity-type is not a dictionary value can never satisfy a *present* requirement,
+  // but they do satisfy an absent one: keep them visible through a catch-all bit when the key is inactive.
+  // (When zone/ct keys are inactive every offering maps to z=0/ct=0 above, which is exactly "key not constrained".)
+
+  // ------------------------------------------------------------------ templates
+  const int NV = (int)E.template_provisioner.size();
+  E.templates.resize(NV);
+  E.template_bounds.resize(NV);
+  std::vector<ksched_bounds> tb(NV);
+  for (int v = 0; v < NV; ++v) {
+    const Provisioner& pr = P.provisioners[E.template_provisioner[v]];
+    ksched_template& t = E.templates[v];
+    std::memset(&t, 0, sizeof t);
+    std::memset(&tb[v], 0, sizeof(ksched_bounds));
+    Builder::Special sp;
+    B.add_selector_reqs(t.reqs, tb[v], pr.requirements, &sp);  // NewMachineTemplate machinetemplate.go:46-62
+    Labels l = pr.labels;
+    l[kProvisionerName] = pr.name;
+    B.add_selector_reqs(t.reqs, tb[v], Builder::label_reqs(l), &sp);
+    if (!sp.hostname.empty()) unsupported("provisioner with a hostname requirement");
+    // instance-type requirement of the provisioner: fold into membership (types are singletons on that key)
+    std::vector<bool> allowed(NT, true);
+    for (auto& r : sp.itype) {
+      std::set<std::string> names(r.values.begin(), r.values.end());
+      for (int c = 0; c < NT; ++c) {
+        const std::string& name = P.instance_types[E.type_input_index[c]].name;
+        bool ok = true;
+        if (r.op == Op::In) ok = names.count(name) > 0;
+        else if (r.op == Op::NotIn) ok = !names.count(name);
+        else if (r.op == Op::DoesNotExist) ok = false;
+        else if (r.op == Op::Gt || r.op == Op::Lt) unsupported("Gt/Lt on instance-type");
+        allowed[c] = allowed[c] && ok;
+      }
+    }
+    for (int idx : pr.instance_types) {
+      int c = B.type_col.at(P.instance_types.at(idx).name);
+      if (allowed[c]) E.types[c].template_members |= 1ull << v;
+    }
+    t.taintset = (uint32_t)B.taintset(pr.taints);
+    t.has_limits = pr.has_limits ? 1 : 0;
+    t.limit_present = B.fill_resources(pr.limits, t.remaining);
+    if (t.reqs.meta >> KSCHED_META_HASGT_SHIFT) E.any_template_bounds = true;
+  }
+  E.template_bounds = tb;
+
+  // ------------------------------------------------------------------ daemonset overhead (scheduler.go:250-267)
+  auto daemon_reqs = [&](const Pod& d, ksched_reqset& rs, ksched_bounds& bd) {
+    Builder::Special sp;
+    B.pod_requirements(d, rs, bd, &sp);
+    return sp;
+  };
+  for (int v = 0; v < NV; ++v) {
+    const Provisioner& pr = P.provisioners[E.template_provisioner[v]];
+    ResourceList total;
+    int count = 0;
+    for (auto& d : daemons) {
+      if (!tolerates_all(pr.taints, d.tolerations)) continue;
+      ksched_reqset rs{}; ksched_bounds bd{};
+      auto sp = daemon_reqs(d, rs, bd);
+      if (!sp.hostname.empty() || !sp.itype.empty()) unsupported("daemonset pod with hostname / instance-type requirement");
+      if (!B.compatible(E.templates[v].reqs, tb[v], rs, bd)) continue;
+      total = merge(total, pod_requests(d));
+      ++count;
+    }
+    total["pods"] = (int64_t)count * 1000;
+    E.templates[v].daemon_res_present = B.fill_resources(total, E.templates[v].daemon_requests);
+  }
+
+  // ------------------------------------------------------------------ existing nodes (scheduler.go:221-248, existingnode.go:41-75)
+  std::map<std::string, int> hostname_slot;  // hostname -> existing slot
+  for (int si : state_nodes) {
+    const StateNode& n = P.nodes[si];
+    auto own = n.labels.find(kProvisionerName);
+    if (own == n.labels.end() || own->second.empty()) continue;  // !node.Owned()
+    ksched_existing_node e;
+    std::memset(&e, 0, sizeof e);
+    ksched_bounds nb{};
+    Builder::Special sp;
+    B.add_selector_reqs(e.reqs, nb, Builder::label_reqs(n.labels), &sp);
+    ResourceList daemon_total;
+    int dcount = 0;
+    for (auto& d : daemons) {
+      if (!tolerates_all(n.taints, d.tolerations)) continue;  // raw Spec.Taints (scheduler.go:231)
+      ksched_reqset rs{}; ksched_bounds bd{};
+      daemon_reqs(d, rs, bd);
+      if (!B.compatible(e.reqs, nb, rs, bd)) continue;
+      daemon_total = merge(daemon_total, pod_requests(d));
+      ++dcount;
+    }
+    daemon_total["pods"] = (int64_t)dcount * 1000;
+    ResourceList pod_req, ds_req;
+    for (auto& p : n.pods) {
+      pod_req = merge(pod_req, pod_requests(p));
+      if (p.is_daemonset) ds_req = merge(ds_req, pod_requests(p));
+    }
+    ResourceList rem = daemon_total;  // resources.Subtract over keys of lhs, clamped at 0
+    for (auto& kv : rem) { auto f = ds_req.find(kv.first); if (f != ds_req.end()) kv.second -= f->second; if (kv.second < 0) kv.second = 0; }
+    ResourceList avail = n.allocatable;
+    for (auto& kv : avail) { auto f = pod_req.find(kv.first); if (f != pod_req.end()) kv.second -= f->second; }
+    e.available_present = B.fill_resources(avail, e.available);
+    e.requests_present = B.fill_resources(rem, e.requests);
+    e.taintset = (uint32_t)B.taintset(state_node_taints(n));
+    e.itype = KSCHED_NONE;
+    auto itl = n.labels.find(kInstanceType);
+    if (itl != n.labels.end()) { auto c = B.type_col.find(itl->second); if (c != B.type_col.end()) e.itype = (uint32_t)c->second; }
+    for (auto& p : n.pods)
+      for (auto& hp : host_ports(p)) e.hostport_entries |= 1ull << B.hp_entry(hp);
+    std::string hostname;
+    auto h = n.labels.find(kHostname);
+    if (h != n.labels.end()) hostname = h->second;
+    if (hostname.empty()) hostname = n.name;
+    hostname_slot[hostname] = (int)E.existing.size();
+    E.existing_state_index.push_back(si);
+    auto ini = n.labels.find(kInitialized);
+    E.existing_initialized.push_back(ini != n.labels.end() && ini->second == "true");
+    E.existing.push_back(e);
+    for (int v = 0; v < NV; ++v)  // scheduler.go:244-246
+      if (P.provisioners[E.template_provisioner[v]].name == own->second && E.templates[v].has_limits) {
+        int64_t cap[KSCHED_MAX_RES];
+        uint32_t present = B.fill_resources(n.capacity, cap);
+        for (int r = 0; r < KSCHED_MAX_RES; ++r)
+          if ((E.templates[v].limit_present >> r) & 1 && (present >> r) & 1) E.templates[v].remaining[r] -= cap[r];
+      }
+  }
+  const int NE = (int)E.existing.size();
+
+  // ------------------------------------------------------------------ topology groups (topology.go)
+  std::vector<Group> groups;
+  std::map<std::string, size_t> group_of;          // hash -> index, non-inverse
+  std::map<std::string, size_t> inverse_group_of;  // hash -> index, inverse
+  // domain universe: provisioner.go:266-276 (requirement.Values() of every type + provisioner In requirements)
+  std::map<std::string, std::set<std::string>> universe;
+  for (int v = 0; v < NV; ++v) {
+    const Provisioner& pr = P.provisioners[E.template_provisioner[v]];
+    for (int idx : pr.instance_types)
+      for (auto& r : P.instance_types[idx].requirements)
+        if (r.op == Op::In || r.op == Op::NotIn) universe[normalize_key(r.key)].insert(r.values.begin(), r.values.end());
+    // NewNodeSelectorRequirements(provisioner.Spec.Requirements...) then Operator()==In
+    std::map<std::string, std::vector<NodeSelectorRequirement>> by_key;
+    for (auto& r : pr.requirements) by_key[normalize_key(r.key)].push_back(r);
+    for (auto& kv : by_key) {
+      int k = B.key_of(kv.first);
+      if (k < 0) {  // inactive key: only needed when a single In requirement exists
+        if (kv.second.size() == 1 && kv.second[0].op == Op::In) universe[kv.first].insert(kv.second[0].values.begin(), kv.second[0].values.end());
+        continue;
+      }
+      ksched_reqset rs{}; ksched_bounds bd{};
+      B.add_selector_reqs(rs, bd, kv.second, nullptr);
+      Req r = ksched::req_load(rs, &bd, k);
+      if (!r.complement && r.values)
+        for (int b = 0; b < 64; ++b) if ((r.values >> b) & 1) universe[kv.first].insert(E.key_values[k][b]);
+    }
+  }
+  auto namespace_list = [](const std::string& ns, const std::vector<std::string>& nss) {
+    if (nss.empty()) return std::set<std::string>{ns};
+    return std::set<std::string>(nss.begin(), nss.end());
+  };
+  auto make_filter = [&](Group& g, const Pod& p) {  // MakeTopologyNodeFilter topologynodefilter.go:30-47
+    g.filter_nil = false;
+    auto canon = [&](const ksched_reqset& rs, const ksched_bounds& bd) {
+      std::string s;
+      for (int k = 0; k < NK; ++k) {
+        Req r = ksched::req_load(rs, &bd, k);
+        if (!r.present) continue;
+        s += std::to_string(k) + ":" + std::to_string(r.complement) + ":" + std::to_string(r.values) + ":" +
+             (r.has_gt ? std::to_string(r.gt) : "") + ":" + (r.has_lt ? std::to_string(r.lt) : "") + ";";
+      }
+      return s;
+    };
+    std::vector<std::string> parts;
+    auto add_term = [&](const std::vector<NodeSelectorRequirement>* term) {
+      ksched_reqset rs{}; ksched_bounds bd{};
+      Builder::Special sp;
+      B.add_selector_reqs(rs, bd, Builder::label_reqs(p.node_selector), &sp);
+      if (term) B.add_selector_reqs(rs, bd, *term, &sp);
+      if (!sp.hostname.empty() || !sp.itype.empty()) unsupported("topology spread node filter on hostname / instance-type");
+      g.filter.push_back({rs, bd});
+      parts.push_back(canon(rs, bd));
+    };
+    if (!p.has_node_affinity || !p.has_required_node_affinity) add_term(nullptr);
+    else for (auto& t : p.required_node_terms) add_term(&t);
+    std::sort(parts.begin(), parts.end());
+    for (auto& s : parts) g.filter_key += "(" + s + ")";
+  };
+  auto filter_matches_labels = [&](const Group& g, const Labels& labels) {  // TopologyNodeFilter.Matches
+    if (g.filter_nil || g.filter.empty()) return true;
+    ksched_reqset rs{}; ksched_bounds bd{};
+    Builder::Special sp;
+    B.add_selector_reqs(rs, bd, Builder::label_reqs(labels), &sp);
+    for (auto& f : g.filter)
+      if (B.compatible(rs, bd, f.first, f.second)) return true;
+    return false;
+  };
+  std::set<std::string> excluded;
+  for (auto* p : E.pods) excluded.insert(p->uid);
+  auto new_group = [&](int type, const std::string& key, const Pod& p, std::set<std::string> nss, const LabelSelector& sel, int32_t skew) {
+    Group g;
+    g.type = type; g.key = key; g.max_skew = skew; g.namespaces = std::move(nss); g.selector = sel;
+    if (type == 0) make_filter(g, p);
+    else g.filter_key = "<nil>";
+    auto u = universe.find(key);
+    if (u != universe.end()) for (auto& d : u->second) g.counts[d] = 0;
+    return g;
+  };
+  auto count_domains = [&](Group& g) {  // topology.go:231-276
+    for (auto& n : P.nodes)
+      for (auto& p : n.pods) {
+        if (!g.namespaces.count(p.ns)) continue;
+        if (!g.selector.is_nil && !selector_matches(g.selector, p.labels)) continue;  // TopologyListOptions: nil lists everything
+        if (p.terminal || p.terminating) continue;
+        if (excluded.count(p.uid)) continue;
+        std::string domain;
+        auto it = n.labels.find(g.key);
+        bool ok = it != n.labels.end();
+        if (ok) domain = it->second;
+        if (!ok && g.key == kHostname) { domain = n.name; ok = true; }
+        if (!ok) continue;
+        if (!filter_matches_labels(g, n.labels)) continue;
+        g.counts[domain]++;
+      }
+  };
+  auto spec_groups = [&](const Pod& p) {  // newForTopologies + newForAffinities topology.go:278-322
+    std::vector<Group> out;
+    for (auto& cs : p.topology_spread) out.push_back(new_group(0, cs.topology_key, p, {p.ns}, cs.selector, cs.max_skew));
+    for (auto& t : p.pod_affinity_required) out.push_back(new_group(1, t.topology_key, p, namespace_list(p.ns, t.namespaces), t.selector, INT32_MAX));
+    for (auto& t : p.pod_affinity_preferred) out.push_back(new_group(1, t.term.topology_key, p, namespace_list(p.ns, t.term.namespaces), t.term.selector, INT32_MAX));
+    for (auto& t : p.pod_anti_affinity_required) out.push_back(new_group(2, t.topology_key, p, namespace_list(p.ns, t.namespaces), t.selector, INT32_MAX));
+    for (auto& t : p.pod_anti_affinity_preferred) out.push_back(new_group(2, t.term.topology_key, p, namespace_list(p.ns, t.term.namespaces), t.term.selector, INT32_MAX));
+    return out;
+  };
+  auto inverse_groups = [&](const Pod& p, const Labels* node_labels, int owner_spec) {  // updateInverseAntiAffinity topology.go:202-227
+    for (auto& term : p.pod_anti_affinity_required) {
+      Group g = new_group(2, term.topology_key, p, namespace_list(p.ns, term.namespaces), term.selector, INT32_MAX);
+      g.inverse = true;
+      std::string h = g.hash();
+      auto it = inverse_group_of.find(h);
+      size_t gi;
+      if (it == inverse_group_of.end()) { gi = groups.size(); inverse_group_of[h] = gi; groups.push_back(std::move(g)); }
+      else gi = it->second;
+      if (node_labels) {
+        auto d = node_labels->find(groups[gi].key);
+        if (d != node_labels->end()) groups[gi].counts[d->second]++;
+      }
+      if (owner_spec >= 0) groups[gi].owner_specs.insert((size_t)owner_spec);
+    }
+  };
+  if (!P.empty_topology) {
+    for (auto& n : P.nodes)  // updateInverseAffinities topology.go:185-198
+      for (auto& p : n.pods) {
+        if (p.pod_anti_affinity_required.empty() || excluded.count(p.uid)) continue;
+        inverse_groups(p, &n.labels, -1);
+      }
+    // Topology.Update for every pod of the batch, in Solve's pod order (topology.go:73-75); group creation order
+    // only matters for countDomains, which is order-independent.
+    std::vector<bool> seen(specs.size(), false);
+    for (size_t i = 0; i < NP; ++i) {
+      uint32_t s = E.pod_class[i];
+      if (seen[s]) continue;
+      seen[s] = true;
+      const Pod& p = specs[s].pod;
+      if (!p.pod_anti_affinity_required.empty() || !p.pod_anti_affinity_preferred.empty()) inverse_groups(p, nullptr, (int)s);
+      for (auto& g : spec_groups(p)) {
+        std::string h = g.hash();
+        auto it = group_of.find(h);
+        size_t gi;
+        if (it == group_of.end()) { gi = groups.size(); group_of[h] = gi; count_domains(g); groups.push_back(std::move(g)); }
+        else gi = it->second;
+        groups[gi].owner_specs.insert(s);
+      }
+    }
+    // relaxed variants: Topology.Update after Relax (scheduler.go:119-123). Their groups must already exist.
+    for (size_t s = 0; s < specs.size(); ++s) {
+      if (seen[s]) continue;
+      const Pod& p = specs[s].pod;
+      if (!p.pod_anti_affinity_required.empty() || !p.pod_anti_affinity_preferred.empty()) {
+        for (auto& term : p.pod_anti_affinity_required) {
+          Group g = new_group(2, term.topology_key, p, namespace_list(p.ns, term.namespaces), term.selector, INT32_MAX);
+          g.inverse = true;
+          auto it = inverse_group_of.find(g.hash());
+          if (it == inverse_group_of.end()) unsupported("relaxation creates a new inverse topology group");
+          groups[it->second].owner_specs.insert(s);
+        }
+      }
+      for (auto& g : spec_groups(p)) {
+        auto it = group_of.find(g.hash());
+        if (it == group_of.end()) unsupported("relaxation creates a new topology group (node filter changes)");
+        groups[it->second].owner_specs.insert(s);
+      }
+    }
+  }
+  const int NG = (int)groups.size();
+  E.groups.resize(NG);
+  E.group_domain_counts.assign((size_t)NG * 64, 0);
+  E.group_existing_counts.assign((size_t)NG * std::max(NE, 1), 0);
+  for (int g = 0; g < NG; ++g) {
+    Group& G = groups[g];
+    ksched_topo_group& o = E.groups[g];
+    std::memset(&o, 0, sizeof o);
+    o.type = (uint8_t)G.type;
+    o.inverse = G.inverse;
+    o.max_skew = G.max_skew;
+    o.filter_begin = (uint32_t)E.filter_terms.size();
+    for (auto& f : G.filter) {
+      if (f.first.meta >> KSCHED_META_HASGT_SHIFT) unsupported("Gt/Lt inside a topology node filter");
+      E.filter_terms.push_back(f.first);
+    }
+    o.filter_end = (uint32_t)E.filter_terms.size();
+    if (G.key == kHostname) {
+      o.key = KSCHED_KEY_HOSTNAME;
+      for (auto& kv : G.counts) {
+        auto s = hostname_slot.find(kv.first);
+        if (s != hostname_slot.end()) E.group_existing_counts[(size_t)g * std::max(NE, 1) + s->second] = kv.second;
+        else if (kv.second > 0) o.extra_nonzero_domains++;
+      }
+    } else {
+      int k = B.key_of(G.key);
+      if (k < 0) throw std::runtime_error("internal: topology key not active: " + G.key);
+      o.key = (uint8_t)k;
+      for (auto& kv : G.counts) {
+        auto v = B.value_id[k].find(kv.first);
+        if (v == B.value_id[k].end()) {
+          if (kv.second > 0) unsupported("topology domain outside the dictionary: " + kv.first);
+          // zero-count universe domain that no requirement mentions (e.g. a type-only value): it is still a
+          // domain of the group; the dictionary holds every type / template / node value, so this is unreachable.
+          throw std::runtime_error("internal: universe domain missing from dictionary: " + kv.first);
+        }
+        o.registered |= 1ull << v->second;
+        E.group_domain_counts[(size_t)g * 64 + v->second] = kv.second;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ class rows
+  const int NC = (int)specs.size();
+  E.classes.resize(NC);
+  E.class_bounds.resize(NC);
+  std::map<std::string, uint32_t> itype_req_id;
+  for (int c = 0; c < NC; ++c) {
+    const Pod& p = specs[c].pod;
+    ksched_pod_row& row = E.classes[c];
+    std::memset(&row, 0, sizeof row);
+    std::memset(&E.class_bounds[c], 0, sizeof(ksched_bounds));
+    row.res_present = B.fill_resources(specs[c].req, row.requests);
+    ksched_reqset rs{};
+    Builder::Special sp;
+    B.pod_requirements(p, rs, E.class_bounds[c], &sp);
+    std::memcpy(row.values, rs.values, sizeof row.values);
+    row.meta = rs.meta;
+    if (rs.meta >> KSCHED_META_HASGT_SHIFT) E.any_class_bounds = true;
+    row.relax_next = specs[c].next;
+    row.itype_req = KSCHED_NONE;
+    row.hostname_req = KSCHED_NONE;
+    if (!sp.itype.empty()) {
+      // intersection of all instance-type requirements of the pod as (complement, name set)
+      bool comp = true;
+      std::set<std::string> names;
+      bool first = true;
+      for (auto& r : sp.itype) {
+        if (r.op == Op::Gt || r.op == Op::Lt) unsupported("Gt/Lt on instance-type");
+        bool rc = !(r.op == Op::In || r.op == Op::DoesNotExist);
+        std::set<std::string> rv;
+        if (r.op == Op::In || r.op == Op::NotIn) rv.insert(r.values.begin(), r.values.end());
+        if (first) { comp = rc; names = rv; first = false; continue; }
+        std::set<std::string> nv;
+        if (comp && rc) { nv = names; nv.insert(rv.begin(), rv.end()); }
+        else if (comp && !rc) { for (auto& x : rv) if (!names.count(x)) nv.insert(x); }
+        else if (!comp && rc) { for (auto& x : names) if (!rv.count(x)) nv.insert(x); }
+        else { for (auto& x : names) if (rv.count(x)) nv.insert(x); }
+        comp = comp && rc;
+        names = nv;
+      }
+      std::string key = std::to_string(comp) + ":";
+      for (auto& n : names) key += n + ",";
+      auto it = itype_req_id.find(key);
+      if (it == itype_req_id.end()) {
+        uint32_t id = (uint32_t)E.itype_req_complement.size();
+        itype_req_id[key] = id;
+        E.itype_req_complement.push_back(comp ? 1 : 0);
+        size_t base = E.itype_req_sets.size();
+        E.itype_req_sets.resize(base + E.type_words, 0);
+        for (int col = 0; col < NT; ++col) {
+          bool in = names.count(P.instance_types[E.type_input_index[col]].name) > 0;
+          if (comp ? !in : in) E.itype_req_sets[base + col / 64] |= 1ull << (col % 64);
+        }
+        row.itype_req = id;
+      } else {
+        row.itype_req = it->second;
+      }
+    }
+    if (!sp.hostname.empty()) {
+      if (sp.hostname.size() != 1) unsupported("more than one hostname requirement on a pod");
+      auto& r = sp.hostname[0];
+      int32_t comp, slot = -1;
+      if (r.op == Op::In && r.values.size() == 1) comp = 0;
+      else if (r.op == Op::NotIn && r.values.size() == 1) comp = 1;
+      else if (r.op == Op::Exists) comp = 1;
+      else unsupported("hostname requirement form");
+      if (!r.values.empty()) { auto s = hostname_slot.find(r.values[0]); if (s != hostname_slot.end()) slot = s->second; }
+      row.hostname_req = (uint32_t)(E.hostname_reqs.size() / 2);
+      E.hostname_reqs.push_back(comp);
+      E.hostname_reqs.push_back(slot);
+    }
+    auto hps = host_ports(p);
+    for (auto& hp : hps) row.hostport_entries |= 1ull << B.hp_entry(hp);
+    // topology relations
+    row.topo_begin = (uint32_t)E.class_topo.size();
+    for (int g = 0; g < NG; ++g) {
+      const Group& G = groups[g];
+      bool owns = G.owner_specs.count((size_t)c) > 0;
+      bool sel = G.selects(p);
+      uint32_t flags = 0;
+      if (sel) flags |= KSCHED_TOPO_SELECTS;
+      if (!G.inverse && owns) flags |= KSCHED_TOPO_CONSTRAINS;
+      if (G.inverse && sel) flags |= KSCHED_TOPO_CONSTRAINS;  // Counts(): nil node filter always matches
+      if (!G.inverse && sel) flags |= KSCHED_TOPO_RECORDS;
+      if (G.inverse && owns) flags |= KSCHED_TOPO_RECORDS_INVERSE;
+      if (flags & ~KSCHED_TOPO_SELECTS) E.class_topo.push_back({(uint32_t)g, flags});
+    }
+    row.topo_end = (uint32_t)E.class_topo.size();
+  }
+  // host-port conflict masks and tolerated taint sets need the complete entry / taint-set tables
+  for (int c = 0; c < NC; ++c) {
+    const Pod& p = specs[c].pod;
+    for (auto& hp : host_ports(p))
+      for (size_t e = 0; e < B.hp_entries.size(); ++e)
+        if (hp_matches(hp, B.hp_entries[e])) E.classes[c].hostport_conflicts |= 1ull << e;
+    for (size_t s = 0; s < B.taintsets.size(); ++s)
+      if (tolerates_all(B.taintsets[s], p.tolerations)) E.classes[c].tolerated_taintsets |= 1ull << s;
+  }
+
+  // ------------------------------------------------------------------ per-pod queue keys (queue.go:74-110)
+  E.pod_timestamp.resize(NP);
+  E.pod_uid_rank.resize(NP);
+  {
+    std::vector<uint32_t> order(NP);
+    for (size_t i = 0; i < NP; ++i) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return E.pods[a]->uid < E.pods[b]->uid; });
+    for (size_t r = 0; r < NP; ++r) E.pod_uid_rank[order[r]] = (uint32_t)r;
+    for (size_t i = 0; i < NP; ++i) E.pod_timestamp[i] = E.pods[i]->creation_ts;
+  }
+
+  // ------------------------------------------------------------------ wire up the flat structs
+  ksched_catalog& cat = E.catalog;
+  cat.n_keys = NK; cat.n_res = (int)E.res_names.size(); cat.n_types = NT; cat.n_templates = NV;
+  cat.keys = E.keys.data();
+  cat.key_int_values = E.key_int_values.data();
+  cat.types = E.types.data();
+  cat.type_bounds = nullptr;
+  cat.type_capacity = E.type_capacity.data();
+  cat.templates = E.templates.data();
+  cat.template_bounds = E.any_template_bounds ? E.template_bounds.data() : nullptr;
+  ksched_problem& pr = E.problem;
+  pr.n_pods = (int)NP; pr.n_classes = NC; pr.n_existing = NE; pr.n_groups = NG;
+  pr.classes = E.classes.data();
+  pr.class_bounds = E.any_class_bounds ? E.class_bounds.data() : nullptr;
+  pr.pod_class = E.pod_class.data();
+  pr.pod_timestamp = E.pod_timestamp.data();
+  pr.pod_uid_rank = E.pod_uid_rank.data();
+  pr.existing = E.existing.data();
+  pr.existing_bounds = nullptr;
+  pr.groups = E.groups.data();
+  pr.group_domain_counts = E.group_domain_counts.data();
+  pr.group_existing_counts = E.group_existing_counts.data();
+  pr.class_topo = E.class_topo.data();
+  pr.n_class_topo = (int)E.class_topo.size();
+  pr.filter_terms = E.filter_terms.data();
+  pr.n_filter_terms = (int)E.filter_terms.size();
+  pr.itype_req_sets = E.itype_req_sets.data();
+  pr.itype_req_complement = E.itype_req_complement.data();
+  pr.n_itype_reqs = (int)E.itype_req_complement.size();
+  pr.hostname_reqs = E.hostname_reqs.data();
+  pr.n_hostname_reqs = (int)E.hostname_reqs.size() / 2;
+  pr.max_new_nodes = (int)NP;
+  pr.write_feasibility = 0;
+  if (E.any_class_bounds || E.any_template_bounds)
+    unsupported("Gt/Lt requirements on pods / provisioners are not carried on the device path yet");
+  return enc;
+}
+
+std::string render_requirement(const Encoded& E, const ksched_reqset& rs, int k) {
+  static const ksched_bounds zero{};
+  Req r = ksched::req_load(rs, &zero, k);
+  const char* op;
+  if (r.complement) op = r.values ? "NotIn" : "Exists";
+  else op = r.values ? "In" : "DoesNotExist";
+  std::string s = std::string(op) + " [";
+  bool first = true;
+  for (size_t b = 0; b < E.key_values[k].size(); ++b)
+    if ((r.values >> b) & 1) { if (!first) s += " "; s += E.key_values[k][b]; first = false; }
+  return s + "]";
+}
+
+}  // namespace khost

@@ -1,0 +1,61 @@
+// Host-side marshalling of a string-level kmodel::Problem into the flat C-ABI structures of
+// include/ksched.h — what a cgo shim would do from the Go objects handed to
+// scheduling.NewScheduler (provisioner.go:237-296, scheduler.go:42-78).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ksched.h"
+#include "model.h"
+
+namespace khost {
+
+struct Encoded {
+  // ---- dictionary
+  std::vector<std::string> key_names;                 // mask keys
+  std::vector<std::vector<std::string>> key_values;   // per key, ascending string order (canonical domain order)
+  std::vector<std::string> res_names;                 // resource ids: cpu, memory, pods, then ascending
+  // ---- which objects take part (provisioner.go:119-144 / deprovisioning/helpers.go:42-93)
+  std::vector<const kmodel::Pod*> pods;               // Solve's pod list
+  std::vector<int> existing_state_index;              // existing slot -> Problem.nodes index
+  std::vector<bool> existing_initialized;
+  std::vector<int> template_provisioner;              // template v -> Problem.provisioners index
+  std::vector<int> type_input_index;                  // column -> Problem.instance_types index
+  int type_words = 0;
+
+  // ---- backing storage of the flat structures
+  std::vector<ksched_keyinfo> keys;
+  std::vector<int64_t> key_int_values;
+  std::vector<ksched_type_row> types;
+  std::vector<int64_t> type_capacity;
+  std::vector<ksched_template> templates;
+  std::vector<ksched_bounds> template_bounds;
+  std::vector<ksched_pod_row> classes;
+  std::vector<ksched_bounds> class_bounds;
+  bool any_class_bounds = false, any_template_bounds = false;
+  std::vector<uint32_t> pod_class;
+  std::vector<int64_t> pod_timestamp;
+  std::vector<uint32_t> pod_uid_rank;
+  std::vector<ksched_existing_node> existing;
+  std::vector<ksched_topo_group> groups;
+  std::vector<int32_t> group_domain_counts;
+  std::vector<int32_t> group_existing_counts;
+  std::vector<ksched_class_topo> class_topo;
+  std::vector<ksched_reqset> filter_terms;
+  std::vector<uint64_t> itype_req_sets;
+  std::vector<uint8_t> itype_req_complement;
+  std::vector<int32_t> hostname_reqs;
+
+  ksched_catalog catalog{};
+  ksched_problem problem{};
+};
+
+// Throws std::runtime_error; messages starting with "unsupported:" map to KSCHED_ERR_UNSUPPORTED.
+std::unique_ptr<Encoded> encode(const kmodel::Problem& P, const std::vector<int>& candidates);
+
+// Render one requirement of a reqset the way the oracle's Requirement::Canonical() does ("In [a b]").
+std::string render_requirement(const Encoded& E, const ksched_reqset& rs, int key);
+
+}  // namespace khost

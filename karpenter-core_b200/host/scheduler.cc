@@ -1,0 +1,439 @@
+// Host-side mirror of the reference's entry points for the hot path, on top of the C-ABI:
+//   Scheduler.Solve                      pkg/controllers/provisioning/scheduling/scheduler.go:96
+//   simulateScheduling                   pkg/controllers/deprovisioning/helpers.go:42-115
+//   computeConsolidation / firstNNode... consolidation.go:190-274, multinodeconsolidation.go:74-165
+// Everything that decides a placement runs on the GPU through ksched_* (include/ksched.h). There is NO CPU
+// fallback: without a CUDA device every call here fails with KSCHED_ERR_NO_DEVICE.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <stdexcept>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "encoder.h"
+#include "ksched.h"
+#include "model.h"
+#include "reqmask.cuh"
+
+using namespace kmodel;
+using khost::Encoded;
+
+namespace {
+
+thread_local std::string g_err;
+ksched_handle* g_handle = nullptr;
+int g_device = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int ensure_handle() {
+  if (g_handle) return KSCHED_OK;
+  int rc = ksched_create(g_device, &g_handle);
+  if (rc != KSCHED_OK) return fail(rc, "ksched_create failed: no usable CUDA device (the product has no CPU path)");
+  return KSCHED_OK;
+}
+
+struct ResultBuffers {
+  std::vector<int32_t> assign, relax, seq;
+  std::vector<ksched_new_node> nodes;
+  std::vector<uint64_t> types;
+  std::vector<ksched_reqset> existing_reqs;
+  std::vector<uint64_t> feasibility;
+  std::vector<uint64_t> best;
+  ksched_result r{};
+  void prepare(const Encoded& E, bool want_feasibility) {
+    const size_t P = E.pods.size(), N = (size_t)std::max(1, E.problem.max_new_nodes);
+    assign.assign(P, -1);
+    relax.assign(P, 0);
+    seq.assign(P, -1);
+    nodes.resize(N);
+    types.assign(N * E.type_words, 0);
+    existing_reqs.resize(std::max<size_t>(1, E.existing.size()));
+    std::memset(&r, 0, sizeof r);
+    r.assign = assign.data();
+    r.relax_level = relax.data();
+    r.place_seq = seq.data();
+    r.new_nodes = nodes.data();
+    r.new_node_types = types.data();
+    r.existing_reqs = existing_reqs.data();
+    if (want_feasibility) {
+      feasibility.assign(P * E.templates.size() * E.type_words, 0);
+      best.assign(P, 0);
+      r.feasibility = feasibility.data();
+      r.best_column = best.data();
+    }
+  }
+};
+
+// ksched_result -> the reference's ([]*Node, []*ExistingNode) shape (node.go:34-40, existingnode.go:28-39)
+void decode(const Encoded& E, const ResultBuffers& B, Result& out) {
+  const size_t P = E.pods.size(), NE = E.existing.size();
+  out.assign.assign(B.assign.begin(), B.assign.end());
+  out.relax_level.assign(B.relax.begin(), B.relax.end());
+  out.nodes_visited = B.r.nodes_visited;
+  out.add_calls = B.r.add_calls;
+  out.existing_node_index = E.existing_state_index;
+  out.existing_pods.assign(NE, {});
+  out.new_nodes.assign((size_t)B.r.n_new_nodes, {});
+  // pods in Add order
+  std::vector<int32_t> order(P);
+  for (size_t i = 0; i < P; ++i) order[i] = (int32_t)i;
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return B.seq[a] < B.seq[b]; });
+  for (int32_t p : order) {
+    int32_t a = B.assign[p];
+    if (a < 0) continue;
+    if ((size_t)a < NE) out.existing_pods[a].push_back(p);
+    else out.new_nodes[(size_t)a - NE].pods.push_back(p);
+  }
+  for (int n = 0; n < B.r.n_new_nodes; ++n) {
+    const ksched_new_node& src = B.nodes[n];
+    NewNodeResult& dst = out.new_nodes[n];
+    dst.provisioner = src.template_index;
+    const uint64_t* bits = &B.types[(size_t)n * E.type_words];
+    for (size_t c = 0; c < E.type_input_index.size(); ++c)
+      if ((bits[c / 64] >> (c % 64)) & 1) dst.instance_type_options.push_back(E.type_input_index[c]);
+    std::sort(dst.instance_type_options.begin(), dst.instance_type_options.end());  // lo.Filter keeps input order
+    for (size_t r = 0; r < E.res_names.size(); ++r)
+      if ((src.requests_present >> r) & 1) dst.requests[E.res_names[r]] = src.requests[r];
+    for (size_t k = 0; k < E.key_names.size(); ++k)
+      if ((src.reqs.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1) dst.requirements[E.key_names[k]] = khost::render_requirement(E, src.reqs, (int)k);
+  }
+}
+
+int error_code(const std::exception& e) {
+  std::string m = e.what();
+  return m.rfind("unsupported:", 0) == 0 ? KSCHED_ERR_UNSUPPORTED : KSCHED_ERR_INVALID;
+}
+
+int solve_encoded(Encoded& E, ResultBuffers& B, bool want_feasibility) {
+  int rc = ensure_handle();
+  if (rc != KSCHED_OK) return rc;
+  rc = ksched_load_catalog(g_handle, &E.catalog);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  B.prepare(E, want_feasibility);
+  rc = ksched_solve(g_handle, &E.problem, &B.r);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  return KSCHED_OK;
+}
+
+// ---- consolidation price helpers (deprovisioning/helpers.go:148-157,292-315) on the decoded new node
+bool req_has(const Encoded& E, const ksched_reqset& rs, const std::string& key, const std::string& value) {
+  for (size_t k = 0; k < E.key_names.size(); ++k) {
+    if (E.key_names[k] != key) continue;
+    static const ksched_bounds zero{};
+    ksched::Req r = ksched::req_load(rs, &zero, (int)k);
+    if (!r.present) return true;  // Requirements.Get of an undefined key is Exists
+    for (size_t b = 0; b < E.key_values[k].size(); ++b)
+      if (E.key_values[k][b] == value) return r.complement ? !((r.values >> b) & 1) : ((r.values >> b) & 1);
+    return r.complement;  // value outside the dictionary: only a complement set admits it
+  }
+  return true;
+}
+double worst_launch_price(const Encoded& E, const InstanceType& it, const ksched_reqset& rs) {
+  auto worst = [&](const char* ct, double* out) {
+    bool any = false;
+    double mx = 0;
+    for (auto& o : it.offerings) {
+      if (!o.available || o.capacity_type != ct) continue;
+      if (!req_has(E, rs, "topology.kubernetes.io/zone", o.zone)) continue;
+      if (!any || o.price > mx) mx = o.price;
+      any = true;
+    }
+    *out = mx;
+    return any;
+  };
+  double p;
+  if (req_has(E, rs, "karpenter.sh/capacity-type", "spot") && worst("spot", &p)) return p;
+  if (req_has(E, rs, "karpenter.sh/capacity-type", "on-demand") && worst("on-demand", &p)) return p;
+  return std::numeric_limits<double>::max();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* kh_scheduler_error() { return g_err.c_str(); }
+int kh_set_device(int ordinal) {
+  if (g_handle) { ksched_destroy(g_handle); g_handle = nullptr; }
+  g_device = ordinal;
+  return KSCHED_OK;
+}
+ksched_handle* kh_handle() { return ensure_handle() == KSCHED_OK ? g_handle : nullptr; }
+
+// Scheduler.Solve through the C-ABI with host buffers (upload + kernels + download inside the call).
+int kh_scheduler_solve(const Problem* P, const int* candidates, int ncand, Result* out) {
+  *out = Result();
+  try {
+    std::vector<int> c(candidates, candidates + ncand);
+    auto E = khost::encode(*P, c);
+    ResultBuffers B;
+    int rc = solve_encoded(*E, B, false);
+    if (rc != KSCHED_OK) { out->error = g_err; return rc; }
+    decode(*E, B, *out);
+    return KSCHED_OK;
+  } catch (const std::exception& e) {
+    out->error = e.what();
+    return fail(error_code(e), e.what());
+  }
+}
+
+// ---- split API for benchmarking / kernel tests: encode once, keep the problem resident, time kernels only
+Encoded* kh_encode(const Problem* P, const int* candidates, int ncand) {
+  try {
+    std::vector<int> c(candidates, candidates + ncand);
+    return khost::encode(*P, c).release();
+  } catch (const std::exception& e) {
+    fail(error_code(e), e.what());
+    return nullptr;
+  }
+}
+void kh_encoded_free(Encoded* E) { delete E; }
+// dims: [pods, classes, existing, groups, types, templates, keys, resources, type_words, class_topo]
+void kh_encoded_dims(const Encoded* E, long long* out) {
+  out[0] = (long long)E->pods.size(); out[1] = (long long)E->classes.size(); out[2] = (long long)E->existing.size();
+  out[3] = (long long)E->groups.size(); out[4] = (long long)E->types.size(); out[5] = (long long)E->templates.size();
+  out[6] = (long long)E->key_names.size(); out[7] = (long long)E->res_names.size(); out[8] = E->type_words;
+  out[9] = (long long)E->class_topo.size();
+}
+const ksched_catalog* kh_encoded_catalog(const Encoded* E) { return &E->catalog; }
+const ksched_problem* kh_encoded_problem(const Encoded* E) { return &E->problem; }
+int kh_gpu_load(Encoded* E) {
+  int rc = ensure_handle();
+  if (rc != KSCHED_OK) return rc;
+  rc = ksched_load_catalog(g_handle, &E->catalog);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  rc = ksched_upload(g_handle, &E->problem);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  return KSCHED_OK;
+}
+int kh_gpu_run(int flush_l2) {
+  if (!g_handle) return fail(KSCHED_ERR_INVALID, "no handle");
+  int rc = ksched_run_resident(g_handle, flush_l2);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  return rc;
+}
+int kh_gpu_run_feasibility(int flush_l2, float* us) {
+  if (!g_handle) return fail(KSCHED_ERR_INVALID, "no handle");
+  int rc = ksched_run_feasibility_only(g_handle, flush_l2, us);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  return rc;
+}
+// download + decode; feasibility_out (optional) receives [pods][templates][type_words] uint64 in caller pod order,
+// columns in the caller's instance-type order (bit i of template v = instance_types[i])
+int kh_gpu_download(Encoded* E, Result* out, unsigned long long* feasibility_out, unsigned long long* best_out) {
+  if (!g_handle) return fail(KSCHED_ERR_INVALID, "no handle");
+  *out = Result();
+  ResultBuffers B;
+  B.prepare(*E, feasibility_out != nullptr || best_out != nullptr);
+  int rc = ksched_download(g_handle, &E->problem, &B.r);
+  if (rc != KSCHED_OK) { out->error = ksched_last_error(g_handle); return fail(rc, out->error); }
+  decode(*E, B, *out);
+  if (feasibility_out) {
+    const size_t P = E->pods.size(), V = E->templates.size(), W = (size_t)E->type_words, T = E->types.size();
+    std::memset(feasibility_out, 0, P * V * W * 8);
+    for (size_t p = 0; p < P; ++p)
+      for (size_t v = 0; v < V; ++v) {
+        const uint64_t* src = &B.feasibility[(p * V + v) * W];
+        unsigned long long* dst = feasibility_out + (p * V + v) * W;
+        for (size_t c = 0; c < T; ++c)
+          if ((src[c / 64] >> (c % 64)) & 1) { size_t i = (size_t)E->type_input_index[c]; dst[i / 64] |= 1ull << (i % 64); }
+      }
+  }
+  if (best_out) std::memcpy(best_out, B.best.data(), E->pods.size() * 8);
+  return KSCHED_OK;
+}
+// One Scheduler.Solve through the C-ABI with HOST buffers: pod/node/topology upload, kernels and result download are
+// all inside the call (the catalog stays resident, as it would across reconciles). Returns wall-clock microseconds.
+int kh_gpu_solve_e2e(Encoded* E, Result* out, double* wall_us) {
+  if (!g_handle) return fail(KSCHED_ERR_INVALID, "no handle");
+  ResultBuffers B;
+  B.prepare(*E, false);
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = ksched_solve(g_handle, &E->problem, &B.r);
+  auto t1 = std::chrono::steady_clock::now();
+  if (wall_us) *wall_us = std::chrono::duration<double, std::micro>(t1 - t0).count();
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  if (out) { *out = Result(); decode(*E, B, *out); }
+  return KSCHED_OK;
+}
+int kh_gpu_load_catalog(Encoded* E) {
+  int rc = ensure_handle();
+  if (rc != KSCHED_OK) return rc;
+  rc = ksched_load_catalog(g_handle, &E->catalog);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  return KSCHED_OK;
+}
+int kh_gpu_timings(ksched_timings* t) { return g_handle ? ksched_get_timings(g_handle, t) : KSCHED_ERR_INVALID; }
+
+// MultiNodeConsolidation.firstNNodeConsolidationOption on the GPU path: one ksched_solve per probe.
+// out ints: [action, nodes_removed, simulations, n_options]; options = instance type indices.
+int kh_consolidate(const Problem* P, int* out4, int* options, int options_cap, int* probes, int* probe_actions, int probes_cap, int* n_probes) {
+  try {
+    struct Cand { int node; const InstanceType* it; std::string ct, zone; double cost; };
+    std::vector<Cand> cands;
+    for (size_t i = 0; i < P->nodes.size(); ++i) {
+      const StateNode& n = P->nodes[i];
+      if (!n.candidate) continue;
+      Cand c{(int)i, nullptr, "", "", n.disruption_cost};
+      auto itn = n.labels.find("node.kubernetes.io/instance-type");
+      if (itn != n.labels.end())
+        for (auto& t : P->instance_types) if (t.name == itn->second) c.it = &t;
+      auto ct = n.labels.find("karpenter.sh/capacity-type");
+      if (ct != n.labels.end()) c.ct = ct->second;
+      auto z = n.labels.find("topology.kubernetes.io/zone");
+      if (z != n.labels.end()) c.zone = z->second;
+      cands.push_back(c);
+    }
+    std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.cost < b.cost; });  // consolidation.go:100-103
+    int sims = 0;
+    struct Cmd { int action = 0; std::vector<int> options; };
+    auto compute = [&](int count) -> Cmd {  // computeConsolidation + filterOutSameType
+      Cmd cmd;
+      std::vector<int> nodes;
+      for (int i = 0; i < count; ++i) nodes.push_back(cands[i].node);
+      auto E = khost::encode(*P, nodes);
+      ResultBuffers B;
+      int rc = solve_encoded(*E, B, false);
+      if (rc != KSCHED_OK) throw std::runtime_error(g_err);
+      ++sims;
+      size_t scheduled = 0;
+      for (auto a : B.assign) if (a >= 0) ++scheduled;
+      for (size_t p = 0; p < B.assign.size(); ++p)  // helpers.go:109-113: an uninitialised existing node was used
+        if (B.assign[p] >= 0 && (size_t)B.assign[p] < E->existing.size() && !E->existing_initialized[B.assign[p]]) return cmd;
+      if (scheduled != E->pods.size()) return cmd;
+      if (B.r.n_new_nodes == 0) { cmd.action = 1; return cmd; }
+      if (B.r.n_new_nodes != 1) return cmd;
+      double price = 0;  // getNodePrices consolidation.go:277-287
+      for (int i = 0; i < count; ++i) {
+        const Cand& c = cands[i];
+        if (!c.it) throw std::runtime_error("candidate without a known instance type");
+        bool ok = false;
+        for (auto& o : c.it->offerings) if (o.capacity_type == c.ct && o.zone == c.zone) { price += o.price; ok = true; break; }
+        if (!ok) throw std::runtime_error("unable to determine offering");
+      }
+      ksched_reqset reqs = B.nodes[0].reqs;
+      std::vector<int> opts;
+      const uint64_t* bits = &B.types[0];
+      for (size_t c = 0; c < E->type_input_index.size(); ++c)
+        if ((bits[c / 64] >> (c % 64)) & 1) opts.push_back(E->type_input_index[c]);
+      std::sort(opts.begin(), opts.end());
+      std::vector<int> kept;
+      for (int t : opts) if (worst_launch_price(*E, P->instance_types[t], reqs) < price) kept.push_back(t);  // filterByPrice
+      if (kept.empty()) return cmd;
+      bool all_spot = true;
+      for (int i = 0; i < count; ++i) if (cands[i].ct != "spot") all_spot = false;
+      if (all_spot && req_has(*E, reqs, "karpenter.sh/capacity-type", "spot")) return cmd;
+      if (req_has(*E, reqs, "karpenter.sh/capacity-type", "spot") && req_has(*E, reqs, "karpenter.sh/capacity-type", "on-demand")) {
+        // Requirements.Add(capacity-type In [spot]) (consolidation.go:262-265)
+        for (size_t k = 0; k < E->key_names.size(); ++k) {
+          if (E->key_names[k] != "karpenter.sh/capacity-type") continue;
+          uint64_t spot = 0;
+          for (size_t b = 0; b < E->key_values[k].size(); ++b) if (E->key_values[k][b] == "spot") spot = 1ull << b;
+          ksched::Req in{spot, 0, 0, true, false, false, false};
+          static const ksched_bounds zero{};
+          ksched::KeyMeta km{0, nullptr};
+          ksched_bounds tmp{};
+          ksched::req_store(reqs, &tmp, (int)k, ksched::key_add(ksched::req_load(reqs, &zero, (int)k), in, km));
+        }
+      }
+      std::set<std::string> existing_types;  // filterOutSameType multinodeconsolidation.go:132-165
+      std::map<std::string, double> by_type;
+      for (int i = 0; i < count; ++i) {
+        const Cand& c = cands[i];
+        existing_types.insert(c.it->name);
+        for (auto& o : c.it->offerings)
+          if (o.capacity_type == c.ct && o.zone == c.zone) {
+            double ex = by_type.count(c.it->name) ? by_type[c.it->name] : std::numeric_limits<double>::max();
+            if (o.price < ex) by_type[c.it->name] = o.price;
+            break;
+          }
+      }
+      double max_price = std::numeric_limits<double>::max();
+      for (int t : kept) {
+        const std::string& name = P->instance_types[t].name;
+        if (existing_types.count(name) && by_type[name] < max_price) max_price = by_type[name];
+      }
+      std::vector<int> kept2;
+      for (int t : kept) if (worst_launch_price(*E, P->instance_types[t], reqs) < max_price) kept2.push_back(t);
+      if (kept2.empty()) return cmd;
+      cmd.action = 2;
+      cmd.options = kept2;
+      return cmd;
+    };
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    *n_probes = 0;
+    if (cands.size() < 2) return KSCHED_OK;
+    int mn = 1, mx = (int)cands.size() - 1, last_count = 0;
+    Cmd last;
+    while (mn <= mx) {
+      int mid = (mn + mx) / 2;
+      Cmd c = compute(mid + 1);
+      if (*n_probes < probes_cap) { probes[*n_probes] = mid + 1; probe_actions[*n_probes] = c.action; }
+      ++*n_probes;
+      if (c.action == 1 || c.action == 2) { last = c; last_count = mid + 1; mn = mid + 1; }
+      else mx = mid - 1;
+    }
+    out4[0] = last.action;
+    out4[1] = last_count;
+    out4[2] = sims;
+    out4[3] = (int)last.options.size();
+    for (size_t i = 0; i < last.options.size() && (int)i < options_cap; ++i) options[i] = last.options[i];
+    return KSCHED_OK;
+  } catch (const std::exception& e) {
+    return fail(error_code(e), e.what());
+  }
+}
+
+// ---- host-side mask algebra exposed for the CPU golden-vector tests (same code the kernels run)
+// spec: op ("In","NotIn","Exists","DoesNotExist","Gt","Lt") + comma separated values; dictionary = A,B,1,2,9
+static ksched::Req spec_req(const char* op_c, const char* vals_c, const std::vector<std::string>& dict) {
+  std::string op = op_c, vals = vals_c;
+  std::vector<std::string> v;
+  size_t pos = 0;
+  while (pos <= vals.size() && !vals.empty()) {
+    size_t c = vals.find(',', pos);
+    if (c == std::string::npos) c = vals.size();
+    v.push_back(vals.substr(pos, c - pos));
+    pos = c + 1;
+  }
+  ksched::Req r{0, 0, 0, true, true, false, false};
+  r.complement = !(op == "In" || op == "DoesNotExist");
+  if (op == "In" || op == "NotIn")
+    for (auto& x : v)
+      for (size_t b = 0; b < dict.size(); ++b) if (dict[b] == x) r.values |= 1ull << b;
+  if (op == "Gt") { r.has_gt = true; r.gt = std::stoll(v.at(0)); }
+  if (op == "Lt") { r.has_lt = true; r.lt = std::stoll(v.at(0)); }
+  return r;
+}
+struct TestDict {
+  std::vector<std::string> dict{"1", "2", "9", "A", "B"};
+  int64_t ints[64] = {1, 2, 9};
+  ksched::KeyMeta km{0x7, ints};
+};
+// out: [present, complement, values, has_gt, gt, has_lt, lt, len_zero, op_negative]
+void kh_mask_intersection(const char* aop, const char* avals, const char* bop, const char* bvals, long long* out) {
+  TestDict d;
+  ksched::Req a = spec_req(aop, avals, d.dict), b = spec_req(bop, bvals, d.dict);
+  ksched::Req r = ksched::req_intersect(a, b, d.km);
+  out[0] = r.present; out[1] = r.complement; out[2] = (long long)r.values; out[3] = r.has_gt; out[4] = r.gt; out[5] = r.has_lt; out[6] = r.lt;
+  out[7] = ksched::req_len_zero(r); out[8] = ksched::req_op_negative(r);
+}
+long long kh_mask_allowed(const char* aop, const char* avals) {
+  TestDict d;
+  return (long long)ksched::req_allowed(spec_req(aop, avals, d.dict), 0x1F, d.km);
+}
+int kh_mask_compatible(const char* aop, const char* avals, int a_present, const char* bop, const char* bvals, int b_present, int well_known) {
+  TestDict d;
+  ksched::Req a = spec_req(aop, avals, d.dict), b = spec_req(bop, bvals, d.dict);
+  a.present = a_present;
+  b.present = b_present;
+  return ksched::key_compatible(a, b, well_known != 0, d.km) ? 1 : 0;
+}
+}
