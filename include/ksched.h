@@ -83,7 +83,7 @@ typedef struct ksched_pod_row {
   uint32_t itype_req;           /* index into problem.itype_req_sets (instance-type key), or KSCHED_NONE */
   uint32_t hostname_req;        /* index into problem.hostname_reqs, or KSCHED_NONE */
   uint32_t topo_begin, topo_end; /* range in problem.class_topo (groups that constrain / record this class) */
-  uint64_t reserved;
+  uint64_t reserved;            /* must hold the row's own index in problem.classes */
 } ksched_pod_row; /* 256 bytes */
 
 /* 256-byte instance-type column. Replaces cloudprovider.InstanceType (cloudprovider/types.go:72-85). */
@@ -188,6 +188,7 @@ typedef struct ksched_problem {
   int32_t n_hostname_reqs;
   int32_t max_new_nodes;              /* capacity for new nodes (<= n_pods) */
   int32_t write_feasibility;          /* also copy the dense feasibility bitmask back (result.feasibility) */
+  int32_t count_nodes_visited;        /* keep the exact nodes_visited statistic (one extra pass over the in-flight nodes per pod) */
 } ksched_problem;
 
 typedef struct ksched_new_node {

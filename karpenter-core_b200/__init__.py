@@ -97,6 +97,7 @@ def lib():
     L.kh_encoded_free.argtypes = [C.c_void_p]
     L.kh_encoded_dims.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     L.kh_gpu_load.argtypes = [C.c_void_p]
+    L.kh_encoded_set_count_visited.argtypes = [C.c_void_p, C.c_int]
     L.kh_gpu_run.argtypes = [C.c_int]
     L.kh_gpu_run_feasibility.argtypes = [C.c_int, C.POINTER(C.c_float)]
     L.kh_gpu_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -276,6 +277,10 @@ class ResidentSolve:
         d = (C.c_longlong * 10)()
         lib().kh_encoded_dims(self.enc, d)
         self.dims = dict(zip(["pods", "classes", "existing", "groups", "types", "templates", "keys", "resources", "type_words", "class_topo"], list(d)))
+
+    def set_count_visited(self, on):
+        """exact nodes_visited statistic on/off (off for timed runs: it costs a pass over all in-flight nodes per pod)"""
+        lib().kh_encoded_set_count_visited(self.enc, int(on))
 
     def load(self):
         _check(lib().kh_gpu_load(self.enc))

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
@@ -44,7 +45,7 @@ namespace {
 
 constexpr int kMaxCG = 8;        // topology groups that may constrain one pod class
 constexpr int kMaxTouched = 8;   // requirement keys one Add may touch (pod keys + topology keys)
-constexpr int kPackThreads = 1024;
+constexpr int kPackThreads = 512;
 constexpr uint64_t kNoBest = ~0ull;
 
 // ------------------------------------------------------------------------------------------------
@@ -69,6 +70,8 @@ struct DevCatalog {
   const uint32_t* member;            // [n_templates][W32]
   const int64_t* alloc_sorted;       // [n_res][n_types] ascending
   const uint32_t* fitset;            // [n_res][n_types+1][W32]  rank -> types with alloc >= alloc_sorted[rank]
+  const int32_t* perm_desc;          // [n_res][n_types] types by descending allocatable
+  const int64_t* alloc_rt;           // [n_res][n_types] allocatable, resource-major
   int zone_key, ct_key;
 };
 
@@ -77,9 +80,9 @@ __device__ __forceinline__ KeyMeta key_meta(const DevCatalog& c, int k) {
 }
 
 // number of types with alloc_r < q  (lower bound)
-__device__ __forceinline__ int fit_rank(const DevCatalog& c, int r, int64_t q) {
-  const int64_t* a = c.alloc_sorted + (size_t)r * c.n_types;
-  int lo = 0, hi = c.n_types;
+__device__ __forceinline__ int fit_rank(const int64_t* alloc_sorted, int n_types, int r, int64_t q) {
+  const int64_t* a = alloc_sorted + (size_t)r * n_types;
+  int lo = 0, hi = n_types;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
     if (a[mid] < q) lo = mid + 1; else hi = mid;
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
       if (lane < c.n_res) {
         uint32_t pres = pod_res_present | tm.daemon_res_present;
         res_used = (pres >> lane) & 1;
-        if (res_used) rank = fit_rank(c, lane, (int64_t)word + tm.daemon_requests[lane]);
+        if (res_used) rank = fit_rank(c.alloc_sorted, c.n_types, lane, (int64_t)word + tm.daemon_requests[lane]);
       }
       const uint32_t res_mask = __ballot_sync(0xffffffffu, res_used);
       uint64_t zallowed = 0xFFFF, callowed = 0xF;
@@ -287,6 +290,7 @@ struct PackState {
   const uint8_t* itype_complement;
   const int32_t* hostname_reqs;      // [n][2]
   const uint32_t* order;             // FFD order: queue position -> pod
+  const uint64_t* rows;              // [n_pods][32] dense pod-row matrix in FFD order (K0)
   uint32_t* pod_pos;                 // pod -> FFD position (row of F / best)
   int use_F;                         // F / best cover every column on this device (not column-sharded)
   const uint32_t* F;                 // [n_pods][V][W32] in FFD order (nullptr: compute fresh-node types dynamically)
@@ -318,13 +322,23 @@ struct PackState {
   int32_t* nn_tb;
   int64_t* nn_req;                   // [8][max_new]
   uint32_t* nn_req_present;
-  int64_t* nn_maxalloc;              // [8][max_new] upper bound of allocatable over surviving options
-  int32_t* nn_argmax;                // [8][max_new] a type attaining it
   uint64_t* nn_vals;                 // [16][max_new]
   uint64_t* nn_meta;
   uint32_t* nn_opts;                 // [W32][max_new]
   uint64_t* nn_hp;
-  int32_t* active;                   // open new nodes
+  // hot state of open nodes beyond the shared-memory window (pack_kernel.cuh: Hot)
+  unsigned long long* ov_key;
+  long long* ov_q;
+  long long* ov_bound;
+  int* ov_node;
+  unsigned short* ov_flags;
+  // fresh-node option cache per (class, template)
+  uint8_t* fc_state;                 // 0 unknown, 1 cached, 2 cached: no surviving type
+  uint32_t* fc_opts;                 // [n_classes*V][W32]
+  long long* fc_bound;               // [n_classes*V][4]
+  uint8_t* fc_dom;
+  int count_visited;                 // keep the exact nodes_visited statistic (costs a pass over all in-flight nodes per pod)
+  int alloc_in_smem;
   // topology counters
   int32_t* grp_cnt;                  // [n_groups][64]
   uint64_t* grp_registered;          // [n_groups]
@@ -523,10 +537,11 @@ struct TypeCtx {
   uint32_t zmask, cmask;
   uint32_t itype_req;
 };
-__device__ void build_type_ctx(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const Touched& t, const int64_t* q,
-                               uint32_t q_present, const uint64_t* vals, uint64_t meta, int stride, int idx, bool fresh, TypeCtx& x) {
+__device__ void build_type_ctx(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const Touched& t, const long long* q,
+                               uint32_t q_present, const uint64_t* vals, uint64_t meta, int stride, int idx, bool fresh,
+                               const int64_t* alloc_sorted, TypeCtx& x) {
   x.res_mask = q_present;
-  for (int r = 0; r < c.n_res; ++r) x.rank[r] = ((q_present >> r) & 1) ? fit_rank(c, r, q[r]) : 0;
+  for (int r = 0; r < c.n_res; ++r) x.rank[r] = ((q_present >> r) & 1) ? fit_rank(alloc_sorted, c.n_types, r, q[r]) : 0;
   x.nkeys = 0;
   x.offer_needed = fresh;
   auto add_key = [&](int k, const Req& f) {
@@ -704,442 +719,11 @@ __device__ void topo_record(const DevCatalog& c, const PackState& s, const ksche
   }
 }
 
-__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long* smem) {
-  for (int o = 16; o; o >>= 1) {
-    unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o);
-    v = x < v ? x : v;
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) smem[warp] = v;
-  __syncthreads();
-  unsigned long long r = smem[lane < (blockDim.x >> 5) ? lane : 0];
-  if (lane >= (blockDim.x >> 5)) r = ~0ull;
-  for (int o = 16; o; o >>= 1) {
-    unsigned long long x = __shfl_xor_sync(0xffffffffu, r, o);
-    r = x < r ? x : r;
-  }
-  return r;
-}
+}  // namespace
 
-__global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(K2Params p) {
-  const DevCatalog& c = p.cat;
-  const PackState& s = p.st;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int W32 = c.W32, V = c.n_templates, NE = s.n_existing, MAXN = s.max_new;
+#include "pack_kernel.cuh"
 
-  __shared__ ksched_pod_row row;
-  __shared__ PodTopo pt;
-  __shared__ Touched win_t;
-  __shared__ TypeCtx win_x;
-  __shared__ unsigned long long red[32];
-  __shared__ int sh_flag, sh_useF;
-  __shared__ uint32_t sh_any;
-  __shared__ int64_t sh_q[KSCHED_MAX_RES];
-  __shared__ uint32_t sh_qp;
-
-  int head = 0, qlen = s.n_pods;  // queue[head .. head+qlen) circular, capacity n_pods+1
-  const int qcap = s.n_pods + 1;
-  int n_new = 0, n_active = 0, tick = 0, seq = 0;
-  uint32_t epoch = 1;
-  int node_id = 0;  // hostname placeholders handed out (one per NewNode attempt, node.go:46)
-  long long nodes_visited = 0, add_calls = 0, steps = 0;
-  int fatal = 0;
-
-  for (int i = tid; i < s.n_pods; i += blockDim.x) {
-    s.queue[i] = s.order[i];
-    s.pod_pos[s.order[i]] = (uint32_t)i;
-    s.assign[i] = -1;
-    s.place_seq[i] = -1;
-    s.last_epoch[i] = 0;
-  }
-  __syncthreads();
-
-  while (qlen > 0) {
-    const uint32_t pod = s.queue[head];
-    // Pop(): stop when the pod comes round again with an unchanged queue length (queue.go:52)
-    if (s.last_epoch[pod] == epoch && s.last_len[pod] == qlen) break;
-    head = (head + 1) % qcap;
-    --qlen;
-    ++add_calls;
-    ++steps;
-    const uint32_t cls = s.pod_class[pod];
-    __syncthreads();
-    if (warp == 0) reinterpret_cast<uint64_t*>(&row)[lane] = reinterpret_cast<const uint64_t*>(&s.classes[cls])[lane];
-    __syncthreads();
-    if (tid == 0) build_pod_topo(c, s, row, pt);
-    __syncthreads();
-    if (pt.overflow) { fatal = KSCHED_ERR_UNSUPPORTED; break; }
-
-    bool placed = false;
-    // ---------------------------------------------------------------- 1) existing nodes, caller order (scheduler.go:176-180)
-    if (NE > 0) {
-      unsigned long long mine = ~0ull;
-      for (int e = tid; e < NE; e += blockDim.x) {
-        if (s.ex_closed[e]) continue;
-        if (!((row.tolerated_taintsets >> s.ex_taintset[e]) & 1)) continue;
-        if (s.ex_hp[e] & row.hostport_conflicts) continue;
-        bool ok = true;  // Fits(requests, available) first (existingnode.go:98-102)
-        const uint32_t qp = s.ex_req_present[e] | row.res_present;
-        for (int r = 0; r < c.n_res && ok; ++r) {
-          if (!((qp >> r) & 1)) continue;
-          int64_t q = s.ex_req[(size_t)r * NE + e] + row.requests[r];
-          int64_t a = ((s.ex_avail_present[e] >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
-          ok = q <= a;
-        }
-        if (!ok) continue;
-        if (row.itype_req != KSCHED_NONE) {
-          const uint32_t it = s.ex_itype[e];
-          bool allowed = it == KSCHED_NONE ? (s.itype_complement[row.itype_req] != 0)
-                                           : ((s.itype_sets[(size_t)row.itype_req * W32 + (it >> 5)] >> (it & 31)) & 1);
-          if (!allowed) continue;
-        }
-        Touched t;
-        if (!requirements_phase(c, s, row, pt, s.ex_vals, s.ex_meta[e], NE, e, e, true, t)) continue;
-        mine = (unsigned long long)e;
-        break;  // this thread's later nodes have larger indices
-      }
-      unsigned long long w = block_min_u64(mine, red);
-      if (w != ~0ull) {
-        const int e = (int)w;
-        nodes_visited += e + 1;
-        if (tid == 0) {
-          Touched t;
-          requirements_phase(c, s, row, pt, s.ex_vals, s.ex_meta[e], NE, e, e, true, t);
-          uint64_t meta = s.ex_meta[e];
-          for (int i = 0; i < t.n; ++i) {
-            const int k = t.key[i];
-            const Req& f = t.fin[i];
-            uint64_t bit = 1ull << k;
-            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
-            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
-            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
-            s.ex_vals[(size_t)k * NE + e] = f.values;
-          }
-          s.ex_meta[e] = meta;
-          bool closed = false;
-          for (int r = 0; r < c.n_res; ++r) {
-            if ((row.res_present >> r) & 1) s.ex_req[(size_t)r * NE + e] += row.requests[r];
-            int64_t a = ((s.ex_avail_present[e] >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
-            if (s.min_req[r] > 0 && s.ex_req[(size_t)r * NE + e] + s.min_req[r] > a) closed = true;
-          }
-          s.ex_req_present[e] |= row.res_present;
-          s.ex_hp[e] |= row.hostport_entries;
-          s.ex_closed[e] = closed;
-          topo_record(c, s, row, s.ex_vals, meta, NE, e, e);
-          s.assign[pod] = e;
-          s.place_seq[pod] = seq;
-        }
-        ++seq;
-        placed = true;
-      } else {
-        nodes_visited += NE;
-      }
-    }
-    // ---------------------------------------------------------------- 2) in-flight nodes, fewest pods first (scheduler.go:183-190)
-    if (!placed && n_active > 0) {
-      unsigned long long mine = ~0ull;
-      for (int a = tid; a < n_active; a += blockDim.x) {
-        const int n = s.active[a];
-        const int v = s.nn_tmpl[n];
-        if (!((row.tolerated_taintsets >> c.templates[v].taintset) & 1)) continue;
-        if (s.nn_hp[n] & row.hostport_conflicts) continue;
-        int64_t q[KSCHED_MAX_RES];
-        const uint32_t qp = s.nn_req_present[n] | row.res_present;
-        bool ok = true;
-        for (int r = 0; r < c.n_res && ok; ++r) {
-          q[r] = s.nn_req[(size_t)r * MAXN + n] + (((row.res_present >> r) & 1) ? row.requests[r] : 0);
-          if ((qp >> r) & 1) ok = q[r] <= s.nn_maxalloc[(size_t)r * MAXN + n];
-        }
-        if (!ok) continue;
-        Touched t;
-        if (!requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, t)) continue;
-        TypeCtx x;
-        build_type_ctx(c, s, row, t, q, qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, x);
-        bool any = false;
-        for (int w = 0; w < W32 && !any; ++w) {
-          uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
-          if (base) any = type_word(c, s, x, base, w) != 0;
-        }
-        if (!any) continue;
-        // order key: (pod count, tie-break) — the stable-sorted position of the node in s.newNodes
-        unsigned long long key = ((unsigned long long)(uint32_t)s.nn_count[n] << 32) | (uint32_t)(s.nn_tb[n] ^ 0x80000000);
-        if (key < mine) mine = key;
-      }
-      unsigned long long wkey = block_min_u64(mine, red);
-      if (wkey != ~0ull) {
-        // find the winner: (count, tb) is unique per node
-        __syncthreads();
-        if (tid == 0) sh_flag = -1;
-        __syncthreads();
-        for (int a = tid; a < n_active; a += blockDim.x) {
-          const int n = s.active[a];
-          unsigned long long key = ((unsigned long long)(uint32_t)s.nn_count[n] << 32) | (uint32_t)(s.nn_tb[n] ^ 0x80000000);
-          if (key == wkey) sh_flag = a;
-        }
-        __syncthreads();
-        const int a_win = sh_flag;
-        const int n = s.active[a_win];
-        // nodes_visited: rank of the winner in scan order = number of in-flight nodes with a smaller key + 1
-        // (closed nodes are also scanned by the reference; count all created nodes with smaller key)
-        {
-          int cntless = 0;
-          for (int i = tid; i < n_new; i += blockDim.x) {
-            unsigned long long key = ((unsigned long long)(uint32_t)s.nn_count[i] << 32) | (uint32_t)(s.nn_tb[i] ^ 0x80000000);
-            if (key < wkey) ++cntless;
-          }
-          for (int o = 16; o; o >>= 1) cntless += __shfl_xor_sync(0xffffffffu, cntless, o);
-          __syncthreads();
-          if (lane == 0) red[warp] = cntless;
-          __syncthreads();
-          long long tot = 0;
-          for (int i = 0; i < (blockDim.x >> 5); ++i) tot += (long long)red[i];
-          nodes_visited += tot + 1;
-        }
-        // commit by warp 0
-        if (tid == 0) {
-          requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, win_t);
-          uint32_t qp = s.nn_req_present[n] | row.res_present;
-          for (int r = 0; r < c.n_res; ++r) sh_q[r] = s.nn_req[(size_t)r * MAXN + n] + (((row.res_present >> r) & 1) ? row.requests[r] : 0);
-          sh_qp = qp;
-          build_type_ctx(c, s, row, win_t, sh_q, qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, win_x);
-        }
-        __syncthreads();
-        if (warp == 0) {
-          for (int w = lane; w < W32; w += 32) {
-            uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
-            uint32_t sw = base ? type_word(c, s, win_x, base, w) : 0;
-            s.nn_opts[(size_t)w * MAXN + n] = sw;
-          }
-        }
-        __syncthreads();
-        if (tid == 0) {
-          uint64_t meta = s.nn_meta[n];
-          for (int i = 0; i < win_t.n; ++i) {
-            const int k = win_t.key[i];
-            const Req& f = win_t.fin[i];
-            uint64_t bit = 1ull << k;
-            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
-            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
-            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
-            s.nn_vals[(size_t)k * MAXN + n] = f.values;
-          }
-          s.nn_meta[n] = meta;
-          for (int r = 0; r < c.n_res; ++r) s.nn_req[(size_t)r * MAXN + n] = sh_q[r];
-          s.nn_req_present[n] = sh_qp;
-          s.nn_hp[n] |= row.hostport_entries;
-          s.nn_count[n] += 1;
-          s.nn_tb[n] = -(tick + 1);  // moves to the front of the next pod-count block under a stable sort
-          topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
-          s.assign[pod] = NE + n;
-          s.place_seq[pod] = seq;
-        }
-        ++tick;
-        ++seq;
-        placed = true;
-        __syncthreads();
-        // refresh maxalloc bounds where the arg-max type dropped out, and close the node when nothing can fit
-        if (warp == 0) {
-          bool closed = false;
-          for (int r = 0; r < c.n_res; ++r) {
-            int am = s.nn_argmax[(size_t)r * MAXN + n];
-            bool still = (s.nn_opts[(size_t)(am >> 5) * MAXN + n] >> (am & 31)) & 1;
-            if (!still) {
-              long long best = INT64_MIN;
-              int bt = 0;
-              for (int w = lane; w < W32; w += 32) {
-                uint32_t m = s.nn_opts[(size_t)w * MAXN + n];
-                while (m) {
-                  int b = __ffs(m) - 1;
-                  m &= m - 1;
-                  int t = w * 32 + b;
-                  long long al = c.types[t].allocatable[r];
-                  if (al > best) { best = al; bt = t; }
-                }
-              }
-              for (int o = 16; o; o >>= 1) {
-                long long ob = __shfl_xor_sync(0xffffffffu, best, o);
-                int ot = __shfl_xor_sync(0xffffffffu, bt, o);
-                if (ob > best || (ob == best && ot < bt)) { best = ob; bt = ot; }
-              }
-              if (lane == 0) { s.nn_maxalloc[(size_t)r * MAXN + n] = best; s.nn_argmax[(size_t)r * MAXN + n] = bt; }
-            }
-            __syncwarp();
-            int64_t mx = s.nn_maxalloc[(size_t)r * MAXN + n];
-            if (s.min_req[r] > 0 && s.nn_req[(size_t)r * MAXN + n] + s.min_req[r] > mx) closed = true;
-          }
-          if (closed && lane == 0) s.active[a_win] = s.active[n_active - 1];
-          if (lane == 0) sh_flag = closed ? 1 : 0;
-        }
-        __syncthreads();
-        if (sh_flag) --n_active;
-      } else {
-        nodes_visited += n_new;
-      }
-    } else if (!placed) {
-      nodes_visited += n_new;  // every in-flight node is full: the reference still walks them
-    }
-    // ---------------------------------------------------------------- 3) open a new node, templates in weight order (scheduler.go:194-217)
-    if (!placed) {
-      // K1's row of this pod is valid while the pod still has its original class (relaxation changes the row)
-      const bool f_valid = s.use_F && s.relax_level[pod] == 0;
-      const uint32_t fpos = s.pod_pos[pod];
-      const bool no_column = f_valid && s.best[fpos] == kNoBest;  // no feasible (template, type) column at all
-      if (no_column) { nodes_visited += V; node_id += V; }
-      for (int v = 0; v < V && !placed && !no_column; ++v) {
-        const ksched_template& tm = c.templates[v];
-        __syncthreads();
-        // filterByRemainingResources (scheduler.go:293-309) folded into the base set below
-        ++nodes_visited;
-        ++node_id;
-        if (n_new >= MAXN) { fatal = KSCHED_ERR_OVERFLOW; break; }
-        const int n = n_new;  // tentative slot: the hostname placeholder of this attempt
-        if (tid == 0) {
-          sh_flag = 0;
-          sh_any = 0;
-          bool ok = (row.tolerated_taintsets >> tm.taintset) & 1;
-          // template requirements become the node requirements (NewNode node.go:44-60)
-          for (int k = 0; k < c.n_keys; ++k) s.nn_vals[(size_t)k * MAXN + n] = tm.reqs.values[k];
-          s.nn_meta[n] = tm.reqs.meta & 0xFFFFFFFFull;
-          if (ok) ok = requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, win_t);
-          if (ok) {
-            uint32_t qp = tm.daemon_res_present | row.res_present;
-            for (int r = 0; r < c.n_res; ++r) sh_q[r] = tm.daemon_requests[r] + (((row.res_present >> r) & 1) ? row.requests[r] : 0);
-            sh_qp = qp;
-            build_type_ctx(c, s, row, win_t, sh_q, qp, s.nn_vals, s.nn_meta[n], MAXN, n, true, win_x);
-            // topology left every requirement as K1 saw it -> the precomputed row is the exact answer
-            bool same = f_valid;
-            for (int i = 0; i < win_t.n && same; ++i) same = req_equal(win_t.fin[i], win_t.merged[i]);
-            sh_useF = same ? 1 : 0;
-          }
-          sh_flag = ok ? 1 : 0;
-        }
-        __syncthreads();
-        if (!sh_flag) continue;
-        // surviving types: template members ∧ limits ∧ full predicate
-        bool local_any = false;
-        for (int w = tid; w < W32; w += blockDim.x) {
-          uint32_t base = c.member[(size_t)v * W32 + w];
-          if (base && tm.has_limits && tm.limit_present) {
-            uint32_t m = base;
-            while (m) {
-              int b = __ffs(m) - 1;
-              m &= m - 1;
-              int t = w * 32 + b;
-              bool viable = true;
-              for (int r = 0; r < c.n_res; ++r)
-                if (((tm.limit_present >> r) & 1) && c.capacity[(size_t)t * KSCHED_MAX_RES + r] > s.remaining[(size_t)v * KSCHED_MAX_RES + r]) viable = false;
-              if (!viable) base &= ~(1u << b);
-            }
-          }
-          uint32_t sw = 0;
-          if (base) sw = sh_useF ? (base & s.F[((size_t)fpos * V + v) * W32 + w]) : type_word(c, s, win_x, base, w);
-          s.nn_opts[(size_t)w * MAXN + n] = sw;
-          if (sw) local_any = true;
-        }
-        if (local_any) atomicOr(&sh_any, 1u);
-        __syncthreads();
-        // "all available instance types exceed provisioner limits" -> continue without NewNode in the reference;
-        // here the attempt is made and fails identically (no types), only the placeholder counter differs.
-        if (!sh_any) continue;
-        // commit the new node
-        if (tid == 0) {
-          uint64_t meta = s.nn_meta[n];
-          for (int i = 0; i < win_t.n; ++i) {
-            const int k = win_t.key[i];
-            const Req& f = win_t.fin[i];
-            uint64_t bit = 1ull << k;
-            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
-            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
-            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
-            s.nn_vals[(size_t)k * MAXN + n] = f.values;
-          }
-          s.nn_meta[n] = meta;
-          s.nn_tmpl[n] = (uint8_t)v;
-          for (int r = 0; r < KSCHED_MAX_RES; ++r) s.nn_req[(size_t)r * MAXN + n] = r < c.n_res ? sh_q[r] : 0;
-          s.nn_req_present[n] = sh_qp;
-          s.nn_hp[n] = row.hostport_entries;
-          s.nn_count[n] = 1;
-          s.nn_tb[n] = tick + 1;  // appended: last of the one-pod block
-          topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
-          s.assign[pod] = NE + n;
-          s.place_seq[pod] = seq;
-          s.active[n_active] = n;
-        }
-        ++tick;
-        ++seq;
-        __syncthreads();
-        // maxalloc bounds + limits bookkeeping (subtractMax scheduler.go:273-290) by warp 0
-        if (warp == 0) {
-          bool closed = false;
-          for (int r = 0; r < c.n_res; ++r) {
-            long long best = INT64_MIN, bestcap = INT64_MIN;
-            int bt = 0;
-            for (int w = lane; w < W32; w += 32) {
-              uint32_t m = s.nn_opts[(size_t)w * MAXN + n];
-              while (m) {
-                int b = __ffs(m) - 1;
-                m &= m - 1;
-                int t = w * 32 + b;
-                long long al = c.types[t].allocatable[r];
-                if (al > best) { best = al; bt = t; }
-                long long cp = c.capacity[(size_t)t * KSCHED_MAX_RES + r];
-                if (cp > bestcap) bestcap = cp;
-              }
-            }
-            for (int o = 16; o; o >>= 1) {
-              long long ob = __shfl_xor_sync(0xffffffffu, best, o);
-              int ot = __shfl_xor_sync(0xffffffffu, bt, o);
-              long long oc = __shfl_xor_sync(0xffffffffu, bestcap, o);
-              if (ob > best || (ob == best && ot < bt)) { best = ob; bt = ot; }
-              if (oc > bestcap) bestcap = oc;
-            }
-            if (lane == 0) {
-              s.nn_maxalloc[(size_t)r * MAXN + n] = best;
-              s.nn_argmax[(size_t)r * MAXN + n] = bt;
-              if (tm.has_limits && ((tm.limit_present >> r) & 1)) s.remaining[(size_t)v * KSCHED_MAX_RES + r] -= bestcap;
-            }
-            if (s.min_req[r] > 0 && sh_q[r] + s.min_req[r] > best) closed = true;
-          }
-          if (lane == 0) sh_flag = closed ? 1 : 0;
-        }
-        __syncthreads();
-        ++n_new;
-        if (!sh_flag) ++n_active;
-        placed = true;
-      }
-      if (fatal) break;
-    }
-    // ---------------------------------------------------------------- failure: relax + requeue (scheduler.go:117-123, queue.go:61-68)
-    if (!placed) {
-      const uint32_t nx = row.relax_next;
-      const int tail = (head + qlen) % qcap;
-      __syncthreads();
-      if (tid == 0) {
-        s.queue[tail] = pod;
-        if (nx != KSCHED_NONE) {
-          s.pod_class[pod] = nx;
-          s.relax_level[pod] += 1;
-        } else {
-          s.last_len[pod] = qlen + 1;
-          s.last_epoch[pod] = epoch;
-        }
-      }
-      ++qlen;
-      if (nx != KSCHED_NONE) ++epoch;  // relaxed: lastLen map is reset
-      __syncthreads();
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    s.counters[0] = n_new;
-    s.counters[1] = qlen;
-    s.counters[2] = nodes_visited;
-    s.counters[3] = add_calls;
-    s.counters[4] = fatal;
-    s.counters[5] = steps;
-  }
-}
+namespace {
 
 // L2 flush helper: write a buffer larger than L2 between timed iterations
 __global__ void flush_kernel(uint32_t* buf, size_t n) {
@@ -1194,11 +778,17 @@ struct ksched_handle {
   DevBuf<ksched_topo_group> d_groups;
   DevBuf<ksched_class_topo> d_class_topo;
   DevBuf<ksched_reqset> d_filter_terms;
-  DevBuf<int32_t> d_hostname_reqs, d_relax, d_assign, d_place_seq, d_last_len, d_nn_count, d_nn_tb, d_nn_argmax, d_active, d_grp_cnt,
+  DevBuf<int32_t> d_hostname_reqs, d_relax, d_assign, d_place_seq, d_last_len, d_nn_count, d_nn_tb, d_ov_node, d_perm_desc, d_grp_cnt,
       d_grp_cnt0, d_grp_host_row, d_grp_host_total, d_grp_host_total0;
   DevBuf<uint32_t> d_F;
   DevBuf<unsigned long long> d_best;
-  DevBuf<int64_t> d_ex_req, d_ex_req0, d_ex_avail, d_nn_req, d_nn_maxalloc, d_remaining;
+  DevBuf<int64_t> d_ex_req, d_ex_req0, d_ex_avail, d_nn_req, d_remaining, d_alloc_rt;
+  DevBuf<long long> d_ov_q, d_ov_bound, d_fc_bound;
+  DevBuf<unsigned long long> d_ov_key;
+  DevBuf<unsigned short> d_ov_flags;
+  DevBuf<uint8_t> d_fc_state, d_fc_dom;
+  DevBuf<uint32_t> d_fc_opts;
+  int count_visited = 1;
   DevBuf<uint32_t> d_ex_req_present, d_ex_req_present0, d_ex_avail_present, d_ex_taintset, d_ex_itype, d_nn_req_present, d_nn_opts;
   DevBuf<uint64_t> d_ex_vals, d_ex_vals0, d_ex_meta, d_ex_meta0, d_ex_hp, d_ex_hp0, d_nn_vals, d_nn_meta, d_nn_hp, d_grp_registered,
       d_grp_registered0;
@@ -1263,7 +853,7 @@ void ksched_destroy(ksched_handle* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   // device buffers are released with the context at process exit; free the big ones eagerly
   h->d_F.release(); h->d_rows.release(); h->d_grp_host.release(); h->d_grp_host0.release(); h->d_fitset.release(); h->d_flush.release();
-  h->d_nn_opts.release(); h->d_nn_vals.release(); h->d_nn_req.release(); h->d_nn_maxalloc.release();
+  h->d_nn_opts.release(); h->d_nn_vals.release(); h->d_nn_req.release(); h->d_fc_opts.release();
   delete h;
 }
 
@@ -1327,6 +917,8 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   }
   if (valset.empty()) valset.resize(W32, 0);
   if (offset.empty()) offset.resize(W32, 0);
+  std::vector<int32_t> perm_desc((size_t)std::max(R, 1) * std::max(T, 1), 0);
+  std::vector<int64_t> alloc_rt((size_t)std::max(R, 1) * std::max(T, 1), 0);
   std::vector<int64_t> alloc_sorted((size_t)std::max(R, 1) * std::max(T, 1), 0);
   std::vector<uint32_t> fitset((size_t)std::max(R, 1) * (T + 1) * W32, 0);
   {
@@ -1334,7 +926,11 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
     for (int r = 0; r < R; ++r) {
       for (int t = 0; t < T; ++t) perm[t] = t;
       std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cat->types[a].allocatable[r] < cat->types[b].allocatable[r]; });
-      for (int i = 0; i < T; ++i) alloc_sorted[(size_t)r * T + i] = cat->types[perm[i]].allocatable[r];
+      for (int i = 0; i < T; ++i) {
+        alloc_sorted[(size_t)r * T + i] = cat->types[perm[i]].allocatable[r];
+        perm_desc[(size_t)r * T + (T - 1 - i)] = perm[i];
+        alloc_rt[(size_t)r * T + i] = cat->types[i].allocatable[r];
+      }
       uint32_t* base = &fitset[(size_t)r * (T + 1) * W32];
       for (int i = T - 1; i >= 0; --i) {
         uint32_t* cur = base + (size_t)i * W32;
@@ -1358,6 +954,8 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   CUDA_TRY(h, upload_vec(h, h->d_anyoffer, anyoffer));
   CUDA_TRY(h, upload_vec(h, h->d_member, member));
   CUDA_TRY(h, upload_vec(h, h->d_alloc_sorted, alloc_sorted));
+  CUDA_TRY(h, upload_vec(h, h->d_perm_desc, perm_desc));
+  CUDA_TRY(h, upload_vec(h, h->d_alloc_rt, alloc_rt));
   CUDA_TRY(h, upload_vec(h, h->d_fitset, fitset));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->h_templates.assign(cat->templates, cat->templates + V);
@@ -1373,6 +971,7 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   c.type_relevant = type_relevant;
   c.offrow = h->d_offrow.ptr; c.offset = h->d_offset.ptr; c.anyoffer = h->d_anyoffer.ptr; c.member = h->d_member.ptr;
   c.alloc_sorted = h->d_alloc_sorted.ptr; c.fitset = h->d_fitset.ptr;
+  c.perm_desc = h->d_perm_desc.ptr; c.alloc_rt = h->d_alloc_rt.ptr;
   c.zone_key = zone_key; c.ct_key = ct_key;
   h->have_catalog = true;
   h->uploaded = false;
@@ -1416,6 +1015,7 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   const int P = pb->n_pods, NC = pb->n_classes, NE = pb->n_existing, NG = pb->n_groups, W32 = c.W32, V = c.n_templates;
   const int MAXN = std::max(1, std::min(pb->max_new_nodes > 0 ? pb->max_new_nodes : P, std::max(P, 1)));
   h->n_pods = P; h->n_classes = NC; h->n_existing = NE; h->n_groups = NG; h->max_new = MAXN;
+  h->count_visited = pb->count_nodes_visited;
   for (int c2 = 0; c2 < NC; ++c2) {
     const ksched_pod_row& row = pb->classes[c2];
     if (row.relax_next != KSCHED_NONE && row.relax_next >= (uint32_t)NC) { h->err = "relax_next out of range"; return KSCHED_ERR_INVALID; }
@@ -1524,11 +1124,18 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   CUDA_TRY(h, h->d_queue.ensure(p1 + 1)); CUDA_TRY(h, h->d_last_len.ensure(p1)); CUDA_TRY(h, h->d_last_epoch.ensure(p1));
   const size_t mn = (size_t)MAXN;
   CUDA_TRY(h, h->d_nn_tmpl.ensure(mn)); CUDA_TRY(h, h->d_nn_count.ensure(mn)); CUDA_TRY(h, h->d_nn_tb.ensure(mn));
-  CUDA_TRY(h, h->d_nn_req.ensure(8 * mn)); CUDA_TRY(h, h->d_nn_req_present.ensure(mn)); CUDA_TRY(h, h->d_nn_maxalloc.ensure(8 * mn));
-  CUDA_TRY(h, h->d_nn_argmax.ensure(8 * mn)); CUDA_TRY(h, h->d_nn_vals.ensure(16 * mn)); CUDA_TRY(h, h->d_nn_meta.ensure(mn));
-  CUDA_TRY(h, h->d_nn_opts.ensure((size_t)W32 * mn)); CUDA_TRY(h, h->d_nn_hp.ensure(mn)); CUDA_TRY(h, h->d_active.ensure(mn));
+  CUDA_TRY(h, h->d_nn_req.ensure(8 * mn)); CUDA_TRY(h, h->d_nn_req_present.ensure(mn));
+  CUDA_TRY(h, h->d_nn_vals.ensure(16 * mn)); CUDA_TRY(h, h->d_nn_meta.ensure(mn));
+  CUDA_TRY(h, h->d_nn_opts.ensure((size_t)W32 * mn)); CUDA_TRY(h, h->d_nn_hp.ensure(mn));
+  CUDA_TRY(h, h->d_ov_key.ensure(mn)); CUDA_TRY(h, h->d_ov_q.ensure(4 * mn)); CUDA_TRY(h, h->d_ov_bound.ensure(4 * mn));
+  CUDA_TRY(h, h->d_ov_node.ensure(mn)); CUDA_TRY(h, h->d_ov_flags.ensure(mn));
+  {
+    const size_t nfc = (size_t)std::max(NC, 1) * V;
+    CUDA_TRY(h, h->d_fc_state.ensure(nfc)); CUDA_TRY(h, h->d_fc_dom.ensure(nfc)); CUDA_TRY(h, h->d_fc_bound.ensure(nfc * 4));
+    CUDA_TRY(h, h->d_fc_opts.ensure(nfc * W32));
+  }
   CUDA_TRY(h, h->d_remaining.ensure((size_t)V * KSCHED_MAX_RES));
-  CUDA_TRY(h, h->d_counters.ensure(8));
+  CUDA_TRY(h, h->d_counters.ensure(24));
   {
     size_t need = 0, n2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)p1, 0, 64, h->stream);
@@ -1615,7 +1222,8 @@ static int reset_state(ksched_handle* h) {
     for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[(size_t)v * KSCHED_MAX_RES + r] = h->h_templates[v].remaining[r];
   CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, rem.data(), rem.size() * 8, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rem is a stack vector
-  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 8 * sizeof(long long), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 24 * sizeof(long long), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_fc_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
   return KSCHED_OK;
 }
 
@@ -1625,7 +1233,7 @@ static int run_pack(ksched_handle* h) {
   PackState& s = k2.st;
   s.classes = h->d_classes.ptr; s.groups = h->d_groups.ptr; s.class_topo = h->d_class_topo.ptr; s.filter_terms = h->d_filter_terms.ptr;
   s.itype_sets = h->d_itype_sets.ptr; s.itype_complement = h->d_itype_comp.ptr; s.hostname_reqs = h->d_hostname_reqs.ptr;
-  s.order = h->d_order.ptr; s.F = h->d_F.ptr; s.best = h->d_best.ptr;
+  s.order = h->d_order.ptr; s.rows = h->d_rows.ptr; s.F = h->d_F.ptr; s.best = h->d_best.ptr;
   s.pod_pos = h->d_pod_pos.ptr; s.use_F = h->world == 1 ? 1 : 0;
   s.n_pods = h->n_pods; s.n_classes = h->n_classes; s.n_existing = h->n_existing; s.n_groups = h->n_groups; s.max_new = h->max_new;
   for (int r = 0; r < KSCHED_MAX_RES; ++r) s.min_req[r] = h->min_req[r];
@@ -1635,13 +1243,25 @@ static int run_pack(ksched_handle* h) {
   s.ex_vals = h->d_ex_vals.ptr; s.ex_meta = h->d_ex_meta.ptr; s.ex_taintset = h->d_ex_taintset.ptr; s.ex_itype = h->d_ex_itype.ptr;
   s.ex_hp = h->d_ex_hp.ptr; s.ex_closed = h->d_ex_closed.ptr;
   s.nn_tmpl = h->d_nn_tmpl.ptr; s.nn_count = h->d_nn_count.ptr; s.nn_tb = h->d_nn_tb.ptr; s.nn_req = h->d_nn_req.ptr;
-  s.nn_req_present = h->d_nn_req_present.ptr; s.nn_maxalloc = h->d_nn_maxalloc.ptr; s.nn_argmax = h->d_nn_argmax.ptr;
-  s.nn_vals = h->d_nn_vals.ptr; s.nn_meta = h->d_nn_meta.ptr; s.nn_opts = h->d_nn_opts.ptr; s.nn_hp = h->d_nn_hp.ptr; s.active = h->d_active.ptr;
+  s.nn_req_present = h->d_nn_req_present.ptr;
+  s.nn_vals = h->d_nn_vals.ptr; s.nn_meta = h->d_nn_meta.ptr; s.nn_opts = h->d_nn_opts.ptr; s.nn_hp = h->d_nn_hp.ptr;
+  s.ov_key = h->d_ov_key.ptr; s.ov_q = h->d_ov_q.ptr; s.ov_bound = h->d_ov_bound.ptr; s.ov_node = h->d_ov_node.ptr; s.ov_flags = h->d_ov_flags.ptr;
+  s.fc_state = h->d_fc_state.ptr; s.fc_opts = h->d_fc_opts.ptr; s.fc_bound = h->d_fc_bound.ptr; s.fc_dom = h->d_fc_dom.ptr;
+  s.count_visited = h->count_visited;
   s.grp_cnt = h->d_grp_cnt.ptr; s.grp_registered = h->d_grp_registered.ptr; s.grp_host = h->d_grp_host.ptr;
   s.grp_host_row = h->d_grp_host_row.ptr; s.grp_host_total = h->d_grp_host_total.ptr; s.remaining = h->d_remaining.ptr;
   s.counters = h->d_counters.ptr;
-  pack_kernel<<<1, kPackThreads, 0, h->stream>>>(k2);
-  h->tm.pack_launches = 1;
+  const size_t alloc_bytes = (size_t)h->cat.n_res * h->cat.n_types * sizeof(int64_t);
+  s.alloc_in_smem = alloc_bytes <= (size_t)(64 << 10) ? 1 : 0;
+  const size_t smem = sizeof(HotSmem) + (s.alloc_in_smem ? alloc_bytes : 0);
+  CUDA_TRY(h, cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // block size: the chain is latency-bound on ONE thread's commit; more warps only help when there are many candidate
+  // nodes to examine per pod (existing nodes, large in-flight sets)
+  int threads = h->n_existing >= 2048 ? kPackThreads : (h->n_existing >= 256 ? 256 : 128);
+  if (const char* e = getenv("KSCHED_PACK_THREADS")) { int v = atoi(e); if (v >= 32 && v <= kPackThreads && v % 32 == 0) threads = v; }
+  pack_kernel<<<1, threads, smem, h->stream>>>(k2);
+  finalize_options_kernel<<<148, 256, 0, h->stream>>>(h->cat, h->d_counters.ptr, h->d_nn_req.ptr, h->d_nn_req_present.ptr, h->d_nn_opts.ptr, h->max_new);
+  h->tm.pack_launches = 2;
   return KSCHED_OK;
 }
 
@@ -1706,9 +1326,13 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
   if (!h || !pb || !res || !h->uploaded) return KSCHED_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int P = h->n_pods, NE = h->n_existing, MAXN = h->max_new, W32 = h->cat.W32, W64 = h->W64, V = h->cat.n_templates;
-  long long counters[8];
+  long long counters[24];
   CUDA_TRY(h, cudaMemcpyAsync(counters, h->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+#ifdef KSCHED_PROFILE_PACK
+  fprintf(stderr, "[pack profile] cycles: top=%lld eval=%lld reduce=%lld commit=%lld sync=%lld generic=%lld  steps=%lld\n",
+          counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[5]);
+#endif
   if (counters[4] != 0) {
     h->err = counters[4] == KSCHED_ERR_OVERFLOW ? "new-node capacity exceeded" : "a pod is constrained by more topology groups than the kernel supports";
     return (int)counters[4];

@@ -1,0 +1,782 @@
+// K2 — pack_kernel: Scheduler.add's sequential first-fit (scheduler.go:174-219) in one persistent CTA.
+//
+// Design (B200-first, latency-bound integer work):
+//  * one CTA of 1024 threads, one pod per iteration; candidate nodes are examined one per thread and the
+//    reference's scan order is recovered by a block-wide argmin over (pod count, stable tie-break);
+//  * the state every candidate check needs (order key, request vector, allocatable bound of the node's
+//    dominant instance type) lives in SHARED MEMORY for the first kActCap open nodes; everything colder
+//    (requirement masks, instance-type bitsets, host ports) stays in global memory / L2;
+//  * the instance-type bitset of a node is filtered LAZILY by resources: Fits() is monotone in the request
+//    vector, so options_true = options_stored AND FIT(requests) and the AND is applied once, by
+//    finalize_options_kernel, after the pack loop. A node whose surviving options contain a type that is
+//    maximal in every resource ("dominant") is accept-tested with R integer compares;
+//  * the winning thread commits its own candidate — no re-evaluation by a leader thread;
+//  * fresh nodes of the same (pod class, template) reuse a cached option set (the K1 row).
+#pragma once
+
+namespace {
+
+constexpr int kActCap = 1536;  // open in-flight nodes whose hot state is held in shared memory
+constexpr int kHotRes = 4;     // resources covered by the hot request / bound vectors (cpu, memory, pods, +1)
+
+struct HotSmem {
+  unsigned long long key[kActCap];     // (pod count << 32) | biased tie-break  == position under a stable sort
+  long long q[kHotRes][kActCap];       // node.Requests
+  long long bound[kHotRes][kActCap];   // allocatable of the dominant option, or per-resource max over the options
+  int node[kActCap];
+  unsigned short flags[kActCap];       // bit0 dominant option exists; bits 1..4 request-map keys; bits 8.. template
+};
+
+struct Hot {
+  HotSmem* sm;
+  unsigned long long* ov_key;
+  long long* ov_q;      // [kHotRes][ov_stride]
+  long long* ov_bound;  // [kHotRes][ov_stride]
+  int* ov_node;
+  unsigned short* ov_flags;
+  int ov_stride;
+  __device__ __forceinline__ unsigned long long& key(int a) const { return a < kActCap ? sm->key[a] : ov_key[a - kActCap]; }
+  __device__ __forceinline__ long long& q(int r, int a) const { return a < kActCap ? sm->q[r][a] : ov_q[(size_t)r * ov_stride + (a - kActCap)]; }
+  __device__ __forceinline__ long long& bound(int r, int a) const { return a < kActCap ? sm->bound[r][a] : ov_bound[(size_t)r * ov_stride + (a - kActCap)]; }
+  __device__ __forceinline__ int& node(int a) const { return a < kActCap ? sm->node[a] : ov_node[a - kActCap]; }
+  __device__ __forceinline__ unsigned short& flags(int a) const { return a < kActCap ? sm->flags[a] : ov_flags[a - kActCap]; }
+  __device__ void move(int dst, int src) const {
+    key(dst) = key(src);
+    for (int r = 0; r < kHotRes; ++r) { q(r, dst) = q(r, src); bound(r, dst) = bound(r, src); }
+    node(dst) = node(src);
+    flags(dst) = flags(src);
+  }
+};
+
+__device__ __forceinline__ unsigned long long order_key(int count, int tb) {
+  return ((unsigned long long)(unsigned)count << 32) | (unsigned)(tb ^ 0x80000000);
+}
+
+// Upper bounds of allocatable over a node's stored options, by probing each resource's descending order.
+// has_dom: one option attains the maximum in every resource, so "requests <= bound" is an exact accept test.
+__device__ void compute_bounds(const DevCatalog& c, const uint32_t* opts, int stride, int n, long long* bound, bool* has_dom) {
+  int arg0 = -1;
+  for (int r = 0; r < kHotRes; ++r) bound[r] = INT64_MIN;
+  const int R = c.n_res < kHotRes ? c.n_res : kHotRes;
+  for (int r = 0; r < R; ++r) {
+    const int32_t* perm = c.perm_desc + (size_t)r * c.n_types;
+    for (int i = 0; i < c.n_types; ++i) {
+      const int t = perm[i];
+      if ((opts[(size_t)(t >> 5) * stride + n] >> (t & 31)) & 1) {
+        bound[r] = c.alloc_rt[(size_t)r * c.n_types + t];
+        if (r == 0) arg0 = t;
+        break;
+      }
+    }
+  }
+  bool dom = arg0 >= 0 && c.n_res <= kHotRes;
+  for (int r = 1; r < R && dom; ++r) dom = c.alloc_rt[(size_t)r * c.n_types + arg0] == bound[r];
+  *has_dom = dom;
+}
+
+// 64-bit min over a warp with two 32-bit REDUX operations (hi word first, then lo word among the hi-minimal lanes)
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+// single-sync block argmin (double-buffered scratch)
+__device__ __forceinline__ unsigned long long block_min_u64_db(unsigned long long v, unsigned long long (*red)[32], int& parity) {
+  v = warp_min_u64(v);
+  if (blockDim.x == 32) return v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* buf = red[parity];
+  parity ^= 1;
+  if (lane == 0) buf[warp] = v;
+  __syncthreads();
+  const unsigned long long r = lane < (int)(blockDim.x >> 5) ? buf[lane] : ~0ull;
+  return warp_min_u64(r);
+}
+
+struct StepShared {
+  int placed_closed;   // commit outcome: 1 = the accepting node became full and left the active set
+  int path;            // fresh-node path
+  unsigned any;
+  long long q[KSCHED_MAX_RES];
+  unsigned qp;
+  long long bound[kHotRes];
+  int has_dom;
+  long long visited;
+};
+
+enum { kPathReject = 0, kPathCached = 1, kPathRow = 2, kPathDynamic = 3, kPathCachedEmpty = 4 };
+
+// The words of a pod row every candidate check needs. Loaded RAW one iteration ahead for first-pass pods (anything
+// derived from them is computed by the consuming iteration, so the prefetch never waits on its own loads).
+struct PodRegs {
+  const ksched_pod_row* row;
+  uint32_t pod, res, itype, hostname, topo_begin, topo_end;
+  long long req[kHotRes];
+  uint64_t tol, hpc, hpe, meta, cls64;
+};
+__device__ __forceinline__ PodRegs load_pod_regs(const ksched_pod_row* row, uint32_t pod) {
+  PodRegs r;
+  r.row = row;
+  r.pod = pod;
+  r.res = row->res_present;
+#pragma unroll
+  for (int i = 0; i < kHotRes; ++i) r.req[i] = row->requests[i];  // 0 where the resource is absent
+  r.tol = row->tolerated_taintsets;
+  r.hpc = row->hostport_conflicts;
+  r.hpe = row->hostport_entries;
+  r.meta = row->meta;
+  r.itype = row->itype_req;
+  r.hostname = row->hostname_req;
+  r.topo_begin = row->topo_begin;
+  r.topo_end = row->topo_end;
+  r.cls64 = row->reserved;
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Slow part of a candidate check (requirement keys / topology / instance-type words), kept out of line so that the
+// common path (no requirement can change, dominant option fits) stays in registers.
+struct SlowEval {
+  Touched t;
+  TypeCtx x;
+  long long q[KSCHED_MAX_RES];
+  uint32_t qp;
+  bool changed;
+};
+__device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const PodTopo& pt, bool plain,
+                                           int n, unsigned short fl, const long long* q_hot, const int64_t* alloc_sorted, SlowEval& e) {
+  const int MAXN = s.max_new, NE = s.n_existing, R = c.n_res, W32 = c.W32;
+  const uint32_t p_res = row.res_present;
+  e.t.n = 0;
+  e.changed = false;
+  bool need_types = !(fl & 1) || row.itype_req != KSCHED_NONE;
+  if (!plain) {
+    if (!requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, e.t)) return false;
+    for (int i = 0; i < e.t.n; ++i) e.changed = e.changed || e.t.changed[i];
+    need_types = need_types || e.changed;
+  }
+  for (int r = 0; r < kHotRes; ++r) e.q[r] = q_hot[r];
+  for (int r = kHotRes; r < R; ++r) e.q[r] = s.nn_req[(size_t)r * MAXN + n] + (((p_res >> r) & 1) ? row.requests[r] : 0);
+  e.qp = s.nn_req_present[n] | p_res;
+  if (!need_types) return true;  // the dominant option fits and no requirement changed
+  build_type_ctx(c, s, row, e.t, e.q, e.qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, alloc_sorted, e.x);
+  for (int w = 0; w < W32; ++w) {
+    const uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
+    if (base && type_word(c, s, e.x, base, w)) return true;
+  }
+  return false;
+}
+// Requirement-changing part of a commit: new masks, requirement-driven narrowing of the stored options, new bounds.
+__device__ __noinline__ void commit_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, int n, SlowEval& e, long long* bound,
+                                         bool* dom, uint64_t* meta_out) {
+  const int MAXN = s.max_new, W32 = c.W32;
+  uint64_t meta = s.nn_meta[n];
+  for (int i = 0; i < e.t.n; ++i) {
+    const int k = e.t.key[i];
+    const Req& f = e.t.fin[i];
+    const uint64_t bit = 1ull << k;
+    meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+    if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+    if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+    s.nn_vals[(size_t)k * MAXN + n] = f.values;
+  }
+  s.nn_meta[n] = meta;
+  *meta_out = meta;
+  e.x.res_mask = 0;  // resources stay lazy (finalize_options_kernel)
+  for (int w = 0; w < W32; ++w) {
+    const uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
+    if (base) s.nn_opts[(size_t)w * MAXN + n] = type_word(c, s, e.x, base, w);
+  }
+  compute_bounds(c, s.nn_opts, MAXN, n, bound, dom);
+}
+
+struct StepCtx {  // per-CTA objects shared by the slow path
+  PodTopo* pt;
+  Touched* fresh_t;
+  TypeCtx* fresh_x;
+  unsigned long long (*red)[32];
+  StepShared* sh;
+  const uint32_t* tmpl_taintset;
+  Hot H;
+  const int64_t* alloc_sorted;
+};
+struct LoopVars {
+  int head, qlen, n_new, n_active, tick, seq, parity, fatal;
+  uint32_t epoch;
+  bool pt_nonempty;
+  long long nodes_visited;
+};
+
+// One full Scheduler.add for one pod (existing nodes -> in-flight nodes -> new node -> relax/requeue). Every thread of
+// the CTA calls it together. Kept out of line: the steady-state path in pack_kernel must stay a few KB of code, because a
+// single resident CTA runs straight out of the instruction cache hierarchy (L0 ~6 KB, L1.5 32 KB).
+__device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, const PodRegs& cur, bool first_pass, int fpos_first, LoopVars& L) {
+  const DevCatalog& c = p.cat;
+  const PackState& s = p.st;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int W32 = c.W32, V = c.n_templates, NE = s.n_existing, MAXN = s.max_new;
+  const int R = c.n_res, RH = R < kHotRes ? R : kHotRes;
+  const int qcap = s.n_pods + 1;
+  PodTopo& pt = *X.pt;
+  Touched& fresh_t = *X.fresh_t;
+  TypeCtx& fresh_x = *X.fresh_x;
+  unsigned long long (*red)[32] = X.red;
+  StepShared& sh = *X.sh;
+  const uint32_t* tmpl_taintset = X.tmpl_taintset;
+  const Hot& H = X.H;
+  const int64_t* alloc_sorted = X.alloc_sorted;
+  int &head = L.head, &qlen = L.qlen, &n_new = L.n_new, &n_active = L.n_active, &tick = L.tick, &seq = L.seq, &parity = L.parity, &fatal = L.fatal;
+  uint32_t& epoch = L.epoch;
+  bool& pt_nonempty = L.pt_nonempty;
+  long long& nodes_visited = L.nodes_visited;
+    const uint32_t pod = cur.pod, cls = (uint32_t)cur.cls64;
+    const ksched_pod_row& row = *cur.row;
+    const uint32_t p_res = cur.res;
+    long long preq[kHotRes];
+#pragma unroll
+    for (int r = 0; r < kHotRes; ++r) preq[r] = cur.req[r];
+    const uint64_t p_tol = cur.tol, p_hpc = cur.hpc, p_hpe = cur.hpe;
+    const uint32_t p_keys = (uint32_t)(cur.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF, p_itype = cur.itype, p_hostname = cur.hostname;
+    const bool has_topo = cur.topo_begin != cur.topo_end;
+    if (has_topo || pt_nonempty) {
+      __syncthreads();  // previous step's readers of pt are done
+      if (tid == 0) build_pod_topo(c, s, row, pt);
+      __syncthreads();
+      pt_nonempty = pt.n != 0;
+      if (pt.overflow) { fatal = KSCHED_ERR_UNSUPPORTED; return; }
+    }
+    const bool plain = p_keys == 0 && !pt_nonempty && p_itype == KSCHED_NONE && p_hostname == KSCHED_NONE;  // no requirement can change
+
+    bool placed = false;
+    // ------------------------------------------------------------ 1) existing nodes in caller order (scheduler.go:176-180)
+    if (NE > 0) {
+      unsigned long long mine = ~0ull;
+      Touched t;
+      t.n = 0;
+      for (int e = tid; e < NE; e += blockDim.x) {
+        if (s.ex_closed[e]) continue;
+        if (!((p_tol >> s.ex_taintset[e]) & 1)) continue;
+        if (p_hpc && (s.ex_hp[e] & p_hpc)) continue;
+        bool ok = true;  // Fits(requests, available) comes first (existingnode.go:98-102)
+        const uint32_t qp = s.ex_req_present[e] | p_res;
+        for (int r = 0; r < R && ok; ++r) {
+          if (!((qp >> r) & 1)) continue;
+          long long q = s.ex_req[(size_t)r * NE + e] + (((p_res >> r) & 1) ? row.requests[r] : 0);
+          long long a = ((s.ex_avail_present[e] >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
+          ok = q <= a;
+        }
+        if (!ok) continue;
+        if (p_itype != KSCHED_NONE) {
+          const uint32_t it = s.ex_itype[e];
+          bool allowed = it == KSCHED_NONE ? (s.itype_complement[p_itype] != 0) : ((s.itype_sets[(size_t)p_itype * W32 + (it >> 5)] >> (it & 31)) & 1);
+          if (!allowed) continue;
+        }
+        if (!plain && !requirements_phase(c, s, row, pt, s.ex_vals, s.ex_meta[e], NE, e, e, true, t)) continue;
+        mine = (unsigned long long)e;
+        break;  // this thread's remaining nodes have larger indices
+      }
+      const unsigned long long w = block_min_u64_db(mine, red, parity);
+      if (w != ~0ull) {
+        const int e = (int)w;
+        nodes_visited += e + 1;
+        if (mine == w) {  // the winning thread commits its own candidate
+          uint64_t meta = s.ex_meta[e];
+          if (!plain) {
+            for (int i = 0; i < t.n; ++i) {
+              const int k = t.key[i];
+              const Req& f = t.fin[i];
+              const uint64_t bit = 1ull << k;
+              meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+              if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+              if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+              s.ex_vals[(size_t)k * NE + e] = f.values;
+            }
+            s.ex_meta[e] = meta;
+          }
+          bool closed = false;
+          for (int r = 0; r < R; ++r) {
+            if ((p_res >> r) & 1) s.ex_req[(size_t)r * NE + e] += row.requests[r];
+            long long a = ((s.ex_avail_present[e] >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
+            if (s.min_req[r] > 0 && s.ex_req[(size_t)r * NE + e] + s.min_req[r] > a) closed = true;
+          }
+          s.ex_req_present[e] |= p_res;
+          if (p_hpe) s.ex_hp[e] |= p_hpe;
+          s.ex_closed[e] = closed;
+          if (has_topo) topo_record(c, s, row, s.ex_vals, meta, NE, e, e);
+          s.assign[pod] = e;
+          s.place_seq[pod] = seq;
+        }
+        ++seq;
+        placed = true;
+        __syncthreads();  // the commit is read by every thread in the next step
+      } else {
+        nodes_visited += NE;
+      }
+    }
+    // ------------------------------------------------------------ 2) in-flight nodes, fewest pods first (scheduler.go:183-190)
+    if (!placed && n_active > 0) {
+      unsigned long long mine = ~0ull;
+      int best_a = -1, last_slow = -1;
+      long long bq[kHotRes] = {0, 0, 0, 0};
+      SlowEval ev;
+      bool best_slow = false;
+      for (int a = tid; a < n_active; a += blockDim.x) {
+        const unsigned long long key = H.key(a);
+        if (key >= mine) continue;  // cannot beat this thread's current candidate
+        const unsigned short fl = H.flags(a);
+        if (!((p_tol >> tmpl_taintset[fl >> 8]) & 1)) continue;  // Taints.Tolerates
+        const uint32_t qp = ((fl >> 1) & 0xF) | p_res;
+        long long q[kHotRes];
+        bool ok = true;
+#pragma unroll
+        for (int r = 0; r < kHotRes; ++r) {
+          q[r] = H.q(r, a) + preq[r];
+          if (r < RH && ((qp >> r) & 1)) ok = ok && q[r] <= H.bound(r, a);
+        }
+        if (!ok) continue;
+        if (p_hpc && (s.nn_hp[H.node(a)] & p_hpc)) continue;
+        const bool fast = plain && (fl & 1);  // no requirement can change and the dominant option fits
+        if (!fast) {
+          last_slow = a;
+          if (!evaluate_slow(c, s, row, pt, plain, H.node(a), fl, q, alloc_sorted, ev)) continue;
+        }
+        mine = key;
+        best_a = a;
+        best_slow = !fast;
+#pragma unroll
+        for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
+      }
+      const unsigned long long wkey = block_min_u64_db(mine, red, parity);
+      if (wkey != ~0ull) {
+        if (s.count_visited) {  // rank of the winner among ALL in-flight nodes (the reference also walks the full ones)
+          int less = 0;
+          for (int i = tid; i < n_new; i += blockDim.x) less += order_key(s.nn_count[i], s.nn_tb[i]) < wkey;
+          for (int o = 16; o; o >>= 1) less += __shfl_xor_sync(0xffffffffu, less, o);
+          __syncthreads();
+          if (tid == 0) sh.visited = 0;
+          __syncthreads();
+          if (lane == 0 && less) atomicAdd((unsigned long long*)&sh.visited, (unsigned long long)less);
+          __syncthreads();
+          nodes_visited += sh.visited + 1;
+        }
+        if (mine == wkey) {  // the winning thread commits its own candidate
+          const int a = best_a;
+          const int n = H.node(a);
+          unsigned short fl = H.flags(a);
+          if (best_slow && last_slow != a) evaluate_slow(c, s, row, pt, plain, n, fl, bq, alloc_sorted, ev);
+#pragma unroll
+          for (int r = 0; r < kHotRes; ++r) H.q(r, a) = bq[r];
+          for (int r = kHotRes; r < R; ++r)
+            if ((p_res >> r) & 1) s.nn_req[(size_t)r * MAXN + n] += row.requests[r];
+          if ((p_res >> kHotRes) || ((p_res & 0xF) & ~((fl >> 1) & 0xF))) s.nn_req_present[n] |= p_res;
+          fl |= (unsigned short)((p_res & 0xF) << 1);
+          if (p_hpe) s.nn_hp[n] |= p_hpe;
+          const int count = (int)(wkey >> 32) + 1;
+          s.nn_count[n] = count;
+          s.nn_tb[n] = -(tick + 1);  // front of the next pod-count block under a stable sort
+          H.key(a) = order_key(count, -(tick + 1));
+          uint64_t meta = 0;
+          if (best_slow && (ev.changed || p_itype != KSCHED_NONE)) {
+            long long b[kHotRes];
+            bool dom;
+            commit_slow(c, s, row, n, ev, b, &dom, &meta);
+#pragma unroll
+            for (int r = 0; r < kHotRes; ++r) H.bound(r, a) = b[r];
+            fl = dom ? (fl | 1) : (fl & ~1);
+          } else if (has_topo) {
+            meta = s.nn_meta[n];
+          }
+          H.flags(a) = fl;
+          bool closed = false;
+          for (int r = 0; r < RH; ++r)
+            if (s.min_req[r] > 0 && bq[r] + s.min_req[r] > H.bound(r, a)) closed = true;
+          if (has_topo) topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
+          s.assign[pod] = NE + n;
+          s.place_seq[pod] = seq;
+          if (closed) {  // the node leaves the active set: its request vector goes back to global memory
+            for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + n] = bq[r];
+            if (a != n_active - 1) H.move(a, n_active - 1);
+          }
+          sh.placed_closed = closed ? 1 : 0;
+        }
+        ++tick;
+        ++seq;
+        placed = true;
+        __syncthreads();
+        if (sh.placed_closed) --n_active;
+      } else {
+        nodes_visited += n_new;
+      }
+    } else if (!placed) {
+      nodes_visited += n_new;  // every in-flight node is full; the reference still walks them
+    }
+    // ------------------------------------------------------------ 3) open a new node, templates in weight order (scheduler.go:194-217)
+    if (!placed) {
+      const bool f_valid = s.use_F && (first_pass || s.relax_level[pod] == 0);  // K1's row is valid while the pod has its original class
+      const uint32_t fpos = first_pass ? (uint32_t)fpos_first : s.pod_pos[pod];
+      const bool no_column = f_valid && s.best[fpos] == kNoBest;  // no feasible (template, type) column at all
+      if (no_column) nodes_visited += V;
+      for (int v = 0; v < V && !placed && !no_column; ++v) {
+        const ksched_template& tm = c.templates[v];
+        ++nodes_visited;
+        if (n_new >= MAXN) { fatal = KSCHED_ERR_OVERFLOW; break; }
+        const int n = n_new;  // tentative slot: the hostname placeholder of this attempt (node.go:46)
+        const bool limits_active = tm.has_limits && tm.limit_present;
+        __syncthreads();
+        if (tid == 0) {
+          bool ok = (p_tol >> tm.taintset) & 1;
+          fresh_t.n = 0;
+          if (ok && !plain) ok = requirements_phase(c, s, row, pt, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, NE + n, false, fresh_t);
+          int path = kPathReject;
+          if (ok) {
+            sh.qp = tm.daemon_res_present | p_res;
+            for (int r = 0; r < R; ++r) sh.q[r] = tm.daemon_requests[r] + (((p_res >> r) & 1) ? row.requests[r] : 0);
+            bool same = f_valid;  // topology left every requirement exactly as K1 saw it
+            for (int i = 0; i < fresh_t.n && same; ++i) same = req_equal(fresh_t.fin[i], fresh_t.merged[i]);
+            const uint8_t st = (same && !limits_active) ? s.fc_state[(size_t)cls * V + v] : 0;
+            if (st == 1) path = kPathCached;
+            else if (st == 2) path = kPathCachedEmpty;
+            else if (same) path = kPathRow;
+            else {
+              path = kPathDynamic;
+              build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, true, alloc_sorted, fresh_x);
+            }
+          }
+          sh.path = path;
+          sh.any = 0;
+        }
+        __syncthreads();
+        const int path = sh.path;
+        if (path == kPathReject || path == kPathCachedEmpty) continue;
+        const size_t fc = ((size_t)cls * V + v);
+        if (path == kPathCached) {
+          for (int w = tid; w < W32; w += blockDim.x) s.nn_opts[(size_t)w * MAXN + n] = s.fc_opts[fc * W32 + w];
+          if (tid == 0) {
+            for (int r = 0; r < kHotRes; ++r) sh.bound[r] = s.fc_bound[fc * kHotRes + r];
+            sh.has_dom = s.fc_dom[fc];
+          }
+        } else {
+          bool local_any = false;
+          for (int w = tid; w < W32; w += blockDim.x) {
+            uint32_t base = c.member[(size_t)v * W32 + w];
+            if (base && limits_active) {  // filterByRemainingResources (scheduler.go:293-309)
+              uint32_t m = base;
+              while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int t = w * 32 + b;
+                for (int r = 0; r < R; ++r)
+                  if (((tm.limit_present >> r) & 1) && c.capacity[(size_t)t * KSCHED_MAX_RES + r] > s.remaining[(size_t)v * KSCHED_MAX_RES + r]) base &= ~(1u << b);
+              }
+            }
+            uint32_t sw = 0;
+            if (base) sw = path == kPathRow ? (base & s.F[((size_t)fpos * V + v) * W32 + w]) : type_word(c, s, fresh_x, base, w);
+            s.nn_opts[(size_t)w * MAXN + n] = sw;
+            local_any = local_any || sw;
+          }
+          if (local_any) atomicOr(&sh.any, 1u);
+          __syncthreads();
+          const bool cacheable = path == kPathRow && !limits_active;
+          if (!sh.any) {
+            if (cacheable && tid == 0) s.fc_state[fc] = 2;
+            continue;
+          }
+          if (tid == 0) {
+            bool dom;
+            compute_bounds(c, s.nn_opts, MAXN, n, sh.bound, &dom);
+            sh.has_dom = dom;
+            if (cacheable) {
+              for (int r = 0; r < kHotRes; ++r) s.fc_bound[fc * kHotRes + r] = sh.bound[r];
+              s.fc_dom[fc] = dom;
+            }
+          }
+          if (cacheable)
+            for (int w = tid; w < W32; w += blockDim.x) s.fc_opts[fc * W32 + w] = s.nn_opts[(size_t)w * MAXN + n];
+          __syncthreads();
+          if (cacheable && tid == 0) s.fc_state[fc] = 1;
+        }
+        // ---- commit the new node (NewNode + Add, node.go:44-107)
+        const int a = n_active;
+        if (tid < c.n_keys) {
+          uint64_t val = tm.reqs.values[tid];
+          for (int i = 0; i < fresh_t.n; ++i) if (fresh_t.key[i] == tid) val = fresh_t.fin[i].values;
+          s.nn_vals[(size_t)tid * MAXN + n] = val;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          uint64_t meta = tm.reqs.meta & 0xFFFFFFFFull;
+          for (int i = 0; i < fresh_t.n; ++i) {
+            const int k = fresh_t.key[i];
+            const Req& f = fresh_t.fin[i];
+            const uint64_t bit = 1ull << k;
+            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+          }
+          s.nn_meta[n] = meta;
+          s.nn_tmpl[n] = (uint8_t)v;
+          for (int r = 0; r < KSCHED_MAX_RES; ++r) s.nn_req[(size_t)r * MAXN + n] = r < R ? sh.q[r] : 0;
+          s.nn_req_present[n] = sh.qp;
+          s.nn_hp[n] = p_hpe;
+          s.nn_count[n] = 1;
+          s.nn_tb[n] = tick + 1;  // appended: last of the one-pod block
+          bool closed = false;
+          for (int r = 0; r < RH; ++r)
+            if (s.min_req[r] > 0 && sh.q[r] + s.min_req[r] > sh.bound[r]) closed = true;
+          if (!closed) {
+            H.key(a) = order_key(1, tick + 1);
+            for (int r = 0; r < kHotRes; ++r) { H.q(r, a) = r < R ? sh.q[r] : 0; H.bound(r, a) = sh.bound[r]; }
+            H.node(a) = n;
+            H.flags(a) = (unsigned short)((sh.has_dom ? 1 : 0) | ((sh.qp & 0xF) << 1) | (v << 8));
+          }
+          sh.placed_closed = closed ? 1 : 0;
+          if (has_topo) topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
+          s.assign[pod] = NE + n;
+          s.place_seq[pod] = seq;
+          if (limits_active) {  // subtractMax (scheduler.go:273-290): largest capacity among the surviving options
+            // capacity maximum is taken over the options that survive resources too
+            for (int r = 0; r < R; ++r) {
+              if (!((tm.limit_present >> r) & 1)) continue;
+              long long mx = INT64_MIN;
+              for (int w = 0; w < W32; ++w) {
+                uint32_t m = s.nn_opts[(size_t)w * MAXN + n];
+                while (m) {
+                  const int b = __ffs(m) - 1;
+                  m &= m - 1;
+                  const long long cp = c.capacity[(size_t)(w * 32 + b) * KSCHED_MAX_RES + r];
+                  mx = cp > mx ? cp : mx;
+                }
+              }
+              if (mx != INT64_MIN) s.remaining[(size_t)v * KSCHED_MAX_RES + r] -= mx;
+            }
+          }
+        }
+        ++tick;
+        ++seq;
+        __syncthreads();
+        ++n_new;
+        if (!sh.placed_closed) ++n_active;
+        placed = true;
+      }
+      if (fatal) return;
+    }
+    // ------------------------------------------------------------ failure: relax + requeue (scheduler.go:117-123, queue.go:61-68)
+    if (!placed) {
+      const uint32_t nx = row.relax_next;
+      int tail = head + qlen;
+      if (tail >= qcap) tail -= qcap;
+      if (tid == 0) {
+        s.queue[tail] = pod;
+        if (nx != KSCHED_NONE) {
+          s.pod_class[pod] = nx;
+          s.relax_level[pod] += 1;
+        } else {
+          s.last_len[pod] = qlen + 1;
+          s.last_epoch[pod] = epoch;
+        }
+      }
+      ++qlen;
+      if (nx != KSCHED_NONE) ++epoch;  // a successful relaxation resets the lastLen map
+      __syncthreads();
+    }
+  }
+
+#ifdef KSCHED_PROFILE_PACK
+#define PK_T(i) { long long _now = clock64(); pk_acc[i] += _now - pk_last; pk_last = _now; }
+#else
+#define PK_T(i)
+#endif
+
+__global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_constant__ K2Params p) {
+#ifdef KSCHED_PROFILE_PACK
+  long long pk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long pk_last = clock64();
+#endif
+  const DevCatalog& c = p.cat;
+  const PackState& s = p.st;
+  const int tid = threadIdx.x;
+  const int NE = s.n_existing, MAXN = s.max_new;
+  const int R = c.n_res, RH = R < kHotRes ? R : kHotRes;
+
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  HotSmem* hs = reinterpret_cast<HotSmem*>(dyn_smem);
+  int64_t* sm_alloc = reinterpret_cast<int64_t*>(dyn_smem + sizeof(HotSmem));
+  const Hot H{hs, s.ov_key, s.ov_q, s.ov_bound, s.ov_node, s.ov_flags, MAXN};
+  if (s.alloc_in_smem)
+    for (int i = tid; i < R * c.n_types; i += blockDim.x) sm_alloc[i] = c.alloc_sorted[i];
+
+  __shared__ PodTopo pt;
+  __shared__ Touched fresh_t;
+  __shared__ TypeCtx fresh_x;
+  __shared__ unsigned long long red[2][32];
+  __shared__ StepShared sh;
+  __shared__ uint32_t tmpl_taintset[KSCHED_MAX_TEMPLATES];
+  if (tid < c.n_templates) tmpl_taintset[tid] = c.templates[tid].taintset;
+  if (tid == 0) pt.n = 0;
+  const StepCtx X{&pt, &fresh_t, &fresh_x, red, &sh, tmpl_taintset, H, s.alloc_in_smem ? sm_alloc : c.alloc_sorted};
+
+  int head = 0, qlen = s.n_pods;
+  const int qcap = s.n_pods + 1;
+  int n_new = 0, n_active = 0, tick = 0, seq = 0, parity = 0;
+  uint32_t epoch = 1;
+  long long nodes_visited = 0, add_calls = 0;
+  int fatal = 0;
+  bool pt_nonempty = false;
+
+  for (int i = tid; i < s.n_pods; i += blockDim.x) {
+    s.queue[i] = s.order[i];
+    s.pod_pos[s.order[i]] = (uint32_t)i;
+    s.assign[i] = -1;
+    s.place_seq[i] = -1;
+    s.last_epoch[i] = 0;
+  }
+  __syncthreads();
+
+  // First pass over the queue = FFD order: row qi of the dense pod-row matrix (K0) belongs to pod order[qi], so the
+  // next pod's words are fetched one iteration ahead with addresses that depend on no earlier load.
+  int qi = 0;
+  const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
+  PodRegs nxt{};
+  if (s.n_pods > 0) nxt = load_pod_regs(ffd_rows, s.order[0]);
+  const bool fast_allowed = NE == 0 && !s.count_visited;
+
+  while (qlen > 0) {
+    PodRegs cur;
+    const bool first_pass = qi < s.n_pods;
+    if (first_pass) {
+      cur = nxt;
+      if (qi + 1 < s.n_pods) nxt = load_pod_regs(ffd_rows + qi + 1, s.order[qi + 1]);
+      if (tid < 2 && qi + 24 < s.n_pods) prefetch_l2(reinterpret_cast<const char*>(ffd_rows + qi + 24) + tid * 128);
+      if (tid == 2 && (qi & 31) == 0 && qi + 96 < s.n_pods) prefetch_l2(s.order + qi + 96);
+    } else {
+      const uint32_t qpod = s.queue[head];
+      if (s.last_epoch[qpod] == epoch && s.last_len[qpod] == qlen) break;  // Pop(): no progress in a whole cycle (queue.go:52)
+      cur = load_pod_regs(s.classes + s.pod_class[qpod], qpod);
+    }
+    PK_T(0)
+    const int fpos_first = qi;
+    ++qi;
+    head = head + 1 == qcap ? 0 : head + 1;
+    --qlen;
+    ++add_calls;
+
+    // ---- steady-state path: a pod whose requirements cannot change anything, against in-flight nodes whose surviving
+    // options contain a dominant type. R integer compares per candidate, block argmin, the winner commits.
+    bool done = false;
+    const bool plain_pod = ((cur.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0 && cur.itype == KSCHED_NONE && cur.hostname == KSCHED_NONE &&
+                           cur.topo_begin == cur.topo_end;
+    if (fast_allowed && plain_pod && n_active > 0 && n_active <= kActCap) {
+      unsigned long long mine = ~0ull;
+      int best_a = -1;
+      long long bq[kHotRes] = {0, 0, 0, 0};
+      for (int a = tid; a < n_active; a += blockDim.x) {  // hot state straight from shared memory
+        const unsigned long long key = hs->key[a];
+        if (key >= mine) continue;
+        const unsigned short fl = hs->flags[a];
+        if (!((cur.tol >> tmpl_taintset[fl >> 8]) & 1)) continue;
+        const uint32_t qp = ((fl >> 1) & 0xF) | cur.res;
+        long long q[kHotRes];
+        bool ok = true;
+#pragma unroll
+        for (int r = 0; r < kHotRes; ++r) {
+          q[r] = hs->q[r][a] + cur.req[r];
+          if (r < RH && ((qp >> r) & 1)) ok = ok && q[r] <= hs->bound[r][a];
+        }
+        if (!ok) continue;
+        if (cur.hpc && (s.nn_hp[hs->node[a]] & cur.hpc)) continue;
+        if (!(fl & 1)) { mine = 0; break; }  // no dominant option: this pod takes the generic path
+        mine = key;
+        best_a = a;
+#pragma unroll
+        for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
+      }
+      PK_T(1)
+      const unsigned long long wkey = block_min_u64_db(mine, red, parity);
+      PK_T(2)
+      if (wkey != 0 && wkey != ~0ull) {
+        if (mine == wkey) {
+          const int a = best_a, n = H.node(a);
+          unsigned short fl = H.flags(a);
+#pragma unroll
+          for (int r = 0; r < kHotRes; ++r) H.q(r, a) = bq[r];
+          for (int r = kHotRes; r < R; ++r)
+            if ((cur.res >> r) & 1) s.nn_req[(size_t)r * MAXN + n] += cur.row->requests[r];
+          if ((cur.res >> kHotRes) || ((cur.res & 0xF) & ~((fl >> 1) & 0xF))) {
+            s.nn_req_present[n] |= cur.res;
+            H.flags(a) = fl | (unsigned short)((cur.res & 0xF) << 1);
+          }
+          if (cur.hpe) s.nn_hp[n] |= cur.hpe;
+          const int count = (int)(wkey >> 32) + 1;
+          s.nn_count[n] = count;
+          s.nn_tb[n] = -(tick + 1);
+          H.key(a) = order_key(count, -(tick + 1));
+          bool closed = false;
+          for (int r = 0; r < RH; ++r)
+            if (s.min_req[r] > 0 && bq[r] + s.min_req[r] > H.bound(r, a)) closed = true;
+          s.assign[cur.pod] = NE + n;
+          s.place_seq[cur.pod] = seq;
+          if (closed) {
+            for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + n] = bq[r];
+            if (a != n_active - 1) H.move(a, n_active - 1);
+          }
+          sh.placed_closed = closed ? 1 : 0;
+        }
+        ++tick;
+        ++seq;
+        PK_T(3)
+        __syncthreads();
+        PK_T(4)
+        if (sh.placed_closed) --n_active;
+        done = true;
+      }
+    }
+    if (!done) {
+      LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited};
+      generic_step(p, X, cur, first_pass, fpos_first, L);
+      head = L.head; qlen = L.qlen; n_new = L.n_new; n_active = L.n_active; tick = L.tick; seq = L.seq; parity = L.parity; fatal = L.fatal;
+      epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited;
+      if (fatal) break;
+      PK_T(5)
+    }
+  }
+  __syncthreads();
+  for (int a = tid; a < n_active; a += blockDim.x) {
+    const int n = H.node(a);
+    for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + n] = H.q(r, a);
+  }
+  if (tid == 0) {
+    s.counters[0] = n_new;
+    s.counters[1] = qlen;
+    s.counters[2] = nodes_visited;
+    s.counters[3] = add_calls;
+    s.counters[4] = fatal;
+    s.counters[5] = add_calls;
+#ifdef KSCHED_PROFILE_PACK
+    for (int i = 0; i < 10; ++i) s.counters[8 + i] = pk_acc[i];
+#endif
+  }
+}
+
+// options_true = options_stored AND Fits(requests): one warp per new node (resources.Fits, utils/resources/resources.go:138).
+__global__ void finalize_options_kernel(DevCatalog c, const long long* counters, const int64_t* nn_req, const uint32_t* nn_req_present,
+                                        uint32_t* nn_opts, int max_new) {
+  const int n_new = (int)counters[0];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = warp; n < n_new; n += nwarps) {
+    const uint32_t qp = nn_req_present[n];
+    int rank = 0;
+    if (lane < c.n_res && ((qp >> lane) & 1)) rank = fit_rank(c.alloc_sorted, c.n_types, lane, nn_req[(size_t)lane * max_new + n]);
+    for (int w = lane; w < c.W32; w += 32) {
+      uint32_t sw = nn_opts[(size_t)w * max_new + n];
+      for (int r = 0; r < c.n_res; ++r) {
+        const int rk = __shfl_sync(0xffffffffu, rank, r);
+        if ((qp >> r) & 1) sw &= c.fitset[((size_t)r * (c.n_types + 1) + rk) * c.W32 + w];
+      }
+      nn_opts[(size_t)w * max_new + n] = sw;
+    }
+  }
+}
+
+}  // namespace

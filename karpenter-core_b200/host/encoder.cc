@@ -967,6 +967,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     row.meta = rs.meta;
     if (rs.meta >> KSCHED_META_HASGT_SHIFT) E.any_class_bounds = true;
     row.relax_next = specs[c].next;
+    row.reserved = (uint64_t)c;  // class index, so a row copied into the FFD-ordered pod matrix knows its class
     row.itype_req = KSCHED_NONE;
     row.hostname_req = KSCHED_NONE;
     if (!sp.itype.empty()) {
@@ -1091,6 +1092,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   pr.n_hostname_reqs = (int)E.hostname_reqs.size() / 2;
   pr.max_new_nodes = (int)NP;
   pr.write_feasibility = 0;
+  pr.count_nodes_visited = 1;
   if (E.any_class_bounds || E.any_template_bounds)
     unsupported("Gt/Lt requirements on pods / provisioners are not carried on the device path yet");
   return enc;

@@ -202,6 +202,7 @@ void kh_encoded_dims(const Encoded* E, long long* out) {
   out[6] = (long long)E->key_names.size(); out[7] = (long long)E->res_names.size(); out[8] = E->type_words;
   out[9] = (long long)E->class_topo.size();
 }
+void kh_encoded_set_count_visited(Encoded* E, int on) { E->problem.count_nodes_visited = on; }
 const ksched_catalog* kh_encoded_catalog(const Encoded* E) { return &E->catalog; }
 const ksched_problem* kh_encoded_problem(const Encoded* E) { return &E->problem; }
 int kh_gpu_load(Encoded* E) {
