@@ -240,6 +240,8 @@ int ksched_type_words(int n_types);
 int ksched_load_catalog(ksched_handle* h, const ksched_catalog* catalog);
 /* Column sharding for multi-GPU feasibility: this handle owns types [begin, end). Default: all. */
 int ksched_set_shard(ksched_handle* h, int rank, int world);
+/* The [begin, end) range of 32-bit column words rank owns out of n_words32 (pure host arithmetic, no device needed). */
+int ksched_shard_range(int n_words32, int rank, int world, int* begin, int* end);
 /* NCCL: rank 0 calls ksched_nccl_unique_id, the host distributes the 128 bytes, every rank calls ksched_nccl_init. */
 int ksched_nccl_unique_id(void* out128);
 int ksched_nccl_init(ksched_handle* h, const void* id128, int rank, int world);

@@ -28,7 +28,7 @@ KSCHED_ERR_OVERFLOW = -6
 # every symbol include/ksched.h declares
 ABI_SYMBOLS = [
     "ksched_abi_version", "ksched_device_count", "ksched_create", "ksched_destroy", "ksched_last_error",
-    "ksched_type_words", "ksched_load_catalog", "ksched_set_shard", "ksched_nccl_unique_id", "ksched_nccl_init",
+    "ksched_type_words", "ksched_load_catalog", "ksched_set_shard", "ksched_shard_range", "ksched_nccl_unique_id", "ksched_nccl_init",
     "ksched_solve", "ksched_upload", "ksched_run_resident", "ksched_download", "ksched_run_feasibility_only",
     "ksched_get_timings",
 ]
@@ -115,6 +115,7 @@ def lib():
     L.ksched_nccl_unique_id.argtypes = [C.c_void_p]
     L.ksched_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.ksched_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ksched_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -122,6 +123,15 @@ def lib():
 def device_count():
     n = lib().ksched_device_count()
     return max(n, 0)
+
+
+def shard_range(n_words32, rank, world):
+    """column words [begin, end) of the feasibility matrix that `rank` computes"""
+    b, e = C.c_int(), C.c_int()
+    rc = lib().ksched_shard_range(n_words32, rank, world, C.byref(b), C.byref(e))
+    if rc != KSCHED_OK:
+        raise KschedError(rc, "ksched_shard_range")
+    return b.value, e.value
 
 
 def _check(rc):

@@ -1,7 +1,6 @@
 """In-tree build of the native pieces (no JIT cache: the built .so files travel to the GPU box).
 
   csrc/ksched.cu + host/*.cc  ->  karpenter-core_b200/libksched.so   (C-ABI of include/ksched.h + host layer)
-  oracle/                     ->  oracle/_build/liboracle.so          (test infrastructure; `make -C oracle`)
 """
 import os
 import subprocess
@@ -45,16 +44,8 @@ def build_product(force=False, verbose_ptxas=False):
     return out
 
 
-def build_oracle(force=False):
-    if force:
-        _run(["make", "-C", ROOT / "oracle", "clean"])
-    _run(["make", "-C", ROOT / "oracle"])
-    return ROOT / "oracle" / "_build" / "liboracle.so"
-
-
 def build_all(force=False):
     build_product(force)
-    build_oracle(force)
 
 
 if __name__ == "__main__":

@@ -985,6 +985,14 @@ int ksched_set_shard(ksched_handle* h, int rank, int world) {
   return KSCHED_OK;
 }
 
+int ksched_shard_range(int n_words32, int rank, int world, int* begin, int* end) {
+  if (n_words32 < 0 || world < 1 || rank < 0 || rank >= world || !begin || !end) return KSCHED_ERR_INVALID;
+  const int per = (n_words32 + world - 1) / world;
+  *begin = std::min(n_words32, rank * per);
+  *end = std::min(n_words32, *begin + per);
+  return KSCHED_OK;
+}
+
 int ksched_nccl_unique_id(void* out128) {
   ncclUniqueId id;
   if (ncclGetUniqueId(&id) != ncclSuccess) return KSCHED_ERR_NCCL;
@@ -1180,9 +1188,7 @@ static void fill_k1(ksched_handle* h, K1Params& k1) {
   k1.best = h->d_best.ptr;
   const int W32 = h->cat.W32;
   if (h->world > 1) {
-    int per = (W32 + h->world - 1) / h->world;
-    k1.word_begin = std::min(W32, h->rank * per);
-    k1.word_end = std::min(W32, k1.word_begin + per);
+    ksched_shard_range(W32, h->rank, h->world, &k1.word_begin, &k1.word_end);
   } else {
     k1.word_begin = 0;
     k1.word_end = W32;

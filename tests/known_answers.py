@@ -1,0 +1,448 @@
+"""Known-answer scheduling cases restated from the reference's own test suites. Each case builds a
+problem with the reference's fixtures (tests/fixtures.py) and checks the ORDER-FREE invariant the Go test asserts
+(node count, chosen instance type, skew multiset, scheduled / not scheduled, same / different node).
+
+Used twice: on CPU against the oracle (pins the oracle), and on the GPU where the CUDA path must reproduce the
+oracle bit-for-bit AND satisfy the same invariant."""
+import fixtures as fx
+from fixtures import ARCH, CAPACITY_TYPE, HOSTNAME, INSTANCE_TYPE, ZONE, ZONES, pod, pods, problem, provisioner
+
+CASES = []
+
+
+def case(ref):
+    def deco(fn):
+        CASES.append((fn.__name__, ref, fn))
+        return fn
+    return deco
+
+
+def scheduled(res, i):
+    return res["assign"][i] >= 0
+
+
+def each_alone(pod_list, expect, **kw):
+    """the Go tests provision these pods in separate specs: one Solve per pod"""
+    prob = {"multi": [problem([p], **kw) for p in pod_list]}
+
+    def check(results):
+        got = [r["assign"][0] >= 0 for r in results]
+        assert got == expect, (got, expect)
+    return prob, check
+
+
+def new_nodes_used(res):
+    ne = len(res["existing"])
+    return sorted({a - ne for a in res["assign"] if a >= ne})
+
+
+def launched_type(prob, res, pod_index):
+    ne = len(res["existing"])
+    return fx.launch(prob, res["newNodes"][res["assign"][pod_index] - ne])[1]
+
+
+# ------------------------------------------------------------------ bin packing (scheduling/suite_test.go:1079-1340)
+@case("suite_test.go:1079-1089")
+def small_pod_smallest_instance():
+    prob = problem([pod({"memory": "100M"})])
+
+    def check(res):
+        assert scheduled(res, 0)
+        assert launched_type(prob, res, 0) == "small-instance-type"
+    return prob, check
+
+
+@case("suite_test.go:1101-1118")
+def five_small_pods_one_node():
+    prob = problem(pods(5, requests={"memory": "10M"}))
+
+    def check(res):
+        assert all(scheduled(res, i) for i in range(5))
+        assert len(set(res["assign"])) == 1
+        assert launched_type(prob, res, 0) == "small-instance-type"
+    return prob, check
+
+
+@case("suite_test.go:1119-1137")
+def forty_large_pods_twenty_nodes():
+    prob = problem(pods(40, requests={"memory": "1.8G"}, nodeSelector={ARCH: "amd64"}))
+
+    def check(res):
+        assert all(a >= 0 for a in res["assign"])
+        assert len(set(res["assign"])) == 20
+        assert {launched_type(prob, res, i) for i in range(40)} == {"default-instance-type"}
+    return prob, check
+
+
+@case("suite_test.go:1138-1169")
+def small_and_large_pods_pack_together():
+    prob = problem(pods(40, requests={"memory": "1.8G"}, nodeSelector={ARCH: "amd64"}) +
+                   pods(20, requests={"memory": "400M"}, nodeSelector={ARCH: "amd64"}))
+
+    def check(res):
+        assert all(a >= 0 for a in res["assign"])
+        assert len(set(res["assign"])) == 20
+        assert {launched_type(prob, res, i) for i in range(60)} == {"default-instance-type"}
+    return prob, check
+
+
+@case("suite_test.go:1170-1192")
+def pack_new_nodes_tightly():
+    prob = problem([pod({"cpu": "4.5"}), pod({"cpu": "1"})], instance_types=fx.fake_instance_types(5))
+
+    def check(res):
+        assert scheduled(res, 0) and scheduled(res, 1)
+        assert res["assign"][0] != res["assign"][1]
+        assert launched_type(prob, res, 0) != launched_type(prob, res, 1)
+    return prob, check
+
+
+@case("suite_test.go:1193-1204")
+def zero_quantity_unknown_resource():
+    prob = problem([{"name": "p", "uid": "p", "containers": [{"requests": {"foo.com/weird-resources": "0"}, "limits": {"foo.com/weird-resources": "0"}}]}])
+    return prob, lambda res: scheduled(res, 0) or (_ for _ in ()).throw(AssertionError("not scheduled"))
+
+
+@case("suite_test.go:1205-1214")
+def exceeds_every_instance_type():
+    prob = problem([pod({"memory": "2Ti"})])
+
+    def check(res):
+        assert not scheduled(res, 0)
+        assert res["newNodes"] == []
+    return prob, check
+
+
+@case("suite_test.go:1215-1235")
+def pod_count_limit_per_node():
+    prob = problem(pods(25, requests={"memory": "1m", "cpu": "1m"}, nodeSelector={ARCH: "amd64"}))
+
+    def check(res):
+        assert all(a >= 0 for a in res["assign"])
+        assert len(set(res["assign"])) == 5
+        assert {launched_type(prob, res, i) for i in range(25)} == {"small-instance-type"}
+    return prob, check
+
+
+@case("suite_test.go:1236-1274")
+def init_container_max_counts():
+    fits = {"name": "a", "uid": "a", "containers": [{"requests": {"memory": "1Gi", "cpu": "1"}}], "initContainers": [{"requests": {"memory": "2Gi", "cpu": "2"}}]}
+    too_big = {"name": "b", "uid": "b", "containers": [{"requests": {"memory": "1Gi"}}], "initContainers": [{"requests": {"memory": "1Ti"}}]}
+    prob = problem([fits, too_big])
+
+    def check(res):
+        assert scheduled(res, 0) and not scheduled(res, 1)
+        assert res["newNodes"][0]["requests"]["memory"] == 2 * 1024 ** 3 * 1000 + 0  # ceiling of init container
+    return prob, check
+
+
+# ------------------------------------------------------------------ custom labels (suite_test.go:401-551)
+def _req(key, op, *values):
+    return {"nodeAffinity": {"required": [[{"key": key, "operator": op, "values": list(values)}]]}}
+
+
+@case("suite_test.go:401-434")
+def undefined_custom_key_operators():
+    return each_alone([pod(**_req("test-key", "In", "test-value")), pod(**_req("test-key", "NotIn", "test-value")),
+                       pod(**_req("test-key", "Exists")), pod(**_req("test-key", "DoesNotExist"))], [False, True, False, True])
+
+
+@case("suite_test.go:443-506")
+def defined_custom_key_operators():
+    pr = provisioner(labels={"test-key": "test-value"})
+    return each_alone([pod(**_req("test-key", "In", "test-value")), pod(**_req("test-key", "NotIn", "test-value")),
+                       pod(**_req("test-key", "Exists")), pod(**_req("test-key", "DoesNotExist")),
+                       pod(**_req("test-key", "In", "another-value")), pod(**_req("test-key", "NotIn", "another-value"))],
+                      [True, False, True, False, False, True], provisioners=[pr])
+
+
+@case("suite_test.go:507-540")
+def compatible_pods_share_incompatible_split():
+    pr = provisioner(requirements=[{"key": "test-key", "operator": "In", "values": ["test-value", "another-value"]}])
+    same = problem([pod(**_req("test-key", "In", "test-value")), pod(**_req("test-key", "NotIn", "another-value"))], provisioners=[pr])
+    diff = problem([pod(**_req("test-key", "In", "test-value")), pod(**_req("test-key", "In", "another-value"))], provisioners=[pr])
+    prob = {"multi": [same, diff]}
+
+    def check(results):
+        a, b = results
+        assert a["assign"][0] == a["assign"][1] and a["assign"][0] >= 0
+        assert b["assign"][0] != b["assign"][1] and min(b["assign"]) >= 0
+    return prob, check
+
+
+@case("suite_test.go:115-202")
+def node_selectors_and_provisioner_constraints():
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-1"]}])
+    return each_alone([pod(), pod(nodeSelector={ZONE: "unknown"}), pod(nodeSelector={ZONE: "test-zone-2"}), pod(nodeSelector={ZONE: "test-zone-1"}),
+                       pod(nodeSelector={HOSTNAME: "red-node"})], [True, False, False, True, False], provisioners=[pr])
+
+
+# ------------------------------------------------------------------ preferential fallback (suite_test.go:555-675)
+@case("suite_test.go:557-572")
+def final_required_term_is_not_relaxed():
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-1"]},
+                                   {"key": INSTANCE_TYPE, "operator": "In", "values": ["default-instance-type"]}])
+    prob = problem([pod(nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["invalid"]}]]})], provisioners=[pr])
+    return prob, lambda res: (not scheduled(res, 0)) or (_ for _ in ()).throw(AssertionError("scheduled"))
+
+
+@case("suite_test.go:573-595")
+def relax_multiple_required_terms():
+    terms = [[{"key": ZONE, "operator": "In", "values": [z]}] for z in ("invalid", "invalid", "test-zone-1", "test-zone-2")]
+    prob = problem([pod(nodeAffinity={"required": terms})])
+
+    def check(res):
+        assert scheduled(res, 0)
+        assert res["relax"][0] == 2
+        assert res["newNodes"][0]["requirements"][ZONE] == "In [test-zone-1]"
+    return prob, check
+
+
+@case("suite_test.go:616-642")
+def relax_to_lighter_preferences():
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-1", "test-zone-2"]}])
+    pref = [{"weight": 100, "terms": [{"key": INSTANCE_TYPE, "operator": "In", "values": ["test-zone-3"]}]},
+            {"weight": 50, "terms": [{"key": ZONE, "operator": "In", "values": ["test-zone-2"]}]},
+            {"weight": 1, "terms": [{"key": ZONE, "operator": "In", "values": ["test-zone-1"]}]}]
+    prob = problem([pod(nodeAffinity={"preferred": pref})], provisioners=[pr])
+
+    def check(res):
+        assert scheduled(res, 0)
+        assert res["relax"][0] == 1
+        assert res["newNodes"][0]["requirements"][ZONE] == "In [test-zone-2]"
+    return prob, check
+
+
+# ------------------------------------------------------------------ instance selection (suite_test.go:676-862)
+@case("suite_test.go:688-707")
+def different_archs_different_instances():
+    prob = problem([pod(nodeSelector={ARCH: "amd64"}), pod(nodeSelector={ARCH: "arm64"})])
+
+    def check(res):
+        assert res["assign"][0] != res["assign"][1] and min(res["assign"]) >= 0
+        assert launched_type(prob, res, 1) == "arm-instance-type"
+    return prob, check
+
+
+@case("suite_test.go:708-726")
+def instance_type_node_affinity_excludes_types():
+    prob = problem([pod(nodeAffinity={"required": [[{"key": INSTANCE_TYPE, "operator": "In", "values": ["arm-instance-type"]}]]}),
+                    pod(nodeSelector={INSTANCE_TYPE: "small-instance-type"})])
+
+    def check(res):
+        assert min(res["assign"]) >= 0 and res["assign"][0] != res["assign"][1]
+        its = prob["instanceTypes"]
+        assert [its[i]["name"] for i in res["newNodes"][res["assign"][0]]["options"]] == ["arm-instance-type"]
+        assert [its[i]["name"] for i in res["newNodes"][res["assign"][1]]["options"]] == ["small-instance-type"]
+    return prob, check
+
+
+@case("suite_test.go:820-861")
+def resources_not_on_a_single_type():
+    prob = problem([pod({"fake.com/vendor-a": "1"}), pod({"fake.com/vendor-b": "1"}), pod({"fake.com/vendor-a": "1", "fake.com/vendor-b": "1"})])
+
+    def check(res):
+        assert scheduled(res, 0) and scheduled(res, 1) and not scheduled(res, 2)
+        assert res["assign"][0] != res["assign"][1]
+    return prob, check
+
+
+# ------------------------------------------------------------------ taints (topology_test.go:2209-2257, provisioning/suite_test.go:583-622)
+@case("topology_test.go:2209-2257")
+def taints_and_tolerations():
+    pr = provisioner(taints=[{"key": "test-key", "value": "test-value", "effect": "NoSchedule"}])
+    tol = lambda **kw: {"tolerations": [kw]}
+    return each_alone([pod(), pod(**tol(key="test-key", operator="Equal", value="test-value", effect="NoSchedule")),
+                       pod(**tol(key="test-key", operator="Exists")), pod(**tol(operator="Exists")),
+                       pod(**tol(key="test-key", operator="Equal", value="other", effect="NoSchedule")),
+                       pod(**tol(key="test-key", operator="Exists", effect="NoExecute"))], [False, True, True, True, False, False], provisioners=[pr])
+
+
+# ------------------------------------------------------------------ host ports (suite_test.go:923-1078)
+@case("suite_test.go:923-1078")
+def host_ports():
+    hp = lambda port, ip="", proto="TCP": {"ports": [{"hostPort": port, "hostIP": ip, "protocol": proto}], "requests": {"cpu": "10m"}}
+    same = problem([pod(**hp(80)), pod(**hp(80))])
+    wildcard = problem([pod(**hp(80, "1.2.3.4")), pod(**hp(80, "0.0.0.0"))])
+    proto = problem([pod(**hp(80, proto="TCP")), pod(**hp(80, proto="UDP"))])
+    ips = problem([pod(**hp(80, "1.2.3.4")), pod(**hp(80, "1.2.3.5"))])
+    prob = {"multi": [same, wildcard, proto, ips]}
+
+    def check(results):
+        a, b, c, d = results
+        assert a["assign"][0] != a["assign"][1]
+        assert b["assign"][0] != b["assign"][1]
+        assert c["assign"][0] == c["assign"][1]
+        assert d["assign"][0] == d["assign"][1]
+    return prob, check
+
+
+# ------------------------------------------------------------------ limits (provisioning/suite_test.go:237-358)
+@case("provisioning/suite_test.go:237-358")
+def provisioner_cpu_limits():
+    pr = provisioner(limits={"cpu": "20"})
+    # default-instance-type has 4 cpu: five nodes exhaust the limit pessimistically (subtractMax uses the largest option)
+    prob = problem(pods(12, requests={"cpu": "3"}, nodeSelector={ARCH: "amd64", INSTANCE_TYPE: "default-instance-type"}), provisioners=[pr])
+
+    def check(res):
+        assert sum(1 for a in res["assign"] if a >= 0) == 5
+        assert len(res["newNodes"]) == 5
+    return prob, check
+
+
+# ------------------------------------------------------------------ topology spread (topology_test.go:65-490)
+@case("topology_test.go:66-80")
+def zonal_spread_four_pods():
+    labels = {"test": "test"}
+    prob = problem(pods(4, labels=labels, topologySpreadConstraints=[fx.spread(ZONE, labels)]))
+    return prob, lambda res: _eq(fx.skew(prob, res, ZONE), [1, 1, 2])
+
+
+@case("topology_test.go:124-160")
+def zonal_spread_with_existing_pod_in_excluded_zone():
+    """provisioner limited to zone-1/2, one matching pod already runs in zone-3: at most two per zone fit max skew 1"""
+    labels = {"test": "test"}
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-1", "test-zone-2"]}])
+    existing = fx.state_node("node-z3", "small-instance-type", zone="test-zone-3", allocatable={"cpu": "1900m", "memory": "2038Mi", "pods": "5"},
+                             pods_=[pod({"cpu": "1.1"}, labels=labels, nodeName="node-z3")])
+    prob = problem(pods(6, requests={"cpu": "1.1"}, labels=labels, topologySpreadConstraints=[fx.spread(ZONE, labels)]), provisioners=[pr],
+                   nodes=[existing])
+
+    def check(res):
+        assert sum(1 for a in res["assign"] if a >= 0) == 4
+        assert fx.skew(prob, res, ZONE) == [2, 2]  # plus the existing pod in zone-3 -> (1, 2, 2)
+    return prob, check
+
+
+@case("topology_test.go:381-394")
+def hostname_spread_max_skew_one():
+    labels = {"test": "test"}
+    prob = problem(pods(4, labels=labels, topologySpreadConstraints=[fx.spread(HOSTNAME, labels)]))
+    return prob, lambda res: _eq(fx.skew(prob, res, HOSTNAME), [1, 1, 1, 1])
+
+
+@case("topology_test.go:396-410")
+def hostname_spread_max_skew_four():
+    labels = {"test": "test"}
+    prob = problem(pods(4, labels=labels, topologySpreadConstraints=[fx.spread(HOSTNAME, labels, max_skew=4)]))
+    return prob, lambda res: _eq(fx.skew(prob, res, HOSTNAME), [4])
+
+
+@case("topology_test.go:412-445")
+def two_deployments_hostname_spread_two_nodes():
+    a, b = {"app": "a"}, {"app": "b"}
+    prob = problem(pods(2, labels=a, topologySpreadConstraints=[fx.spread(HOSTNAME, a)]) +
+                   pods(2, labels=b, topologySpreadConstraints=[fx.spread(HOSTNAME, b)]))
+
+    def check(res):
+        assert min(res["assign"]) >= 0
+        assert len(set(res["assign"])) == 2
+    return prob, check
+
+
+@case("topology_test.go:341-352")
+def nil_selector_spread_schedules():
+    cons = [{"maxSkew": 1, "topologyKey": ZONE, "whenUnsatisfiable": "DoNotSchedule", "labelSelector": None}]
+    prob = problem(pods(2, labels={"test": "test"}, topologySpreadConstraints=cons))
+    return prob, lambda res: _eq([a >= 0 for a in res["assign"]], [True, True])
+
+
+@case("topology_test.go:ScheduleAnyway relaxation")
+def schedule_anyway_spread_is_relaxed():
+    labels = {"test": "test"}
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-1"]}])
+    prob = problem(pods(3, labels=labels, topologySpreadConstraints=[fx.spread(ZONE, labels, when="ScheduleAnyway")]), provisioners=[pr])
+
+    def check(res):
+        assert all(a >= 0 for a in res["assign"])
+    return prob, check
+
+
+# ------------------------------------------------------------------ pod affinity / anti-affinity (topology_test.go:1195-2207)
+@case("topology_test.go:1503-1530")
+def hostname_anti_affinity_splits_nodes():
+    labels = {"security": "s2"}
+    prob = problem(pods(3, labels=labels, podAntiAffinity={"required": [fx.affinity_term(HOSTNAME, labels)]}))
+
+    def check(res):
+        assert min(res["assign"]) >= 0 and len(set(res["assign"])) == 3
+    return prob, check
+
+
+@case("topology_test.go:1713-1744")
+def schroedinger_zonal_anti_affinity():
+    """A zone-unconstrained pod with required zonal anti-affinity blocks every zone it might land in."""
+    labels = {"security": "s2"}
+    anti = pod(labels=labels, podAntiAffinity={"required": [fx.affinity_term(ZONE, labels)]})
+    target = pod(labels=labels)
+    prob = problem([anti, target])
+
+    def check(res):
+        assert scheduled(res, 0)
+        assert not scheduled(res, 1)
+    return prob, check
+
+
+@case("topology_test.go:1195-1250")
+def self_affinity_hostname_same_node():
+    labels = {"security": "s2"}
+    prob = problem(pods(3, labels=labels, podAffinity={"required": [fx.affinity_term(HOSTNAME, labels)]}))
+
+    def check(res):
+        assert min(res["assign"]) >= 0 and len(set(res["assign"])) == 1
+    return prob, check
+
+
+@case("topology_test.go:1300-1340")
+def zonal_affinity_follows_target():
+    target_labels = {"security": "s2"}
+    target = pod(labels=target_labels, nodeSelector={ZONE: "test-zone-2"})
+    followers = pods(3, podAffinity={"required": [fx.affinity_term(ZONE, target_labels)]})
+    prob = problem([target] + followers)
+
+    def check(res):
+        assert min(res["assign"]) >= 0
+        ne = len(res["existing"])
+        for i in range(4):
+            assert res["newNodes"][res["assign"][i] - ne]["requirements"][ZONE] == "In [test-zone-2]"
+    return prob, check
+
+
+# ------------------------------------------------------------------ existing / in-flight nodes (suite_test.go:1343-1893)
+@case("suite_test.go:1344-1358")
+def reuse_existing_node():
+    node = fx.state_node("node-a")
+    prob = problem([pod({"cpu": "10m"})], nodes=[node])
+
+    def check(res):
+        assert res["assign"][0] == 0 and res["newNodes"] == []
+    return prob, check
+
+
+@case("suite_test.go:1405-1421")
+def second_node_when_existing_is_full():
+    node = fx.state_node("node-a", pods_=[pod({"cpu": "3"}, nodeName="node-a")])
+    prob = problem([pod({"cpu": "2"})], nodes=[node])
+
+    def check(res):
+        assert res["assign"][0] == 1 and len(res["newNodes"]) == 1
+    return prob, check
+
+
+@case("suite_test.go:1554-1578")
+def tainted_existing_node_is_skipped():
+    node = fx.state_node("node-a", taints=[{"key": "foo.com/taint", "value": "tainted", "effect": "NoSchedule"}])
+    prob = problem([pod({"cpu": "10m"})], nodes=[node])
+    return prob, lambda res: _eq(res["assign"], [1])
+
+
+@case("suite_test.go:1579-1609")
+def startup_taint_ignored_until_initialized():
+    taint = {"key": "foo.com/taint", "value": "tainted", "effect": "NoSchedule"}
+    node = fx.state_node("node-a", taints=[taint], startupTaints=[taint], initialized=False)
+    prob = problem([pod({"cpu": "10m"})], nodes=[node])
+    return prob, lambda res: _eq(res["assign"], [0])
+
+
+def _eq(a, b):
+    assert a == b, (a, b)

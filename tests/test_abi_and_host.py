@@ -1,0 +1,102 @@
+"""CPU-side checks of the C-ABI library and the host layer: every symbol include/ksched.h declares is exported,
+struct sizes match the header, the encoder produces the documented shapes, unsupported inputs fail LOUDLY, and without
+a GPU the solver refuses to run (there is no CPU fallback in the product)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+import fixtures as fx
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_header_symbol(pkg):
+    header = (ROOT / "include" / "ksched.h").read_text()
+    declared = set(re.findall(r"^(?:int|void|const char\*)\s+(ksched_\w+)\(", header, re.M))
+    assert declared == set(pkg.ABI_SYMBOLS), declared ^ set(pkg.ABI_SYMBOLS)
+    lib = pkg.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.ksched_abi_version() == 1
+    assert lib.ksched_type_words(1000) == 16 and lib.ksched_type_words(1) == 1 and lib.ksched_type_words(65) == 2
+
+
+def test_no_torch_types_in_the_abi():
+    header = (ROOT / "include" / "ksched.h").read_text()
+    assert "torch" not in header and "at::" not in header and "std::" not in header
+
+
+def test_shard_ranges_partition_the_columns(pkg):
+    for words in (1, 7, 32, 33, 250):
+        for world in (1, 2, 4, 8):
+            spans = [pkg.shard_range(words, r, world) for r in range(world)]
+            covered = [w for b, e in spans for w in range(b, e)]
+            assert covered == list(range(words)), (words, world, spans)
+
+
+def test_quantity_parser(pkg):
+    q = pkg.lib().kh_parse_quantity
+    assert q(b"100m") == 100 and q(b"1") == 1000 and q(b"1.8G") == 1_800_000_000_000 and q(b"4Gi") == 4 * 1024 ** 3 * 1000
+    assert q(b"10Mi") == 10 * 1024 ** 2 * 1000 and q(b"2Ti") == 2 * 1024 ** 4 * 1000 and q(b"4.5") == 4500 and q(b"1m") == 1
+    assert q(b"1u") == -2 ** 63  # sub-milli quantities are rejected, not rounded
+
+
+@pytest.mark.parametrize("config,pods,types,nodes", [(1, 100, 10, 0), (2, 500, 500, 0), (3, 500, 1000, 0), (4, 500, 1000, 0), (5, 200, 1000, 20)])
+def test_encoder_shapes(pkg, config, pods, types, nodes):
+    problem = pkg.Problem.synth(config, pods, types, 42, nodes)
+    rs = pkg.ResidentSolve(problem)
+    d = rs.dims
+    assert d["types"] == types and d["type_words"] == (types + 63) // 64
+    assert d["pods"] == (0 if config == 5 else pods)
+    assert d["existing"] == nodes
+    assert d["templates"] == (3 if config == 3 else 1)
+    assert d["keys"] <= 16 and d["resources"] == 3
+    if config == 2:
+        assert d["classes"] <= 30  # 5 cpu x 6 memory request classes
+    if config == 4:
+        assert d["groups"] > 0
+
+
+def test_duplicate_uids_are_rejected(pkg, oracle):
+    prob = fx.problem([fx.pod({"cpu": "1"}, uid="same"), fx.pod({"cpu": "1"}, uid="same")])
+    p = pkg.Problem.from_dict(prob)
+    with pytest.raises(pkg.KschedError):
+        pkg.ResidentSolve(p)
+    res = pkg.Result()
+    assert oracle.solve(p, res) != 0 and "unique UIDs" in res.error
+
+
+def test_unsupported_inputs_fail_loudly(pkg):
+    its = fx.default_instance_types()
+    its[0]["requirements"].append({"key": "custom", "operator": "NotIn", "values": ["x"]})
+    pr = fx.provisioner(labels={"custom": "y"})
+    with pytest.raises(pkg.KschedError) as e:
+        pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem([fx.pod({"cpu": "1"})], instance_types=its, provisioners=[pr])))
+    assert "unsupported" in str(e.value)
+    gt = fx.pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "integer", "operator": "Gt", "values": ["2"]}]]})
+    with pytest.raises(pkg.KschedError) as e:
+        pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem([gt])))
+    assert "unsupported" in str(e.value)
+
+
+def test_no_cpu_fallback(pkg):
+    """On a box without a CUDA device the product must refuse, not silently compute on the CPU."""
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    problem = pkg.Problem.synth(1, 100, 10, 42, 0)
+    with pytest.raises(pkg.KschedError) as e:
+        pkg.Scheduler(problem).solve()
+    assert e.value.code == pkg.KSCHED_ERR_NO_DEVICE
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    import subprocess
+    out = subprocess.run(["ldd", str(ROOT / "karpenter-core_b200" / "libksched.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    exts = ("*.cc", "*.cu", "*.cuh", "*.h", "*.py")
+    for path in [p for e in exts for p in (ROOT / "karpenter-core_b200").rglob(e)]:
+        text = path.read_text()
+        for needle in ('#include "../oracle', "#include \"oracle", "liboracle", "oracle_lib", "import oracle", "oracle_solve"):
+            assert needle not in text, (path, needle)
