@@ -768,12 +768,14 @@ __global__ void finalize_options_kernel(DevCatalog c, const long long* counters,
     const uint32_t qp = nn_req_present[n];
     int rank = 0;
     if (lane < c.n_res && ((qp >> lane) & 1)) rank = fit_rank(c.alloc_sorted, c.n_types, lane, nn_req[(size_t)lane * max_new + n]);
+    int ranks[KSCHED_MAX_RES];
+#pragma unroll
+    for (int r = 0; r < KSCHED_MAX_RES; ++r) ranks[r] = __shfl_sync(0xffffffffu, rank, r);  // every lane takes part
     for (int w = lane; w < c.W32; w += 32) {
       uint32_t sw = nn_opts[(size_t)w * max_new + n];
-      for (int r = 0; r < c.n_res; ++r) {
-        const int rk = __shfl_sync(0xffffffffu, rank, r);
-        if ((qp >> r) & 1) sw &= c.fitset[((size_t)r * (c.n_types + 1) + rk) * c.W32 + w];
-      }
+#pragma unroll
+      for (int r = 0; r < KSCHED_MAX_RES; ++r)
+        if (r < c.n_res && ((qp >> r) & 1)) sw &= c.fitset[((size_t)r * (c.n_types + 1) + ranks[r]) * c.W32 + w];
       nn_opts[(size_t)w * max_new + n] = sw;
     }
   }
