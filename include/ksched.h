@@ -147,7 +147,8 @@ typedef struct ksched_topo_group {
   uint8_t type;      /* 0 spread, 1 pod affinity, 2 pod anti-affinity */
   uint8_t key;       /* mask key index or KSCHED_KEY_HOSTNAME */
   uint8_t inverse;   /* lives in Topology.inverseTopologies (topology.go:47) */
-  uint8_t pad;
+  uint8_t dormant;   /* created only by Topology.Update after a relaxation (topology.go:86-117): it records nothing and
+                        knows no hostname registered before the first pod that owns it is relaxed */
   int32_t max_skew;
   uint32_t filter_begin, filter_end; /* TopologyNodeFilter terms in problem.filter_terms; empty = always matches */
   uint64_t registered;               /* mask-key groups: domains the group knows (universe + recorded) */

@@ -345,6 +345,8 @@ struct PackState {
   uint16_t* grp_host;                // [n_hostgroups][n_existing+max_new]
   const int32_t* grp_host_row;       // [n_groups] row in grp_host or -1
   int32_t* grp_host_total;           // [n_groups] schedulable-slot domains with count > 0 (+ extra_nonzero_domains)
+  uint8_t* grp_active;               // [n_groups] 0 while a relaxation-created group does not exist yet (topology.go:86-117)
+  int32_t* grp_min_slot;             // [n_groups] hostname slots below this were never Register()ed with the group
   int64_t* remaining;                // [V][8] provisioner limits
   // outputs / counters: [0]=n_new [1]=n_unscheduled [2]=nodes_visited [3]=add_calls [4]=error [5]=steps
   long long* counters;
@@ -446,6 +448,8 @@ __device__ bool topo_hostname_ok(const PackState& s, const PodTopo& pt, int j, i
   const int row = s.grp_host_row[gi];
   const int stride = s.n_existing + s.max_new;
   const int32_t cnt = s.grp_host[(size_t)row * stride + slot];
+  // a group created by a later Topology.Update only knows hostnames registered after that, plus those it counted pods on
+  if (slot < s.grp_min_slot[gi] && !(slot < s.n_existing && cnt > 0)) return false;
   if (g.type == 0) {  // spread, min is 0 for hostname (topologygroup.go:186-188); candidate = the node's own hostname
     int64_t c2 = (int64_t)cnt + ((pt.flags[j] & KSCHED_TOPO_SELECTS) ? 1 : 0);
     return c2 <= (int64_t)g.max_skew;
@@ -690,6 +694,7 @@ __device__ void topo_record(const DevCatalog& c, const PackState& s, const ksche
     const ksched_class_topo ct = s.class_topo[e];
     const int gi = (int)ct.group;
     const ksched_topo_group& g = s.groups[gi];
+    if (!s.grp_active[gi]) continue;  // the group does not exist yet
     bool rec = false, all_values = false;
     if (ct.flags & KSCHED_TOPO_RECORDS) {
       if (filter_matches(c, s, g, vals, meta, stride, idx)) { rec = true; all_values = (g.type == 2); }
@@ -786,7 +791,8 @@ struct ksched_handle {
   DevBuf<long long> d_ov_q, d_ov_bound, d_fc_bound;
   DevBuf<unsigned long long> d_ov_key;
   DevBuf<unsigned short> d_ov_flags;
-  DevBuf<uint8_t> d_fc_state, d_fc_dom;
+  DevBuf<uint8_t> d_fc_state, d_fc_dom, d_grp_active, d_grp_active0;
+  DevBuf<int32_t> d_grp_min_slot;
   DevBuf<uint32_t> d_fc_opts;
   int count_visited = 1;
   DevBuf<uint32_t> d_ex_req_present, d_ex_req_present0, d_ex_avail_present, d_ex_taintset, d_ex_itype, d_nn_req_present, d_nn_opts;
@@ -1110,6 +1116,11 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
       }
       host_total[g] = total;
     }
+    std::vector<uint8_t> active(std::max(NG, 1), 1);
+    for (int g = 0; g < NG; ++g) active[g] = pb->groups[g].dormant ? 0 : 1;
+    CUDA_TRY(h, upload_vec(h, h->d_grp_active0, active));
+    CUDA_TRY(h, h->d_grp_active.ensure(std::max(NG, 1)));
+    CUDA_TRY(h, h->d_grp_min_slot.ensure(std::max(NG, 1)));
     CUDA_TRY(h, upload_vec(h, h->d_grp_host_row, host_row));
     CUDA_TRY(h, upload_vec(h, h->d_grp_host_total0, host_total));
     CUDA_TRY(h, upload_vec(h, h->d_grp_cnt0, cnt));
@@ -1221,6 +1232,8 @@ static int reset_state(ksched_handle* h) {
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_cnt.ptr, h->d_grp_cnt0.ptr, (size_t)NG * 64 * 4, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_registered.ptr, h->d_grp_registered0.ptr, (size_t)NG * 8, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host_total.ptr, h->d_grp_host_total0.ptr, (size_t)NG * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_active.ptr, h->d_grp_active0.ptr, (size_t)NG, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_grp_min_slot.ptr, 0, (size_t)NG * 4, h->stream));
   const size_t hs = (size_t)std::max(h->n_hostgroups, 1) * ((size_t)h->n_existing + h->max_new);
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host.ptr, h->d_grp_host0.ptr, hs * 2, cudaMemcpyDeviceToDevice, h->stream));
   std::vector<int64_t> rem((size_t)h->cat.n_templates * KSCHED_MAX_RES);
@@ -1256,6 +1269,7 @@ static int run_pack(ksched_handle* h) {
   s.count_visited = h->count_visited;
   s.grp_cnt = h->d_grp_cnt.ptr; s.grp_registered = h->d_grp_registered.ptr; s.grp_host = h->d_grp_host.ptr;
   s.grp_host_row = h->d_grp_host_row.ptr; s.grp_host_total = h->d_grp_host_total.ptr; s.remaining = h->d_remaining.ptr;
+  s.grp_active = h->d_grp_active.ptr; s.grp_min_slot = h->d_grp_min_slot.ptr;
   s.counters = h->d_counters.ptr;
   const size_t alloc_bytes = (size_t)h->cat.n_res * h->cat.n_types * sizeof(int64_t);
   s.alloc_in_smem = alloc_bytes <= (size_t)(64 << 10) ? 1 : 0;

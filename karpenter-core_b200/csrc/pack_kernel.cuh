@@ -571,6 +571,15 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         if (nx != KSCHED_NONE) {
           s.pod_class[pod] = nx;
           s.relax_level[pod] += 1;
+          // Topology.Update(pod): groups that only the relaxed spec owns come into existence now
+          const ksched_pod_row& nrow = s.classes[nx];
+          for (uint32_t e = nrow.topo_begin; e < nrow.topo_end; ++e) {
+            const ksched_class_topo ct = s.class_topo[e];
+            if ((ct.flags & KSCHED_TOPO_CONSTRAINS) && !s.grp_active[ct.group]) {
+              s.grp_active[ct.group] = 1;
+              s.grp_min_slot[ct.group] = NE + n_new;
+            }
+          }
         } else {
           s.last_len[pod] = qlen + 1;
           s.last_epoch[pod] = epoch;

@@ -376,6 +376,7 @@ struct Group {
   std::vector<std::pair<ksched_reqset, ksched_bounds>> filter;  // TopologyNodeFilter terms
   std::string filter_key;
   bool inverse = false;
+  bool dormant = false;
   std::map<std::string, int32_t> counts;  // domain string -> count (countDomains / inverse Record)
   std::set<size_t> owner_specs;           // indices into the spec table (classes)
   bool selects(const Pod& p) const {      // topologygroup.go:246-252
@@ -901,9 +902,22 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
         }
       }
       for (auto& g : spec_groups(p)) {
-        auto it = group_of.find(g.hash());
-        if (it == group_of.end()) unsupported("relaxation creates a new topology group (node filter changes)");
-        groups[it->second].owner_specs.insert(s);
+        std::string h = g.hash();
+        auto it = group_of.find(h);
+        size_t gi;
+        if (it == group_of.end()) {
+          // Topology.Update creates this group when the pod is relaxed (e.g. the node filter of a spread constraint
+          // changes with the required node-affinity terms): counts come from the cluster at that moment, which is the
+          // same static state countDomains sees at the start of the solve.
+          gi = groups.size();
+          group_of[h] = gi;
+          g.dormant = true;
+          count_domains(g);
+          groups.push_back(std::move(g));
+        } else {
+          gi = it->second;
+        }
+        groups[gi].owner_specs.insert(s);
       }
     }
   }
@@ -917,6 +931,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     std::memset(&o, 0, sizeof o);
     o.type = (uint8_t)G.type;
     o.inverse = G.inverse;
+    o.dormant = G.dormant;
     o.max_skew = G.max_skew;
     o.filter_begin = (uint32_t)E.filter_terms.size();
     for (auto& f : G.filter) {

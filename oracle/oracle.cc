@@ -672,12 +672,12 @@ struct Scheduler {
       if (node_add(new_nodes_storage[idx], pi)) return true;
     }
     for (size_t v = 0; v < templates.size(); ++v) {
+      ++nodes_visited;  // one per template considered (statistic defined by this repo, see Result::nodes_visited)
       std::vector<const IType*> types = template_types[v];
       if (has_remaining[v]) {
         types = filter_by_remaining(template_types[v], remaining[v]);
         if (types.empty()) continue;
       }
-      ++nodes_visited;
       // NewNode node.go:44-60
       SchedNode n;
       n.tmpl = (int)v;

@@ -1,0 +1,32 @@
+"""GPU differential fuzz: random problems mixing every feature; the CUDA path must equal the oracle bit-for-bit, or refuse
+loudly with KSCHED_ERR_UNSUPPORTED (never a silently different answer)."""
+import pytest
+
+from fuzz_problems import random_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", range(300))
+def test_gpu_equals_oracle_on_random_problem(pkg, oracle, seed):
+    prob = random_problem(seed)
+    problem = pkg.Problem.from_dict(prob)
+    want = pkg.Result()
+    assert oracle.solve(problem, want) == 0, want.error
+    try:
+        got = pkg.Scheduler(problem).solve()
+    except pkg.KschedError as e:
+        if e.code == pkg.KSCHED_ERR_UNSUPPORTED:
+            pytest.skip(f"refused loudly: {e}")
+        raise
+    g, w = got.to_dict(), want.to_dict()
+    assert g["assign"] == w["assign"]
+    assert g["relax"] == w["relax"]
+    assert g["existing"] == w["existing"]
+    assert len(g["newNodes"]) == len(w["newNodes"])
+    for a, b in zip(g["newNodes"], w["newNodes"]):
+        assert a["provisioner"] == b["provisioner"] and a["pods"] == b["pods"]
+        assert a["options"] == b["options"]
+        assert a["requests"] == b["requests"]
+        assert a["requirements"] == {k: v for k, v in b["requirements"].items() if k != "node.kubernetes.io/instance-type"}
+    assert got.nodes_visited == want.nodes_visited
