@@ -90,6 +90,7 @@ def lib():
     L.kh_result_to_json.restype = C.c_longlong
     L.kh_result_to_json.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     L.kh_set_device.argtypes = [C.c_int]
+    L.kh_set_count_visited.argtypes = [C.c_int]
     L.kh_handle.restype = C.c_void_p
     L.kh_scheduler_solve.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]
     L.kh_encode.restype = C.c_void_p
@@ -246,7 +247,10 @@ class Scheduler:
     def __init__(self, problem: Problem):
         self.problem = problem
 
-    def solve(self, candidates=()):
+    def solve(self, candidates=(), count_visited=True):
+        """count_visited=False is the production setting: the exact nodes_visited statistic is dropped and the pack
+        kernel may use its steady-state paths (register-resident warp loop, block-wide fast path)."""
+        lib().kh_set_count_visited(int(count_visited))
         res = Result()
         arr, n = _cand_array(list(candidates))
         rc = lib().kh_scheduler_solve(self.problem.ptr, arr, n, res.ptr)

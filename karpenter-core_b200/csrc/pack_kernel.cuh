@@ -591,6 +591,114 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
     }
   }
 
+// ---- register-resident steady state -----------------------------------------------------------------------------
+// When at most 32 in-flight nodes are open, warp 0 keeps one node per lane IN REGISTERS and places consecutive
+// "plain" pods (no requirement can change, no host ports) without touching shared or global node state: R compares per
+// lane, a 2-REDUX argmin, the winning lane updates its own registers. The other warps wait at a block barrier.
+struct WarpIO {
+  int qi, head, qlen, tick, seq, n_active;
+  long long add_calls;
+};
+
+__device__ __forceinline__ bool plain_pod_regs(const PodRegs& r) {
+  return ((r.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0 && r.itype == KSCHED_NONE && r.hostname == KSCHED_NONE && r.topo_begin == r.topo_end;
+}
+
+__device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, const uint32_t* tmpl_taintset, WarpIO* io) {
+  const PackState& s = p.st;
+  const int lane = threadIdx.x & 31;
+  const int NE = s.n_existing, MAXN = s.max_new;
+  const int RH = p.cat.n_res < kHotRes ? p.cat.n_res : kHotRes;
+  const int qcap = s.n_pods + 1;
+  int qi = io->qi, head = io->head, qlen = io->qlen, tick = io->tick, seq = io->seq;
+  long long add_calls = io->add_calls;
+  const int n_active = io->n_active;
+  // lane state
+  bool live = lane < n_active, dirty = false;
+  unsigned long long key = live ? hs->key[lane] : ~0ull;
+  long long q[kHotRes], b[kHotRes];
+#pragma unroll
+  for (int r = 0; r < kHotRes; ++r) { q[r] = live ? hs->q[r][lane] : 0; b[r] = live ? hs->bound[r][lane] : 0; }
+  const int node = live ? hs->node[lane] : 0;
+  unsigned short fl = live ? hs->flags[lane] : 0;
+  const bool tol_dep = true;
+  (void)tol_dep;
+  const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
+  PodRegs cur = load_pod_regs(ffd_rows + qi, s.order[qi]);
+  PodRegs nxt = cur;
+  if (qi + 1 < s.n_pods) nxt = load_pod_regs(ffd_rows + qi + 1, s.order[qi + 1]);
+  long long min_req[kHotRes];
+#pragma unroll
+  for (int r = 0; r < kHotRes; ++r) min_req[r] = r < RH ? s.min_req[r] : 0;
+
+  while (true) {
+    if (!plain_pod_regs(cur) || cur.hpc || cur.hpe || (cur.res >> kHotRes)) break;  // this pod takes the block-wide path
+    bool ok = live && ((cur.tol >> tmpl_taintset[fl >> 8]) & 1);
+    const uint32_t qp = ((fl >> 1) & 0xF) | cur.res;
+    long long nq[kHotRes];
+#pragma unroll
+    for (int r = 0; r < kHotRes; ++r) {
+      nq[r] = q[r] + cur.req[r];
+      if (r < RH && ((qp >> r) & 1)) ok = ok && nq[r] <= b[r];
+    }
+    if (__any_sync(0xffffffffu, ok && !(fl & 1))) break;  // a candidate without a dominant option needs the type bitsets
+    const unsigned long long wkey = warp_min_u64(ok ? key : ~0ull);
+    if (wkey == ~0ull) break;  // nobody accepts: a new node has to be opened
+    if (ok && key == wkey) {
+#pragma unroll
+      for (int r = 0; r < kHotRes; ++r) q[r] = nq[r];
+      const int count = (int)(wkey >> 32) + 1;
+      key = order_key(count, -(tick + 1));
+      if ((cur.res & 0xF) & ~((fl >> 1) & 0xF)) {
+        s.nn_req_present[node] |= cur.res;
+        fl |= (unsigned short)((cur.res & 0xF) << 1);
+      }
+      dirty = true;
+      s.assign[cur.pod] = NE + node;
+      s.place_seq[cur.pod] = seq;
+      bool closed = false;
+#pragma unroll
+      for (int r = 0; r < kHotRes; ++r)
+        if (min_req[r] > 0 && q[r] + min_req[r] > b[r]) closed = true;
+      if (closed) {  // the node leaves the active set
+        for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + node] = q[r];
+        s.nn_count[node] = count;
+        s.nn_tb[node] = -(tick + 1);
+        live = false;
+        dirty = false;
+        key = ~0ull;
+      }
+    }
+    ++tick; ++seq; ++qi; ++add_calls;
+    head = head + 1 == qcap ? 0 : head + 1;
+    --qlen;
+    if (qi >= s.n_pods || qlen == 0) break;
+    cur = nxt;
+    if (qi + 1 < s.n_pods) nxt = load_pod_regs(ffd_rows + qi + 1, s.order[qi + 1]);
+    if (lane < 2 && qi + 24 < s.n_pods) prefetch_l2(reinterpret_cast<const char*>(ffd_rows + qi + 24) + lane * 128);
+    if (lane == 2 && (qi & 31) == 0 && qi + 96 < s.n_pods) prefetch_l2(s.order + qi + 96);
+  }
+  // write the lanes back, compacted
+  const unsigned livemask = __ballot_sync(0xffffffffu, live);
+  const int slot = __popc(livemask & ((1u << lane) - 1));
+  __syncwarp();
+  if (live) {
+    hs->key[slot] = key;
+#pragma unroll
+    for (int r = 0; r < kHotRes; ++r) { hs->q[r][slot] = q[r]; hs->bound[r][slot] = b[r]; }
+    hs->node[slot] = node;
+    hs->flags[slot] = fl;
+    if (dirty) {
+      s.nn_count[node] = (int)(key >> 32);
+      s.nn_tb[node] = (int)((unsigned)key ^ 0x80000000u);
+    }
+  }
+  if (lane == 0) {
+    io->qi = qi; io->head = head; io->qlen = qlen; io->tick = tick; io->seq = seq; io->n_active = __popc(livemask);
+    io->add_calls = add_calls;
+  }
+}
+
 #ifdef KSCHED_PROFILE_PACK
 #define PK_T(i) { long long _now = clock64(); pk_acc[i] += _now - pk_last; pk_last = _now; }
 #else
@@ -621,6 +729,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
   __shared__ unsigned long long red[2][32];
   __shared__ StepShared sh;
   __shared__ uint32_t tmpl_taintset[KSCHED_MAX_TEMPLATES];
+  __shared__ WarpIO wio;
   if (tid < c.n_templates) tmpl_taintset[tid] = c.templates[tid].taintset;
   if (tid == 0) pt.n = 0;
   const StepCtx X{&pt, &fresh_t, &fresh_x, red, &sh, tmpl_taintset, H, s.alloc_in_smem ? sm_alloc : c.alloc_sorted};
@@ -651,6 +760,18 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
   const bool fast_allowed = NE == 0 && !s.count_visited;
 
   while (qlen > 0) {
+    // ---- register-resident mode (see warp_resident_loop): entered when the next pod is plain and <= 32 nodes are open
+    if (fast_allowed && qi < s.n_pods && n_active > 0 && n_active <= 32 && plain_pod_regs(nxt) && !nxt.hpc && !nxt.hpe) {
+      __syncthreads();
+      if (tid == 0) { wio.qi = qi; wio.head = head; wio.qlen = qlen; wio.tick = tick; wio.seq = seq; wio.n_active = n_active; wio.add_calls = add_calls; }
+      __syncthreads();
+      if (tid < 32) warp_resident_loop(p, hs, tmpl_taintset, &wio);
+      __syncthreads();
+      qi = wio.qi; head = wio.head; qlen = wio.qlen; tick = wio.tick; seq = wio.seq; n_active = wio.n_active; add_calls = wio.add_calls;
+      if (qlen == 0) break;
+      if (qi < s.n_pods) nxt = load_pod_regs(ffd_rows + qi, s.order[qi]);
+      // the pod the warp loop stopped at (new node needed, non-plain pod, end of the first pass) takes the block-wide path
+    }
     PodRegs cur;
     const bool first_pass = qi < s.n_pods;
     if (first_pass) {

@@ -28,6 +28,7 @@ namespace {
 thread_local std::string g_err;
 ksched_handle* g_handle = nullptr;
 int g_device = 0;
+int g_count_visited = 1;  // exact nodes_visited statistic; switches the pack kernel's steady-state paths off
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -165,6 +166,7 @@ int kh_set_device(int ordinal) {
   g_device = ordinal;
   return KSCHED_OK;
 }
+void kh_set_count_visited(int on) { g_count_visited = on; }
 ksched_handle* kh_handle() { return ensure_handle() == KSCHED_OK ? g_handle : nullptr; }
 
 // Scheduler.Solve through the C-ABI with host buffers (upload + kernels + download inside the call).
@@ -173,6 +175,7 @@ int kh_scheduler_solve(const Problem* P, const int* candidates, int ncand, Resul
   try {
     std::vector<int> c(candidates, candidates + ncand);
     auto E = khost::encode(*P, c);
+    E->problem.count_nodes_visited = g_count_visited;
     ResultBuffers B;
     int rc = solve_encoded(*E, B, false);
     if (rc != KSCHED_OK) { out->error = g_err; return rc; }
@@ -300,6 +303,7 @@ int kh_consolidate(const Problem* P, int* out4, int* options, int options_cap, i
       std::vector<int> nodes;
       for (int i = 0; i < count; ++i) nodes.push_back(cands[i].node);
       auto E = khost::encode(*P, nodes);
+      E->problem.count_nodes_visited = g_count_visited;
       ResultBuffers B;
       int rc = solve_encoded(*E, B, false);
       if (rc != KSCHED_OK) throw std::runtime_error(g_err);

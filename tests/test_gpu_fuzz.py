@@ -30,3 +30,6 @@ def test_gpu_equals_oracle_on_random_problem(pkg, oracle, seed):
         assert a["requests"] == b["requests"]
         assert a["requirements"] == {k: v for k, v in b["requirements"].items() if k != "node.kubernetes.io/instance-type"}
     assert got.nodes_visited == want.nodes_visited
+    fast = pkg.Scheduler(problem).solve(count_visited=False).to_dict()  # production setting: steady-state kernel paths
+    assert fast["assign"] == w["assign"] and fast["relax"] == w["relax"] and fast["existing"] == w["existing"]
+    assert fast["newNodes"] == g["newNodes"]

@@ -12,6 +12,8 @@ SMALL = [
     (1, 100, 10, 0, 42),
     (2, 1000, 500, 0, 42),
     (2, 3000, 500, 0, 7),
+    (2, 10000, 500, 0, 42),
+    (2, 6000, 40, 0, 5),
     (3, 1500, 1000, 0, 42),
     (3, 1000, 1000, 0, 3),
     (4, 1500, 1000, 0, 42),
@@ -37,6 +39,12 @@ def _compare(pkg, oracle, problem, candidates=()):
     assert g["existing"] == w["existing"]
     assert got.nodes_visited == want.nodes_visited
     assert got.add_calls == want.add_calls
+    # production setting (no nodes_visited statistic): the steady-state kernel paths must give the identical result
+    fast = pkg.Scheduler(problem).solve(candidates, count_visited=False)
+    f = fast.to_dict()
+    assert f["assign"] == w["assign"] and f["relax"] == w["relax"] and f["existing"] == w["existing"]
+    for a, b in zip(f["newNodes"], g["newNodes"]):
+        assert a == b
     return got, want
 
 
