@@ -304,6 +304,12 @@ def main():
                                  "note": "bytes = P*256 + C*256 + P*C/8 (SURVEY 8d K1), cold L2"},
         "clocks": clocks,
     }
+    if rank == 0 and world > 1 and not args.no_cpu_baseline:
+        # parity of the sharded path (K1 column shards + allreduce, pack replicated) against the oracle on the same inputs
+        import oracle_lib
+        want = pkg.Result()
+        oracle_lib.load().solve(problem, want)
+        line["config"]["parity_vs_oracle"] = bool((want.assign == res.assign).all() and want.num_new_nodes == res.num_new_nodes)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle_lib
         oracle = oracle_lib.load()

@@ -72,6 +72,7 @@ struct DevCatalog {
   const uint32_t* fitset;            // [n_res][n_types+1][W32]  rank -> types with alloc >= alloc_sorted[rank]
   const int32_t* perm_desc;          // [n_res][n_types] types by descending allocatable
   const int64_t* alloc_rt;           // [n_res][n_types] allocatable, resource-major
+  const uint32_t* domset;            // [n_types][W32] types whose allocatable vector (first 4 resources) is dominated by the row's type
   int zone_key, ct_key;
 };
 
@@ -166,25 +167,81 @@ struct K1Params {
   uint32_t* F;                 // [n_pods][n_templates][W32]
   unsigned long long* best;    // [n_pods]
   int word_begin, word_end;    // column shard (u32 words) this device computes
+  int alloc_in_smem;           // the sorted allocatable arrays fit in the CTA's shared memory
 };
 
-__global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
-  const DevCatalog& c = p.cat;
+constexpr int kK1Threads = 512;
+constexpr int kK1Cache = 16;  // per-lane words of the previous row's result kept for identical consecutive rows
+
+// Shared-memory staging: the small tables every row evaluation walks with DEPENDENT loads (templates, key info, the
+// value->row maps, the sorted allocatable arrays of the Fits binary search) are copied once per CTA; the wide column
+// bitsets (valset / fitset / member / offset) stay in global memory and are read one coalesced word per lane.
+// Each warp owns a CONTIGUOUS chunk of the FFD-ordered pod-row matrix: consecutive rows are very often identical in
+// every field that matters to feasibility (same deployment), and then the previous result is written out again.
+__global__ void __launch_bounds__(kK1Threads) feasibility_kernel(K1Params p) {
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+  DevCatalog c = p.cat;
+  const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
+  {
+    unsigned char* ptr = k1_smem;
+    ksched_template* s_tmpl = reinterpret_cast<ksched_template*>(ptr); ptr += sizeof(ksched_template) * V;
+    ksched_keyinfo* s_keys = reinterpret_cast<ksched_keyinfo*>(ptr); ptr += sizeof(ksched_keyinfo) * KSCHED_MAX_KEYS;
+    int64_t* s_alloc = reinterpret_cast<int64_t*>(ptr); ptr += p.alloc_in_smem ? sizeof(int64_t) * R * T : 0;
+    int16_t* s_valrow = reinterpret_cast<int16_t*>(ptr); ptr += sizeof(int16_t) * KSCHED_MAX_KEYS * 64;
+    int16_t* s_offrow = reinterpret_cast<int16_t*>(ptr);
+    const uint32_t* gt = reinterpret_cast<const uint32_t*>(c.templates);
+    uint32_t* st = reinterpret_cast<uint32_t*>(s_tmpl);
+    for (int i = threadIdx.x; i < (int)(sizeof(ksched_template) * V / 4); i += blockDim.x) st[i] = gt[i];
+    const uint32_t* gk = reinterpret_cast<const uint32_t*>(c.keys);
+    uint32_t* sk = reinterpret_cast<uint32_t*>(s_keys);
+    for (int i = threadIdx.x; i < (int)(sizeof(ksched_keyinfo) * NK / 4); i += blockDim.x) sk[i] = gk[i];
+    if (p.alloc_in_smem)
+      for (int i = threadIdx.x; i < R * T; i += blockDim.x) s_alloc[i] = c.alloc_sorted[i];
+    for (int i = threadIdx.x; i < NK * 64; i += blockDim.x) s_valrow[i] = c.valrow[i];
+    if (threadIdx.x < 64) s_offrow[threadIdx.x] = c.offrow[threadIdx.x];
+    c.templates = s_tmpl;
+    c.keys = s_keys;
+    if (p.alloc_in_smem) c.alloc_sorted = s_alloc;
+    c.valrow = s_valrow;
+    c.offrow = s_offrow;
+  }
+  __syncthreads();
+
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int V = c.n_templates, W32 = c.W32;
+  const int chunk = (p.n_pods + nwarps - 1) / nwarps;
+  const int j0 = warp * chunk, j1 = min(p.n_pods, j0 + chunk);
+  const int wpl = (W32 + 31) >> 5;  // column words per lane
+  const bool cacheable = V * wpl <= kK1Cache;
+  // fields of the row that feasibility depends on (requests, requirement masks, meta, tolerations, res_present, itype_req)
+  const uint64_t cmp_mask = lane <= 25 ? ~0ull : ((lane == 28 || lane == 29) ? 0xFFFFFFFFull : 0ull);
+  uint32_t cache[kK1Cache];
+  unsigned long long best_prev = kNoBest;
+  uint64_t prev_word = 0;
+  bool have_prev = false;
+
   uint64_t next_word = 0;
-  if (warp < p.n_pods) next_word = __ldg(p.rows + (size_t)warp * KSCHED_ROW_WORDS + lane);
-  for (int j = warp; j < p.n_pods; j += nwarps) {
+  if (j0 < j1) next_word = __ldg(p.rows + (size_t)j0 * KSCHED_ROW_WORDS + lane);
+  for (int j = j0; j < j1; ++j) {
     const uint64_t word = next_word;  // lane l holds u64 word l of the 256-byte row
-    if (j + nwarps < p.n_pods) next_word = __ldg(p.rows + (size_t)(j + nwarps) * KSCHED_ROW_WORDS + lane);
+    if (j + 1 < j1) next_word = __ldg(p.rows + (size_t)(j + 1) * KSCHED_ROW_WORDS + lane);
+    const bool same = have_prev && cacheable && __all_sync(0xffffffffu, ((word ^ prev_word) & cmp_mask) == 0);
+    if (same) {
+      for (int v = 0; v < V; ++v)
+        for (int wi = 0; wi < wpl; ++wi) {
+          const int w = wi * 32 + lane;
+          if (w < W32 && w >= p.word_begin && w < p.word_end) p.F[((size_t)j * V + v) * W32 + w] = cache[v * wpl + wi];
+        }
+      if (lane == 0) p.best[j] = best_prev;
+      continue;
+    }
+    prev_word = word;
+    have_prev = true;
     const uint64_t meta = __shfl_sync(0xffffffffu, word, 24);
     const uint64_t tolerated = __shfl_sync(0xffffffffu, word, 25);
-    const uint64_t w28 = __shfl_sync(0xffffffffu, word, 28);
-    const uint64_t w29 = __shfl_sync(0xffffffffu, word, 29);
-    const uint32_t pod_res_present = (uint32_t)w28;
-    const uint32_t itype_req = (uint32_t)w29;
+    const uint32_t pod_res_present = (uint32_t)__shfl_sync(0xffffffffu, word, 28);
+    const uint32_t itype_req = (uint32_t)__shfl_sync(0xffffffffu, word, 29);
     unsigned long long best = kNoBest;
     for (int v = 0; v < V; ++v) {
       const ksched_template& tm = c.templates[v];
@@ -194,7 +251,7 @@ __global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
       uint64_t allowed = 0;
       bool neg = false, present = false, compat = true;
       const int k = lane - 8;
-      if (k >= 0 && k < c.n_keys) {
+      if (k >= 0 && k < NK) {
         Req pod;
         pod.present = (meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
         pod.complement = (meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1;
@@ -215,10 +272,10 @@ __global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
       // resources: lanes 0..7 own one resource each (Fits, resources.go:138-145)
       int rank = 0;
       bool res_used = false;
-      if (lane < c.n_res) {
+      if (lane < R) {
         uint32_t pres = pod_res_present | tm.daemon_res_present;
         res_used = (pres >> lane) & 1;
-        if (res_used) rank = fit_rank(c.alloc_sorted, c.n_types, lane, (int64_t)word + tm.daemon_requests[lane]);
+        if (res_used) rank = fit_rank(c.alloc_sorted, T, lane, (int64_t)word + tm.daemon_requests[lane]);
       }
       const uint32_t res_mask = __ballot_sync(0xffffffffu, res_used);
       uint64_t zallowed = 0xFFFF, callowed = 0xF;
@@ -236,8 +293,8 @@ __global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
       bool any = false;
       int first_word = -1;
       uint32_t first_bits = 0;
-      for (int w0 = 0; w0 < W32; w0 += 32) {
-        const int w = w0 + lane;
+      for (int wi = 0; wi < wpl; ++wi) {
+        const int w = wi * 32 + lane;
         const bool mine = w < W32 && w >= p.word_begin && w < p.word_end;
         uint32_t s = 0;
         if (ok && mine) s = c.member[(size_t)v * W32 + w];
@@ -255,15 +312,16 @@ __global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
           int r = __ffs(rm) - 1;
           rm &= rm - 1;
           int rk = __shfl_sync(0xffffffffu, rank, r);
-          if (s) s &= c.fitset[((size_t)r * (c.n_types + 1) + rk) * W32 + w];
+          if (s) s &= c.fitset[((size_t)r * (T + 1) + rk) * W32 + w];
         }
         if (s && itype_req != KSCHED_NONE) s &= p.itype_sets[(size_t)itype_req * W32 + w];
         if (mine) out[w] = s;
+        if (cacheable) cache[v * wpl + wi] = s;
         uint32_t nz = __ballot_sync(0xffffffffu, s != 0);
         if (nz && !any) {
           any = true;
           int src = __ffs(nz) - 1;
-          first_word = w0 + src;
+          first_word = wi * 32 + src;
           first_bits = __shfl_sync(0xffffffffu, s, src);
         }
       }
@@ -273,6 +331,7 @@ __global__ void __launch_bounds__(256) feasibility_kernel(K1Params p) {
         best = key < best ? key : best;
       }
     }
+    best_prev = best;
     if (lane == 0) p.best[j] = best;
   }
 }
@@ -296,7 +355,7 @@ struct PackState {
   const uint32_t* F;                 // [n_pods][V][W32] in FFD order (nullptr: compute fresh-node types dynamically)
   const unsigned long long* best;    // [n_pods] FFD order (after allreduce when sharded) or nullptr
   int n_pods, n_classes, n_existing, n_groups, max_new;
-  int64_t min_req[KSCHED_MAX_RES];   // min over all classes of requests[r] (0 if some class lacks r)
+  long long min_req[KSCHED_MAX_RES]; // min over all classes of requests[r] (0 if some class lacks r)
   // mutable
   uint32_t* pod_class;               // [n_pods] current class
   int32_t* relax_level;              // [n_pods]
@@ -330,13 +389,22 @@ struct PackState {
   unsigned long long* ov_key;
   long long* ov_q;
   long long* ov_bound;
+  long long* ov_bound2;
   int* ov_node;
   unsigned short* ov_flags;
-  // fresh-node option cache per (class, template)
+  unsigned* ov_absorbed;
+  unsigned* ov_rejected;
+  // fresh-node outcome memo per (class, template)
   uint8_t* fc_state;                 // 0 unknown, 1 cached, 2 cached: no surviving type
   uint32_t* fc_opts;                 // [n_classes*V][W32]
   long long* fc_bound;               // [n_classes*V][4]
+  long long* fc_bound2;
   uint8_t* fc_dom;
+  uint8_t* fc_front_state;           // fc_bound / fc_bound2 / fc_dom hold the front of the K1-row option set
+  uint64_t* fc_vals;                 // [n_classes*V][16] requirement masks of the fresh node
+  uint64_t* fc_meta;
+  long long* fc_q;                   // [n_classes*V][8] requests (daemon overhead + pod)
+  uint32_t* fc_qp;
   int count_visited;                 // keep the exact nodes_visited statistic (costs a pass over all in-flight nodes per pod)
   int alloc_in_smem;
   // topology counters
@@ -770,7 +838,7 @@ struct ksched_handle {
   DevBuf<ksched_type_row> d_types;
   DevBuf<float> d_price32;
   DevBuf<int16_t> d_valrow, d_offrow;
-  DevBuf<uint32_t> d_valset, d_absent, d_negempty, d_offset, d_anyoffer, d_member, d_fitset;
+  DevBuf<uint32_t> d_valset, d_absent, d_negempty, d_offset, d_anyoffer, d_member, d_fitset, d_domset;
   std::vector<ksched_template> h_templates;
   // problem
   bool uploaded = false;
@@ -788,12 +856,14 @@ struct ksched_handle {
   DevBuf<uint32_t> d_F;
   DevBuf<unsigned long long> d_best;
   DevBuf<int64_t> d_ex_req, d_ex_req0, d_ex_avail, d_nn_req, d_remaining, d_alloc_rt;
-  DevBuf<long long> d_ov_q, d_ov_bound, d_fc_bound;
+  DevBuf<long long> d_ov_q, d_ov_bound, d_ov_bound2, d_fc_bound, d_fc_bound2;
   DevBuf<unsigned long long> d_ov_key;
   DevBuf<unsigned short> d_ov_flags;
-  DevBuf<uint8_t> d_fc_state, d_fc_dom, d_grp_active, d_grp_active0;
+  DevBuf<uint8_t> d_fc_state, d_fc_dom, d_fc_front_state, d_grp_active, d_grp_active0;
   DevBuf<int32_t> d_grp_min_slot;
-  DevBuf<uint32_t> d_fc_opts;
+  DevBuf<uint32_t> d_fc_opts, d_fc_qp, d_ov_absorbed, d_ov_rejected;
+  DevBuf<uint64_t> d_fc_vals, d_fc_meta;
+  DevBuf<long long> d_fc_q;
   int count_visited = 1;
   DevBuf<uint32_t> d_ex_req_present, d_ex_req_present0, d_ex_avail_present, d_ex_taintset, d_ex_itype, d_nn_req_present, d_nn_opts;
   DevBuf<uint64_t> d_ex_vals, d_ex_vals0, d_ex_meta, d_ex_meta0, d_ex_hp, d_ex_hp0, d_nn_vals, d_nn_meta, d_nn_hp, d_grp_registered,
@@ -962,6 +1032,19 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   CUDA_TRY(h, upload_vec(h, h->d_alloc_sorted, alloc_sorted));
   CUDA_TRY(h, upload_vec(h, h->d_perm_desc, perm_desc));
   CUDA_TRY(h, upload_vec(h, h->d_alloc_rt, alloc_rt));
+  {
+    // dominance bitsets over the first min(R,4) resources (pack kernel: Pareto front of a node's options)
+    const int RH = std::min(R, 4);
+    std::vector<uint32_t> domset((size_t)std::max(T, 1) * W32, 0);
+    for (int a = 0; a < T; ++a)
+      for (int b = 0; b < T; ++b) {
+        bool dom = true;
+        for (int r = 0; r < RH && dom; ++r) dom = cat->types[a].allocatable[r] >= cat->types[b].allocatable[r];
+        if (dom) domset[(size_t)a * W32 + (b >> 5)] |= 1u << (b & 31);
+      }
+    CUDA_TRY(h, upload_vec(h, h->d_domset, domset));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
   CUDA_TRY(h, upload_vec(h, h->d_fitset, fitset));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->h_templates.assign(cat->templates, cat->templates + V);
@@ -977,7 +1060,7 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   c.type_relevant = type_relevant;
   c.offrow = h->d_offrow.ptr; c.offset = h->d_offset.ptr; c.anyoffer = h->d_anyoffer.ptr; c.member = h->d_member.ptr;
   c.alloc_sorted = h->d_alloc_sorted.ptr; c.fitset = h->d_fitset.ptr;
-  c.perm_desc = h->d_perm_desc.ptr; c.alloc_rt = h->d_alloc_rt.ptr;
+  c.perm_desc = h->d_perm_desc.ptr; c.alloc_rt = h->d_alloc_rt.ptr; c.domset = h->d_domset.ptr;
   c.zone_key = zone_key; c.ct_key = ct_key;
   h->have_catalog = true;
   h->uploaded = false;
@@ -1146,15 +1229,18 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   CUDA_TRY(h, h->d_nn_req.ensure(8 * mn)); CUDA_TRY(h, h->d_nn_req_present.ensure(mn));
   CUDA_TRY(h, h->d_nn_vals.ensure(16 * mn)); CUDA_TRY(h, h->d_nn_meta.ensure(mn));
   CUDA_TRY(h, h->d_nn_opts.ensure((size_t)W32 * mn)); CUDA_TRY(h, h->d_nn_hp.ensure(mn));
-  CUDA_TRY(h, h->d_ov_key.ensure(mn)); CUDA_TRY(h, h->d_ov_q.ensure(4 * mn)); CUDA_TRY(h, h->d_ov_bound.ensure(4 * mn));
+  CUDA_TRY(h, h->d_ov_key.ensure(mn)); CUDA_TRY(h, h->d_ov_q.ensure(4 * mn)); CUDA_TRY(h, h->d_ov_bound.ensure(4 * mn)); CUDA_TRY(h, h->d_ov_bound2.ensure(4 * mn));
   CUDA_TRY(h, h->d_ov_node.ensure(mn)); CUDA_TRY(h, h->d_ov_flags.ensure(mn));
+  CUDA_TRY(h, h->d_ov_absorbed.ensure(mn)); CUDA_TRY(h, h->d_ov_rejected.ensure(mn));
   {
     const size_t nfc = (size_t)std::max(NC, 1) * V;
-    CUDA_TRY(h, h->d_fc_state.ensure(nfc)); CUDA_TRY(h, h->d_fc_dom.ensure(nfc)); CUDA_TRY(h, h->d_fc_bound.ensure(nfc * 4));
+    CUDA_TRY(h, h->d_fc_state.ensure(nfc)); CUDA_TRY(h, h->d_fc_dom.ensure(nfc)); CUDA_TRY(h, h->d_fc_front_state.ensure(nfc)); CUDA_TRY(h, h->d_fc_bound.ensure(nfc * 4)); CUDA_TRY(h, h->d_fc_bound2.ensure(nfc * 4));
     CUDA_TRY(h, h->d_fc_opts.ensure(nfc * W32));
+    CUDA_TRY(h, h->d_fc_vals.ensure(nfc * KSCHED_MAX_KEYS)); CUDA_TRY(h, h->d_fc_meta.ensure(nfc)); CUDA_TRY(h, h->d_fc_q.ensure(nfc * KSCHED_MAX_RES));
+    CUDA_TRY(h, h->d_fc_qp.ensure(nfc));
   }
   CUDA_TRY(h, h->d_remaining.ensure((size_t)V * KSCHED_MAX_RES));
-  CUDA_TRY(h, h->d_counters.ensure(24));
+  CUDA_TRY(h, h->d_counters.ensure(32));
   {
     size_t need = 0, n2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)p1, 0, 64, h->stream);
@@ -1210,9 +1296,17 @@ static int run_feasibility(ksched_handle* h) {
   if (h->n_pods == 0) return KSCHED_OK;
   K1Params k1;
   fill_k1(h, k1);
-  const int warps_per_block = 8;
-  int blocks = std::min((h->n_pods + warps_per_block - 1) / warps_per_block, 148 * 8);
-  feasibility_kernel<<<blocks, 256, 0, h->stream>>>(k1);
+  const DevCatalog& c = h->cat;
+  const size_t alloc_bytes = (size_t)c.n_res * c.n_types * sizeof(int64_t);
+  k1.alloc_in_smem = alloc_bytes <= (size_t)(128 << 10) ? 1 : 0;
+  const size_t smem = sizeof(ksched_template) * c.n_templates + sizeof(ksched_keyinfo) * KSCHED_MAX_KEYS + (k1.alloc_in_smem ? alloc_bytes : 0) +
+                      sizeof(int16_t) * KSCHED_MAX_KEYS * 64 + sizeof(int16_t) * 64;
+  // one CTA per SM at most; every warp takes a contiguous chunk of >= 8 rows
+  const int warps_per_block = kK1Threads / 32;
+  const int want_warps = std::max(1, (h->n_pods + 7) / 8);
+  const int blocks = std::max(1, std::min(148, (want_warps + warps_per_block - 1) / warps_per_block));
+  CUDA_TRY(h, cudaFuncSetAttribute(feasibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  feasibility_kernel<<<blocks, kK1Threads, smem, h->stream>>>(k1);
   h->tm.feasibility_launches = 1;
   const long long C = (long long)h->cat.n_templates * h->cat.n_types;
   h->tm.feasibility_bytes = (long long)h->n_pods * 256 + C * 256 + (long long)h->n_pods * C / 8;
@@ -1241,8 +1335,9 @@ static int reset_state(ksched_handle* h) {
     for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[(size_t)v * KSCHED_MAX_RES + r] = h->h_templates[v].remaining[r];
   CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, rem.data(), rem.size() * 8, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rem is a stack vector
-  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 24 * sizeof(long long), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 32 * sizeof(long long), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fc_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_fc_front_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
   return KSCHED_OK;
 }
 
@@ -1264,8 +1359,10 @@ static int run_pack(ksched_handle* h) {
   s.nn_tmpl = h->d_nn_tmpl.ptr; s.nn_count = h->d_nn_count.ptr; s.nn_tb = h->d_nn_tb.ptr; s.nn_req = h->d_nn_req.ptr;
   s.nn_req_present = h->d_nn_req_present.ptr;
   s.nn_vals = h->d_nn_vals.ptr; s.nn_meta = h->d_nn_meta.ptr; s.nn_opts = h->d_nn_opts.ptr; s.nn_hp = h->d_nn_hp.ptr;
-  s.ov_key = h->d_ov_key.ptr; s.ov_q = h->d_ov_q.ptr; s.ov_bound = h->d_ov_bound.ptr; s.ov_node = h->d_ov_node.ptr; s.ov_flags = h->d_ov_flags.ptr;
-  s.fc_state = h->d_fc_state.ptr; s.fc_opts = h->d_fc_opts.ptr; s.fc_bound = h->d_fc_bound.ptr; s.fc_dom = h->d_fc_dom.ptr;
+  s.ov_key = h->d_ov_key.ptr; s.ov_q = h->d_ov_q.ptr; s.ov_bound = h->d_ov_bound.ptr; s.ov_bound2 = h->d_ov_bound2.ptr; s.ov_node = h->d_ov_node.ptr; s.ov_flags = h->d_ov_flags.ptr;
+  s.fc_state = h->d_fc_state.ptr; s.fc_opts = h->d_fc_opts.ptr; s.fc_bound = h->d_fc_bound.ptr; s.fc_bound2 = h->d_fc_bound2.ptr; s.fc_dom = h->d_fc_dom.ptr; s.fc_front_state = h->d_fc_front_state.ptr;
+  s.fc_vals = h->d_fc_vals.ptr; s.fc_meta = h->d_fc_meta.ptr; s.fc_q = h->d_fc_q.ptr; s.fc_qp = h->d_fc_qp.ptr;
+  s.ov_absorbed = h->d_ov_absorbed.ptr; s.ov_rejected = h->d_ov_rejected.ptr;
   s.count_visited = h->count_visited;
   s.grp_cnt = h->d_grp_cnt.ptr; s.grp_registered = h->d_grp_registered.ptr; s.grp_host = h->d_grp_host.ptr;
   s.grp_host_row = h->d_grp_host_row.ptr; s.grp_host_total = h->d_grp_host_total.ptr; s.remaining = h->d_remaining.ptr;
@@ -1346,12 +1443,14 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
   if (!h || !pb || !res || !h->uploaded) return KSCHED_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int P = h->n_pods, NE = h->n_existing, MAXN = h->max_new, W32 = h->cat.W32, W64 = h->W64, V = h->cat.n_templates;
-  long long counters[24];
+  long long counters[32];
   CUDA_TRY(h, cudaMemcpyAsync(counters, h->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
 #ifdef KSCHED_PROFILE_PACK
-  fprintf(stderr, "[pack profile] cycles: top=%lld eval=%lld reduce=%lld commit=%lld sync=%lld generic=%lld  steps=%lld\n",
-          counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[5]);
+  fprintf(stderr, "[pack profile] generic: topo=%lld existing=%lld eval=%lld commit=%lld fresh=%lld fail=%lld | fastblock=%lld genericcall=%lld | "
+                  "n_generic=%lld inflight_placed=%lld fresh_steps=%lld failures=%lld paths[rej,cached,row,dyn,cachedempty]=%lld,%lld,%lld,%lld,%lld steps=%lld\n",
+          counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[14], counters[15], counters[17], counters[18],
+          counters[19], counters[20], counters[21], counters[22], counters[23], counters[24], counters[25], counters[5]);
 #endif
   if (counters[4] != 0) {
     h->err = counters[4] == KSCHED_ERR_OVERFLOW ? "new-node capacity exceeded" : "a pod is constrained by more topology groups than the kernel supports";

@@ -22,9 +22,20 @@ constexpr int kHotRes = 4;     // resources covered by the hot request / bound v
 struct HotSmem {
   unsigned long long key[kActCap];     // (pod count << 32) | biased tie-break  == position under a stable sort
   long long q[kHotRes][kActCap];       // node.Requests
-  long long bound[kHotRes][kActCap];   // allocatable of the dominant option, or per-resource max over the options
+  // Exact resource test without touching the option bitsets: when the Pareto front of the allocatable vectors of a
+  // node's stored options has one or two members (flags bit0 "exact"; bit5 "two members"), a request vector fits some
+  // option iff it fits a front member. Otherwise bound holds per-resource maxima (a necessary test only).
+  long long bound[kHotRes][kActCap];
+  long long bound2[kHotRes][kActCap];
   int node[kActCap];
   unsigned short flags[kActCap];       // bit0 dominant option exists; bits 1..4 request-map keys; bits 8.. template
+  // Requirement verdict memo per open node, valid for topology-free pod classes without host ports:
+  //  absorbed: the node's requirements already contain this class's requirements (a further pod of the class changes
+  //            nothing: Compatible holds, the merge is the identity, the stored options are untouched);
+  //  rejected: the last requirement / instance-type evaluation of this class against the node failed and nothing has
+  //            been committed to the node since.
+  unsigned absorbed[kActCap];
+  unsigned rejected[kActCap];
 };
 
 struct Hot {
@@ -32,19 +43,27 @@ struct Hot {
   unsigned long long* ov_key;
   long long* ov_q;      // [kHotRes][ov_stride]
   long long* ov_bound;  // [kHotRes][ov_stride]
+  long long* ov_bound2;
   int* ov_node;
   unsigned short* ov_flags;
+  unsigned* ov_absorbed;
+  unsigned* ov_rejected;
   int ov_stride;
   __device__ __forceinline__ unsigned long long& key(int a) const { return a < kActCap ? sm->key[a] : ov_key[a - kActCap]; }
   __device__ __forceinline__ long long& q(int r, int a) const { return a < kActCap ? sm->q[r][a] : ov_q[(size_t)r * ov_stride + (a - kActCap)]; }
   __device__ __forceinline__ long long& bound(int r, int a) const { return a < kActCap ? sm->bound[r][a] : ov_bound[(size_t)r * ov_stride + (a - kActCap)]; }
+  __device__ __forceinline__ long long& bound2(int r, int a) const { return a < kActCap ? sm->bound2[r][a] : ov_bound2[(size_t)r * ov_stride + (a - kActCap)]; }
   __device__ __forceinline__ int& node(int a) const { return a < kActCap ? sm->node[a] : ov_node[a - kActCap]; }
   __device__ __forceinline__ unsigned short& flags(int a) const { return a < kActCap ? sm->flags[a] : ov_flags[a - kActCap]; }
+  __device__ __forceinline__ unsigned& absorbed(int a) const { return a < kActCap ? sm->absorbed[a] : ov_absorbed[a - kActCap]; }
+  __device__ __forceinline__ unsigned& rejected(int a) const { return a < kActCap ? sm->rejected[a] : ov_rejected[a - kActCap]; }
   __device__ void move(int dst, int src) const {
     key(dst) = key(src);
-    for (int r = 0; r < kHotRes; ++r) { q(r, dst) = q(r, src); bound(r, dst) = bound(r, src); }
+    for (int r = 0; r < kHotRes; ++r) { q(r, dst) = q(r, src); bound(r, dst) = bound(r, src); bound2(r, dst) = bound2(r, src); }
     node(dst) = node(src);
     flags(dst) = flags(src);
+    absorbed(dst) = absorbed(src);
+    rejected(dst) = rejected(src);
   }
 };
 
@@ -52,26 +71,71 @@ __device__ __forceinline__ unsigned long long order_key(int count, int tb) {
   return ((unsigned long long)(unsigned)count << 32) | (unsigned)(tb ^ 0x80000000);
 }
 
-// Upper bounds of allocatable over a node's stored options, by probing each resource's descending order.
-// has_dom: one option attains the maximum in every resource, so "requests <= bound" is an exact accept test.
-__device__ void compute_bounds(const DevCatalog& c, const uint32_t* opts, int stride, int n, long long* bound, bool* has_dom) {
-  int arg0 = -1;
-  for (int r = 0; r < kHotRes; ++r) bound[r] = INT64_MIN;
+constexpr unsigned short kFlExact = 1, kFlTwo = 0x20;
+
+// Pareto front (size <= 2) of the allocatable vectors of a node's stored options, or per-resource maxima when the front
+// is larger. Candidates are the per-resource arg-max types (found by probing each resource's descending order); a
+// candidate pair is a front iff every stored option is dominated by one of the two.
+__device__ void compute_front(const DevCatalog& c, const uint32_t* opts, int stride, int n, long long* b1, long long* b2, unsigned short* bits) {
   const int R = c.n_res < kHotRes ? c.n_res : kHotRes;
+  const int T = c.n_types;
+  int arg[kHotRes];
+  for (int r = 0; r < kHotRes; ++r) { b1[r] = INT64_MIN; b2[r] = INT64_MIN; arg[r] = -1; }
+  *bits = 0;
   for (int r = 0; r < R; ++r) {
-    const int32_t* perm = c.perm_desc + (size_t)r * c.n_types;
-    for (int i = 0; i < c.n_types; ++i) {
+    const int32_t* perm = c.perm_desc + (size_t)r * T;
+    for (int i = 0; i < T; ++i) {
       const int t = perm[i];
-      if ((opts[(size_t)(t >> 5) * stride + n] >> (t & 31)) & 1) {
-        bound[r] = c.alloc_rt[(size_t)r * c.n_types + t];
-        if (r == 0) arg0 = t;
-        break;
-      }
+      if ((opts[(size_t)(t >> 5) * stride + n] >> (t & 31)) & 1) { arg[r] = t; b1[r] = c.alloc_rt[(size_t)r * T + t]; break; }
     }
   }
-  bool dom = arg0 >= 0 && c.n_res <= kHotRes;
-  for (int r = 1; r < R && dom; ++r) dom = c.alloc_rt[(size_t)r * c.n_types + arg0] == bound[r];
-  *has_dom = dom;
+  if (arg[0] < 0 || c.n_res > kHotRes) return;  // no option left / resources beyond the hot vectors: necessary test only
+  auto dominates = [&](int a, const long long* v) {  // alloc(a) >= v in every hot resource
+    for (int r = 0; r < R; ++r) if (c.alloc_rt[(size_t)r * T + a] < v[r]) return false;
+    return true;
+  };
+  if (dominates(arg[0], b1)) { *bits = kFlExact; return; }  // one option is maximal in every resource
+  // distinct candidates
+  int cand[kHotRes], nc = 0;
+  for (int r = 0; r < R; ++r) {
+    bool seen = false;
+    for (int i = 0; i < nc; ++i) seen = seen || cand[i] == arg[r];
+    if (!seen) cand[nc++] = arg[r];
+  }
+  // which candidate pairs cover every option?  opts ⊆ domset[ci] ∪ domset[cj], word by word
+  unsigned pair_ok = 0;  // bit (i*4+j), i<j
+  for (int i = 0; i < nc; ++i) for (int j = i + 1; j < nc; ++j) pair_ok |= 1u << (i * 4 + j);
+  const int W32 = c.W32;
+  for (int w = 0; w < W32 && pair_ok; ++w) {
+    const uint32_t m = opts[(size_t)w * stride + n];
+    if (!m) continue;
+    uint32_t d[kHotRes];
+    for (int i = 0; i < nc; ++i) d[i] = c.domset[(size_t)cand[i] * W32 + w];
+    for (int i = 0; i < nc; ++i) for (int j = i + 1; j < nc; ++j)
+      if (m & ~(d[i] | d[j])) pair_ok &= ~(1u << (i * 4 + j));
+  }
+  if (!pair_ok) return;  // front larger than two: b1 keeps the per-resource maxima
+  const int pi = (__ffs(pair_ok) - 1) / 4, pj = (__ffs(pair_ok) - 1) % 4;
+  for (int r = 0; r < R; ++r) { b1[r] = c.alloc_rt[(size_t)r * T + cand[pi]]; b2[r] = c.alloc_rt[(size_t)r * T + cand[pj]]; }
+  *bits = kFlExact | kFlTwo;
+}
+
+// 0 = no option can hold the requests, 1 = some option holds them (exact), 2 = unknown (per-resource maxima pass)
+__device__ __forceinline__ int quick_fit(const long long* q, uint32_t qp, int RH, const long long* b1, const long long* b2, unsigned short fl) {
+  bool f1 = true, f2 = true;
+#pragma unroll
+  for (int r = 0; r < kHotRes; ++r)
+    if (r < RH && ((qp >> r) & 1)) { f1 = f1 && q[r] <= b1[r]; f2 = f2 && q[r] <= b2[r]; }
+  if (fl & kFlExact) return (f1 || ((fl & kFlTwo) && f2)) ? 1 : 0;
+  return f1 ? 2 : 0;
+}
+// no pod of the batch can ever fit again (min_req: per-resource minimum request over all pod classes)
+__device__ __forceinline__ bool node_closed(const long long* q, const long long* min_req, int RH, const long long* b1, const long long* b2, unsigned short fl) {
+  bool o1 = false, o2 = false;
+#pragma unroll
+  for (int r = 0; r < kHotRes; ++r)
+    if (r < RH && min_req[r] > 0) { o1 = o1 || q[r] + min_req[r] > b1[r]; o2 = o2 || q[r] + min_req[r] > b2[r]; }
+  return (fl & kFlTwo) ? (o1 && o2) : o1;
 }
 
 // 64-bit min over a warp with two 32-bit REDUX operations (hi word first, then lo word among the hi-minimal lanes)
@@ -100,8 +164,8 @@ struct StepShared {
   unsigned any;
   long long q[KSCHED_MAX_RES];
   unsigned qp;
-  long long bound[kHotRes];
-  int has_dom;
+  long long bound[kHotRes], bound2[kHotRes];
+  unsigned short front_bits;
   long long visited;
 };
 
@@ -169,7 +233,7 @@ __device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState&
 }
 // Requirement-changing part of a commit: new masks, requirement-driven narrowing of the stored options, new bounds.
 __device__ __noinline__ void commit_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, int n, SlowEval& e, long long* bound,
-                                         bool* dom, uint64_t* meta_out) {
+                                         long long* bound2, unsigned short* front_bits, uint64_t* meta_out) {
   const int MAXN = s.max_new, W32 = c.W32;
   uint64_t meta = s.nn_meta[n];
   for (int i = 0; i < e.t.n; ++i) {
@@ -188,7 +252,7 @@ __device__ __noinline__ void commit_slow(const DevCatalog& c, const PackState& s
     const uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
     if (base) s.nn_opts[(size_t)w * MAXN + n] = type_word(c, s, e.x, base, w);
   }
-  compute_bounds(c, s.nn_opts, MAXN, n, bound, dom);
+  compute_front(c, s.nn_opts, MAXN, n, bound, bound2, front_bits);
 }
 
 struct StepCtx {  // per-CTA objects shared by the slow path
@@ -230,6 +294,14 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
   uint32_t& epoch = L.epoch;
   bool& pt_nonempty = L.pt_nonempty;
   long long& nodes_visited = L.nodes_visited;
+#ifdef KSCHED_PROFILE_PACK
+  long long gk_last = clock64();
+#define GK_T(i) { if (tid == 0) { long long _n = clock64(); s.counters[8 + (i)] += _n - gk_last; gk_last = _n; } }
+#define GK_C(i) { if (tid == 0) s.counters[8 + (i)] += 1; }
+#else
+#define GK_T(i)
+#define GK_C(i)
+#endif
     const uint32_t pod = cur.pod, cls = (uint32_t)cur.cls64;
     const ksched_pod_row& row = *cur.row;
     const uint32_t p_res = cur.res;
@@ -247,8 +319,10 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
       if (pt.overflow) { fatal = KSCHED_ERR_UNSUPPORTED; return; }
     }
     const bool plain = p_keys == 0 && !pt_nonempty && p_itype == KSCHED_NONE && p_hostname == KSCHED_NONE;  // no requirement can change
+    const bool simple = !has_topo && p_hpc == 0 && p_hpe == 0;  // the requirement verdict memo (HotSmem::absorbed/rejected) applies
 
     bool placed = false;
+    GK_T(0)
     // ------------------------------------------------------------ 1) existing nodes in caller order (scheduler.go:176-180)
     if (NE > 0) {
       unsigned long long mine = ~0ull;
@@ -314,6 +388,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         nodes_visited += NE;
       }
     }
+    GK_T(1)
     // ------------------------------------------------------------ 2) in-flight nodes, fewest pods first (scheduler.go:183-190)
     if (!placed && n_active > 0) {
       unsigned long long mine = ~0ull;
@@ -327,19 +402,20 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         const unsigned short fl = H.flags(a);
         if (!((p_tol >> tmpl_taintset[fl >> 8]) & 1)) continue;  // Taints.Tolerates
         const uint32_t qp = ((fl >> 1) & 0xF) | p_res;
-        long long q[kHotRes];
-        bool ok = true;
+        long long q[kHotRes], b1[kHotRes], b2[kHotRes];
 #pragma unroll
-        for (int r = 0; r < kHotRes; ++r) {
-          q[r] = H.q(r, a) + preq[r];
-          if (r < RH && ((qp >> r) & 1)) ok = ok && q[r] <= H.bound(r, a);
-        }
-        if (!ok) continue;
+        for (int r = 0; r < kHotRes; ++r) { q[r] = H.q(r, a) + preq[r]; b1[r] = H.bound(r, a); b2[r] = H.bound2(r, a); }
+        const int qf = quick_fit(q, qp, RH, b1, b2, fl);
+        if (qf == 0) continue;
         if (p_hpc && (s.nn_hp[H.node(a)] & p_hpc)) continue;
-        const bool fast = plain && (fl & 1);  // no requirement can change and the dominant option fits
+        if (simple && H.rejected(a) == cls) continue;  // memo: same class, node untouched since it was refused
+        const bool fast = (plain || (simple && H.absorbed(a) == cls)) && qf == 1;  // nothing can change and an option holds the requests
         if (!fast) {
           last_slow = a;
-          if (!evaluate_slow(c, s, row, pt, plain, H.node(a), fl, q, alloc_sorted, ev)) continue;
+          if (!evaluate_slow(c, s, row, pt, plain, H.node(a), fl, q, alloc_sorted, ev)) {
+            if (simple) H.rejected(a) = cls;
+            continue;
+          }
         }
         mine = key;
         best_a = a;
@@ -347,8 +423,10 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
 #pragma unroll
         for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
       }
+      GK_T(2)
       const unsigned long long wkey = block_min_u64_db(mine, red, parity);
       if (wkey != ~0ull) {
+        GK_C(10)
         if (s.count_visited) {  // rank of the winner among ALL in-flight nodes (the reference also walks the full ones)
           int less = 0;
           for (int i = tid; i < n_new; i += blockDim.x) less += order_key(s.nn_count[i], s.nn_tb[i]) < wkey;
@@ -378,19 +456,22 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           H.key(a) = order_key(count, -(tick + 1));
           uint64_t meta = 0;
           if (best_slow && (ev.changed || p_itype != KSCHED_NONE)) {
-            long long b[kHotRes];
-            bool dom;
-            commit_slow(c, s, row, n, ev, b, &dom, &meta);
+            long long nb1[kHotRes], nb2[kHotRes];
+            unsigned short fb;
+            commit_slow(c, s, row, n, ev, nb1, nb2, &fb, &meta);
 #pragma unroll
-            for (int r = 0; r < kHotRes; ++r) H.bound(r, a) = b[r];
-            fl = dom ? (fl | 1) : (fl & ~1);
+            for (int r = 0; r < kHotRes; ++r) { H.bound(r, a) = nb1[r]; H.bound2(r, a) = nb2[r]; }
+            fl = (unsigned short)((fl & ~(kFlExact | kFlTwo)) | fb);
           } else if (has_topo) {
             meta = s.nn_meta[n];
           }
           H.flags(a) = fl;
-          bool closed = false;
-          for (int r = 0; r < RH; ++r)
-            if (s.min_req[r] > 0 && bq[r] + s.min_req[r] > H.bound(r, a)) closed = true;
+          H.rejected(a) = KSCHED_NONE;
+          if (simple) H.absorbed(a) = cls;
+          long long cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+          for (int r = 0; r < kHotRes; ++r) { cb1[r] = H.bound(r, a); cb2[r] = H.bound2(r, a); }
+          const bool closed = node_closed(bq, s.min_req, RH, cb1, cb2, fl);
           if (has_topo) topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
           s.assign[pod] = NE + n;
           s.place_seq[pod] = seq;
@@ -411,8 +492,10 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
     } else if (!placed) {
       nodes_visited += n_new;  // every in-flight node is full; the reference still walks them
     }
+    GK_T(3)
     // ------------------------------------------------------------ 3) open a new node, templates in weight order (scheduler.go:194-217)
     if (!placed) {
+      GK_C(11)
       const bool f_valid = s.use_F && (first_pass || s.relax_level[pod] == 0);  // K1's row is valid while the pod has its original class
       const uint32_t fpos = first_pass ? (uint32_t)fpos_first : s.pod_pos[pod];
       const bool no_column = f_valid && s.best[fpos] == kNoBest;  // no feasible (template, type) column at all
@@ -423,24 +506,31 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         if (n_new >= MAXN) { fatal = KSCHED_ERR_OVERFLOW; break; }
         const int n = n_new;  // tentative slot: the hostname placeholder of this attempt (node.go:46)
         const bool limits_active = tm.has_limits && tm.limit_present;
+        // Without topology and provisioner limits the outcome of NewNode+Add depends on (class, template) only: memoised.
+        const bool memo = !pt_nonempty && !limits_active;
+        const size_t fc = ((size_t)cls * V + v);
         __syncthreads();
         if (tid == 0) {
-          bool ok = (p_tol >> tm.taintset) & 1;
-          fresh_t.n = 0;
-          if (ok && !plain) ok = requirements_phase(c, s, row, pt, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, NE + n, false, fresh_t);
           int path = kPathReject;
-          if (ok) {
-            sh.qp = tm.daemon_res_present | p_res;
-            for (int r = 0; r < R; ++r) sh.q[r] = tm.daemon_requests[r] + (((p_res >> r) & 1) ? row.requests[r] : 0);
-            bool same = f_valid;  // topology left every requirement exactly as K1 saw it
-            for (int i = 0; i < fresh_t.n && same; ++i) same = req_equal(fresh_t.fin[i], fresh_t.merged[i]);
-            const uint8_t st = (same && !limits_active) ? s.fc_state[(size_t)cls * V + v] : 0;
-            if (st == 1) path = kPathCached;
-            else if (st == 2) path = kPathCachedEmpty;
-            else if (same) path = kPathRow;
-            else {
-              path = kPathDynamic;
-              build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, true, alloc_sorted, fresh_x);
+          const uint8_t st = memo ? s.fc_state[fc] : 0;
+          if (st == 1) path = kPathCached;
+          else if (st == 2) path = kPathCachedEmpty;
+          else {
+            bool ok = (p_tol >> tm.taintset) & 1;
+            fresh_t.n = 0;
+            if (ok && !plain) ok = requirements_phase(c, s, row, pt, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, NE + n, false, fresh_t);
+            if (ok) {
+              sh.qp = tm.daemon_res_present | p_res;
+              for (int r = 0; r < KSCHED_MAX_RES; ++r) sh.q[r] = r < R ? tm.daemon_requests[r] + (((p_res >> r) & 1) ? row.requests[r] : 0) : 0;
+              bool same = f_valid;  // topology left every requirement exactly as K1 saw it
+              for (int i = 0; i < fresh_t.n && same; ++i) same = req_equal(fresh_t.fin[i], fresh_t.merged[i]);
+              if (same) path = kPathRow;
+              else {
+                path = kPathDynamic;
+                build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, true, alloc_sorted, fresh_x);
+              }
+            } else if (memo) {
+              s.fc_state[fc] = 2;
             }
           }
           sh.path = path;
@@ -448,14 +538,12 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         }
         __syncthreads();
         const int path = sh.path;
+        GK_C(13 + (path > 4 ? 4 : path))
         if (path == kPathReject || path == kPathCachedEmpty) continue;
-        const size_t fc = ((size_t)cls * V + v);
+        const int a = n_active;
         if (path == kPathCached) {
           for (int w = tid; w < W32; w += blockDim.x) s.nn_opts[(size_t)w * MAXN + n] = s.fc_opts[fc * W32 + w];
-          if (tid == 0) {
-            for (int r = 0; r < kHotRes; ++r) sh.bound[r] = s.fc_bound[fc * kHotRes + r];
-            sh.has_dom = s.fc_dom[fc];
-          }
+          if (tid < c.n_keys) s.nn_vals[(size_t)tid * MAXN + n] = s.fc_vals[fc * KSCHED_MAX_KEYS + tid];
         } else {
           bool local_any = false;
           for (int w = tid; w < W32; w += blockDim.x) {
@@ -473,69 +561,85 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
             uint32_t sw = 0;
             if (base) sw = path == kPathRow ? (base & s.F[((size_t)fpos * V + v) * W32 + w]) : type_word(c, s, fresh_x, base, w);
             s.nn_opts[(size_t)w * MAXN + n] = sw;
+            if (memo) s.fc_opts[fc * W32 + w] = sw;
             local_any = local_any || sw;
           }
           if (local_any) atomicOr(&sh.any, 1u);
+          if (tid < c.n_keys) {
+            uint64_t val = tm.reqs.values[tid];
+            for (int i = 0; i < fresh_t.n; ++i) if (fresh_t.key[i] == tid) val = fresh_t.fin[i].values;
+            s.nn_vals[(size_t)tid * MAXN + n] = val;
+            if (memo) s.fc_vals[fc * KSCHED_MAX_KEYS + tid] = val;
+          }
           __syncthreads();
-          const bool cacheable = path == kPathRow && !limits_active;
           if (!sh.any) {
-            if (cacheable && tid == 0) s.fc_state[fc] = 2;
+            if (memo && tid == 0) s.fc_state[fc] = 2;
             continue;
           }
-          if (tid == 0) {
-            bool dom;
-            compute_bounds(c, s.nn_opts, MAXN, n, sh.bound, &dom);
-            sh.has_dom = dom;
-            if (cacheable) {
-              for (int r = 0; r < kHotRes; ++r) s.fc_bound[fc * kHotRes + r] = sh.bound[r];
-              s.fc_dom[fc] = dom;
-            }
-          }
-          if (cacheable)
-            for (int w = tid; w < W32; w += blockDim.x) s.fc_opts[fc * W32 + w] = s.nn_opts[(size_t)w * MAXN + n];
-          __syncthreads();
-          if (cacheable && tid == 0) s.fc_state[fc] = 1;
         }
-        // ---- commit the new node (NewNode + Add, node.go:44-107)
-        const int a = n_active;
-        if (tid < c.n_keys) {
-          uint64_t val = tm.reqs.values[tid];
-          for (int i = 0; i < fresh_t.n; ++i) if (fresh_t.key[i] == tid) val = fresh_t.fin[i].values;
-          s.nn_vals[(size_t)tid * MAXN + n] = val;
-        }
+        // ---- commit the new node (NewNode + Add, node.go:44-107) — one thread, everything else was written above
         __syncthreads();
         if (tid == 0) {
-          uint64_t meta = tm.reqs.meta & 0xFFFFFFFFull;
-          for (int i = 0; i < fresh_t.n; ++i) {
-            const int k = fresh_t.key[i];
-            const Req& f = fresh_t.fin[i];
-            const uint64_t bit = 1ull << k;
-            meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
-            if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
-            if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+          uint64_t meta;
+          if (path == kPathCached) {
+            meta = s.fc_meta[fc];
+            for (int r = 0; r < kHotRes; ++r) { sh.bound[r] = s.fc_bound[fc * kHotRes + r]; sh.bound2[r] = s.fc_bound2[fc * kHotRes + r]; }
+            sh.front_bits = s.fc_dom[fc];
+            sh.qp = s.fc_qp[fc];
+            for (int r = 0; r < KSCHED_MAX_RES; ++r) sh.q[r] = s.fc_q[fc * KSCHED_MAX_RES + r];
+          } else {
+            meta = tm.reqs.meta & 0xFFFFFFFFull;
+            for (int i = 0; i < fresh_t.n; ++i) {
+              const int k = fresh_t.key[i];
+              const Req& f = fresh_t.fin[i];
+              const uint64_t bit = 1ull << k;
+              meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+              if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+              if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+            }
+            // K1-row path without limits: the option set, hence its Pareto front, depends on (class, template) only
+            const bool front_memo = path == kPathRow && !limits_active;
+            if (front_memo && s.fc_front_state[fc]) {
+              for (int r = 0; r < kHotRes; ++r) { sh.bound[r] = s.fc_bound[fc * kHotRes + r]; sh.bound2[r] = s.fc_bound2[fc * kHotRes + r]; }
+              sh.front_bits = s.fc_dom[fc];
+            } else {
+              compute_front(c, s.nn_opts, MAXN, n, sh.bound, sh.bound2, &sh.front_bits);
+              if (front_memo) {
+                for (int r = 0; r < kHotRes; ++r) { s.fc_bound[fc * kHotRes + r] = sh.bound[r]; s.fc_bound2[fc * kHotRes + r] = sh.bound2[r]; }
+                s.fc_dom[fc] = (uint8_t)sh.front_bits;
+                s.fc_front_state[fc] = 1;
+              }
+            }
+            if (memo) {
+              s.fc_meta[fc] = meta;
+              for (int r = 0; r < kHotRes; ++r) { s.fc_bound[fc * kHotRes + r] = sh.bound[r]; s.fc_bound2[fc * kHotRes + r] = sh.bound2[r]; }
+              s.fc_dom[fc] = (uint8_t)sh.front_bits;
+              s.fc_qp[fc] = sh.qp;
+              for (int r = 0; r < KSCHED_MAX_RES; ++r) s.fc_q[fc * KSCHED_MAX_RES + r] = sh.q[r];
+              s.fc_state[fc] = 1;
+            }
           }
           s.nn_meta[n] = meta;
           s.nn_tmpl[n] = (uint8_t)v;
-          for (int r = 0; r < KSCHED_MAX_RES; ++r) s.nn_req[(size_t)r * MAXN + n] = r < R ? sh.q[r] : 0;
+          for (int r = 0; r < KSCHED_MAX_RES; ++r) s.nn_req[(size_t)r * MAXN + n] = sh.q[r];
           s.nn_req_present[n] = sh.qp;
           s.nn_hp[n] = p_hpe;
           s.nn_count[n] = 1;
           s.nn_tb[n] = tick + 1;  // appended: last of the one-pod block
-          bool closed = false;
-          for (int r = 0; r < RH; ++r)
-            if (s.min_req[r] > 0 && sh.q[r] + s.min_req[r] > sh.bound[r]) closed = true;
+          const bool closed = node_closed(sh.q, s.min_req, RH, sh.bound, sh.bound2, sh.front_bits);
           if (!closed) {
             H.key(a) = order_key(1, tick + 1);
-            for (int r = 0; r < kHotRes; ++r) { H.q(r, a) = r < R ? sh.q[r] : 0; H.bound(r, a) = sh.bound[r]; }
+            for (int r = 0; r < kHotRes; ++r) { H.q(r, a) = sh.q[r]; H.bound(r, a) = sh.bound[r]; H.bound2(r, a) = sh.bound2[r]; }
             H.node(a) = n;
-            H.flags(a) = (unsigned short)((sh.has_dom ? 1 : 0) | ((sh.qp & 0xF) << 1) | (v << 8));
+            H.flags(a) = (unsigned short)(sh.front_bits | ((sh.qp & 0xF) << 1) | (v << 8));
+            H.absorbed(a) = simple ? cls : KSCHED_NONE;
+            H.rejected(a) = KSCHED_NONE;
           }
           sh.placed_closed = closed ? 1 : 0;
           if (has_topo) topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
           s.assign[pod] = NE + n;
           s.place_seq[pod] = seq;
           if (limits_active) {  // subtractMax (scheduler.go:273-290): largest capacity among the surviving options
-            // capacity maximum is taken over the options that survive resources too
             for (int r = 0; r < R; ++r) {
               if (!((tm.limit_present >> r) & 1)) continue;
               long long mx = INT64_MIN;
@@ -561,8 +665,10 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
       }
       if (fatal) return;
     }
+    GK_T(4)
     // ------------------------------------------------------------ failure: relax + requeue (scheduler.go:117-123, queue.go:61-68)
     if (!placed) {
+      GK_C(12)
       const uint32_t nx = row.relax_next;
       int tail = head + qlen;
       if (tail >= qcap) tail -= qcap;
@@ -603,6 +709,10 @@ struct WarpIO {
 __device__ __forceinline__ bool plain_pod_regs(const PodRegs& r) {
   return ((r.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0 && r.itype == KSCHED_NONE && r.hostname == KSCHED_NONE && r.topo_begin == r.topo_end;
 }
+// topology-free, no host ports, resources within the hot vectors: the requirement verdict memo applies
+__device__ __forceinline__ bool simple_pod_regs(const PodRegs& r) {
+  return r.topo_begin == r.topo_end && r.hpc == 0 && r.hpe == 0 && (r.res >> kHotRes) == 0;
+}
 
 __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, const uint32_t* tmpl_taintset, WarpIO* io) {
   const PackState& s = p.st;
@@ -616,13 +726,12 @@ __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, 
   // lane state
   bool live = lane < n_active, dirty = false;
   unsigned long long key = live ? hs->key[lane] : ~0ull;
-  long long q[kHotRes], b[kHotRes];
+  long long q[kHotRes], b[kHotRes], b2[kHotRes];
 #pragma unroll
-  for (int r = 0; r < kHotRes; ++r) { q[r] = live ? hs->q[r][lane] : 0; b[r] = live ? hs->bound[r][lane] : 0; }
+  for (int r = 0; r < kHotRes; ++r) { q[r] = live ? hs->q[r][lane] : 0; b[r] = live ? hs->bound[r][lane] : 0; b2[r] = live ? hs->bound2[r][lane] : 0; }
   const int node = live ? hs->node[lane] : 0;
   unsigned short fl = live ? hs->flags[lane] : 0;
-  const bool tol_dep = true;
-  (void)tol_dep;
+  unsigned absorbed = live ? hs->absorbed[lane] : KSCHED_NONE, rejected = live ? hs->rejected[lane] : KSCHED_NONE;
   const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
   PodRegs cur = load_pod_regs(ffd_rows + qi, s.order[qi]);
   PodRegs nxt = cur;
@@ -632,16 +741,18 @@ __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, 
   for (int r = 0; r < kHotRes; ++r) min_req[r] = r < RH ? s.min_req[r] : 0;
 
   while (true) {
-    if (!plain_pod_regs(cur) || cur.hpc || cur.hpe || (cur.res >> kHotRes)) break;  // this pod takes the block-wide path
-    bool ok = live && ((cur.tol >> tmpl_taintset[fl >> 8]) & 1);
+    if (!simple_pod_regs(cur)) break;  // this pod takes the block-wide path
+    const bool plain = plain_pod_regs(cur);
+    const unsigned cls = (unsigned)cur.cls64;
+    const bool cand = live && rejected != cls && ((cur.tol >> tmpl_taintset[fl >> 8]) & 1);
     const uint32_t qp = ((fl >> 1) & 0xF) | cur.res;
     long long nq[kHotRes];
 #pragma unroll
-    for (int r = 0; r < kHotRes; ++r) {
-      nq[r] = q[r] + cur.req[r];
-      if (r < RH && ((qp >> r) & 1)) ok = ok && nq[r] <= b[r];
-    }
-    if (__any_sync(0xffffffffu, ok && !(fl & 1))) break;  // a candidate without a dominant option needs the type bitsets
+    for (int r = 0; r < kHotRes; ++r) nq[r] = q[r] + cur.req[r];
+    const int qf = cand ? quick_fit(nq, qp, RH, b, b2, fl) : 0;
+    const bool ok = qf != 0;
+    // a candidate whose resource test is not exact, or whose requirement verdict for this class is unknown, needs the full check
+    if (__any_sync(0xffffffffu, ok && (qf == 2 || !(plain || absorbed == cls)))) break;
     const unsigned long long wkey = warp_min_u64(ok ? key : ~0ull);
     if (wkey == ~0ull) break;  // nobody accepts: a new node has to be opened
     if (ok && key == wkey) {
@@ -654,12 +765,10 @@ __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, 
         fl |= (unsigned short)((cur.res & 0xF) << 1);
       }
       dirty = true;
+      rejected = KSCHED_NONE;
       s.assign[cur.pod] = NE + node;
       s.place_seq[cur.pod] = seq;
-      bool closed = false;
-#pragma unroll
-      for (int r = 0; r < kHotRes; ++r)
-        if (min_req[r] > 0 && q[r] + min_req[r] > b[r]) closed = true;
+      const bool closed = node_closed(q, min_req, RH, b, b2, fl);
       if (closed) {  // the node leaves the active set
         for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + node] = q[r];
         s.nn_count[node] = count;
@@ -685,9 +794,11 @@ __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, 
   if (live) {
     hs->key[slot] = key;
 #pragma unroll
-    for (int r = 0; r < kHotRes; ++r) { hs->q[r][slot] = q[r]; hs->bound[r][slot] = b[r]; }
+    for (int r = 0; r < kHotRes; ++r) { hs->q[r][slot] = q[r]; hs->bound[r][slot] = b[r]; hs->bound2[r][slot] = b2[r]; }
     hs->node[slot] = node;
     hs->flags[slot] = fl;
+    hs->absorbed[slot] = absorbed;
+    hs->rejected[slot] = rejected;
     if (dirty) {
       s.nn_count[node] = (int)(key >> 32);
       s.nn_tb[node] = (int)((unsigned)key ^ 0x80000000u);
@@ -719,7 +830,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   HotSmem* hs = reinterpret_cast<HotSmem*>(dyn_smem);
   int64_t* sm_alloc = reinterpret_cast<int64_t*>(dyn_smem + sizeof(HotSmem));
-  const Hot H{hs, s.ov_key, s.ov_q, s.ov_bound, s.ov_node, s.ov_flags, MAXN};
+  const Hot H{hs, s.ov_key, s.ov_q, s.ov_bound, s.ov_bound2, s.ov_node, s.ov_flags, s.ov_absorbed, s.ov_rejected, MAXN};
   if (s.alloc_in_smem)
     for (int i = tid; i < R * c.n_types; i += blockDim.x) sm_alloc[i] = c.alloc_sorted[i];
 
@@ -761,7 +872,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
 
   while (qlen > 0) {
     // ---- register-resident mode (see warp_resident_loop): entered when the next pod is plain and <= 32 nodes are open
-    if (fast_allowed && qi < s.n_pods && n_active > 0 && n_active <= 32 && plain_pod_regs(nxt) && !nxt.hpc && !nxt.hpe) {
+    if (fast_allowed && qi < s.n_pods && n_active > 0 && n_active <= 32 && simple_pod_regs(nxt)) {
       __syncthreads();
       if (tid == 0) { wio.qi = qi; wio.head = head; wio.qlen = qlen; wio.tick = tick; wio.seq = seq; wio.n_active = n_active; wio.add_calls = add_calls; }
       __syncthreads();
@@ -796,7 +907,9 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
     bool done = false;
     const bool plain_pod = ((cur.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0 && cur.itype == KSCHED_NONE && cur.hostname == KSCHED_NONE &&
                            cur.topo_begin == cur.topo_end;
-    if (fast_allowed && plain_pod && n_active > 0 && n_active <= kActCap) {
+    const bool simple_pod = simple_pod_regs(cur);
+    const unsigned cur_cls = (unsigned)cur.cls64;
+    if (fast_allowed && (plain_pod || simple_pod) && n_active > 0 && n_active <= kActCap) {
       unsigned long long mine = ~0ull;
       int best_a = -1;
       long long bq[kHotRes] = {0, 0, 0, 0};
@@ -805,17 +918,16 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
         if (key >= mine) continue;
         const unsigned short fl = hs->flags[a];
         if (!((cur.tol >> tmpl_taintset[fl >> 8]) & 1)) continue;
+        if (simple_pod && hs->rejected[a] == cur_cls) continue;  // memo: refused this class, untouched since
         const uint32_t qp = ((fl >> 1) & 0xF) | cur.res;
-        long long q[kHotRes];
-        bool ok = true;
+        long long q[kHotRes], b1[kHotRes], b2[kHotRes];
 #pragma unroll
-        for (int r = 0; r < kHotRes; ++r) {
-          q[r] = hs->q[r][a] + cur.req[r];
-          if (r < RH && ((qp >> r) & 1)) ok = ok && q[r] <= hs->bound[r][a];
-        }
-        if (!ok) continue;
+        for (int r = 0; r < kHotRes; ++r) { q[r] = hs->q[r][a] + cur.req[r]; b1[r] = hs->bound[r][a]; b2[r] = hs->bound2[r][a]; }
+        const int qf = quick_fit(q, qp, RH, b1, b2, fl);
+        if (qf == 0) continue;
         if (cur.hpc && (s.nn_hp[hs->node[a]] & cur.hpc)) continue;
-        if (!(fl & 1)) { mine = 0; break; }  // no dominant option: this pod takes the generic path
+        // inexact resource test, or an unknown requirement verdict for this class: the pod takes the generic path
+        if (qf == 2 || !(plain_pod || (simple_pod && hs->absorbed[a] == cur_cls))) { mine = 0; break; }
         mine = key;
         best_a = a;
 #pragma unroll
@@ -841,9 +953,11 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
           s.nn_count[n] = count;
           s.nn_tb[n] = -(tick + 1);
           H.key(a) = order_key(count, -(tick + 1));
-          bool closed = false;
-          for (int r = 0; r < RH; ++r)
-            if (s.min_req[r] > 0 && bq[r] + s.min_req[r] > H.bound(r, a)) closed = true;
+          H.rejected(a) = KSCHED_NONE;
+          long long cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+          for (int r = 0; r < kHotRes; ++r) { cb1[r] = H.bound(r, a); cb2[r] = H.bound2(r, a); }
+          const bool closed = node_closed(bq, s.min_req, RH, cb1, cb2, H.flags(a));
           s.assign[cur.pod] = NE + n;
           s.place_seq[cur.pod] = seq;
           if (closed) {
@@ -862,6 +976,9 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
       }
     }
     if (!done) {
+#ifdef KSCHED_PROFILE_PACK
+      if (tid == 0) s.counters[8 + 9] += 1;
+#endif
       LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited};
       generic_step(p, X, cur, first_pass, fpos_first, L);
       head = L.head; qlen = L.qlen; n_new = L.n_new; n_active = L.n_active; tick = L.tick; seq = L.seq; parity = L.parity; fatal = L.fatal;
@@ -883,7 +1000,8 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
     s.counters[4] = fatal;
     s.counters[5] = add_calls;
 #ifdef KSCHED_PROFILE_PACK
-    for (int i = 0; i < 10; ++i) s.counters[8 + i] = pk_acc[i];
+    s.counters[8 + 6] = pk_acc[0] + pk_acc[1] + pk_acc[2] + pk_acc[3] + pk_acc[4];  // block-wide fast path cycles
+    s.counters[8 + 7] = pk_acc[5];                                                       // cycles inside generic calls (incl. call)
 #endif
   }
 }

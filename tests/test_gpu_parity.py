@@ -68,22 +68,45 @@ def test_multi_node_consolidation_matches_oracle(pkg, oracle):
 
 
 def test_feasibility_matrix_matches_fresh_node_options(pkg, oracle):
-    """K1: F[p, v, :] must equal the option set of a fresh node of template v holding only pod p."""
-    problem = pkg.Problem.synth(3, 250 * 8, 1000, 42, 0)
-    rs = pkg.ResidentSolve(problem)
-    rs.load()
-    rs.run()
-    res, feas, best = rs.download(want_feasibility=True)
-    n_templates = rs.dims["templates"]
-    # single-pod problems through the oracle give the reference answer for one (pod, template-order) pair
-    import json
+    """K1: F[p, v, :] must equal the option set of a fresh node of template v that holds only pod p
+    (Node.Add on a new node, node.go:62-107) — checked for every (pod, provisioner) pair against the oracle."""
+    import copy
+    from fuzz_problems import random_problem
     checked = 0
-    for p in range(0, 2000, 250):  # one pod per deployment
-        single = pkg.Problem.synth(3, 250 * 8, 1000, 42, 0)
-        # oracle on the full batch is not needed: a fresh node's options only depend on the pod itself
-        bits = feas[p]
-        for v in range(n_templates):
-            cols = [i for i in range(1000) if (int(bits[v][i // 64]) >> (i % 64)) & 1]
-            checked += 1
-            assert cols == sorted(cols)
-    assert checked == 8 * n_templates
+    for seed in range(60):
+        prob = random_problem(seed)
+        prob["nodes"] = []
+        prob["daemonSetPods"] = []
+        for pr in prob["provisioners"]:
+            pr.pop("limits", None)
+        for pd in prob["pods"]:
+            for k in ("topologySpreadConstraints", "podAntiAffinity", "podAffinity"):
+                pd.pop(k, None)
+        # weight order is the template order of the kernel
+        order = sorted(range(len(prob["provisioners"])), key=lambda i: -prob["provisioners"][i].get("weight", 0))
+        problem = pkg.Problem.from_dict(prob)
+        rs = pkg.ResidentSolve(problem)
+        rs.load()
+        rs.run()
+        _, feas, best = rs.download(want_feasibility=True)
+        n_types = len(prob["instanceTypes"])
+        for p_i, pd in enumerate(prob["pods"]):
+            for v, prov_i in enumerate(order):
+                single = copy.deepcopy(prob)
+                single["pods"] = [pd]
+                single["provisioners"] = [prob["provisioners"][prov_i]]
+                want = pkg.Result()
+                assert oracle.solve(pkg.Problem.from_dict(single), want) == 0, want.error
+                w = want.to_dict()
+                # relaxation changes the pod: K1's row describes the unrelaxed pod only
+                expect = w["newNodes"][0]["options"] if (w["assign"][0] >= 0 and w["relax"][0] == 0) else None
+                got = [i for i in range(n_types) if (int(feas[p_i][v][i // 64]) >> (i % 64)) & 1]
+                if expect is None:
+                    if w["relax"][0] == 0:
+                        assert got == [], (seed, p_i, v)
+                else:
+                    assert got == expect, (seed, p_i, v)
+                checked += 1
+            any_col = any(int(x) for x in feas[p_i].ravel())
+            assert (int(best[p_i]) != 2 ** 64 - 1) == any_col
+    assert checked > 1500
