@@ -38,6 +38,8 @@ def build_product(force=False, verbose_ptxas=False):
            "-I", ROOT / "include", "-I", PKG / "host", "-I", PKG / "csrc", "-o", out, *srcs, "-lnccl"]
     if verbose_ptxas:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("KSCHED_PROFILE_K1"):
+        cmd.insert(1, "-DKSCHED_PROFILE_K1")
     if os.environ.get("KSCHED_PROFILE_PACK"):
         cmd.insert(1, "-DKSCHED_PROFILE_PACK")
     _run(cmd)

@@ -168,76 +168,17 @@ struct K1Params {
   unsigned long long* best;    // [n_pods]
   int word_begin, word_end;    // column shard (u32 words) this device computes
   int alloc_in_smem;           // the sorted allocatable arrays fit in the CTA's shared memory
+  long long* dbg;              // optional cycle counters (KSCHED_PROFILE_K1)
+  int tables_in_smem;          // valset / absent / negempty / offset / anyoffer / member are staged too
+  int n_valrows, n_offrows;
 };
 
-constexpr int kK1Threads = 512;
-constexpr int kK1Cache = 16;  // per-lane words of the previous row's result kept for identical consecutive rows
-
-// Shared-memory staging: the small tables every row evaluation walks with DEPENDENT loads (templates, key info, the
-// value->row maps, the sorted allocatable arrays of the Fits binary search) are copied once per CTA; the wide column
-// bitsets (valset / fitset / member / offset) stay in global memory and are read one coalesced word per lane.
-// Each warp owns a CONTIGUOUS chunk of the FFD-ordered pod-row matrix: consecutive rows are very often identical in
-// every field that matters to feasibility (same deployment), and then the previous result is written out again.
-__global__ void __launch_bounds__(kK1Threads) feasibility_kernel(K1Params p) {
-  extern __shared__ __align__(16) unsigned char k1_smem[];
-  DevCatalog c = p.cat;
-  const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
-  {
-    unsigned char* ptr = k1_smem;
-    ksched_template* s_tmpl = reinterpret_cast<ksched_template*>(ptr); ptr += sizeof(ksched_template) * V;
-    ksched_keyinfo* s_keys = reinterpret_cast<ksched_keyinfo*>(ptr); ptr += sizeof(ksched_keyinfo) * KSCHED_MAX_KEYS;
-    int64_t* s_alloc = reinterpret_cast<int64_t*>(ptr); ptr += p.alloc_in_smem ? sizeof(int64_t) * R * T : 0;
-    int16_t* s_valrow = reinterpret_cast<int16_t*>(ptr); ptr += sizeof(int16_t) * KSCHED_MAX_KEYS * 64;
-    int16_t* s_offrow = reinterpret_cast<int16_t*>(ptr);
-    const uint32_t* gt = reinterpret_cast<const uint32_t*>(c.templates);
-    uint32_t* st = reinterpret_cast<uint32_t*>(s_tmpl);
-    for (int i = threadIdx.x; i < (int)(sizeof(ksched_template) * V / 4); i += blockDim.x) st[i] = gt[i];
-    const uint32_t* gk = reinterpret_cast<const uint32_t*>(c.keys);
-    uint32_t* sk = reinterpret_cast<uint32_t*>(s_keys);
-    for (int i = threadIdx.x; i < (int)(sizeof(ksched_keyinfo) * NK / 4); i += blockDim.x) sk[i] = gk[i];
-    if (p.alloc_in_smem)
-      for (int i = threadIdx.x; i < R * T; i += blockDim.x) s_alloc[i] = c.alloc_sorted[i];
-    for (int i = threadIdx.x; i < NK * 64; i += blockDim.x) s_valrow[i] = c.valrow[i];
-    if (threadIdx.x < 64) s_offrow[threadIdx.x] = c.offrow[threadIdx.x];
-    c.templates = s_tmpl;
-    c.keys = s_keys;
-    if (p.alloc_in_smem) c.alloc_sorted = s_alloc;
-    c.valrow = s_valrow;
-    c.offrow = s_offrow;
-  }
-  __syncthreads();
-
+// One row's feasibility against every (template, column): the rarely taken path of feasibility_kernel (rows that differ
+// from their predecessor), kept out of line so that the batched streaming loop stays small.
+__device__ __noinline__ unsigned long long k1_compute_row(const DevCatalog& c, const K1Params& p, int j, uint64_t word, uint32_t* cache, bool cacheable) {
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int chunk = (p.n_pods + nwarps - 1) / nwarps;
-  const int j0 = warp * chunk, j1 = min(p.n_pods, j0 + chunk);
-  const int wpl = (W32 + 31) >> 5;  // column words per lane
-  const bool cacheable = V * wpl <= kK1Cache;
-  // fields of the row that feasibility depends on (requests, requirement masks, meta, tolerations, res_present, itype_req)
-  const uint64_t cmp_mask = lane <= 25 ? ~0ull : ((lane == 28 || lane == 29) ? 0xFFFFFFFFull : 0ull);
-  uint32_t cache[kK1Cache];
-  unsigned long long best_prev = kNoBest;
-  uint64_t prev_word = 0;
-  bool have_prev = false;
-
-  uint64_t next_word = 0;
-  if (j0 < j1) next_word = __ldg(p.rows + (size_t)j0 * KSCHED_ROW_WORDS + lane);
-  for (int j = j0; j < j1; ++j) {
-    const uint64_t word = next_word;  // lane l holds u64 word l of the 256-byte row
-    if (j + 1 < j1) next_word = __ldg(p.rows + (size_t)(j + 1) * KSCHED_ROW_WORDS + lane);
-    const bool same = have_prev && cacheable && __all_sync(0xffffffffu, ((word ^ prev_word) & cmp_mask) == 0);
-    if (same) {
-      for (int v = 0; v < V; ++v)
-        for (int wi = 0; wi < wpl; ++wi) {
-          const int w = wi * 32 + lane;
-          if (w < W32 && w >= p.word_begin && w < p.word_end) p.F[((size_t)j * V + v) * W32 + w] = cache[v * wpl + wi];
-        }
-      if (lane == 0) p.best[j] = best_prev;
-      continue;
-    }
-    prev_word = word;
-    have_prev = true;
+  const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
+  const int wpl = (W32 + 31) >> 5;
     const uint64_t meta = __shfl_sync(0xffffffffu, word, 24);
     const uint64_t tolerated = __shfl_sync(0xffffffffu, word, 25);
     const uint32_t pod_res_present = (uint32_t)__shfl_sync(0xffffffffu, word, 28);
@@ -331,9 +272,133 @@ __global__ void __launch_bounds__(kK1Threads) feasibility_kernel(K1Params p) {
         best = key < best ? key : best;
       }
     }
+  return best;
+}
+
+
+constexpr int kK1Threads = 512;
+constexpr int kK1Cache = 16;  // per-lane words of the previous row's result kept for identical consecutive rows
+
+struct K1Params;
+
+// Shared-memory staging: the small tables every row evaluation walks with DEPENDENT loads (templates, key info, the
+// value->row maps, the sorted allocatable arrays of the Fits binary search) are copied once per CTA; the wide column
+// bitsets (valset / fitset / member / offset) stay in global memory and are read one coalesced word per lane.
+// Each warp owns a CONTIGUOUS chunk of the FFD-ordered pod-row matrix: consecutive rows are very often identical in
+// every field that matters to feasibility (same deployment), and then the previous result is written out again.
+__global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel(K1Params p) {
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+#ifdef KSCHED_PROFILE_K1
+  long long t_start = clock64(), t_stage = 0, t_compute = 0, n_compute = 0;
+#endif
+  DevCatalog c = p.cat;
+  const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
+  {
+    unsigned char* ptr = k1_smem;
+    ksched_template* s_tmpl = reinterpret_cast<ksched_template*>(ptr); ptr += sizeof(ksched_template) * V;
+    ksched_keyinfo* s_keys = reinterpret_cast<ksched_keyinfo*>(ptr); ptr += sizeof(ksched_keyinfo) * KSCHED_MAX_KEYS;
+    int64_t* s_alloc = reinterpret_cast<int64_t*>(ptr); ptr += p.alloc_in_smem ? sizeof(int64_t) * R * T : 0;
+    int16_t* s_valrow = reinterpret_cast<int16_t*>(ptr); ptr += sizeof(int16_t) * KSCHED_MAX_KEYS * 64;
+    int16_t* s_offrow = reinterpret_cast<int16_t*>(ptr);
+    // cp.async (LDGSTS): every 4-byte element of every table is requested before anything is waited on, so the whole
+    // staging costs about one memory round trip instead of one per table.
+    auto stage4 = [&](void* dst, const void* src, int n_words) {
+      const uint32_t* g = reinterpret_cast<const uint32_t*>(src);
+      for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(dst) + i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g + i));
+      }
+    };
+    stage4(s_tmpl, c.templates, (int)(sizeof(ksched_template) * V / 4));
+    stage4(s_keys, c.keys, (int)(sizeof(ksched_keyinfo) * NK / 4));
+    if (p.alloc_in_smem) stage4(s_alloc, c.alloc_sorted, R * T * 2);
+    stage4(s_valrow, c.valrow, NK * 64 / 2);
+    stage4(s_offrow, c.offrow, 32);
+    if (p.tables_in_smem) {
+      // the narrow column bitsets: one 4*W32-byte row per (key,value) / key / offering / template
+      uint32_t* sp = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_offrow) + sizeof(int16_t) * 64);
+      auto stage = [&](const uint32_t*& tbl, int rows) {
+        stage4(sp, tbl, rows * W32);
+        tbl = sp;
+        sp += rows * W32;
+      };
+      stage(c.valset, p.n_valrows);
+      stage(c.absent, NK);
+      stage(c.negempty, NK);
+      stage(c.offset, p.n_offrows);
+      stage(c.anyoffer, 1);
+      stage(c.member, V);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    c.templates = s_tmpl;
+    c.keys = s_keys;
+    if (p.alloc_in_smem) c.alloc_sorted = s_alloc;
+    c.valrow = s_valrow;
+    c.offrow = s_offrow;
+  }
+  __syncthreads();
+#ifdef KSCHED_PROFILE_K1
+  t_stage = clock64() - t_start;
+#endif
+
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int chunk = (p.n_pods + nwarps - 1) / nwarps;
+  const int j0 = warp * chunk, j1 = min(p.n_pods, j0 + chunk);
+  const int wpl = (W32 + 31) >> 5;  // column words per lane
+  const bool cacheable = V * wpl <= kK1Cache;
+  // fields of the row that feasibility depends on (requests, requirement masks, meta, tolerations, res_present, itype_req)
+  const uint64_t cmp_mask = lane <= 25 ? ~0ull : ((lane == 28 || lane == 29) ? 0xFFFFFFFFull : 0ull);
+  uint32_t cache[kK1Cache];
+  unsigned long long best_prev = kNoBest;
+  uint64_t prev_word = 0;
+  bool have_prev = false;
+
+  // rows are fetched kBatch at a time (kBatch independent 256-byte loads in flight per warp), then consumed in order
+  constexpr int kBatch = 16;
+  uint64_t wbuf[kBatch];
+  for (int jb = j0; jb < j1; jb += kBatch) {
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) wbuf[b] = jb + b < j1 ? __ldg(p.rows + (size_t)(jb + b) * KSCHED_ROW_WORDS + lane) : 0;
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+    const int j = jb + b;
+    if (j >= j1) break;
+    const uint64_t word = wbuf[b];  // lane l holds u64 word l of the 256-byte row
+    const bool same = have_prev && cacheable && __all_sync(0xffffffffu, ((word ^ prev_word) & cmp_mask) == 0);
+    if (same) {
+      for (int v = 0; v < V; ++v)
+        for (int wi = 0; wi < wpl; ++wi) {
+          const int w = wi * 32 + lane;
+          if (w < W32 && w >= p.word_begin && w < p.word_end) p.F[((size_t)j * V + v) * W32 + w] = cache[v * wpl + wi];
+        }
+      if (lane == 0) p.best[j] = best_prev;
+      continue;
+    }
+    prev_word = word;
+    have_prev = true;
+#ifdef KSCHED_PROFILE_K1
+    long long tc0 = clock64();
+#endif
+    const unsigned long long best = k1_compute_row(c, p, j, word, cache, cacheable);
+#ifdef KSCHED_PROFILE_K1
+    t_compute += clock64() - tc0; ++n_compute;
+#endif
     best_prev = best;
     if (lane == 0) p.best[j] = best;
+    }
   }
+#ifdef KSCHED_PROFILE_K1
+  if (p.dbg && lane == 0) {
+    atomicMax((unsigned long long*)&p.dbg[0], (unsigned long long)t_stage);
+    atomicMax((unsigned long long*)&p.dbg[1], (unsigned long long)t_compute);
+    atomicMax((unsigned long long*)&p.dbg[2], (unsigned long long)(clock64() - t_start));
+    atomicMax((unsigned long long*)&p.dbg[3], (unsigned long long)n_compute);
+    atomicAdd((unsigned long long*)&p.dbg[4], (unsigned long long)n_compute);
+    atomicAdd((unsigned long long*)&p.dbg[5], (unsigned long long)t_compute);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -840,8 +905,10 @@ struct ksched_handle {
   DevBuf<int16_t> d_valrow, d_offrow;
   DevBuf<uint32_t> d_valset, d_absent, d_negempty, d_offset, d_anyoffer, d_member, d_fitset, d_domset;
   std::vector<ksched_template> h_templates;
+  int n_valrows = 1, n_offrows = 1;
   // problem
   bool uploaded = false;
+  bool sorted = false;  // the FFD-ordered pod-row matrix of the uploaded problem exists
   int n_pods = 0, n_classes = 0, n_existing = 0, n_groups = 0, max_new = 0, n_hostgroups = 0;
   DevBuf<ksched_pod_row> d_classes;
   DevBuf<uint32_t> d_pod_pos, d_pod_class0, d_pod_class, d_uid_rank, d_order, d_idx_tmp, d_itype_sets, d_queue, d_last_epoch;
@@ -869,7 +936,7 @@ struct ksched_handle {
   DevBuf<uint64_t> d_ex_vals, d_ex_vals0, d_ex_meta, d_ex_meta0, d_ex_hp, d_ex_hp0, d_nn_vals, d_nn_meta, d_nn_hp, d_grp_registered,
       d_grp_registered0;
   DevBuf<uint16_t> d_grp_host, d_grp_host0;
-  DevBuf<long long> d_counters;
+  DevBuf<long long> d_counters, d_k1dbg;
   DevBuf<uint32_t> d_flush;
   size_t cub_tmp_bytes = 0;
   int64_t min_req[KSCHED_MAX_RES] = {0};
@@ -1048,6 +1115,8 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   CUDA_TRY(h, upload_vec(h, h->d_fitset, fitset));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->h_templates.assign(cat->templates, cat->templates + V);
+  h->n_valrows = (int)(valset.size() / W32);
+  h->n_offrows = (int)(offset.size() / W32);
   DevCatalog& c = h->cat;
   c.n_keys = NK; c.n_res = R; c.n_types = T; c.n_templates = V; c.W32 = W32;
   c.keys = h->d_keys.ptr;
@@ -1250,6 +1319,7 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->uploaded = true;
+  h->sorted = false;
   return KSCHED_OK;
 }
 
@@ -1273,6 +1343,7 @@ static int run_sort(ksched_handle* h) {
   const int gblocks = std::min((P + 7) / 8, 148 * 8);
   gather_rows_kernel<<<gblocks, 256, 0, h->stream>>>(P, h->d_classes.ptr, h->d_pod_class.ptr, h->d_order.ptr, h->d_rows.ptr);
   h->tm.sort_launches = 7;
+  h->sorted = true;
   return KSCHED_OK;
 }
 
@@ -1299,14 +1370,34 @@ static int run_feasibility(ksched_handle* h) {
   const DevCatalog& c = h->cat;
   const size_t alloc_bytes = (size_t)c.n_res * c.n_types * sizeof(int64_t);
   k1.alloc_in_smem = alloc_bytes <= (size_t)(128 << 10) ? 1 : 0;
-  const size_t smem = sizeof(ksched_template) * c.n_templates + sizeof(ksched_keyinfo) * KSCHED_MAX_KEYS + (k1.alloc_in_smem ? alloc_bytes : 0) +
-                      sizeof(int16_t) * KSCHED_MAX_KEYS * 64 + sizeof(int16_t) * 64;
+  size_t smem = sizeof(ksched_template) * c.n_templates + sizeof(ksched_keyinfo) * KSCHED_MAX_KEYS + (k1.alloc_in_smem ? alloc_bytes : 0) +
+                sizeof(int16_t) * KSCHED_MAX_KEYS * 64 + sizeof(int16_t) * 64;
+  k1.n_valrows = h->n_valrows;
+  k1.n_offrows = h->n_offrows;
+  const size_t table_bytes = (size_t)(h->n_valrows + 2 * c.n_keys + h->n_offrows + 1 + c.n_templates) * c.W32 * sizeof(uint32_t);
+  k1.tables_in_smem = smem + table_bytes <= (size_t)(160 << 10) ? 1 : 0;
+  if (k1.tables_in_smem) smem += table_bytes;
   // one CTA per SM at most; every warp takes a contiguous chunk of >= 8 rows
   const int warps_per_block = kK1Threads / 32;
   const int want_warps = std::max(1, (h->n_pods + 7) / 8);
   const int blocks = std::max(1, std::min(148, (want_warps + warps_per_block - 1) / warps_per_block));
   CUDA_TRY(h, cudaFuncSetAttribute(feasibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1.dbg = nullptr;
+#ifdef KSCHED_PROFILE_K1
+  CUDA_TRY(h, h->d_k1dbg.ensure(8));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_k1dbg.ptr, 0, 8 * sizeof(long long), h->stream));
+  k1.dbg = h->d_k1dbg.ptr;
+#endif
   feasibility_kernel<<<blocks, kK1Threads, smem, h->stream>>>(k1);
+#ifdef KSCHED_PROFILE_K1
+  {
+    long long dbg[8];
+    cudaMemcpyAsync(dbg, h->d_k1dbg.ptr, sizeof dbg, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    fprintf(stderr, "[k1 profile] blocks=%d max cycles: stage=%lld compute=%lld total=%lld max_computes_per_warp=%lld | total computes=%lld avg compute cycles=%lld\n",
+            blocks, dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[4] ? dbg[5] / dbg[4] : 0);
+  }
+#endif
   h->tm.feasibility_launches = 1;
   const long long C = (long long)h->cat.n_templates * h->cat.n_types;
   h->tm.feasibility_bytes = (long long)h->n_pods * 256 + C * 256 + (long long)h->n_pods * C / 8;
@@ -1428,6 +1519,10 @@ int ksched_run_feasibility_only(ksched_handle* h, int do_flush, float* elapsed_u
   if (!h || !h->uploaded) return KSCHED_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
   int rc;
+  if (!h->sorted) {  // K0 first: the kernel streams the FFD-ordered pod-row matrix
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)h->n_pods * 4, cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = run_sort(h)) != KSCHED_OK) return rc;
+  }
   if (do_flush && (rc = flush_l2(h)) != KSCHED_OK) return rc;
   CUDA_TRY(h, cudaEventRecord(h->ev[5], h->stream));
   if ((rc = run_feasibility(h)) != KSCHED_OK) return rc;
