@@ -733,9 +733,12 @@ __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, 
   unsigned short fl = live ? hs->flags[lane] : 0;
   unsigned absorbed = live ? hs->absorbed[lane] : KSCHED_NONE, rejected = live ? hs->rejected[lane] : KSCHED_NONE;
   const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
+  // Consecutive pods of the queue usually belong to the same class (identical row): only the next pod's id and class are
+  // prefetched; the row's words are reloaded on a class change.
   PodRegs cur = load_pod_regs(ffd_rows + qi, s.order[qi]);
-  PodRegs nxt = cur;
-  if (qi + 1 < s.n_pods) nxt = load_pod_regs(ffd_rows + qi + 1, s.order[qi + 1]);
+  uint32_t npod = 0;
+  uint64_t ncls = ~0ull;
+  if (qi + 1 < s.n_pods) { npod = s.order[qi + 1]; ncls = ffd_rows[qi + 1].reserved; }
   long long min_req[kHotRes];
 #pragma unroll
   for (int r = 0; r < kHotRes; ++r) min_req[r] = r < RH ? s.min_req[r] : 0;
@@ -782,9 +785,10 @@ __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, 
     head = head + 1 == qcap ? 0 : head + 1;
     --qlen;
     if (qi >= s.n_pods || qlen == 0) break;
-    cur = nxt;
-    if (qi + 1 < s.n_pods) nxt = load_pod_regs(ffd_rows + qi + 1, s.order[qi + 1]);
-    if (lane < 2 && qi + 24 < s.n_pods) prefetch_l2(reinterpret_cast<const char*>(ffd_rows + qi + 24) + lane * 128);
+    if (ncls == cur.cls64) { cur.pod = npod; cur.row = ffd_rows + qi; }
+    else cur = load_pod_regs(ffd_rows + qi, npod);
+    if (qi + 1 < s.n_pods) { npod = s.order[qi + 1]; ncls = ffd_rows[qi + 1].reserved; }
+    if (lane == 0 && qi + 32 < s.n_pods) prefetch_l2(reinterpret_cast<const char*>(ffd_rows + qi + 32) + 128);  // the line holding `reserved`
     if (lane == 2 && (qi & 31) == 0 && qi + 96 < s.n_pods) prefetch_l2(s.order + qi + 96);
   }
   // write the lanes back, compacted
