@@ -107,6 +107,8 @@ def lib():
     L.kh_gpu_load_catalog.argtypes = [C.c_void_p]
     L.kh_consolidate.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                  C.POINTER(C.c_int)]
+    L.kh_consolidate_candidates.argtypes = [C.c_void_p]
+    L.kh_consolidate_probe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
     L.kh_mask_intersection.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_longlong)]
     L.kh_mask_allowed.restype = C.c_longlong
     L.kh_mask_allowed.argtypes = [C.c_char_p, C.c_char_p]
@@ -277,6 +279,83 @@ class MultiNodeConsolidation:
         _check(rc)
         return {"action": out4[0], "nodes_removed": out4[1], "simulations": out4[2], "options": list(opts[:out4[3]]),
                 "probes": list(probes[:npr.value]), "probe_actions": list(acts[:npr.value])}
+
+
+    def candidates(self):
+        return int(lib().kh_consolidate_candidates(self.problem.ptr))
+
+    def probe(self, count):
+        """computeConsolidation over the `count` cheapest candidates (one simulateScheduling on this rank's GPU)."""
+        opts = (C.c_int * 8192)()
+        n = C.c_int()
+        rc = lib().kh_consolidate_probe(self.problem.ptr, int(count), opts, 8192, C.byref(n))
+        if rc < 0:
+            _check(rc)
+        return (int(rc), list(opts[:n.value]))
+
+    def first_n_node_consolidation_option_sharded(self, rank=0, world=1, all_gather=None):
+        """The same binary search with its probes sharded over ranks (consolidation probes are
+        independent simulations). Each round evaluates, in parallel, every probe the sequential search could reach within
+        the next log2(world+1) steps and then replays the sequential decisions on the gathered outcomes, so the command
+        is identical to first_n_node_consolidation_option for any world size. `all_gather(obj) -> [obj per rank]`
+        (torch.distributed.all_gather_object wrapped by the caller); None = single process."""
+        n = self.candidates()
+
+        def probe_many(counts):
+            mine = {c: self.probe(c) for i, c in enumerate(counts) if i % world == rank}
+            if all_gather is None or world == 1:
+                return mine
+            merged = {}
+            for part in all_gather(mine):
+                merged.update(part)
+            return merged
+
+        action, count, options, rounds, probes = speculative_binary_search(n, probe_many, world)
+        return {"action": action, "nodes_removed": count, "options": options, "rounds": rounds, "probes": probes}
+
+
+def speculation_frontier(lo, hi, width):
+    """Probe sizes (mid+1) of the binary-search decision tree rooted at [lo, hi], breadth first, at most `width` of them
+    and always whole levels first (multinodeconsolidation.go:84-112 visits exactly one root-to-leaf path of this tree)."""
+    out, level = [], [(lo, hi)]
+    while level and len(out) < width:
+        nxt = []
+        for (a, b) in level:
+            if a > b:
+                continue
+            mid = (a + b) // 2
+            if len(out) < width:
+                out.append(mid + 1)
+            nxt.append((mid + 1, b))
+            nxt.append((a, mid - 1))
+        level = nxt
+    return out
+
+
+def speculative_binary_search(n_candidates, probe_many, width):
+    """firstNNodeConsolidationOption (multinodeconsolidation.go:74-114) with `width` probes evaluated per round.
+    probe_many(list of probe sizes) -> {size: (action, options)}. Returns (action, nodes_removed, options, rounds, probes):
+    the decisions replayed are the sequential ones, so the answer does not depend on `width`."""
+    if n_candidates < 2:
+        return 0, 0, [], 0, []
+    lo, hi = 1, n_candidates - 1
+    last = (0, 0, [])
+    rounds, path = 0, []
+    while lo <= hi:
+        known = probe_many(speculation_frontier(lo, hi, max(1, width)))
+        rounds += 1
+        while lo <= hi:
+            mid = (lo + hi) // 2
+            if mid + 1 not in known:
+                break
+            action, options = known[mid + 1]
+            path.append(mid + 1)
+            if action in (1, 2):
+                last = (action, mid + 1, options)
+                lo = mid + 1
+            else:
+                hi = mid - 1
+    return last[0], last[1], last[2], rounds, path
 
 
 class ResidentSolve:

@@ -276,102 +276,134 @@ int kh_gpu_load_catalog(Encoded* E) {
 }
 int kh_gpu_timings(ksched_timings* t) { return g_handle ? ksched_get_timings(g_handle, t) : KSCHED_ERR_INVALID; }
 
-// MultiNodeConsolidation.firstNNodeConsolidationOption on the GPU path: one ksched_solve per probe.
+}  // extern "C"
+
+// ---- consolidation (deprovisioning/consolidation.go, multinodeconsolidation.go) on the GPU path ------------------
+namespace {
+struct Cand { int node; const InstanceType* it; std::string ct, zone; double cost; };
+struct Cmd { int action = 0; std::vector<int> options; };
+
+std::vector<Cand> sorted_candidates(const Problem* P) {
+  std::vector<Cand> cands;
+  for (size_t i = 0; i < P->nodes.size(); ++i) {
+    const StateNode& n = P->nodes[i];
+    if (!n.candidate) continue;
+    Cand c{(int)i, nullptr, "", "", n.disruption_cost};
+    auto itn = n.labels.find("node.kubernetes.io/instance-type");
+    if (itn != n.labels.end())
+      for (auto& t : P->instance_types) if (t.name == itn->second) c.it = &t;
+    auto ct = n.labels.find("karpenter.sh/capacity-type");
+    if (ct != n.labels.end()) c.ct = ct->second;
+    auto z = n.labels.find("topology.kubernetes.io/zone");
+    if (z != n.labels.end()) c.zone = z->second;
+    cands.push_back(c);
+  }
+  std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.cost < b.cost; });  // consolidation.go:100-103
+  return cands;
+}
+
+// computeConsolidation (consolidation.go:190-274) + filterOutSameType (multinodeconsolidation.go:132-165) for the
+// first `count` candidates: one simulateScheduling = one ksched_solve.
+Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int count) {
+  Cmd cmd;
+  std::vector<int> nodes;
+  for (int i = 0; i < count; ++i) nodes.push_back(cands[i].node);
+  auto E = khost::encode(*P, nodes);
+  E->problem.count_nodes_visited = g_count_visited;
+  ResultBuffers B;
+  int rc = solve_encoded(*E, B, false);
+  if (rc != KSCHED_OK) throw std::runtime_error(g_err);
+  size_t scheduled = 0;
+  for (auto a : B.assign) if (a >= 0) ++scheduled;
+  for (size_t p = 0; p < B.assign.size(); ++p)  // helpers.go:109-113: an uninitialised existing node was used
+    if (B.assign[p] >= 0 && (size_t)B.assign[p] < E->existing.size() && !E->existing_initialized[B.assign[p]]) return cmd;
+  if (scheduled != E->pods.size()) return cmd;
+  if (B.r.n_new_nodes == 0) { cmd.action = 1; return cmd; }
+  if (B.r.n_new_nodes != 1) return cmd;
+  double price = 0;  // getNodePrices consolidation.go:277-287
+  for (int i = 0; i < count; ++i) {
+    const Cand& c = cands[i];
+    if (!c.it) throw std::runtime_error("candidate without a known instance type");
+    bool ok = false;
+    for (auto& o : c.it->offerings) if (o.capacity_type == c.ct && o.zone == c.zone) { price += o.price; ok = true; break; }
+    if (!ok) throw std::runtime_error("unable to determine offering");
+  }
+  ksched_reqset reqs = B.nodes[0].reqs;
+  std::vector<int> opts;
+  const uint64_t* bits = &B.types[0];
+  for (size_t c = 0; c < E->type_input_index.size(); ++c)
+    if ((bits[c / 64] >> (c % 64)) & 1) opts.push_back(E->type_input_index[c]);
+  std::sort(opts.begin(), opts.end());
+  std::vector<int> kept;
+  for (int t : opts) if (worst_launch_price(*E, P->instance_types[t], reqs) < price) kept.push_back(t);  // filterByPrice
+  if (kept.empty()) return cmd;
+  bool all_spot = true;
+  for (int i = 0; i < count; ++i) if (cands[i].ct != "spot") all_spot = false;
+  if (all_spot && req_has(*E, reqs, "karpenter.sh/capacity-type", "spot")) return cmd;
+  if (req_has(*E, reqs, "karpenter.sh/capacity-type", "spot") && req_has(*E, reqs, "karpenter.sh/capacity-type", "on-demand")) {
+    // Requirements.Add(capacity-type In [spot]) (consolidation.go:262-265)
+    for (size_t k = 0; k < E->key_names.size(); ++k) {
+      if (E->key_names[k] != "karpenter.sh/capacity-type") continue;
+      uint64_t spot = 0;
+      for (size_t b = 0; b < E->key_values[k].size(); ++b) if (E->key_values[k][b] == "spot") spot = 1ull << b;
+      ksched::Req in{spot, 0, 0, true, false, false, false};
+      static const ksched_bounds zero{};
+      ksched::KeyMeta km{0, nullptr};
+      ksched_bounds tmp{};
+      ksched::req_store(reqs, &tmp, (int)k, ksched::key_add(ksched::req_load(reqs, &zero, (int)k), in, km));
+    }
+  }
+  std::set<std::string> existing_types;  // filterOutSameType
+  std::map<std::string, double> by_type;
+  for (int i = 0; i < count; ++i) {
+    const Cand& c = cands[i];
+    existing_types.insert(c.it->name);
+    for (auto& o : c.it->offerings)
+      if (o.capacity_type == c.ct && o.zone == c.zone) {
+        double ex = by_type.count(c.it->name) ? by_type[c.it->name] : std::numeric_limits<double>::max();
+        if (o.price < ex) by_type[c.it->name] = o.price;
+        break;
+      }
+  }
+  double max_price = std::numeric_limits<double>::max();
+  for (int t : kept) {
+    const std::string& name = P->instance_types[t].name;
+    if (existing_types.count(name) && by_type[name] < max_price) max_price = by_type[name];
+  }
+  std::vector<int> kept2;
+  for (int t : kept) if (worst_launch_price(*E, P->instance_types[t], reqs) < max_price) kept2.push_back(t);
+  if (kept2.empty()) return cmd;
+  cmd.action = 2;
+  cmd.options = kept2;
+  return cmd;
+}
+}  // namespace
+
+extern "C" {
+// number of consolidation candidates (nodes flagged `candidate`)
+int kh_consolidate_candidates(const Problem* P) { return (int)sorted_candidates(P).size(); }
+
+// One probe of the search: computeConsolidation over the `count` cheapest-to-disrupt candidates.
+// Returns the action (0 nothing, 1 delete, 2 replace) or a negative error; options = surviving replacement types.
+int kh_consolidate_probe(const Problem* P, int count, int* options, int options_cap, int* n_options) {
+  try {
+    auto cands = sorted_candidates(P);
+    if (count < 1 || count > (int)cands.size()) return fail(KSCHED_ERR_INVALID, "probe size out of range");
+    Cmd c = compute_consolidation(P, cands, count);
+    *n_options = (int)c.options.size();
+    for (size_t i = 0; i < c.options.size() && (int)i < options_cap; ++i) options[i] = c.options[i];
+    return c.action;
+  } catch (const std::exception& e) {
+    return fail(error_code(e), e.what());
+  }
+}
+
+// MultiNodeConsolidation.firstNNodeConsolidationOption (multinodeconsolidation.go:74-114): binary search, one probe per step.
 // out ints: [action, nodes_removed, simulations, n_options]; options = instance type indices.
 int kh_consolidate(const Problem* P, int* out4, int* options, int options_cap, int* probes, int* probe_actions, int probes_cap, int* n_probes) {
   try {
-    struct Cand { int node; const InstanceType* it; std::string ct, zone; double cost; };
-    std::vector<Cand> cands;
-    for (size_t i = 0; i < P->nodes.size(); ++i) {
-      const StateNode& n = P->nodes[i];
-      if (!n.candidate) continue;
-      Cand c{(int)i, nullptr, "", "", n.disruption_cost};
-      auto itn = n.labels.find("node.kubernetes.io/instance-type");
-      if (itn != n.labels.end())
-        for (auto& t : P->instance_types) if (t.name == itn->second) c.it = &t;
-      auto ct = n.labels.find("karpenter.sh/capacity-type");
-      if (ct != n.labels.end()) c.ct = ct->second;
-      auto z = n.labels.find("topology.kubernetes.io/zone");
-      if (z != n.labels.end()) c.zone = z->second;
-      cands.push_back(c);
-    }
-    std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.cost < b.cost; });  // consolidation.go:100-103
+    auto cands = sorted_candidates(P);
     int sims = 0;
-    struct Cmd { int action = 0; std::vector<int> options; };
-    auto compute = [&](int count) -> Cmd {  // computeConsolidation + filterOutSameType
-      Cmd cmd;
-      std::vector<int> nodes;
-      for (int i = 0; i < count; ++i) nodes.push_back(cands[i].node);
-      auto E = khost::encode(*P, nodes);
-      E->problem.count_nodes_visited = g_count_visited;
-      ResultBuffers B;
-      int rc = solve_encoded(*E, B, false);
-      if (rc != KSCHED_OK) throw std::runtime_error(g_err);
-      ++sims;
-      size_t scheduled = 0;
-      for (auto a : B.assign) if (a >= 0) ++scheduled;
-      for (size_t p = 0; p < B.assign.size(); ++p)  // helpers.go:109-113: an uninitialised existing node was used
-        if (B.assign[p] >= 0 && (size_t)B.assign[p] < E->existing.size() && !E->existing_initialized[B.assign[p]]) return cmd;
-      if (scheduled != E->pods.size()) return cmd;
-      if (B.r.n_new_nodes == 0) { cmd.action = 1; return cmd; }
-      if (B.r.n_new_nodes != 1) return cmd;
-      double price = 0;  // getNodePrices consolidation.go:277-287
-      for (int i = 0; i < count; ++i) {
-        const Cand& c = cands[i];
-        if (!c.it) throw std::runtime_error("candidate without a known instance type");
-        bool ok = false;
-        for (auto& o : c.it->offerings) if (o.capacity_type == c.ct && o.zone == c.zone) { price += o.price; ok = true; break; }
-        if (!ok) throw std::runtime_error("unable to determine offering");
-      }
-      ksched_reqset reqs = B.nodes[0].reqs;
-      std::vector<int> opts;
-      const uint64_t* bits = &B.types[0];
-      for (size_t c = 0; c < E->type_input_index.size(); ++c)
-        if ((bits[c / 64] >> (c % 64)) & 1) opts.push_back(E->type_input_index[c]);
-      std::sort(opts.begin(), opts.end());
-      std::vector<int> kept;
-      for (int t : opts) if (worst_launch_price(*E, P->instance_types[t], reqs) < price) kept.push_back(t);  // filterByPrice
-      if (kept.empty()) return cmd;
-      bool all_spot = true;
-      for (int i = 0; i < count; ++i) if (cands[i].ct != "spot") all_spot = false;
-      if (all_spot && req_has(*E, reqs, "karpenter.sh/capacity-type", "spot")) return cmd;
-      if (req_has(*E, reqs, "karpenter.sh/capacity-type", "spot") && req_has(*E, reqs, "karpenter.sh/capacity-type", "on-demand")) {
-        // Requirements.Add(capacity-type In [spot]) (consolidation.go:262-265)
-        for (size_t k = 0; k < E->key_names.size(); ++k) {
-          if (E->key_names[k] != "karpenter.sh/capacity-type") continue;
-          uint64_t spot = 0;
-          for (size_t b = 0; b < E->key_values[k].size(); ++b) if (E->key_values[k][b] == "spot") spot = 1ull << b;
-          ksched::Req in{spot, 0, 0, true, false, false, false};
-          static const ksched_bounds zero{};
-          ksched::KeyMeta km{0, nullptr};
-          ksched_bounds tmp{};
-          ksched::req_store(reqs, &tmp, (int)k, ksched::key_add(ksched::req_load(reqs, &zero, (int)k), in, km));
-        }
-      }
-      std::set<std::string> existing_types;  // filterOutSameType multinodeconsolidation.go:132-165
-      std::map<std::string, double> by_type;
-      for (int i = 0; i < count; ++i) {
-        const Cand& c = cands[i];
-        existing_types.insert(c.it->name);
-        for (auto& o : c.it->offerings)
-          if (o.capacity_type == c.ct && o.zone == c.zone) {
-            double ex = by_type.count(c.it->name) ? by_type[c.it->name] : std::numeric_limits<double>::max();
-            if (o.price < ex) by_type[c.it->name] = o.price;
-            break;
-          }
-      }
-      double max_price = std::numeric_limits<double>::max();
-      for (int t : kept) {
-        const std::string& name = P->instance_types[t].name;
-        if (existing_types.count(name) && by_type[name] < max_price) max_price = by_type[name];
-      }
-      std::vector<int> kept2;
-      for (int t : kept) if (worst_launch_price(*E, P->instance_types[t], reqs) < max_price) kept2.push_back(t);
-      if (kept2.empty()) return cmd;
-      cmd.action = 2;
-      cmd.options = kept2;
-      return cmd;
-    };
     out4[0] = out4[1] = out4[2] = out4[3] = 0;
     *n_probes = 0;
     if (cands.size() < 2) return KSCHED_OK;
@@ -379,7 +411,8 @@ int kh_consolidate(const Problem* P, int* out4, int* options, int options_cap, i
     Cmd last;
     while (mn <= mx) {
       int mid = (mn + mx) / 2;
-      Cmd c = compute(mid + 1);
+      Cmd c = compute_consolidation(P, cands, mid + 1);
+      ++sims;
       if (*n_probes < probes_cap) { probes[*n_probes] = mid + 1; probe_actions[*n_probes] = c.action; }
       ++*n_probes;
       if (c.action == 1 || c.action == 2) { last = c; last_count = mid + 1; mn = mid + 1; }

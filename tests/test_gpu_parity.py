@@ -67,6 +67,27 @@ def test_multi_node_consolidation_matches_oracle(pkg, oracle):
     assert got == want
 
 
+@pytest.mark.parametrize("width", [1, 3, 7])
+def test_sharded_consolidation_search_matches_oracle(pkg, oracle, width):
+    """Probes evaluated `width` at a time (what `width` ranks would do) give the oracle's sequential command."""
+    problem = pkg.Problem.synth(5, 400, 1000, 43, 40)
+    want = oracle.consolidate(problem)
+    mnc = pkg.MultiNodeConsolidation(problem)
+    assert mnc.candidates() == 40
+    seen = []
+
+    def probe_many(counts):
+        seen.append(list(counts))
+        return {c: mnc.probe(c) for c in counts}
+
+    action, count, options, rounds, path = pkg.speculative_binary_search(mnc.candidates(), probe_many, width)
+    assert (action, count, options) == (want["action"], want["nodes_removed"], want["options"])
+    assert path == want["probes"]
+    assert rounds <= len(want["probes"])
+    single = mnc.first_n_node_consolidation_option_sharded()
+    assert (single["action"], single["nodes_removed"], single["options"]) == (want["action"], want["nodes_removed"], want["options"])
+
+
 def test_feasibility_matrix_matches_fresh_node_options(pkg, oracle):
     """K1: F[p, v, :] must equal the option set of a fresh node of template v that holds only pod p
     (Node.Add on a new node, node.go:62-107) — checked for every (pod, provisioner) pair against the oracle."""
