@@ -46,6 +46,7 @@ namespace {
 constexpr int kMaxCG = 8;        // topology groups that may constrain one pod class
 constexpr int kMaxTouched = 8;   // requirement keys one Add may touch (pod keys + topology keys)
 constexpr int kPackThreads = 512;
+constexpr int kFreshMemoSlots = 8192;  // PackState::fd_*
 constexpr uint64_t kNoBest = ~0ull;
 
 // ------------------------------------------------------------------------------------------------
@@ -470,6 +471,18 @@ struct PackState {
   uint64_t* fc_meta;
   long long* fc_q;                   // [n_classes*V][8] requests (daemon overhead + pod)
   uint32_t* fc_qp;
+  // fresh-node outcome memo for topology-constrained classes: a hash table keyed by (class, template, the new node's
+  // requirement masks) -- the option set of NewNode+Add is a function of exactly those (node.go:62-107) when the
+  // provisioner has no limits. Direct mapped, full tag compare, so a collision only costs a recomputation.
+  int fd_cap;                        // power of two
+  uint8_t* fd_state;                 // 0 empty, 1 options cached, 2 cached: no surviving type
+  uint32_t* fd_fc;                   // tag: class * V + template
+  uint64_t* fd_meta;                 // tag
+  uint64_t* fd_vals;                 // tag [fd_cap][16]
+  uint32_t* fd_opts;                 // [fd_cap][W32]
+  long long* fd_bound;               // [fd_cap][4]
+  long long* fd_bound2;
+  uint8_t* fd_dom;
   int count_visited;                 // keep the exact nodes_visited statistic (costs a pass over all in-flight nodes per pod)
   int alloc_in_smem;
   // topology counters
@@ -506,6 +519,15 @@ struct PodTopo {  // per (pod step, constraining group): node-independent part o
   uint64_t options[kMaxCG];    // affinity / anti-affinity: admissible domains (mask keys)
   uint8_t bootstrap[kMaxCG];   // affinity: no domain has a matching pod and the pod selects itself
   uint64_t pod_allowed[kMaxCG]; // pod's own admissible domains for the key
+  // the group's own fields, copied once per step so that the per-node checks read shared memory only
+  uint8_t gkey[kMaxCG], gtype[kMaxCG];
+  int32_t gskew[kMaxCG], host_row[kMaxCG], min_slot[kMaxCG];
+  uint64_t registered[kMaxCG];
+  // spread over a mask key: the registered domains within max-skew, in (count, domain id) order. The domain the
+  // reference picks for a node is the first entry the node's requirement admits (topologygroup.go:157-183).
+  uint8_t n_sorted[kMaxCG];
+  uint8_t sorted[kMaxCG][64];
+  uint64_t ok_mask[kMaxCG];    // the same domains as a set
   int overflow;
 };
 
@@ -533,30 +555,20 @@ __device__ __forceinline__ bool req_equal(const Req& a, const Req& b) {
 
 // TopologyGroup.Get for a mask-key group (topologygroup.go:88-243). node_dom = the node's requirement for the
 // key after the pod's own requirements were merged (topology.go:156-159). Returns false when Len()==0.
-__device__ bool topo_domains_mask(const DevCatalog& c, const PackState& s, const PodTopo& pt, int j, const Req& node_dom, uint64_t* out) {
-  const ksched_topo_group& g = s.groups[pt.group[j]];
-  const int gi = pt.group[j];
-  const int k = g.key;
+__device__ __noinline__ bool topo_domains_mask(const DevCatalog& c, const PackState& s, const PodTopo& pt, int j, const Req& node_dom, uint64_t* out) {
+  const int k = pt.gkey[j];
   KeyMeta km = key_meta(c, k);
-  const uint64_t registered = s.grp_registered[gi];
+  const uint64_t registered = pt.registered[j];
   const uint64_t node_allowed = node_dom.present ? ksched::req_allowed(node_dom, c.keys[k].dict_mask, km) : c.keys[k].dict_mask;
-  if (g.type == 0) {  // nextDomainTopologySpread
-    const bool self = pt.flags[j] & KSCHED_TOPO_SELECTS;
-    const int32_t mn = pt.min_count[j];
-    int best = -1;
-    int32_t best_count = INT32_MAX;
-    uint64_t m = registered & node_allowed;
-    while (m) {  // ascending domain id = ascending string order (canonical rule R3)
-      int d = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      int64_t cnt = (int64_t)s.grp_cnt[(size_t)gi * 64 + d] + (self ? 1 : 0);
-      if (cnt - (int64_t)mn <= (int64_t)g.max_skew && cnt < best_count) { best = d; best_count = (int32_t)cnt; }
+  if (pt.gtype[j] == 0) {  // nextDomainTopologySpread: min (count, domain id) among the admissible domains of the node
+    const int ns = pt.n_sorted[j];
+    for (int i = 0; i < ns; ++i) {
+      const int d = pt.sorted[j][i];
+      if ((node_allowed >> d) & 1) { *out = 1ull << d; return true; }
     }
-    if (best < 0) return false;
-    *out = 1ull << best;
-    return true;
+    return false;
   }
-  if (g.type == 1) {  // nextDomainAffinity
+  if (pt.gtype[j] == 1) {  // nextDomainAffinity
     uint64_t opts = pt.options[j];
     if (pt.bootstrap[j]) {
       uint64_t inter = registered & pt.pod_allowed[j] & node_allowed;  // podDomains.Intersection(nodeDomains).Has
@@ -575,19 +587,17 @@ __device__ bool topo_domains_mask(const DevCatalog& c, const PackState& s, const
 }
 
 // hostname-key groups: the node's hostname domain is its slot.
-__device__ bool topo_hostname_ok(const PackState& s, const PodTopo& pt, int j, int slot, bool pod_allows_slot) {
-  const int gi = pt.group[j];
-  const ksched_topo_group& g = s.groups[gi];
-  const int row = s.grp_host_row[gi];
+__device__ __noinline__ bool topo_hostname_ok(const PackState& s, const PodTopo& pt, int j, int slot, bool pod_allows_slot) {
   const int stride = s.n_existing + s.max_new;
-  const int32_t cnt = s.grp_host[(size_t)row * stride + slot];
+  const int32_t cnt = s.grp_host[(size_t)pt.host_row[j] * stride + slot];
   // a group created by a later Topology.Update only knows hostnames registered after that, plus those it counted pods on
-  if (slot < s.grp_min_slot[gi] && !(slot < s.n_existing && cnt > 0)) return false;
-  if (g.type == 0) {  // spread, min is 0 for hostname (topologygroup.go:186-188); candidate = the node's own hostname
+  if (slot < pt.min_slot[j] && !(slot < s.n_existing && cnt > 0)) return false;
+  const int type = pt.gtype[j];
+  if (type == 0) {  // spread, min is 0 for hostname (topologygroup.go:186-188); candidate = the node's own hostname
     int64_t c2 = (int64_t)cnt + ((pt.flags[j] & KSCHED_TOPO_SELECTS) ? 1 : 0);
-    return c2 <= (int64_t)g.max_skew;
+    return c2 <= (int64_t)pt.gskew[j];
   }
-  if (g.type == 1) {  // affinity
+  if (type == 1) {  // affinity
     if (cnt > 0 && pod_allows_slot) return true;
     if (pt.bootstrap[j]) return pod_allows_slot;  // first loop picks the node's own (registered) hostname
     return false;
@@ -605,7 +615,7 @@ __device__ __forceinline__ bool hostname_allows(const PackState& s, const ksched
 
 // Requirement phase of Node.Add / ExistingNode.Add: Compatible(pod) + merge, topology tighten + Compatible + merge.
 // vals/meta/stride/idx describe the node's requirement set. Returns false on reject.
-__device__ bool requirements_phase(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const PodTopo& pt,
+__device__ __noinline__ bool requirements_phase(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const PodTopo& pt,
                                    const uint64_t* vals, uint64_t meta, int stride, int idx, int slot, bool is_existing, Touched& t) {
   t.n = 0;
   if (!hostname_allows(s, row, slot, is_existing)) return false;
@@ -626,13 +636,11 @@ __device__ bool requirements_phase(const DevCatalog& c, const PackState& s, cons
     ++t.n;
   }
   for (int j = 0; j < pt.n; ++j) {
-    if (!(pt.flags[j] & KSCHED_TOPO_CONSTRAINS)) continue;
-    const ksched_topo_group& g = s.groups[pt.group[j]];
-    if (g.key == KSCHED_KEY_HOSTNAME) {
+    if (pt.gkey[j] == KSCHED_KEY_HOSTNAME) {
       if (!topo_hostname_ok(s, pt, j, slot, hostname_allows(s, row, slot, is_existing))) return false;
       continue;
     }
-    const int k = g.key;
+    const int k = pt.gkey[j];
     int ti = -1;
     for (int i = 0; i < t.n; ++i) if (t.key[i] == k) ti = i;
     if (ti < 0) {
@@ -674,11 +682,12 @@ struct TypeCtx {
   uint32_t zmask, cmask;
   uint32_t itype_req;
 };
-__device__ void build_type_ctx(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const Touched& t, const long long* q,
+__device__ __noinline__ void build_type_ctx(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const Touched& t, const long long* q,
                                uint32_t q_present, const uint64_t* vals, uint64_t meta, int stride, int idx, bool fresh,
-                               const int64_t* alloc_sorted, TypeCtx& x) {
+                               const int64_t* alloc_sorted, TypeCtx& x, bool with_ranks = true) {
   x.res_mask = q_present;
-  for (int r = 0; r < c.n_res; ++r) x.rank[r] = ((q_present >> r) & 1) ? fit_rank(alloc_sorted, c.n_types, r, q[r]) : 0;
+  if (with_ranks)
+    for (int r = 0; r < c.n_res; ++r) x.rank[r] = ((q_present >> r) & 1) ? fit_rank(alloc_sorted, c.n_types, r, q[r]) : 0;
   x.nkeys = 0;
   x.offer_needed = fresh;
   auto add_key = [&](int k, const Req& f) {
@@ -723,84 +732,165 @@ __device__ void build_type_ctx(const DevCatalog& c, const PackState& s, const ks
   }
   x.itype_req = row.itype_req;
 }
-__device__ __forceinline__ uint32_t type_word(const DevCatalog& c, const PackState& s, const TypeCtx& x, uint32_t base, int w) {
-  uint32_t sw = base;
+// resource part (Fits) and requirement part (keys / offerings / instance-type requirement) of the per-word filter
+__device__ __forceinline__ uint32_t type_word_res(const DevCatalog& c, const TypeCtx& x, uint32_t sw, int w) {
   uint32_t rm = x.res_mask;
   while (sw && rm) {
     int r = __ffs(rm) - 1;
     rm &= rm - 1;
     sw &= c.fitset[((size_t)r * (c.n_types + 1) + x.rank[r]) * c.W32 + w];
   }
+  return sw;
+}
+__device__ __forceinline__ uint32_t type_word_keys(const DevCatalog& c, const PackState& s, const TypeCtx& x, uint32_t sw, int w) {
   for (int i = 0; i < x.nkeys && sw; ++i) sw &= key_typeset_word(c, x.key[i], x.allowed[i], x.neg[i], w);
   if (sw && x.offer_needed) sw &= offer_word(c, x.zmask, x.cmask, x.offer_unconstrained, w);
   if (sw && x.itype_req != KSCHED_NONE) sw &= s.itype_sets[(size_t)x.itype_req * c.W32 + w];
   return sw;
 }
+__device__ __forceinline__ uint32_t type_word(const DevCatalog& c, const PackState& s, const TypeCtx& x, uint32_t base, int w) {
+  return type_word_keys(c, s, x, type_word_res(c, x, base, w), w);
+}
 
-// Node-independent part of the pod's topology constraints for this step.
-__device__ void build_pod_topo(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt) {
-  pt.n = 0;
-  pt.overflow = 0;
-  for (uint32_t e = row.topo_begin; e < row.topo_end; ++e) {
-    const ksched_class_topo ct = s.class_topo[e];
-    if (!(ct.flags & KSCHED_TOPO_CONSTRAINS)) continue;
-    if (pt.n >= kMaxCG) { pt.overflow = 1; return; }
-    const int j = pt.n++;
-    const int gi = (int)ct.group;
-    const ksched_topo_group& g = s.groups[gi];
-    pt.group[j] = gi;
-    pt.flags[j] = ct.flags;
-    pt.min_count[j] = 0;
-    pt.options[j] = 0;
-    pt.bootstrap[j] = 0;
-    pt.pod_allowed[j] = 0;
-    if (g.key == KSCHED_KEY_HOSTNAME) {
-      if (g.type == 1) {
-        // options.Len()==0 <=> no admissible hostname has a matching pod (hostname requirements on the pod are
-        // restricted to a single existing slot, handled in topo_hostname_ok)
-        pt.bootstrap[j] = (s.grp_host_total[gi] == 0) && (ct.flags & KSCHED_TOPO_SELECTS);
-      }
-      continue;
+// Node-independent part of the pod's topology constraints for this step, one constraining (class, group) relation j.
+// Static half: what the relation and its group are (a function of the pod class only).
+__device__ __noinline__ void fill_pod_topo_static(const PackState& s, const ksched_class_topo ct, PodTopo& pt, int j) {
+  const int gi = (int)ct.group;
+  const ksched_topo_group& g = s.groups[gi];
+  pt.group[j] = gi;
+  pt.flags[j] = ct.flags;
+  pt.gkey[j] = g.key;
+  pt.gtype[j] = g.type;
+  pt.gskew[j] = g.max_skew;
+  pt.host_row[j] = s.grp_host_row[gi];
+}
+// Dynamic half: everything derived from the group's counters, re-read every step.
+__device__ __noinline__ void fill_pod_topo_dynamic(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt, int j) {
+  const int gi = pt.group[j];
+  const uint32_t flags = pt.flags[j];
+  const int gkey = pt.gkey[j], gtype = pt.gtype[j], gskew = pt.gskew[j];
+  pt.min_count[j] = 0;
+  pt.options[j] = 0;
+  pt.bootstrap[j] = 0;
+  pt.pod_allowed[j] = 0;
+  pt.min_slot[j] = s.grp_min_slot[gi];
+  pt.registered[j] = 0;
+  pt.n_sorted[j] = 0;
+  pt.ok_mask[j] = 0;
+  if (gkey == KSCHED_KEY_HOSTNAME) {
+    if (gtype == 1) {
+      // options.Len()==0 <=> no admissible hostname has a matching pod (hostname requirements on the pod are
+      // restricted to a single existing slot, handled in topo_hostname_ok)
+      pt.bootstrap[j] = (s.grp_host_total[gi] == 0) && (flags & KSCHED_TOPO_SELECTS);
     }
-    const int k = g.key;
-    KeyMeta km = key_meta(c, k);
-    Req pd = pod_req(row, k);
-    const uint64_t pod_allowed = pd.present ? ksched::req_allowed(pd, c.keys[k].dict_mask, km) : c.keys[k].dict_mask;
-    pt.pod_allowed[j] = pod_allowed;
-    const uint64_t registered = s.grp_registered[gi];
-    uint64_t m = registered & pod_allowed;
-    if (g.type == 0) {
-      int32_t mn = INT32_MAX;
-      while (m) {
-        int d = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        int32_t cnt = s.grp_cnt[(size_t)gi * 64 + d];
-        mn = cnt < mn ? cnt : mn;
-      }
-      pt.min_count[j] = mn;
-    } else if (g.type == 1) {
-      uint64_t opts = 0;
-      while (m) {
-        int d = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        if (s.grp_cnt[(size_t)gi * 64 + d] > 0) opts |= 1ull << d;
-      }
-      pt.options[j] = opts;
-      pt.bootstrap[j] = (opts == 0) && (ct.flags & KSCHED_TOPO_SELECTS);
-    } else {
-      uint64_t opts = 0;
-      while (m) {
-        int d = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        if (s.grp_cnt[(size_t)gi * 64 + d] == 0) opts |= 1ull << d;
-      }
-      pt.options[j] = opts;
+    return;
+  }
+  const int k = gkey;
+  KeyMeta km = key_meta(c, k);
+  Req pd = pod_req(row, k);
+  const uint64_t pod_allowed = pd.present ? ksched::req_allowed(pd, c.keys[k].dict_mask, km) : c.keys[k].dict_mask;
+  pt.pod_allowed[j] = pod_allowed;
+  const uint64_t registered = s.grp_registered[gi];
+  pt.registered[j] = registered;
+  uint64_t m = registered & pod_allowed;
+  if (gtype == 0) {
+    int32_t mn = INT32_MAX;
+    while (m) {
+      int d = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      int32_t cnt = s.grp_cnt[(size_t)gi * 64 + d];
+      mn = cnt < mn ? cnt : mn;
     }
+    pt.min_count[j] = mn;
+    // registered domains within the skew bound, insertion-sorted by (count, id); ids arrive in ascending order
+    const int self = (flags & KSCHED_TOPO_SELECTS) ? 1 : 0;
+    int ns = 0;
+    int32_t cnts[64];
+    uint64_t all = registered, okm = 0;
+    while (all) {
+      int d = __ffsll((long long)all) - 1;
+      all &= all - 1;
+      const int64_t cnt = (int64_t)s.grp_cnt[(size_t)gi * 64 + d] + self;
+      if (cnt - (int64_t)mn > (int64_t)gskew) continue;
+      okm |= 1ull << d;
+      int i = ns++;
+      while (i > 0 && cnts[i - 1] > (int32_t)cnt) { cnts[i] = cnts[i - 1]; pt.sorted[j][i] = pt.sorted[j][i - 1]; --i; }
+      cnts[i] = (int32_t)cnt;
+      pt.sorted[j][i] = (uint8_t)d;
+    }
+    pt.n_sorted[j] = (uint8_t)ns;
+    pt.ok_mask[j] = okm;
+  } else if (gtype == 1) {
+    uint64_t opts = 0;
+    while (m) {
+      int d = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      if (s.grp_cnt[(size_t)gi * 64 + d] > 0) opts |= 1ull << d;
+    }
+    pt.options[j] = opts;
+    pt.bootstrap[j] = (opts == 0) && (flags & KSCHED_TOPO_SELECTS);
+  } else {
+    uint64_t opts = 0;
+    while (m) {
+      int d = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      if (s.grp_cnt[(size_t)gi * 64 + d] == 0) opts |= 1ull << d;
+    }
+    pt.options[j] = opts;
   }
 }
 
+// Called by the 32 lanes of warp 0: one (class, group) relation per lane, constraining ones compacted in order.
+__device__ void build_pod_topo(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t begin = row.topo_begin, end = row.topo_end;
+  int n = 0, overflow = 0;
+  for (uint32_t base = begin; base < end; base += 32) {  // uniform trip count
+    const uint32_t e = base + lane;
+    ksched_class_topo ct{0, 0};
+    if (e < end) ct = s.class_topo[e];
+    const bool cons = e < end && (ct.flags & KSCHED_TOPO_CONSTRAINS);
+    const unsigned bal = __ballot_sync(0xffffffffu, cons);
+    const int j = n + __popc(bal & ((1u << lane) - 1));
+    if (cons && j < kMaxCG) {
+      fill_pod_topo_static(s, ct, pt, j);
+      fill_pod_topo_dynamic(c, s, row, pt, j);
+    }
+    n += __popc(bal);
+    if (n > kMaxCG) { overflow = 1; n = kMaxCG; }
+  }
+  if (lane == 0) { pt.n = n; pt.overflow = overflow; }
+}
+// The previous step's pod had the same class: the relations are the same, only the counters moved.
+__device__ void refresh_pod_topo(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt) {
+  const int lane = threadIdx.x & 31;
+  if (lane < pt.n) fill_pod_topo_dynamic(c, s, row, pt, lane);
+}
+
+// A NECESSARY condition of requirements_phase for an in-flight node, cheap enough to run on every candidate: the
+// hostname groups exactly, spread groups over mask keys through the set of admissible domains. The node that wins the
+// argmin is then checked in full (and excluded if it fails).
+__device__ __forceinline__ bool topo_prefilter(const DevCatalog& c, const PackState& s, const PodTopo& pt, const uint64_t* vals, uint64_t meta,
+                                               int stride, int idx, int slot) {
+  for (int j = 0; j < pt.n; ++j) {
+    const int k = pt.gkey[j];
+    if (k == KSCHED_KEY_HOSTNAME) {
+      if (!topo_hostname_ok(s, pt, j, slot, true)) return false;
+      continue;
+    }
+    if (pt.gtype[j] != 0) {
+      if (!pt.options[j] && !pt.bootstrap[j]) return false;
+      continue;
+    }
+    const Req node = load_soa(vals, meta, stride, idx, k);
+    const uint64_t node_allowed = node.present ? ksched::req_allowed(node, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask;
+    if (!(node_allowed & pt.ok_mask[j])) return false;
+  }
+  return true;
+}
+
 // TopologyNodeFilter.MatchesRequirements (topologynodefilter.go:57-70): any term Compatible with the node requirements
-__device__ bool filter_matches(const DevCatalog& c, const PackState& s, const ksched_topo_group& g, const uint64_t* vals, uint64_t meta,
+__device__ __noinline__ bool filter_matches(const DevCatalog& c, const PackState& s, const ksched_topo_group& g, const uint64_t* vals, uint64_t meta,
                                int stride, int idx) {
   if (g.filter_begin == g.filter_end) return true;
   for (uint32_t f = g.filter_begin; f < g.filter_end; ++f) {
@@ -819,42 +909,45 @@ __device__ bool filter_matches(const DevCatalog& c, const PackState& s, const ks
   return false;
 }
 
-// Topology.Record (topology.go:120-143) after the node's requirements were committed. Single thread.
-__device__ void topo_record(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const uint64_t* vals, uint64_t meta, int stride,
-                            int idx, int slot) {
+// Topology.Record (topology.go:120-143) for ONE (class, group) relation, after the node's requirements were committed.
+// Relations of one class name distinct groups, so different threads may record different relations concurrently.
+__device__ __noinline__ void topo_record_entry(const DevCatalog& c, const PackState& s, uint32_t e, const uint64_t* vals, uint64_t meta, int stride, int idx, int slot) {
   const int hstride = s.n_existing + s.max_new;
-  for (uint32_t e = row.topo_begin; e < row.topo_end; ++e) {
-    const ksched_class_topo ct = s.class_topo[e];
-    const int gi = (int)ct.group;
-    const ksched_topo_group& g = s.groups[gi];
-    if (!s.grp_active[gi]) continue;  // the group does not exist yet
-    bool rec = false, all_values = false;
-    if (ct.flags & KSCHED_TOPO_RECORDS) {
-      if (filter_matches(c, s, g, vals, meta, stride, idx)) { rec = true; all_values = (g.type == 2); }
-    }
-    bool rec_inv = (ct.flags & KSCHED_TOPO_RECORDS_INVERSE) != 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      const bool doit = pass == 0 ? rec : rec_inv;
-      const bool allv = pass == 0 ? all_values : true;
-      if (!doit) continue;
-      if (g.key == KSCHED_KEY_HOSTNAME) {  // the node's hostname requirement is always In [its own hostname]
-        uint16_t* cell = &s.grp_host[(size_t)s.grp_host_row[gi] * hstride + slot];
-        if (*cell == 0) s.grp_host_total[gi]++;
-        if (*cell < 0xFFFF) (*cell)++;
-      } else {
-        Req r = load_soa(vals, meta, stride, idx, g.key);
-        uint64_t v = 0;
-        if (allv) v = r.present ? r.values : 0;  // domains.Values(): members, or the excluded set of a complement
-        else if (r.present && ksched::req_len_one(r)) v = r.values;
-        while (v) {
-          int d = __ffsll((long long)v) - 1;
-          v &= v - 1;
-          s.grp_cnt[(size_t)gi * 64 + d]++;
-          s.grp_registered[gi] |= 1ull << d;
-        }
+  const ksched_class_topo ct = s.class_topo[e];
+  const int gi = (int)ct.group;
+  const ksched_topo_group& g = s.groups[gi];
+  if (!s.grp_active[gi]) return;  // the group does not exist yet
+  bool rec = false, all_values = false;
+  if (ct.flags & KSCHED_TOPO_RECORDS) {
+    if (filter_matches(c, s, g, vals, meta, stride, idx)) { rec = true; all_values = (g.type == 2); }
+  }
+  bool rec_inv = (ct.flags & KSCHED_TOPO_RECORDS_INVERSE) != 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool doit = pass == 0 ? rec : rec_inv;
+    const bool allv = pass == 0 ? all_values : true;
+    if (!doit) continue;
+    if (g.key == KSCHED_KEY_HOSTNAME) {  // the node's hostname requirement is always In [its own hostname]
+      uint16_t* cell = &s.grp_host[(size_t)s.grp_host_row[gi] * hstride + slot];
+      if (*cell == 0) s.grp_host_total[gi]++;
+      if (*cell < 0xFFFF) (*cell)++;
+    } else {
+      Req r = load_soa(vals, meta, stride, idx, g.key);
+      uint64_t v = 0;
+      if (allv) v = r.present ? r.values : 0;  // domains.Values(): members, or the excluded set of a complement
+      else if (r.present && ksched::req_len_one(r)) v = r.values;
+      while (v) {
+        int d = __ffsll((long long)v) - 1;
+        v &= v - 1;
+        s.grp_cnt[(size_t)gi * 64 + d]++;
+        s.grp_registered[gi] |= 1ull << d;
       }
     }
   }
+}
+// every thread of the CTA: relation tid, tid + blockDim, ... (the commit this records must be visible: call after a barrier)
+__device__ __forceinline__ void topo_record_block(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const uint64_t* vals, uint64_t meta,
+                                                  int stride, int idx, int slot) {
+  for (uint32_t e = row.topo_begin + threadIdx.x; e < row.topo_end; e += blockDim.x) topo_record_entry(c, s, e, vals, meta, stride, idx, slot);
 }
 
 }  // namespace
@@ -885,6 +978,10 @@ struct DevBuf {
     return e;
   }
   void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
 };
 
 }  // namespace
@@ -931,6 +1028,10 @@ struct ksched_handle {
   DevBuf<uint32_t> d_fc_opts, d_fc_qp, d_ov_absorbed, d_ov_rejected;
   DevBuf<uint64_t> d_fc_vals, d_fc_meta;
   DevBuf<long long> d_fc_q;
+  DevBuf<uint8_t> d_fd_state, d_fd_dom;
+  DevBuf<uint32_t> d_fd_fc, d_fd_opts;
+  DevBuf<uint64_t> d_fd_meta, d_fd_vals;
+  DevBuf<long long> d_fd_bound, d_fd_bound2;
   int count_visited = 1;
   DevBuf<uint32_t> d_ex_req_present, d_ex_req_present0, d_ex_avail_present, d_ex_taintset, d_ex_itype, d_nn_req_present, d_nn_opts;
   DevBuf<uint64_t> d_ex_vals, d_ex_vals0, d_ex_meta, d_ex_meta0, d_ex_hp, d_ex_hp0, d_nn_vals, d_nn_meta, d_nn_hp, d_grp_registered,
@@ -994,10 +1095,7 @@ void ksched_destroy(ksched_handle* h) {
   if (h->comm) ncclCommDestroy(h->comm);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
-  // device buffers are released with the context at process exit; free the big ones eagerly
-  h->d_F.release(); h->d_rows.release(); h->d_grp_host.release(); h->d_grp_host0.release(); h->d_fitset.release(); h->d_flush.release();
-  h->d_nn_opts.release(); h->d_nn_vals.release(); h->d_nn_req.release(); h->d_fc_opts.release();
-  delete h;
+  delete h;  // every DevBuf frees its allocation
 }
 
 const char* ksched_last_error(const ksched_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -1008,6 +1106,14 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   if (cat->n_keys > KSCHED_MAX_KEYS || cat->n_res > KSCHED_MAX_RES || cat->n_templates > KSCHED_MAX_TEMPLATES || cat->n_templates < 1 ||
       cat->n_types < 0) { h->err = "catalog dimensions out of range"; return KSCHED_ERR_INVALID; }
   if (cat->type_bounds) { h->err = "instance types with Gt/Lt requirements are not supported"; return KSCHED_ERR_UNSUPPORTED; }
+  // device code carries no Gt/Lt bounds at all (reqmask.cuh compiles them out): refuse any requirement set that has one
+  for (int v = 0; v < cat->n_templates; ++v)
+    if (cat->template_bounds || (cat->templates[v].reqs.meta >> KSCHED_META_HASGT_SHIFT)) {
+      h->err = "provisioners with Gt/Lt requirements are not supported on the device path";
+      return KSCHED_ERR_UNSUPPORTED;
+    }
+  for (int t = 0; t < cat->n_types; ++t)
+    if (cat->types[t].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "instance types with Gt/Lt requirements are not supported"; return KSCHED_ERR_UNSUPPORTED; }
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int T = cat->n_types, NK = cat->n_keys, V = cat->n_templates, R = cat->n_res;
   const int W64 = type_words64(T), W32 = W64 * 2;
@@ -1175,6 +1281,12 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   if (!h || !pb) return KSCHED_ERR_INVALID;
   if (!h->have_catalog) { h->err = "ksched_load_catalog must be called first"; return KSCHED_ERR_INVALID; }
   if (pb->class_bounds || pb->existing_bounds) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+  for (int i = 0; i < pb->n_classes; ++i)
+    if (pb->classes[i].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+  for (int i = 0; i < pb->n_existing; ++i)
+    if (pb->existing[i].reqs.meta >> KSCHED_META_HASGT_SHIFT) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+  for (int i = 0; i < pb->n_filter_terms; ++i)
+    if (pb->filter_terms[i].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
   CUDA_TRY(h, cudaSetDevice(h->device));
   h->tm.h2d_bytes = 0;
   const DevCatalog& c = h->cat;
@@ -1307,6 +1419,10 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
     CUDA_TRY(h, h->d_fc_opts.ensure(nfc * W32));
     CUDA_TRY(h, h->d_fc_vals.ensure(nfc * KSCHED_MAX_KEYS)); CUDA_TRY(h, h->d_fc_meta.ensure(nfc)); CUDA_TRY(h, h->d_fc_q.ensure(nfc * KSCHED_MAX_RES));
     CUDA_TRY(h, h->d_fc_qp.ensure(nfc));
+    const size_t nfd = kFreshMemoSlots;
+    CUDA_TRY(h, h->d_fd_state.ensure(nfd)); CUDA_TRY(h, h->d_fd_dom.ensure(nfd)); CUDA_TRY(h, h->d_fd_fc.ensure(nfd)); CUDA_TRY(h, h->d_fd_meta.ensure(nfd));
+    CUDA_TRY(h, h->d_fd_vals.ensure(nfd * KSCHED_MAX_KEYS)); CUDA_TRY(h, h->d_fd_opts.ensure(nfd * W32));
+    CUDA_TRY(h, h->d_fd_bound.ensure(nfd * 4)); CUDA_TRY(h, h->d_fd_bound2.ensure(nfd * 4));
   }
   CUDA_TRY(h, h->d_remaining.ensure((size_t)V * KSCHED_MAX_RES));
   CUDA_TRY(h, h->d_counters.ensure(32));
@@ -1429,6 +1545,7 @@ static int reset_state(ksched_handle* h) {
   CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 32 * sizeof(long long), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fc_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fc_front_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_fd_state.ptr, 0, (size_t)kFreshMemoSlots, h->stream));
   return KSCHED_OK;
 }
 
@@ -1454,13 +1571,17 @@ static int run_pack(ksched_handle* h) {
   s.fc_state = h->d_fc_state.ptr; s.fc_opts = h->d_fc_opts.ptr; s.fc_bound = h->d_fc_bound.ptr; s.fc_bound2 = h->d_fc_bound2.ptr; s.fc_dom = h->d_fc_dom.ptr; s.fc_front_state = h->d_fc_front_state.ptr;
   s.fc_vals = h->d_fc_vals.ptr; s.fc_meta = h->d_fc_meta.ptr; s.fc_q = h->d_fc_q.ptr; s.fc_qp = h->d_fc_qp.ptr;
   s.ov_absorbed = h->d_ov_absorbed.ptr; s.ov_rejected = h->d_ov_rejected.ptr;
+  s.fd_cap = kFreshMemoSlots; s.fd_state = h->d_fd_state.ptr; s.fd_fc = h->d_fd_fc.ptr; s.fd_meta = h->d_fd_meta.ptr; s.fd_vals = h->d_fd_vals.ptr;
+  s.fd_opts = h->d_fd_opts.ptr; s.fd_bound = h->d_fd_bound.ptr; s.fd_bound2 = h->d_fd_bound2.ptr; s.fd_dom = h->d_fd_dom.ptr;
   s.count_visited = h->count_visited;
   s.grp_cnt = h->d_grp_cnt.ptr; s.grp_registered = h->d_grp_registered.ptr; s.grp_host = h->d_grp_host.ptr;
   s.grp_host_row = h->d_grp_host_row.ptr; s.grp_host_total = h->d_grp_host_total.ptr; s.remaining = h->d_remaining.ptr;
   s.grp_active = h->d_grp_active.ptr; s.grp_min_slot = h->d_grp_min_slot.ptr;
   s.counters = h->d_counters.ptr;
   const size_t alloc_bytes = (size_t)h->cat.n_res * h->cat.n_types * sizeof(int64_t);
-  s.alloc_in_smem = alloc_bytes <= (size_t)(64 << 10) ? 1 : 0;
+  // 227 KB per CTA on sm_100a: the hot node window + ~4 KB of static shared memory come first
+  const size_t smem_left = (size_t)(227 << 10) - sizeof(HotSmem) - (size_t)(6 << 10);
+  s.alloc_in_smem = alloc_bytes <= smem_left ? 1 : 0;
   const size_t smem = sizeof(HotSmem) + (s.alloc_in_smem ? alloc_bytes : 0);
   CUDA_TRY(h, cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // block size: the chain is latency-bound on ONE thread's commit; more warps only help when there are many candidate
@@ -1546,6 +1667,8 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
                   "n_generic=%lld inflight_placed=%lld fresh_steps=%lld failures=%lld paths[rej,cached,row,dyn,cachedempty]=%lld,%lld,%lld,%lld,%lld steps=%lld\n",
           counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[14], counters[15], counters[17], counters[18],
           counters[19], counters[20], counters[21], counters[22], counters[23], counters[24], counters[25], counters[5]);
+  fprintf(stderr, "[pack profile] fresh: decide=%lld words=%lld commit=%lld rest=%lld | in-flight verify=%lld\n", counters[26], counters[27], counters[28],
+          counters[12], counters[29]);
 #endif
   if (counters[4] != 0) {
     h->err = counters[4] == KSCHED_ERR_OVERFLOW ? "new-node capacity exceeded" : "a pod is constrained by more topology groups than the kernel supports";

@@ -76,7 +76,7 @@ constexpr unsigned short kFlExact = 1, kFlTwo = 0x20;
 // Pareto front (size <= 2) of the allocatable vectors of a node's stored options, or per-resource maxima when the front
 // is larger. Candidates are the per-resource arg-max types (found by probing each resource's descending order); a
 // candidate pair is a front iff every stored option is dominated by one of the two.
-__device__ void compute_front(const DevCatalog& c, const uint32_t* opts, int stride, int n, long long* b1, long long* b2, unsigned short* bits) {
+__device__ __noinline__ void compute_front(const DevCatalog& c, const uint32_t* opts, int stride, int n, long long* b1, long long* b2, unsigned short* bits) {
   const int R = c.n_res < kHotRes ? c.n_res : kHotRes;
   const int T = c.n_types;
   int arg[kHotRes];
@@ -167,9 +167,16 @@ struct StepShared {
   long long bound[kHotRes], bound2[kHotRes];
   unsigned short front_bits;
   long long visited;
+  // in-flight winner posted for the cooperative instance-type check / commit
+  int win_a, win_n, win_need, win_commit, win_fail;
+  int excl[16];        // nodes that won the argmin of this step but failed the instance-type check
+  // fresh node of a topology-constrained class: slot of the outcome memo (PackState::fd_*), new node's requirement meta
+  int fd_slot;
+  uint64_t meta;
 };
+constexpr int kMaxExcl = 16;
 
-enum { kPathReject = 0, kPathCached = 1, kPathRow = 2, kPathDynamic = 3, kPathCachedEmpty = 4 };
+enum { kPathReject = 0, kPathCached = 1, kPathRow = 2, kPathDynamic = 3, kPathCachedEmpty = 4, kPathDynCached = 5, kPathDynEmpty = 6 };
 
 // The words of a pod row every candidate check needs. Loaded RAW one iteration ahead for first-pass pods (anything
 // derived from them is computed by the consuming iteration, so the prefetch never waits on its own loads).
@@ -207,9 +214,10 @@ struct SlowEval {
   long long q[KSCHED_MAX_RES];
   uint32_t qp;
   bool changed;
+  bool need_types;  // with_types == false: the instance-type options still have to be checked (by the whole CTA, for the winner only)
 };
 __device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const PodTopo& pt, bool plain,
-                                           int n, unsigned short fl, const long long* q_hot, const int64_t* alloc_sorted, SlowEval& e) {
+                                           int n, unsigned short fl, const long long* q_hot, const int64_t* alloc_sorted, bool with_types, SlowEval& e) {
   const int MAXN = s.max_new, NE = s.n_existing, R = c.n_res, W32 = c.W32;
   const uint32_t p_res = row.res_present;
   e.t.n = 0;
@@ -223,7 +231,8 @@ __device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState&
   for (int r = 0; r < kHotRes; ++r) e.q[r] = q_hot[r];
   for (int r = kHotRes; r < R; ++r) e.q[r] = s.nn_req[(size_t)r * MAXN + n] + (((p_res >> r) & 1) ? row.requests[r] : 0);
   e.qp = s.nn_req_present[n] | p_res;
-  if (!need_types) return true;  // the dominant option fits and no requirement changed
+  e.need_types = need_types && !with_types;
+  if (!need_types || !with_types) return true;  // the dominant option fits and no requirement changed / checked later
   build_type_ctx(c, s, row, e.t, e.q, e.qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, alloc_sorted, e.x);
   for (int w = 0; w < W32; ++w) {
     const uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
@@ -231,14 +240,13 @@ __device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState&
   }
   return false;
 }
-// Requirement-changing part of a commit: new masks, requirement-driven narrowing of the stored options, new bounds.
-__device__ __noinline__ void commit_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, int n, SlowEval& e, long long* bound,
-                                         long long* bound2, unsigned short* front_bits, uint64_t* meta_out) {
-  const int MAXN = s.max_new, W32 = c.W32;
+// Requirement part of a commit: the node's new masks.
+__device__ __forceinline__ uint64_t commit_reqs(const PackState& s, int n, const Touched& t) {
+  const int MAXN = s.max_new;
   uint64_t meta = s.nn_meta[n];
-  for (int i = 0; i < e.t.n; ++i) {
-    const int k = e.t.key[i];
-    const Req& f = e.t.fin[i];
+  for (int i = 0; i < t.n; ++i) {
+    const int k = t.key[i];
+    const Req& f = t.fin[i];
     const uint64_t bit = 1ull << k;
     meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
     if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
@@ -246,7 +254,14 @@ __device__ __noinline__ void commit_slow(const DevCatalog& c, const PackState& s
     s.nn_vals[(size_t)k * MAXN + n] = f.values;
   }
   s.nn_meta[n] = meta;
-  *meta_out = meta;
+  return meta;
+}
+// Requirement-changing commit done by ONE thread (fallback mode): new masks, requirement-driven narrowing of the stored
+// options, new bounds.
+__device__ __noinline__ void commit_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, int n, SlowEval& e, long long* bound,
+                                         long long* bound2, unsigned short* front_bits, uint64_t* meta_out) {
+  const int MAXN = s.max_new, W32 = c.W32;
+  *meta_out = commit_reqs(s, n, e.t);
   e.x.res_mask = 0;  // resources stay lazy (finalize_options_kernel)
   for (int w = 0; w < W32; ++w) {
     const uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
@@ -270,6 +285,7 @@ struct LoopVars {
   uint32_t epoch;
   bool pt_nonempty;
   long long nodes_visited;
+  uint32_t pt_class;  // class the shared PodTopo was built for (KSCHED_NONE: none)
 };
 
 // One full Scheduler.add for one pod (existing nodes -> in-flight nodes -> new node -> relax/requeue). Every thread of
@@ -294,6 +310,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
   uint32_t& epoch = L.epoch;
   bool& pt_nonempty = L.pt_nonempty;
   long long& nodes_visited = L.nodes_visited;
+  uint32_t& pt_class = L.pt_class;
 #ifdef KSCHED_PROFILE_PACK
   long long gk_last = clock64();
 #define GK_T(i) { if (tid == 0) { long long _n = clock64(); s.counters[8 + (i)] += _n - gk_last; gk_last = _n; } }
@@ -313,7 +330,11 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
     const bool has_topo = cur.topo_begin != cur.topo_end;
     if (has_topo || pt_nonempty) {
       __syncthreads();  // previous step's readers of pt are done
-      if (tid == 0) build_pod_topo(c, s, row, pt);
+      if (tid < 32) {
+        if (pt_class == cls && !pt.overflow) refresh_pod_topo(c, s, row, pt);  // same relations as the previous step, new counters
+        else build_pod_topo(c, s, row, pt);
+      }
+      pt_class = cls;
       __syncthreads();
       pt_nonempty = pt.n != 0;
       if (pt.overflow) { fatal = KSCHED_ERR_UNSUPPORTED; return; }
@@ -377,55 +398,149 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           s.ex_req_present[e] |= p_res;
           if (p_hpe) s.ex_hp[e] |= p_hpe;
           s.ex_closed[e] = closed;
-          if (has_topo) topo_record(c, s, row, s.ex_vals, meta, NE, e, e);
           s.assign[pod] = e;
           s.place_seq[pod] = seq;
         }
         ++seq;
         placed = true;
         __syncthreads();  // the commit is read by every thread in the next step
+        if (has_topo) topo_record_block(c, s, row, s.ex_vals, s.ex_meta[e], NE, e, e);
       } else {
         nodes_visited += NE;
       }
     }
     GK_T(1)
     // ------------------------------------------------------------ 2) in-flight nodes, fewest pods first (scheduler.go:183-190)
+    // Every thread checks candidates for everything except the instance-type options (requirements, topology, the
+    // resource pre-test); the block argmin picks the first such node in the reference's order; the whole CTA then
+    // verifies the winner's instance-type options word-parallel and, if they survive, narrows them in place. A winner
+    // whose options do not survive is excluded and the argmin is repeated (after kMaxExcl such failures every candidate is
+    // checked in full by its own thread, which needs no verification).
     if (!placed && n_active > 0) {
-      unsigned long long mine = ~0ull;
-      int best_a = -1, last_slow = -1;
-      long long bq[kHotRes] = {0, 0, 0, 0};
-      SlowEval ev;
-      bool best_slow = false;
-      for (int a = tid; a < n_active; a += blockDim.x) {
-        const unsigned long long key = H.key(a);
-        if (key >= mine) continue;  // cannot beat this thread's current candidate
-        const unsigned short fl = H.flags(a);
-        if (!((p_tol >> tmpl_taintset[fl >> 8]) & 1)) continue;  // Taints.Tolerates
-        const uint32_t qp = ((fl >> 1) & 0xF) | p_res;
-        long long q[kHotRes], b1[kHotRes], b2[kHotRes];
+      int n_excl = 0;
+      bool full_eval = false;
+      const bool two_stage = pt_nonempty;  // topology-constrained pod
+      while (true) {
+        unsigned long long mine = ~0ull;
+        int best_a = -1, last_slow = -1;
+        long long bq[kHotRes] = {0, 0, 0, 0};
+        SlowEval ev;
+        bool best_slow = false;
+        for (int a = tid; a < n_active; a += blockDim.x) {
+          const unsigned long long key = H.key(a);
+          if (key >= mine) continue;  // cannot beat this thread's current candidate
+          if (n_excl) {
+            bool excluded = false;
+            for (int i = 0; i < n_excl && i < kMaxExcl; ++i) excluded = excluded || sh.excl[i] == a;
+            if (excluded) continue;
+          }
+          const unsigned short fl = H.flags(a);
+          if (!((p_tol >> tmpl_taintset[fl >> 8]) & 1)) continue;  // Taints.Tolerates
+          const uint32_t qp = ((fl >> 1) & 0xF) | p_res;
+          long long q[kHotRes], b1[kHotRes], b2[kHotRes];
 #pragma unroll
-        for (int r = 0; r < kHotRes; ++r) { q[r] = H.q(r, a) + preq[r]; b1[r] = H.bound(r, a); b2[r] = H.bound2(r, a); }
-        const int qf = quick_fit(q, qp, RH, b1, b2, fl);
-        if (qf == 0) continue;
-        if (p_hpc && (s.nn_hp[H.node(a)] & p_hpc)) continue;
-        if (simple && H.rejected(a) == cls) continue;  // memo: same class, node untouched since it was refused
-        const bool fast = (plain || (simple && H.absorbed(a) == cls)) && qf == 1;  // nothing can change and an option holds the requests
-        if (!fast) {
-          last_slow = a;
-          if (!evaluate_slow(c, s, row, pt, plain, H.node(a), fl, q, alloc_sorted, ev)) {
-            if (simple) H.rejected(a) = cls;
-            continue;
+          for (int r = 0; r < kHotRes; ++r) { q[r] = H.q(r, a) + preq[r]; b1[r] = H.bound(r, a); b2[r] = H.bound2(r, a); }
+          const int qf = quick_fit(q, qp, RH, b1, b2, fl);
+          if (qf == 0) continue;
+          if (p_hpc && (s.nn_hp[H.node(a)] & p_hpc)) continue;
+          if (simple && H.rejected(a) == cls) continue;  // memo: same class, node untouched since it was refused
+          const bool fast = (plain || (simple && H.absorbed(a) == cls)) && qf == 1;  // nothing can change and an option holds the requests
+          if (!fast) {
+            if (two_stage && !full_eval) {  // necessary condition only; the winner is checked in full
+              const int n = H.node(a);
+              if (!topo_prefilter(c, s, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n)) continue;
+            } else {
+              last_slow = a;
+              if (!evaluate_slow(c, s, row, pt, plain, H.node(a), fl, q, alloc_sorted, full_eval, ev)) {
+                if (simple) H.rejected(a) = cls;
+                continue;
+              }
+            }
+          }
+          mine = key;
+          best_a = a;
+          best_slow = !fast;
+#pragma unroll
+          for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
+        }
+        GK_T(2)
+        const unsigned long long wkey = block_min_u64_db(mine, red, parity);
+        if (wkey == ~0ull) {
+          nodes_visited += n_new;
+          break;
+        }
+        const bool winner = mine == wkey;
+        if (winner) {  // post the candidate for the cooperative instance-type check
+          const int a = best_a;
+          bool okw = true;
+          if (best_slow && last_slow != a) okw = evaluate_slow(c, s, row, pt, plain, H.node(a), H.flags(a), bq, alloc_sorted, full_eval, ev);
+          sh.win_a = a;
+          sh.win_n = H.node(a);
+          sh.win_fail = okw ? 0 : 1;
+          sh.win_need = (okw && best_slow && ev.need_types) ? 1 : 0;
+          sh.win_commit = (okw && best_slow && (ev.changed || p_itype != KSCHED_NONE)) ? 1 : 0;
+          if (sh.win_need) {
+            fresh_t = ev.t;
+            for (int r = 0; r < KSCHED_MAX_RES; ++r) sh.q[r] = r < R ? ev.q[r] : 0;
+            sh.qp = ev.qp;
           }
         }
-        mine = key;
-        best_a = a;
-        best_slow = !fast;
-#pragma unroll
-        for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
-      }
-      GK_T(2)
-      const unsigned long long wkey = block_min_u64_db(mine, red, parity);
-      if (wkey != ~0ull) {
+        __syncthreads();
+        const int wa = sh.win_a, wn = sh.win_n;
+        if (sh.win_fail) {  // the prefilter let through a node the full requirement check refuses
+          if (tid == 0) {
+            if (n_excl < kMaxExcl) sh.excl[n_excl] = wa;
+            if (simple) H.rejected(wa) = cls;
+          }
+          ++n_excl;
+          if (n_excl >= kMaxExcl) full_eval = true;
+          __syncthreads();
+          continue;
+        }
+        const bool coop = sh.win_need != 0;
+        bool opts_changed = false;
+        if (coop) {
+          // TypeCtx of the winner: requirement part by thread 0, one Fits rank per resource by the first lanes of warp 1
+          const int rbase = blockDim.x >= 64 ? 32 : 0;
+          if (tid == 0) build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, s.nn_vals, s.nn_meta[wn], MAXN, wn, false, alloc_sorted, fresh_x, rbase == 0);
+          if (rbase && tid >= rbase && tid < rbase + R) {
+            const int r = tid - rbase;
+            fresh_x.rank[r] = ((sh.qp >> r) & 1) ? fit_rank(alloc_sorted, c.n_types, r, sh.q[r]) : 0;
+          }
+          __syncthreads();
+          // one pass: requirement-narrowed word kept in a register, resource test on top of it
+          uint32_t keep_base = 0, keep = 0;
+          int local_any = 0;
+          for (int w = tid; w < W32; w += blockDim.x) {
+            const uint32_t base = s.nn_opts[(size_t)w * MAXN + wn];
+            if (!base) continue;
+            const uint32_t sw = type_word_keys(c, s, fresh_x, base, w);
+            if (w == tid) { keep_base = base; keep = sw; }
+            if (sw && type_word_res(c, fresh_x, sw, w)) local_any = 1;
+          }
+          if (!__syncthreads_or(local_any)) {  // no option survives: Node.Add fails on this node (node.go:92-95)
+            if (tid == 0) {
+              if (n_excl < kMaxExcl) sh.excl[n_excl] = wa;
+              if (simple) H.rejected(wa) = cls;
+            }
+            ++n_excl;
+            if (n_excl >= kMaxExcl) full_eval = true;
+            __syncthreads();
+            continue;
+          }
+          if (sh.win_commit) {  // requirement-driven narrowing of the stored options; resources stay lazy
+            int local_changed = 0;
+            if (tid < W32 && keep != keep_base) { s.nn_opts[(size_t)tid * MAXN + wn] = keep; local_changed = 1; }
+            for (int w = tid + blockDim.x; w < W32; w += blockDim.x) {
+              const uint32_t base = s.nn_opts[(size_t)w * MAXN + wn];
+              if (!base) continue;
+              const uint32_t sw = type_word_keys(c, s, fresh_x, base, w);
+              if (sw != base) { s.nn_opts[(size_t)w * MAXN + wn] = sw; local_changed = 1; }
+            }
+            opts_changed = __syncthreads_or(local_changed) != 0;
+          }
+        }
+        GK_T(21)
         GK_C(10)
         if (s.count_visited) {  // rank of the winner among ALL in-flight nodes (the reference also walks the full ones)
           int less = 0;
@@ -438,11 +553,10 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           __syncthreads();
           nodes_visited += sh.visited + 1;
         }
-        if (mine == wkey) {  // the winning thread commits its own candidate
+        if (winner) {  // the winning thread commits its own candidate
           const int a = best_a;
-          const int n = H.node(a);
+          const int n = wn;
           unsigned short fl = H.flags(a);
-          if (best_slow && last_slow != a) evaluate_slow(c, s, row, pt, plain, n, fl, bq, alloc_sorted, ev);
 #pragma unroll
           for (int r = 0; r < kHotRes; ++r) H.q(r, a) = bq[r];
           for (int r = kHotRes; r < R; ++r)
@@ -454,16 +568,23 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           s.nn_count[n] = count;
           s.nn_tb[n] = -(tick + 1);  // front of the next pod-count block under a stable sort
           H.key(a) = order_key(count, -(tick + 1));
-          uint64_t meta = 0;
           if (best_slow && (ev.changed || p_itype != KSCHED_NONE)) {
             long long nb1[kHotRes], nb2[kHotRes];
             unsigned short fb;
-            commit_slow(c, s, row, n, ev, nb1, nb2, &fb, &meta);
+            bool new_front = true;
+            if (coop) {
+              commit_reqs(s, n, ev.t);
+              if (opts_changed) compute_front(c, s.nn_opts, MAXN, n, nb1, nb2, &fb);
+              else new_front = false;  // same option set, same Pareto front
+            } else {
+              uint64_t meta;
+              commit_slow(c, s, row, n, ev, nb1, nb2, &fb, &meta);
+            }
+            if (new_front) {
 #pragma unroll
-            for (int r = 0; r < kHotRes; ++r) { H.bound(r, a) = nb1[r]; H.bound2(r, a) = nb2[r]; }
-            fl = (unsigned short)((fl & ~(kFlExact | kFlTwo)) | fb);
-          } else if (has_topo) {
-            meta = s.nn_meta[n];
+              for (int r = 0; r < kHotRes; ++r) { H.bound(r, a) = nb1[r]; H.bound2(r, a) = nb2[r]; }
+              fl = (unsigned short)((fl & ~(kFlExact | kFlTwo)) | fb);
+            }
           }
           H.flags(a) = fl;
           H.rejected(a) = KSCHED_NONE;
@@ -472,7 +593,6 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
 #pragma unroll
           for (int r = 0; r < kHotRes; ++r) { cb1[r] = H.bound(r, a); cb2[r] = H.bound2(r, a); }
           const bool closed = node_closed(bq, s.min_req, RH, cb1, cb2, fl);
-          if (has_topo) topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
           s.assign[pod] = NE + n;
           s.place_seq[pod] = seq;
           if (closed) {  // the node leaves the active set: its request vector goes back to global memory
@@ -486,8 +606,8 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         placed = true;
         __syncthreads();
         if (sh.placed_closed) --n_active;
-      } else {
-        nodes_visited += n_new;
+        if (has_topo) topo_record_block(c, s, row, s.nn_vals, s.nn_meta[wn], MAXN, wn, NE + wn);  // Topology.Record, one relation per thread
+        break;
       }
     } else if (!placed) {
       nodes_visited += n_new;  // every in-flight node is full; the reference still walks them
@@ -524,10 +644,46 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
               for (int r = 0; r < KSCHED_MAX_RES; ++r) sh.q[r] = r < R ? tm.daemon_requests[r] + (((p_res >> r) & 1) ? row.requests[r] : 0) : 0;
               bool same = f_valid;  // topology left every requirement exactly as K1 saw it
               for (int i = 0; i < fresh_t.n && same; ++i) same = req_equal(fresh_t.fin[i], fresh_t.merged[i]);
+              // the new node's requirement set: the template's, overlaid by what this Add touched
+              uint64_t meta = tm.reqs.meta & 0xFFFFFFFFull;
+              for (int i = 0; i < fresh_t.n; ++i) {
+                const int k = fresh_t.key[i];
+                const Req& f = fresh_t.fin[i];
+                const uint64_t bit = 1ull << k;
+                meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
+                if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
+                if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
+              }
+              sh.meta = meta;
+              sh.fd_slot = -1;
               if (same) path = kPathRow;
               else {
                 path = kPathDynamic;
-                build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, true, alloc_sorted, fresh_x);
+                if (!memo && !limits_active) {  // topology-constrained class: outcome memo keyed by the node's requirement set
+                  uint64_t vals[KSCHED_MAX_KEYS];
+                  uint64_t hsh = ((uint64_t)fc + 1) * 0x9E3779B97F4A7C15ull ^ meta;
+                  for (int k = 0; k < c.n_keys; ++k) {
+                    uint64_t val = tm.reqs.values[k];
+                    for (int i = 0; i < fresh_t.n; ++i) if (fresh_t.key[i] == k) val = fresh_t.fin[i].values;
+                    vals[k] = val;
+                    hsh = (hsh ^ val) * 0xBF58476D1CE4E5B9ull;
+                    hsh ^= hsh >> 29;
+                  }
+                  const int slot = (int)((hsh >> 13) & (uint64_t)(s.fd_cap - 1));
+                  const uint8_t st = s.fd_state[slot];
+                  bool hit = st != 0 && s.fd_fc[slot] == (uint32_t)fc && s.fd_meta[slot] == meta;
+                  for (int k = 0; k < c.n_keys && hit; ++k) hit = s.fd_vals[(size_t)slot * KSCHED_MAX_KEYS + k] == vals[k];
+                  sh.fd_slot = slot;
+                  if (hit) path = st == 1 ? kPathDynCached : kPathDynEmpty;
+                  else {
+                    s.fd_state[slot] = 0;  // being refilled: tags now, state when the outcome is known
+                    s.fd_fc[slot] = (uint32_t)fc;
+                    s.fd_meta[slot] = meta;
+                    for (int k = 0; k < c.n_keys; ++k) s.fd_vals[(size_t)slot * KSCHED_MAX_KEYS + k] = vals[k];
+                  }
+                }
+                if (path == kPathDynamic)
+                  build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, true, alloc_sorted, fresh_x);
               }
             } else if (memo) {
               s.fc_state[fc] = 2;
@@ -539,7 +695,9 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         __syncthreads();
         const int path = sh.path;
         GK_C(13 + (path > 4 ? 4 : path))
-        if (path == kPathReject || path == kPathCachedEmpty) continue;
+        GK_T(18)
+        if (path == kPathReject || path == kPathCachedEmpty || path == kPathDynEmpty) continue;
+        const int fd_slot = (path == kPathDynamic || path == kPathDynCached) ? sh.fd_slot : -1;
         const int a = n_active;
         if (path == kPathCached) {
           for (int w = tid; w < W32; w += blockDim.x) s.nn_opts[(size_t)w * MAXN + n] = s.fc_opts[fc * W32 + w];
@@ -559,9 +717,11 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
               }
             }
             uint32_t sw = 0;
-            if (base) sw = path == kPathRow ? (base & s.F[((size_t)fpos * V + v) * W32 + w]) : type_word(c, s, fresh_x, base, w);
+            if (path == kPathDynCached) sw = s.fd_opts[(size_t)fd_slot * W32 + w];
+            else if (base) sw = path == kPathRow ? (base & s.F[((size_t)fpos * V + v) * W32 + w]) : type_word(c, s, fresh_x, base, w);
             s.nn_opts[(size_t)w * MAXN + n] = sw;
             if (memo) s.fc_opts[fc * W32 + w] = sw;
+            if (path == kPathDynamic && fd_slot >= 0) s.fd_opts[(size_t)fd_slot * W32 + w] = sw;
             local_any = local_any || sw;
           }
           if (local_any) atomicOr(&sh.any, 1u);
@@ -574,9 +734,11 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           __syncthreads();
           if (!sh.any) {
             if (memo && tid == 0) s.fc_state[fc] = 2;
+            if (path == kPathDynamic && fd_slot >= 0 && tid == 0) s.fd_state[fd_slot] = 2;
             continue;
           }
         }
+        GK_T(19)
         // ---- commit the new node (NewNode + Add, node.go:44-107) — one thread, everything else was written above
         __syncthreads();
         if (tid == 0) {
@@ -588,26 +750,26 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
             sh.qp = s.fc_qp[fc];
             for (int r = 0; r < KSCHED_MAX_RES; ++r) sh.q[r] = s.fc_q[fc * KSCHED_MAX_RES + r];
           } else {
-            meta = tm.reqs.meta & 0xFFFFFFFFull;
-            for (int i = 0; i < fresh_t.n; ++i) {
-              const int k = fresh_t.key[i];
-              const Req& f = fresh_t.fin[i];
-              const uint64_t bit = 1ull << k;
-              meta &= ~((bit << KSCHED_META_PRESENT_SHIFT) | (bit << KSCHED_META_COMPLEMENT_SHIFT));
-              if (f.present) meta |= bit << KSCHED_META_PRESENT_SHIFT;
-              if (f.present && f.complement) meta |= bit << KSCHED_META_COMPLEMENT_SHIFT;
-            }
+            meta = sh.meta;
             // K1-row path without limits: the option set, hence its Pareto front, depends on (class, template) only
             const bool front_memo = path == kPathRow && !limits_active;
             if (front_memo && s.fc_front_state[fc]) {
               for (int r = 0; r < kHotRes; ++r) { sh.bound[r] = s.fc_bound[fc * kHotRes + r]; sh.bound2[r] = s.fc_bound2[fc * kHotRes + r]; }
               sh.front_bits = s.fc_dom[fc];
+            } else if (path == kPathDynCached) {
+              for (int r = 0; r < kHotRes; ++r) { sh.bound[r] = s.fd_bound[(size_t)fd_slot * kHotRes + r]; sh.bound2[r] = s.fd_bound2[(size_t)fd_slot * kHotRes + r]; }
+              sh.front_bits = s.fd_dom[fd_slot];
             } else {
               compute_front(c, s.nn_opts, MAXN, n, sh.bound, sh.bound2, &sh.front_bits);
               if (front_memo) {
                 for (int r = 0; r < kHotRes; ++r) { s.fc_bound[fc * kHotRes + r] = sh.bound[r]; s.fc_bound2[fc * kHotRes + r] = sh.bound2[r]; }
                 s.fc_dom[fc] = (uint8_t)sh.front_bits;
                 s.fc_front_state[fc] = 1;
+              }
+              if (path == kPathDynamic && fd_slot >= 0) {
+                for (int r = 0; r < kHotRes; ++r) { s.fd_bound[(size_t)fd_slot * kHotRes + r] = sh.bound[r]; s.fd_bound2[(size_t)fd_slot * kHotRes + r] = sh.bound2[r]; }
+                s.fd_dom[fd_slot] = (uint8_t)sh.front_bits;
+                s.fd_state[fd_slot] = 1;
               }
             }
             if (memo) {
@@ -636,7 +798,6 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
             H.rejected(a) = KSCHED_NONE;
           }
           sh.placed_closed = closed ? 1 : 0;
-          if (has_topo) topo_record(c, s, row, s.nn_vals, meta, MAXN, n, NE + n);
           s.assign[pod] = NE + n;
           s.place_seq[pod] = seq;
           if (limits_active) {  // subtractMax (scheduler.go:273-290): largest capacity among the surviving options
@@ -659,9 +820,11 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         ++tick;
         ++seq;
         __syncthreads();
+        if (has_topo) topo_record_block(c, s, row, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n);  // Topology.Record, one relation per thread
         ++n_new;
         if (!sh.placed_closed) ++n_active;
         placed = true;
+        GK_T(20)
       }
       if (fatal) return;
     }
@@ -856,6 +1019,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
   long long nodes_visited = 0, add_calls = 0;
   int fatal = 0;
   bool pt_nonempty = false;
+  uint32_t pt_class = KSCHED_NONE;
 
   for (int i = tid; i < s.n_pods; i += blockDim.x) {
     s.queue[i] = s.order[i];
@@ -983,10 +1147,10 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
 #ifdef KSCHED_PROFILE_PACK
       if (tid == 0) s.counters[8 + 9] += 1;
 #endif
-      LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited};
+      LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited, pt_class};
       generic_step(p, X, cur, first_pass, fpos_first, L);
       head = L.head; qlen = L.qlen; n_new = L.n_new; n_active = L.n_active; tick = L.tick; seq = L.seq; parity = L.parity; fatal = L.fatal;
-      epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited;
+      epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited; pt_class = L.pt_class;
       if (fatal) break;
       PK_T(5)
     }

@@ -71,6 +71,10 @@ KS_HD void req_store(ksched_reqset& s, ksched_bounds* b, int k, const Req& r) {
 
 // dictionary entries inside (gt, lt): withinIntPtrs (requirement.go:227-243) as a mask
 KS_HD uint64_t within_mask(bool has_gt, int64_t gt, bool has_lt, int64_t lt, const KeyMeta& km) {
+#if defined(__CUDA_ARCH__)
+  // Device code never sees Gt/Lt: ksched_load_catalog / ksched_upload refuse every requirement set that carries a bound.
+  return ~0ull;
+#endif
   if (!has_gt && !has_lt) return ~0ull;
   uint64_t out = 0;
   uint64_t m = km.int_mask;  // non-integer values are invalid once bounds are set
@@ -101,6 +105,15 @@ KS_HD Req req_intersect(const Req& a, const Req& b, const KeyMeta& km) {
   Req r;
   r.present = true;
   r.complement = a.complement && b.complement;
+#if defined(__CUDA_ARCH__)
+  r.has_gt = r.has_lt = false;
+  r.gt = r.lt = 0;
+  if (a.complement && b.complement) r.values = a.values | b.values;
+  else if (a.complement && !b.complement) r.values = b.values & ~a.values;
+  else if (!a.complement && b.complement) r.values = a.values & ~b.values;
+  else r.values = a.values & b.values;
+  return r;
+#endif
   r.has_gt = a.has_gt || b.has_gt;
   r.has_lt = a.has_lt || b.has_lt;
   r.gt = a.has_gt ? (b.has_gt ? (a.gt > b.gt ? a.gt : b.gt) : a.gt) : b.gt;
