@@ -24,6 +24,7 @@
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "ksched.h"
@@ -405,7 +406,19 @@ __global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel(K1Params p) 
 // ------------------------------------------------------------------------------------------------
 // K2: pack
 // ------------------------------------------------------------------------------------------------
+// One (class, group) relation with the group's immutable fields folded in (built at upload): everything
+// Topology.Record and the per-step topology build need about the relation arrives with ONE load.
+struct RelX {
+  uint32_t group, flags;
+  uint8_t key, type, has_filter, pad;
+  int32_t max_skew;
+  int32_t host_row;
+  uint32_t pad2[3];
+};
+static_assert(sizeof(RelX) == 32, "RelX is loaded as two 16-byte vectors");
+
 struct PackState {
+  const RelX* relx;                  // [n_class_topo], parallel to class_topo
   // problem (read-only)
   const ksched_pod_row* classes;
   const ksched_topo_group* groups;
@@ -502,6 +515,12 @@ struct K2Params {
   DevCatalog cat;
   PackState st;
 };
+// The pack kernel and every out-of-line device function it calls read their parameters from constant memory with
+// immediate offsets (a reference to a __grid_constant__ kernel parameter handed to a __noinline__ function degrades every
+// field access to a generic load with ~100 cycles of latency, on a code path that is one dependent chain).
+// One copy per device: run_pack() orders launches of different handles on the same device behind each other.
+__constant__ K2Params g_k2;
+#define KS_K2 const DevCatalog& c = g_k2.cat; const PackState& s = g_k2.st; (void)c; (void)s;
 
 struct Touched {
   int n;
@@ -531,6 +550,13 @@ struct PodTopo {  // per (pod step, constraining group): node-independent part o
   int overflow;
 };
 
+// Per-CTA working set of the pack kernel's generic step, at file scope so that every out-of-line function reaches it with
+// immediate shared-memory addresses instead of pointers handed down the call chain.
+__shared__ ksched_pod_row g_row;  // the pod of the current step (copied from its FFD row / class row by warp 0)
+__shared__ PodTopo g_pt;          // its topology constraints
+#define KS_ROW const ksched_pod_row& row = g_row; (void)row;
+#define KS_PT PodTopo& pt = g_pt; (void)pt;
+
 __device__ __forceinline__ Req load_soa(const uint64_t* vals, uint64_t meta, int stride, int idx, int k) {
   Req r;
   r.present = (meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
@@ -555,7 +581,9 @@ __device__ __forceinline__ bool req_equal(const Req& a, const Req& b) {
 
 // TopologyGroup.Get for a mask-key group (topologygroup.go:88-243). node_dom = the node's requirement for the
 // key after the pod's own requirements were merged (topology.go:156-159). Returns false when Len()==0.
-__device__ __noinline__ bool topo_domains_mask(const DevCatalog& c, const PackState& s, const PodTopo& pt, int j, const Req& node_dom, uint64_t* out) {
+__device__ __noinline__ bool topo_domains_mask(int j, const Req& node_dom, uint64_t* out) {
+  KS_K2
+  KS_PT
   const int k = pt.gkey[j];
   KeyMeta km = key_meta(c, k);
   const uint64_t registered = pt.registered[j];
@@ -587,7 +615,9 @@ __device__ __noinline__ bool topo_domains_mask(const DevCatalog& c, const PackSt
 }
 
 // hostname-key groups: the node's hostname domain is its slot.
-__device__ __noinline__ bool topo_hostname_ok(const PackState& s, const PodTopo& pt, int j, int slot, bool pod_allows_slot) {
+__device__ __noinline__ bool topo_hostname_ok(int j, int slot, bool pod_allows_slot) {
+  KS_K2
+  KS_PT
   const int stride = s.n_existing + s.max_new;
   const int32_t cnt = s.grp_host[(size_t)pt.host_row[j] * stride + slot];
   // a group created by a later Topology.Update only knows hostnames registered after that, plus those it counted pods on
@@ -615,8 +645,9 @@ __device__ __forceinline__ bool hostname_allows(const PackState& s, const ksched
 
 // Requirement phase of Node.Add / ExistingNode.Add: Compatible(pod) + merge, topology tighten + Compatible + merge.
 // vals/meta/stride/idx describe the node's requirement set. Returns false on reject.
-__device__ __noinline__ bool requirements_phase(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const PodTopo& pt,
-                                   const uint64_t* vals, uint64_t meta, int stride, int idx, int slot, bool is_existing, Touched& t) {
+__device__ __noinline__ bool requirements_phase(const uint64_t* vals, uint64_t meta, int stride, int idx, int slot, bool is_existing, Touched& t) {
+  KS_K2
+  KS_ROW KS_PT
   t.n = 0;
   if (!hostname_allows(s, row, slot, is_existing)) return false;
   uint32_t podkeys = (uint32_t)(row.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF;
@@ -637,7 +668,7 @@ __device__ __noinline__ bool requirements_phase(const DevCatalog& c, const PackS
   }
   for (int j = 0; j < pt.n; ++j) {
     if (pt.gkey[j] == KSCHED_KEY_HOSTNAME) {
-      if (!topo_hostname_ok(s, pt, j, slot, hostname_allows(s, row, slot, is_existing))) return false;
+      if (!topo_hostname_ok(j, slot, hostname_allows(s, row, slot, is_existing))) return false;
       continue;
     }
     const int k = pt.gkey[j];
@@ -653,7 +684,7 @@ __device__ __noinline__ bool requirements_phase(const DevCatalog& c, const PackS
       t.changed[ti] = false;
     }
     uint64_t dom;
-    if (!topo_domains_mask(c, s, pt, j, t.merged[ti], &dom)) return false;
+    if (!topo_domains_mask(j, t.merged[ti], &dom)) return false;
     Req d{dom, 0, 0, true, false, false, false};
     KeyMeta km = key_meta(c, k);
     t.fin[ti] = ksched::key_add(t.fin[ti], d, km);  // requirements.Add(domains) topology.go:164
@@ -682,9 +713,11 @@ struct TypeCtx {
   uint32_t zmask, cmask;
   uint32_t itype_req;
 };
-__device__ __noinline__ void build_type_ctx(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const Touched& t, const long long* q,
+__device__ __noinline__ void build_type_ctx(const Touched& t, const long long* q,
                                uint32_t q_present, const uint64_t* vals, uint64_t meta, int stride, int idx, bool fresh,
                                const int64_t* alloc_sorted, TypeCtx& x, bool with_ranks = true) {
+  KS_K2
+  KS_ROW
   x.res_mask = q_present;
   if (with_ranks)
     for (int r = 0; r < c.n_res; ++r) x.rank[r] = ((q_present >> r) & 1) ? fit_rank(alloc_sorted, c.n_types, r, q[r]) : 0;
@@ -754,18 +787,18 @@ __device__ __forceinline__ uint32_t type_word(const DevCatalog& c, const PackSta
 
 // Node-independent part of the pod's topology constraints for this step, one constraining (class, group) relation j.
 // Static half: what the relation and its group are (a function of the pod class only).
-__device__ __noinline__ void fill_pod_topo_static(const PackState& s, const ksched_class_topo ct, PodTopo& pt, int j) {
-  const int gi = (int)ct.group;
-  const ksched_topo_group& g = s.groups[gi];
-  pt.group[j] = gi;
-  pt.flags[j] = ct.flags;
-  pt.gkey[j] = g.key;
-  pt.gtype[j] = g.type;
-  pt.gskew[j] = g.max_skew;
-  pt.host_row[j] = s.grp_host_row[gi];
+__device__ __forceinline__ void fill_pod_topo_static(const RelX& x, PodTopo& pt, int j) {
+  pt.group[j] = (int)x.group;
+  pt.flags[j] = x.flags;
+  pt.gkey[j] = x.key;
+  pt.gtype[j] = x.type;
+  pt.gskew[j] = x.max_skew;
+  pt.host_row[j] = x.host_row;
 }
 // Dynamic half: everything derived from the group's counters, re-read every step.
-__device__ __noinline__ void fill_pod_topo_dynamic(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt, int j) {
+__device__ __noinline__ void fill_pod_topo_dynamic(int j) {
+  KS_K2
+  KS_ROW KS_PT
   const int gi = pt.group[j];
   const uint32_t flags = pt.flags[j];
   const int gkey = pt.gkey[j], gtype = pt.gtype[j], gskew = pt.gskew[j];
@@ -794,29 +827,33 @@ __device__ __noinline__ void fill_pod_topo_dynamic(const DevCatalog& c, const Pa
   pt.registered[j] = registered;
   uint64_t m = registered & pod_allowed;
   if (gtype == 0) {
-    int32_t mn = INT32_MAX;
-    while (m) {
-      int d = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      int32_t cnt = s.grp_cnt[(size_t)gi * 64 + d];
-      mn = cnt < mn ? cnt : mn;
+    // counts of every registered domain, loaded once (independent loads), ids in ascending order
+    int32_t cnts[64];
+    uint8_t ids[64];
+    int nd = 0;
+    for (uint64_t all = registered; all; all &= all - 1) {
+      const int d = __ffsll((long long)all) - 1;
+      ids[nd] = (uint8_t)d;
+      cnts[nd] = s.grp_cnt[(size_t)gi * 64 + d];
+      ++nd;
     }
+    int32_t mn = INT32_MAX;  // domainMinCount over the pod's own domains (topologygroup.go:186-203)
+    for (int i = 0; i < nd; ++i)
+      if (((m >> ids[i]) & 1) && cnts[i] < mn) mn = cnts[i];
     pt.min_count[j] = mn;
-    // registered domains within the skew bound, insertion-sorted by (count, id); ids arrive in ascending order
+    // registered domains within the skew bound, insertion-sorted by (count, id)
     const int self = (flags & KSCHED_TOPO_SELECTS) ? 1 : 0;
     int ns = 0;
-    int32_t cnts[64];
-    uint64_t all = registered, okm = 0;
-    while (all) {
-      int d = __ffsll((long long)all) - 1;
-      all &= all - 1;
-      const int64_t cnt = (int64_t)s.grp_cnt[(size_t)gi * 64 + d] + self;
+    int32_t sc[64];
+    uint64_t okm = 0;
+    for (int i = 0; i < nd; ++i) {
+      const int64_t cnt = (int64_t)cnts[i] + self;
       if (cnt - (int64_t)mn > (int64_t)gskew) continue;
-      okm |= 1ull << d;
-      int i = ns++;
-      while (i > 0 && cnts[i - 1] > (int32_t)cnt) { cnts[i] = cnts[i - 1]; pt.sorted[j][i] = pt.sorted[j][i - 1]; --i; }
-      cnts[i] = (int32_t)cnt;
-      pt.sorted[j][i] = (uint8_t)d;
+      okm |= 1ull << ids[i];
+      int q = ns++;
+      while (q > 0 && sc[q - 1] > (int32_t)cnt) { sc[q] = sc[q - 1]; pt.sorted[j][q] = pt.sorted[j][q - 1]; --q; }
+      sc[q] = (int32_t)cnt;
+      pt.sorted[j][q] = ids[i];
     }
     pt.n_sorted[j] = (uint8_t)ns;
     pt.ok_mask[j] = okm;
@@ -841,20 +878,22 @@ __device__ __noinline__ void fill_pod_topo_dynamic(const DevCatalog& c, const Pa
 }
 
 // Called by the 32 lanes of warp 0: one (class, group) relation per lane, constraining ones compacted in order.
-__device__ void build_pod_topo(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt) {
+__device__ void build_pod_topo() {
+  KS_K2
+  KS_ROW KS_PT
   const int lane = threadIdx.x & 31;
   const uint32_t begin = row.topo_begin, end = row.topo_end;
   int n = 0, overflow = 0;
   for (uint32_t base = begin; base < end; base += 32) {  // uniform trip count
     const uint32_t e = base + lane;
-    ksched_class_topo ct{0, 0};
-    if (e < end) ct = s.class_topo[e];
-    const bool cons = e < end && (ct.flags & KSCHED_TOPO_CONSTRAINS);
+    RelX x{};
+    if (e < end) x = s.relx[e];
+    const bool cons = e < end && (x.flags & KSCHED_TOPO_CONSTRAINS);
     const unsigned bal = __ballot_sync(0xffffffffu, cons);
     const int j = n + __popc(bal & ((1u << lane) - 1));
     if (cons && j < kMaxCG) {
-      fill_pod_topo_static(s, ct, pt, j);
-      fill_pod_topo_dynamic(c, s, row, pt, j);
+      fill_pod_topo_static(x, pt, j);
+      fill_pod_topo_dynamic(j);
     }
     n += __popc(bal);
     if (n > kMaxCG) { overflow = 1; n = kMaxCG; }
@@ -862,20 +901,24 @@ __device__ void build_pod_topo(const DevCatalog& c, const PackState& s, const ks
   if (lane == 0) { pt.n = n; pt.overflow = overflow; }
 }
 // The previous step's pod had the same class: the relations are the same, only the counters moved.
-__device__ void refresh_pod_topo(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, PodTopo& pt) {
+__device__ void refresh_pod_topo() {
+  KS_K2
+  KS_ROW KS_PT
   const int lane = threadIdx.x & 31;
-  if (lane < pt.n) fill_pod_topo_dynamic(c, s, row, pt, lane);
+  if (lane < pt.n) fill_pod_topo_dynamic(lane);
 }
 
 // A NECESSARY condition of requirements_phase for an in-flight node, cheap enough to run on every candidate: the
 // hostname groups exactly, spread groups over mask keys through the set of admissible domains. The node that wins the
 // argmin is then checked in full (and excluded if it fails).
-__device__ __forceinline__ bool topo_prefilter(const DevCatalog& c, const PackState& s, const PodTopo& pt, const uint64_t* vals, uint64_t meta,
+__device__ __forceinline__ bool topo_prefilter(const uint64_t* vals, uint64_t meta,
                                                int stride, int idx, int slot) {
+  KS_K2
+  KS_PT
   for (int j = 0; j < pt.n; ++j) {
     const int k = pt.gkey[j];
     if (k == KSCHED_KEY_HOSTNAME) {
-      if (!topo_hostname_ok(s, pt, j, slot, true)) return false;
+      if (!topo_hostname_ok(j, slot, true)) return false;
       continue;
     }
     if (pt.gtype[j] != 0) {
@@ -890,8 +933,9 @@ __device__ __forceinline__ bool topo_prefilter(const DevCatalog& c, const PackSt
 }
 
 // TopologyNodeFilter.MatchesRequirements (topologynodefilter.go:57-70): any term Compatible with the node requirements
-__device__ __noinline__ bool filter_matches(const DevCatalog& c, const PackState& s, const ksched_topo_group& g, const uint64_t* vals, uint64_t meta,
+__device__ __noinline__ bool filter_matches(const ksched_topo_group& g, const uint64_t* vals, uint64_t meta,
                                int stride, int idx) {
+  KS_K2
   if (g.filter_begin == g.filter_end) return true;
   for (uint32_t f = g.filter_begin; f < g.filter_end; ++f) {
     const ksched_reqset& term = s.filter_terms[f];
@@ -911,43 +955,53 @@ __device__ __noinline__ bool filter_matches(const DevCatalog& c, const PackState
 
 // Topology.Record (topology.go:120-143) for ONE (class, group) relation, after the node's requirements were committed.
 // Relations of one class name distinct groups, so different threads may record different relations concurrently.
-__device__ __noinline__ void topo_record_entry(const DevCatalog& c, const PackState& s, uint32_t e, const uint64_t* vals, uint64_t meta, int stride, int idx, int slot) {
+__device__ __noinline__ void topo_record_entry(uint32_t e, const uint64_t* vals, uint64_t meta, int stride, int idx, int slot) {
+  KS_K2
   const int hstride = s.n_existing + s.max_new;
-  const ksched_class_topo ct = s.class_topo[e];
-  const int gi = (int)ct.group;
-  const ksched_topo_group& g = s.groups[gi];
-  if (!s.grp_active[gi]) return;  // the group does not exist yet
+  const RelX x = s.relx[e];
+  const int gi = (int)x.group;
+  if (!(x.flags & (KSCHED_TOPO_RECORDS | KSCHED_TOPO_RECORDS_INVERSE))) return;
+  // the loads the record needs are issued together (one memory round trip, not three)
+  const uint8_t active = s.grp_active[gi];
+  uint16_t* const host_cell = x.key == KSCHED_KEY_HOSTNAME ? &s.grp_host[(size_t)x.host_row * hstride + slot] : nullptr;
+  const uint32_t host_old = host_cell ? *host_cell : 0;
+  const int32_t host_total = host_cell ? s.grp_host_total[gi] : 0;
+  if (!active) return;  // the group does not exist yet
   bool rec = false, all_values = false;
-  if (ct.flags & KSCHED_TOPO_RECORDS) {
-    if (filter_matches(c, s, g, vals, meta, stride, idx)) { rec = true; all_values = (g.type == 2); }
+  if (x.flags & KSCHED_TOPO_RECORDS) {
+    if (!x.has_filter || filter_matches(s.groups[gi], vals, meta, stride, idx)) { rec = true; all_values = (x.type == 2); }
   }
-  bool rec_inv = (ct.flags & KSCHED_TOPO_RECORDS_INVERSE) != 0;
+  const bool rec_inv = (x.flags & KSCHED_TOPO_RECORDS_INVERSE) != 0;
+  if (x.key == KSCHED_KEY_HOSTNAME) {  // the node's hostname requirement is always In [its own hostname]
+    const int times = (rec ? 1 : 0) + (rec_inv ? 1 : 0);
+    if (!times) return;
+    if (host_old == 0) s.grp_host_total[gi] = host_total + 1;
+    const uint32_t now = host_old + times;
+    *host_cell = (uint16_t)(now > 0xFFFF ? 0xFFFF : now);
+    return;
+  }
   for (int pass = 0; pass < 2; ++pass) {
     const bool doit = pass == 0 ? rec : rec_inv;
     const bool allv = pass == 0 ? all_values : true;
     if (!doit) continue;
-    if (g.key == KSCHED_KEY_HOSTNAME) {  // the node's hostname requirement is always In [its own hostname]
-      uint16_t* cell = &s.grp_host[(size_t)s.grp_host_row[gi] * hstride + slot];
-      if (*cell == 0) s.grp_host_total[gi]++;
-      if (*cell < 0xFFFF) (*cell)++;
-    } else {
-      Req r = load_soa(vals, meta, stride, idx, g.key);
-      uint64_t v = 0;
-      if (allv) v = r.present ? r.values : 0;  // domains.Values(): members, or the excluded set of a complement
-      else if (r.present && ksched::req_len_one(r)) v = r.values;
-      while (v) {
-        int d = __ffsll((long long)v) - 1;
-        v &= v - 1;
-        s.grp_cnt[(size_t)gi * 64 + d]++;
-        s.grp_registered[gi] |= 1ull << d;
-      }
+    Req r = load_soa(vals, meta, stride, idx, x.key);
+    uint64_t v = 0;
+    if (allv) v = r.present ? r.values : 0;  // domains.Values(): members, or the excluded set of a complement
+    else if (r.present && ksched::req_len_one(r)) v = r.values;
+    while (v) {
+      int d = __ffsll((long long)v) - 1;
+      v &= v - 1;
+      s.grp_cnt[(size_t)gi * 64 + d]++;
+      s.grp_registered[gi] |= 1ull << d;
     }
   }
 }
 // every thread of the CTA: relation tid, tid + blockDim, ... (the commit this records must be visible: call after a barrier)
-__device__ __forceinline__ void topo_record_block(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const uint64_t* vals, uint64_t meta,
+__device__ __forceinline__ void topo_record_block(const uint64_t* vals, uint64_t meta,
                                                   int stride, int idx, int slot) {
-  for (uint32_t e = row.topo_begin + threadIdx.x; e < row.topo_end; e += blockDim.x) topo_record_entry(c, s, e, vals, meta, stride, idx, slot);
+  KS_K2
+  KS_ROW
+  for (uint32_t e = row.topo_begin + threadIdx.x; e < row.topo_end; e += blockDim.x) topo_record_entry(e, vals, meta, stride, idx, slot);
 }
 
 }  // namespace
@@ -987,6 +1041,7 @@ struct DevBuf {
 }  // namespace
 
 struct ksched_handle {
+  K2Params k2_host;  // staging copy of the pack kernel's constant-memory parameters (must outlive the async copy)
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -1014,6 +1069,7 @@ struct ksched_handle {
   DevBuf<uint8_t> d_cub_tmp, d_itype_comp, d_ex_closed, d_nn_tmpl;
   DevBuf<ksched_topo_group> d_groups;
   DevBuf<ksched_class_topo> d_class_topo;
+  DevBuf<RelX> d_relx;
   DevBuf<ksched_reqset> d_filter_terms;
   DevBuf<int32_t> d_hostname_reqs, d_relax, d_assign, d_place_seq, d_last_len, d_nn_count, d_nn_tb, d_ov_node, d_perm_desc, d_grp_cnt,
       d_grp_cnt0, d_grp_host_row, d_grp_host_total, d_grp_host_total0;
@@ -1085,6 +1141,16 @@ int ksched_create(int device_ordinal, ksched_handle** out) {
     return KSCHED_ERR_CUDA;
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
+  {
+    // CUDA loads kernels lazily on first launch: pull ours in here, not inside the first Solve
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, pack_kernel);
+    cudaFuncGetAttributes(&fa, feasibility_kernel);
+    cudaFuncGetAttributes(&fa, finalize_options_kernel);
+    cudaFuncGetAttributes(&fa, gather_rows_kernel);
+    cudaFuncGetAttributes(&fa, sort_keys_kernel);
+    cudaFuncGetAttributes(&fa, gather_u64_kernel);
+  }
   *out = h;
   return KSCHED_OK;
 }
@@ -1386,6 +1452,19 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
     CUDA_TRY(h, h->d_grp_active.ensure(std::max(NG, 1)));
     CUDA_TRY(h, h->d_grp_min_slot.ensure(std::max(NG, 1)));
     CUDA_TRY(h, upload_vec(h, h->d_grp_host_row, host_row));
+    {
+      std::vector<RelX> relx((size_t)std::max(pb->n_class_topo, 1));
+      for (int e = 0; e < pb->n_class_topo; ++e) {
+        const ksched_class_topo& ct = pb->class_topo[e];
+        if ((int)ct.group >= NG) { h->err = "class_topo names a group out of range"; return KSCHED_ERR_INVALID; }
+        const ksched_topo_group& g = pb->groups[ct.group];
+        RelX x{};
+        x.group = ct.group; x.flags = ct.flags; x.key = g.key; x.type = g.type; x.has_filter = g.filter_begin != g.filter_end;
+        x.max_skew = g.max_skew; x.host_row = host_row[ct.group];
+        relx[e] = x;
+      }
+      CUDA_TRY(h, upload_vec(h, h->d_relx, relx));
+    }
     CUDA_TRY(h, upload_vec(h, h->d_grp_host_total0, host_total));
     CUDA_TRY(h, upload_vec(h, h->d_grp_cnt0, cnt));
     CUDA_TRY(h, upload_vec(h, h->d_grp_registered0, registered));
@@ -1549,10 +1628,16 @@ static int reset_state(ksched_handle* h) {
   return KSCHED_OK;
 }
 
+// g_k2 is one __constant__ object per device: a launch may only overwrite it after the previous pack kernel on that
+// device (possibly of another handle, on another stream) has finished. Ordered on the device, never on the host.
+static std::mutex g_k2_mu;
+static cudaEvent_t g_k2_done[64] = {};
+
 static int run_pack(ksched_handle* h) {
-  K2Params k2;
+  K2Params& k2 = h->k2_host;
   k2.cat = h->cat;
   PackState& s = k2.st;
+  s.relx = h->d_relx.ptr;
   s.classes = h->d_classes.ptr; s.groups = h->d_groups.ptr; s.class_topo = h->d_class_topo.ptr; s.filter_terms = h->d_filter_terms.ptr;
   s.itype_sets = h->d_itype_sets.ptr; s.itype_complement = h->d_itype_comp.ptr; s.hostname_reqs = h->d_hostname_reqs.ptr;
   s.order = h->d_order.ptr; s.rows = h->d_rows.ptr; s.F = h->d_F.ptr; s.best = h->d_best.ptr;
@@ -1588,7 +1673,16 @@ static int run_pack(ksched_handle* h) {
   // nodes to examine per pod (existing nodes, large in-flight sets)
   int threads = h->n_existing >= 2048 ? kPackThreads : (h->n_existing >= 256 ? 256 : 128);
   if (const char* e = getenv("KSCHED_PACK_THREADS")) { int v = atoi(e); if (v >= 32 && v <= kPackThreads && v % 32 == 0) threads = v; }
-  pack_kernel<<<1, threads, smem, h->stream>>>(k2);
+  {
+    std::lock_guard<std::mutex> lock(g_k2_mu);
+    if (h->device < 0 || h->device >= 64) { h->err = "device ordinal out of range"; return KSCHED_ERR_INVALID; }
+    cudaEvent_t& done = g_k2_done[h->device];
+    if (!done) CUDA_TRY(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, done, 0));  // no-op for an event that was never recorded
+    CUDA_TRY(h, cudaMemcpyToSymbolAsync(g_k2, &k2, sizeof(K2Params), 0, cudaMemcpyHostToDevice, h->stream));
+    pack_kernel<<<1, threads, smem, h->stream>>>();
+    CUDA_TRY(h, cudaEventRecord(done, h->stream));
+  }
   finalize_options_kernel<<<148, 256, 0, h->stream>>>(h->cat, h->d_counters.ptr, h->d_nn_req.ptr, h->d_nn_req_present.ptr, h->d_nn_opts.ptr, h->max_new);
   h->tm.pack_launches = 2;
   return KSCHED_OK;
@@ -1669,6 +1763,7 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
           counters[19], counters[20], counters[21], counters[22], counters[23], counters[24], counters[25], counters[5]);
   fprintf(stderr, "[pack profile] fresh: decide=%lld words=%lld commit=%lld rest=%lld | in-flight verify=%lld\n", counters[26], counters[27], counters[28],
           counters[12], counters[29]);
+  fprintf(stderr, "[pack profile] in-flight commit: winner+barrier=%lld record=%lld rest=%lld\n", counters[30], counters[31], counters[11]);
 #endif
   if (counters[4] != 0) {
     h->err = counters[4] == KSCHED_ERR_OVERFLOW ? "new-node capacity exceeded" : "a pod is constrained by more topology groups than the kernel supports";

@@ -76,7 +76,8 @@ constexpr unsigned short kFlExact = 1, kFlTwo = 0x20;
 // Pareto front (size <= 2) of the allocatable vectors of a node's stored options, or per-resource maxima when the front
 // is larger. Candidates are the per-resource arg-max types (found by probing each resource's descending order); a
 // candidate pair is a front iff every stored option is dominated by one of the two.
-__device__ __noinline__ void compute_front(const DevCatalog& c, const uint32_t* opts, int stride, int n, long long* b1, long long* b2, unsigned short* bits) {
+__device__ __noinline__ void compute_front(const uint32_t* opts, int stride, int n, long long* b1, long long* b2, unsigned short* bits) {
+  KS_K2
   const int R = c.n_res < kHotRes ? c.n_res : kHotRes;
   const int T = c.n_types;
   int arg[kHotRes];
@@ -216,16 +217,20 @@ struct SlowEval {
   bool changed;
   bool need_types;  // with_types == false: the instance-type options still have to be checked (by the whole CTA, for the winner only)
 };
-__device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, const PodTopo& pt, bool plain,
-                                           int n, unsigned short fl, const long long* q_hot, const int64_t* alloc_sorted, bool with_types, SlowEval& e) {
+// `t` receives the touched requirement keys: the thread's own e.t, or the CTA's shared Touched when the caller is the argmin winner
+__device__ __noinline__ bool evaluate_slow(bool plain,
+                                           int n, unsigned short fl, const long long* q_hot, const int64_t* alloc_sorted, bool with_types, Touched& t,
+                                           SlowEval& e) {
+  KS_K2
+  KS_ROW
   const int MAXN = s.max_new, NE = s.n_existing, R = c.n_res, W32 = c.W32;
   const uint32_t p_res = row.res_present;
-  e.t.n = 0;
+  t.n = 0;
   e.changed = false;
   bool need_types = !(fl & 1) || row.itype_req != KSCHED_NONE;
   if (!plain) {
-    if (!requirements_phase(c, s, row, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, e.t)) return false;
-    for (int i = 0; i < e.t.n; ++i) e.changed = e.changed || e.t.changed[i];
+    if (!requirements_phase(s.nn_vals, s.nn_meta[n], MAXN, n, NE + n, false, t)) return false;
+    for (int i = 0; i < t.n; ++i) e.changed = e.changed || t.changed[i];
     need_types = need_types || e.changed;
   }
   for (int r = 0; r < kHotRes; ++r) e.q[r] = q_hot[r];
@@ -233,7 +238,7 @@ __device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState&
   e.qp = s.nn_req_present[n] | p_res;
   e.need_types = need_types && !with_types;
   if (!need_types || !with_types) return true;  // the dominant option fits and no requirement changed / checked later
-  build_type_ctx(c, s, row, e.t, e.q, e.qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, alloc_sorted, e.x);
+  build_type_ctx(t, e.q, e.qp, s.nn_vals, s.nn_meta[n], MAXN, n, false, alloc_sorted, e.x);
   for (int w = 0; w < W32; ++w) {
     const uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
     if (base && type_word(c, s, e.x, base, w)) return true;
@@ -241,7 +246,8 @@ __device__ __noinline__ bool evaluate_slow(const DevCatalog& c, const PackState&
   return false;
 }
 // Requirement part of a commit: the node's new masks.
-__device__ __forceinline__ uint64_t commit_reqs(const PackState& s, int n, const Touched& t) {
+__device__ __forceinline__ uint64_t commit_reqs(int n, const Touched& t) {
+  KS_K2
   const int MAXN = s.max_new;
   uint64_t meta = s.nn_meta[n];
   for (int i = 0; i < t.n; ++i) {
@@ -258,54 +264,59 @@ __device__ __forceinline__ uint64_t commit_reqs(const PackState& s, int n, const
 }
 // Requirement-changing commit done by ONE thread (fallback mode): new masks, requirement-driven narrowing of the stored
 // options, new bounds.
-__device__ __noinline__ void commit_slow(const DevCatalog& c, const PackState& s, const ksched_pod_row& row, int n, SlowEval& e, long long* bound,
+__device__ __noinline__ void commit_slow(int n, SlowEval& e, long long* bound,
                                          long long* bound2, unsigned short* front_bits, uint64_t* meta_out) {
+  KS_K2
+  KS_ROW
   const int MAXN = s.max_new, W32 = c.W32;
-  *meta_out = commit_reqs(s, n, e.t);
+  *meta_out = commit_reqs(n, e.t);
   e.x.res_mask = 0;  // resources stay lazy (finalize_options_kernel)
   for (int w = 0; w < W32; ++w) {
     const uint32_t base = s.nn_opts[(size_t)w * MAXN + n];
     if (base) s.nn_opts[(size_t)w * MAXN + n] = type_word(c, s, e.x, base, w);
   }
-  compute_front(c, s.nn_opts, MAXN, n, bound, bound2, front_bits);
+  compute_front(s.nn_opts, MAXN, n, bound, bound2, front_bits);
 }
 
-struct StepCtx {  // per-CTA objects shared by the slow path
-  PodTopo* pt;
-  Touched* fresh_t;
-  TypeCtx* fresh_x;
-  unsigned long long (*red)[32];
-  StepShared* sh;
-  const uint32_t* tmpl_taintset;
-  Hot H;
-  const int64_t* alloc_sorted;
-};
+// per-CTA objects of the generic step (file scope: see g_row / g_pt in ksched.cu)
+__shared__ Touched g_fresh_t;
+__shared__ TypeCtx g_fresh_x;
+__shared__ unsigned long long g_red[2][32];
+__shared__ StepShared g_sh;
+__shared__ uint32_t g_tmpl_taintset[KSCHED_MAX_TEMPLATES];
+extern __shared__ __align__(16) unsigned char dyn_smem[];  // HotSmem, then (optionally) the sorted allocatable arrays
+__device__ __forceinline__ Hot make_hot(const PackState& s) {
+  return Hot{reinterpret_cast<HotSmem*>(dyn_smem), s.ov_key, s.ov_q, s.ov_bound, s.ov_bound2, s.ov_node, s.ov_flags, s.ov_absorbed, s.ov_rejected, s.max_new};
+}
+__device__ __forceinline__ const int64_t* alloc_table(const DevCatalog& c, const PackState& s) {
+  return s.alloc_in_smem ? reinterpret_cast<const int64_t*>(dyn_smem + sizeof(HotSmem)) : c.alloc_sorted;
+}
 struct LoopVars {
   int head, qlen, n_new, n_active, tick, seq, parity, fatal;
   uint32_t epoch;
   bool pt_nonempty;
   long long nodes_visited;
-  uint32_t pt_class;  // class the shared PodTopo was built for (KSCHED_NONE: none)
+  uint32_t pt_class;   // class the shared PodTopo was built for (KSCHED_NONE: none)
+  uint32_t row_class;  // class whose row g_row holds
 };
 
 // One full Scheduler.add for one pod (existing nodes -> in-flight nodes -> new node -> relax/requeue). Every thread of
 // the CTA calls it together. Kept out of line: the steady-state path in pack_kernel must stay a few KB of code, because a
 // single resident CTA runs straight out of the instruction cache hierarchy (L0 ~6 KB, L1.5 32 KB).
-__device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, const PodRegs& cur, bool first_pass, int fpos_first, LoopVars& L) {
-  const DevCatalog& c = p.cat;
-  const PackState& s = p.st;
+__device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, int fpos_first, LoopVars& L) {
+  KS_K2
   const int tid = threadIdx.x, lane = tid & 31;
   const int W32 = c.W32, V = c.n_templates, NE = s.n_existing, MAXN = s.max_new;
   const int R = c.n_res, RH = R < kHotRes ? R : kHotRes;
   const int qcap = s.n_pods + 1;
-  PodTopo& pt = *X.pt;
-  Touched& fresh_t = *X.fresh_t;
-  TypeCtx& fresh_x = *X.fresh_x;
-  unsigned long long (*red)[32] = X.red;
-  StepShared& sh = *X.sh;
-  const uint32_t* tmpl_taintset = X.tmpl_taintset;
-  const Hot& H = X.H;
-  const int64_t* alloc_sorted = X.alloc_sorted;
+  PodTopo& pt = g_pt;
+  Touched& fresh_t = g_fresh_t;
+  TypeCtx& fresh_x = g_fresh_x;
+  unsigned long long (*red)[32] = g_red;
+  StepShared& sh = g_sh;
+  const uint32_t* tmpl_taintset = g_tmpl_taintset;
+  const Hot H = make_hot(s);
+  const int64_t* alloc_sorted = alloc_table(c, s);
   int &head = L.head, &qlen = L.qlen, &n_new = L.n_new, &n_active = L.n_active, &tick = L.tick, &seq = L.seq, &parity = L.parity, &fatal = L.fatal;
   uint32_t& epoch = L.epoch;
   bool& pt_nonempty = L.pt_nonempty;
@@ -320,7 +331,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
 #define GK_C(i)
 #endif
     const uint32_t pod = cur.pod, cls = (uint32_t)cur.cls64;
-    const ksched_pod_row& row = *cur.row;
+    const ksched_pod_row& row = g_row;
     const uint32_t p_res = cur.res;
     long long preq[kHotRes];
 #pragma unroll
@@ -328,16 +339,29 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
     const uint64_t p_tol = cur.tol, p_hpc = cur.hpc, p_hpe = cur.hpe;
     const uint32_t p_keys = (uint32_t)(cur.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF, p_itype = cur.itype, p_hostname = cur.hostname;
     const bool has_topo = cur.topo_begin != cur.topo_end;
-    if (has_topo || pt_nonempty) {
-      __syncthreads();  // previous step's readers of pt are done
+    // The pod's 256-byte row lives in shared memory (everything below reads it with immediate addresses); rows of one
+    // class are identical, so it is copied on a class change only.
+    const bool new_row = L.row_class != cls;
+    const bool topo_step = has_topo || pt_nonempty;
+    if (new_row || topo_step) {
+      __syncthreads();  // previous step's readers of g_row / g_pt are done
       if (tid < 32) {
-        if (pt_class == cls && !pt.overflow) refresh_pod_topo(c, s, row, pt);  // same relations as the previous step, new counters
-        else build_pod_topo(c, s, row, pt);
+        if (new_row) {
+          reinterpret_cast<uint64_t*>(&g_row)[tid] = reinterpret_cast<const uint64_t*>(cur.row)[tid];
+          __syncwarp();
+        }
+        if (topo_step) {
+          if (pt_class == cls && !pt.overflow) refresh_pod_topo();  // same relations as the previous step, new counters
+          else build_pod_topo();
+        }
       }
-      pt_class = cls;
+      L.row_class = cls;
+      if (topo_step) pt_class = cls;
       __syncthreads();
-      pt_nonempty = pt.n != 0;
-      if (pt.overflow) { fatal = KSCHED_ERR_UNSUPPORTED; return; }
+      if (topo_step) {
+        pt_nonempty = pt.n != 0;
+        if (pt.overflow) { fatal = KSCHED_ERR_UNSUPPORTED; return; }
+      }
     }
     const bool plain = p_keys == 0 && !pt_nonempty && p_itype == KSCHED_NONE && p_hostname == KSCHED_NONE;  // no requirement can change
     const bool simple = !has_topo && p_hpc == 0 && p_hpe == 0;  // the requirement verdict memo (HotSmem::absorbed/rejected) applies
@@ -367,7 +391,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           bool allowed = it == KSCHED_NONE ? (s.itype_complement[p_itype] != 0) : ((s.itype_sets[(size_t)p_itype * W32 + (it >> 5)] >> (it & 31)) & 1);
           if (!allowed) continue;
         }
-        if (!plain && !requirements_phase(c, s, row, pt, s.ex_vals, s.ex_meta[e], NE, e, e, true, t)) continue;
+        if (!plain && !requirements_phase(s.ex_vals, s.ex_meta[e], NE, e, e, true, t)) continue;
         mine = (unsigned long long)e;
         break;  // this thread's remaining nodes have larger indices
       }
@@ -404,7 +428,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         ++seq;
         placed = true;
         __syncthreads();  // the commit is read by every thread in the next step
-        if (has_topo) topo_record_block(c, s, row, s.ex_vals, s.ex_meta[e], NE, e, e);
+        if (has_topo) topo_record_block(s.ex_vals, s.ex_meta[e], NE, e, e);
       } else {
         nodes_visited += NE;
       }
@@ -448,10 +472,10 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           if (!fast) {
             if (two_stage && !full_eval) {  // necessary condition only; the winner is checked in full
               const int n = H.node(a);
-              if (!topo_prefilter(c, s, pt, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n)) continue;
+              if (!topo_prefilter(s.nn_vals, s.nn_meta[n], MAXN, n, NE + n)) continue;
             } else {
               last_slow = a;
-              if (!evaluate_slow(c, s, row, pt, plain, H.node(a), fl, q, alloc_sorted, full_eval, ev)) {
+              if (!evaluate_slow(plain, H.node(a), fl, q, alloc_sorted, full_eval, ev.t, ev)) {
                 if (simple) H.rejected(a) = cls;
                 continue;
               }
@@ -472,15 +496,19 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         const bool winner = mine == wkey;
         if (winner) {  // post the candidate for the cooperative instance-type check
           const int a = best_a;
-          bool okw = true;
-          if (best_slow && last_slow != a) okw = evaluate_slow(c, s, row, pt, plain, H.node(a), H.flags(a), bq, alloc_sorted, full_eval, ev);
+          bool okw = true, in_shared = false;
+          if (best_slow && last_slow != a) {
+            // without the instance-type part the touched keys go straight into the CTA's shared Touched
+            in_shared = !full_eval;
+            okw = evaluate_slow(plain, H.node(a), H.flags(a), bq, alloc_sorted, full_eval, in_shared ? fresh_t : ev.t, ev);
+          }
           sh.win_a = a;
           sh.win_n = H.node(a);
           sh.win_fail = okw ? 0 : 1;
           sh.win_need = (okw && best_slow && ev.need_types) ? 1 : 0;
           sh.win_commit = (okw && best_slow && (ev.changed || p_itype != KSCHED_NONE)) ? 1 : 0;
           if (sh.win_need) {
-            fresh_t = ev.t;
+            if (!in_shared) fresh_t = ev.t;
             for (int r = 0; r < KSCHED_MAX_RES; ++r) sh.q[r] = r < R ? ev.q[r] : 0;
             sh.qp = ev.qp;
           }
@@ -502,7 +530,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         if (coop) {
           // TypeCtx of the winner: requirement part by thread 0, one Fits rank per resource by the first lanes of warp 1
           const int rbase = blockDim.x >= 64 ? 32 : 0;
-          if (tid == 0) build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, s.nn_vals, s.nn_meta[wn], MAXN, wn, false, alloc_sorted, fresh_x, rbase == 0);
+          if (tid == 0) build_type_ctx(fresh_t, sh.q, sh.qp, s.nn_vals, s.nn_meta[wn], MAXN, wn, false, alloc_sorted, fresh_x, rbase == 0);
           if (rbase && tid >= rbase && tid < rbase + R) {
             const int r = tid - rbase;
             fresh_x.rank[r] = ((sh.qp >> r) & 1) ? fit_rank(alloc_sorted, c.n_types, r, sh.q[r]) : 0;
@@ -573,12 +601,12 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
             unsigned short fb;
             bool new_front = true;
             if (coop) {
-              commit_reqs(s, n, ev.t);
-              if (opts_changed) compute_front(c, s.nn_opts, MAXN, n, nb1, nb2, &fb);
+              commit_reqs(n, fresh_t);
+              if (opts_changed) compute_front(s.nn_opts, MAXN, n, nb1, nb2, &fb);
               else new_front = false;  // same option set, same Pareto front
             } else {
               uint64_t meta;
-              commit_slow(c, s, row, n, ev, nb1, nb2, &fb, &meta);
+              commit_slow(n, ev, nb1, nb2, &fb, &meta);
             }
             if (new_front) {
 #pragma unroll
@@ -605,8 +633,10 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         ++seq;
         placed = true;
         __syncthreads();
+        GK_T(22)
         if (sh.placed_closed) --n_active;
-        if (has_topo) topo_record_block(c, s, row, s.nn_vals, s.nn_meta[wn], MAXN, wn, NE + wn);  // Topology.Record, one relation per thread
+        if (has_topo) topo_record_block(s.nn_vals, s.nn_meta[wn], MAXN, wn, NE + wn);  // Topology.Record, one relation per thread
+        GK_T(23)
         break;
       }
     } else if (!placed) {
@@ -638,7 +668,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
           else {
             bool ok = (p_tol >> tm.taintset) & 1;
             fresh_t.n = 0;
-            if (ok && !plain) ok = requirements_phase(c, s, row, pt, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, NE + n, false, fresh_t);
+            if (ok && !plain) ok = requirements_phase(tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, NE + n, false, fresh_t);
             if (ok) {
               sh.qp = tm.daemon_res_present | p_res;
               for (int r = 0; r < KSCHED_MAX_RES; ++r) sh.q[r] = r < R ? tm.daemon_requests[r] + (((p_res >> r) & 1) ? row.requests[r] : 0) : 0;
@@ -683,7 +713,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
                   }
                 }
                 if (path == kPathDynamic)
-                  build_type_ctx(c, s, row, fresh_t, sh.q, sh.qp, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, true, alloc_sorted, fresh_x);
+                  build_type_ctx(fresh_t, sh.q, sh.qp, tm.reqs.values, tm.reqs.meta & 0xFFFFFFFFull, 1, 0, true, alloc_sorted, fresh_x);
               }
             } else if (memo) {
               s.fc_state[fc] = 2;
@@ -760,7 +790,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
               for (int r = 0; r < kHotRes; ++r) { sh.bound[r] = s.fd_bound[(size_t)fd_slot * kHotRes + r]; sh.bound2[r] = s.fd_bound2[(size_t)fd_slot * kHotRes + r]; }
               sh.front_bits = s.fd_dom[fd_slot];
             } else {
-              compute_front(c, s.nn_opts, MAXN, n, sh.bound, sh.bound2, &sh.front_bits);
+              compute_front(s.nn_opts, MAXN, n, sh.bound, sh.bound2, &sh.front_bits);
               if (front_memo) {
                 for (int r = 0; r < kHotRes; ++r) { s.fc_bound[fc * kHotRes + r] = sh.bound[r]; s.fc_bound2[fc * kHotRes + r] = sh.bound2[r]; }
                 s.fc_dom[fc] = (uint8_t)sh.front_bits;
@@ -820,7 +850,7 @@ __device__ __noinline__ void generic_step(const K2Params& p, const StepCtx& X, c
         ++tick;
         ++seq;
         __syncthreads();
-        if (has_topo) topo_record_block(c, s, row, s.nn_vals, s.nn_meta[n], MAXN, n, NE + n);  // Topology.Record, one relation per thread
+        if (has_topo) topo_record_block(s.nn_vals, s.nn_meta[n], MAXN, n, NE + n);  // Topology.Record, one relation per thread
         ++n_new;
         if (!sh.placed_closed) ++n_active;
         placed = true;
@@ -877,11 +907,13 @@ __device__ __forceinline__ bool simple_pod_regs(const PodRegs& r) {
   return r.topo_begin == r.topo_end && r.hpc == 0 && r.hpe == 0 && (r.res >> kHotRes) == 0;
 }
 
-__device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, const uint32_t* tmpl_taintset, WarpIO* io) {
-  const PackState& s = p.st;
+__device__ __noinline__ void warp_resident_loop(WarpIO* io) {
+  KS_K2
+  HotSmem* hs = reinterpret_cast<HotSmem*>(dyn_smem);
+  const uint32_t* tmpl_taintset = g_tmpl_taintset;
   const int lane = threadIdx.x & 31;
   const int NE = s.n_existing, MAXN = s.max_new;
-  const int RH = p.cat.n_res < kHotRes ? p.cat.n_res : kHotRes;
+  const int RH = c.n_res < kHotRes ? c.n_res : kHotRes;
   const int qcap = s.n_pods + 1;
   int qi = io->qi, head = io->head, qlen = io->qlen, tick = io->tick, seq = io->seq;
   long long add_calls = io->add_calls;
@@ -983,34 +1015,29 @@ __device__ __noinline__ void warp_resident_loop(const K2Params& p, HotSmem* hs, 
 #define PK_T(i)
 #endif
 
-__global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_constant__ K2Params p) {
+__global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
 #ifdef KSCHED_PROFILE_PACK
   long long pk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long pk_last = clock64();
 #endif
-  const DevCatalog& c = p.cat;
-  const PackState& s = p.st;
+  KS_K2
   const int tid = threadIdx.x;
   const int NE = s.n_existing, MAXN = s.max_new;
   const int R = c.n_res, RH = R < kHotRes ? R : kHotRes;
 
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
   HotSmem* hs = reinterpret_cast<HotSmem*>(dyn_smem);
   int64_t* sm_alloc = reinterpret_cast<int64_t*>(dyn_smem + sizeof(HotSmem));
-  const Hot H{hs, s.ov_key, s.ov_q, s.ov_bound, s.ov_bound2, s.ov_node, s.ov_flags, s.ov_absorbed, s.ov_rejected, MAXN};
+  const Hot H = make_hot(s);
   if (s.alloc_in_smem)
     for (int i = tid; i < R * c.n_types; i += blockDim.x) sm_alloc[i] = c.alloc_sorted[i];
 
-  __shared__ PodTopo pt;
-  __shared__ Touched fresh_t;
-  __shared__ TypeCtx fresh_x;
-  __shared__ unsigned long long red[2][32];
-  __shared__ StepShared sh;
-  __shared__ uint32_t tmpl_taintset[KSCHED_MAX_TEMPLATES];
+  PodTopo& pt = g_pt;
+  unsigned long long (*red)[32] = g_red;
+  StepShared& sh = g_sh;
+  uint32_t* tmpl_taintset = g_tmpl_taintset;
   __shared__ WarpIO wio;
   if (tid < c.n_templates) tmpl_taintset[tid] = c.templates[tid].taintset;
   if (tid == 0) pt.n = 0;
-  const StepCtx X{&pt, &fresh_t, &fresh_x, red, &sh, tmpl_taintset, H, s.alloc_in_smem ? sm_alloc : c.alloc_sorted};
 
   int head = 0, qlen = s.n_pods;
   const int qcap = s.n_pods + 1;
@@ -1019,7 +1046,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
   long long nodes_visited = 0, add_calls = 0;
   int fatal = 0;
   bool pt_nonempty = false;
-  uint32_t pt_class = KSCHED_NONE;
+  uint32_t pt_class = KSCHED_NONE, row_class = KSCHED_NONE;
 
   for (int i = tid; i < s.n_pods; i += blockDim.x) {
     s.queue[i] = s.order[i];
@@ -1044,7 +1071,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
       __syncthreads();
       if (tid == 0) { wio.qi = qi; wio.head = head; wio.qlen = qlen; wio.tick = tick; wio.seq = seq; wio.n_active = n_active; wio.add_calls = add_calls; }
       __syncthreads();
-      if (tid < 32) warp_resident_loop(p, hs, tmpl_taintset, &wio);
+      if (tid < 32) warp_resident_loop(&wio);
       __syncthreads();
       qi = wio.qi; head = wio.head; qlen = wio.qlen; tick = wio.tick; seq = wio.seq; n_active = wio.n_active; add_calls = wio.add_calls;
       if (qlen == 0) break;
@@ -1147,10 +1174,10 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel(const __grid_cons
 #ifdef KSCHED_PROFILE_PACK
       if (tid == 0) s.counters[8 + 9] += 1;
 #endif
-      LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited, pt_class};
-      generic_step(p, X, cur, first_pass, fpos_first, L);
+      LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited, pt_class, row_class};
+      generic_step(cur, first_pass, fpos_first, L);
       head = L.head; qlen = L.qlen; n_new = L.n_new; n_active = L.n_active; tick = L.tick; seq = L.seq; parity = L.parity; fatal = L.fatal;
-      epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited; pt_class = L.pt_class;
+      epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited; pt_class = L.pt_class; row_class = L.row_class;
       if (fatal) break;
       PK_T(5)
     }
