@@ -89,6 +89,9 @@ def lib():
     L.kh_result_digest.argtypes = [C.c_void_p]
     L.kh_result_to_json.restype = C.c_longlong
     L.kh_result_to_json.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+    L.kh_result_to_json_brief.restype = C.c_longlong
+    L.kh_result_to_json_brief.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+    L.kh_problem_pod_summary.argtypes = [C.c_void_p, C.c_void_p]
     L.kh_set_device.argtypes = [C.c_int]
     L.kh_set_count_visited.argtypes = [C.c_int]
     L.kh_handle.restype = C.c_void_p
@@ -158,6 +161,13 @@ class Problem:
     def synth(cls, config, n_pods, n_types, seed=42, n_nodes=0):
         """BASELINE.json configurations C1..C5."""
         return cls(lib().kh_problem_synth(config, n_pods, n_types, seed, n_nodes))
+
+    def pod_summary(self):
+        """[n_pods][6] int64: cpu milli, memory milli, app label id, self anti-affinity on hostname, zone spread skew, hostname spread skew"""
+        n = self.counts()["pods"]
+        out = np.zeros((max(n, 1), 6), dtype=np.int64)
+        lib().kh_problem_pod_summary(self.ptr, out.ctypes.data_as(C.c_void_p))
+        return out[:n]
 
     def counts(self):
         out = (C.c_longlong * 6)()
@@ -231,10 +241,12 @@ class Result:
     def digest(self):
         return lib().kh_result_digest(self.ptr)
 
-    def to_dict(self):
-        need = lib().kh_result_to_json(self.ptr, None, 0)
+    def to_dict(self, brief=False):
+        """brief: per-node instance-type lists replaced by their length (full-size problems)"""
+        fn = lib().kh_result_to_json_brief if brief else lib().kh_result_to_json
+        need = fn(self.ptr, None, 0)
         buf = C.create_string_buffer(need)
-        lib().kh_result_to_json(self.ptr, buf, need)
+        fn(self.ptr, buf, need)
         return json.loads(buf.value.decode())
 
 

@@ -86,8 +86,46 @@ unsigned long long kh_result_digest(const Result* r) {
   for (auto& e : r->existing_pods) h = fnv(h, e.data(), e.size() * 4);
   return h;
 }
+// Per pod, the facts an independent checker of placements needs (tests): [cpu milli, memory milli, id of the "app"
+// label (-1 without), required hostname anti-affinity on its own app (0/1), max skew of a DoNotSchedule zone spread (0 =
+// none), max skew of a DoNotSchedule hostname spread (0 = none)].
+void kh_problem_pod_summary(const Problem* p, long long* out) {
+  std::map<std::string, long long> app_id;
+  for (size_t i = 0; i < p->pods.size(); ++i) {
+    const Pod& pd = p->pods[i];
+    long long* o = out + i * 6;
+    long long cpu = 0, mem = 0;
+    for (auto& c : pd.containers) {
+      auto a = c.requests.find("cpu"); if (a != c.requests.end()) cpu += a->second;
+      auto b = c.requests.find("memory"); if (b != c.requests.end()) mem += b->second;
+    }
+    o[0] = cpu; o[1] = mem;
+    auto app = pd.labels.find("app");
+    o[2] = -1;
+    if (app != pd.labels.end()) {
+      auto it = app_id.find(app->second);
+      if (it == app_id.end()) it = app_id.emplace(app->second, (long long)app_id.size()).first;
+      o[2] = it->second;
+    }
+    o[3] = 0; o[4] = 0; o[5] = 0;
+    for (auto& t : pd.pod_anti_affinity_required)
+      if (t.topology_key == "kubernetes.io/hostname" && app != pd.labels.end() && !t.selector.is_nil && t.selector.match_labels.count("app") &&
+          t.selector.match_labels.at("app") == app->second) o[3] = 1;
+    for (auto& t : pd.topology_spread) {
+      if (t.schedule_anyway) continue;
+      if (t.topology_key == "topology.kubernetes.io/zone") o[4] = t.max_skew;
+      if (t.topology_key == "kubernetes.io/hostname") o[5] = t.max_skew;
+    }
+  }
+}
+
 // Canonical JSON dump (small problems). Returns the required size; writes only if it fits.
-long long kh_result_to_json(const Result* r, char* buf, long long cap) {
+static long long result_json(const Result* r, char* buf, long long cap, bool brief);
+long long kh_result_to_json(const Result* r, char* buf, long long cap) { return result_json(r, buf, cap, false); }
+// the same without the per-node instance-type lists ("nOptions" instead): full-size problems
+long long kh_result_to_json_brief(const Result* r, char* buf, long long cap) { return result_json(r, buf, cap, true); }
+}
+static long long result_json(const Result* r, char* buf, long long cap, bool brief) {
   std::ostringstream o;
   o << "{\"error\":";
   json_str(o, r->error);
@@ -106,9 +144,13 @@ long long kh_result_to_json(const Result* r, char* buf, long long cap) {
     auto& nn = r->new_nodes[n];
     o << (n ? "," : "") << "{\"provisioner\":" << nn.provisioner << ",\"pods\":[";
     for (size_t i = 0; i < nn.pods.size(); ++i) o << (i ? "," : "") << nn.pods[i];
-    o << "],\"options\":[";
-    for (size_t i = 0; i < nn.instance_type_options.size(); ++i) o << (i ? "," : "") << nn.instance_type_options[i];
-    o << "],\"requests\":{";
+    if (brief) {
+      o << "],\"nOptions\":" << nn.instance_type_options.size() << ",\"requests\":{";
+    } else {
+      o << "],\"options\":[";
+      for (size_t i = 0; i < nn.instance_type_options.size(); ++i) o << (i ? "," : "") << nn.instance_type_options[i];
+      o << "],\"requests\":{";
+    }
     bool first = true;
     for (auto& kv : nn.requests) { o << (first ? "" : ","); json_str(o, kv.first); o << ":" << kv.second; first = false; }
     o << "},\"requirements\":{";
@@ -121,4 +163,4 @@ long long kh_result_to_json(const Result* r, char* buf, long long cap) {
   if ((long long)s.size() + 1 <= cap) std::memcpy(buf, s.c_str(), s.size() + 1);
   return (long long)s.size() + 1;
 }
-}
+
