@@ -285,6 +285,7 @@ def main():
 
     # ---- the same kernel on a workload large enough not to be launch-bound: C4's shape (100k pods x 1k types, 38.4 MB)
     k1_big = None
+    c4_line = None
     if rank == 0 and not args.no_cpu_baseline:
         big = pkg.Problem.synth(4, 100_000, 1000, 42, 0)
         rb = pkg.ResidentSolve(big)
@@ -295,24 +296,26 @@ def main():
         k1_big = {"kernel": "feasibility_kernel", "workload": "C4 shape: 100k pod rows x 1 provisioner x 1000 instance types", "bound": "hbm",
                   "achieved": bbytes / (bavg * 1e-6) / 1e9, "peak": peak, "unit": "GB/s", "frac": bbytes / (bavg * 1e-6) / 1e9 / peak,
                   "algorithmic_bytes": int(bbytes), "us_per_launch": bavg, "us_min": tb[0], "traffic": ncu_traffic("feasibility_kernel_c4")}
-        # ... and the whole Solve on that configuration (BASELINE.json's target shape), resident, L2 flushed: 1 warm-up + 2 runs
-        rb.set_count_visited(False)
-        rb.load()
-        rb.run(flush_l2=True)
-        c4_ph = {"sort_us": 0.0, "feasibility_us": 0.0, "pack_us": 0.0, "total_us": 0.0}
-        c4_runs = 2
-        for _ in range(c4_runs):
+        if world == 1:  # a sharded handle would wait for the other ranks' allreduce
+            # ... and the whole Solve on that configuration (BASELINE.json's target shape), resident, L2 flushed: 1 warm-up + 2 runs
+            rb.set_count_visited(False)
+            rb.load()
             rb.run(flush_l2=True)
-            t4 = rb.timings()
-            for k in c4_ph:
-                c4_ph[k] += t4[k]
-        r4 = rb.download()
-        s4 = int((r4.assign >= 0).sum())
-        c4_line = {"workload": CONFIGS[4]["name"], "pods": 100_000, "instance_types": 1000, "scheduled": s4, "new_nodes": int(r4.num_new_nodes),
-                   "value": s4 * c4_runs / (c4_ph["total_us"] * 1e-6), "unit": "pods/s", "ms_per_step": c4_ph["total_us"] / c4_runs / 1000,
-                   "phases_ms_per_step": {k[:-3]: v / c4_runs / 1000 for k, v in c4_ph.items()}, "steps": c4_runs, "warmup": 1,
-                   "note": "secondary measurement on one GPU; parity for this shape is covered by tests/test_gpu_fullsize.py"}
-        del rb, big, r4
+            c4_ph = {"sort_us": 0.0, "feasibility_us": 0.0, "pack_us": 0.0, "total_us": 0.0}
+            c4_runs = 2
+            for _ in range(c4_runs):
+                rb.run(flush_l2=True)
+                t4 = rb.timings()
+                for k in c4_ph:
+                    c4_ph[k] += t4[k]
+            r4 = rb.download()
+            s4 = int((r4.assign >= 0).sum())
+            c4_line = {"workload": CONFIGS[4]["name"], "pods": 100_000, "instance_types": 1000, "scheduled": s4, "new_nodes": int(r4.num_new_nodes),
+                       "value": s4 * c4_runs / (c4_ph["total_us"] * 1e-6), "unit": "pods/s", "ms_per_step": c4_ph["total_us"] / c4_runs / 1000,
+                       "phases_ms_per_step": {k[:-3]: v / c4_runs / 1000 for k, v in c4_ph.items()}, "steps": c4_runs, "warmup": 1,
+                       "note": "secondary measurement on one GPU; parity for this shape is covered by tests/test_gpu_fullsize.py"}
+            del r4
+        del rb, big
         rs.load()  # make the benchmarked problem resident again
 
     line = {
@@ -338,6 +341,7 @@ def main():
     }
     if k1_big:
         line["roofline_feasibility_c4"] = k1_big
+    if c4_line:
         line["config_c4"] = c4_line
     if rank == 0 and world > 1 and not args.no_cpu_baseline:
         # parity of the sharded path (K1 column shards + allreduce, pack replicated) against the oracle on the same inputs

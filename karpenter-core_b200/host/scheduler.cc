@@ -13,6 +13,7 @@
 #include <memory>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "encoder.h"
@@ -427,6 +428,50 @@ int kh_consolidate(const Problem* P, int* out4, int* options, int options_cap, i
   } catch (const std::exception& e) {
     return fail(error_code(e), e.what());
   }
+}
+
+// Two handles on one device, one host thread each, solving different problems at the same time. The pack kernel's
+// parameter block is one __constant__ object per device, so concurrent handles only stay correct through the device-side
+// ordering in run_pack(); this entry point lets the GPU tests prove it. Returns 0 when every repetition of each problem
+// reproduced that problem's first result bit for bit, a negative ksched error otherwise, or 1 on a mismatch.
+extern "C" int kh_selftest_two_handles(const Problem* A, const Problem* B, int iters) {
+  int rc = ensure_handle();
+  if (rc != KSCHED_OK) return rc;
+  const Problem* probs[2] = {A, B};
+  int status[2] = {0, 0};
+  std::thread workers[2];
+  for (int w = 0; w < 2; ++w) {
+    workers[w] = std::thread([&, w]() {
+      try {
+        ksched_handle* h = nullptr;
+        if (ksched_create(g_device, &h) != KSCHED_OK) { status[w] = KSCHED_ERR_CUDA; return; }
+        auto E = khost::encode(*probs[w], {});
+        E->problem.count_nodes_visited = 0;
+        std::vector<int32_t> first;
+        for (int it = 0; it < iters && status[w] == 0; ++it) {
+          ResultBuffers R;
+          int r2 = ksched_load_catalog(h, &E->catalog);
+          if (r2 == KSCHED_OK) { R.prepare(*E, false); r2 = ksched_solve(h, &E->problem, &R.r); }
+          if (r2 != KSCHED_OK) { status[w] = r2; break; }
+          std::vector<int32_t> sig(R.assign.begin(), R.assign.end());
+          sig.push_back(R.r.n_new_nodes);
+          for (int n = 0; n < R.r.n_new_nodes; ++n)
+            for (int k = 0; k < E->type_words; ++k) {
+              const uint64_t b = R.types[(size_t)n * E->type_words + k];
+              sig.push_back((int32_t)b);
+              sig.push_back((int32_t)(b >> 32));
+            }
+          if (it == 0) first = sig;
+          else if (sig != first) status[w] = 1;
+        }
+        ksched_destroy(h);
+      } catch (const std::exception& e) {
+        status[w] = error_code(e);
+      }
+    });
+  }
+  for (auto& t : workers) t.join();
+  return status[0] ? status[0] : status[1];
 }
 
 // ---- host-side mask algebra exposed for the CPU golden-vector tests (same code the kernels run)

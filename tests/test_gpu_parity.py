@@ -131,3 +131,13 @@ def test_feasibility_matrix_matches_fresh_node_options(pkg, oracle):
             any_col = any(int(x) for x in feas[p_i].ravel())
             assert (int(best[p_i]) != 2 ** 64 - 1) == any_col
     assert checked > 1500
+
+
+def test_two_handles_on_one_device_solve_concurrently(pkg, oracle):
+    """The pack kernel's parameters live in one __constant__ block per device: two handles driven by two host threads must
+    still each reproduce their own result (device-side ordering in run_pack)."""
+    a = pkg.Problem.synth(4, 1500, 1000, 5, 0)
+    b = pkg.Problem.synth(3, 2000, 1000, 6, 0)
+    assert pkg.lib().kh_selftest_two_handles(a.ptr, b.ptr, 6) == 0
+    # and the singleton handle still agrees with the oracle afterwards
+    _compare(pkg, oracle, a, [])
