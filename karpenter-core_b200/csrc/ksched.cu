@@ -175,9 +175,17 @@ struct K1Params {
   int n_valrows, n_offrows;
 };
 
+// Parameters in constant memory and the CTA's catalog view (table pointers redirected to the staged shared-memory
+// copies) in shared memory: the out-of-line row evaluation reads both with immediate addresses instead of through
+// references to a kernel parameter / a stack copy (see g_k2 below for what that costs).
+__constant__ K1Params g_k1;
+__shared__ DevCatalog g_k1cat;
+
 // One row's feasibility against every (template, column): the rarely taken path of feasibility_kernel (rows that differ
 // from their predecessor), kept out of line so that the batched streaming loop stays small.
-__device__ __noinline__ unsigned long long k1_compute_row(const DevCatalog& c, const K1Params& p, int j, uint64_t word, uint32_t* cache, bool cacheable) {
+__device__ __noinline__ unsigned long long k1_compute_row(int j, uint64_t word, uint32_t* cache, bool cacheable) {
+  const DevCatalog& c = g_k1cat;
+  const K1Params& p = g_k1;
   const int lane = threadIdx.x & 31;
   const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
   const int wpl = (W32 + 31) >> 5;
@@ -250,13 +258,14 @@ __device__ __noinline__ unsigned long long k1_compute_row(const DevCatalog& c, c
           if (s) s &= key_typeset_word(c, kk, a, ng, w);
         }
         if (s) s &= offer_word(c, (uint32_t)zallowed, (uint32_t)callowed, zc_unconstrained, w);
-        uint32_t rm = res_mask;
-        while (rm) {
+        uint32_t rm = res_mask, fit = 0xFFFFFFFFu;
+        while (rm) {  // the loads do not depend on each other (nor on s): one memory round trip for all resources
           int r = __ffs(rm) - 1;
           rm &= rm - 1;
           int rk = __shfl_sync(0xffffffffu, rank, r);
-          if (s) s &= c.fitset[((size_t)r * (T + 1) + rk) * W32 + w];
+          if (w < W32) fit &= c.fitset[((size_t)r * (T + 1) + rk) * W32 + w];
         }
+        s &= fit;
         if (s && itype_req != KSCHED_NONE) s &= p.itype_sets[(size_t)itype_req * W32 + w];
         if (mine) out[w] = s;
         if (cacheable) cache[v * wpl + wi] = s;
@@ -288,11 +297,12 @@ struct K1Params;
 // bitsets (valset / fitset / member / offset) stay in global memory and are read one coalesced word per lane.
 // Each warp owns a CONTIGUOUS chunk of the FFD-ordered pod-row matrix: consecutive rows are very often identical in
 // every field that matters to feasibility (same deployment), and then the previous result is written out again.
-__global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel(K1Params p) {
+__global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel() {
   extern __shared__ __align__(16) unsigned char k1_smem[];
 #ifdef KSCHED_PROFILE_K1
   long long t_start = clock64(), t_stage = 0, t_compute = 0, n_compute = 0;
 #endif
+  const K1Params& p = g_k1;
   DevCatalog c = p.cat;
   const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
   {
@@ -306,7 +316,16 @@ __global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel(K1Params p) 
     // staging costs about one memory round trip instead of one per table.
     auto stage4 = [&](void* dst, const void* src, int n_words) {
       const uint32_t* g = reinterpret_cast<const uint32_t*>(src);
-      for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
+      int done = 0;
+      if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {  // 16-byte copies for the aligned bulk (4x fewer requests)
+        const int n16 = n_words >> 2;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+          const unsigned d = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(dst) + 4 * i);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g + 4 * i));
+        }
+        done = n16 << 2;
+      }
+      for (int i = done + threadIdx.x; i < n_words; i += blockDim.x) {
         const unsigned d = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(dst) + i);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g + i));
       }
@@ -337,6 +356,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel(K1Params p) 
     if (p.alloc_in_smem) c.alloc_sorted = s_alloc;
     c.valrow = s_valrow;
     c.offrow = s_offrow;
+    if (threadIdx.x == 0) g_k1cat = c;
   }
   __syncthreads();
 #ifdef KSCHED_PROFILE_K1
@@ -363,6 +383,27 @@ __global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel(K1Params p) 
   for (int jb = j0; jb < j1; jb += kBatch) {
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) wbuf[b] = jb + b < j1 ? __ldg(p.rows + (size_t)(jb + b) * KSCHED_ROW_WORDS + lane) : 0;
+    if (have_prev && cacheable) {
+      // the usual case: the whole batch repeats the cached row (same deployment) -> one vote, then nothing but stores
+      uint64_t diff = 0;
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) diff |= jb + b < j1 ? ((wbuf[b] ^ prev_word) & cmp_mask) : 0;
+      if (__all_sync(0xffffffffu, diff == 0)) {
+        const int nb = min(kBatch, j1 - jb);
+        const size_t row_stride = (size_t)V * W32;
+        for (int v = 0; v < V; ++v)
+          for (int wi = 0; wi < wpl; ++wi) {
+            const int w = wi * 32 + lane;
+            if (w < W32 && w >= p.word_begin && w < p.word_end) {
+              const uint32_t val = cache[v * wpl + wi];
+              uint32_t* dst = p.F + ((size_t)jb * V + v) * W32 + w;
+              for (int b = 0; b < nb; ++b, dst += row_stride) *dst = val;
+            }
+          }
+        if (lane < nb) p.best[jb + lane] = best_prev;
+        continue;
+      }
+    }
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
     const int j = jb + b;
@@ -383,7 +424,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel(K1Params p) 
 #ifdef KSCHED_PROFILE_K1
     long long tc0 = clock64();
 #endif
-    const unsigned long long best = k1_compute_row(c, p, j, word, cache, cacheable);
+    const unsigned long long best = k1_compute_row(j, word, cache, cacheable);
 #ifdef KSCHED_PROFILE_K1
     t_compute += clock64() - tc0; ++n_compute;
 #endif
@@ -1041,6 +1082,7 @@ struct DevBuf {
 }  // namespace
 
 struct ksched_handle {
+  K1Params k1_host;  // staging copies of the kernels' constant-memory parameters (must outlive the async copies)
   K2Params k2_host;  // staging copy of the pack kernel's constant-memory parameters (must outlive the async copy)
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -1558,6 +1600,9 @@ static void fill_k1(ksched_handle* h, K1Params& k1) {
   }
 }
 
+static std::mutex g_k1_mu;
+static cudaEvent_t g_k1_done[64] = {};
+
 static int run_feasibility(ksched_handle* h) {
   if (h->n_pods == 0) return KSCHED_OK;
   K1Params k1;
@@ -1583,7 +1628,17 @@ static int run_feasibility(ksched_handle* h) {
   CUDA_TRY(h, cudaMemsetAsync(h->d_k1dbg.ptr, 0, 8 * sizeof(long long), h->stream));
   k1.dbg = h->d_k1dbg.ptr;
 #endif
-  feasibility_kernel<<<blocks, kK1Threads, smem, h->stream>>>(k1);
+  {
+    std::lock_guard<std::mutex> lock(g_k1_mu);  // one __constant__ parameter block per device: see run_pack
+    if (h->device < 0 || h->device >= 64) { h->err = "device ordinal out of range"; return KSCHED_ERR_INVALID; }
+    cudaEvent_t& done = g_k1_done[h->device];
+    if (!done) CUDA_TRY(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, done, 0));
+    h->k1_host = k1;
+    CUDA_TRY(h, cudaMemcpyToSymbolAsync(g_k1, &h->k1_host, sizeof(K1Params), 0, cudaMemcpyHostToDevice, h->stream));
+    feasibility_kernel<<<blocks, kK1Threads, smem, h->stream>>>();
+    CUDA_TRY(h, cudaEventRecord(done, h->stream));
+  }
 #ifdef KSCHED_PROFILE_K1
   {
     long long dbg[8];
