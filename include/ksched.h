@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KSCHED_ABI_VERSION 1
+#define KSCHED_ABI_VERSION 2
 #define KSCHED_MAX_KEYS 16
 #define KSCHED_MAX_RES 8
 #define KSCHED_MAX_TEMPLATES 16
@@ -128,6 +128,11 @@ typedef struct ksched_catalog {
   const int64_t* type_capacity;    /* [n_types][KSCHED_MAX_RES] Capacity (limits bookkeeping, scheduler.go:273-309) */
   const ksched_template* templates; /* [n_templates], weight order (v1alpha5/provisioner.go:132) */
   const ksched_bounds* template_bounds; /* [n_templates] or NULL */
+  /* Launch choice (the step after the path: fake/cloudprovider.go:74-84 orders the surviving options by their cheapest
+     compatible offering, cloudprovider/types.go:128-145 picks that offering). [n_types][64], slot = ct*16 + zone:
+     (rank of the offering's price among all distinct prices of the catalog) << 16 | position in the type's Offerings
+     list << 8 | slot, for AVAILABLE offerings; ~0 elsewhere. NULL: ksched_result.launch is not filled. */
+  const uint64_t* offering_keys;
 } ksched_catalog;
 
 /* Existing (real / in-flight) node: NewExistingNode, existingnode.go:41-75. */
@@ -201,6 +206,15 @@ typedef struct ksched_new_node {
   ksched_reqset reqs; /* final requirements on the mask keys (hostname removed, node.go:111-115) */
 } ksched_new_node;
 
+/* What the cloud provider would launch for a new node: the option whose cheapest compatible AVAILABLE offering is
+   cheapest (ties: provider input order), and that offering (ties: Offerings list order). */
+typedef struct ksched_launch_choice {
+  int32_t type_column;    /* column (price order) of the chosen instance type, -1 if the node has no option */
+  int32_t offering_slot;  /* ct*16 + zone */
+  uint32_t price_rank;    /* rank of the offering's price (see ksched_catalog.offering_keys) */
+  uint32_t offering_index; /* position of that offering in the instance type's Offerings list */
+} ksched_launch_choice;
+
 typedef struct ksched_result {
   int32_t* assign;       /* [n_pods] -1 | existing slot | n_existing + new node index (creation order) */
   int32_t* relax_level;  /* [n_pods] successful Relax calls */
@@ -214,6 +228,7 @@ typedef struct ksched_result {
   int32_t n_unscheduled;
   int64_t nodes_visited; /* candidate nodes examined, reference scan order (SURVEY.md 8d K2 bytes) */
   int64_t add_calls;     /* queue pops = Scheduler.add calls */
+  ksched_launch_choice* launch; /* [max_new_nodes] or NULL (needs ksched_catalog.offering_keys) */
 } ksched_result;
 
 typedef struct ksched_timings {

@@ -29,6 +29,7 @@
 
 #include "ksched.h"
 #include "reqmask.cuh"
+#include "launch.cuh"
 
 using ksched::KeyMeta;
 using ksched::Req;
@@ -76,6 +77,8 @@ struct DevCatalog {
   const int64_t* alloc_rt;           // [n_res][n_types] allocatable, resource-major
   const uint32_t* domset;            // [n_types][W32] types whose allocatable vector (first 4 resources) is dominated by the row's type
   int zone_key, ct_key;
+  const uint64_t* offer_keys;        // [n_types][64] launch-choice keys (ksched_catalog.offering_keys) or nullptr
+  const uint32_t* input_index;       // [n_types] provider input order of the column
 };
 
 __device__ __forceinline__ KeyMeta key_meta(const DevCatalog& c, int k) {
@@ -1051,6 +1054,57 @@ __device__ __forceinline__ void topo_record_block(const uint64_t* vals, uint64_t
 
 namespace {
 
+// Launch choice per finished new node (launch.cuh): one warp per node, lanes over the words of its final option set.
+__global__ void launch_choice_kernel(DevCatalog c, const long long* counters, const uint64_t* nn_vals, const uint64_t* nn_meta,
+                                     const uint32_t* nn_opts, int max_new, ksched_launch_choice* out) {
+  const int n_new = (int)counters[0];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = warp; n < n_new; n += nwarps) {
+    // zones / capacity types the node's requirements admit (Offerings.Requirements, types.go:120-126)
+    uint32_t zmask = 0xFFFF, cmask = 0xF;
+    const uint64_t meta = nn_meta[n];
+    if (c.zone_key >= 0) {
+      const Req z = load_soa(nn_vals, meta, max_new, n, c.zone_key);
+      if (z.present) zmask = (uint32_t)ksched::req_allowed(z, c.keys[c.zone_key].dict_mask, key_meta(c, c.zone_key));
+    }
+    if (c.ct_key >= 0) {
+      const Req ct = load_soa(nn_vals, meta, max_new, n, c.ct_key);
+      if (ct.present) cmask = (uint32_t)ksched::req_allowed(ct, c.keys[c.ct_key].dict_mask, key_meta(c, c.ct_key));
+    }
+    unsigned long long best = ~0ull, best_off = ksched::kNoOffering;
+    int best_col = -1;
+    for (int w = lane; w < c.W32; w += 32) {
+      uint32_t m = nn_opts[(size_t)w * max_new + n];
+      while (m) {
+        const int t = w * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t ok = ksched::offering_min_key(c.offer_keys + (size_t)t * 64, zmask, cmask);
+        if (ok == ksched::kNoOffering) continue;
+        const unsigned long long key = ksched::option_key(ok, c.input_index[t]);
+        if (key < best) { best = key; best_off = ok; best_col = t; }
+      }
+    }
+    const unsigned long long wbest = warp_min_u64(best);
+    const unsigned owner = __ballot_sync(0xffffffffu, best == wbest && best != ~0ull);  // keys are unique per option
+    if (owner) {
+      const int src = __ffs(owner) - 1;
+      best_col = __shfl_sync(0xffffffffu, best_col, src);
+      best_off = __shfl_sync(0xffffffffu, best_off, src);
+    } else {
+      best_col = -1;
+    }
+    if (lane == 0) {
+      ksched_launch_choice o;
+      o.type_column = best_col;
+      o.offering_slot = best_col >= 0 ? (int32_t)(best_off & 0xFF) : -1;
+      o.price_rank = best_col >= 0 ? (uint32_t)(best_off >> 16) : 0;
+      o.offering_index = best_col >= 0 ? (uint32_t)((best_off >> 8) & 0xFF) : 0;
+      out[n] = o;
+    }
+  }
+}
+
 // L2 flush helper: write a buffer larger than L2 between timed iterations
 __global__ void flush_kernel(uint32_t* buf, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1097,7 +1151,9 @@ struct ksched_handle {
   DevBuf<ksched_type_row> d_types;
   DevBuf<float> d_price32;
   DevBuf<int16_t> d_valrow, d_offrow;
-  DevBuf<uint32_t> d_valset, d_absent, d_negempty, d_offset, d_anyoffer, d_member, d_fitset, d_domset;
+  DevBuf<uint32_t> d_valset, d_absent, d_negempty, d_offset, d_anyoffer, d_member, d_fitset, d_domset, d_input_index;
+  DevBuf<uint64_t> d_offer_keys;
+  DevBuf<ksched_launch_choice> d_launch;
   std::vector<ksched_template> h_templates;
   int n_valrows = 1, n_offrows = 1;
   // problem
@@ -1344,6 +1400,17 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   c.offrow = h->d_offrow.ptr; c.offset = h->d_offset.ptr; c.anyoffer = h->d_anyoffer.ptr; c.member = h->d_member.ptr;
   c.alloc_sorted = h->d_alloc_sorted.ptr; c.fitset = h->d_fitset.ptr;
   c.perm_desc = h->d_perm_desc.ptr; c.alloc_rt = h->d_alloc_rt.ptr; c.domset = h->d_domset.ptr;
+  c.offer_keys = nullptr;
+  c.input_index = nullptr;
+  if (cat->offering_keys && T > 0) {
+    std::vector<uint32_t> input_index(T);
+    for (int t = 0; t < T; ++t) input_index[t] = cat->types[t].input_index;
+    CUDA_TRY(h, upload(h, h->d_offer_keys, cat->offering_keys, (size_t)T * 64));
+    CUDA_TRY(h, upload_vec(h, h->d_input_index, input_index));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // input_index is a stack vector
+    c.offer_keys = h->d_offer_keys.ptr;
+    c.input_index = h->d_input_index.ptr;
+  }
   c.zone_key = zone_key; c.ct_key = ct_key;
   h->have_catalog = true;
   h->uploaded = false;
@@ -1827,6 +1894,7 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
   const int n_new = (int)counters[0];
   h->tm.d2h_bytes = (int64_t)sizeof counters + (int64_t)P * 4 * ((res->assign != nullptr) + (res->relax_level != nullptr) + (res->place_seq != nullptr)) +
                     (int64_t)n_new * (1 + 4 + 4 + 8 + 64 + 128 + (int64_t)W32 * 4) + (res->existing_reqs ? (int64_t)NE * 136 : 0) +
+                    (res->launch ? (int64_t)n_new * (int64_t)sizeof(ksched_launch_choice) : 0) +
                     (res->feasibility ? (int64_t)P * V * W32 * 4 + (int64_t)P * 4 : 0) + (res->best_column ? (int64_t)P * 12 : 0);
   res->n_new_nodes = n_new;
   res->n_unscheduled = (int)counters[1];
@@ -1862,6 +1930,14 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
       uint32_t* dst = reinterpret_cast<uint32_t*>(res->new_node_types + (size_t)n * W64);
       for (int w = 0; w < W32; ++w) dst[w] = opts[(size_t)w * n_new + n];
     }
+  }
+  if (res->launch && n_new > 0) {
+    if (!h->cat.offer_keys) { h->err = "ksched_result.launch needs ksched_catalog.offering_keys"; return KSCHED_ERR_INVALID; }
+    CUDA_TRY(h, h->d_launch.ensure((size_t)n_new));
+    launch_choice_kernel<<<148, 256, 0, h->stream>>>(h->cat, h->d_counters.ptr, h->d_nn_vals.ptr, h->d_nn_meta.ptr, h->d_nn_opts.ptr, MAXN,
+                                                     h->d_launch.ptr);
+    CUDA_TRY(h, cudaMemcpyAsync(res->launch, h->d_launch.ptr, (size_t)n_new * sizeof(ksched_launch_choice), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   }
   if (res->existing_reqs && NE > 0) {
     std::vector<uint64_t> vals((size_t)16 * NE), meta(NE);

@@ -395,6 +395,7 @@ struct Group {
 std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candidates) {
   auto enc = std::make_unique<Encoded>();
   Encoded& E = *enc;
+  E.problem_ref = &P;
   Builder B(P, E);
 
   // ------------------------------------------------------------------ who takes part
@@ -517,6 +518,13 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   for (auto& s : specs) note_pod_vals(s.pod);
   for (auto& d : daemons) note_pod_vals(d);
   for (auto& it : P.instance_types) note_vals(it.requirements);
+  // offerings name zones / capacity types too (a node without a requirement on the key admits all of them)
+  for (auto& it : P.instance_types)
+    for (auto& o : it.offerings) {
+      int kz = B.key_of(kZone), kc = B.key_of(kCapacityType);
+      if (kz >= 0) vals[kz].insert(o.zone);
+      if (kc >= 0) vals[kc].insert(o.capacity_type);
+    }
   for (auto& pr : P.provisioners) {
     note_vals(pr.requirements);
     Labels l = pr.labels;
@@ -578,6 +586,14 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     std::stable_sort(E.type_input_index.begin(), E.type_input_index.end(), [&](int a, int b) { return min_price[a] < min_price[b]; });
     E.types.resize(NT);
     E.type_capacity.assign((size_t)NT * KSCHED_MAX_RES, 0);
+    // launch-choice table: exact price order through ranks of the distinct (double) prices
+    {
+      std::set<double> prices;
+      for (auto& it : P.instance_types)
+        for (auto& o : it.offerings) if (o.available) prices.insert(o.price);
+      E.price_by_rank.assign(prices.begin(), prices.end());
+      E.offering_keys.assign((size_t)NT * 64, ~0ull);
+    }
     for (int c = 0; c < NT; ++c) {
       const InstanceType& it = P.instance_types[E.type_input_index[c]];
       if (B.type_col.count(it.name)) unsupported("duplicate instance type name " + it.name);
@@ -606,13 +622,20 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
       for (auto& kv : alloc) { auto o = overhead.find(kv.first); if (o != overhead.end()) kv.second -= o->second; }
       row.res_present = B.fill_resources(alloc, row.allocatable);
       B.fill_resources(it.capacity, &E.type_capacity[(size_t)c * KSCHED_MAX_RES]);
-      for (auto& o : it.offerings) {
+      for (size_t oi = 0; oi < it.offerings.size(); ++oi) {
+        const Offering& o = it.offerings[oi];
         if (!o.available) continue;
         int z = 0, ct = 0;
         if (zone_key >= 0) { auto f = B.value_id[zone_key].find(o.zone); if (f == B.value_id[zone_key].end()) continue; z = f->second; }
         if (ct_key >= 0) { auto f = B.value_id[ct_key].find(o.capacity_type); if (f == B.value_id[ct_key].end()) continue; ct = f->second; }
         if (z >= 16 || ct >= 4) unsupported("more than 16 zones or 4 capacity types");
         row.offerings |= 1ull << (ct * 16 + z);
+        // (price rank, Offerings list position, slot): the smallest key of a slot wins when several offerings share it
+        if (oi > 255) unsupported("instance type " + it.name + " has more than 256 offerings");
+        const uint64_t rank = (uint64_t)(std::lower_bound(E.price_by_rank.begin(), E.price_by_rank.end(), o.price) - E.price_by_rank.begin());
+        const uint64_t key = (rank << 16) | ((uint64_t)oi << 8) | (uint64_t)(ct * 16 + z);
+        uint64_t& cell = E.offering_keys[(size_t)c * 64 + ct * 16 + z];
+        if (key < cell) cell = key;
       }
       row.min_price = min_price[E.type_input_index[c]];
       row.input_index = (uint32_t)E.type_input_index[c];
@@ -1084,6 +1107,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   cat.type_capacity = E.type_capacity.data();
   cat.templates = E.templates.data();
   cat.template_bounds = E.any_template_bounds ? E.template_bounds.data() : nullptr;
+  cat.offering_keys = E.offering_keys.data();
   ksched_problem& pr = E.problem;
   pr.n_pods = (int)NP; pr.n_classes = NC; pr.n_existing = NE; pr.n_groups = NG;
   pr.classes = E.classes.data();

@@ -24,12 +24,15 @@ struct Encoded {
   std::vector<int> template_provisioner;              // template v -> Problem.provisioners index
   std::vector<int> type_input_index;                  // column -> Problem.instance_types index
   int type_words = 0;
+  const kmodel::Problem* problem_ref = nullptr;       // the problem this encoding was made from (must outlive it)
 
   // ---- backing storage of the flat structures
   std::vector<ksched_keyinfo> keys;
   std::vector<int64_t> key_int_values;
   std::vector<ksched_type_row> types;
   std::vector<int64_t> type_capacity;
+  std::vector<uint64_t> offering_keys;                // [n_types][64] launch-choice table (ksched_catalog.offering_keys)
+  std::vector<double> price_by_rank;                  // distinct available offering prices, ascending (rank -> price)
   std::vector<ksched_template> templates;
   std::vector<ksched_bounds> template_bounds;
   std::vector<ksched_pod_row> classes;

@@ -163,6 +163,10 @@ struct NewNodeResult {
   ResourceList requests;
   // final requirement per key (hostname removed), rendered "key Op [v1 v2]" style for comparison
   std::map<std::string, std::string> requirements;
+  // what the cloud provider would launch (fake/cloudprovider.go:74-84, cloudprovider/types.go:128-145); -1 = not computed
+  int32_t launch_type = -1;                   // index into Problem.instance_types
+  std::string launch_capacity_type, launch_zone;
+  double launch_price = 0;
 };
 
 struct Result {

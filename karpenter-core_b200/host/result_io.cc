@@ -1,5 +1,6 @@
 // Result accessors shared by every producer of a kmodel::Result (the GPU scheduler facade and,
 // in tests, the oracle): flat copies for numpy, a canonical JSON dump, and a 64-bit digest.
+#include <cstdio>
 #include <cstring>
 #include <sstream>
 
@@ -156,7 +157,17 @@ static long long result_json(const Result* r, char* buf, long long cap, bool bri
     o << "},\"requirements\":{";
     first = true;
     for (auto& kv : nn.requirements) { o << (first ? "" : ","); json_str(o, kv.first); o << ":"; json_str(o, kv.second); first = false; }
-    o << "}}";
+    o << "}";
+    if (nn.launch_type >= 0) {
+      o << ",\"launch\":{\"type\":" << nn.launch_type << ",\"capacityType\":";
+      json_str(o, nn.launch_capacity_type);
+      o << ",\"zone\":";
+      json_str(o, nn.launch_zone);
+      char pb[64];
+      std::snprintf(pb, sizeof pb, "%.17g", nn.launch_price);
+      o << ",\"price\":" << pb << "}";
+    }
+    o << "}";
   }
   o << "],\"nodesVisited\":" << r->nodes_visited << ",\"addCalls\":" << r->add_calls << "}";
   std::string s = o.str();

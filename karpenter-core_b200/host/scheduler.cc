@@ -20,6 +20,7 @@
 #include "ksched.h"
 #include "model.h"
 #include "reqmask.cuh"
+#include "launch.cuh"
 
 using namespace kmodel;
 using khost::Encoded;
@@ -49,6 +50,7 @@ struct ResultBuffers {
   std::vector<ksched_reqset> existing_reqs;
   std::vector<uint64_t> feasibility;
   std::vector<uint64_t> best;
+  std::vector<ksched_launch_choice> launch;
   ksched_result r{};
   void prepare(const Encoded& E, bool want_feasibility) {
     const size_t P = E.pods.size(), N = (size_t)std::max(1, E.problem.max_new_nodes);
@@ -65,6 +67,8 @@ struct ResultBuffers {
     r.new_nodes = nodes.data();
     r.new_node_types = types.data();
     r.existing_reqs = existing_reqs.data();
+    launch.assign(nodes.size(), ksched_launch_choice{-1, -1, 0, 0});
+    r.launch = launch.data();
     if (want_feasibility) {
       feasibility.assign(P * E.templates.size() * E.type_words, 0);
       best.assign(P, 0);
@@ -106,6 +110,18 @@ void decode(const Encoded& E, const ResultBuffers& B, Result& out) {
       if ((src.requests_present >> r) & 1) dst.requests[E.res_names[r]] = src.requests[r];
     for (size_t k = 0; k < E.key_names.size(); ++k)
       if ((src.reqs.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1) dst.requirements[E.key_names[k]] = khost::render_requirement(E, src.reqs, (int)k);
+    // launch choice: column -> the provider's instance type, offering by its position in that type's Offerings list
+    if ((size_t)n < B.launch.size() && B.launch[n].type_column >= 0 && E.problem_ref) {
+      const ksched_launch_choice& lc = B.launch[n];
+      const int ti = E.type_input_index[(size_t)lc.type_column];
+      const kmodel::InstanceType& it = E.problem_ref->instance_types[(size_t)ti];
+      dst.launch_type = ti;
+      if (lc.offering_index < it.offerings.size()) {
+        dst.launch_capacity_type = it.offerings[lc.offering_index].capacity_type;
+        dst.launch_zone = it.offerings[lc.offering_index].zone;
+      }
+      if (lc.price_rank < E.price_by_rank.size()) dst.launch_price = E.price_by_rank[lc.price_rank];
+    }
   }
 }
 
@@ -472,6 +488,70 @@ extern "C" int kh_selftest_two_handles(const Problem* A, const Problem* B, int i
   }
   for (auto& t : workers) t.join();
   return status[0] ? status[0] : status[1];
+}
+
+// ---- launch-choice table + shared core (csrc/launch.cuh) checked on the CPU: for every new node of `ref` (a Result of
+// the same problem, e.g. the oracle's) recompute the launch choice from the ENCODED offering table exactly as the device
+// kernel does, and compare with the fields `ref` carries. Returns the number of nodes that differ, or a negative error.
+extern "C" int kh_launch_table_selfcheck(const Problem* P, const Result* ref) {
+  try {
+    auto E = khost::encode(*P, {});
+    int zone_key = -1, ct_key = -1;
+    for (size_t k = 0; k < E->key_names.size(); ++k) {
+      if (E->key_names[k] == "topology.kubernetes.io/zone") zone_key = (int)k;
+      if (E->key_names[k] == "karpenter.sh/capacity-type") ct_key = (int)k;
+    }
+    // admissible dictionary ids of a rendered requirement ("In [a b]", "NotIn [a]", "Exists", "DoesNotExist")
+    auto allowed = [&](int key, const std::map<std::string, std::string>& reqs, uint32_t all) -> uint32_t {
+      if (key < 0) return all;
+      auto it = reqs.find(E->key_names[(size_t)key]);
+      if (it == reqs.end()) return all;
+      const std::string& r = it->second;
+      std::set<std::string> vals;
+      size_t lb = r.find('['), rb = r.rfind(']');
+      if (lb != std::string::npos && rb != std::string::npos && rb > lb) {
+        std::string body = r.substr(lb + 1, rb - lb - 1), cur;
+        for (char ch : body) { if (ch == ' ') { if (!cur.empty()) vals.insert(cur); cur.clear(); } else cur.push_back(ch); }
+        if (!cur.empty()) vals.insert(cur);
+      }
+      const bool is_in = r.rfind("In", 0) == 0, is_notin = r.rfind("NotIn", 0) == 0, exists = r.rfind("Exists", 0) == 0;
+      uint32_t m = 0;
+      for (size_t b = 0; b < E->key_values[(size_t)key].size(); ++b) {
+        const bool has = vals.count(E->key_values[(size_t)key][b]) > 0;
+        if (exists || (is_in && has) || (is_notin && !has)) m |= 1u << b;
+      }
+      return m;
+    };
+    std::vector<int> col_of(P->instance_types.size(), -1);
+    for (size_t c = 0; c < E->type_input_index.size(); ++c) col_of[(size_t)E->type_input_index[c]] = (int)c;
+    int bad = 0;
+    for (auto& nn : ref->new_nodes) {
+      const uint32_t zmask = allowed(zone_key, nn.requirements, 0xFFFF), cmask = allowed(ct_key, nn.requirements, 0xF);
+      uint64_t best = ~0ull, best_off = ksched::kNoOffering;
+      int best_col = -1;
+      for (int ti : nn.instance_type_options) {
+        const int c = col_of[(size_t)ti];
+        const uint64_t ok = ksched::offering_min_key(&E->offering_keys[(size_t)c * 64], zmask, cmask);
+        if (ok == ksched::kNoOffering) continue;
+        const uint64_t key = ksched::option_key(ok, E->types[(size_t)c].input_index);
+        if (key < best) { best = key; best_off = ok; best_col = c; }
+      }
+      int type = -1;
+      std::string ct, zone;
+      double price = 0;
+      if (best_col >= 0) {
+        type = E->type_input_index[(size_t)best_col];
+        const auto& it = P->instance_types[(size_t)type];
+        const size_t oi = (size_t)((best_off >> 8) & 0xFF);
+        if (oi < it.offerings.size()) { ct = it.offerings[oi].capacity_type; zone = it.offerings[oi].zone; }
+        price = E->price_by_rank[(size_t)(best_off >> 16)];
+      }
+      if (type != nn.launch_type || ct != nn.launch_capacity_type || zone != nn.launch_zone || price != nn.launch_price) ++bad;
+    }
+    return bad;
+  } catch (const std::exception& e) {
+    return fail(error_code(e), e.what());
+  }
 }
 
 // ---- host-side mask algebra exposed for the CPU golden-vector tests (same code the kernels run)

@@ -524,6 +524,39 @@ struct IType {
   ResourceList allocatable;  // :87-89, precomputed (pure function of the type)
 };
 
+// What the cloud provider launches for a finished node (the step after Solve). Instance type: the options sorted by the
+// price of Offerings.Available().Requirements(reqs).Cheapest(), element 0 (cloudprovider/fake/cloudprovider.go:74-84;
+// sort.Slice taken as a stable sort over the provider's input order, canonical rule R4). Offering: that type's cheapest
+// compatible available offering, lo.MinBy = first minimum in list order (cloudprovider/types.go:120-145).
+static void launch_choice(const Requirements& reqs, const std::vector<const IType*>& options, NewNodeResult& out) {
+  auto compatible = [&](const Offering& o) {  // Offerings.Requirements, types.go:120-126
+    return (!reqs.Has("topology.kubernetes.io/zone") || reqs.Get("topology.kubernetes.io/zone").Has(o.zone)) &&
+           (!reqs.Has("karpenter.sh/capacity-type") || reqs.Get("karpenter.sh/capacity-type").Has(o.capacity_type));
+  };
+  auto cheapest = [&](const InstanceType& it) -> const Offering* {
+    const Offering* best = nullptr;
+    for (auto& o : it.offerings) {
+      if (!o.available || !compatible(o)) continue;
+      if (!best || o.price < best->price) best = &o;
+    }
+    return best;
+  };
+  std::vector<const IType*> ordered(options.begin(), options.end());
+  std::stable_sort(ordered.begin(), ordered.end(), [](const IType* a, const IType* b) { return a->index < b->index; });  // provider order
+  const IType* chosen = nullptr;
+  const Offering* chosen_of = nullptr;
+  for (auto* t : ordered) {
+    const Offering* of = cheapest(*t->it);
+    if (!of) continue;
+    if (!chosen || of->price < chosen_of->price) { chosen = t; chosen_of = of; }
+  }
+  if (!chosen) return;
+  out.launch_type = chosen->index;
+  out.launch_capacity_type = chosen_of->capacity_type;
+  out.launch_zone = chosen_of->zone;
+  out.launch_price = chosen_of->price;
+}
+
 // ---------------------------------------------------------------- machine template / nodes
 struct MachineTemplate {  // machinetemplate.go:32-62
   int provisioner;        // index in weight order
@@ -897,6 +930,7 @@ struct Scheduler {
       for (auto* t : nn.options) r.instance_type_options.push_back(t->index);
       r.requests = nn.requests;
       for (auto& kv : nn.req.m) r.requirements[kv.first] = kv.second.Canonical();
+      launch_choice(nn.req, nn.options, r);
       for (int pi : nn.pods) out.assign[pi] = (int32_t)(E + i);
       out.new_nodes.push_back(std::move(r));
     }

@@ -29,6 +29,7 @@ def test_gpu_equals_oracle_on_random_problem(pkg, oracle, seed):
         assert a["options"] == b["options"]
         assert a["requests"] == b["requests"]
         assert a["requirements"] == {k: v for k, v in b["requirements"].items() if k != "node.kubernetes.io/instance-type"}
+        assert a.get("launch") == b.get("launch") and a.get("launch") is not None  # launch choice (device kernel vs oracle)
     assert got.nodes_visited == want.nodes_visited
     fast = pkg.Scheduler(problem).solve(count_visited=False).to_dict()  # production setting: steady-state kernel paths
     assert fast["assign"] == w["assign"] and fast["relax"] == w["relax"] and fast["existing"] == w["existing"]

@@ -19,6 +19,7 @@ def both(pkg, oracle, prob_dict):
     for a, b in zip(g["newNodes"], w["newNodes"]):
         assert a["provisioner"] == b["provisioner"] and a["pods"] == b["pods"] and a["options"] == b["options"] and a["requests"] == b["requests"]
         assert a["requirements"] == {k: v for k, v in b["requirements"].items() if k != "node.kubernetes.io/instance-type"}
+        assert a.get("launch") == b.get("launch") and a.get("launch") is not None
     fast = pkg.Scheduler(problem).solve(count_visited=False).to_dict()  # production setting: steady-state kernel paths
     assert fast["assign"] == g["assign"] and fast["newNodes"] == g["newNodes"] and fast["existing"] == g["existing"]
     return g

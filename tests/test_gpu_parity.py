@@ -36,6 +36,7 @@ def _compare(pkg, oracle, problem, candidates=()):
         assert a["requests"] == b["requests"], i
         breq = {k: v for k, v in b["requirements"].items() if k != "node.kubernetes.io/instance-type"}
         assert a["requirements"] == breq, i
+        assert a.get("launch") == b.get("launch") and a.get("launch") is not None, i
     assert g["existing"] == w["existing"]
     assert got.nodes_visited == want.nodes_visited
     assert got.add_calls == want.add_calls
