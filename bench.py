@@ -329,7 +329,8 @@ def main():
                    "library_kernels_per_step": "3x cub::DeviceRadixSort::SortPairs (not counted in gpu_launches)"},
         "e2e": {"value": e2e_value, "unit": "pods/s", "h2d_bytes_per_step": int(tm_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(tm_e2e["d2h_bytes"]),
                 "ms_per_step": 1000 * e2e_s / args.steps, "path": "ksched_solve(handle, problem*, result*) with host buffers"},
-        "gpu_launches": 6 * args.steps,
+        # own kernels per resident Solve: sort_keys, 2x gather_u64, gather_rows, feasibility, pack, finalize_options
+        "gpu_launches": 7 * args.steps,
         "roofline": {"kernel": "pack_kernel", "bound": "hbm", "achieved": pack_gbs, "peak": peak, "unit": "GB/s", "frac": pack_gbs / peak,
                      "traffic": ncu_traffic("pack_kernel"), "peak_source": peak_src, "algorithmic_bytes": int(pack_bytes),
                      "us_per_launch": pack_avg_us, "note": "latency-bound sequential first-fit chain; bytes = nodes_visited*128 + P*256 (SURVEY 8d K2)"},

@@ -1,17 +1,21 @@
 // K2 — pack_kernel: Scheduler.add's sequential first-fit (scheduler.go:174-219) in one persistent CTA.
 //
-// Design (B200-first, latency-bound integer work):
-//  * one CTA of 1024 threads, one pod per iteration; candidate nodes are examined one per thread and the
-//    reference's scan order is recovered by a block-wide argmin over (pod count, stable tie-break);
-//  * the state every candidate check needs (order key, request vector, allocatable bound of the node's
-//    dominant instance type) lives in SHARED MEMORY for the first kActCap open nodes; everything colder
+// Design (B200-first, latency-bound integer work; DESIGN.md section 4 has the long form):
+//  * one CTA (128..512 threads), one pod per iteration, three speeds: a register-resident warp loop when at most 32
+//    nodes are open and the pod cannot change any requirement (warp_resident_loop), a block-wide fast path over the
+//    shared-memory window of open nodes, and the out-of-line generic step (existing nodes, requirement / topology
+//    evaluation, fresh nodes, relaxation);
+//  * candidate nodes are examined one per thread and the reference's scan order is recovered by an argmin over
+//    (pod count, stable tie-break) = the position under sort.Slice(newNodes, len(Pods)<) treated as a stable sort;
+//  * the state every candidate check needs (order key, request vector, Pareto front of the allocatable vectors of the
+//    node's surviving instance types) lives in SHARED MEMORY for the first kActCap open nodes; everything colder
 //    (requirement masks, instance-type bitsets, host ports) stays in global memory / L2;
-//  * the instance-type bitset of a node is filtered LAZILY by resources: Fits() is monotone in the request
-//    vector, so options_true = options_stored AND FIT(requests) and the AND is applied once, by
-//    finalize_options_kernel, after the pack loop. A node whose surviving options contain a type that is
-//    maximal in every resource ("dominant") is accept-tested with R integer compares;
-//  * the winning thread commits its own candidate — no re-evaluation by a leader thread;
-//  * fresh nodes of the same (pod class, template) reuse a cached option set (the K1 row).
+//  * the instance-type bitset of a node is filtered LAZILY by resources: Fits() is monotone in the request vector, so
+//    options_true = options_stored AND FIT(requests) and the AND is applied once, by finalize_options_kernel;
+//  * generic step: cheap per-candidate filter -> block argmin -> full evaluation of the winner only -> the whole CTA
+//    checks / narrows the winner's instance-type words (exclude + retry when it fails);
+//  * parameters come from __constant__ memory (g_k2), the per-CTA working set is file-scope __shared__: out-of-line
+//    functions reach both with immediate addresses.
 #pragma once
 
 namespace {
