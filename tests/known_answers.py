@@ -358,6 +358,71 @@ def schedule_anyway_spread_is_relaxed():
     return prob, check
 
 
+@case("topology_test.go:82-104")
+def zonal_spread_match_expressions():
+    sel = {"matchExpressions": [{"key": "test", "operator": "In", "values": ["test"]}]}
+    cons = [{"maxSkew": 1, "topologyKey": ZONE, "whenUnsatisfiable": "DoNotSchedule", "labelSelector": sel}]
+    prob = problem(pods(4, labels={"test": "test"}, topologySpreadConstraints=cons))
+    return prob, lambda res: _eq(fx.skew(prob, res, ZONE), [1, 1, 2])
+
+
+@case("topology_test.go:106-122")
+def zonal_spread_respects_provisioner_zones():
+    labels = {"test": "test"}
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": list(ZONES)}])
+    prob = problem(pods(4, labels=labels, topologySpreadConstraints=[fx.spread(ZONE, labels)]), provisioners=[pr])
+    return prob, lambda res: _eq(fx.skew(prob, res, ZONE), [1, 1, 2])
+
+
+@case("topology_test.go:492-506")
+def capacity_type_spread():
+    labels = {"test": "test"}
+    prob = problem(pods(4, labels=labels, topologySpreadConstraints=[fx.spread(CAPACITY_TYPE, labels)]))
+    return prob, lambda res: _eq(fx.skew(prob, res, CAPACITY_TYPE), [2, 2])
+
+
+@case("topology_test.go:508-524")
+def capacity_type_spread_respects_provisioner():
+    labels = {"test": "test"}
+    pr = provisioner(requirements=[{"key": CAPACITY_TYPE, "operator": "In", "values": ["spot", "on-demand"]}])
+    prob = problem(pods(4, labels=labels, topologySpreadConstraints=[fx.spread(CAPACITY_TYPE, labels)]), provisioners=[pr])
+    return prob, lambda res: _eq(fx.skew(prob, res, CAPACITY_TYPE), [2, 2])
+
+
+@case("topology_test.go:785-802")
+def zone_and_hostname_spread_first_batch():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels), fx.spread(HOSTNAME, labels, max_skew=3)]
+    prob = problem(pods(2, labels=labels, topologySpreadConstraints=cons))
+
+    def check(res):
+        assert fx.skew(prob, res, ZONE) == [1, 1]
+        assert max(fx.skew(prob, res, HOSTNAME)) <= 3
+    return prob, check
+
+
+@case("topology_test.go:785-823 (eleven pods in one batch)")
+def zone_and_hostname_spread_eleven_pods():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels), fx.spread(HOSTNAME, labels, max_skew=3)]
+    prob = problem(pods(11, labels=labels, topologySpreadConstraints=cons))
+
+    def check(res):
+        assert all(a >= 0 for a in res["assign"])
+        assert fx.skew(prob, res, ZONE) == [3, 4, 4]
+        assert max(fx.skew(prob, res, HOSTNAME)) <= 3
+    return prob, check
+
+
+@case("topology_test.go:1031-1055")
+def spread_options_limited_by_node_selector():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels)]
+    prob = problem(pods(5, labels=labels, topologySpreadConstraints=cons, nodeSelector={ZONE: "test-zone-1"}) +
+                   pods(10, labels=labels, topologySpreadConstraints=cons, nodeSelector={ZONE: "test-zone-2"}))
+    return prob, lambda res: _eq(fx.skew(prob, res, ZONE), [5, 10])
+
+
 # ------------------------------------------------------------------ pod affinity / anti-affinity (topology_test.go:1195-2207)
 @case("topology_test.go:1503-1530")
 def hostname_anti_affinity_splits_nodes():
@@ -409,6 +474,96 @@ def zonal_affinity_follows_target():
 
 
 # ------------------------------------------------------------------ existing / in-flight nodes (suite_test.go:1343-1893)
+@case("topology_test.go:1205-1237")
+def pod_affinity_hostname_with_spread_noise():
+    labels, aff = {"test": "test"}, {"security": "s2"}
+    noise = pods(10, labels=labels, topologySpreadConstraints=[fx.spread(HOSTNAME, labels)])
+    target = pod(labels=aff)
+    follower = pod(podAffinity={"required": [fx.affinity_term(HOSTNAME, aff)]})
+    prob = problem(noise + [target, follower])
+
+    def check(res):
+        assert scheduled(res, 10) and scheduled(res, 11)
+        assert res["assign"][10] == res["assign"][11]
+    return prob, check
+
+
+@case("topology_test.go:1445-1476")
+def preferred_pod_affinity_may_be_violated():
+    labels = {"test": "test"}
+    noise = pods(10, labels=labels, topologySpreadConstraints=[fx.spread(HOSTNAME, labels)])
+    follower = pod(podAffinity={"preferred": [{"weight": 50, "term": fx.affinity_term(HOSTNAME, {"security": "s2"})}]})
+    prob = problem(noise + [follower])
+    return prob, lambda res: _eq(scheduled(res, 10), True)
+
+
+@case("topology_test.go:1478-1509")
+def preferred_pod_anti_affinity_may_be_violated():
+    labels = {"test": "test"}
+    spreaders = pods(3, labels=labels, topologySpreadConstraints=[fx.spread(ZONE, labels)])
+    avoiders = pods(10, podAntiAffinity={"preferred": [{"weight": 50, "term": fx.affinity_term(ZONE, labels)}]})
+    prob = problem(spreaders + avoiders)
+    return prob, lambda res: _eq([scheduled(res, i) for i in range(3, 13)], [True] * 10)
+
+
+@case("topology_test.go:1533-1570")
+def zonal_anti_affinity_with_every_zone_taken():
+    aff = {"security": "s2"}
+    zoned = [pod({"cpu": "2"}, labels=aff, nodeSelector={ZONE: z}) for z in ZONES]
+    avoider = pod(podAntiAffinity={"required": [fx.affinity_term(ZONE, aff)]})
+    prob = problem(zoned + [avoider])
+
+    def check(res):
+        assert all(scheduled(res, i) for i in range(3))
+        assert not scheduled(res, 3)
+    return prob, check
+
+
+@case("topology_test.go:1879-1902")
+def zonal_self_anti_affinity_first_batch_schedules_one():
+    """late committal: the first pod's zone is undetermined, so it blocks all three zones for its siblings"""
+    aff = {"security": "s2"}
+    prob = problem(pods(3, labels=aff, podAntiAffinity={"required": [fx.affinity_term(ZONE, aff)]}))
+    return prob, lambda res: _eq(sum(1 for a in res["assign"] if a >= 0), 1)
+
+
+@case("topology_test.go:1924-1939")
+def affinity_to_a_non_existent_pod():
+    prob = problem(pods(10, podAffinity={"required": [fx.affinity_term(ZONE, {"security": "s2"})]}))
+    return prob, lambda res: _eq([a >= 0 for a in res["assign"]], [False] * 10)
+
+
+@case("topology_test.go:1941-1962")
+def zonal_affinity_unconstrained_target_first_batch():
+    aff = {"security": "s2"}
+    followers = pods(10, podAffinity={"required": [fx.affinity_term(ZONE, aff)]})
+    target = pod(labels=aff)
+    prob = problem(followers + [target])
+
+    def check(res):
+        assert scheduled(res, 10)
+        assert not any(scheduled(res, i) for i in range(10))
+    return prob, check
+
+
+@case("topology_test.go:2003-2035")
+def multiple_dependent_affinities():
+    db, web = {"type": "db", "spread": "spread"}, {"type": "web", "spread": "spread"}
+    cache, ui = {"type": "cache", "spread": "spread"}, {"type": "ui", "spread": "spread"}
+    prob = problem([pod(labels=db),
+                    pod(labels=web, podAffinity={"required": [fx.affinity_term(HOSTNAME, db)]}),
+                    pod(labels=cache, podAffinity={"required": [fx.affinity_term(HOSTNAME, web)]}),
+                    pod(labels=ui, podAffinity={"required": [fx.affinity_term(HOSTNAME, cache)]})])
+    return prob, lambda res: _eq([a >= 0 for a in res["assign"]], [True] * 4)
+
+
+@case("topology_test.go:2037-2052")
+def unsatisfiable_affinity_dependency_terminates():
+    db, web = {"type": "db", "spread": "spread"}, {"type": "web", "spread": "spread"}
+    prob = problem([pod(labels=db, podAffinity={"required": [fx.affinity_term(HOSTNAME, web)]})])
+    return prob, lambda res: _eq(scheduled(res, 0), False)
+
+
 @case("suite_test.go:1344-1358")
 def reuse_existing_node():
     node = fx.state_node("node-a")
