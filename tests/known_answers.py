@@ -290,6 +290,100 @@ def provisioner_cpu_limits():
     return prob, check
 
 
+# ------------------------------------------------------------------ node affinity: requirements x preferences (suite_test.go:231-346, 643-676)
+def _r(key, op, *values):
+    return {"key": key, "operator": op, "values": list(values)}
+
+
+def _node_aff(required=None, preferred=None, **kw):
+    na = {}
+    if required is not None:
+        na["required"] = [required]
+    if preferred is not None:
+        na["preferred"] = [{"weight": 1, "terms": preferred}]
+    return pod(nodeAffinity=na, **kw)
+
+
+def _zone_of(prob, res):
+    return fx.launch(prob, res["newNodes"][res["assign"][0] - len(res["existing"])])[2]
+
+
+@case("suite_test.go:231-308")
+def node_affinity_requirements_and_preferences_on_zone():
+    all3u = list(ZONES) + ["unknown"]
+    cases = [
+        (_node_aff([_r(ZONE, "In", "unknown")]), None),                                                     # :231 not scheduled
+        (_node_aff([_r(ZONE, "NotIn", "test-zone-1", "test-zone-2", "unknown")]), "test-zone-3"),             # :240
+        (_node_aff([_r(ZONE, "NotIn", *all3u)]), None),                                                      # :250 not scheduled
+        (_node_aff([_r(ZONE, "In", *all3u)], [_r(ZONE, "In", "test-zone-2", "unknown")]), "test-zone-2"),    # :260
+        (_node_aff([_r(ZONE, "In", *all3u)], [_r(ZONE, "In", "unknown")]), "any"),                          # :273 preference relaxed
+        (_node_aff([_r(ZONE, "In", *all3u)], [_r(ZONE, "NotIn", "test-zone-1", "test-zone-3")]), "test-zone-2"),  # :285
+        (_node_aff([_r(ZONE, "In", *all3u)], [_r(ZONE, "NotIn", *ZONES)]), "any"),                          # :298 preference relaxed
+    ]
+    probs = [problem([p]) for p, _ in cases]
+
+    def check(results):
+        for (p, want), prob, res in zip(cases, probs, results):
+            if want is None:
+                assert res["assign"] == [-1], want
+            else:
+                assert res["assign"][0] >= 0
+                if want != "any":
+                    assert _zone_of(prob, res) == want
+    return {"multi": probs}, check
+
+
+@case("suite_test.go:310-346")
+def node_selectors_preferences_and_requirements_combine():
+    p1 = _node_aff([_r(ZONE, "In", *ZONES)], [_r(ZONE, "In", *ZONES)], nodeSelector={ZONE: "test-zone-3"})
+    p2 = _node_aff([_r(ZONE, "In", "test-zone-1", "test-zone-3"), _r(INSTANCE_TYPE, "In", "default-instance-type", "arm-instance-type")],
+                   [_r(ZONE, "NotIn", "unknown"), _r(INSTANCE_TYPE, "NotIn", "unknown")],
+                   nodeSelector={ZONE: "test-zone-3", INSTANCE_TYPE: "arm-instance-type"})
+    probs = [problem([p1]), problem([p2])]
+
+    def check(results):
+        assert _zone_of(probs[0], results[0]) == "test-zone-3"
+        assert _zone_of(probs[1], results[1]) == "test-zone-3"
+        node = results[1]["newNodes"][results[1]["assign"][0]]
+        assert fx.launch(probs[1], node)[1] == "arm-instance-type"
+    return {"multi": probs}, check
+
+
+@case("suite_test.go:643-676")
+def conflicting_preferences_do_not_block_scheduling():
+    p1 = _node_aff([_r(ZONE, "In", "test-zone-3")], [_r(ZONE, "NotIn", "test-zone-3")])
+    p2 = _node_aff(None, [_r(ZONE, "In", "invalid"), _r(ZONE, "NotIn", "invalid")])
+    probs = [problem([p1]), problem([p2])]
+
+    def check(results):
+        assert _zone_of(probs[0], results[0]) == "test-zone-3"
+        assert results[1]["assign"][0] >= 0
+    return {"multi": probs}, check
+
+
+# ------------------------------------------------------------------ instance type compatibility (suite_test.go:727-819)
+@case("suite_test.go:727-759")
+def provisioner_arch_excludes_the_only_fitting_types():
+    pr = provisioner(requirements=[{"key": ARCH, "operator": "In", "values": ["amd64"]}])
+    ios = _node_aff([_r("kubernetes.io/os", "In", "ios")])          # only the arm type runs ios
+    big = pod({"cpu": "14"})                                           # only the arm type has 14 cpus
+    return each_alone([ios, big], [False, False], provisioners=[pr])
+
+
+@case("suite_test.go:760-819")
+def different_selectors_different_instances():
+    pr = provisioner(requirements=[{"key": ARCH, "operator": "In", "values": ["arm64", "amd64"]}])
+    by_os = problem([pod(nodeSelector={"kubernetes.io/os": "linux"}), pod(nodeSelector={"kubernetes.io/os": "windows"})], provisioners=[pr])
+    by_type = problem([pod(nodeSelector={"beta.kubernetes.io/instance-type": "small-instance-type"}),
+                       pod(nodeSelector={INSTANCE_TYPE: "default-instance-type"})], provisioners=[pr])
+    by_zone = problem([pod(nodeSelector={ZONE: "test-zone-1"}), pod(nodeSelector={ZONE: "test-zone-2"})], provisioners=[pr])
+
+    def check(results):
+        for res in results:
+            assert min(res["assign"]) >= 0 and len(set(res["assign"])) == 2
+    return {"multi": [by_os, by_type, by_zone]}, check
+
+
 # ------------------------------------------------------------------ topology spread (topology_test.go:65-490)
 @case("topology_test.go:66-80")
 def zonal_spread_four_pods():
@@ -597,6 +691,67 @@ def startup_taint_ignored_until_initialized():
     node = fx.state_node("node-a", taints=[taint], startupTaints=[taint], initialized=False)
     prob = problem([pod({"cpu": "10m"})], nodes=[node])
     return prob, lambda res: _eq(res["assign"], [0])
+
+
+@case("suite_test.go:1460-1497")
+def zonal_spread_continues_on_in_flight_nodes():
+    """second round of the Go test: three nodes already hold (1, 1, 2) matching pods; five more pods fill them to (3, 3, 3)"""
+    labels = {"foo": "bar"}
+    spread = [fx.spread(ZONE, labels)]
+
+    def bound(node, n):
+        return [pod(labels=labels, topologySpreadConstraints=spread, nodeName=node) for _ in range(n)]
+    nodes = [fx.state_node("node-1", zone="test-zone-1", pods_=bound("node-1", 1)),
+             fx.state_node("node-2", zone="test-zone-2", pods_=bound("node-2", 1)),
+             fx.state_node("node-3", zone="test-zone-3", pods_=bound("node-3", 2))]
+    prob = problem(pods(5, labels=labels, topologySpreadConstraints=spread), nodes=nodes)
+
+    def check(res):
+        assert res["newNodes"] == []  # the in-flight nodes can hold all five
+        counts = [1, 1, 2]
+        for a in res["assign"]:
+            assert 0 <= a < 3
+            counts[a] += 1
+        assert counts == [3, 3, 3]
+    return prob, check
+
+
+@case("suite_test.go:1498-1532")
+def hostname_spread_prefers_new_nodes_over_in_flight():
+    labels = {"foo": "bar"}
+    spread = [fx.spread(HOSTNAME, labels)]
+    nodes = [fx.state_node(f"node-{i}", pods_=[pod(labels=labels, topologySpreadConstraints=spread, nodeName=f"node-{i}")]) for i in range(4)]
+    prob = problem(pods(5, labels=labels, topologySpreadConstraints=spread), nodes=nodes)
+
+    def check(res):
+        assert min(res["assign"]) >= 4 and len(set(res["assign"])) == 5  # (1 x 9): every new pod on its own new node
+    return prob, check
+
+
+@case("suite_test.go:1660-1731")
+def bound_daemonset_pod_leaves_no_overhead_to_reserve():
+    """16-cpu node (15.9 allocatable) with the daemonset's pod already bound (1 cpu): a 14.9-cpu pod still fits on it"""
+    ds = pod({"cpu": "1", "memory": "1Gi"})
+    ds_bound = pod({"cpu": "1", "memory": "2Gi"}, nodeName="node-a", isDaemonSet=True)
+    node = fx.state_node("node-a", "arm-instance-type", allocatable={"cpu": "15900m", "memory": "131062Mi", "pods": "5"}, pods_=[ds_bound],
+                         labels={ARCH: "arm64"})
+    prob = problem([pod({"cpu": "14.9"})], nodes=[node], daemonSetPods=[ds])
+
+    def check(res):
+        assert res["assign"] == [0] and res["newNodes"] == []
+    return prob, check
+
+
+@case("suite_test.go:1824-1863")
+def in_flight_nodes_are_packed_before_new_ones():
+    medium = fx.instance_type("medium", {"cpu": "4.25", "pods": "4"})
+    node = fx.state_node("node-a", "medium", allocatable={"cpu": "4150m", "memory": "4086Mi", "pods": "4"}, pods_=[pod({"cpu": "1"}, nodeName="node-a")])
+    prob = problem(pods(5, requests={"cpu": "1"}), instance_types=[medium], nodes=[node])
+
+    def check(res):
+        assert sorted(res["assign"]).count(0) == 3  # three more fit next to the bound pod
+        assert len(res["newNodes"]) == 1 and len(res["newNodes"][0]["pods"]) == 2
+    return prob, check
 
 
 def _eq(a, b):
