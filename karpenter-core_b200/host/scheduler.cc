@@ -154,7 +154,10 @@ bool req_has(const Encoded& E, const ksched_reqset& rs, const std::string& key, 
   }
   return true;
 }
-double worst_launch_price(const Encoded& E, const InstanceType& it, const ksched_reqset& rs) {
+// spot_only: the caller has added `capacity-type In [spot]` to the node's requirements (consolidation.go:262-265). The
+// flag carries that restriction even when capacity-type is not one of the encoded mask keys (no pod or provisioner
+// mentions it), where the reqset cannot.
+double worst_launch_price(const Encoded& E, const InstanceType& it, const ksched_reqset& rs, bool spot_only = false) {
   auto worst = [&](const char* ct, double* out) {
     bool any = false;
     double mx = 0;
@@ -169,7 +172,7 @@ double worst_launch_price(const Encoded& E, const InstanceType& it, const ksched
   };
   double p;
   if (req_has(E, rs, "karpenter.sh/capacity-type", "spot") && worst("spot", &p)) return p;
-  if (req_has(E, rs, "karpenter.sh/capacity-type", "on-demand") && worst("on-demand", &p)) return p;
+  if (!spot_only && req_has(E, rs, "karpenter.sh/capacity-type", "on-demand") && worst("on-demand", &p)) return p;
   return std::numeric_limits<double>::max();
 }
 
@@ -357,7 +360,9 @@ Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int 
   bool all_spot = true;
   for (int i = 0; i < count; ++i) if (cands[i].ct != "spot") all_spot = false;
   if (all_spot && req_has(*E, reqs, "karpenter.sh/capacity-type", "spot")) return cmd;
+  bool spot_only = false;
   if (req_has(*E, reqs, "karpenter.sh/capacity-type", "spot") && req_has(*E, reqs, "karpenter.sh/capacity-type", "on-demand")) {
+    spot_only = true;
     // Requirements.Add(capacity-type In [spot]) (consolidation.go:262-265)
     for (size_t k = 0; k < E->key_names.size(); ++k) {
       if (E->key_names[k] != "karpenter.sh/capacity-type") continue;
@@ -388,7 +393,7 @@ Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int 
     if (existing_types.count(name) && by_type[name] < max_price) max_price = by_type[name];
   }
   std::vector<int> kept2;
-  for (int t : kept) if (worst_launch_price(*E, P->instance_types[t], reqs) < max_price) kept2.push_back(t);
+  for (int t : kept) if (worst_launch_price(*E, P->instance_types[t], reqs, spot_only) < max_price) kept2.push_back(t);
   if (kept2.empty()) return cmd;
   cmd.action = 2;
   cmd.options = kept2;

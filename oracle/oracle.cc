@@ -1000,7 +1000,7 @@ double worst_launch_price(const InstanceType& it, const std::map<std::string, st
 
 // The scheduler result keeps requirements only as canonical strings; for the price guard we need the
 // Requirements object of the single new node, so the simulation is re-run here with access to internals.
-void consolidate(const Problem& P, ConsolidationResult& out) {
+void consolidate(const Problem& P, ConsolidationResult& out, int only_count) {
   out = ConsolidationResult();
   try {
     std::vector<Candidate> cands;
@@ -1090,6 +1090,14 @@ void consolidate(const Problem& P, ConsolidationResult& out) {
       return cmd;
     };
 
+    if (only_count > 0) {  // one computeConsolidation over the `only_count` cheapest candidates (tests of the price guards)
+      if (only_count > (int)cands.size()) throw std::runtime_error("probe size out of range");
+      Cmd c = compute(only_count);
+      out.action = c.action;
+      out.nodes_removed = (c.action == 1 || c.action == 2) ? only_count : 0;
+      out.replacement_options = c.options;
+      return;
+    }
     // firstNNodeConsolidationOption multinodeconsolidation.go:74-114
     if (cands.size() < 2) return;
     int mn = 1, mx = (int)cands.size() - 1;

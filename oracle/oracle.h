@@ -27,6 +27,7 @@ struct ConsolidationResult {
   std::string error;
 };
 // MultiNodeConsolidation.firstNNodeConsolidationOption (multinodeconsolidation.go:74-114)
-void consolidate(const kmodel::Problem& P, ConsolidationResult& out);
+// only_count > 0: a single computeConsolidation over that many candidates instead of the search
+void consolidate(const kmodel::Problem& P, ConsolidationResult& out, int only_count = 0);
 
 }  // namespace oracle

@@ -71,6 +71,16 @@ int oracle_solve(const kmodel::Problem* P, const int* candidates, int ncand, kmo
 }
 
 // consolidate: returns action; fills scalars; options/probes copied up to caps
+// one probe: computeConsolidation over the `count` cheapest-to-disrupt candidates; returns the action, fills the options
+int oracle_consolidate_probe(const kmodel::Problem* P, int count, int* options, int options_cap, int* n_options, char* err, int err_cap) {
+  ConsolidationResult r;
+  consolidate(*P, r, count);
+  *n_options = (int)r.replacement_options.size();
+  for (int i = 0; i < *n_options && i < options_cap; ++i) options[i] = r.replacement_options[i];
+  put(r.error, err, err_cap);
+  return r.error.empty() ? r.action : -1;
+}
+
 int oracle_consolidate(const kmodel::Problem* P, int* nodes_removed, int* simulations, int* options, int options_cap,
                        int* n_options, int* probes, int* probe_actions, int probes_cap, int* n_probes, char* err, int err_cap) {
   ConsolidationResult r;

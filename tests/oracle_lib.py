@@ -20,6 +20,7 @@ class Oracle:
         lib.oracle_reqs_compatible.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         lib.oracle_normalize_key.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         lib.oracle_solve.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+        lib.oracle_consolidate_probe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]
         lib.oracle_consolidate.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                            C.POINTER(C.c_int), C.c_char_p, C.c_int]
@@ -58,6 +59,16 @@ class Oracle:
         arr = (C.c_int * max(1, len(candidates)))(*candidates)
         rc = self.lib.oracle_solve(problem.ptr, arr, len(candidates), result.ptr)
         return rc
+
+    def consolidate_probe(self, problem, count):
+        """computeConsolidation over the `count` cheapest candidates -> (action, options)"""
+        nopt = C.c_int()
+        opts = (C.c_int * 8192)()
+        err = C.create_string_buffer(1024)
+        action = self.lib.oracle_consolidate_probe(problem.ptr, int(count), opts, 8192, C.byref(nopt), err, 1024)
+        if action < 0:
+            raise RuntimeError(err.value.decode())
+        return action, list(opts[:nopt.value])
 
     def consolidate(self, problem):
         nr, sims, nopt, npr = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -142,3 +142,27 @@ def test_two_handles_on_one_device_solve_concurrently(pkg, oracle):
     assert pkg.lib().kh_selftest_two_handles(a.ptr, b.ptr, 6) == 0
     # and the singleton handle still agrees with the oracle afterwards
     _compare(pkg, oracle, a, [])
+
+
+from consolidation_answers import CASES as CONSOLIDATION_CASES
+
+
+@pytest.mark.parametrize("name,ref,build", CONSOLIDATION_CASES, ids=[c[0] for c in CONSOLIDATION_CASES])
+def test_consolidation_known_answers_match_oracle(pkg, oracle, name, ref, build):
+    """deprovisioning/suite_test.go cases: the product's probe / search must satisfy the same checks AND equal the oracle"""
+    prob, check = build()
+    problem = pkg.Problem.from_dict(prob)
+    mnc = pkg.MultiNodeConsolidation(problem)
+
+    def search():
+        out = mnc.first_n_node_consolidation_option()
+        want = oracle.consolidate(problem)
+        assert (out["action"], out["nodes_removed"], out["options"], out["probes"]) == (want["action"], want["nodes_removed"], want["options"], want["probes"])
+        return out
+
+    def probe(count):
+        got = mnc.probe(count)
+        assert got == oracle.consolidate_probe(problem, count)
+        return got
+
+    check(probe, search)
