@@ -153,3 +153,68 @@ def will_not_merge_two_nodes_into_one_of_the_same_type():
         assert out["action"] == 0 and out["nodes_removed"] == 0
         assert probe(1) == (1, [])  # deleting the node with the fewest pods alone is the valid single-node action
     return prob, check
+
+
+# ---- cases added after the round's GPU budget was spent: pinned on the oracle (CPU); the GPU parametrisation of
+# tests/test_gpu_parity.py takes CASES only, these join it once they have been run on a B200.
+CPU_ONLY_CASES = []
+
+
+def cpu_case(ref):
+    def deco(fn):
+        CPU_ONLY_CASES.append((fn.__name__, ref, fn))
+        return fn
+    return deco
+
+
+def _in_zone(its, zone, cheapest=True):
+    od = [it for it in on_demand_by_price(its) if it["offerings"][0]["zone"] == zone]
+    return od[0] if cheapest else od[-1]
+
+
+def _small_node(name, it, zone, pods_, cost):
+    of = it["offerings"][0]
+    n = fx.state_node(name, it["name"], zone=zone, capacity_type=of["capacityType"], allocatable={"cpu": "1", "memory": "64Gi", "pods": "100"}, pods_=pods_)
+    n["candidate"] = True
+    n["disruptionCost"] = cost
+    return n
+
+
+@cpu_case("deprovisioning/suite_test.go:1828-1934")
+def replacement_keeps_the_zonal_spread():
+    """three one-pod nodes in three zones, the zone-2 node is the most expensive: its replacement must stay in zone 2"""
+    its = assorted()
+    labels = {"app": "test-zonal-spread"}
+    spread = [fx.spread(ZONE, labels)]
+    types = [_in_zone(its, "test-zone-1"), _in_zone(its, "test-zone-2", cheapest=False), _in_zone(its, "test-zone-3")]
+    nodes = []
+    for i, (it, zone) in enumerate(zip(types, ZONES)):
+        bound = [fx.pod({"cpu": "1"}, labels=labels, topologySpreadConstraints=spread, nodeName=f"node-{i}")]
+        nodes.append(_small_node(f"node-{i}", it, zone, bound, 1.0 if i == 1 else 5.0 + i))  # the zone-2 node is the cheapest to disrupt
+    prob = fx.problem([], instance_types=its, nodes=nodes)
+
+    def check(probe, search):
+        action, options = probe(1)
+        assert action == 2 and options
+        assert all(its[i]["offerings"][0]["zone"] == "test-zone-2" for i in options)
+        assert all(price_of(its, i) < types[1]["offerings"][0]["price"] for i in options)
+        assert probe(2)[0] == 0  # two pods of the spread would need two new nodes in two zones: not a consolidation
+    return prob, check
+
+
+@cpu_case("deprovisioning/suite_test.go:1936-2029")
+def nothing_to_do_when_deletion_would_violate_anti_affinity():
+    its = assorted()
+    labels = {"app": "test"}
+    anti = {"required": [fx.affinity_term(fx.HOSTNAME, labels)]}
+    nodes = []
+    for i, zone in enumerate(ZONES):
+        bound = [fx.pod({"cpu": "1"}, labels=labels, podAntiAffinity=anti, nodeName=f"node-{i}")]
+        nodes.append(_small_node(f"node-{i}", _in_zone(its, zone), zone, bound, 1.0 + i))
+    prob = fx.problem([], instance_types=its, nodes=nodes)
+
+    def check(probe, search):
+        for count in (1, 2, 3):
+            assert probe(count)[0] == 0  # already the cheapest types; moving a pod onto a sibling's node violates the anti-affinity
+        assert search()["action"] == 0
+    return prob, check
