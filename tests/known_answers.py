@@ -756,3 +756,100 @@ def in_flight_nodes_are_packed_before_new_ones():
 
 def _eq(a, b):
     assert a == b, (a, b)
+
+
+# ================================================================== cases added after the round's GPU budget was spent
+# Pinned on the oracle (tests/test_oracle_known_answers.py runs CASES + CPU_ONLY_CASES); tests/test_gpu_known_answers.py takes
+# CASES only - these move up once they have been run on a B200.
+CPU_ONLY_CASES = []
+
+
+def cpu_case(ref):
+    def deco(fn):
+        CPU_ONLY_CASES.append((fn.__name__, ref, fn))
+        return fn
+    return deco
+
+
+def _launched_capacity(prob, res):
+    name = launched_type(prob, res, 0)
+    it = next(i for i in prob["instanceTypes"] if i["name"] == name)
+    return it["capacity"]["cpu"], it["capacity"]["memory"]
+
+
+# ------------------------------------------------------------------ daemonset overhead (provisioning/suite_test.go:360-530)
+@cpu_case("provisioning/suite_test.go:360-397")
+def daemonset_overhead_pushes_to_the_larger_type():
+    ds = pod({"cpu": "1", "memory": "1Gi"})
+    plain = problem([pod({"cpu": "1", "memory": "1Gi"})], daemonSetPods=[ds])
+    startup = problem([pod({"cpu": "1", "memory": "1Gi"})], daemonSetPods=[ds],
+                      provisioners=[provisioner(startupTaints=[{"key": "foo.com/taint", "effect": "NoSchedule"}])])
+
+    def check(results):
+        for prob, res in zip((plain, startup), results):
+            assert res["assign"] == [0]
+            assert _launched_capacity(prob, res) == ("4", "4Gi")  # 2 cpu would not hold pod + daemonset + kube-reserved
+    return {"multi": [plain, startup]}, check
+
+
+@cpu_case("provisioning/suite_test.go:398-418")
+def daemonset_overhead_too_large():
+    huge = pod({"cpu": "10000", "memory": "10000Gi"})
+    by_limits = pod(containers=[{"requests": {"cpu": "1"}, "limits": {"cpu": "10000", "memory": "10000Gi"}}])  # limits stand in for missing requests
+    probs = [problem([pod()], daemonSetPods=[huge]), problem([pod()], daemonSetPods=[by_limits])]
+    return {"multi": probs}, lambda results: _eq([r["assign"] for r in results], [[-1], [-1]])
+
+
+@cpu_case("provisioning/suite_test.go:475-530")
+def daemonsets_that_cannot_run_on_the_node_are_not_counted():
+    req = {"cpu": "1", "memory": "1Gi"}
+    tainted = provisioner(taints=[{"key": "foo", "value": "bar", "effect": "NoSchedule"}])
+    p_intolerant = problem([pod(req, tolerations=[{"operator": "Exists"}])], daemonSetPods=[pod(req)], provisioners=[tainted])
+    p_selector = problem([pod(req)], daemonSetPods=[pod(req, nodeSelector={"node": "invalid"})])
+    p_notin = problem([pod(req, nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-2"]}]]})],
+                      daemonSetPods=[pod(req, nodeAffinity={"required": [[{"key": "foo", "operator": "NotIn", "values": ["bar"]}]]})])
+
+    def check(results):
+        assert [r["assign"] for r in results] == [[0], [0], [0]]
+        assert _launched_capacity(p_intolerant, results[0]) == ("2", "2Gi")  # daemonset does not tolerate the provisioner's taint
+        assert _launched_capacity(p_selector, results[1]) == ("2", "2Gi")    # daemonset selects a label the node never has
+        assert _launched_capacity(p_notin, results[2]) == ("4", "4Gi")       # NotIn on an undefined key is compatible: counted
+    return {"multi": [p_intolerant, p_selector, p_notin]}, check
+
+
+# ------------------------------------------------------------------ relaxation order, provisioner selection (provisioning/suite_test.go:1105-1183)
+@cpu_case("provisioning/suite_test.go:1105-1124")
+def prefer_no_schedule_is_tolerated_after_the_preferences_are_relaxed():
+    prefs = [{"weight": 1, "terms": [{"key": ZONE, "operator": "In", "values": ["invalid"]}]},
+             {"weight": 1, "terms": [{"key": INSTANCE_TYPE, "operator": "In", "values": ["invalid"]}]}]
+    pr = provisioner(taints=[{"key": "foo", "value": "bar", "effect": "PreferNoSchedule"}])
+    prob = problem([pod(nodeAffinity={"preferred": prefs})], provisioners=[pr])
+
+    def check(res):
+        assert res["assign"] == [0]
+        assert res["relax"] == [3]  # two preferred terms dropped, then the PreferNoSchedule toleration (preferences.go:36-55)
+    return prob, check
+
+
+@cpu_case("provisioning/suite_test.go:1129-1183")
+def provisioner_selection_by_name_label_taint_and_weight():
+    pn = fx.PROVISIONER_NAME
+    by_name = problem([pod(nodeSelector={pn: "target"})], provisioners=[provisioner("target"), provisioner("other")])
+    by_label = problem([pod(nodeSelector={"foo": "bar"})], provisioners=[provisioner("labelled", labels={"foo": "bar"}), provisioner("other")])
+    avoid_pns = problem([pod()], provisioners=[provisioner("tainted", taints=[{"key": "foo", "value": "bar", "effect": "PreferNoSchedule"}]),
+                                               provisioner("clean")])
+    weights = [provisioner("w0"), provisioner("w20", weight=20), provisioner("w100", weight=100)]
+    heaviest = problem(pods(3), provisioners=weights)
+    explicit = problem([pod(nodeSelector={pn: "w0"})], provisioners=weights)
+
+    def name_of(res, i=0):
+        node = res["newNodes"][res["assign"][i] - len(res["existing"])]
+        return node["requirements"][pn]
+
+    def check(results):
+        assert name_of(results[0]) == "In [target]"
+        assert name_of(results[1]) == "In [labelled]"
+        assert name_of(results[2]) == "In [clean]"
+        assert [name_of(results[3], i) for i in range(3)] == ["In [w100]"] * 3
+        assert name_of(results[4]) == "In [w0]"
+    return {"multi": [by_name, by_label, avoid_pns, heaviest, explicit]}, check

@@ -1,7 +1,7 @@
 """CPU: the oracle must reproduce the reference's own known answers — this is what pins it."""
 import pytest
 
-from known_answers import CASES
+from known_answers import CASES, CPU_ONLY_CASES
 
 
 def run_oracle(pkg, oracle, prob_dict):
@@ -11,7 +11,10 @@ def run_oracle(pkg, oracle, prob_dict):
     return res.to_dict()
 
 
-@pytest.mark.parametrize("name,ref,build", CASES, ids=[c[0] for c in CASES])
+ALL = CASES + CPU_ONLY_CASES
+
+
+@pytest.mark.parametrize("name,ref,build", ALL, ids=[c[0] for c in ALL])
 def test_oracle_known_answer(pkg, oracle, name, ref, build):
     prob, check = build()
     if "multi" in prob:
