@@ -853,3 +853,78 @@ def provisioner_selection_by_name_label_taint_and_weight():
         assert [name_of(results[3], i) for i in range(3)] == ["In [w100]"] * 3
         assert name_of(results[4]) == "In [w0]"
     return {"multi": [by_name, by_label, avoid_pns, heaviest, explicit]}, check
+
+
+# ------------------------------------------------------------------ zonal spread against pods that already run (topology_test.go:163-339)
+def _small_node_with(name, zone, bound):
+    """a 2-cpu node (1.9 allocatable) already holding `bound` pods: a further 1.1-cpu pod does not fit, as in the Go tests"""
+    return fx.state_node(name, "small-instance-type", zone=zone, allocatable={"cpu": "1900m", "memory": "2038Mi", "pods": "5"}, pods_=bound)
+
+
+def _zone_counts(prob, res, base):
+    counts = dict(base)
+    ne = len(res["existing"])
+    for a in res["assign"]:
+        if a < 0:
+            continue
+        assert a >= ne  # the existing nodes are full
+        z = res["newNodes"][a - ne]["requirements"][ZONE]
+        assert z.startswith("In [") and " " not in z[4:-1], z
+        counts[z[4:-1]] = counts.get(z[4:-1], 0) + 1
+    return sorted(counts.values())
+
+
+@cpu_case("topology_test.go:163-204")
+def non_minimum_domain_when_nothing_else_is_available():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels, max_skew=5)]
+    nodes = [_small_node_with("n1", "test-zone-1", [pod({"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons, nodeName="n1")]),
+             _small_node_with("n2", "test-zone-2", [pod({"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons, nodeName="n2")])]
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-3"]}])
+    prob = problem(pods(10, requests={"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons), provisioners=[pr], nodes=nodes)
+    return prob, lambda res: _eq(_zone_counts(prob, res, {"test-zone-1": 1, "test-zone-2": 1}), [1, 1, 6])
+
+
+@cpu_case("topology_test.go:205-242")
+def only_minimum_domains_while_the_skew_is_violated():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels)]
+    nodes = [_small_node_with(f"n{i}", "test-zone-1", [pod({"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons, nodeName=f"n{i}")])
+             for i in range(3)]
+    prob = problem(pods(3, requests={"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons), nodes=nodes)
+    return prob, lambda res: _eq(_zone_counts(prob, res, {"test-zone-1": 3}), [1, 2, 3])
+
+
+@cpu_case("topology_test.go:243-306")
+def max_skew_is_not_violated_do_not_schedule():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels)]
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-2", "test-zone-3"]}])
+    owning = _small_node_with("n1", "test-zone-1", [pod({"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons, nodeName="n1")])
+    discovered = _small_node_with("n1", "test-zone-1", [pod({"cpu": "1.1"}, labels=labels, nodeName="n1")])  # matching labels only (:276-306)
+    probs = [problem(pods(10, requests={"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons), provisioners=[pr], nodes=[n])
+             for n in (owning, discovered)]
+
+    def check(results):
+        for prob, res in zip(probs, results):
+            assert _zone_counts(prob, res, {"test-zone-1": 1}) == [1, 2, 2]
+            assert sum(1 for a in res["assign"] if a < 0) == 6
+    return {"multi": probs}, check
+
+
+@cpu_case("topology_test.go:308-339")
+def only_running_pods_with_matching_labels_and_a_domain_count():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels)]
+    first = fx.state_node("first", zone="test-zone-1", allocatable={"cpu": "0", "memory": "0", "pods": "0"}, pods_=[
+        pod(nodeName="first"),                                           # ignored: no labels
+        pod(labels=labels, namespace="other", nodeName="first"),        # ignored: wrong namespace
+        pod(labels=labels, nodeName="first", terminal=True),            # ignored: phase Failed / Succeeded
+        pod(labels=labels, nodeName="first", terminating=True),         # ignored: terminating
+        pod(labels=labels, nodeName="first"), pod(labels=labels, nodeName="first")])
+    second = fx.state_node("second", zone="test-zone-2", allocatable={"cpu": "0", "memory": "0", "pods": "0"}, pods_=[pod(labels=labels, nodeName="second")])
+    third = fx.state_node("third", allocatable={"cpu": "0", "memory": "0", "pods": "0"}, pods_=[pod(labels=labels, nodeName="third")])
+    del third["labels"][ZONE]                                            # ignored: the node has no zone
+    prob = problem(pods(2, labels=labels, topologySpreadConstraints=cons), nodes=[first, second, third])
+
+    return prob, lambda res: _eq(_zone_counts(prob, res, {"test-zone-1": 2, "test-zone-2": 1}), [1, 2, 2])  # ConsistOf(2, 2, 1)
