@@ -928,3 +928,69 @@ def only_running_pods_with_matching_labels_and_a_domain_count():
     prob = problem(pods(2, labels=labels, topologySpreadConstraints=cons), nodes=[first, second, third])
 
     return prob, lambda res: _eq(_zone_counts(prob, res, {"test-zone-1": 2, "test-zone-2": 1}), [1, 2, 2])  # ConsistOf(2, 2, 1)
+
+
+# ------------------------------------------------------------------ more spread / affinity (topology_test.go:353-590, 1239-1281)
+@cpu_case("topology_test.go:353-378")
+def spread_whose_selector_matches_no_pod_does_not_spread():
+    """the selector counts pods, the owner is what the spread applies to: nothing matches, so nothing has to be spread"""
+    cons = [fx.spread(HOSTNAME, {"test": "test"})]
+    prob = problem(pods(5, topologySpreadConstraints=cons))
+    return prob, lambda res: _eq(len(set(res["assign"])), 1)
+
+
+@cpu_case("topology_test.go:447-489")
+def hostname_spread_of_two_deployments_on_two_archs_needs_four_nodes():
+    def app(name, arch, n):
+        lab = {"app": name}
+        return pods(n, labels=lab, topologySpreadConstraints=[fx.spread(HOSTNAME, lab)],
+                    nodeAffinity={"required": [[{"key": ARCH, "operator": "In", "values": [arch]}]]})
+    prob = problem(app("app1", "amd64", 2) + app("app2", "arm64", 2))
+
+    def check(res):
+        assert min(res["assign"]) >= 0 and len(set(res["assign"])) == 4
+    return prob, check
+
+
+def _ct_counts(res, base):
+    counts = dict(base)
+    ne = len(res["existing"])
+    for a in res["assign"]:
+        if a >= ne:
+            ct = res["newNodes"][a - ne]["requirements"][CAPACITY_TYPE]
+            counts[ct] = counts.get(ct, 0) + 1
+    return sorted(counts.values())
+
+
+@cpu_case("topology_test.go:526-590")
+def capacity_type_skew_do_not_schedule_versus_schedule_anyway():
+    labels = {"test": "test"}
+    od = provisioner(requirements=[{"key": CAPACITY_TYPE, "operator": "In", "values": ["on-demand"]}])
+    probs = []
+    for when in ("DoNotSchedule", "ScheduleAnyway"):
+        cons = [fx.spread(CAPACITY_TYPE, labels, when=when)]
+        spot_node = fx.state_node("n-spot", "small-instance-type", capacity_type="spot", allocatable={"cpu": "1900m", "memory": "2038Mi", "pods": "5"},
+                                  pods_=[pod({"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons, nodeName="n-spot")])
+        probs.append(problem(pods(5, requests={"cpu": "1.1"}, labels=labels, topologySpreadConstraints=cons), provisioners=[od], nodes=[spot_node]))
+
+    def check(results):
+        assert _ct_counts(results[0], {"spot": 1}) == [1, 2]   # on-demand may only get one ahead of spot
+        assert sum(1 for a in results[0]["assign"] if a < 0) == 3
+        assert _ct_counts(results[1], {"spot": 1}) == [1, 5]   # ScheduleAnyway is relaxed away
+    return {"multi": probs}, check
+
+
+@cpu_case("topology_test.go:1239-1281")
+def pod_affinity_on_arch_with_hostname_spread():
+    aff = {"security": "s2"}
+    tsc = [fx.spread(HOSTNAME, aff)]
+    first = pod({"cpu": "2"}, labels=aff, topologySpreadConstraints=tsc, nodeSelector={ARCH: "arm64"})
+    second = pod({"cpu": "1"}, labels=aff, topologySpreadConstraints=tsc, podAffinity={"required": [fx.affinity_term(ARCH, aff)]})
+    prob = problem([first, second])
+
+    def check(res):
+        assert min(res["assign"]) >= 0 and res["assign"][0] != res["assign"][1]  # same arch, but the spread keeps them apart
+        ne = len(res["existing"])
+        archs = [res["newNodes"][a - ne]["requirements"][ARCH] for a in res["assign"]]
+        assert archs == ["In [arm64]", "In [arm64]"]
+    return prob, check
