@@ -994,3 +994,49 @@ def pod_affinity_on_arch_with_hostname_spread():
         archs = [res["newNodes"][a - ne]["requirements"][ARCH] for a in res["assign"]]
         assert archs == ["In [arm64]", "In [arm64]"]
     return prob, check
+
+
+# ------------------------------------------------------------------ self pod affinity (topology_test.go:1306-1444)
+@cpu_case("topology_test.go:1306-1344")
+def self_affinity_on_hostname_fills_exactly_one_node():
+    aff = {"security": "s2"}
+    mk = lambda n: pods(n, labels=aff, podAffinity={"required": [fx.affinity_term(HOSTNAME, aff)]})
+    first = problem(mk(10))
+    # second batch of the Go test: the first node exists (in flight, full: 5 pods) - nobody of the next batch may open a second domain
+    full = fx.state_node("node-a", pods_=[pod(labels=aff, podAffinity={"required": [fx.affinity_term(HOSTNAME, aff)]}, nodeName="node-a") for _ in range(5)])
+    second = problem(mk(10), nodes=[full])
+
+    def check(results):
+        a = results[0]["assign"]
+        assert sum(1 for x in a if x >= 0) == 5 and len({x for x in a if x >= 0}) == 1  # the default types hold 5 pods
+        assert all(x < 0 for x in results[1]["assign"])
+    return {"multi": [first, second]}, check
+
+
+@cpu_case("topology_test.go:1346-1389")
+def self_affinity_is_not_limited_by_the_followers_node_selectors():
+    """a matching pod already runs in zone-1; followers restricted to zone-2/3 cannot bootstrap a second hostname domain"""
+    aff = {"security": "s2"}
+    term = {"required": [fx.affinity_term(HOSTNAME, aff)]}
+    # 3 of 5 pod slots and most of the cpu are taken by unrelated pods: the node is in flight but cannot take a follower
+    holder = fx.state_node("node-z1", zone="test-zone-1", allocatable={"cpu": "3900m", "memory": "4086Mi", "pods": "1"},
+                           pods_=[pod(labels=aff, podAffinity=term, nodeName="node-z1")])
+    followers = pods(10, labels=aff, podAffinity=term,
+                     nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-2", "test-zone-3"]}]]})
+    prob = problem(followers, nodes=[holder])
+    return prob, lambda res: _eq([x >= 0 for x in res["assign"]], [False] * 10)
+
+
+@cpu_case("topology_test.go:1390-1444")
+def self_affinity_on_zone():
+    aff = {"security": "s2"}
+    term = {"required": [fx.affinity_term(ZONE, aff)]}
+    free = problem(pods(3, labels=aff, podAffinity=term))
+    pinned = problem(pods(3, labels=aff, podAffinity=term, nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-3"]}]]}))
+
+    def check(results):
+        for res in results:
+            assert min(res["assign"]) >= 0 and len(set(res["assign"])) == 1
+        node = results[1]["newNodes"][results[1]["assign"][0] - len(results[1]["existing"])]
+        assert node["requirements"][ZONE] == "In [test-zone-3]"
+    return {"multi": [free, pinned]}, check
