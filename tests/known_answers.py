@@ -1040,3 +1040,68 @@ def self_affinity_on_zone():
         node = results[1]["newNodes"][results[1]["assign"][0] - len(results[1]["existing"])]
         assert node["requirements"][ZONE] == "In [test-zone-3]"
     return {"multi": [free, pinned]}, check
+
+
+# ------------------------------------------------------------------ pod anti-affinity variants (topology_test.go:1572-1843)
+@cpu_case("topology_test.go:1572-1593")
+def zonal_anti_affinity_against_a_pod_of_unknown_zone():
+    aff = {"security": "s2"}
+    target = pod({"cpu": "2"}, labels=aff)                                   # schedules first (larger), zone undetermined
+    avoider = pod(podAntiAffinity={"required": [fx.affinity_term(ZONE, aff)]})
+    prob = problem([target, avoider])
+    return prob, lambda res: _eq([a >= 0 for a in res["assign"]], [True, False])
+
+
+@cpu_case("topology_test.go:1594-1635")
+def anti_affinity_on_arch():
+    aff = {"security": "s2"}
+    tsc = [fx.spread(HOSTNAME, aff)]
+    first = pod({"cpu": "2"}, labels=aff, topologySpreadConstraints=tsc, nodeSelector={ARCH: "arm64"})
+    second = pod({"cpu": "1"}, labels=aff, topologySpreadConstraints=tsc, podAntiAffinity={"required": [fx.affinity_term(ARCH, aff)]})
+    prob = problem([first, second])
+
+    def check(res):
+        assert min(res["assign"]) >= 0
+        ne = len(res["existing"])
+        archs = [res["newNodes"][a - ne]["requirements"][ARCH] for a in res["assign"]]
+        assert archs == ["In [arm64]", "In [amd64]"]
+    return prob, check
+
+
+def _zoned_avoiders(term_key, aff):
+    return [pod({"cpu": "2"}, nodeSelector={ZONE: z}, podAntiAffinity={term_key: [term]})
+            for z in ZONES
+            for term in ([fx.affinity_term(ZONE, aff)] if term_key == "required" else [{"weight": 10, "term": fx.affinity_term(ZONE, aff)}])]
+
+
+@cpu_case("topology_test.go:1637-1711")
+def inverse_zonal_anti_affinity_required_versus_preferred():
+    aff = {"security": "s2"}
+    required = problem(_zoned_avoiders("required", aff) + [pod(labels=aff)])
+    preferred = problem(_zoned_avoiders("preferred", aff) + [pod(labels=aff)])
+
+    def check(results):
+        assert [a >= 0 for a in results[0]["assign"]] == [True, True, True, False]  # every zone holds a pod that repels it
+        assert [a >= 0 for a in results[1]["assign"]] == [True, True, True, True]   # a preference only
+    return {"multi": [required, preferred]}, check
+
+
+@cpu_case("topology_test.go:1745-1843")
+def inverse_zonal_anti_affinity_from_pods_that_already_run():
+    aff = {"security": "s2"}
+
+    def cluster(term_key):
+        nodes = []
+        for i, z in enumerate(ZONES):
+            term = fx.affinity_term(ZONE, aff)
+            anti = {"required": [term]} if term_key == "required" else {"preferred": [{"weight": 10, "term": term}]}
+            nodes.append(fx.state_node(f"n{i}", "small-instance-type", zone=z, allocatable={"cpu": "1900m", "memory": "2038Mi", "pods": "5"},
+                                       pods_=[pod({"cpu": "1.5"}, podAntiAffinity=anti, nodeName=f"n{i}")]))
+        return nodes
+    required = problem([pod(labels=aff)], nodes=cluster("required"))
+    preferred = problem([pod(labels=aff)], nodes=cluster("preferred"))
+
+    def check(results):
+        assert results[0]["assign"] == [-1]
+        assert results[1]["assign"][0] >= 0
+    return {"multi": [required, preferred]}, check
