@@ -1105,3 +1105,44 @@ def inverse_zonal_anti_affinity_from_pods_that_already_run():
         assert results[0]["assign"] == [-1]
         assert results[1]["assign"][0] >= 0
     return {"multi": [required, preferred]}, check
+
+
+# ------------------------------------------------------------------ zonal affinity, namespaces, several provisioners (topology_test.go:1974-2207)
+@cpu_case("topology_test.go:1974-2001")
+def zonal_affinity_to_a_zone_constrained_target():
+    aff = {"security": "s2"}
+    followers = pods(10, podAffinity={"required": [fx.affinity_term(ZONE, aff)]})
+    target = pod(labels=aff, nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-1"]}]]})
+    prob = problem(followers + [target])
+
+    def check(res):
+        assert min(res["assign"]) >= 0
+        ne = len(res["existing"])
+        assert {res["newNodes"][a - ne]["requirements"][ZONE] for a in res["assign"]} == {"In [test-zone-1]"}  # ConsistOf(11)
+    return prob, check
+
+
+@cpu_case("topology_test.go:2054-2130")
+def affinity_terms_select_by_namespace():
+    labels, aff = {"test": "test"}, {"security": "s2"}
+    noise = lambda: pods(10, labels=labels, topologySpreadConstraints=[fx.spread(HOSTNAME, labels)])
+    elsewhere = problem(noise() + [pod(labels=aff, namespace="other-ns-no-match"),
+                                   pod(podAffinity={"required": [fx.affinity_term(HOSTNAME, aff)]})])
+    listed = problem(noise() + [pod(labels=aff, namespace="other-ns-list"),
+                                pod(podAffinity={"required": [fx.affinity_term(HOSTNAME, aff, namespaces=["other-ns-list"])]})])
+
+    def check(results):
+        a = results[0]["assign"]
+        assert a[10] >= 0 and a[11] < 0          # the target lives in another namespace: not selected
+        b = results[1]["assign"]
+        assert b[10] >= 0 and b[11] == b[10]     # the term lists that namespace: same node
+    return {"multi": [elsewhere, listed]}, check
+
+
+@cpu_case("topology_test.go:2174-2207")
+def spread_counts_across_provisioners():
+    labels = {"foo": "bar"}
+    prs = [provisioner("zone-1-only", requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-1"]}]),
+           provisioner("zones-2-3", requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-2", "test-zone-3"]}])]
+    prob = problem(pods(10, labels=labels, topologySpreadConstraints=[fx.spread(ZONE, labels)]), provisioners=prs)
+    return prob, lambda res: _eq(fx.skew(prob, res, ZONE), [3, 3, 4])
