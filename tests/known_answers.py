@@ -1146,3 +1146,37 @@ def spread_counts_across_provisioners():
            provisioner("zones-2-3", requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-2", "test-zone-3"]}])]
     prob = problem(pods(10, labels=labels, topologySpreadConstraints=[fx.spread(ZONE, labels)]), provisioners=prs)
     return prob, lambda res: _eq(fx.skew(prob, res, ZONE), [3, 3, 4])
+
+
+# ------------------------------------------------------------------ TopologyNodeFilter: which nodes count for a spread (topology_test.go:661-782)
+@cpu_case("topology_test.go:661-695")
+def node_affinity_of_the_owner_filters_the_counted_nodes():
+    """the spread owners are restricted to (zone-2, spot): the on-demand pod in zone-1 is not counted, all five fit one spot node"""
+    labels = {"test": "test"}
+    existing = fx.state_node("n-od", zone="test-zone-1", capacity_type="on-demand", allocatable={"cpu": "0", "memory": "0", "pods": "0"},
+                             pods_=[pod(labels=labels, nodeName="n-od")])
+    aff = {"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-2"]}, {"key": CAPACITY_TYPE, "operator": "In", "values": ["spot"]}]]}
+    prob = problem(pods(5, labels=labels, nodeAffinity=aff, topologySpreadConstraints=[fx.spread(CAPACITY_TYPE, labels)]), nodes=[existing])
+
+    def check(res):
+        assert min(res["assign"]) >= 1 and len(set(res["assign"])) == 1
+        assert _ct_counts(res, {"on-demand": 1}) == [1, 5]
+    return prob, check
+
+
+@cpu_case("topology_test.go:697-782")
+def unconstrained_owners_see_the_existing_domain():
+    labels = {"test": "test"}
+    probs = []
+    for key, have, only in ((CAPACITY_TYPE, "on-demand", "spot"), (ARCH, "amd64", "arm64")):
+        lab = {CAPACITY_TYPE: "on-demand"} if key == CAPACITY_TYPE else {ARCH: "amd64"}
+        existing = fx.state_node("n-old", "single-pod-instance-type", allocatable={"cpu": "3900m", "memory": "4086Mi", "pods": "1"},
+                                 pods_=[pod(labels=labels, nodeName="n-old")], labels=lab)
+        pr = provisioner(requirements=[{"key": key, "operator": "In", "values": [only]}])
+        probs.append(problem(pods(5, requests={"cpu": "2"}, labels=labels, topologySpreadConstraints=[fx.spread(key, labels)]), provisioners=[pr],
+                             nodes=[existing]))
+
+    def check(results):
+        for res in results:
+            assert sum(1 for a in res["assign"] if a >= 0) == 2  # ConsistOf(1, 2): two more, then the skew would be violated
+    return {"multi": probs}, check
