@@ -1180,3 +1180,22 @@ def unconstrained_owners_see_the_existing_domain():
         for res in results:
             assert sum(1 for a in res["assign"] if a >= 0) == 2  # ConsistOf(1, 2): two more, then the skew would be violated
     return {"multi": probs}, check
+
+
+# ------------------------------------------------------------------ custom spread key defined by provisioner requirements (topology_test.go:825-880)
+@cpu_case("topology_test.go:825-880")
+def spread_over_a_key_the_provisioners_define():
+    """`capacity.spread.4-1` has values 2..5 on the spot provisioner and 1 on the on-demand one: 20 pods end up 16 : 4"""
+    labels = {"test": "test"}
+    key = "capacity.spread.4-1"
+    spot = provisioner("spot", requirements=[{"key": CAPACITY_TYPE, "operator": "In", "values": ["spot"]},
+                                             {"key": key, "operator": "In", "values": ["2", "3", "4", "5"]}])
+    od = provisioner("on-demand", requirements=[{"key": CAPACITY_TYPE, "operator": "In", "values": ["on-demand"]},
+                                                {"key": key, "operator": "In", "values": ["1"]}])
+    prob = problem(pods(20, labels=labels, topologySpreadConstraints=[fx.spread(key, labels)]), provisioners=[spot, od])
+
+    def check(res):
+        assert min(res["assign"]) >= 0
+        assert fx.skew(prob, res, key) == [4, 4, 4, 4, 4]
+        assert _ct_counts(res, {}) == [4, 16]
+    return prob, check
