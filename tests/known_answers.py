@@ -1199,3 +1199,50 @@ def spread_over_a_key_the_provisioners_define():
         assert fx.skew(prob, res, key) == [4, 4, 4, 4, 4]
         assert _ct_counts(res, {}) == [4, 16]
     return prob, check
+
+
+# ------------------------------------------------------------------ spread options limited by the owner's node affinity (topology_test.go:1057-1193)
+@cpu_case("topology_test.go:1057-1078")
+def spread_over_the_two_zones_the_node_affinity_allows():
+    labels = {"test": "test"}
+    aff = {"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-1", "test-zone-2"]}]]}
+    prob = problem(pods(10, labels=labels, nodeAffinity=aff, topologySpreadConstraints=[fx.spread(ZONE, labels)]))
+    return prob, lambda res: _eq(fx.skew(prob, res, ZONE), [5, 5])
+
+
+@cpu_case("topology_test.go:1079-1125")
+def a_new_zone_may_be_entered_when_that_improves_the_skew():
+    """(3, 3, 0) already run in zones 1/2; a pod allowed in zones 2/3 takes the empty zone-3; five unconstrained ones end at (4, 4, 4)"""
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels)]
+    z12 = {"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-1", "test-zone-2"]}]]}
+
+    def cluster():
+        nodes = []
+        for i, z in enumerate(("test-zone-1", "test-zone-2")):
+            bound = [pod(labels=labels, nodeAffinity=z12, topologySpreadConstraints=cons, nodeName=f"n{i}") for _ in range(3)]
+            nodes.append(fx.state_node(f"n{i}", zone=z, allocatable={"cpu": "3900m", "memory": "4086Mi", "pods": "3"}, pods_=bound))
+        return nodes
+    one = problem([pod(labels=labels, topologySpreadConstraints=cons,
+                       nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-2", "test-zone-3"]}]]})], nodes=cluster())
+    third = fx.state_node("n2", zone="test-zone-3", allocatable={"cpu": "3900m", "memory": "4086Mi", "pods": "1"},
+                          pods_=[pod(labels=labels, topologySpreadConstraints=cons, nodeName="n2")])
+    five = problem(pods(5, labels=labels, topologySpreadConstraints=cons), nodes=cluster() + [third])
+
+    def check(results):
+        assert _zone_counts(one, results[0], {"test-zone-1": 3, "test-zone-2": 3}) == [1, 3, 3]
+        assert _zone_counts(five, results[1], {"test-zone-1": 3, "test-zone-2": 3, "test-zone-3": 1}) == [4, 4, 4]
+    return {"multi": [one, five]}, check
+
+
+@cpu_case("topology_test.go:1127-1150")
+def schedule_anyway_capacity_type_spread_with_node_selectors():
+    labels = {"test": "test"}
+    cons = [fx.spread(CAPACITY_TYPE, labels, when="ScheduleAnyway")]
+    prob = problem(pods(5, labels=labels, topologySpreadConstraints=cons, nodeSelector={CAPACITY_TYPE: "spot"}) +
+                   pods(5, labels=labels, topologySpreadConstraints=cons, nodeSelector={CAPACITY_TYPE: "on-demand"}))
+
+    def check(res):
+        assert min(res["assign"]) >= 0
+        assert _ct_counts(res, {}) == [5, 5]
+    return prob, check
