@@ -1246,3 +1246,31 @@ def schedule_anyway_capacity_type_spread_with_node_selectors():
         assert min(res["assign"]) >= 0
         assert _ct_counts(res, {}) == [5, 5]
     return prob, check
+
+
+# ------------------------------------------------------------------ instance selection and in-flight nodes (suite_test.go:1275-1404)
+@cpu_case("suite_test.go:1275-1342")
+def every_valid_type_is_offered_and_the_cheapest_one_launches():
+    mk = lambda name, cpu, mem, price: fx.instance_type(name, {"cpu": cpu, "memory": mem},
+                                                        offerings=[{"capacityType": "on-demand", "zone": "test-zone-1a", "price": price, "available": True}])
+    its = [mk("medium", "2", "2Gi", 3.0), mk("small", "1", "1Gi", 2.0), mk("large", "4", "4Gi", 1.0)]  # sizes and prices do not correlate
+    prob = problem([pod({"cpu": "1m", "memory": "1Mi"})], instance_types=its)
+
+    def check(res):
+        node = res["newNodes"][res["assign"][0]]
+        assert sorted(its[i]["name"] for i in node["options"]) == ["large", "medium", "small"]
+        assert its[node["launch"]["type"]]["name"] == "large" and node["launch"]["price"] == 1.0
+    return prob, check
+
+
+@cpu_case("suite_test.go:1359-1404")
+def in_flight_node_is_reused_when_the_selectors_intersect():
+    node = fx.state_node("node-z2", zone="test-zone-2", pods_=[pod({"cpu": "10m"}, nodeName="node-z2")])
+    fits = pod({"cpu": "10m"}, nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-1", "test-zone-2"]}]]})
+    other = pod({"cpu": "10m"}, nodeAffinity={"required": [[{"key": ZONE, "operator": "In", "values": ["test-zone-1", "test-zone-3"]}]]})
+    probs = [problem([fits], nodes=[node]), problem([other], nodes=[node])]
+
+    def check(results):
+        assert results[0]["assign"] == [0] and results[0]["newNodes"] == []
+        assert results[1]["assign"] == [1] and len(results[1]["newNodes"]) == 1
+    return {"multi": probs}, check
