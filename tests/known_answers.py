@@ -1274,3 +1274,31 @@ def in_flight_node_is_reused_when_the_selectors_intersect():
         assert results[0]["assign"] == [0] and results[0]["newNodes"] == []
         assert results[1]["assign"] == [1] and len(results[1]["newNodes"]) == 1
     return {"multi": probs}, check
+
+
+# ------------------------------------------------------------------ in-flight nodes: deletion and taints (suite_test.go:1438-1659)
+@cpu_case("suite_test.go:1438-1458")
+def node_being_deleted_is_not_a_target():
+    going = fx.state_node("node-a", pods_=[pod({"cpu": "10m"}, nodeName="node-a")], markedForDeletion=True)
+    prob = problem([pod({"cpu": "10m"})], nodes=[going])
+
+    def check(res):
+        assert len(res["newNodes"]) == 1 and res["assign"][0] == len(res["existing"])
+    return prob, check
+
+
+@cpu_case("suite_test.go:1610-1658")
+def startup_taint_after_initialization_blocks_ephemeral_taints_do_not():
+    startup = {"key": "ignore-me", "value": "nothing-to-see-here", "effect": "NoSchedule"}
+    pr = provisioner(startupTaints=[startup])
+    came_back = fx.state_node("node-a", taints=[startup])  # initialized: the startup taint is a real taint now
+    p1 = problem([pod()], provisioners=[pr], nodes=[came_back])
+    not_ready = fx.state_node("node-b", taints=[{"key": "node.kubernetes.io/not-ready", "effect": "NoSchedule"},
+                                                {"key": "node.kubernetes.io/unreachable", "effect": "NoSchedule"}],
+                              pods_=[pod({"cpu": "10m"}, nodeName="node-b")])
+    p2 = problem([pod({"cpu": "10m"})], nodes=[not_ready])
+
+    def check(results):
+        assert len(results[0]["newNodes"]) == 1           # a new node: the startup taint was gone once and is back
+        assert results[1]["assign"] == [0] and results[1]["newNodes"] == []  # NotReady / Unreachable are ephemeral (state/node.go:93-110)
+    return {"multi": [p1, p2]}, check
