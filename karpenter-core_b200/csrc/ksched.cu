@@ -1972,8 +1972,6 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
 
 int ksched_solve(ksched_handle* h, const ksched_problem* pb, ksched_result* res) {
   if (!h || !pb || !res) return KSCHED_ERR_INVALID;
-  cudaEvent_t e0 = h->ev[7];
-  (void)e0;
   auto t0 = std::chrono::steady_clock::now();
   int rc = ksched_upload(h, pb);
   if (rc != KSCHED_OK) return rc;
@@ -1985,7 +1983,6 @@ int ksched_solve(ksched_handle* h, const ksched_problem* pb, ksched_result* res)
   auto t3 = std::chrono::steady_clock::now();
   h->tm.upload_us = std::chrono::duration<double, std::micro>(t1 - t0).count();
   h->tm.download_us = std::chrono::duration<double, std::micro>(t3 - t2).count();
-  (void)t2;
   return rc;
 }
 
