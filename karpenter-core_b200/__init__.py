@@ -92,6 +92,8 @@ def lib():
     L.kh_result_to_json_brief.restype = C.c_longlong
     L.kh_result_to_json_brief.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     L.kh_problem_pod_summary.argtypes = [C.c_void_p, C.c_void_p]
+    L.kh_encoded_digest.restype = C.c_ulonglong
+    L.kh_encoded_digest.argtypes = [C.c_void_p]
     L.kh_launch_table_selfcheck.argtypes = [C.c_void_p, C.c_void_p]
     L.kh_selftest_two_handles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.kh_set_device.argtypes = [C.c_int]

@@ -559,6 +559,39 @@ extern "C" int kh_launch_table_selfcheck(const Problem* P, const Result* ref) {
   }
 }
 
+// ---- digest of everything an encoding hands to the C-ABI (tests: a faster encoder must produce the same bytes)
+extern "C" unsigned long long kh_encoded_digest(const Encoded* E) {
+  unsigned long long h = 1469598103934665603ull;
+  auto bytes = [&](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  };
+  auto str = [&](const std::string& x) { size_t n = x.size(); bytes(&n, sizeof n); bytes(x.data(), n); };
+  auto vec = [&](const auto& v) { size_t n = v.size(); bytes(&n, sizeof n); if (n) bytes(v.data(), n * sizeof(v[0])); };
+  for (auto& k : E->key_names) str(k);
+  for (auto& vs : E->key_values) { size_t n = vs.size(); bytes(&n, sizeof n); for (auto& v : vs) str(v); }
+  for (auto& r : E->res_names) str(r);
+  for (auto* p : E->pods) str(p->uid);
+  vec(E->existing_state_index);
+  for (bool b : E->existing_initialized) { unsigned char c = b; bytes(&c, 1); }
+  vec(E->template_provisioner); vec(E->type_input_index);
+  bytes(&E->type_words, sizeof E->type_words);
+  vec(E->keys); vec(E->key_int_values); vec(E->types); vec(E->type_capacity); vec(E->offering_keys); vec(E->price_by_rank);
+  vec(E->templates); vec(E->template_bounds); vec(E->classes); vec(E->class_bounds);
+  unsigned char flags[2] = {(unsigned char)E->any_class_bounds, (unsigned char)E->any_template_bounds};
+  bytes(flags, 2);
+  vec(E->pod_class); vec(E->pod_timestamp); vec(E->pod_uid_rank); vec(E->existing); vec(E->groups); vec(E->group_domain_counts);
+  vec(E->group_existing_counts); vec(E->class_topo); vec(E->filter_terms); vec(E->itype_req_sets); vec(E->itype_req_complement); vec(E->hostname_reqs);
+  const ksched_catalog& c = E->catalog;
+  int cat[4] = {c.n_keys, c.n_res, c.n_types, c.n_templates};
+  bytes(cat, sizeof cat);
+  const ksched_problem& q = E->problem;
+  int pr[11] = {q.n_pods, q.n_classes, q.n_existing, q.n_groups, q.n_class_topo, q.n_filter_terms, q.n_itype_reqs, q.n_hostname_reqs, q.max_new_nodes,
+                q.write_feasibility, 0};
+  bytes(pr, sizeof pr);
+  return h;
+}
+
 // ---- host-side mask algebra exposed for the CPU golden-vector tests (same code the kernels run)
 // spec: op ("In","NotIn","Exists","DoesNotExist","Gt","Lt") + comma separated values; dictionary = A,B,1,2,9
 static ksched::Req spec_req(const char* op_c, const char* vals_c, const std::vector<std::string>& dict) {
