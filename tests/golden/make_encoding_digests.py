@@ -17,10 +17,18 @@ sys.path.insert(0, str(ROOT / "tests"))
 def corpus(pkg):
     import consolidation_answers as ca
     import known_answers as ka
+    import itertools
+
+    import fixtures as fx
     from fuzz_problems import random_problem
+
+    def fresh():  # pod names / uids come from a process-wide counter in the fixtures: restart it so the corpus does not depend on test order
+        fx._uid = itertools.count()
     for seed in range(300):
+        fresh()
         yield f"fuzz-{seed}", pkg.Problem.from_dict(random_problem(seed)), ()
     for name, _, build in ka.CASES + ka.CPU_ONLY_CASES + ca.CASES + ca.CPU_ONLY_CASES:
+        fresh()
         prob, _ = build()
         for i, pd in enumerate(prob["multi"] if "multi" in prob else [prob]):
             problem = pkg.Problem.from_dict(pd)
