@@ -245,6 +245,50 @@ std::vector<HostPortEntry> host_ports(const Pod& p) {  // hostportusage.go:118-1
   return out;
 }
 
+// Facts about the cluster state that do not depend on which nodes are consolidation candidates nor on the dictionary:
+// computed once per Problem (a consolidation pass encodes the same Problem once per probe), by exactly the code the
+// encoder used to run per node on every call, so the encoding stays byte-identical (tests/test_encoding_digests.py).
+std::vector<Taint> state_node_taints(const StateNode& n);
+struct NodeFacts {
+  ResourceList pod_req, ds_req;          // sum of RequestsForPods over the bound pods / over the bound daemonset pods
+  std::vector<HostPortEntry> hostports;  // host ports of the bound pods, pod order
+  std::vector<NodeSelectorRequirement> label_reqs;  // NewLabelRequirements(node.Labels), requirements.go:54-59
+  std::vector<Taint> taints;             // state.Node.Taints(): Spec.Taints without the ephemeral / not-yet-removed startup ones
+};
+struct ClusterFacts : kmodel::ProblemDerived {
+  std::vector<NodeFacts> node;           // parallel to Problem.nodes
+  std::set<std::string> res_names;       // resource names mentioned by node allocatable / capacity / bound pods
+  std::set<std::string> anti_keys;       // topology keys of the bound pods' required anti-affinity terms
+  std::set<std::pair<std::string, std::string>> label_pairs;  // every (key, value) some node carries as a label
+};
+const ClusterFacts& cluster_facts(const Problem& P) {
+  std::lock_guard<std::mutex> lock(P.derived_mu);
+  if (!P.derived) {
+    auto f = std::make_shared<ClusterFacts>();
+    f->node.resize(P.nodes.size());
+    for (size_t i = 0; i < P.nodes.size(); ++i) {
+      const StateNode& n = P.nodes[i];
+      NodeFacts& nf = f->node[i];
+      for (auto& kv : n.allocatable) f->res_names.insert(kv.first);
+      for (auto& kv : n.capacity) f->res_names.insert(kv.first);
+      for (auto& p : n.pods) {
+        const ResourceList r = pod_requests(p);
+        for (auto& kv : r) f->res_names.insert(kv.first);
+        nf.pod_req = merge(nf.pod_req, r);
+        if (p.is_daemonset) nf.ds_req = merge(nf.ds_req, r);
+        for (auto& hp : host_ports(p)) nf.hostports.push_back(hp);
+      }
+      for (auto& kv : n.labels) nf.label_reqs.push_back({kv.first, Op::In, {kv.second}});
+      nf.taints = state_node_taints(n);
+      for (auto& p : n.pods)
+        for (auto& t : p.pod_anti_affinity_required) f->anti_keys.insert(t.topology_key);
+      for (auto& kv : n.labels) f->label_pairs.insert({kv.first, kv.second});
+    }
+    P.derived = f;
+  }
+  return static_cast<const ClusterFacts&>(*P.derived);
+}
+
 struct Builder {
   const Problem& P;
   Encoded& E;
@@ -397,6 +441,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   Encoded& E = *enc;
   E.problem_ref = &P;
   Builder B(P, E);
+  const ClusterFacts& facts = cluster_facts(P);
 
   // ------------------------------------------------------------------ who takes part
   std::vector<int> state_nodes;
@@ -475,9 +520,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   for (auto& s : specs) note_pod(s.pod);
   for (auto& d : daemons) note_pod(d);
   if (!P.empty_topology)
-    for (auto& n : P.nodes)
-      for (auto& p : n.pods)
-        for (auto& t : p.pod_anti_affinity_required) pod_side.insert(t.topology_key);
+    for (auto& k : facts.anti_keys) pod_side.insert(k);  // bound pods with required anti-affinity (ClusterFacts)
   std::set<std::string> type_keys, template_keys;
   for (auto& it : P.instance_types) for (auto& r : it.requirements) type_keys.insert(normalize_key(r.key));
   for (auto& pr : P.provisioners) {
@@ -531,7 +574,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     l[kProvisionerName] = pr.name;
     note_label_vals(l);
   }
-  for (auto& n : P.nodes) note_label_vals(n.labels);
+  for (auto& kv : facts.label_pairs) { int k = B.key_of(kv.first); if (k >= 0) vals[k].insert(kv.second); }  // every node's labels (ClusterFacts)
   B.value_id.resize(NK);
   E.key_values.resize(NK);
   E.keys.resize(NK);
@@ -565,7 +608,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     for (auto& d : daemons) note(pod_requests(d));
     for (auto& it : P.instance_types) { note(it.capacity); }
     for (auto& pr : P.provisioners) note(pr.limits);
-    for (auto& n : P.nodes) { note(n.allocatable); note(n.capacity); for (auto& p : n.pods) note(pod_requests(p)); }
+    for (auto& n : facts.res_names) names.insert(n);  // node allocatable / capacity / bound pods (ClusterFacts)
     E.res_names = {"cpu", "memory", "pods"};
     for (auto& n : names) if (n != "cpu" && n != "memory" && n != "pods") E.res_names.push_back(n);
     if (E.res_names.size() > KSCHED_MAX_RES) unsupported("more than 8 distinct resources");
@@ -719,7 +762,8 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     std::memset(&e, 0, sizeof e);
     ksched_bounds nb{};
     Builder::Special sp;
-    B.add_selector_reqs(e.reqs, nb, Builder::label_reqs(n.labels), &sp);
+    const NodeFacts& nf = facts.node[(size_t)si];
+    B.add_selector_reqs(e.reqs, nb, nf.label_reqs, &sp);
     ResourceList daemon_total;
     int dcount = 0;
     for (auto& d : daemons) {
@@ -731,23 +775,19 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
       ++dcount;
     }
     daemon_total["pods"] = (int64_t)dcount * 1000;
-    ResourceList pod_req, ds_req;
-    for (auto& p : n.pods) {
-      pod_req = merge(pod_req, pod_requests(p));
-      if (p.is_daemonset) ds_req = merge(ds_req, pod_requests(p));
-    }
+    const ResourceList& pod_req = nf.pod_req;
+    const ResourceList& ds_req = nf.ds_req;
     ResourceList rem = daemon_total;  // resources.Subtract over keys of lhs, clamped at 0
     for (auto& kv : rem) { auto f = ds_req.find(kv.first); if (f != ds_req.end()) kv.second -= f->second; if (kv.second < 0) kv.second = 0; }
     ResourceList avail = n.allocatable;
     for (auto& kv : avail) { auto f = pod_req.find(kv.first); if (f != pod_req.end()) kv.second -= f->second; }
     e.available_present = B.fill_resources(avail, e.available);
     e.requests_present = B.fill_resources(rem, e.requests);
-    e.taintset = (uint32_t)B.taintset(state_node_taints(n));
+    e.taintset = (uint32_t)B.taintset(nf.taints);
     e.itype = KSCHED_NONE;
     auto itl = n.labels.find(kInstanceType);
     if (itl != n.labels.end()) { auto c = B.type_col.find(itl->second); if (c != B.type_col.end()) e.itype = (uint32_t)c->second; }
-    for (auto& p : n.pods)
-      for (auto& hp : host_ports(p)) e.hostport_entries |= 1ull << B.hp_entry(hp);
+    for (auto& hp : nf.hostports) e.hostport_entries |= 1ull << B.hp_entry(hp);
     std::string hostname;
     auto h = n.labels.find(kHostname);
     if (h != n.labels.end()) hostname = h->second;

@@ -14,6 +14,8 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -144,7 +146,15 @@ struct StateNode {
   double disruption_cost = 0;
 };
 
+// Derived, dictionary-independent facts about the cluster state that every encoding of the same Problem needs again
+// (consolidation encodes one Problem once per probe): filled lazily by the encoder, owned by the Problem.
+struct ProblemDerived {
+  virtual ~ProblemDerived() = default;
+};
+
 struct Problem {
+  mutable std::shared_ptr<ProblemDerived> derived;   // see khost::encode; a Problem is immutable once built
+  mutable std::mutex derived_mu;
   std::vector<std::string> extra_well_known_labels;  // v1alpha5.WellKnownLabels additions
   std::vector<InstanceType> instance_types;
   std::vector<Provisioner> provisioners;  // caller order; OrderByWeight applied by the solver
