@@ -218,3 +218,41 @@ def nothing_to_do_when_deletion_would_violate_anti_affinity():
             assert probe(count)[0] == 0  # already the cheapest types; moving a pod onto a sibling's node violates the anti-affinity
         assert search()["action"] == 0
     return prob, check
+
+
+@cpu_case("deprovisioning/suite_test.go:2142-2191")
+def pending_pods_take_part_in_the_simulation():
+    """a pending 125-cpu pod only fits the big expensive node: removing that node would strand it, so nothing is consolidated"""
+    its = assorted()
+    worst = on_demand_by_price(its)[-1]
+    of = worst["offerings"][0]
+
+    def cluster():
+        n = fx.state_node("node-a", worst["name"], zone=of["zone"], capacity_type=of["capacityType"],
+                          allocatable={"cpu": "128", "memory": "512Gi", "pods": "100"}, pods_=[fx.pod({"cpu": "1"}, nodeName="node-a")])
+        n["candidate"] = True
+        n["disruptionCost"] = 1.0
+        return n
+    with_pending = fx.problem([fx.pod({"cpu": "125"})], instance_types=its, nodes=[cluster()])
+
+    def check(probe, search):
+        assert probe(1)[0] == 0
+    # the same cluster without the pending pod is consolidatable: checked through a second problem below
+    return with_pending, check
+
+
+@cpu_case("deprovisioning/suite_test.go:2142-2191 (control)")
+def without_the_pending_pod_the_node_is_replaced():
+    its = assorted()
+    worst = on_demand_by_price(its)[-1]
+    of = worst["offerings"][0]
+    n = fx.state_node("node-a", worst["name"], zone=of["zone"], capacity_type=of["capacityType"],
+                      allocatable={"cpu": "128", "memory": "512Gi", "pods": "100"}, pods_=[fx.pod({"cpu": "1"}, nodeName="node-a")])
+    n["candidate"] = True
+    n["disruptionCost"] = 1.0
+    prob = fx.problem([], instance_types=its, nodes=[n])
+
+    def check(probe, search):
+        action, options = probe(1)
+        assert action == 2 and options
+    return prob, check
