@@ -51,1002 +51,9 @@ constexpr int kPackThreads = 512;
 constexpr int kFreshMemoSlots = 8192;  // PackState::fd_*
 constexpr uint64_t kNoBest = ~0ull;
 
-// ------------------------------------------------------------------------------------------------
-// Device-side catalog: instance-type columns as bit-sliced tables (one bit per column, u32 words).
-// ------------------------------------------------------------------------------------------------
-struct DevCatalog {
-  int n_keys, n_res, n_types, n_templates, W32;
-  const ksched_keyinfo* keys;        // [n_keys]
-  const int64_t* key_int_values;     // [n_keys][64]
-  const ksched_template* templates;  // [n_templates]
-  const ksched_type_row* types;      // [n_types]
-  const int64_t* capacity;           // [n_types][8]
-  const float* price32;              // [n_types]
-  const int16_t* valrow;             // [n_keys*64] row in valset or -1
-  const uint32_t* valset;            // [rows][W32] type has a positive requirement on key containing value
-  const uint32_t* absent;            // [n_keys][W32] type has no requirement on key
-  const uint32_t* negempty;          // [n_keys][W32] type requirement on key is DoesNotExist
-  uint32_t type_relevant;            // bit k: some type defines key k
-  const int16_t* offrow;             // [64] row in offset table or -1
-  const uint32_t* offset;            // [rows][W32] type has an available offering (ct*16+zone)
-  const uint32_t* anyoffer;          // [W32]
-  const uint32_t* member;            // [n_templates][W32]
-  const int64_t* alloc_sorted;       // [n_res][n_types] ascending
-  const uint32_t* fitset;            // [n_res][n_types+1][W32]  rank -> types with alloc >= alloc_sorted[rank]
-  const int32_t* perm_desc;          // [n_res][n_types] types by descending allocatable
-  const int64_t* alloc_rt;           // [n_res][n_types] allocatable, resource-major
-  const uint32_t* domset;            // [n_types][W32] types whose allocatable vector (first 4 resources) is dominated by the row's type
-  int zone_key, ct_key;
-  const uint64_t* offer_keys;        // [n_types][64] launch-choice keys (ksched_catalog.offering_keys) or nullptr
-  const uint32_t* input_index;       // [n_types] provider input order of the column
-};
-
-__device__ __forceinline__ KeyMeta key_meta(const DevCatalog& c, int k) {
-  return KeyMeta{c.keys[k].int_mask, c.key_int_values ? c.key_int_values + (size_t)k * 64 : nullptr};
-}
-
-// number of types with alloc_r < q  (lower bound)
-__device__ __forceinline__ int fit_rank(const int64_t* alloc_sorted, int n_types, int r, int64_t q) {
-  const int64_t* a = alloc_sorted + (size_t)r * n_types;
-  int lo = 0, hi = n_types;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (a[mid] < q) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// Column set {t : instanceType.Requirements.Intersects(node) holds on key k} for one u32 word
-// (requirements.go:189-206 with the type as receiver). `allowed` = dictionary values the node requirement
-// admits, `neg` = its operator is NotIn/DoesNotExist.
-__device__ __forceinline__ uint32_t key_typeset_word(const DevCatalog& c, int k, uint64_t allowed, bool neg, int w) {
-  uint32_t s = c.absent[(size_t)k * c.W32 + w];
-  if (neg) s |= c.negempty[(size_t)k * c.W32 + w];
-  uint64_t m = allowed;
-  while (m) {
-    int b = __ffsll((long long)m) - 1;
-    m &= m - 1;
-    int row = c.valrow[k * 64 + b];
-    if (row >= 0) s |= c.valset[(size_t)row * c.W32 + w];
-  }
-  return s;
-}
-// hasOffering (node.go:151-159) for one word: zmask / cmask = admitted zone / capacity-type value bits
-__device__ __forceinline__ uint32_t offer_word(const DevCatalog& c, uint32_t zmask, uint32_t cmask, bool unconstrained, int w) {
-  if (unconstrained) return c.anyoffer[w];
-  uint32_t s = 0;
-  uint32_t cm = cmask & 0xF;
-  while (cm) {
-    int ct = __ffs(cm) - 1;
-    cm &= cm - 1;
-    uint32_t zm = zmask & 0xFFFF;
-    while (zm) {
-      int z = __ffs(zm) - 1;
-      zm &= zm - 1;
-      int row = c.offrow[ct * 16 + z];
-      if (row >= 0) s |= c.offset[(size_t)row * c.W32 + w];
-    }
-  }
-  return s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K0: queue order
-// ------------------------------------------------------------------------------------------------
-__global__ void sort_keys_kernel(int n, const ksched_pod_row* __restrict__ classes, const uint32_t* __restrict__ pod_class,
-                                 const int64_t* __restrict__ ts, const uint32_t* __restrict__ uid_rank,
-                                 uint64_t* k_cpu, uint64_t* k_mem, uint64_t* k_tie, uint32_t* idx) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const ksched_pod_row& row = classes[pod_class[i]];
-  // descending cpu / memory -> ascending on the complemented value (milli-units are < 2^62)
-  k_cpu[i] = ~(uint64_t)(row.requests[0] + (1ll << 62));
-  k_mem[i] = ~(uint64_t)(row.requests[1] + (1ll << 62));
-  k_tie[i] = ((uint64_t)(ts[i] + (1ll << 32)) << 30) | (uint64_t)uid_rank[i];
-  idx[i] = (uint32_t)i;
-}
-__global__ void gather_u64_kernel(int n, const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t* dst) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[idx[i]];
-}
-// FFD-ordered dense pod-row matrix: row j = class row of the j-th pod of the queue. One warp per row,
-// 256-byte coalesced loads and stores.
-__global__ void gather_rows_kernel(int n, const ksched_pod_row* __restrict__ classes, const uint32_t* __restrict__ pod_class,
-                                   const uint32_t* __restrict__ order, uint64_t* __restrict__ rows) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int j = warp; j < n; j += nwarps) {
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(&classes[pod_class[order[j]]]);
-    rows[(size_t)j * KSCHED_ROW_WORDS + lane] = src[lane];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: feasibility. One warp per pod row; lane l owns column words l, l+32, ...
-// ------------------------------------------------------------------------------------------------
-struct K1Params {
-  DevCatalog cat;
-  const uint64_t* rows;  // [n_pods][32] FFD order
-  int n_pods;
-  const uint32_t* itype_sets;  // [n][W32]
-  uint32_t* F;                 // [n_pods][n_templates][W32]
-  unsigned long long* best;    // [n_pods]
-  int word_begin, word_end;    // column shard (u32 words) this device computes
-  int alloc_in_smem;           // the sorted allocatable arrays fit in the CTA's shared memory
-  long long* dbg;              // optional cycle counters (KSCHED_PROFILE_K1)
-  int tables_in_smem;          // valset / absent / negempty / offset / anyoffer / member are staged too
-  int n_valrows, n_offrows;
-};
-
-// Parameters in constant memory and the CTA's catalog view (table pointers redirected to the staged shared-memory
-// copies) in shared memory: the out-of-line row evaluation reads both with immediate addresses instead of through
-// references to a kernel parameter / a stack copy (see g_k2 below for what that costs).
-__constant__ K1Params g_k1;
-__shared__ DevCatalog g_k1cat;
-
-// One row's feasibility against every (template, column): the rarely taken path of feasibility_kernel (rows that differ
-// from their predecessor), kept out of line so that the batched streaming loop stays small.
-__device__ __noinline__ unsigned long long k1_compute_row(int j, uint64_t word, uint32_t* cache, bool cacheable) {
-  const DevCatalog& c = g_k1cat;
-  const K1Params& p = g_k1;
-  const int lane = threadIdx.x & 31;
-  const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
-  const int wpl = (W32 + 31) >> 5;
-    const uint64_t meta = __shfl_sync(0xffffffffu, word, 24);
-    const uint64_t tolerated = __shfl_sync(0xffffffffu, word, 25);
-    const uint32_t pod_res_present = (uint32_t)__shfl_sync(0xffffffffu, word, 28);
-    const uint32_t itype_req = (uint32_t)__shfl_sync(0xffffffffu, word, 29);
-    unsigned long long best = kNoBest;
-    for (int v = 0; v < V; ++v) {
-      const ksched_template& tm = c.templates[v];
-      uint32_t* out = p.F + ((size_t)j * V + v) * W32;
-      bool ok = (tolerated >> tm.taintset) & 1;  // Taints.Tolerates
-      // lanes 8..23 own one requirement key each: Compatible + merge (node.go:73-81 on a fresh node)
-      uint64_t allowed = 0;
-      bool neg = false, present = false, compat = true;
-      const int k = lane - 8;
-      if (k >= 0 && k < NK) {
-        Req pod;
-        pod.present = (meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
-        pod.complement = (meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1;
-        pod.has_gt = pod.has_lt = false; pod.gt = pod.lt = 0;
-        pod.values = word;
-        Req node = ksched::req_load(tm.reqs, nullptr, k);
-        KeyMeta km = key_meta(c, k);
-        compat = ksched::key_compatible(node, pod, c.keys[k].well_known != 0, km);
-        Req merged = ksched::key_add(node, pod, km);
-        present = merged.present;
-        if (present) {
-          allowed = ksched::req_allowed(merged, c.keys[k].dict_mask, km);
-          neg = ksched::req_op_negative(merged);
-        }
-      }
-      ok = ok && (__ballot_sync(0xffffffffu, !compat) == 0);
-      const uint32_t present_keys = (__ballot_sync(0xffffffffu, present) >> 8) & c.type_relevant;
-      // resources: lanes 0..7 own one resource each (Fits, resources.go:138-145)
-      int rank = 0;
-      bool res_used = false;
-      if (lane < R) {
-        uint32_t pres = pod_res_present | tm.daemon_res_present;
-        res_used = (pres >> lane) & 1;
-        if (res_used) rank = fit_rank(c.alloc_sorted, T, lane, (int64_t)word + tm.daemon_requests[lane]);
-      }
-      const uint32_t res_mask = __ballot_sync(0xffffffffu, res_used);
-      uint64_t zallowed = 0xFFFF, callowed = 0xF;
-      bool zc_unconstrained = true;
-      if (c.zone_key >= 0) {
-        bool zp = __shfl_sync(0xffffffffu, (int)present, 8 + c.zone_key);
-        uint64_t za = __shfl_sync(0xffffffffu, allowed, 8 + c.zone_key);
-        if (zp) { zallowed = za; zc_unconstrained = false; }
-      }
-      if (c.ct_key >= 0) {
-        bool cp = __shfl_sync(0xffffffffu, (int)present, 8 + c.ct_key);
-        uint64_t ca = __shfl_sync(0xffffffffu, allowed, 8 + c.ct_key);
-        if (cp) { callowed = ca; zc_unconstrained = false; }
-      }
-      bool any = false;
-      int first_word = -1;
-      uint32_t first_bits = 0;
-      for (int wi = 0; wi < wpl; ++wi) {
-        const int w = wi * 32 + lane;
-        const bool mine = w < W32 && w >= p.word_begin && w < p.word_end;
-        uint32_t s = 0;
-        if (ok && mine) s = c.member[(size_t)v * W32 + w];
-        uint32_t pk = present_keys;
-        while (pk) {  // uniform loop: every lane walks the same keys
-          int kk = __ffs(pk) - 1;
-          pk &= pk - 1;
-          uint64_t a = __shfl_sync(0xffffffffu, allowed, 8 + kk);
-          bool ng = __shfl_sync(0xffffffffu, (int)neg, 8 + kk);
-          if (s) s &= key_typeset_word(c, kk, a, ng, w);
-        }
-        if (s) s &= offer_word(c, (uint32_t)zallowed, (uint32_t)callowed, zc_unconstrained, w);
-        uint32_t rm = res_mask, fit = 0xFFFFFFFFu;
-        while (rm) {  // the loads do not depend on each other (nor on s): one memory round trip for all resources
-          int r = __ffs(rm) - 1;
-          rm &= rm - 1;
-          int rk = __shfl_sync(0xffffffffu, rank, r);
-          if (w < W32) fit &= c.fitset[((size_t)r * (T + 1) + rk) * W32 + w];
-        }
-        s &= fit;
-        if (s && itype_req != KSCHED_NONE) s &= p.itype_sets[(size_t)itype_req * W32 + w];
-        if (mine) out[w] = s;
-        if (cacheable) cache[v * wpl + wi] = s;
-        uint32_t nz = __ballot_sync(0xffffffffu, s != 0);
-        if (nz && !any) {
-          any = true;
-          int src = __ffs(nz) - 1;
-          first_word = wi * 32 + src;
-          first_bits = __shfl_sync(0xffffffffu, s, src);
-        }
-      }
-      if (any) {
-        int t = first_word * 32 + __ffs(first_bits) - 1;  // columns are in price order: first set bit = cheapest
-        unsigned long long key = ((unsigned long long)__float_as_uint(c.price32[t]) << 32) | ((unsigned long long)v << 24) | (unsigned)t;
-        best = key < best ? key : best;
-      }
-    }
-  return best;
-}
-
-
-constexpr int kK1Threads = 512;
-constexpr int kK1Cache = 16;  // per-lane words of the previous row's result kept for identical consecutive rows
-
-struct K1Params;
-
-// Shared-memory staging: the small tables every row evaluation walks with DEPENDENT loads (templates, key info, the
-// value->row maps, the sorted allocatable arrays of the Fits binary search) are copied once per CTA; the wide column
-// bitsets (valset / fitset / member / offset) stay in global memory and are read one coalesced word per lane.
-// Each warp owns a CONTIGUOUS chunk of the FFD-ordered pod-row matrix: consecutive rows are very often identical in
-// every field that matters to feasibility (same deployment), and then the previous result is written out again.
-__global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel() {
-  extern __shared__ __align__(16) unsigned char k1_smem[];
-#ifdef KSCHED_PROFILE_K1
-  long long t_start = clock64(), t_stage = 0, t_compute = 0, n_compute = 0;
-#endif
-  const K1Params& p = g_k1;
-  DevCatalog c = p.cat;
-  const int V = c.n_templates, W32 = c.W32, NK = c.n_keys, R = c.n_res, T = c.n_types;
-  {
-    unsigned char* ptr = k1_smem;
-    ksched_template* s_tmpl = reinterpret_cast<ksched_template*>(ptr); ptr += sizeof(ksched_template) * V;
-    ksched_keyinfo* s_keys = reinterpret_cast<ksched_keyinfo*>(ptr); ptr += sizeof(ksched_keyinfo) * KSCHED_MAX_KEYS;
-    int64_t* s_alloc = reinterpret_cast<int64_t*>(ptr); ptr += p.alloc_in_smem ? sizeof(int64_t) * R * T : 0;
-    int16_t* s_valrow = reinterpret_cast<int16_t*>(ptr); ptr += sizeof(int16_t) * KSCHED_MAX_KEYS * 64;
-    int16_t* s_offrow = reinterpret_cast<int16_t*>(ptr);
-    // cp.async (LDGSTS): every 4-byte element of every table is requested before anything is waited on, so the whole
-    // staging costs about one memory round trip instead of one per table.
-    auto stage4 = [&](void* dst, const void* src, int n_words) {
-      const uint32_t* g = reinterpret_cast<const uint32_t*>(src);
-      int done = 0;
-      if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {  // 16-byte copies for the aligned bulk (4x fewer requests)
-        const int n16 = n_words >> 2;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) {
-          const unsigned d = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(dst) + 4 * i);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g + 4 * i));
-        }
-        done = n16 << 2;
-      }
-      for (int i = done + threadIdx.x; i < n_words; i += blockDim.x) {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(dst) + i);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g + i));
-      }
-    };
-    stage4(s_tmpl, c.templates, (int)(sizeof(ksched_template) * V / 4));
-    stage4(s_keys, c.keys, (int)(sizeof(ksched_keyinfo) * NK / 4));
-    if (p.alloc_in_smem) stage4(s_alloc, c.alloc_sorted, R * T * 2);
-    stage4(s_valrow, c.valrow, NK * 64 / 2);
-    stage4(s_offrow, c.offrow, 32);
-    if (p.tables_in_smem) {
-      // the narrow column bitsets: one 4*W32-byte row per (key,value) / key / offering / template
-      uint32_t* sp = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_offrow) + sizeof(int16_t) * 64);
-      auto stage = [&](const uint32_t*& tbl, int rows) {
-        stage4(sp, tbl, rows * W32);
-        tbl = sp;
-        sp += rows * W32;
-      };
-      stage(c.valset, p.n_valrows);
-      stage(c.absent, NK);
-      stage(c.negempty, NK);
-      stage(c.offset, p.n_offrows);
-      stage(c.anyoffer, 1);
-      stage(c.member, V);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    c.templates = s_tmpl;
-    c.keys = s_keys;
-    if (p.alloc_in_smem) c.alloc_sorted = s_alloc;
-    c.valrow = s_valrow;
-    c.offrow = s_offrow;
-    if (threadIdx.x == 0) g_k1cat = c;
-  }
-  __syncthreads();
-#ifdef KSCHED_PROFILE_K1
-  t_stage = clock64() - t_start;
-#endif
-
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int chunk = (p.n_pods + nwarps - 1) / nwarps;
-  const int j0 = warp * chunk, j1 = min(p.n_pods, j0 + chunk);
-  const int wpl = (W32 + 31) >> 5;  // column words per lane
-  const bool cacheable = V * wpl <= kK1Cache;
-  // fields of the row that feasibility depends on (requests, requirement masks, meta, tolerations, res_present, itype_req)
-  const uint64_t cmp_mask = lane <= 25 ? ~0ull : ((lane == 28 || lane == 29) ? 0xFFFFFFFFull : 0ull);
-  uint32_t cache[kK1Cache];
-  unsigned long long best_prev = kNoBest;
-  uint64_t prev_word = 0;
-  bool have_prev = false;
-
-  // rows are fetched kBatch at a time (kBatch independent 256-byte loads in flight per warp), then consumed in order
-  constexpr int kBatch = 16;
-  uint64_t wbuf[kBatch];
-  for (int jb = j0; jb < j1; jb += kBatch) {
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) wbuf[b] = jb + b < j1 ? __ldg(p.rows + (size_t)(jb + b) * KSCHED_ROW_WORDS + lane) : 0;
-    if (have_prev && cacheable) {
-      // the usual case: the whole batch repeats the cached row (same deployment) -> one vote, then nothing but stores
-      uint64_t diff = 0;
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) diff |= jb + b < j1 ? ((wbuf[b] ^ prev_word) & cmp_mask) : 0;
-      if (__all_sync(0xffffffffu, diff == 0)) {
-        const int nb = min(kBatch, j1 - jb);
-        const size_t row_stride = (size_t)V * W32;
-        for (int v = 0; v < V; ++v)
-          for (int wi = 0; wi < wpl; ++wi) {
-            const int w = wi * 32 + lane;
-            if (w < W32 && w >= p.word_begin && w < p.word_end) {
-              const uint32_t val = cache[v * wpl + wi];
-              uint32_t* dst = p.F + ((size_t)jb * V + v) * W32 + w;
-              for (int b = 0; b < nb; ++b, dst += row_stride) *dst = val;
-            }
-          }
-        if (lane < nb) p.best[jb + lane] = best_prev;
-        continue;
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-    const int j = jb + b;
-    if (j >= j1) break;
-    const uint64_t word = wbuf[b];  // lane l holds u64 word l of the 256-byte row
-    const bool same = have_prev && cacheable && __all_sync(0xffffffffu, ((word ^ prev_word) & cmp_mask) == 0);
-    if (same) {
-      for (int v = 0; v < V; ++v)
-        for (int wi = 0; wi < wpl; ++wi) {
-          const int w = wi * 32 + lane;
-          if (w < W32 && w >= p.word_begin && w < p.word_end) p.F[((size_t)j * V + v) * W32 + w] = cache[v * wpl + wi];
-        }
-      if (lane == 0) p.best[j] = best_prev;
-      continue;
-    }
-    prev_word = word;
-    have_prev = true;
-#ifdef KSCHED_PROFILE_K1
-    long long tc0 = clock64();
-#endif
-    const unsigned long long best = k1_compute_row(j, word, cache, cacheable);
-#ifdef KSCHED_PROFILE_K1
-    t_compute += clock64() - tc0; ++n_compute;
-#endif
-    best_prev = best;
-    if (lane == 0) p.best[j] = best;
-    }
-  }
-#ifdef KSCHED_PROFILE_K1
-  if (p.dbg && lane == 0) {
-    atomicMax((unsigned long long*)&p.dbg[0], (unsigned long long)t_stage);
-    atomicMax((unsigned long long*)&p.dbg[1], (unsigned long long)t_compute);
-    atomicMax((unsigned long long*)&p.dbg[2], (unsigned long long)(clock64() - t_start));
-    atomicMax((unsigned long long*)&p.dbg[3], (unsigned long long)n_compute);
-    atomicAdd((unsigned long long*)&p.dbg[4], (unsigned long long)n_compute);
-    atomicAdd((unsigned long long*)&p.dbg[5], (unsigned long long)t_compute);
-  }
-#endif
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2: pack
-// ------------------------------------------------------------------------------------------------
-// One (class, group) relation with the group's immutable fields folded in (built at upload): everything
-// Topology.Record and the per-step topology build need about the relation arrives with ONE load.
-struct RelX {
-  uint32_t group, flags;
-  uint8_t key, type, has_filter, pad;
-  int32_t max_skew;
-  int32_t host_row;
-  uint32_t pad2[3];
-};
-static_assert(sizeof(RelX) == 32, "RelX is loaded as two 16-byte vectors");
-
-struct PackState {
-  const RelX* relx;                  // [n_class_topo], parallel to class_topo
-  // problem (read-only)
-  const ksched_pod_row* classes;
-  const ksched_topo_group* groups;
-  const ksched_class_topo* class_topo;
-  const ksched_reqset* filter_terms;
-  const uint32_t* itype_sets;        // [n][W32]
-  const uint8_t* itype_complement;
-  const int32_t* hostname_reqs;      // [n][2]
-  const uint32_t* order;             // FFD order: queue position -> pod
-  const uint64_t* rows;              // [n_pods][32] dense pod-row matrix in FFD order (K0)
-  uint32_t* pod_pos;                 // pod -> FFD position (row of F / best)
-  int use_F;                         // F / best cover every column on this device (not column-sharded)
-  const uint32_t* F;                 // [n_pods][V][W32] in FFD order (nullptr: compute fresh-node types dynamically)
-  const unsigned long long* best;    // [n_pods] FFD order (after allreduce when sharded) or nullptr
-  int n_pods, n_classes, n_existing, n_groups, max_new;
-  long long min_req[KSCHED_MAX_RES]; // min over all classes of requests[r] (0 if some class lacks r)
-  // mutable
-  uint32_t* pod_class;               // [n_pods] current class
-  int32_t* relax_level;              // [n_pods]
-  int32_t* assign;                   // [n_pods]
-  int32_t* place_seq;                // [n_pods]
-  uint32_t* queue;                   // [n_pods+1] circular
-  int32_t* last_len;                 // [n_pods]
-  uint32_t* last_epoch;              // [n_pods]
-  // existing nodes (SoA)
-  int64_t* ex_req;                   // [8][n_existing]
-  const int64_t* ex_avail;           // [8][n_existing]
-  uint32_t* ex_req_present;
-  const uint32_t* ex_avail_present;
-  uint64_t* ex_vals;                 // [16][n_existing]
-  uint64_t* ex_meta;
-  const uint32_t* ex_taintset;
-  const uint32_t* ex_itype;
-  uint64_t* ex_hp;
-  uint8_t* ex_closed;
-  // new nodes (SoA, capacity max_new)
-  uint8_t* nn_tmpl;
-  int32_t* nn_count;
-  int32_t* nn_tb;
-  int64_t* nn_req;                   // [8][max_new]
-  uint32_t* nn_req_present;
-  uint64_t* nn_vals;                 // [16][max_new]
-  uint64_t* nn_meta;
-  uint32_t* nn_opts;                 // [W32][max_new]
-  uint64_t* nn_hp;
-  // hot state of open nodes beyond the shared-memory window (pack_kernel.cuh: Hot)
-  unsigned long long* ov_key;
-  long long* ov_q;
-  long long* ov_bound;
-  long long* ov_bound2;
-  int* ov_node;
-  unsigned short* ov_flags;
-  unsigned* ov_absorbed;
-  unsigned* ov_rejected;
-  // fresh-node outcome memo per (class, template)
-  uint8_t* fc_state;                 // 0 unknown, 1 cached, 2 cached: no surviving type
-  uint32_t* fc_opts;                 // [n_classes*V][W32]
-  long long* fc_bound;               // [n_classes*V][4]
-  long long* fc_bound2;
-  uint8_t* fc_dom;
-  uint8_t* fc_front_state;           // fc_bound / fc_bound2 / fc_dom hold the front of the K1-row option set
-  uint64_t* fc_vals;                 // [n_classes*V][16] requirement masks of the fresh node
-  uint64_t* fc_meta;
-  long long* fc_q;                   // [n_classes*V][8] requests (daemon overhead + pod)
-  uint32_t* fc_qp;
-  // fresh-node outcome memo for topology-constrained classes: a hash table keyed by (class, template, the new node's
-  // requirement masks) -- the option set of NewNode+Add is a function of exactly those (node.go:62-107) when the
-  // provisioner has no limits. Direct mapped, full tag compare, so a collision only costs a recomputation.
-  int fd_cap;                        // power of two
-  uint8_t* fd_state;                 // 0 empty, 1 options cached, 2 cached: no surviving type
-  uint32_t* fd_fc;                   // tag: class * V + template
-  uint64_t* fd_meta;                 // tag
-  uint64_t* fd_vals;                 // tag [fd_cap][16]
-  uint32_t* fd_opts;                 // [fd_cap][W32]
-  long long* fd_bound;               // [fd_cap][4]
-  long long* fd_bound2;
-  uint8_t* fd_dom;
-  int count_visited;                 // keep the exact nodes_visited statistic (costs a pass over all in-flight nodes per pod)
-  int alloc_in_smem;
-  // topology counters
-  int32_t* grp_cnt;                  // [n_groups][64]
-  uint64_t* grp_registered;          // [n_groups]
-  uint16_t* grp_host;                // [n_hostgroups][n_existing+max_new]
-  const int32_t* grp_host_row;       // [n_groups] row in grp_host or -1
-  int32_t* grp_host_total;           // [n_groups] schedulable-slot domains with count > 0 (+ extra_nonzero_domains)
-  uint8_t* grp_active;               // [n_groups] 0 while a relaxation-created group does not exist yet (topology.go:86-117)
-  int32_t* grp_min_slot;             // [n_groups] hostname slots below this were never Register()ed with the group
-  int64_t* remaining;                // [V][8] provisioner limits
-  // outputs / counters: [0]=n_new [1]=n_unscheduled [2]=nodes_visited [3]=add_calls [4]=error [5]=steps
-  long long* counters;
-};
-
-struct K2Params {
-  DevCatalog cat;
-  PackState st;
-};
-// The pack kernel and every out-of-line device function it calls read their parameters from constant memory with
-// immediate offsets (a reference to a __grid_constant__ kernel parameter handed to a __noinline__ function degrades every
-// field access to a generic load with ~100 cycles of latency, on a code path that is one dependent chain).
-// One copy per device: run_pack() orders launches of different handles on the same device behind each other.
-__constant__ K2Params g_k2;
-#define KS_K2 const DevCatalog& c = g_k2.cat; const PackState& s = g_k2.st; (void)c; (void)s;
-
-struct Touched {
-  int n;
-  int8_t key[kMaxTouched];
-  Req merged[kMaxTouched];  // node ∩ pod          (node.go:81)
-  Req fin[kMaxTouched];     // ... ∩ topology      (node.go:90)
-  bool changed[kMaxTouched];
-};
-
-struct PodTopo {  // per (pod step, constraining group): node-independent part of TopologyGroup.Get
-  int n;
-  int32_t group[kMaxCG];
-  uint32_t flags[kMaxCG];
-  int32_t min_count[kMaxCG];   // spread: domainMinCount over the pod's domains
-  uint64_t options[kMaxCG];    // affinity / anti-affinity: admissible domains (mask keys)
-  uint8_t bootstrap[kMaxCG];   // affinity: no domain has a matching pod and the pod selects itself
-  uint64_t pod_allowed[kMaxCG]; // pod's own admissible domains for the key
-  // the group's own fields, copied once per step so that the per-node checks read shared memory only
-  uint8_t gkey[kMaxCG], gtype[kMaxCG];
-  int32_t gskew[kMaxCG], host_row[kMaxCG], min_slot[kMaxCG];
-  uint64_t registered[kMaxCG];
-  // spread over a mask key: the registered domains within max-skew, in (count, domain id) order. The domain the
-  // reference picks for a node is the first entry the node's requirement admits (topologygroup.go:157-183).
-  uint8_t n_sorted[kMaxCG];
-  uint8_t sorted[kMaxCG][64];
-  uint64_t ok_mask[kMaxCG];    // the same domains as a set
-  int overflow;
-};
-
-// Per-CTA working set of the pack kernel's generic step, at file scope so that every out-of-line function reaches it with
-// immediate shared-memory addresses instead of pointers handed down the call chain.
-__shared__ ksched_pod_row g_row;  // the pod of the current step (copied from its FFD row / class row by warp 0)
-__shared__ PodTopo g_pt;          // its topology constraints
-#define KS_ROW const ksched_pod_row& row = g_row; (void)row;
-#define KS_PT PodTopo& pt = g_pt; (void)pt;
-
-__device__ __forceinline__ Req load_soa(const uint64_t* vals, uint64_t meta, int stride, int idx, int k) {
-  Req r;
-  r.present = (meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
-  r.complement = (meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1;
-  r.has_gt = r.has_lt = false;
-  r.gt = r.lt = 0;
-  r.values = r.present ? vals[(size_t)k * stride + idx] : 0;
-  return r;
-}
-__device__ __forceinline__ Req pod_req(const ksched_pod_row& row, int k) {
-  Req r;
-  r.present = (row.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
-  r.complement = (row.meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1;
-  r.has_gt = r.has_lt = false;
-  r.gt = r.lt = 0;
-  r.values = row.values[k];
-  return r;
-}
-__device__ __forceinline__ bool req_equal(const Req& a, const Req& b) {
-  return a.present == b.present && a.complement == b.complement && a.values == b.values;
-}
-
-// TopologyGroup.Get for a mask-key group (topologygroup.go:88-243). node_dom = the node's requirement for the
-// key after the pod's own requirements were merged (topology.go:156-159). Returns false when Len()==0.
-__device__ __noinline__ bool topo_domains_mask(int j, const Req& node_dom, uint64_t* out) {
-  KS_K2
-  KS_PT
-  const int k = pt.gkey[j];
-  KeyMeta km = key_meta(c, k);
-  const uint64_t registered = pt.registered[j];
-  const uint64_t node_allowed = node_dom.present ? ksched::req_allowed(node_dom, c.keys[k].dict_mask, km) : c.keys[k].dict_mask;
-  if (pt.gtype[j] == 0) {  // nextDomainTopologySpread: min (count, domain id) among the admissible domains of the node
-    const int ns = pt.n_sorted[j];
-    for (int i = 0; i < ns; ++i) {
-      const int d = pt.sorted[j][i];
-      if ((node_allowed >> d) & 1) { *out = 1ull << d; return true; }
-    }
-    return false;
-  }
-  if (pt.gtype[j] == 1) {  // nextDomainAffinity
-    uint64_t opts = pt.options[j];
-    if (pt.bootstrap[j]) {
-      uint64_t inter = registered & pt.pod_allowed[j] & node_allowed;  // podDomains.Intersection(nodeDomains).Has
-      if (inter) opts |= inter & (~inter + 1);
-      uint64_t pm = registered & pt.pod_allowed[j];
-      if (pm) opts |= pm & (~pm + 1);
-    }
-    if (!opts) return false;
-    *out = opts;
-    return true;
-  }
-  uint64_t opts = pt.options[j];  // nextDomainAntiAffinity
-  if (!opts) return false;
-  *out = opts;
-  return true;
-}
-
-// hostname-key groups: the node's hostname domain is its slot.
-__device__ __noinline__ bool topo_hostname_ok(int j, int slot, bool pod_allows_slot) {
-  KS_K2
-  KS_PT
-  const int stride = s.n_existing + s.max_new;
-  const int32_t cnt = s.grp_host[(size_t)pt.host_row[j] * stride + slot];
-  // a group created by a later Topology.Update only knows hostnames registered after that, plus those it counted pods on
-  if (slot < pt.min_slot[j] && !(slot < s.n_existing && cnt > 0)) return false;
-  const int type = pt.gtype[j];
-  if (type == 0) {  // spread, min is 0 for hostname (topologygroup.go:186-188); candidate = the node's own hostname
-    int64_t c2 = (int64_t)cnt + ((pt.flags[j] & KSCHED_TOPO_SELECTS) ? 1 : 0);
-    return c2 <= (int64_t)pt.gskew[j];
-  }
-  if (type == 1) {  // affinity
-    if (cnt > 0 && pod_allows_slot) return true;
-    if (pt.bootstrap[j]) return pod_allows_slot;  // first loop picks the node's own (registered) hostname
-    return false;
-  }
-  return cnt == 0 && pod_allows_slot;  // anti-affinity
-}
-
-// Does the pod's hostname requirement admit this slot? (requirement on kubernetes.io/hostname, never well-known)
-__device__ __forceinline__ bool hostname_allows(const PackState& s, const ksched_pod_row& row, int slot, bool is_existing) {
-  if (row.hostname_req == KSCHED_NONE) return true;
-  const int32_t comp = s.hostname_reqs[row.hostname_req * 2], target = s.hostname_reqs[row.hostname_req * 2 + 1];
-  const bool same = is_existing && target == slot;
-  return comp ? !same : same;
-}
-
-// Requirement phase of Node.Add / ExistingNode.Add: Compatible(pod) + merge, topology tighten + Compatible + merge.
-// vals/meta/stride/idx describe the node's requirement set. Returns false on reject.
-__device__ __noinline__ bool requirements_phase(const uint64_t* vals, uint64_t meta, int stride, int idx, int slot, bool is_existing, Touched& t) {
-  KS_K2
-  KS_ROW KS_PT
-  t.n = 0;
-  if (!hostname_allows(s, row, slot, is_existing)) return false;
-  uint32_t podkeys = (uint32_t)(row.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF;
-  while (podkeys) {
-    int k = __ffs(podkeys) - 1;
-    podkeys &= podkeys - 1;
-    Req node = load_soa(vals, meta, stride, idx, k);
-    Req pod = pod_req(row, k);
-    KeyMeta km = key_meta(c, k);
-    if (!ksched::key_compatible(node, pod, c.keys[k].well_known != 0, km)) return false;
-    if (t.n >= kMaxTouched) return false;
-    Req merged = ksched::key_add(node, pod, km);
-    t.key[t.n] = (int8_t)k;
-    t.merged[t.n] = merged;
-    t.fin[t.n] = merged;
-    t.changed[t.n] = !req_equal(merged, node);
-    ++t.n;
-  }
-  for (int j = 0; j < pt.n; ++j) {
-    if (pt.gkey[j] == KSCHED_KEY_HOSTNAME) {
-      if (!topo_hostname_ok(j, slot, hostname_allows(s, row, slot, is_existing))) return false;
-      continue;
-    }
-    const int k = pt.gkey[j];
-    int ti = -1;
-    for (int i = 0; i < t.n; ++i) if (t.key[i] == k) ti = i;
-    if (ti < 0) {
-      if (t.n >= kMaxTouched) return false;
-      ti = t.n++;
-      Req node = load_soa(vals, meta, stride, idx, k);
-      t.key[ti] = (int8_t)k;
-      t.merged[ti] = node;
-      t.fin[ti] = node;
-      t.changed[ti] = false;
-    }
-    uint64_t dom;
-    if (!topo_domains_mask(j, t.merged[ti], &dom)) return false;
-    Req d{dom, 0, 0, true, false, false, false};
-    KeyMeta km = key_meta(c, k);
-    t.fin[ti] = ksched::key_add(t.fin[ti], d, km);  // requirements.Add(domains) topology.go:164
-  }
-  // nodeRequirements.Compatible(topologyRequirements) node.go:87 — only topology keys can differ
-  for (int i = 0; i < t.n; ++i) {
-    if (req_equal(t.fin[i], t.merged[i])) continue;
-    const int k = t.key[i];
-    if (!ksched::key_compatible(t.merged[i], t.fin[i], c.keys[k].well_known != 0, key_meta(c, k))) return false;
-    t.fin[i] = ksched::key_add(t.merged[i], t.fin[i], key_meta(c, k));
-    t.changed[i] = true;
-  }
-  return true;
-}
-
-// Surviving instance types of a node for one word (filterInstanceTypesByRequirements node.go:137-141):
-// previous options ∧ Fits ∧ (keys whose requirement changed) ∧ hasOffering (if zone / capacity-type changed).
-struct TypeCtx {
-  int rank[KSCHED_MAX_RES];
-  uint32_t res_mask;
-  int nkeys;
-  int8_t key[KSCHED_MAX_KEYS];
-  uint64_t allowed[KSCHED_MAX_KEYS];
-  bool neg[KSCHED_MAX_KEYS];
-  bool offer_needed, offer_unconstrained;
-  uint32_t zmask, cmask;
-  uint32_t itype_req;
-};
-__device__ __noinline__ void build_type_ctx(const Touched& t, const long long* q,
-                               uint32_t q_present, const uint64_t* vals, uint64_t meta, int stride, int idx, bool fresh,
-                               const int64_t* alloc_sorted, TypeCtx& x, bool with_ranks = true) {
-  KS_K2
-  KS_ROW
-  x.res_mask = q_present;
-  if (with_ranks)
-    for (int r = 0; r < c.n_res; ++r) x.rank[r] = ((q_present >> r) & 1) ? fit_rank(alloc_sorted, c.n_types, r, q[r]) : 0;
-  x.nkeys = 0;
-  x.offer_needed = fresh;
-  auto add_key = [&](int k, const Req& f) {
-    if (!((c.type_relevant >> k) & 1) || !f.present) return;
-    KeyMeta km = key_meta(c, k);
-    x.key[x.nkeys] = (int8_t)k;
-    x.allowed[x.nkeys] = ksched::req_allowed(f, c.keys[k].dict_mask, km);
-    x.neg[x.nkeys] = ksched::req_op_negative(f);
-    ++x.nkeys;
-  };
-  if (fresh) {
-    // every key of the new node's requirement set is evaluated from scratch
-    uint32_t done = 0;
-    for (int i = 0; i < t.n; ++i) { add_key(t.key[i], t.fin[i]); done |= 1u << t.key[i]; }
-    uint32_t rest = ((uint32_t)(meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) & ~done;
-    while (rest) {
-      int k = __ffs(rest) - 1;
-      rest &= rest - 1;
-      add_key(k, load_soa(vals, meta, stride, idx, k));
-    }
-  } else {
-    for (int i = 0; i < t.n; ++i) {
-      if (!t.changed[i]) continue;
-      add_key(t.key[i], t.fin[i]);
-      if (t.key[i] == c.zone_key || t.key[i] == c.ct_key) x.offer_needed = true;
-    }
-  }
-  x.zmask = 0xFFFF; x.cmask = 0xF; x.offer_unconstrained = true;
-  if (x.offer_needed) {
-    auto final_req = [&](int k) -> Req {
-      for (int i = 0; i < t.n; ++i) if (t.key[i] == k) return t.fin[i];
-      return load_soa(vals, meta, stride, idx, k);
-    };
-    if (c.zone_key >= 0) {
-      Req z = final_req(c.zone_key);
-      if (z.present) { x.zmask = (uint32_t)ksched::req_allowed(z, c.keys[c.zone_key].dict_mask, key_meta(c, c.zone_key)); x.offer_unconstrained = false; }
-    }
-    if (c.ct_key >= 0) {
-      Req ct = final_req(c.ct_key);
-      if (ct.present) { x.cmask = (uint32_t)ksched::req_allowed(ct, c.keys[c.ct_key].dict_mask, key_meta(c, c.ct_key)); x.offer_unconstrained = false; }
-    }
-  }
-  x.itype_req = row.itype_req;
-}
-// resource part (Fits) and requirement part (keys / offerings / instance-type requirement) of the per-word filter
-__device__ __forceinline__ uint32_t type_word_res(const DevCatalog& c, const TypeCtx& x, uint32_t sw, int w) {
-  uint32_t rm = x.res_mask;
-  while (sw && rm) {
-    int r = __ffs(rm) - 1;
-    rm &= rm - 1;
-    sw &= c.fitset[((size_t)r * (c.n_types + 1) + x.rank[r]) * c.W32 + w];
-  }
-  return sw;
-}
-__device__ __forceinline__ uint32_t type_word_keys(const DevCatalog& c, const PackState& s, const TypeCtx& x, uint32_t sw, int w) {
-  for (int i = 0; i < x.nkeys && sw; ++i) sw &= key_typeset_word(c, x.key[i], x.allowed[i], x.neg[i], w);
-  if (sw && x.offer_needed) sw &= offer_word(c, x.zmask, x.cmask, x.offer_unconstrained, w);
-  if (sw && x.itype_req != KSCHED_NONE) sw &= s.itype_sets[(size_t)x.itype_req * c.W32 + w];
-  return sw;
-}
-__device__ __forceinline__ uint32_t type_word(const DevCatalog& c, const PackState& s, const TypeCtx& x, uint32_t base, int w) {
-  return type_word_keys(c, s, x, type_word_res(c, x, base, w), w);
-}
-
-// Node-independent part of the pod's topology constraints for this step, one constraining (class, group) relation j.
-// Static half: what the relation and its group are (a function of the pod class only).
-__device__ __forceinline__ void fill_pod_topo_static(const RelX& x, PodTopo& pt, int j) {
-  pt.group[j] = (int)x.group;
-  pt.flags[j] = x.flags;
-  pt.gkey[j] = x.key;
-  pt.gtype[j] = x.type;
-  pt.gskew[j] = x.max_skew;
-  pt.host_row[j] = x.host_row;
-}
-// Dynamic half: everything derived from the group's counters, re-read every step.
-__device__ __noinline__ void fill_pod_topo_dynamic(int j) {
-  KS_K2
-  KS_ROW KS_PT
-  const int gi = pt.group[j];
-  const uint32_t flags = pt.flags[j];
-  const int gkey = pt.gkey[j], gtype = pt.gtype[j], gskew = pt.gskew[j];
-  pt.min_count[j] = 0;
-  pt.options[j] = 0;
-  pt.bootstrap[j] = 0;
-  pt.pod_allowed[j] = 0;
-  pt.min_slot[j] = s.grp_min_slot[gi];
-  pt.registered[j] = 0;
-  pt.n_sorted[j] = 0;
-  pt.ok_mask[j] = 0;
-  if (gkey == KSCHED_KEY_HOSTNAME) {
-    if (gtype == 1) {
-      // options.Len()==0 <=> no admissible hostname has a matching pod (hostname requirements on the pod are
-      // restricted to a single existing slot, handled in topo_hostname_ok)
-      pt.bootstrap[j] = (s.grp_host_total[gi] == 0) && (flags & KSCHED_TOPO_SELECTS);
-    }
-    return;
-  }
-  const int k = gkey;
-  KeyMeta km = key_meta(c, k);
-  Req pd = pod_req(row, k);
-  const uint64_t pod_allowed = pd.present ? ksched::req_allowed(pd, c.keys[k].dict_mask, km) : c.keys[k].dict_mask;
-  pt.pod_allowed[j] = pod_allowed;
-  const uint64_t registered = s.grp_registered[gi];
-  pt.registered[j] = registered;
-  uint64_t m = registered & pod_allowed;
-  if (gtype == 0) {
-    // counts of every registered domain, loaded once (independent loads), ids in ascending order
-    int32_t cnts[64];
-    uint8_t ids[64];
-    int nd = 0;
-    for (uint64_t all = registered; all; all &= all - 1) {
-      const int d = __ffsll((long long)all) - 1;
-      ids[nd] = (uint8_t)d;
-      cnts[nd] = s.grp_cnt[(size_t)gi * 64 + d];
-      ++nd;
-    }
-    int32_t mn = INT32_MAX;  // domainMinCount over the pod's own domains (topologygroup.go:186-203)
-    for (int i = 0; i < nd; ++i)
-      if (((m >> ids[i]) & 1) && cnts[i] < mn) mn = cnts[i];
-    pt.min_count[j] = mn;
-    // registered domains within the skew bound, insertion-sorted by (count, id)
-    const int self = (flags & KSCHED_TOPO_SELECTS) ? 1 : 0;
-    int ns = 0;
-    int32_t sc[64];
-    uint64_t okm = 0;
-    for (int i = 0; i < nd; ++i) {
-      const int64_t cnt = (int64_t)cnts[i] + self;
-      if (cnt - (int64_t)mn > (int64_t)gskew) continue;
-      okm |= 1ull << ids[i];
-      int q = ns++;
-      while (q > 0 && sc[q - 1] > (int32_t)cnt) { sc[q] = sc[q - 1]; pt.sorted[j][q] = pt.sorted[j][q - 1]; --q; }
-      sc[q] = (int32_t)cnt;
-      pt.sorted[j][q] = ids[i];
-    }
-    pt.n_sorted[j] = (uint8_t)ns;
-    pt.ok_mask[j] = okm;
-  } else if (gtype == 1) {
-    uint64_t opts = 0;
-    while (m) {
-      int d = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      if (s.grp_cnt[(size_t)gi * 64 + d] > 0) opts |= 1ull << d;
-    }
-    pt.options[j] = opts;
-    pt.bootstrap[j] = (opts == 0) && (flags & KSCHED_TOPO_SELECTS);
-  } else {
-    uint64_t opts = 0;
-    while (m) {
-      int d = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      if (s.grp_cnt[(size_t)gi * 64 + d] == 0) opts |= 1ull << d;
-    }
-    pt.options[j] = opts;
-  }
-}
-
-// Called by the 32 lanes of warp 0: one (class, group) relation per lane, constraining ones compacted in order.
-__device__ void build_pod_topo() {
-  KS_K2
-  KS_ROW KS_PT
-  const int lane = threadIdx.x & 31;
-  const uint32_t begin = row.topo_begin, end = row.topo_end;
-  int n = 0, overflow = 0;
-  for (uint32_t base = begin; base < end; base += 32) {  // uniform trip count
-    const uint32_t e = base + lane;
-    RelX x{};
-    if (e < end) x = s.relx[e];
-    const bool cons = e < end && (x.flags & KSCHED_TOPO_CONSTRAINS);
-    const unsigned bal = __ballot_sync(0xffffffffu, cons);
-    const int j = n + __popc(bal & ((1u << lane) - 1));
-    if (cons && j < kMaxCG) {
-      fill_pod_topo_static(x, pt, j);
-      fill_pod_topo_dynamic(j);
-    }
-    n += __popc(bal);
-    if (n > kMaxCG) { overflow = 1; n = kMaxCG; }
-  }
-  if (lane == 0) { pt.n = n; pt.overflow = overflow; }
-}
-// The previous step's pod had the same class: the relations are the same, only the counters moved.
-__device__ void refresh_pod_topo() {
-  KS_K2
-  KS_ROW KS_PT
-  const int lane = threadIdx.x & 31;
-  if (lane < pt.n) fill_pod_topo_dynamic(lane);
-}
-
-// A NECESSARY condition of requirements_phase for an in-flight node, cheap enough to run on every candidate: the
-// hostname groups exactly, spread groups over mask keys through the set of admissible domains. The node that wins the
-// argmin is then checked in full (and excluded if it fails).
-__device__ __forceinline__ bool topo_prefilter(const uint64_t* vals, uint64_t meta,
-                                               int stride, int idx, int slot) {
-  KS_K2
-  KS_PT
-  for (int j = 0; j < pt.n; ++j) {
-    const int k = pt.gkey[j];
-    if (k == KSCHED_KEY_HOSTNAME) {
-      if (!topo_hostname_ok(j, slot, true)) return false;
-      continue;
-    }
-    if (pt.gtype[j] != 0) {
-      if (!pt.options[j] && !pt.bootstrap[j]) return false;
-      continue;
-    }
-    const Req node = load_soa(vals, meta, stride, idx, k);
-    const uint64_t node_allowed = node.present ? ksched::req_allowed(node, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask;
-    if (!(node_allowed & pt.ok_mask[j])) return false;
-  }
-  return true;
-}
-
-// TopologyNodeFilter.MatchesRequirements (topologynodefilter.go:57-70): any term Compatible with the node requirements
-__device__ __noinline__ bool filter_matches(const ksched_topo_group& g, const uint64_t* vals, uint64_t meta,
-                               int stride, int idx) {
-  KS_K2
-  if (g.filter_begin == g.filter_end) return true;
-  for (uint32_t f = g.filter_begin; f < g.filter_end; ++f) {
-    const ksched_reqset& term = s.filter_terms[f];
-    bool ok = true;
-    uint32_t keys = (uint32_t)(term.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF;
-    while (keys && ok) {
-      int k = __ffs(keys) - 1;
-      keys &= keys - 1;
-      Req node = load_soa(vals, meta, stride, idx, k);
-      Req inc = ksched::req_load(term, nullptr, k);
-      ok = ksched::key_compatible(node, inc, c.keys[k].well_known != 0, key_meta(c, k));
-    }
-    if (ok) return true;
-  }
-  return false;
-}
-
-// Topology.Record (topology.go:120-143) for ONE (class, group) relation, after the node's requirements were committed.
-// Relations of one class name distinct groups, so different threads may record different relations concurrently.
-__device__ __noinline__ void topo_record_entry(uint32_t e, const uint64_t* vals, uint64_t meta, int stride, int idx, int slot) {
-  KS_K2
-  const int hstride = s.n_existing + s.max_new;
-  const RelX x = s.relx[e];
-  const int gi = (int)x.group;
-  if (!(x.flags & (KSCHED_TOPO_RECORDS | KSCHED_TOPO_RECORDS_INVERSE))) return;
-  // the loads the record needs are issued together (one memory round trip, not three)
-  const uint8_t active = s.grp_active[gi];
-  uint16_t* const host_cell = x.key == KSCHED_KEY_HOSTNAME ? &s.grp_host[(size_t)x.host_row * hstride + slot] : nullptr;
-  const uint32_t host_old = host_cell ? *host_cell : 0;
-  const int32_t host_total = host_cell ? s.grp_host_total[gi] : 0;
-  if (!active) return;  // the group does not exist yet
-  bool rec = false, all_values = false;
-  if (x.flags & KSCHED_TOPO_RECORDS) {
-    if (!x.has_filter || filter_matches(s.groups[gi], vals, meta, stride, idx)) { rec = true; all_values = (x.type == 2); }
-  }
-  const bool rec_inv = (x.flags & KSCHED_TOPO_RECORDS_INVERSE) != 0;
-  if (x.key == KSCHED_KEY_HOSTNAME) {  // the node's hostname requirement is always In [its own hostname]
-    const int times = (rec ? 1 : 0) + (rec_inv ? 1 : 0);
-    if (!times) return;
-    if (host_old == 0) s.grp_host_total[gi] = host_total + 1;
-    const uint32_t now = host_old + times;
-    *host_cell = (uint16_t)(now > 0xFFFF ? 0xFFFF : now);
-    return;
-  }
-  for (int pass = 0; pass < 2; ++pass) {
-    const bool doit = pass == 0 ? rec : rec_inv;
-    const bool allv = pass == 0 ? all_values : true;
-    if (!doit) continue;
-    Req r = load_soa(vals, meta, stride, idx, x.key);
-    uint64_t v = 0;
-    if (allv) v = r.present ? r.values : 0;  // domains.Values(): members, or the excluded set of a complement
-    else if (r.present && ksched::req_len_one(r)) v = r.values;
-    while (v) {
-      int d = __ffsll((long long)v) - 1;
-      v &= v - 1;
-      s.grp_cnt[(size_t)gi * 64 + d]++;
-      s.grp_registered[gi] |= 1ull << d;
-    }
-  }
-}
-// every thread of the CTA: relation tid, tid + blockDim, ... (the commit this records must be visible: call after a barrier)
-__device__ __forceinline__ void topo_record_block(const uint64_t* vals, uint64_t meta,
-                                                  int stride, int idx, int slot) {
-  KS_K2
-  KS_ROW
-  for (uint32_t e = row.topo_begin + threadIdx.x; e < row.topo_end; e += blockDim.x) topo_record_entry(e, vals, meta, stride, idx, slot);
-}
+#include "catalog.cuh"
+#include "feasibility_kernel.cuh"
+#include "topology.cuh"
 
 }  // namespace
 
