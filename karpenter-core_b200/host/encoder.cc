@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -170,28 +171,33 @@ std::string term_key(const PodAffinityTerm& t) {
 
 // Everything the scheduler can observe about a pod except its identity (uid / name / timestamp).
 std::string class_key(const Pod& p, const ResourceList& req) {
-  std::string s = "ns=" + p.ns + "|L=" + labels_key(p.labels) + "|R=";
-  for (auto& kv : req) s += kv.first + ":" + std::to_string(kv.second) + ",";
-  s += "|S=" + labels_key(p.node_selector) + "|NA=" + std::to_string(p.has_node_affinity) + std::to_string(p.has_required_node_affinity);
-  for (auto& t : p.required_node_terms) s += "[" + reqs_key(t) + "]";
+  // built by appending in place (no temporaries): this runs once per pod of the batch
+  std::string s;
+  s.reserve(256);
+  auto num = [&](long long v) { char b[24]; int n = std::snprintf(b, sizeof b, "%lld", v); s.append(b, (size_t)n); };
+  s += "ns="; s += p.ns; s += "|L="; s += labels_key(p.labels); s += "|R=";
+  for (auto& kv : req) { s += kv.first; s += ':'; num(kv.second); s += ','; }
+  s += "|S="; s += labels_key(p.node_selector); s += "|NA="; num(p.has_node_affinity); num(p.has_required_node_affinity);
+  for (auto& t : p.required_node_terms) { s += '['; s += reqs_key(t); s += ']'; }
   s += "|NP=";
-  for (auto& t : p.preferred_node_terms) s += std::to_string(t.weight) + "[" + reqs_key(t.preference) + "]";
+  for (auto& t : p.preferred_node_terms) { num(t.weight); s += '['; s += reqs_key(t.preference); s += ']'; }
   s += "|PA=";
-  for (auto& t : p.pod_affinity_required) s += "(" + term_key(t) + ")";
+  for (auto& t : p.pod_affinity_required) { s += '('; s += term_key(t); s += ')'; }
   s += "|PAP=";
-  for (auto& t : p.pod_affinity_preferred) s += std::to_string(t.weight) + "(" + term_key(t.term) + ")";
+  for (auto& t : p.pod_affinity_preferred) { num(t.weight); s += '('; s += term_key(t.term); s += ')'; }
   s += "|PAA=";
-  for (auto& t : p.pod_anti_affinity_required) s += "(" + term_key(t) + ")";
+  for (auto& t : p.pod_anti_affinity_required) { s += '('; s += term_key(t); s += ')'; }
   s += "|PAAP=";
-  for (auto& t : p.pod_anti_affinity_preferred) s += std::to_string(t.weight) + "(" + term_key(t.term) + ")";
+  for (auto& t : p.pod_anti_affinity_preferred) { num(t.weight); s += '('; s += term_key(t.term); s += ')'; }
   s += "|TS=";
-  for (auto& t : p.topology_spread)
-    s += std::to_string(t.max_skew) + ":" + t.topology_key + ":" + std::to_string(t.schedule_anyway) + ":" + selector_key(t.selector) + ";";
+  for (auto& t : p.topology_spread) {
+    num(t.max_skew); s += ':'; s += t.topology_key; s += ':'; num(t.schedule_anyway); s += ':'; s += selector_key(t.selector); s += ';';
+  }
   s += "|T=";
-  for (auto& t : p.tolerations) s += t.key + ":" + t.op + ":" + t.value + ":" + t.effect + ";";
+  for (auto& t : p.tolerations) { s += t.key; s += ':'; s += t.op; s += ':'; s += t.value; s += ':'; s += t.effect; s += ';'; }
   s += "|HP=";
   for (auto& c : p.containers)
-    for (auto& hp : c.ports) s += hp.ip + ":" + std::to_string(hp.port) + ":" + hp.protocol + ";";
+    for (auto& hp : c.ports) { s += hp.ip; s += ':'; num(hp.port); s += ':'; s += hp.protocol; s += ';'; }
   return s;
 }
 
