@@ -1302,3 +1302,61 @@ def startup_taint_after_initialization_blocks_ephemeral_taints_do_not():
         assert len(results[0]["newNodes"]) == 1           # a new node: the startup taint was gone once and is back
         assert results[1]["assign"] == [0] and results[1]["newNodes"] == []  # NotReady / Unreachable are ephemeral (state/node.go:93-110)
     return {"multi": [p1, p2]}, check
+
+
+# ------------------------------------------------------------------ several constraints at once (topology_test.go:882-1028)
+def _max_skew(counts, domains):
+    cs = sorted(counts) + [0] * (domains - len(counts))
+    return max(cs) - min(cs) if cs else 0
+
+
+@cpu_case("topology_test.go:882-904")
+def zonal_do_not_schedule_with_hostname_schedule_anyway():
+    labels = {"test": "test"}
+    cons = [fx.spread(ZONE, labels), fx.spread(HOSTNAME, labels, when="ScheduleAnyway")]
+    pr = provisioner(requirements=[{"key": ZONE, "operator": "In", "values": ["test-zone-1", "test-zone-2"]}])
+    prob = problem(pods(10, labels=labels, topologySpreadConstraints=cons), provisioners=[pr])
+
+    def check(res):
+        # zone-3 exists in the universe but the provisioner cannot reach it: one pod per reachable zone, the rest stays pending
+        assert fx.skew(prob, res, ZONE) == [1, 1]
+        assert fx.skew(prob, res, HOSTNAME) == [1, 1]
+    return prob, check
+
+
+@cpu_case("topology_test.go:906-950")
+def capacity_type_and_hostname_spread_first_and_large_batches():
+    labels = {"test": "test"}
+    cons = [fx.spread(CAPACITY_TYPE, labels), fx.spread(HOSTNAME, labels, max_skew=3)]
+    two = problem(pods(2, labels=labels, topologySpreadConstraints=cons))
+    many = problem(pods(21, labels=labels, topologySpreadConstraints=cons))
+
+    def check(results):
+        assert _ct_counts(results[0], {}) == [1, 1]
+        assert max(fx.skew(two, results[0], HOSTNAME)) <= 3
+        assert min(results[1]["assign"]) >= 0
+        assert _ct_counts(results[1], {}) == [10, 11]
+        assert max(fx.skew(many, results[1], HOSTNAME)) <= 3
+    return {"multi": [two, many]}, check
+
+
+@cpu_case("topology_test.go:993-1028")
+def capacity_type_zone_and_hostname_spread_together():
+    labels = {"test": "test"}
+    cons = [fx.spread(CAPACITY_TYPE, labels), fx.spread(ZONE, labels, max_skew=2), fx.spread(HOSTNAME, labels, max_skew=3)]
+    its = []
+    for cpu in (2, 4, 8):
+        for zone in ZONES:
+            for ct in ("spot", "on-demand"):
+                res = {"cpu": str(cpu), "memory": f"{cpu * 2}Gi", "pods": "10"}
+                its.append(fx.instance_type(f"{cpu}c-{zone}-{ct}", res, offerings=[{"capacityType": ct, "zone": zone, "price": fx.price_from_resources(res),
+                                                                                 "available": True}]))
+    probs = [problem(pods(n, labels=labels, topologySpreadConstraints=cons), instance_types=its) for n in (1, 2, 3, 7, 14)]
+
+    def check(results):
+        for prob, res in zip(probs, results):
+            assert min(res["assign"]) >= 0
+            assert _max_skew(_ct_counts(res, {}), 2) <= 1
+            assert _max_skew(fx.skew(prob, res, ZONE), 3) <= 2
+            assert max(fx.skew(prob, res, HOSTNAME)) <= 3
+    return {"multi": probs}, check
