@@ -1360,3 +1360,37 @@ def capacity_type_zone_and_hostname_spread_together():
             assert _max_skew(fx.skew(prob, res, ZONE), 3) <= 2
             assert max(fx.skew(prob, res, HOSTNAME)) <= 3
     return {"multi": probs}, check
+
+
+# ------------------------------------------------------------------ daemonset bookkeeping on existing nodes (suite_test.go:1732-1821)
+@cpu_case("suite_test.go:1732-1821")
+def unexpected_daemonset_pod_does_not_free_capacity():
+    """a label Karpenter did not put there makes a second daemonset land on the node; its pod is bound (1 cpu of 15.9):
+    a 15.5-cpu pod must NOT be placed there, whatever the remaining-daemonset arithmetic says (clamped at zero)"""
+    ds1 = pod({"cpu": "1", "memory": "1Gi"}, nodeSelector={"my-node-label": "value"})
+    ds2 = pod({"cpu": "1m"})
+    bound = pod({"cpu": "1", "memory": "2Gi"}, nodeSelector={"my-node-label": "value"}, nodeName="node-a", isDaemonSet=True)
+    node = fx.state_node("node-a", "arm-instance-type", allocatable={"cpu": "15900m", "memory": "131062Mi", "pods": "5"}, pods_=[bound],
+                         labels={ARCH: "arm64", "my-node-label": "value"})
+    prob = problem([pod({"cpu": "15.5"})], nodes=[node], daemonSetPods=[ds1, ds2])
+
+    def check(res):
+        assert res["assign"] == [1] and len(res["newNodes"]) == 1
+        assert launched_type(prob, res, 0) == "arm-instance-type"
+    return prob, check
+
+
+@cpu_case("suite_test.go:1963-1993")
+def self_zone_affinity_prefers_the_in_flight_nodes_domain():
+    """Issue #1975: nothing matches yet (the first pod is not bound), the bootstrap domain must be the in-flight node's zone"""
+    aff = {"security": "s2"}
+    term = {"required": [fx.affinity_term(ZONE, aff)]}
+    for_zone = {}
+    for z in ZONES:
+        node = fx.state_node("node-a", zone=z, initialized=False)
+        for_zone[z] = problem([pod(labels=aff, podAffinity=term)], nodes=[node])
+
+    def check(results):
+        for res in results:
+            assert res["assign"] == [0] and res["newNodes"] == []
+    return {"multi": [for_zone[z] for z in ZONES]}, check
