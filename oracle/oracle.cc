@@ -37,6 +37,25 @@
 namespace oracle {
 using namespace kmodel;
 
+// FAST MODE (oracle_set_fast / ORACLE_FAST=1) — still test infrastructure. The literal restatement below is O(nodes x
+// instance types x string-set work) per Add and needs ~20 h for BASELINE C4 at full size. Fast mode adds RESULT-NEUTRAL
+// shortcuts only (each one derives the same verdict / the same committed state as the literal code next to it; they are
+// marked "fast:" and tests/test_oracle_fast_mode.py asserts digest equality with the literal path on every known answer,
+// the fuzz corpus and C3/C4/C5 samples):
+//   F1 a node whose merged requests exceed the per-resource maximum allocatable of its remaining options is rejected
+//      before the requirement / topology stages (node_add has no side effects before its commit, so only `false` matters);
+//   F2 filter_types evaluates Fits first and memoises the requirement part (Intersects && hasOffering) per distinct
+//      requirement set (restricted to the keys instance types define);
+//   F3 hostname-keyed spread / anti-affinity groups look up the node's concrete hostname set instead of walking every
+//      registered hostname (same visiting order, same result); the "any empty domain" emptiness test uses a maintained
+//      zero-count counter;
+//   F4 getMatchingTopologies / Record memoise, per pod, which groups own / select it (pure in the pod and the group set;
+//      flushed by every Topology.Update);
+//   F5 per-pod requests_for_pod / new_pod_requirements are cached until the pod is relaxed.
+// cpu_baseline and every small-size parity test use the LITERAL path; fast mode exists for the full-size golden digests.
+bool g_fast = false;
+void set_fast(bool on) { g_fast = on; }
+
 // ---------------------------------------------------------------- resources (utils/resources/resources.go)
 static ResourceList merge(const ResourceList& a, const ResourceList& b) {  // :47-60
   ResourceList r = a;
@@ -276,8 +295,14 @@ struct TopologyGroup {
   bool Counts(const Pod& p, const Requirements& req, const std::set<std::string>& wk) const {  // :109-111
     return selects(p) && node_filter.MatchesRequirements(req, wk);
   }
-  void Record(const std::string& d) { domains[d]++; }                                   // :101-105
-  void Register(const std::string& d) { if (!domains.count(d)) domains[d] = 0; }        // :114-120
+  int64_t zero_domains = 0;  // fast: number of registered domains whose count is 0 (maintained by Record / Register)
+  void Record(const std::string& d) {                                                   // :101-105
+    auto it = domains.find(d);
+    if (it == domains.end()) { domains[d] = 1; return; }
+    if (it->second == 0) --zero_domains;
+    it->second++;
+  }
+  void Register(const std::string& d) { if (!domains.count(d)) { domains[d] = 0; ++zero_domains; } }  // :114-120
 
   int32_t domainMinCount(const Requirement& pod_domains) const {  // :184-200
     if (key == kHostname) return 0;
@@ -324,7 +349,49 @@ struct TopologyGroup {
       if (pod_domains.Has(kv.first) && kv.second == 0) options.values.insert(kv.first);
     return options;
   }
+  // fast (F3): hostname groups hold one domain per node ever attempted. When the node's own requirement for the key is a
+  // concrete set (always: hostname In [own name]) the literal loops below only ever admit members of that set, so they are
+  // walked in the same ascending order instead of all domains. Anti-affinity: the literal result is {d : count==0 and the pod
+  // allows d}; its emptiness (the `Len()==0` reject in AddRequirements) is decided by zero_domains when the pod allows
+  // everything, and the caller only intersects the result with the node's set, so returning the members of the node's set
+  // that qualify leaves the merged requirement identical.
+  bool fast_applicable(const Requirement& pd, const Requirement& nd) const {
+    return key == kHostname && !nd.complement && pd.complement && pd.values.empty() && !pd.greater_than && !pd.less_than &&
+           (type == TopologyType::Spread || type == TopologyType::PodAntiAffinity);
+  }
+  Requirement GetFast(const Pod& pod, const Requirement& pd, const Requirement& nd) const {
+    if (type == TopologyType::Spread) {
+      bool self = selects(pod);
+      std::string min_domain;
+      bool found = false;
+      int32_t min_count = INT32_MAX;
+      for (auto& v : nd.values) {  // ascending, like the literal walk restricted to node_domains.Has
+        auto it = domains.find(v);
+        if (it == domains.end() || !nd.Has(v)) continue;
+        int64_t count = it->second;
+        if (self) count++;
+        if (count - 0 <= max_skew && count < min_count) { min_domain = v; min_count = (int32_t)count; found = true; }
+      }
+      if (!found || min_domain.empty()) return Requirement::New(pd.key, Op::DoesNotExist);
+      return Requirement::New(pd.key, Op::In, {min_domain});
+    }
+    Requirement options = Requirement::New(pd.key, Op::DoesNotExist);
+    if (zero_domains == 0) return options;  // literal: no domain with count 0 -> Len()==0
+    bool any_in_node = false;
+    for (auto& v : nd.values) {
+      auto it = domains.find(v);
+      if (it != domains.end() && it->second == 0) { options.values.insert(v); any_in_node = true; }
+    }
+    if (!any_in_node) {
+      // literal result is non-empty but disjoint from the node's set: keep ONE witness domain outside the node's set so
+      // that Len()!=0 here and the later intersection / Compatible behave exactly as with the full set
+      for (auto& kv : domains)
+        if (kv.second == 0 && !nd.values.count(kv.first)) { options.values.insert(kv.first); break; }
+    }
+    return options;
+  }
   Requirement Get(const Pod& pod, const Requirement& pd, const Requirement& nd) const {  // :88-99
+    if (g_fast && fast_applicable(pd, nd)) return GetFast(pod, pd, nd);
     switch (type) {
       case TopologyType::Spread: return nextDomainTopologySpread(pod, pd, nd);
       case TopologyType::PodAffinity: return nextDomainAffinity(pod, pd, nd);
@@ -357,7 +424,7 @@ struct Topology {
     TopologyGroup g;
     g.type = t; g.key = key; g.namespaces = std::move(nss); g.selector = sel; g.max_skew = max_skew;
     auto it = domains.find(key);
-    if (it != domains.end()) for (auto& d : it->second) g.domains[d] = 0;
+    if (it != domains.end()) for (auto& d : it->second) g.Register(d);
     if (t == TopologyType::Spread) g.node_filter = TopologyNodeFilter::Make(pod);
     return g;
   }
@@ -393,7 +460,26 @@ struct Topology {
       it->second.owners.insert(pod.uid);
     }
   }
+  // fast (F4): per pod uid, the groups that own it / the inverse groups and groups whose selector matches it. Pure in
+  // (pod, set of groups); every Update (the only place groups or owners change after NewTopology) flushes the memo.
+  struct PodMemo { std::vector<TopologyGroup*> owned, inverse_selecting, selecting, inverse_owned; };
+  std::map<std::string, PodMemo> memo;
+  const PodMemo& memo_for(const Pod& p) {
+    auto it = memo.find(p.uid);
+    if (it != memo.end()) return it->second;
+    PodMemo m;
+    for (auto& kv : topologies) {
+      if (kv.second.owners.count(p.uid)) m.owned.push_back(&kv.second);
+      if (kv.second.selects(p)) m.selecting.push_back(&kv.second);
+    }
+    for (auto& kv : inverse) {
+      if (kv.second.selects(p)) m.inverse_selecting.push_back(&kv.second);
+      if (kv.second.owners.count(p.uid)) m.inverse_owned.push_back(&kv.second);
+    }
+    return memo.emplace(p.uid, std::move(m)).first->second;
+  }
   void Update(const Pod& p) {  // :86-117
+    memo.clear();
     for (auto& kv : topologies) kv.second.owners.erase(p.uid);
     bool has_anti = !p.pod_anti_affinity_required.empty() || !p.pod_anti_affinity_preferred.empty();
     if (has_anti) updateInverseAntiAffinity(p, nullptr);
@@ -426,6 +512,23 @@ struct Topology {
   }
   void Record(const Pod& p, const Requirements& req) {  // :120-143
     if (inert) return;
+    if (g_fast) {  // same two loops over the memoised subsets, in the same (ascending hash) order
+      const PodMemo& m = memo_for(p);
+      for (auto* tc : m.selecting) {
+        if (!tc->node_filter.MatchesRequirements(req, *wk)) continue;
+        Requirement d = req.Get(tc->key);
+        if (tc->type == TopologyType::PodAntiAffinity) {
+          for (auto& v : d.values) tc->Record(v);
+        } else if (d.Len() == 1) {
+          tc->Record(*d.values.begin());
+        }
+      }
+      for (auto* tc : m.inverse_owned) {
+        Requirement d = req.Get(tc->key);
+        for (auto& v : d.values) tc->Record(v);
+      }
+      return;
+    }
     for (auto& kv : topologies) {
       TopologyGroup& tc = kv.second;
       if (!tc.Counts(p, req, *wk)) continue;
@@ -450,8 +553,14 @@ struct Topology {
     req.AddAll(node_req);
     if (!inert) {
       std::vector<const TopologyGroup*> matching;  // getMatchingTopologies :351-364
-      for (auto& kv : topologies) if (kv.second.owners.count(p.uid)) matching.push_back(&kv.second);
-      for (auto& kv : inverse) if (kv.second.Counts(p, node_req, *wk)) matching.push_back(&kv.second);
+      if (g_fast) {
+        const PodMemo& m = memo_for(p);
+        for (auto* tg : m.owned) matching.push_back(tg);
+        for (auto* tg : m.inverse_selecting) if (tg->node_filter.MatchesRequirements(node_req, *wk)) matching.push_back(tg);
+      } else {
+        for (auto& kv : topologies) if (kv.second.owners.count(p.uid)) matching.push_back(&kv.second);
+        for (auto& kv : inverse) if (kv.second.Counts(p, node_req, *wk)) matching.push_back(&kv.second);
+      }
       for (auto* tg : matching) {
         Requirement pd = pod_req.Has(tg->key) ? pod_req.Get(tg->key) : Requirement::New(tg->key, Op::Exists);
         Requirement nd = node_req.Has(tg->key) ? node_req.Get(tg->key) : Requirement::New(tg->key, Op::Exists);
@@ -572,6 +681,8 @@ struct SchedNode {  // node.go:34-40
   std::vector<const IType*> options;
   std::vector<int> pods;
   HostPortUsage ports;
+  ResourceList max_alloc;  // fast (F1): per-resource maximum of allocatable over `options` (valid when max_alloc_valid)
+  bool max_alloc_valid = false;
 };
 
 struct ExistingNode {  // existingnode.go:28-39
@@ -635,8 +746,36 @@ struct Scheduler {
     }
     return false;
   }
-  std::vector<const IType*> filter_types(const std::vector<const IType*>& in, const Requirements& req, const ResourceList& requests) const {  // node.go:137-141
+  // fast (F2): requirement part of the filter per distinct requirement set, over ALL instance types
+  std::map<std::string, std::vector<char>> req_part_memo;
+  std::set<std::string> type_keys;  // keys any instance type defines (+ zone / capacity-type, read by hasOffering)
+  const std::vector<char>& req_part(const Requirements& req) {
+    std::string key;
+    for (auto& kv : req.m)
+      if (type_keys.count(kv.first)) key += kv.first + "\x01" + kv.second.Canonical() + "\x02";
+    auto it = req_part_memo.find(key);
+    if (it != req_part_memo.end()) return it->second;
+    std::vector<char> v(itypes.size());
+    for (auto& t : itypes) v[t.index] = t.req.Intersects(req) && has_offering(t, req);
+    return req_part_memo.emplace(key, std::move(v)).first->second;
+  }
+  // fast (F5)
+  std::vector<ResourceList> pod_requests_memo;
+  std::vector<char> pod_requests_valid;
+  ResourceList pod_requests(int pi) {
+    if (!g_fast) return requests_for_pod(pods[pi]);
+    if (pod_requests_valid.size() != pods.size()) { pod_requests_valid.assign(pods.size(), 0); pod_requests_memo.resize(pods.size()); }
+    if (!pod_requests_valid[pi]) { pod_requests_memo[pi] = requests_for_pod(pods[pi]); pod_requests_valid[pi] = 1; }
+    return pod_requests_memo[pi];
+  }
+  std::vector<const IType*> filter_types(const std::vector<const IType*>& in, const Requirements& req, const ResourceList& requests) {  // node.go:137-141
     std::vector<const IType*> out;
+    if (g_fast) {
+      const std::vector<char>& ok = req_part(req);
+      for (auto* t : in)
+        if (fits(requests, t->allocatable) && ok[t->index]) out.push_back(t);
+      return out;
+    }
     for (auto* t : in)
       if (t->req.Intersects(req) && fits(requests, t->allocatable) && has_offering(*t, req)) out.push_back(t);
     return out;
@@ -644,6 +783,16 @@ struct Scheduler {
 
   bool node_add(SchedNode& n, int pi) {  // node.go:62-107
     Pod& pod = pods[pi];
+    if (g_fast) {  // F1: no remaining option can hold the merged requests -> filter_types below would come back empty
+      if (!n.max_alloc_valid) {
+        n.max_alloc.clear();  // max over options of allocatable[r], a missing entry counting as 0 exactly like fits() does
+        for (auto* t : n.options) for (auto& kv : t->allocatable) n.max_alloc.emplace(kv.first, INT64_MIN);
+        for (auto* t : n.options)
+          for (auto& kv : n.max_alloc) kv.second = std::max(kv.second, getq(t->allocatable, kv.first));
+        n.max_alloc_valid = true;
+      }
+      if (!fits(merge(n.requests, pod_requests(pi)), n.max_alloc)) return false;
+    }
     if (!tolerates(templates[n.tmpl].taints, pod)) return false;
     if (!n.ports.validate(pod)) return false;
     Requirements node_req;
@@ -655,10 +804,11 @@ struct Scheduler {
     if (!topology.AddRequirements(pod_req, node_req, pod, &topo_req)) return false;
     if (!node_req.Compatible(topo_req, wk)) return false;
     node_req.AddAll(topo_req);
-    ResourceList requests = merge(n.requests, requests_for_pod(pod));
+    ResourceList requests = merge(n.requests, pod_requests(pi));
     auto types = filter_types(n.options, node_req, requests);
     if (types.empty()) return false;
     n.pods.push_back(pi);
+    n.max_alloc_valid = false;
     n.options = std::move(types);
     n.requests = std::move(requests);
     n.req = std::move(node_req);
@@ -767,6 +917,9 @@ struct Scheduler {
       t.allocatable = subtract(t.it->capacity, overhead);
       itypes.push_back(std::move(t));
     }
+    for (auto& t : itypes) for (auto& kv : t.req.m) type_keys.insert(kv.first);
+    type_keys.insert(kZone);
+    type_keys.insert(kCapacityType);
     // OrderByWeight (R4 stable)
     for (size_t i = 0; i < P.provisioners.size(); ++i) prov_order.push_back((int)i);
     std::stable_sort(prov_order.begin(), prov_order.end(), [&](int a, int b) { return P.provisioners[a].weight > P.provisioners[b].weight; });
@@ -902,6 +1055,7 @@ struct Scheduler {
       ++head;
       if (add(p)) continue;
       bool relaxed = prefs.Relax(pods[p]);
+      if (relaxed && !pod_requests_valid.empty()) pod_requests_valid[p] = 0;
       q.push_back(p);
       if (relaxed) {
         last_len.clear();

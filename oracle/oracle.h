@@ -8,6 +8,9 @@
 
 namespace oracle {
 
+// Result-neutral shortcuts for full-size runs (see oracle.cc header: FAST MODE). Default off = literal restatement.
+void set_fast(bool on);
+
 // pkg/utils/resources/resources.go:25-33
 kmodel::ResourceList requests_for_pods(const std::vector<const kmodel::Pod*>& pods);
 

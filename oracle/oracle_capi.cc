@@ -41,6 +41,7 @@ static int put(const std::string& s, char* out, int cap) {
 }
 
 extern "C" {
+void oracle_set_fast(int on) { set_fast(on != 0); }
 int oracle_req_render(const char* a, char* out, int cap) { return put(render(parse_spec("key", a)), out, cap); }
 int oracle_req_intersection(const char* a, const char* b, char* out, int cap) {
   return put(render(parse_spec("key", a).Intersection(parse_spec("key", b))), out, cap);
