@@ -29,6 +29,11 @@ struct DevCatalog {
   const int64_t* alloc_rt;           // [n_res][n_types] allocatable, resource-major
   const uint32_t* domset;            // [n_types][W32] types whose allocatable vector (first 4 resources) is dominated by the row's type
   int zone_key, ct_key;
+  // bit d of pin_neutral[k]: narrowing a node's requirement on key k to the single value d can never remove an instance type
+  // of any template (every member type admits d on k, and - for the zone / capacity-type keys - has an available offering
+  // for d combined with every value of the other key). Built by ksched_load_catalog; lets the pack kernel's class-run loop
+  // accept a topology-spread placement that pins a node's domain without re-filtering its options.
+  uint64_t pin_neutral[KSCHED_MAX_KEYS];
   const uint64_t* offer_keys;        // [n_types][64] launch-choice keys (ksched_catalog.offering_keys) or nullptr
   const uint32_t* input_index;       // [n_types] provider input order of the column
 };

@@ -419,6 +419,59 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
     c.input_index = h->d_input_index.ptr;
   }
   c.zone_key = zone_key; c.ct_key = ct_key;
+  {
+    // pin_neutral (catalog.cuh): U = union of every template's member types
+    std::vector<uint32_t> U(W32, 0);
+    for (int v = 0; v < V; ++v) for (int w = 0; w < W32; ++w) U[w] |= member[(size_t)v * W32 + w];
+    auto covers = [&](const std::vector<uint32_t>& set) { for (int w = 0; w < W32; ++w) if (U[w] & ~set[w]) return false; return true; };
+    auto offer_rows = [&](int ct, int z, std::vector<uint32_t>& acc) {
+      const int16_t r = offrow[ct * 16 + z];
+      if (r >= 0) for (int w = 0; w < W32; ++w) acc[w] |= offset[(size_t)r * W32 + w];
+    };
+    for (int k = 0; k < KSCHED_MAX_KEYS; ++k) c.pin_neutral[k] = 0;
+    for (int k = 0; k < NK; ++k) {
+      for (int b = 0; b < 64; ++b) {
+        if (!((cat->keys[k].dict_mask >> b) & 1)) continue;
+        std::vector<uint32_t> set(W32, 0);
+        for (int w = 0; w < W32; ++w) set[w] = absent[(size_t)k * W32 + w];
+        if (valrow[(size_t)k * 64 + b] >= 0) for (int w = 0; w < W32; ++w) set[w] |= valset[(size_t)valrow[(size_t)k * 64 + b] * W32 + w];
+        bool ok = covers(set);
+        if (ok && k == zone_key) {
+          if (b >= 16) ok = false;
+          else if (ct_key >= 0) {
+            for (int ct = 0; ct < 4 && ok; ++ct) {
+              if (!((cat->keys[ct_key].dict_mask >> ct) & 1)) continue;
+              std::vector<uint32_t> acc(W32, 0);
+              offer_rows(ct, b, acc);
+              ok = covers(acc);
+            }
+            if (cat->keys[ct_key].dict_mask >> 4) ok = false;
+          } else {
+            std::vector<uint32_t> acc(W32, 0);
+            for (int ct = 0; ct < 4; ++ct) offer_rows(ct, b, acc);
+            ok = covers(acc);
+          }
+        }
+        if (ok && k == ct_key) {
+          if (b >= 4) ok = false;
+          else if (zone_key >= 0) {
+            for (int z = 0; z < 16 && ok; ++z) {
+              if (!((cat->keys[zone_key].dict_mask >> z) & 1)) continue;
+              std::vector<uint32_t> acc(W32, 0);
+              offer_rows(b, z, acc);
+              ok = covers(acc);
+            }
+            if (cat->keys[zone_key].dict_mask >> 16) ok = false;
+          } else {
+            std::vector<uint32_t> acc(W32, 0);
+            for (int z = 0; z < 16; ++z) offer_rows(b, z, acc);
+            ok = covers(acc);
+          }
+        }
+        if (ok) c.pin_neutral[k] |= 1ull << b;
+      }
+    }
+  }
   h->have_catalog = true;
   h->uploaded = false;
   return KSCHED_OK;
@@ -620,7 +673,7 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
     CUDA_TRY(h, h->d_fd_bound.ensure(nfd * 4)); CUDA_TRY(h, h->d_fd_bound2.ensure(nfd * 4));
   }
   CUDA_TRY(h, h->d_remaining.ensure((size_t)V * KSCHED_MAX_RES));
-  CUDA_TRY(h, h->d_counters.ensure(32));
+  CUDA_TRY(h, h->d_counters.ensure(48));
   {
     size_t need = 0, n2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)p1, 0, 64, h->stream);
@@ -750,7 +803,7 @@ static int reset_state(ksched_handle* h) {
     for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[(size_t)v * KSCHED_MAX_RES + r] = h->h_templates[v].remaining[r];
   CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, rem.data(), rem.size() * 8, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rem is a stack vector
-  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 32 * sizeof(long long), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 48 * sizeof(long long), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fc_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fc_front_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fd_state.ptr, 0, (size_t)kFreshMemoSlots, h->stream));
@@ -794,9 +847,15 @@ static int run_pack(ksched_handle* h) {
   s.counters = h->d_counters.ptr;
   const size_t alloc_bytes = (size_t)h->cat.n_res * h->cat.n_types * sizeof(int64_t);
   // 227 KB per CTA on sm_100a: the hot node window + ~4 KB of static shared memory come first
-  const size_t smem_left = (size_t)(227 << 10) - sizeof(HotSmem) - (size_t)(6 << 10);
+  const size_t static_smem = (size_t)(14 << 10);  // file-scope __shared__ objects (pod row, PodTopo, RunCtx with its variants, scratch)
+  const size_t smem_left = (size_t)(227 << 10) - sizeof(HotSmem) - kRunArrayBytes - static_smem;
   s.alloc_in_smem = alloc_bytes <= smem_left ? 1 : 0;
-  const size_t smem = sizeof(HotSmem) + (s.alloc_in_smem ? alloc_bytes : 0);
+  s.run_off = s.alloc_in_smem ? (int)((alloc_bytes + 15) & ~(size_t)15) : 0;
+  const size_t smem = sizeof(HotSmem) + (size_t)s.run_off + kRunArrayBytes;
+  s.any_limits = 0;
+  for (const ksched_template& tm : h->h_templates) if (tm.has_limits && tm.limit_present) s.any_limits = 1;
+  s.use_warp_loop = getenv("KSCHED_NO_WARPLOOP") ? 0 : 1;
+  s.use_class_run = getenv("KSCHED_NO_CLASSRUN") ? 0 : 1;
   CUDA_TRY(h, cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // block size: the chain is latency-bound on ONE thread's commit; more warps only help when there are many candidate
   // nodes to examine per pod (existing nodes, large in-flight sets)
@@ -882,7 +941,7 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
   if (!h || !pb || !res || !h->uploaded) return KSCHED_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int P = h->n_pods, NE = h->n_existing, MAXN = h->max_new, W32 = h->cat.W32, W64 = h->W64, V = h->cat.n_templates;
-  long long counters[32];
+  long long counters[48];
   CUDA_TRY(h, cudaMemcpyAsync(counters, h->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
 #ifdef KSCHED_PROFILE_PACK
@@ -893,6 +952,8 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
   fprintf(stderr, "[pack profile] fresh: decide=%lld words=%lld commit=%lld rest=%lld | in-flight verify=%lld\n", counters[26], counters[27], counters[28],
           counters[12], counters[29]);
   fprintf(stderr, "[pack profile] in-flight commit: winner+barrier=%lld record=%lld rest=%lld\n", counters[30], counters[31], counters[11]);
+  fprintf(stderr, "[pack profile] class_run: calls=%lld pods=%lld bails=%lld ineligible=%lld cycles=%lld\n", counters[40], counters[41], counters[42], counters[43],
+          counters[14]);
 #endif
   if (counters[4] != 0) {
     h->err = counters[4] == KSCHED_ERR_OVERFLOW ? "new-node capacity exceeded" : "a pod is constrained by more topology groups than the kernel supports";

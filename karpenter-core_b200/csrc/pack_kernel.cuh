@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int kActCap = 1536;  // open in-flight nodes whose hot state is held in shared memory
+constexpr int kActCap = 1280;  // open in-flight nodes whose hot state is held in shared memory
 constexpr int kHotRes = 4;     // resources covered by the hot request / bound vectors (cpu, memory, pods, +1)
 
 struct HotSmem {
@@ -302,6 +302,9 @@ struct LoopVars {
   long long nodes_visited;
   uint32_t pt_class;   // class the shared PodTopo was built for (KSCHED_NONE: none)
   uint32_t row_class;  // class whose row g_row holds
+  // the step has just opened node slot fresh_a for a pod of class fresh_cls and the node is still open (class_run captures it)
+  int fresh_valid, fresh_a;
+  uint32_t fresh_cls;
 };
 
 // One full Scheduler.add for one pod (existing nodes -> in-flight nodes -> new node -> relax/requeue). Every thread of
@@ -335,6 +338,7 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
 #define GK_C(i)
 #endif
     const uint32_t pod = cur.pod, cls = (uint32_t)cur.cls64;
+    L.fresh_valid = 0;
     const ksched_pod_row& row = g_row;
     const uint32_t p_res = cur.res;
     long long preq[kHotRes];
@@ -856,7 +860,7 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
         __syncthreads();
         if (has_topo) topo_record_block(s.nn_vals, s.nn_meta[n], MAXN, n, NE + n);  // Topology.Record, one relation per thread
         ++n_new;
-        if (!sh.placed_closed) ++n_active;
+        if (!sh.placed_closed) { L.fresh_valid = 1; L.fresh_a = n_active; L.fresh_cls = cls; ++n_active; }
         placed = true;
         GK_T(20)
       }
@@ -1013,6 +1017,455 @@ __device__ __noinline__ void warp_resident_loop(WarpIO* io) {
   }
 }
 
+// ---- class-run loop ------------------------------------------------------------------------------------------------
+// Consecutive pods of the queue usually belong to ONE class (a deployment: identical row, identical topology terms). For
+// such a run the whole CTA stays in this loop: ONE block barrier per pod, no global LOAD on the chain.
+//  * every open node is owned by thread (slot % blockDim): only its owner ever reads or writes its hot state, so a
+//    commit needs no barrier to become visible; the block argmin carries a payload (slot, closed, pinned domains) from
+//    which every thread updates the loop-carried scalars and every warp its own copy of the spread counters;
+//  * for topology classes the per-node inputs of TopologyGroup.Get live in shared memory next to the hot state: the
+//    count of every hostname-keyed group of the class on the node, and the node's admissible domains for every spread key
+//    (loaded once per run, kept in step by the commits; counters are written through to global memory with plain stores /
+//    smem-mirrored values, so the generic step always finds them current);
+//  * a candidate is accepted here only when the verdict is EXACT and nothing but counters changes: resources by the
+//    Pareto-front test, requirements untouched (plain / absorbed classes) or a spread domain that is already pinned on the
+//    node - or that can be pinned without touching the option set (DevCatalog::pin_neutral). Any other winner, a pod that
+//    fails, or a fresh node of a shape not seen before in the run hands the pod to generic_step (status 1);
+//  * fresh nodes replay a VARIANT: NewNode+Add for (class, template, resulting requirement masks) is a pure function
+//    when no provisioner limit is active (same argument as PackState::fd_*), so the node generic_step created last for
+//    this class is captured (options, masks, requests, Pareto front) and replayed for every later pod of the run whose
+//    spread domains come out the same.
+constexpr int kRunHost = 4;      // hostname-keyed relations of a run-eligible class
+constexpr int kRunMask = 2;      // spread relations over a mask key
+constexpr int kRunDom = 16;      // domains of such a key
+constexpr int kTopoCap = 768;    // open nodes whose per-class topology inputs fit in shared memory
+constexpr int kRunVariants = 4;
+constexpr int kRunW32 = 64;      // option words a variant holds (T <= 2048)
+constexpr int kRunWarps = kPackThreads / 32;
+constexpr size_t kRunArrayBytes = (size_t)kTopoCap * (kRunMask * 8 + kRunHost * 2 + kRunMask);
+
+struct RunVariant {
+  uint32_t opts[kRunW32];
+  uint64_t vals[KSCHED_MAX_KEYS];
+  uint64_t meta;
+  long long q[KSCHED_MAX_RES];
+  long long b1[kHotRes], b2[kHotRes];
+  uint32_t qp;
+  unsigned short fl;      // HotSmem::flags of the fresh node (front bits, request keys, template)
+  uint8_t dom[kRunMask];  // domain each spread relation pinned
+};
+struct RunCtx {
+  uint32_t cls;           // class the relation tables and variants belong to (KSCHED_NONE: none)
+  int eligible;
+  int n_host, n_mask, n_var, var_next;
+  int h_row[kRunHost], h_group[kRunHost], h_skew[kRunHost];
+  int h_total[kRunHost];  // mirror of grp_host_total (written by the committing thread; one commit per barrier interval)
+  uint8_t h_type[kRunHost], h_self[kRunHost], h_times[kRunHost];
+  int m_group[kRunMask], m_skew[kRunMask];
+  uint8_t m_key[kRunMask], m_self[kRunMask], m_rec[kRunMask], m_wk[kRunMask];
+  uint64_t m_registered[kRunMask], m_neutral[kRunMask], m_tallow[kRunMask];
+  int32_t cnt[kRunWarps][kRunMask][kRunDom];  // one copy of the spread counters per warp (updated by its lane 0)
+  unsigned long long red_key[2][32];
+  unsigned red_pay[2][32];
+  RunVariant var[kRunVariants];
+};
+__shared__ RunCtx g_rc;
+
+struct RunIO {
+  int qi, head, qlen, tick, seq, n_active, n_new, parity;
+  long long add_calls;
+  int placed;        // pods this call consumed
+  int status;        // 0 the run ended (class change / end of the first pass); 1 the pod at qi needs generic_step; 2 class not eligible
+  int fresh_valid, fresh_a;  // in: generic_step has just created node slot fresh_a for fresh_cls (nothing happened since)
+  uint32_t fresh_cls;
+};
+__shared__ RunIO g_rio;
+
+// payload of the block argmin
+__device__ __forceinline__ unsigned run_pay(int a, bool slow, bool closed, unsigned pin, const int* d) {
+  return (unsigned)a | (slow ? 1u << 11 : 0) | (closed ? 1u << 12 : 0) | (pin << 13) | ((unsigned)d[0] << 15) | ((unsigned)d[1] << 19);
+}
+// first domain in (count, id) order among `cand` (non-empty)
+__device__ __forceinline__ int run_pick(uint64_t cand, const int32_t* cn) {
+  int d = __ffsll((long long)cand) - 1;
+  cand &= cand - 1;
+  int32_t best = cn[d];
+  while (cand) {
+    const int e = __ffsll((long long)cand) - 1;
+    cand &= cand - 1;
+    if (cn[e] < best) { best = cn[e]; d = e; }
+  }
+  return d;
+}
+
+__device__ __noinline__ void class_run(const PodRegs& first) {
+  KS_K2
+  RunCtx& rc = g_rc;
+  RunIO& io = g_rio;
+  HotSmem* hs = reinterpret_cast<HotSmem*>(dyn_smem);
+  uint64_t* zval = reinterpret_cast<uint64_t*>(dyn_smem + sizeof(HotSmem) + s.run_off);   // [kRunMask][kTopoCap]
+  uint16_t* hc = reinterpret_cast<uint16_t*>(zval + (size_t)kRunMask * kTopoCap);           // [kRunHost][kTopoCap]
+  uint8_t* zfl = reinterpret_cast<uint8_t*>(hc + (size_t)kRunHost * kTopoCap);              // [kRunMask][kTopoCap] bit0 present, bit1 present && !complement
+  const uint32_t* tmpl_taintset = g_tmpl_taintset;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int NE = s.n_existing, MAXN = s.max_new, W32 = c.W32;
+  const int RH = c.n_res < kHotRes ? c.n_res : kHotRes;
+  const int qcap = s.n_pods + 1;
+  const int hstride = s.n_existing + s.max_new;
+  const unsigned cls = (unsigned)first.cls64;
+  const bool topo = first.topo_begin != first.topo_end;
+  const bool plain = plain_pod_regs(first);
+  const bool simple = !topo;
+  int qi = io.qi, head = io.head, qlen = io.qlen, tick = io.tick, seq = io.seq, n_active = io.n_active, n_new = io.n_new, parity = io.parity;
+  long long add_calls = io.add_calls;
+  const int fresh_valid = io.fresh_valid && io.fresh_cls == cls, fresh_a = io.fresh_a;
+  __syncthreads();  // everybody has read g_rio; earlier readers of g_rc are done
+
+  // ---- relation tables (once per class)
+  if (rc.cls != cls) {
+    if (tid == 0) {
+      rc.cls = cls;
+      rc.n_var = 0; rc.var_next = 0; rc.n_host = 0; rc.n_mask = 0;
+      int ok = 1;
+      if (topo) {
+        if (c.n_templates != 1) ok = 0;
+        for (uint32_t e = first.topo_begin; e < first.topo_end && ok; ++e) {
+          const RelX x = s.relx[e];
+          const int g = (int)x.group;
+          if (!(x.flags & KSCHED_TOPO_CONSTRAINS)) { ok = 0; break; }            // record-only relations: generic step
+          if (!s.grp_active[g] || s.grp_min_slot[g] != 0) { ok = 0; break; }      // relaxation-created groups: generic step
+          if ((x.flags & KSCHED_TOPO_RECORDS) && x.has_filter) { ok = 0; break; }  // TopologyNodeFilter: generic step
+          const int times = ((x.flags & KSCHED_TOPO_RECORDS) ? 1 : 0) + ((x.flags & KSCHED_TOPO_RECORDS_INVERSE) ? 1 : 0);
+          if (x.key == KSCHED_KEY_HOSTNAME) {
+            if (x.type == 1 || rc.n_host == kRunHost) { ok = 0; break; }
+            const int j = rc.n_host++;
+            rc.h_row[j] = x.host_row; rc.h_group[j] = g; rc.h_skew[j] = x.max_skew; rc.h_type[j] = x.type;
+            rc.h_self[j] = (x.flags & KSCHED_TOPO_SELECTS) ? 1 : 0; rc.h_times[j] = (uint8_t)times;
+          } else {
+            const int k = x.key;
+            if (x.type != 0 || rc.n_mask == kRunMask || (x.flags & KSCHED_TOPO_RECORDS_INVERSE) || (c.keys[k].dict_mask >> kRunDom)) { ok = 0; break; }
+            for (int i = 0; i < rc.n_mask; ++i) if (rc.m_key[i] == k) ok = 0;
+            if (!ok) break;
+            const int j = rc.n_mask++;
+            rc.m_group[j] = g; rc.m_skew[j] = x.max_skew; rc.m_key[j] = (uint8_t)k;
+            rc.m_self[j] = (x.flags & KSCHED_TOPO_SELECTS) ? 1 : 0; rc.m_rec[j] = (x.flags & KSCHED_TOPO_RECORDS) ? 1 : 0;
+            rc.m_wk[j] = c.keys[k].well_known != 0; rc.m_neutral[j] = c.pin_neutral[k];
+            const Req tr = ksched::req_load(c.templates[0].reqs, nullptr, k);
+            rc.m_tallow[j] = tr.present ? ksched::req_allowed(tr, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask;
+          }
+        }
+      }
+      rc.eligible = ok;
+    }
+    __syncthreads();
+  }
+  if (!rc.eligible || (topo && n_active > kTopoCap)) {
+    if (tid == 0) { io.status = rc.eligible ? 1 : 2; io.placed = 0; io.parity = parity; }
+    __syncthreads();
+    return;
+  }
+  const int n_host = rc.n_host, n_mask = rc.n_mask;
+
+  // ---- per-run state: spread counters (one copy per warp), per-node topology inputs (each thread loads the slots it owns)
+  if (topo) {
+    for (int j = 0; j < n_mask; ++j) {
+      if (lane < kRunDom) rc.cnt[warp][j][lane] = s.grp_cnt[(size_t)rc.m_group[j] * 64 + lane];
+      if (tid == 0) rc.m_registered[j] = s.grp_registered[rc.m_group[j]];
+    }
+    if (tid < n_host) rc.h_total[tid] = s.grp_host_total[rc.h_group[tid]];
+    for (int a = tid; a < n_active; a += T) {
+      const int n = hs->node[a];
+      for (int j = 0; j < n_host; ++j) hc[j * kTopoCap + a] = s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n];
+      const uint64_t meta = s.nn_meta[n];
+      for (int j = 0; j < n_mask; ++j) {
+        const int k = rc.m_key[j];
+        const Req r = load_soa(s.nn_vals, meta, MAXN, n, k);
+        zval[j * kTopoCap + a] = r.present ? ksched::req_allowed(r, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask;
+        zfl[j * kTopoCap + a] = (uint8_t)((r.present ? 1 : 0) | ((r.present && !r.complement) ? 2 : 0));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- capture the node generic_step has just created for this class as a fresh-node variant
+  if (fresh_valid && !s.any_limits && W32 <= kRunW32 && fresh_a == n_active - 1 && fresh_a >= 0) {
+    const int a = fresh_a, n = hs->node[a];
+    int dom[kRunMask] = {0, 0};
+    bool ok = true;
+    for (int j = 0; j < n_mask; ++j) {
+      const uint64_t v = zval[j * kTopoCap + a];
+      if (!v || (v & (v - 1)) || !(zfl[j * kTopoCap + a] & 2)) ok = false;
+      else dom[j] = __ffsll((long long)v) - 1;
+    }
+    for (int i = 0; i < rc.n_var && ok; ++i) {
+      bool same = (rc.var[i].fl >> 8) == (hs->flags[a] >> 8);
+      for (int j = 0; j < n_mask; ++j) same = same && rc.var[i].dom[j] == dom[j];
+      if (same) ok = false;  // already known
+    }
+    __syncthreads();  // rc.n_var / var_next read by everybody before thread 0 moves them
+    if (ok) {
+      const int slot = rc.var_next;
+      RunVariant& v = rc.var[slot];
+      for (int w = tid; w < W32; w += T) v.opts[w] = s.nn_opts[(size_t)w * MAXN + n];
+      if (tid < KSCHED_MAX_KEYS) v.vals[tid] = tid < c.n_keys ? s.nn_vals[(size_t)tid * MAXN + n] : 0;
+      if (tid == 0) {
+        v.meta = s.nn_meta[n];
+        for (int r = 0; r < KSCHED_MAX_RES; ++r) v.q[r] = r < kHotRes ? hs->q[r][a] : s.nn_req[(size_t)r * MAXN + n];
+        for (int r = 0; r < kHotRes; ++r) { v.b1[r] = hs->bound[r][a]; v.b2[r] = hs->bound2[r][a]; }
+        v.qp = s.nn_req_present[n];
+        v.fl = hs->flags[a];
+        for (int j = 0; j < kRunMask; ++j) v.dom[j] = (uint8_t)dom[j];
+        rc.var_next = (slot + 1) % kRunVariants;
+        if (rc.n_var < kRunVariants) rc.n_var++;
+      }
+      __syncthreads();
+    }
+  }
+
+  long long min_req[kHotRes];
+#pragma unroll
+  for (int r = 0; r < kHotRes; ++r) min_req[r] = r < RH ? s.min_req[r] : 0;
+  const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
+  // the next two pods of the queue (id, class), fetched two iterations ahead
+  uint32_t pod = first.pod, pod1 = 0, pod2 = 0;
+  uint64_t cls1 = ~0ull, cls2 = ~0ull;
+  if (qi + 1 < s.n_pods) { pod1 = s.order[qi + 1]; cls1 = ffd_rows[qi + 1].reserved; }
+  if (qi + 2 < s.n_pods) { pod2 = s.order[qi + 2]; cls2 = ffd_rows[qi + 2].reserved; }
+  int placed = 0, status = 0;
+
+  while (true) {
+    // node-independent half of nextDomainTopologySpread: min count over the pod's domains, domains within max-skew
+    uint64_t okm[kRunMask] = {0, 0};
+    for (int j = 0; j < n_mask; ++j) {
+      const int32_t* cn = rc.cnt[warp][j];
+      const uint64_t reg = rc.m_registered[j];
+      int32_t mn = INT32_MAX;
+      for (uint64_t m = reg; m; m &= m - 1) { const int32_t v = cn[__ffsll((long long)m) - 1]; mn = v < mn ? v : mn; }
+      uint64_t ok = 0;
+      for (uint64_t m = reg; m; m &= m - 1) {
+        const int d = __ffsll((long long)m) - 1;
+        if ((long long)cn[d] + rc.m_self[j] - (long long)mn <= (long long)rc.m_skew[j]) ok |= 1ull << d;
+      }
+      okm[j] = ok;
+    }
+    // ---- scan the slots this thread owns
+    unsigned long long mine = ~0ull;
+    int best_a = -1, best_d[kRunMask] = {0, 0};
+    unsigned best_pin = 0;
+    bool best_slow = false;
+    long long bq[kHotRes] = {0, 0, 0, 0};
+    for (int a = tid; a < n_active; a += T) {
+      const unsigned long long key = hs->key[a];
+      if (key >= mine) continue;
+      const unsigned short fl = hs->flags[a];
+      if (!((first.tol >> tmpl_taintset[fl >> 8]) & 1)) continue;  // Taints.Tolerates
+      if (simple && hs->rejected[a] == cls) continue;
+      const uint32_t qp = ((fl >> 1) & 0xF) | first.res;
+      long long q[kHotRes], b1[kHotRes], b2[kHotRes];
+#pragma unroll
+      for (int r = 0; r < kHotRes; ++r) { q[r] = hs->q[r][a] + first.req[r]; b1[r] = hs->bound[r][a]; b2[r] = hs->bound2[r][a]; }
+      const int qf = quick_fit(q, qp, RH, b1, b2, fl);
+      if (qf == 0) continue;
+      bool slow = qf == 2;
+      unsigned pin = 0;
+      int dd[kRunMask] = {0, 0};
+      if (simple) {
+        if (!(plain || hs->absorbed[a] == cls)) slow = true;  // requirement verdict unknown for this class
+      } else {
+        bool rej = false;
+        for (int j = 0; j < n_host; ++j) {  // hostname groups: exact from the node's counts
+          const int cnt = hc[j * kTopoCap + a];
+          rej = rej || (rc.h_type[j] == 0 ? cnt + rc.h_self[j] > rc.h_skew[j] : cnt != 0);
+        }
+        if (rej) continue;
+        for (int j = 0; j < n_mask; ++j) {
+          const uint64_t na = zval[j * kTopoCap + a];
+          const uint64_t cand = na & okm[j];
+          if (!cand) { rej = true; break; }
+          const int d = run_pick(cand, rc.cnt[warp][j]);
+          const uint8_t zf = zfl[j * kTopoCap + a];
+          if (!(na == (1ull << d) && (zf & 2))) {  // the placement pins the node's domain
+            pin |= 1u << j;
+            if (!((rc.m_neutral[j] >> d) & 1) || !((zf & 1) || rc.m_wk[j])) slow = true;
+          }
+          dd[j] = d;
+        }
+        if (rej) continue;
+      }
+      mine = key;
+      best_a = a;
+      best_slow = slow;
+      best_pin = pin;
+      best_d[0] = dd[0]; best_d[1] = dd[1];
+#pragma unroll
+      for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
+    }
+    unsigned pay = 0;
+    bool my_closed = false;
+    if (best_a >= 0) {
+      long long cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+      for (int r = 0; r < kHotRes; ++r) { cb1[r] = hs->bound[r][best_a]; cb2[r] = hs->bound2[r][best_a]; }
+      const unsigned short fl2 = (unsigned short)(hs->flags[best_a] | ((first.res & 0xF) << 1));
+      my_closed = node_closed(bq, min_req, RH, cb1, cb2, fl2);
+      pay = run_pay(best_a, best_slow, my_closed, best_pin, best_d);
+    }
+    // ---- block argmin with payload: ONE barrier (double-buffered scratch)
+    const unsigned long long wmin = warp_min_u64(mine);
+    if (mine == wmin && mine != ~0ull) { rc.red_key[parity][warp] = wmin; rc.red_pay[parity][warp] = pay; }
+    else if (lane == 0 && wmin == ~0ull) rc.red_key[parity][warp] = ~0ull;
+    __syncthreads();
+    const unsigned long long rk = lane < nwarps ? rc.red_key[parity][lane] : ~0ull;
+    const unsigned rp = lane < nwarps ? rc.red_pay[parity][lane] : 0;
+    parity ^= 1;
+    const unsigned long long wkey = warp_min_u64(rk);
+    if (wkey != ~0ull) {
+      const unsigned src = __ballot_sync(0xffffffffu, rk == wkey);
+      const unsigned wp = __shfl_sync(0xffffffffu, rp, __ffs(src) - 1);
+      if (wp & (1u << 11)) { status = 1; break; }  // the winner needs the full evaluation
+      const bool closed = (wp >> 12) & 1;
+      const int wd[kRunMask] = {(int)((wp >> 15) & 0xF), (int)((wp >> 19) & 0xF)};
+      if (mine == wkey) {  // the owner commits its node
+        const int a = best_a, n = hs->node[a];
+        const unsigned short fl = hs->flags[a];
+#pragma unroll
+        for (int r = 0; r < kHotRes; ++r) hs->q[r][a] = bq[r];
+        if ((first.res & 0xF) & ~((fl >> 1) & 0xF)) {
+          s.nn_req_present[n] |= first.res;  // rare (a request key new to the node): the only global load of a commit
+          hs->flags[a] = fl | (unsigned short)((first.res & 0xF) << 1);
+        }
+        const int count = (int)(wkey >> 32) + 1;
+        s.nn_count[n] = count;
+        s.nn_tb[n] = -(tick + 1);
+        hs->key[a] = order_key(count, -(tick + 1));
+        hs->rejected[a] = KSCHED_NONE;
+        for (int j = 0; j < n_host; ++j) {  // Topology.Record, hostname groups
+          const int times = rc.h_times[j];
+          if (!times) continue;
+          const int old = hc[j * kTopoCap + a];
+          const int now = old + times > 0xFFFF ? 0xFFFF : old + times;
+          hc[j * kTopoCap + a] = (uint16_t)now;
+          s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n] = (uint16_t)now;
+          if (old == 0) s.grp_host_total[rc.h_group[j]] = ++rc.h_total[j];
+        }
+        for (int j = 0; j < n_mask; ++j) {
+          const int d = best_d[j], k = rc.m_key[j];
+          if ((best_pin >> j) & 1) {  // requirements.Add(In{d}) on the node
+            zval[j * kTopoCap + a] = 1ull << d;
+            zfl[j * kTopoCap + a] = 3;
+            s.nn_vals[(size_t)k * MAXN + n] = 1ull << d;
+            s.nn_meta[n] = (s.nn_meta[n] | (1ull << (KSCHED_META_PRESENT_SHIFT + k))) & ~(1ull << (KSCHED_META_COMPLEMENT_SHIFT + k));  // once per node and key
+          }
+          // the node's domain is the single value d: Record it (this warp's copy still holds the old count; lane 0 bumps it below)
+          if (rc.m_rec[j]) s.grp_cnt[(size_t)rc.m_group[j] * 64 + d] = rc.cnt[warp][j][d] + 1;
+        }
+        s.assign[pod] = NE + n;
+        s.place_seq[pod] = seq;
+        if (closed) {  // the node leaves the active set; the last open node takes its slot (and this thread becomes its owner)
+          for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + n] = bq[r];
+          const int last = n_active - 1;
+          if (a != last) {
+            hs->key[a] = hs->key[last];
+#pragma unroll
+            for (int r = 0; r < kHotRes; ++r) { hs->q[r][a] = hs->q[r][last]; hs->bound[r][a] = hs->bound[r][last]; hs->bound2[r][a] = hs->bound2[r][last]; }
+            hs->node[a] = hs->node[last]; hs->flags[a] = hs->flags[last]; hs->absorbed[a] = hs->absorbed[last]; hs->rejected[a] = hs->rejected[last];
+            if (topo) {
+              for (int j = 0; j < n_host; ++j) hc[j * kTopoCap + a] = hc[j * kTopoCap + last];
+              for (int j = 0; j < n_mask; ++j) { zval[j * kTopoCap + a] = zval[j * kTopoCap + last]; zfl[j * kTopoCap + a] = zfl[j * kTopoCap + last]; }
+            }
+          }
+        }
+      }
+      __syncwarp();  // the owner has read its warp's counters
+      if (lane == 0)
+        for (int j = 0; j < n_mask; ++j) if (rc.m_rec[j]) rc.cnt[warp][j][wd[j]]++;
+      __syncwarp();
+      if (closed) --n_active;
+      ++tick;
+      ++seq;
+    } else {
+      // ---- nobody accepts: NewNode + Add replayed from a variant (templates: the one the variant was created from)
+      if (n_new >= MAXN || n_active >= kActCap || (topo && n_active >= kTopoCap) || rc.n_var == 0) { status = 1; break; }
+      int fd[kRunMask] = {0, 0};
+      bool ok = true;
+      for (int j = 0; j < n_host; ++j) ok = ok && !(rc.h_type[j] == 0 && rc.h_self[j] > rc.h_skew[j]);
+      for (int j = 0; j < n_mask && ok; ++j) {
+        const uint64_t cand = rc.m_tallow[j] & okm[j];
+        if (!cand) { ok = false; break; }
+        fd[j] = run_pick(cand, rc.cnt[warp][j]);
+      }
+      int vi = -1;
+      for (int i = 0; i < rc.n_var && ok; ++i) {
+        bool same = true;
+        for (int j = 0; j < n_mask; ++j) same = same && rc.var[i].dom[j] == fd[j];
+        if (same) { vi = i; break; }
+      }
+      if (vi < 0) { status = 1; break; }
+      const RunVariant& v = rc.var[vi];
+      const int n = n_new, a = n_active;
+      for (int w = tid; w < W32; w += T) s.nn_opts[(size_t)w * MAXN + n] = v.opts[w];
+      if (tid < c.n_keys) s.nn_vals[(size_t)tid * MAXN + n] = v.vals[tid];
+      if (tid == a % T) {  // the new slot's owner
+        hs->key[a] = order_key(1, tick + 1);
+#pragma unroll
+        for (int r = 0; r < kHotRes; ++r) { hs->q[r][a] = v.q[r]; hs->bound[r][a] = v.b1[r]; hs->bound2[r][a] = v.b2[r]; }
+        hs->node[a] = n;
+        hs->flags[a] = v.fl;
+        hs->absorbed[a] = simple ? cls : KSCHED_NONE;
+        hs->rejected[a] = KSCHED_NONE;
+        s.nn_meta[n] = v.meta;
+        s.nn_tmpl[n] = (uint8_t)(v.fl >> 8);
+        for (int r = 0; r < KSCHED_MAX_RES; ++r) s.nn_req[(size_t)r * MAXN + n] = v.q[r];
+        s.nn_req_present[n] = v.qp;
+        s.nn_hp[n] = 0;
+        s.nn_count[n] = 1;
+        s.nn_tb[n] = tick + 1;
+        s.assign[pod] = NE + n;
+        s.place_seq[pod] = seq;
+        for (int j = 0; j < n_host; ++j) {
+          const int times = rc.h_times[j];
+          hc[j * kTopoCap + a] = (uint16_t)times;
+          if (times) {
+            s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n] = (uint16_t)times;
+            s.grp_host_total[rc.h_group[j]] = ++rc.h_total[j];
+          }
+        }
+        for (int j = 0; j < n_mask; ++j) {
+          zval[j * kTopoCap + a] = 1ull << fd[j];
+          zfl[j * kTopoCap + a] = 3;
+          if (rc.m_rec[j]) s.grp_cnt[(size_t)rc.m_group[j] * 64 + fd[j]] = rc.cnt[warp][j][fd[j]] + 1;
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        for (int j = 0; j < n_mask; ++j) if (rc.m_rec[j]) rc.cnt[warp][j][fd[j]]++;
+      __syncwarp();
+      ++tick;
+      ++seq;
+      ++n_new;
+      ++n_active;
+    }
+    // ---- the pod is placed: pop it, move to the next one of the same class
+    ++qi;
+    head = head + 1 == qcap ? 0 : head + 1;
+    --qlen;
+    ++add_calls;
+    ++placed;
+    if (qi >= s.n_pods || qlen == 0) break;
+    if (cls1 != first.cls64) break;
+    pod = pod1;
+    pod1 = pod2; cls1 = cls2;
+    if (qi + 2 < s.n_pods) { pod2 = s.order[qi + 2]; cls2 = ffd_rows[qi + 2].reserved; } else cls2 = ~0ull;
+    if (tid == 0 && qi + 32 < s.n_pods) prefetch_l2(reinterpret_cast<const char*>(ffd_rows + qi + 32) + 128);
+    if (tid == 2 && (qi & 31) == 0 && qi + 96 < s.n_pods) prefetch_l2(s.order + qi + 96);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    io.qi = qi; io.head = head; io.qlen = qlen; io.tick = tick; io.seq = seq; io.n_active = n_active; io.n_new = n_new; io.parity = parity;
+    io.add_calls = add_calls; io.placed = placed; io.status = status;
+  }
+  __syncthreads();
+}
+
 #ifdef KSCHED_PROFILE_PACK
 #define PK_T(i) { long long _now = clock64(); pk_acc[i] += _now - pk_last; pk_last = _now; }
 #else
@@ -1029,19 +1482,16 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
   const int NE = s.n_existing, MAXN = s.max_new;
   const int R = c.n_res, RH = R < kHotRes ? R : kHotRes;
 
-  HotSmem* hs = reinterpret_cast<HotSmem*>(dyn_smem);
   int64_t* sm_alloc = reinterpret_cast<int64_t*>(dyn_smem + sizeof(HotSmem));
   const Hot H = make_hot(s);
   if (s.alloc_in_smem)
     for (int i = tid; i < R * c.n_types; i += blockDim.x) sm_alloc[i] = c.alloc_sorted[i];
 
   PodTopo& pt = g_pt;
-  unsigned long long (*red)[32] = g_red;
-  StepShared& sh = g_sh;
   uint32_t* tmpl_taintset = g_tmpl_taintset;
   __shared__ WarpIO wio;
   if (tid < c.n_templates) tmpl_taintset[tid] = c.templates[tid].taintset;
-  if (tid == 0) pt.n = 0;
+  if (tid == 0) { pt.n = 0; g_rc.cls = KSCHED_NONE; g_rc.eligible = 0; }
 
   int head = 0, qlen = s.n_pods;
   const int qcap = s.n_pods + 1;
@@ -1051,6 +1501,11 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
   int fatal = 0;
   bool pt_nonempty = false;
   uint32_t pt_class = KSCHED_NONE, row_class = KSCHED_NONE;
+  int fresh_valid = 0, fresh_a = 0;
+  uint32_t fresh_cls = KSCHED_NONE;
+  // class-run bookkeeping: classes found ineligible are not tried again; a run that places nothing backs off
+  uint32_t run_block_cls = KSCHED_NONE;
+  int run_skip = 0, run_fail = 0;
 
   for (int i = tid; i < s.n_pods; i += blockDim.x) {
     s.queue[i] = s.order[i];
@@ -1071,7 +1526,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
 
   while (qlen > 0) {
     // ---- register-resident mode (see warp_resident_loop): entered when the next pod is plain and <= 32 nodes are open
-    if (fast_allowed && qi < s.n_pods && n_active > 0 && n_active <= 32 && simple_pod_regs(nxt)) {
+    if (fast_allowed && s.use_warp_loop && !fresh_valid && qi < s.n_pods && n_active > 0 && n_active <= 32 && simple_pod_regs(nxt)) {
       __syncthreads();
       if (tid == 0) { wio.qi = qi; wio.head = head; wio.qlen = qlen; wio.tick = tick; wio.seq = seq; wio.n_active = n_active; wio.add_calls = add_calls; }
       __syncthreads();
@@ -1081,6 +1536,48 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
       if (qlen == 0) break;
       if (qi < s.n_pods) nxt = load_pod_regs(ffd_rows + qi, s.order[qi]);
       // the pod the warp loop stopped at (new node needed, non-plain pod, end of the first pass) takes the block-wide path
+    }
+    PK_T(0)
+    // ---- class-run mode (see class_run): first-pass pods of a class whose accept test is exact from shared memory
+    bool skip_run = true;
+    if (fast_allowed && s.use_class_run && qi < s.n_pods && n_active <= kActCap) {
+      const bool topo_cls = nxt.topo_begin != nxt.topo_end;
+      const bool shape_ok = nxt.hpc == 0 && nxt.hpe == 0 && (nxt.res >> kHotRes) == 0 &&
+                            (!topo_cls || (((nxt.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0 && nxt.itype == KSCHED_NONE && nxt.hostname == KSCHED_NONE));
+      if (shape_ok && (unsigned)nxt.cls64 != run_block_cls) {
+        if (fresh_valid && fresh_cls == (unsigned)nxt.cls64) skip_run = false;  // a fresh node of this class to capture
+        else if (run_skip > 0) --run_skip;
+        else skip_run = false;
+      }
+    }
+    if (!skip_run) {
+      __syncthreads();
+      if (tid == 0) {
+        RunIO& io = g_rio;
+        io.qi = qi; io.head = head; io.qlen = qlen; io.tick = tick; io.seq = seq; io.n_active = n_active; io.n_new = n_new; io.parity = parity;
+        io.add_calls = add_calls; io.placed = 0; io.status = 0;
+        io.fresh_valid = fresh_valid; io.fresh_a = fresh_a; io.fresh_cls = fresh_cls;
+      }
+      __syncthreads();
+      class_run(nxt);
+      const RunIO& io = g_rio;
+      const int placed = io.placed, status = io.status;
+      qi = io.qi; head = io.head; qlen = io.qlen; tick = io.tick; seq = io.seq; n_active = io.n_active; n_new = io.n_new; parity = io.parity;
+      add_calls = io.add_calls;
+      fresh_valid = 0;
+#ifdef KSCHED_PROFILE_PACK
+      if (tid == 0) { s.counters[40] += 1; s.counters[41] += placed; s.counters[42] += status == 1; s.counters[43] += status == 2; }
+#endif
+      if (status == 2) run_block_cls = (unsigned)nxt.cls64;
+      if (placed == 0 && status == 1) { run_fail = run_fail < 6 ? run_fail + 1 : 6; run_skip = (1 << run_fail) - 1; }
+      else if (placed > 0) run_fail = 0;
+      PK_T(1)
+      if (qlen == 0) break;
+      if (placed > 0) {
+        if (qi < s.n_pods) nxt = load_pod_regs(ffd_rows + qi, s.order[qi]);
+        if (status == 0) continue;  // class change / end of the first pass: pick the mode for the next pod
+      }
+      // status 1 / 2: the pod at qi takes the generic step
     }
     PodRegs cur;
     const bool first_pass = qi < s.n_pods;
@@ -1094,97 +1591,21 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
       if (s.last_epoch[qpod] == epoch && s.last_len[qpod] == qlen) break;  // Pop(): no progress in a whole cycle (queue.go:52)
       cur = load_pod_regs(s.classes + s.pod_class[qpod], qpod);
     }
-    PK_T(0)
     const int fpos_first = qi;
     ++qi;
     head = head + 1 == qcap ? 0 : head + 1;
     --qlen;
     ++add_calls;
-
-    // ---- steady-state path: a pod whose requirements cannot change anything, against in-flight nodes whose surviving
-    // options contain a dominant type. R integer compares per candidate, block argmin, the winner commits.
-    bool done = false;
-    const bool plain_pod = ((cur.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0 && cur.itype == KSCHED_NONE && cur.hostname == KSCHED_NONE &&
-                           cur.topo_begin == cur.topo_end;
-    const bool simple_pod = simple_pod_regs(cur);
-    const unsigned cur_cls = (unsigned)cur.cls64;
-    if (fast_allowed && (plain_pod || simple_pod) && n_active > 0 && n_active <= kActCap) {
-      unsigned long long mine = ~0ull;
-      int best_a = -1;
-      long long bq[kHotRes] = {0, 0, 0, 0};
-      for (int a = tid; a < n_active; a += blockDim.x) {  // hot state straight from shared memory
-        const unsigned long long key = hs->key[a];
-        if (key >= mine) continue;
-        const unsigned short fl = hs->flags[a];
-        if (!((cur.tol >> tmpl_taintset[fl >> 8]) & 1)) continue;
-        if (simple_pod && hs->rejected[a] == cur_cls) continue;  // memo: refused this class, untouched since
-        const uint32_t qp = ((fl >> 1) & 0xF) | cur.res;
-        long long q[kHotRes], b1[kHotRes], b2[kHotRes];
-#pragma unroll
-        for (int r = 0; r < kHotRes; ++r) { q[r] = hs->q[r][a] + cur.req[r]; b1[r] = hs->bound[r][a]; b2[r] = hs->bound2[r][a]; }
-        const int qf = quick_fit(q, qp, RH, b1, b2, fl);
-        if (qf == 0) continue;
-        if (cur.hpc && (s.nn_hp[hs->node[a]] & cur.hpc)) continue;
-        // inexact resource test, or an unknown requirement verdict for this class: the pod takes the generic path
-        if (qf == 2 || !(plain_pod || (simple_pod && hs->absorbed[a] == cur_cls))) { mine = 0; break; }
-        mine = key;
-        best_a = a;
-#pragma unroll
-        for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
-      }
-      PK_T(1)
-      const unsigned long long wkey = block_min_u64_db(mine, red, parity);
-      PK_T(2)
-      if (wkey != 0 && wkey != ~0ull) {
-        if (mine == wkey) {
-          const int a = best_a, n = H.node(a);
-          unsigned short fl = H.flags(a);
-#pragma unroll
-          for (int r = 0; r < kHotRes; ++r) H.q(r, a) = bq[r];
-          for (int r = kHotRes; r < R; ++r)
-            if ((cur.res >> r) & 1) s.nn_req[(size_t)r * MAXN + n] += cur.row->requests[r];
-          if ((cur.res >> kHotRes) || ((cur.res & 0xF) & ~((fl >> 1) & 0xF))) {
-            s.nn_req_present[n] |= cur.res;
-            H.flags(a) = fl | (unsigned short)((cur.res & 0xF) << 1);
-          }
-          if (cur.hpe) s.nn_hp[n] |= cur.hpe;
-          const int count = (int)(wkey >> 32) + 1;
-          s.nn_count[n] = count;
-          s.nn_tb[n] = -(tick + 1);
-          H.key(a) = order_key(count, -(tick + 1));
-          H.rejected(a) = KSCHED_NONE;
-          long long cb1[kHotRes], cb2[kHotRes];
-#pragma unroll
-          for (int r = 0; r < kHotRes; ++r) { cb1[r] = H.bound(r, a); cb2[r] = H.bound2(r, a); }
-          const bool closed = node_closed(bq, s.min_req, RH, cb1, cb2, H.flags(a));
-          s.assign[cur.pod] = NE + n;
-          s.place_seq[cur.pod] = seq;
-          if (closed) {
-            for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + n] = bq[r];
-            if (a != n_active - 1) H.move(a, n_active - 1);
-          }
-          sh.placed_closed = closed ? 1 : 0;
-        }
-        ++tick;
-        ++seq;
-        PK_T(3)
-        __syncthreads();
-        PK_T(4)
-        if (sh.placed_closed) --n_active;
-        done = true;
-      }
-    }
-    if (!done) {
 #ifdef KSCHED_PROFILE_PACK
-      if (tid == 0) s.counters[8 + 9] += 1;
+    if (tid == 0) s.counters[8 + 9] += 1;
 #endif
-      LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited, pt_class, row_class};
-      generic_step(cur, first_pass, fpos_first, L);
-      head = L.head; qlen = L.qlen; n_new = L.n_new; n_active = L.n_active; tick = L.tick; seq = L.seq; parity = L.parity; fatal = L.fatal;
-      epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited; pt_class = L.pt_class; row_class = L.row_class;
-      if (fatal) break;
-      PK_T(5)
-    }
+    LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited, pt_class, row_class, 0, 0, KSCHED_NONE};
+    generic_step(cur, first_pass, fpos_first, L);
+    head = L.head; qlen = L.qlen; n_new = L.n_new; n_active = L.n_active; tick = L.tick; seq = L.seq; parity = L.parity; fatal = L.fatal;
+    epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited; pt_class = L.pt_class; row_class = L.row_class;
+    fresh_valid = L.fresh_valid; fresh_a = L.fresh_a; fresh_cls = L.fresh_cls;
+    if (fatal) break;
+    PK_T(5)
   }
   __syncthreads();
   for (int a = tid; a < n_active; a += blockDim.x) {
@@ -1199,8 +1620,8 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
     s.counters[4] = fatal;
     s.counters[5] = add_calls;
 #ifdef KSCHED_PROFILE_PACK
-    s.counters[8 + 6] = pk_acc[0] + pk_acc[1] + pk_acc[2] + pk_acc[3] + pk_acc[4];  // block-wide fast path cycles
-    s.counters[8 + 7] = pk_acc[5];                                                       // cycles inside generic calls (incl. call)
+    s.counters[8 + 6] = pk_acc[1];  // cycles inside class_run calls
+    s.counters[8 + 7] = pk_acc[5];  // cycles inside generic calls (incl. call)
 #endif
   }
 }

@@ -98,6 +98,10 @@ struct PackState {
   uint8_t* fd_dom;
   int count_visited;                 // keep the exact nodes_visited statistic (costs a pass over all in-flight nodes per pod)
   int alloc_in_smem;
+  int run_off;                       // byte offset (after HotSmem) of the class-run loop's per-node arrays in dynamic shared memory
+  int any_limits;                    // some template has active provisioner limits (fresh nodes are then never replayed from a variant)
+  int use_warp_loop;                 // register-resident warp loop enabled (KSCHED_NO_WARPLOOP=1 turns it off for A/B timing)
+  int use_class_run;                 // class-run loop enabled (KSCHED_NO_CLASSRUN=1 turns it off for A/B timing)
   // topology counters
   int32_t* grp_cnt;                  // [n_groups][64]
   uint64_t* grp_registered;          // [n_groups]

@@ -144,7 +144,9 @@ def test_two_handles_on_one_device_solve_concurrently(pkg, oracle):
     _compare(pkg, oracle, a, [])
 
 
-from consolidation_answers import CASES as CONSOLIDATION_CASES
+from consolidation_answers import CASES as _CONS, CPU_ONLY_CASES as _CONS_LATE
+
+CONSOLIDATION_CASES = _CONS + _CONS_LATE
 
 
 @pytest.mark.parametrize("name,ref,build", CONSOLIDATION_CASES, ids=[c[0] for c in CONSOLIDATION_CASES])
