@@ -629,6 +629,9 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
         const ksched_topo_group& g = pb->groups[ct.group];
         RelX x{};
         x.group = ct.group; x.flags = ct.flags; x.key = g.key; x.type = g.type; x.has_filter = g.filter_begin != g.filter_end;
+        // a term without any requirement is Compatible with every node (topologynodefilter.go:57-70): such a filter always matches
+        for (uint32_t f = g.filter_begin; f < g.filter_end && f < (uint32_t)pb->n_filter_terms; ++f)
+          if (((pb->filter_terms[f].meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0) x.has_filter = 0;
         x.max_skew = g.max_skew; x.host_row = host_row[ct.group];
         relx[e] = x;
       }
@@ -748,7 +751,6 @@ static int run_feasibility(ksched_handle* h) {
   const int warps_per_block = kK1Threads / 32;
   const int want_warps = std::max(1, (h->n_pods + 7) / 8);
   const int blocks = std::max(1, std::min(148, (want_warps + warps_per_block - 1) / warps_per_block));
-  CUDA_TRY(h, cudaFuncSetAttribute(feasibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k1.dbg = nullptr;
 #ifdef KSCHED_PROFILE_K1
   CUDA_TRY(h, h->d_k1dbg.ensure(8));
@@ -763,7 +765,9 @@ static int run_feasibility(ksched_handle* h) {
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, done, 0));
     h->k1_host = k1;
     CUDA_TRY(h, cudaMemcpyToSymbolAsync(g_k1, &h->k1_host, sizeof(K1Params), 0, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaFuncSetAttribute(feasibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per function: under the launch lock
     feasibility_kernel<<<blocks, kK1Threads, smem, h->stream>>>();
+    CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(done, h->stream));
   }
 #ifdef KSCHED_PROFILE_K1
@@ -854,9 +858,8 @@ static int run_pack(ksched_handle* h) {
   const size_t smem = sizeof(HotSmem) + (size_t)s.run_off + kRunArrayBytes;
   s.any_limits = 0;
   for (const ksched_template& tm : h->h_templates) if (tm.has_limits && tm.limit_present) s.any_limits = 1;
-  s.use_warp_loop = getenv("KSCHED_NO_WARPLOOP") ? 0 : 1;
+  s.use_warp_loop = getenv("KSCHED_WARPLOOP") ? 1 : 0;  // superseded by the class-run loop (kept for A/B timing: 18 ms vs 8 ms on C2 when both are on)
   s.use_class_run = getenv("KSCHED_NO_CLASSRUN") ? 0 : 1;
-  CUDA_TRY(h, cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // block size: the chain is latency-bound on ONE thread's commit; more warps only help when there are many candidate
   // nodes to examine per pod (existing nodes, large in-flight sets)
   int threads = h->n_existing >= 2048 ? kPackThreads : (h->n_existing >= 256 ? 256 : 128);
@@ -868,7 +871,10 @@ static int run_pack(ksched_handle* h) {
     if (!done) CUDA_TRY(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, done, 0));  // no-op for an event that was never recorded
     CUDA_TRY(h, cudaMemcpyToSymbolAsync(g_k2, &k2, sizeof(K2Params), 0, cudaMemcpyHostToDevice, h->stream));
+    // the attribute belongs to the function, not to the handle: set it under the same lock as the launch
+    CUDA_TRY(h, cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pack_kernel<<<1, threads, smem, h->stream>>>();
+    CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(done, h->stream));
   }
   finalize_options_kernel<<<148, 256, 0, h->stream>>>(h->cat, h->d_counters.ptr, h->d_nn_req.ptr, h->d_nn_req_present.ptr, h->d_nn_opts.ptr, h->max_new);

@@ -40,6 +40,7 @@ struct HotSmem {
   //            been committed to the node since.
   unsigned absorbed[kActCap];
   unsigned rejected[kActCap];
+  unsigned long long nn_last[kActCap];  // class_run: the key a tombstoned node had when it left the active set
 };
 
 struct Hot {
@@ -1019,18 +1020,26 @@ __device__ __noinline__ void warp_resident_loop(WarpIO* io) {
 
 // ---- class-run loop ------------------------------------------------------------------------------------------------
 // Consecutive pods of the queue usually belong to ONE class (a deployment: identical row, identical topology terms). For
-// such a run the whole CTA stays in this loop: ONE block barrier per pod, no global LOAD on the chain.
-//  * every open node is owned by thread (slot % blockDim): only its owner ever reads or writes its hot state, so a
-//    commit needs no barrier to become visible; the block argmin carries a payload (slot, closed, pinned domains) from
-//    which every thread updates the loop-carried scalars and every warp its own copy of the spread counters;
-//  * for topology classes the per-node inputs of TopologyGroup.Get live in shared memory next to the hot state: the
-//    count of every hostname-keyed group of the class on the node, and the node's admissible domains for every spread key
-//    (loaded once per run, kept in step by the commits; counters are written through to global memory with plain stores /
-//    smem-mirrored values, so the generic step always finds them current);
-//  * a candidate is accepted here only when the verdict is EXACT and nothing but counters changes: resources by the
-//    Pareto-front test, requirements untouched (plain / absorbed classes) or a spread domain that is already pinned on the
-//    node - or that can be pinned without touching the option set (DevCatalog::pin_neutral). Any other winner, a pod that
-//    fails, or a fresh node of a shape not seen before in the run hands the pod to generic_step (status 1);
+// such a run the whole CTA stays in this loop: ONE block barrier per pod, no global load and (almost) no global store on
+// the chain, ~120 instructions per warp and pod.
+//  * every open node is owned by thread (slot % blockDim): only its owner ever reads or writes its state, so a commit
+//    needs no barrier to become visible; the block argmin carries a payload (slot, domains) from which every warp updates
+//    its own copy of the spread counters;
+//  * everything the accept test of a run needs from a node collapses into ONE word per node, `rp`:
+//      room   = how many more pods of THIS class fit by the exact Pareto-front resource test (computed once per run with
+//               integer divisions, decremented by the commits; 0 also covers untolerated taints / a memoised refusal,
+//               kRoomSlow = "verdict not exact here"),
+//      dead   = a hostname-keyed group of the class (anti-affinity, hostname spread) no longer admits the node - known at
+//               the commit that fills it, because only this run's commits change those counts,
+//      placed = pods of the run the node took; requests, order statistics and hostname counters are written back from it
+//               when the run ends;
+//    plus, per spread key of the class, the node's admissible domains (`zv`);
+//  * a candidate is accepted here only when the verdict is EXACT and nothing but counters changes: requirements untouched
+//    (plain / absorbed classes) or a spread domain that is already pinned on the node - or that can be pinned without
+//    touching the option set (DevCatalog::pin_neutral). Any other winner, a pod that fails, or a fresh node of a shape not
+//    seen before in the run hands the pod to generic_step (status 1);
+//  * a node that becomes full is tombstoned (key = ~0) and the active list is compacted when the run ends; assignments
+//    are staged per queue chunk and stored coalesced;
 //  * fresh nodes replay a VARIANT: NewNode+Add for (class, template, resulting requirement masks) is a pure function
 //    when no provisioner limit is active (same argument as PackState::fd_*), so the node generic_step created last for
 //    this class is captured (options, masks, requests, Pareto front) and replayed for every later pod of the run whose
@@ -1042,7 +1051,9 @@ constexpr int kTopoCap = 768;    // open nodes whose per-class topology inputs f
 constexpr int kRunVariants = 4;
 constexpr int kRunW32 = 64;      // option words a variant holds (T <= 2048)
 constexpr int kRunWarps = kPackThreads / 32;
-constexpr size_t kRunArrayBytes = (size_t)kTopoCap * (kRunMask * 8 + kRunHost * 2 + kRunMask);
+constexpr int kRunChunk = 128;   // queue entries staged in shared memory at a time
+constexpr unsigned kRoomSlow = 0xFFFFu, kRoomMax = 0x7FFEu, kRpDead = 0x80000000u;
+constexpr size_t kRunArrayBytes = (size_t)kTopoCap * (kRunMask * 4 + kRunHost * 2) + (size_t)kActCap * 4;
 
 struct RunVariant {
   uint32_t opts[kRunW32];
@@ -1051,6 +1062,7 @@ struct RunVariant {
   long long q[KSCHED_MAX_RES];
   long long b1[kHotRes], b2[kHotRes];
   uint32_t qp;
+  uint32_t rp;            // room of the fresh node for further pods of the class (+ dead flag)
   unsigned short fl;      // HotSmem::flags of the fresh node (front bits, request keys, template)
   uint8_t dom[kRunMask];  // domain each spread relation pinned
 };
@@ -1058,15 +1070,18 @@ struct RunCtx {
   uint32_t cls;           // class the relation tables and variants belong to (KSCHED_NONE: none)
   int eligible;
   int n_host, n_mask, n_var, var_next;
-  int h_row[kRunHost], h_group[kRunHost], h_skew[kRunHost];
-  int h_total[kRunHost];  // mirror of grp_host_total (written by the committing thread; one commit per barrier interval)
-  uint8_t h_type[kRunHost], h_self[kRunHost], h_times[kRunHost];
+  int tomb;               // nodes tombstoned by the current run
+  int h_row[kRunHost], h_group[kRunHost], h_lim[kRunHost];  // h_lim: largest count of the group on a node that still admits the pod
+  int h_inc[kRunHost];    // hostnames that got their first matching pod in this run (grp_host_total)
+  uint8_t h_times[kRunHost];
   int m_group[kRunMask], m_skew[kRunMask];
   uint8_t m_key[kRunMask], m_self[kRunMask], m_rec[kRunMask], m_wk[kRunMask];
-  uint64_t m_registered[kRunMask], m_neutral[kRunMask], m_tallow[kRunMask];
+  uint32_t m_registered[kRunMask], m_neutral[kRunMask], m_tallow[kRunMask];
   int32_t cnt[kRunWarps][kRunMask][kRunDom];  // one copy of the spread counters per warp (updated by its lane 0)
   unsigned long long red_key[2][32];
   unsigned red_pay[2][32];
+  uint32_t q_pod[2][kRunChunk], q_cls[2][kRunChunk];  // upcoming queue entries (pod, class), double-buffered
+  int32_t q_node[2][kRunChunk];                        // where the entry was placed (ksched_result.assign)
   RunVariant var[kRunVariants];
 };
 __shared__ RunCtx g_rc;
@@ -1081,43 +1096,69 @@ struct RunIO {
 };
 __shared__ RunIO g_rio;
 
-// payload of the block argmin
-__device__ __forceinline__ unsigned run_pay(int a, bool slow, bool closed, unsigned pin, const int* d) {
-  return (unsigned)a | (slow ? 1u << 11 : 0) | (closed ? 1u << 12 : 0) | (pin << 13) | ((unsigned)d[0] << 15) | ((unsigned)d[1] << 19);
-}
 // first domain in (count, id) order among `cand` (non-empty)
-__device__ __forceinline__ int run_pick(uint64_t cand, const int32_t* cn) {
-  int d = __ffsll((long long)cand) - 1;
+__device__ __forceinline__ int run_pick(uint32_t cand, const int32_t* cn) {
+  int d = __ffs(cand) - 1;
   cand &= cand - 1;
   int32_t best = cn[d];
   while (cand) {
-    const int e = __ffsll((long long)cand) - 1;
+    const int e = __ffs(cand) - 1;
     cand &= cand - 1;
     if (cn[e] < best) { best = cn[e]; d = e; }
   }
   return d;
 }
+// How many more pods with request vector `req` (keys `res`) the node at slot a can take: exact by the Pareto front of its
+// options (quick_fit for the k-th pod <=> k <= room); kRoomSlow when the front is not exact.
+__device__ __noinline__ unsigned run_room(const HotSmem* hs, int a, const long long* req, uint32_t res, int RH) {
+  const unsigned short fl = hs->flags[a];
+  const uint32_t qp = ((fl >> 1) & 0xF) | res;
+  long long best = 0;
+  bool inexact_ok = true;
+  for (int f = 0; f < 2; ++f) {
+    if (f == 1 && !(fl & kFlTwo)) break;
+    long long rf = kRoomMax;
+    for (int r = 0; r < RH; ++r) {
+      if (!((qp >> r) & 1)) continue;
+      const long long slack = (f ? hs->bound2[r][a] : hs->bound[r][a]) - hs->q[r][a];
+      if (req[r] > 0) {
+        const long long k = slack < req[r] ? 0 : slack / req[r];
+        rf = k < rf ? k : rf;
+      } else if (slack < 0) rf = 0;
+    }
+    if (f == 0) inexact_ok = rf > 0;
+    best = rf > best ? rf : best;
+  }
+  if (!(fl & kFlExact)) return inexact_ok ? kRoomSlow : 0;  // per-resource maxima only: a necessary test
+  return (unsigned)best;
+}
 
-__device__ __noinline__ void class_run(const PodRegs& first) {
+__device__ __noinline__ void class_run(const PodRegs& first_in) {
   KS_K2
   RunCtx& rc = g_rc;
   RunIO& io = g_rio;
   HotSmem* hs = reinterpret_cast<HotSmem*>(dyn_smem);
-  uint64_t* zval = reinterpret_cast<uint64_t*>(dyn_smem + sizeof(HotSmem) + s.run_off);   // [kRunMask][kTopoCap]
-  uint16_t* hc = reinterpret_cast<uint16_t*>(zval + (size_t)kRunMask * kTopoCap);           // [kRunHost][kTopoCap]
-  uint8_t* zfl = reinterpret_cast<uint8_t*>(hc + (size_t)kRunHost * kTopoCap);              // [kRunMask][kTopoCap] bit0 present, bit1 present && !complement
+  uint32_t* zv = reinterpret_cast<uint32_t*>(dyn_smem + sizeof(HotSmem) + s.run_off);  // [kRunMask][kTopoCap] bits 0..15 admitted domains, 16 exact (In), 17 present
+  uint32_t* rpv = zv + (size_t)kRunMask * kTopoCap;                                      // [kActCap] room | placed << 16 | dead
+  uint16_t* hc = reinterpret_cast<uint16_t*>(rpv + kActCap);                             // [kRunHost][kTopoCap]
   const uint32_t* tmpl_taintset = g_tmpl_taintset;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int NE = s.n_existing, MAXN = s.max_new, W32 = c.W32;
   const int RH = c.n_res < kHotRes ? c.n_res : kHotRes;
-  const int qcap = s.n_pods + 1;
   const int hstride = s.n_existing + s.max_new;
-  const unsigned cls = (unsigned)first.cls64;
-  const bool topo = first.topo_begin != first.topo_end;
-  const bool plain = plain_pod_regs(first);
+  // the pod row's words, in registers (identical for every pod of the run)
+  const unsigned cls = (unsigned)first_in.cls64;
+  const uint32_t p_res = first_in.res;
+  const uint64_t p_tol = first_in.tol;
+  long long p_req[kHotRes];
+#pragma unroll
+  for (int r = 0; r < kHotRes; ++r) p_req[r] = first_in.req[r];
+  const bool topo = first_in.topo_begin != first_in.topo_end;
+  const bool plain = plain_pod_regs(first_in);
   const bool simple = !topo;
-  int qi = io.qi, head = io.head, qlen = io.qlen, tick = io.tick, seq = io.seq, n_active = io.n_active, n_new = io.n_new, parity = io.parity;
-  long long add_calls = io.add_calls;
+  const uint32_t topo_begin = first_in.topo_begin, topo_end = first_in.topo_end;
+  const int qi0 = io.qi, seq0 = io.seq;
+  int qi = qi0, qlen = io.qlen, tick = io.tick, n_active = io.n_active, n_new = io.n_new, parity = io.parity;
   const int fresh_valid = io.fresh_valid && io.fresh_cls == cls, fresh_a = io.fresh_a;
   __syncthreads();  // everybody has read g_rio; earlier readers of g_rc are done
 
@@ -1129,18 +1170,21 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
       int ok = 1;
       if (topo) {
         if (c.n_templates != 1) ok = 0;
-        for (uint32_t e = first.topo_begin; e < first.topo_end && ok; ++e) {
+        for (uint32_t e = topo_begin; e < topo_end && ok; ++e) {
           const RelX x = s.relx[e];
           const int g = (int)x.group;
           if (!(x.flags & KSCHED_TOPO_CONSTRAINS)) { ok = 0; break; }            // record-only relations: generic step
           if (!s.grp_active[g] || s.grp_min_slot[g] != 0) { ok = 0; break; }      // relaxation-created groups: generic step
           if ((x.flags & KSCHED_TOPO_RECORDS) && x.has_filter) { ok = 0; break; }  // TopologyNodeFilter: generic step
           const int times = ((x.flags & KSCHED_TOPO_RECORDS) ? 1 : 0) + ((x.flags & KSCHED_TOPO_RECORDS_INVERSE) ? 1 : 0);
+          const int self = (x.flags & KSCHED_TOPO_SELECTS) ? 1 : 0;
           if (x.key == KSCHED_KEY_HOSTNAME) {
             if (x.type == 1 || rc.n_host == kRunHost) { ok = 0; break; }
             const int j = rc.n_host++;
-            rc.h_row[j] = x.host_row; rc.h_group[j] = g; rc.h_skew[j] = x.max_skew; rc.h_type[j] = x.type;
-            rc.h_self[j] = (x.flags & KSCHED_TOPO_SELECTS) ? 1 : 0; rc.h_times[j] = (uint8_t)times;
+            rc.h_row[j] = x.host_row; rc.h_group[j] = g; rc.h_times[j] = (uint8_t)times;
+            // spread: count + self <= maxSkew (min is 0 for hostnames, topologygroup.go:186-188); anti-affinity: count == 0
+            long long lim = x.type == 0 ? (long long)x.max_skew - self : 0;
+            rc.h_lim[j] = lim > 0x10000 ? 0x10000 : (lim < -1 ? -1 : (int)lim);
           } else {
             const int k = x.key;
             if (x.type != 0 || rc.n_mask == kRunMask || (x.flags & KSCHED_TOPO_RECORDS_INVERSE) || (c.keys[k].dict_mask >> kRunDom)) { ok = 0; break; }
@@ -1148,10 +1192,10 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
             if (!ok) break;
             const int j = rc.n_mask++;
             rc.m_group[j] = g; rc.m_skew[j] = x.max_skew; rc.m_key[j] = (uint8_t)k;
-            rc.m_self[j] = (x.flags & KSCHED_TOPO_SELECTS) ? 1 : 0; rc.m_rec[j] = (x.flags & KSCHED_TOPO_RECORDS) ? 1 : 0;
-            rc.m_wk[j] = c.keys[k].well_known != 0; rc.m_neutral[j] = c.pin_neutral[k];
+            rc.m_self[j] = (uint8_t)self; rc.m_rec[j] = (x.flags & KSCHED_TOPO_RECORDS) ? 1 : 0;
+            rc.m_wk[j] = c.keys[k].well_known != 0; rc.m_neutral[j] = (uint32_t)c.pin_neutral[k];
             const Req tr = ksched::req_load(c.templates[0].reqs, nullptr, k);
-            rc.m_tallow[j] = tr.present ? ksched::req_allowed(tr, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask;
+            rc.m_tallow[j] = (uint32_t)(tr.present ? ksched::req_allowed(tr, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask);
           }
         }
       }
@@ -1166,24 +1210,51 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
   }
   const int n_host = rc.n_host, n_mask = rc.n_mask;
 
-  // ---- per-run state: spread counters (one copy per warp), per-node topology inputs (each thread loads the slots it owns)
+  // ---- queue staging: the next CH (pod, class) entries; the chunk after them is fetched into registers meanwhile
+  const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
+  const int CH = T < kRunChunk ? T : kRunChunk;  // one entry per thread
+  int cb = qi, buf = 0;
+  uint32_t nx_pod = 0, nx_cls = KSCHED_NONE;
+  if (tid < CH) {
+    const int idx = cb + tid;
+    uint32_t pd = 0, pc = KSCHED_NONE;
+    if (idx < s.n_pods) { pd = s.order[idx]; pc = (uint32_t)ffd_rows[idx].reserved; }
+    rc.q_pod[0][tid] = pd; rc.q_cls[0][tid] = pc;
+    const int idx2 = idx + CH;
+    if (idx2 < s.n_pods) { nx_pod = s.order[idx2]; nx_cls = (uint32_t)ffd_rows[idx2].reserved; }
+  }
+  // ---- per-run state: spread counters (one copy per warp), per-node inputs (each thread fills the slots it owns)
+  if (tid == 0) rc.tomb = 0;
+  if (tid < kRunHost) rc.h_inc[tid] = 0;
   if (topo) {
     for (int j = 0; j < n_mask; ++j) {
       if (lane < kRunDom) rc.cnt[warp][j][lane] = s.grp_cnt[(size_t)rc.m_group[j] * 64 + lane];
-      if (tid == 0) rc.m_registered[j] = s.grp_registered[rc.m_group[j]];
+      if (tid == 0) rc.m_registered[j] = (uint32_t)s.grp_registered[rc.m_group[j]];
     }
-    if (tid < n_host) rc.h_total[tid] = s.grp_host_total[rc.h_group[tid]];
-    for (int a = tid; a < n_active; a += T) {
+  }
+  for (int a = tid; a < n_active; a += T) {
+    const unsigned short fl = hs->flags[a];
+    unsigned rm;
+    if (!((p_tol >> tmpl_taintset[fl >> 8]) & 1)) rm = 0;                        // Taints.Tolerates
+    else if (simple && hs->rejected[a] == cls) rm = 0;                           // memo: refused this class, untouched since
+    else if (simple && !plain && hs->absorbed[a] != cls) rm = kRoomSlow;         // requirement verdict unknown for this class
+    else rm = run_room(hs, a, p_req, p_res, RH);
+    if (topo) {
       const int n = hs->node[a];
-      for (int j = 0; j < n_host; ++j) hc[j * kTopoCap + a] = s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n];
+      for (int j = 0; j < n_host; ++j) {
+        const uint16_t v = s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n];
+        hc[j * kTopoCap + a] = v;
+        if ((int)v > rc.h_lim[j]) rm |= kRpDead;
+      }
       const uint64_t meta = s.nn_meta[n];
       for (int j = 0; j < n_mask; ++j) {
         const int k = rc.m_key[j];
         const Req r = load_soa(s.nn_vals, meta, MAXN, n, k);
-        zval[j * kTopoCap + a] = r.present ? ksched::req_allowed(r, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask;
-        zfl[j * kTopoCap + a] = (uint8_t)((r.present ? 1 : 0) | ((r.present && !r.complement) ? 2 : 0));
+        const uint32_t allowed = (uint32_t)(r.present ? ksched::req_allowed(r, c.keys[k].dict_mask, key_meta(c, k)) : c.keys[k].dict_mask);
+        zv[j * kTopoCap + a] = allowed | ((r.present && !r.complement) ? 1u << 16 : 0) | (r.present ? 1u << 17 : 0);
       }
     }
+    rpv[a] = rm;
   }
   __syncthreads();
   // ---- capture the node generic_step has just created for this class as a fresh-node variant
@@ -1191,14 +1262,17 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
     const int a = fresh_a, n = hs->node[a];
     int dom[kRunMask] = {0, 0};
     bool ok = true;
-    for (int j = 0; j < n_mask; ++j) {
-      const uint64_t v = zval[j * kTopoCap + a];
-      if (!v || (v & (v - 1)) || !(zfl[j * kTopoCap + a] & 2)) ok = false;
-      else dom[j] = __ffsll((long long)v) - 1;
+#pragma unroll
+    for (int j = 0; j < kRunMask; ++j) {
+      if (j >= n_mask) continue;
+      const uint32_t z = zv[j * kTopoCap + a], v = z & 0xFFFF;
+      if (!v || (v & (v - 1)) || !(z & (1u << 16))) ok = false;
+      else dom[j] = __ffs(v) - 1;
     }
     for (int i = 0; i < rc.n_var && ok; ++i) {
       bool same = (rc.var[i].fl >> 8) == (hs->flags[a] >> 8);
-      for (int j = 0; j < n_mask; ++j) same = same && rc.var[i].dom[j] == dom[j];
+#pragma unroll
+      for (int j = 0; j < kRunMask; ++j) same = same && (j >= n_mask || rc.var[i].dom[j] == dom[j]);
       if (same) ok = false;  // already known
     }
     __syncthreads();  // rc.n_var / var_next read by everybody before thread 0 moves them
@@ -1213,6 +1287,7 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
         for (int r = 0; r < kHotRes; ++r) { v.b1[r] = hs->bound[r][a]; v.b2[r] = hs->bound2[r][a]; }
         v.qp = s.nn_req_present[n];
         v.fl = hs->flags[a];
+        v.rp = rpv[a] & (kRpDead | 0xFFFF);
         for (int j = 0; j < kRunMask; ++j) v.dom[j] = (uint8_t)dom[j];
         rc.var_next = (slot + 1) % kRunVariants;
         if (rc.n_var < kRunVariants) rc.n_var++;
@@ -1224,90 +1299,90 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
   long long min_req[kHotRes];
 #pragma unroll
   for (int r = 0; r < kHotRes; ++r) min_req[r] = r < RH ? s.min_req[r] : 0;
-  const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
-  // the next two pods of the queue (id, class), fetched two iterations ahead
-  uint32_t pod = first.pod, pod1 = 0, pod2 = 0;
-  uint64_t cls1 = ~0ull, cls2 = ~0ull;
-  if (qi + 1 < s.n_pods) { pod1 = s.order[qi + 1]; cls1 = ffd_rows[qi + 1].reserved; }
-  if (qi + 2 < s.n_pods) { pod2 = s.order[qi + 2]; cls2 = ffd_rows[qi + 2].reserved; }
-  int placed = 0, status = 0;
+  // relation constants of the commit, in registers
+  int h_times_sum = 0;
+#pragma unroll
+  for (int j = 0; j < kRunHost; ++j) if (j < n_host) h_times_sum += rc.h_times[j];
+  const uint32_t m_reg0 = n_mask > 0 ? rc.m_registered[0] : 0, m_reg1 = n_mask > 1 ? rc.m_registered[1] : 0;
+  const int m_bias0 = n_mask > 0 ? (int)rc.m_self[0] - rc.m_skew[0] : 0, m_bias1 = n_mask > 1 ? (int)rc.m_self[1] - rc.m_skew[1] : 0;
+  const bool m_rec0 = n_mask > 0 && rc.m_rec[0], m_rec1 = n_mask > 1 && rc.m_rec[1];
+  int status = 0;
 
   while (true) {
-    // node-independent half of nextDomainTopologySpread: min count over the pod's domains, domains within max-skew
-    uint64_t okm[kRunMask] = {0, 0};
-    for (int j = 0; j < n_mask; ++j) {
-      const int32_t* cn = rc.cnt[warp][j];
-      const uint64_t reg = rc.m_registered[j];
-      int32_t mn = INT32_MAX;
-      for (uint64_t m = reg; m; m &= m - 1) { const int32_t v = cn[__ffsll((long long)m) - 1]; mn = v < mn ? v : mn; }
-      uint64_t ok = 0;
-      for (uint64_t m = reg; m; m &= m - 1) {
-        const int d = __ffsll((long long)m) - 1;
-        if ((long long)cn[d] + rc.m_self[j] - (long long)mn <= (long long)rc.m_skew[j]) ok |= 1ull << d;
+    int i = qi - cb;
+    if (i == CH) {  // chunk consumed: store its assignments, registers -> the other buffer, fetch the chunk after
+      __syncthreads();  // the last commit's q_node entry is visible
+      if (tid < CH) {
+        const uint32_t pd = rc.q_pod[buf][tid];
+        s.assign[pd] = rc.q_node[buf][tid];
+        s.place_seq[pd] = seq0 + (cb - qi0) + tid;
       }
-      okm[j] = ok;
+      buf ^= 1;
+      cb += CH;
+      i = 0;
+      if (tid < CH) {
+        rc.q_pod[buf][tid] = nx_pod; rc.q_cls[buf][tid] = nx_cls;
+        const int idx2 = cb + CH + tid;
+        nx_cls = KSCHED_NONE;
+        if (idx2 < s.n_pods) { nx_pod = s.order[idx2]; nx_cls = (uint32_t)ffd_rows[idx2].reserved; }
+      }
+      __syncthreads();
     }
-    // ---- scan the slots this thread owns
+    if (rc.q_cls[buf][i] != cls) break;  // class change or end of the first pass
+    // node-independent half of nextDomainTopologySpread, one domain per lane: min count over the pod's domains, the
+    // domains within max-skew (count + self - min <= maxSkew)
+    uint32_t okm0 = 0, okm1 = 0;
+    if (n_mask > 0) {
+      const bool valid = (m_reg0 >> lane) & 1;  // registered domains have ids < kRunDom
+      const int cn = rc.cnt[warp][0][lane & (kRunDom - 1)];
+      const int mn = __reduce_min_sync(0xffffffffu, valid ? cn : INT32_MAX);
+      okm0 = __ballot_sync(0xffffffffu, valid && (long long)cn + m_bias0 <= (long long)mn);
+      if (n_mask > 1) {
+        const bool valid1 = (m_reg1 >> lane) & 1;
+        const int cn1 = rc.cnt[warp][1][lane & (kRunDom - 1)];
+        const int mn1 = __reduce_min_sync(0xffffffffu, valid1 ? cn1 : INT32_MAX);
+        okm1 = __ballot_sync(0xffffffffu, valid1 && (long long)cn1 + m_bias1 <= (long long)mn1);
+      }
+    }
+    // ---- scan the slots this thread owns: key, rp and (topology classes) the admissible domains
     unsigned long long mine = ~0ull;
-    int best_a = -1, best_d[kRunMask] = {0, 0};
-    unsigned best_pin = 0;
-    bool best_slow = false;
-    long long bq[kHotRes] = {0, 0, 0, 0};
+    int best_a = 0;
+    uint32_t best_rp = 0, best_z0 = 0, best_z1 = 0;
     for (int a = tid; a < n_active; a += T) {
       const unsigned long long key = hs->key[a];
-      if (key >= mine) continue;
-      const unsigned short fl = hs->flags[a];
-      if (!((first.tol >> tmpl_taintset[fl >> 8]) & 1)) continue;  // Taints.Tolerates
-      if (simple && hs->rejected[a] == cls) continue;
-      const uint32_t qp = ((fl >> 1) & 0xF) | first.res;
-      long long q[kHotRes], b1[kHotRes], b2[kHotRes];
-#pragma unroll
-      for (int r = 0; r < kHotRes; ++r) { q[r] = hs->q[r][a] + first.req[r]; b1[r] = hs->bound[r][a]; b2[r] = hs->bound2[r][a]; }
-      const int qf = quick_fit(q, qp, RH, b1, b2, fl);
-      if (qf == 0) continue;
-      bool slow = qf == 2;
-      unsigned pin = 0;
-      int dd[kRunMask] = {0, 0};
-      if (simple) {
-        if (!(plain || hs->absorbed[a] == cls)) slow = true;  // requirement verdict unknown for this class
-      } else {
-        bool rej = false;
-        for (int j = 0; j < n_host; ++j) {  // hostname groups: exact from the node's counts
-          const int cnt = hc[j * kTopoCap + a];
-          rej = rej || (rc.h_type[j] == 0 ? cnt + rc.h_self[j] > rc.h_skew[j] : cnt != 0);
-        }
-        if (rej) continue;
-        for (int j = 0; j < n_mask; ++j) {
-          const uint64_t na = zval[j * kTopoCap + a];
-          const uint64_t cand = na & okm[j];
-          if (!cand) { rej = true; break; }
-          const int d = run_pick(cand, rc.cnt[warp][j]);
-          const uint8_t zf = zfl[j * kTopoCap + a];
-          if (!(na == (1ull << d) && (zf & 2))) {  // the placement pins the node's domain
-            pin |= 1u << j;
-            if (!((rc.m_neutral[j] >> d) & 1) || !((zf & 1) || rc.m_wk[j])) slow = true;
-          }
-          dd[j] = d;
-        }
-        if (rej) continue;
-      }
-      mine = key;
-      best_a = a;
-      best_slow = slow;
-      best_pin = pin;
-      best_d[0] = dd[0]; best_d[1] = dd[1];
-#pragma unroll
-      for (int r = 0; r < kHotRes; ++r) bq[r] = q[r];
+      const uint32_t rp = rpv[a];
+      uint32_t z0 = 0, z1 = 0;
+      bool ok = key < mine && (rp & 0xFFFF) != 0 && !(rp & kRpDead);  // tombstones carry key = ~0
+      if (n_mask > 0) { z0 = zv[a]; ok = ok && (z0 & okm0) != 0; }
+      if (n_mask > 1) { z1 = zv[kTopoCap + a]; ok = ok && (z1 & okm1) != 0; }
+      if (ok) { mine = key; best_a = a; best_rp = rp; best_z0 = z0; best_z1 = z1; }
     }
-    unsigned pay = 0;
-    bool my_closed = false;
-    if (best_a >= 0) {
-      long long cb1[kHotRes], cb2[kHotRes];
-#pragma unroll
-      for (int r = 0; r < kHotRes; ++r) { cb1[r] = hs->bound[r][best_a]; cb2[r] = hs->bound2[r][best_a]; }
-      const unsigned short fl2 = (unsigned short)(hs->flags[best_a] | ((first.res & 0xF) << 1));
-      my_closed = node_closed(bq, min_req, RH, cb1, cb2, fl2);
-      pay = run_pay(best_a, best_slow, my_closed, best_pin, best_d);
+    // payload of this thread's candidate: slot | slow << 11 | pin bits << 13 | domains << 15 / 19
+    unsigned pay = (unsigned)best_a;
+    if (mine != ~0ull) {
+      if ((best_rp & 0xFFFF) == kRoomSlow) pay |= 1u << 11;
+      if (n_mask > 0) {
+        const uint32_t cand = best_z0 & okm0;
+        int d;
+        if (!(best_z0 & 0xFFFF & ((best_z0 & 0xFFFF) - 1)) && (best_z0 & (1u << 16))) d = __ffs(cand) - 1;  // pinned already
+        else {  // the placement pins the node's domain
+          d = run_pick(cand, rc.cnt[warp][0]);
+          pay |= 1u << 13;
+          if (!((rc.m_neutral[0] >> d) & 1) || !((best_z0 & (1u << 17)) || rc.m_wk[0])) pay |= 1u << 11;
+        }
+        pay |= (unsigned)d << 15;
+      }
+      if (n_mask > 1) {
+        const uint32_t cand = best_z1 & okm1;
+        int d;
+        if (!(best_z1 & 0xFFFF & ((best_z1 & 0xFFFF) - 1)) && (best_z1 & (1u << 16))) d = __ffs(cand) - 1;
+        else {
+          d = run_pick(cand, rc.cnt[warp][1]);
+          pay |= 1u << 14;
+          if (!((rc.m_neutral[1] >> d) & 1) || !((best_z1 & (1u << 17)) || rc.m_wk[1])) pay |= 1u << 11;
+        }
+        pay |= (unsigned)d << 19;
+      }
     }
     // ---- block argmin with payload: ONE barrier (double-buffered scratch)
     const unsigned long long wmin = warp_min_u64(mine);
@@ -1315,95 +1390,90 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
     else if (lane == 0 && wmin == ~0ull) rc.red_key[parity][warp] = ~0ull;
     __syncthreads();
     const unsigned long long rk = lane < nwarps ? rc.red_key[parity][lane] : ~0ull;
-    const unsigned rp = lane < nwarps ? rc.red_pay[parity][lane] : 0;
+    const unsigned rp_l = lane < nwarps ? rc.red_pay[parity][lane] : 0;
     parity ^= 1;
     const unsigned long long wkey = warp_min_u64(rk);
+    int fd0 = 0, fd1 = 0;
     if (wkey != ~0ull) {
       const unsigned src = __ballot_sync(0xffffffffu, rk == wkey);
-      const unsigned wp = __shfl_sync(0xffffffffu, rp, __ffs(src) - 1);
+      const unsigned wp = __shfl_sync(0xffffffffu, rp_l, __ffs(src) - 1);
       if (wp & (1u << 11)) { status = 1; break; }  // the winner needs the full evaluation
-      const bool closed = (wp >> 12) & 1;
-      const int wd[kRunMask] = {(int)((wp >> 15) & 0xF), (int)((wp >> 19) & 0xF)};
-      if (mine == wkey) {  // the owner commits its node
-        const int a = best_a, n = hs->node[a];
-        const unsigned short fl = hs->flags[a];
+      fd0 = (wp >> 15) & 0xF;
+      fd1 = (wp >> 19) & 0xF;
+      if (mine == wkey) {  // the owner commits its node: a handful of shared-memory stores
+        const int a = best_a;
+        uint32_t rp = best_rp - 1 + (1u << 16);
+        bool host_first = false;
 #pragma unroll
-        for (int r = 0; r < kHotRes; ++r) hs->q[r][a] = bq[r];
-        if ((first.res & 0xF) & ~((fl >> 1) & 0xF)) {
-          s.nn_req_present[n] |= first.res;  // rare (a request key new to the node): the only global load of a commit
-          hs->flags[a] = fl | (unsigned short)((first.res & 0xF) << 1);
-        }
-        const int count = (int)(wkey >> 32) + 1;
-        s.nn_count[n] = count;
-        s.nn_tb[n] = -(tick + 1);
-        hs->key[a] = order_key(count, -(tick + 1));
-        hs->rejected[a] = KSCHED_NONE;
-        for (int j = 0; j < n_host; ++j) {  // Topology.Record, hostname groups
+        for (int j = 0; j < kRunHost; ++j) {  // Topology.Record, hostname groups
+          if (j >= n_host) continue;
           const int times = rc.h_times[j];
-          if (!times) continue;
           const int old = hc[j * kTopoCap + a];
           const int now = old + times > 0xFFFF ? 0xFFFF : old + times;
-          hc[j * kTopoCap + a] = (uint16_t)now;
-          s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n] = (uint16_t)now;
-          if (old == 0) s.grp_host_total[rc.h_group[j]] = ++rc.h_total[j];
+          if (times) hc[j * kTopoCap + a] = (uint16_t)now;
+          if (now > rc.h_lim[j]) rp |= kRpDead;  // no further pod of the class here
+          host_first = host_first || (times && old == 0);
         }
-        for (int j = 0; j < n_mask; ++j) {
-          const int d = best_d[j], k = rc.m_key[j];
-          if ((best_pin >> j) & 1) {  // requirements.Add(In{d}) on the node
-            zval[j * kTopoCap + a] = 1ull << d;
-            zfl[j * kTopoCap + a] = 3;
+        if (pay & (3u << 13)) {  // requirements.Add(In{d}) on the node: once per node and key
+          const int n = hs->node[a];
+          for (int j = 0; j < n_mask; ++j) {
+            if (!((pay >> (13 + j)) & 1)) continue;
+            const int d = j ? fd1 : fd0, k = rc.m_key[j];
+            zv[j * kTopoCap + a] = (1u << d) | (3u << 16);
             s.nn_vals[(size_t)k * MAXN + n] = 1ull << d;
-            s.nn_meta[n] = (s.nn_meta[n] | (1ull << (KSCHED_META_PRESENT_SHIFT + k))) & ~(1ull << (KSCHED_META_COMPLEMENT_SHIFT + k));  // once per node and key
+            s.nn_meta[n] = (s.nn_meta[n] | (1ull << (KSCHED_META_PRESENT_SHIFT + k))) & ~(1ull << (KSCHED_META_COMPLEMENT_SHIFT + k));
           }
-          // the node's domain is the single value d: Record it (this warp's copy still holds the old count; lane 0 bumps it below)
-          if (rc.m_rec[j]) s.grp_cnt[(size_t)rc.m_group[j] * 64 + d] = rc.cnt[warp][j][d] + 1;
         }
-        s.assign[pod] = NE + n;
-        s.place_seq[pod] = seq;
-        if (closed) {  // the node leaves the active set; the last open node takes its slot (and this thread becomes its owner)
-          for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + n] = bq[r];
-          const int last = n_active - 1;
-          if (a != last) {
-            hs->key[a] = hs->key[last];
+        const int count = (int)(wkey >> 32) + 1;
+        unsigned long long nkey = order_key(count, -(tick + 1));
+        rc.q_node[buf][i] = NE + hs->node[a];
+        if ((rp & 0xFFFF) == 0) {  // the class no longer fits by resources: does anything? (node_closed)
+          const int placed = (rp >> 16) & 0x7FFF;
+          long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
 #pragma unroll
-            for (int r = 0; r < kHotRes; ++r) { hs->q[r][a] = hs->q[r][last]; hs->bound[r][a] = hs->bound[r][last]; hs->bound2[r][a] = hs->bound2[r][last]; }
-            hs->node[a] = hs->node[last]; hs->flags[a] = hs->flags[last]; hs->absorbed[a] = hs->absorbed[last]; hs->rejected[a] = hs->rejected[last];
-            if (topo) {
-              for (int j = 0; j < n_host; ++j) hc[j * kTopoCap + a] = hc[j * kTopoCap + last];
-              for (int j = 0; j < n_mask; ++j) { zval[j * kTopoCap + a] = zval[j * kTopoCap + last]; zfl[j * kTopoCap + a] = zfl[j * kTopoCap + last]; }
-            }
+          for (int r = 0; r < kHotRes; ++r) { nq[r] = hs->q[r][a] + placed * p_req[r]; cb1[r] = hs->bound[r][a]; cb2[r] = hs->bound2[r][a]; }
+          const unsigned short fl = (unsigned short)(hs->flags[a] | ((p_res & 0xF) << 1));
+          if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {  // leaves the active set: tombstone, compacted when the run ends
+            nkey = ~0ull;
+            hs->nn_last[a] = ((unsigned long long)(unsigned)count << 32) | (unsigned)(-(tick + 1));
+            rc.tomb = rc.tomb + 1;
           }
         }
+        hs->key[a] = nkey;
+        rpv[a] = rp;
+        (void)host_first;
       }
-      __syncwarp();  // the owner has read its warp's counters
-      if (lane == 0)
-        for (int j = 0; j < n_mask; ++j) if (rc.m_rec[j]) rc.cnt[warp][j][wd[j]]++;
-      __syncwarp();
-      if (closed) --n_active;
+      if (n_mask > 0) {  // every warp keeps its copy of the spread counters in step (the node's domain is the single value d)
+        if (lane == 0) {
+          if (m_rec0) rc.cnt[warp][0][fd0]++;
+          if (m_rec1) rc.cnt[warp][1][fd1]++;
+        }
+        __syncwarp();
+      }
       ++tick;
-      ++seq;
     } else {
       // ---- nobody accepts: NewNode + Add replayed from a variant (templates: the one the variant was created from)
       if (n_new >= MAXN || n_active >= kActCap || (topo && n_active >= kTopoCap) || rc.n_var == 0) { status = 1; break; }
-      int fd[kRunMask] = {0, 0};
       bool ok = true;
-      for (int j = 0; j < n_host; ++j) ok = ok && !(rc.h_type[j] == 0 && rc.h_self[j] > rc.h_skew[j]);
-      for (int j = 0; j < n_mask && ok; ++j) {
-        const uint64_t cand = rc.m_tallow[j] & okm[j];
-        if (!cand) { ok = false; break; }
-        fd[j] = run_pick(cand, rc.cnt[warp][j]);
+#pragma unroll
+      for (int j = 0; j < kRunHost; ++j) ok = ok && (j >= n_host || rc.h_lim[j] >= 0);  // a fresh hostname has count 0
+      if (n_mask > 0 && ok) {
+        const uint32_t cand = rc.m_tallow[0] & okm0;
+        if (!cand) ok = false; else fd0 = run_pick(cand, rc.cnt[warp][0]);
+      }
+      if (n_mask > 1 && ok) {
+        const uint32_t cand = rc.m_tallow[1] & okm1;
+        if (!cand) ok = false; else fd1 = run_pick(cand, rc.cnt[warp][1]);
       }
       int vi = -1;
-      for (int i = 0; i < rc.n_var && ok; ++i) {
-        bool same = true;
-        for (int j = 0; j < n_mask; ++j) same = same && rc.var[i].dom[j] == fd[j];
-        if (same) { vi = i; break; }
-      }
+      for (int v2 = 0; v2 < rc.n_var && ok && vi < 0; ++v2)
+        if ((n_mask < 1 || rc.var[v2].dom[0] == fd0) && (n_mask < 2 || rc.var[v2].dom[1] == fd1)) vi = v2;
       if (vi < 0) { status = 1; break; }
       const RunVariant& v = rc.var[vi];
       const int n = n_new, a = n_active;
       for (int w = tid; w < W32; w += T) s.nn_opts[(size_t)w * MAXN + n] = v.opts[w];
       if (tid < c.n_keys) s.nn_vals[(size_t)tid * MAXN + n] = v.vals[tid];
+      if (tid < KSCHED_MAX_RES) s.nn_req[(size_t)tid * MAXN + n] = v.q[tid];
       if (tid == a % T) {  // the new slot's owner
         hs->key[a] = order_key(1, tick + 1);
 #pragma unroll
@@ -1412,59 +1482,107 @@ __device__ __noinline__ void class_run(const PodRegs& first) {
         hs->flags[a] = v.fl;
         hs->absorbed[a] = simple ? cls : KSCHED_NONE;
         hs->rejected[a] = KSCHED_NONE;
+        rpv[a] = v.rp;
         s.nn_meta[n] = v.meta;
         s.nn_tmpl[n] = (uint8_t)(v.fl >> 8);
-        for (int r = 0; r < KSCHED_MAX_RES; ++r) s.nn_req[(size_t)r * MAXN + n] = v.q[r];
         s.nn_req_present[n] = v.qp;
         s.nn_hp[n] = 0;
         s.nn_count[n] = 1;
         s.nn_tb[n] = tick + 1;
-        s.assign[pod] = NE + n;
-        s.place_seq[pod] = seq;
+        rc.q_node[buf][i] = NE + n;
         for (int j = 0; j < n_host; ++j) {
           const int times = rc.h_times[j];
           hc[j * kTopoCap + a] = (uint16_t)times;
           if (times) {
             s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n] = (uint16_t)times;
-            s.grp_host_total[rc.h_group[j]] = ++rc.h_total[j];
+            rc.h_inc[j] = rc.h_inc[j] + 1;
           }
         }
-        for (int j = 0; j < n_mask; ++j) {
-          zval[j * kTopoCap + a] = 1ull << fd[j];
-          zfl[j * kTopoCap + a] = 3;
-          if (rc.m_rec[j]) s.grp_cnt[(size_t)rc.m_group[j] * 64 + fd[j]] = rc.cnt[warp][j][fd[j]] + 1;
-        }
+        if (n_mask > 0) zv[a] = (1u << fd0) | (3u << 16);
+        if (n_mask > 1) zv[kTopoCap + a] = (1u << fd1) | (3u << 16);
       }
-      __syncwarp();
-      if (lane == 0)
-        for (int j = 0; j < n_mask; ++j) if (rc.m_rec[j]) rc.cnt[warp][j][fd[j]]++;
-      __syncwarp();
+      if (n_mask > 0) {
+        if (lane == 0) {
+          if (m_rec0) rc.cnt[warp][0][fd0]++;
+          if (m_rec1) rc.cnt[warp][1][fd1]++;
+        }
+        __syncwarp();
+      }
       ++tick;
-      ++seq;
       ++n_new;
       ++n_active;
     }
-    // ---- the pod is placed: pop it, move to the next one of the same class
+    // ---- the pod is placed: pop it
     ++qi;
-    head = head + 1 == qcap ? 0 : head + 1;
     --qlen;
-    ++add_calls;
-    ++placed;
-    if (qi >= s.n_pods || qlen == 0) break;
-    if (cls1 != first.cls64) break;
-    pod = pod1;
-    pod1 = pod2; cls1 = cls2;
-    if (qi + 2 < s.n_pods) { pod2 = s.order[qi + 2]; cls2 = ffd_rows[qi + 2].reserved; } else cls2 = ~0ull;
-    if (tid == 0 && qi + 32 < s.n_pods) prefetch_l2(reinterpret_cast<const char*>(ffd_rows + qi + 32) + 128);
-    if (tid == 2 && (qi & 31) == 0 && qi + 96 < s.n_pods) prefetch_l2(s.order + qi + 96);
+    if (qlen == 0) break;
   }
   __syncthreads();
+  // ---- the run is over: write back what the commits deferred
+  const int placed_total = qi - qi0;
+  if (tid < CH && tid < qi - cb) {  // assignments of the partly consumed chunk
+    const uint32_t pd = rc.q_pod[buf][tid];
+    s.assign[pd] = rc.q_node[buf][tid];
+    s.place_seq[pd] = seq0 + (cb - qi0) + tid;
+  }
+  for (int a = tid; a < n_active; a += T) {  // requests, order statistics, hostname counters of the nodes that took pods
+    const uint32_t rp = rpv[a];
+    const int placed = (rp >> 16) & 0x7FFF;
+    if (!placed) continue;
+    const int n = hs->node[a];
+    unsigned long long key = hs->key[a];
+    const bool tomb = key == ~0ull;
+    if (tomb) key = hs->nn_last[a];
+#pragma unroll
+    for (int r = 0; r < kHotRes; ++r) {
+      const long long nq = hs->q[r][a] + placed * p_req[r];
+      hs->q[r][a] = nq;
+      if (tomb && r < RH) s.nn_req[(size_t)r * MAXN + n] = nq;
+    }
+    hs->rejected[a] = KSCHED_NONE;
+    const unsigned short fl = hs->flags[a];
+    if ((p_res & 0xF) & ~((fl >> 1) & 0xF)) {  // a request key new to the node
+      s.nn_req_present[n] |= p_res;
+      hs->flags[a] = fl | (unsigned short)((p_res & 0xF) << 1);
+    }
+    s.nn_count[n] = (int)(key >> 32);
+    s.nn_tb[n] = (int)((unsigned)key ^ 0x80000000u);
+    for (int j = 0; j < n_host; ++j) {
+      const int times = rc.h_times[j];
+      if (!times) continue;
+      const int now = hc[j * kTopoCap + a];
+      s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n] = (uint16_t)now;
+      if (now - placed * times == 0) atomicAdd(&rc.h_inc[j], 1);  // the hostname's first matching pod (not saturated: counts <= pods per node)
+    }
+  }
+  for (int j = 0; j < n_mask; ++j)
+    if (rc.m_rec[j] && warp == 0 && lane < kRunDom && ((rc.m_registered[j] >> lane) & 1)) s.grp_cnt[(size_t)rc.m_group[j] * 64 + lane] = rc.cnt[0][j][lane];
+  __syncthreads();
+  if (tid < n_host && rc.h_inc[tid]) s.grp_host_total[rc.h_group[tid]] += rc.h_inc[tid];
+  // ---- compact the active list (tombstones out); slot order is irrelevant, ownership ends with the run
+  if (rc.tomb > 0) {
+    if (tid == 0) {
+      int i = 0, j = n_active - 1;
+      while (true) {
+        while (j >= 0 && hs->key[j] == ~0ull) --j;
+        while (i < j && hs->key[i] != ~0ull) ++i;
+        if (i >= j) break;
+        hs->key[i] = hs->key[j];
+        for (int r = 0; r < kHotRes; ++r) { hs->q[r][i] = hs->q[r][j]; hs->bound[r][i] = hs->bound[r][j]; hs->bound2[r][i] = hs->bound2[r][j]; }
+        hs->node[i] = hs->node[j]; hs->flags[i] = hs->flags[j]; hs->absorbed[i] = hs->absorbed[j]; hs->rejected[i] = hs->rejected[j];
+        hs->key[j] = ~0ull;
+      }
+    }
+    n_active -= rc.tomb;
+  }
   if (tid == 0) {
-    io.qi = qi; io.head = head; io.qlen = qlen; io.tick = tick; io.seq = seq; io.n_active = n_active; io.n_new = n_new; io.parity = parity;
-    io.add_calls = add_calls; io.placed = placed; io.status = status;
+    const int qcap = s.n_pods + 1;
+    io.qi = qi; io.head = (io.head + placed_total) % qcap; io.qlen = qlen; io.tick = tick; io.seq = seq0 + placed_total; io.n_active = n_active; io.n_new = n_new; io.parity = parity;
+    io.add_calls += placed_total; io.placed = placed_total; io.status = status;
   }
   __syncthreads();
 }
+
 
 #ifdef KSCHED_PROFILE_PACK
 #define PK_T(i) { long long _now = clock64(); pk_acc[i] += _now - pk_last; pk_last = _now; }

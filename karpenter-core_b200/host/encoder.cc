@@ -44,18 +44,20 @@ std::string normalize_key(const std::string& k) {  // v1alpha5.NormalizedLabels,
   return k;
 }
 
-bool parse_int(const std::string& s, int64_t* out) {  // strconv.Atoi
+bool parse_int(const std::string& s, int64_t* out) {  // strconv.Atoi: optional sign, decimal digits, must fit in int64
   if (s.empty()) return false;
   size_t i = 0;
   bool neg = false;
   if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
-  if (i >= s.size() || s.size() - i > 18) return false;
-  int64_t v = 0;
+  if (i >= s.size()) return false;
+  unsigned __int128 v = 0;
+  const unsigned __int128 lim = neg ? ((unsigned __int128)1 << 63) : (((unsigned __int128)1 << 63) - 1);
   for (; i < s.size(); ++i) {
     if (s[i] < '0' || s[i] > '9') return false;
-    v = v * 10 + (s[i] - '0');
+    v = v * 10 + (unsigned)(s[i] - '0');
+    if (v > lim) return false;
   }
-  *out = neg ? -v : v;
+  *out = neg ? (int64_t)(0 - (uint64_t)v) : (int64_t)v;
   return true;
 }
 
@@ -1177,7 +1179,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   pr.n_hostname_reqs = (int)E.hostname_reqs.size() / 2;
   pr.max_new_nodes = (int)NP;
   pr.write_feasibility = 0;
-  pr.count_nodes_visited = 1;
+  pr.count_nodes_visited = 0;  // the exact nodes_visited statistic is opt-in (kh_set_count_visited / tests): it turns the pack kernel's steady-state paths off
   if (E.any_class_bounds || E.any_template_bounds)
     unsupported("Gt/Lt requirements on pods / provisioners are not carried on the device path yet");
   return enc;

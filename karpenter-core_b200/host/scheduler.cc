@@ -30,7 +30,7 @@ namespace {
 thread_local std::string g_err;
 ksched_handle* g_handle = nullptr;
 int g_device = 0;
-int g_count_visited = 1;  // exact nodes_visited statistic; switches the pack kernel's steady-state paths off
+int g_count_visited = 0;  // exact nodes_visited statistic (opt-in: tests); switches the pack kernel's steady-state paths off
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -335,8 +335,10 @@ Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int 
   if (rc != KSCHED_OK) throw std::runtime_error(g_err);
   size_t scheduled = 0;
   for (auto a : B.assign) if (a >= 0) ++scheduled;
-  for (size_t p = 0; p < B.assign.size(); ++p)  // helpers.go:109-113: an uninitialised existing node was used
-    if (B.assign[p] >= 0 && (size_t)B.assign[p] < E->existing.size() && !E->existing_initialized[B.assign[p]]) return cmd;
+  // helpers.go:109-113 walks EVERY ExistingNode Solve returns (all owned nodes that are neither candidates nor marked for
+  // deletion) and gives up when one of them is not initialised - whether or not a pod landed on it
+  for (size_t e = 0; e < E->existing.size(); ++e)
+    if (!E->existing_initialized[e]) return cmd;
   if (scheduled != E->pods.size()) return cmd;
   if (B.r.n_new_nodes == 0) { cmd.action = 1; return cmd; }
   if (B.r.n_new_nodes != 1) return cmd;

@@ -1195,8 +1195,8 @@ void consolidate(const Problem& P, ConsolidationResult& out, int only_count) {
       ++out.simulations;
       size_t scheduled = 0;
       for (auto a : r.assign) if (a >= 0) ++scheduled;
-      for (auto& e : s.existing)  // helpers.go:109-113
-        if (!e.pods.empty() && !e.initialized) return cmd;
+      for (auto& e : s.existing)  // helpers.go:109-113: EVERY existing node Solve returns, whether or not a pod landed on it
+        if (!e.initialized) return cmd;
       if (scheduled != pods.size()) return cmd;
       if (s.new_nodes_storage.empty()) { cmd.action = 1; return cmd; }
       if (s.new_nodes_storage.size() != 1) return cmd;

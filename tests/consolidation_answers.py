@@ -256,3 +256,24 @@ def without_the_pending_pod_the_node_is_replaced():
         action, options = probe(1)
         assert action == 2 and options
     return prob, check
+
+
+@cpu_case("deprovisioning/helpers.go:106-113 (simulateScheduling walks every ExistingNode Solve returns)")
+def an_idle_uninitialised_node_blocks_every_command():
+    """The expensive node could be replaced (control case above), but another owned node of the cluster is not initialised yet:
+    simulateScheduling reports allPodsScheduled == false even though no pod would land on that node."""
+    its = assorted()
+    worst = on_demand_by_price(its)[-1]
+    of = worst["offerings"][0]
+    n = fx.state_node("node-a", worst["name"], zone=of["zone"], capacity_type=of["capacityType"],
+                      allocatable={"cpu": "128", "memory": "512Gi", "pods": "100"}, pods_=[fx.pod({"cpu": "1"}, nodeName="node-a")])
+    n["candidate"] = True
+    n["disruptionCost"] = 1.0
+    # too small for the pod (cpu 500m) and not a candidate: it only matters through its missing karpenter.sh/initialized label
+    idle = fx.state_node("node-b", its[0]["name"], zone=its[0]["offerings"][0]["zone"], capacity_type=its[0]["offerings"][0]["capacityType"],
+                         allocatable={"cpu": "500m", "memory": "1Gi", "pods": "100"}, initialized=False)
+    prob = fx.problem([], instance_types=its, nodes=[n, idle])
+
+    def check(probe, search):
+        assert probe(1) == (0, [])
+    return prob, check

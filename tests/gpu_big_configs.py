@@ -4,7 +4,7 @@ sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from conftest import load_pkg
 import numpy as np
 k = load_pkg()
-ALL = {3: (3, 50000, 1000), 4: (4, 100000, 1000)}
+ALL = {2: (2, 10000, 500), 3: (3, 50000, 1000), 4: (4, 100000, 1000)}
 which = [int(x) for x in sys.argv[1:]] or [3, 4]
 for cfg, P, T in [ALL[w] for w in which]:
     t0 = time.time(); p = k.Problem.synth(cfg, P, T, 42, 0); t1 = time.time()
