@@ -100,6 +100,7 @@ def lib():
     L.kh_set_count_visited.argtypes = [C.c_int]
     L.kh_handle.restype = C.c_void_p
     L.kh_scheduler_solve.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+    L.kh_scheduler_solve_timed.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p, C.POINTER(C.c_double)]
     L.kh_encode.restype = C.c_void_p
     L.kh_encode.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
     L.kh_encoded_free.argtypes = [C.c_void_p]
@@ -274,6 +275,16 @@ class Scheduler:
         rc = lib().kh_scheduler_solve(self.problem.ptr, arr, n, res.ptr)
         _check(rc)
         return res
+
+
+def solve_timed(problem: Problem, candidates=(), count_visited=False):
+    """Scheduler.solve with its host phases timed: (Result, {encode_us, catalog_us, solve_us, decode_us, total_us})."""
+    lib().kh_set_count_visited(int(count_visited))
+    res = Result()
+    arr, n = _cand_array(list(candidates))
+    ph = (C.c_double * 5)()
+    _check(lib().kh_scheduler_solve_timed(problem.ptr, arr, n, res.ptr, ph))
+    return res, dict(zip(["encode_us", "catalog_us", "solve_us", "decode_us", "total_us"], list(ph)))
 
 
 def simulate_scheduling(problem: Problem, nodes_to_delete):

@@ -162,6 +162,7 @@ struct ksched_handle {
   DevBuf<uint64_t> d_offer_keys;
   DevBuf<ksched_launch_choice> d_launch;
   std::vector<ksched_template> h_templates;
+  std::vector<unsigned char> catalog_blob;  // host copy of the resident catalog's inputs (ksched_load_catalog early-out)
   int n_valrows = 1, n_offrows = 1;
   // problem
   bool uploaded = false;
@@ -288,6 +289,33 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int T = cat->n_types, NK = cat->n_keys, V = cat->n_templates, R = cat->n_res;
   const int W64 = type_words64(T), W32 = W64 * 2;
+  {
+    // Instance types change rarely: when the byte-identical catalog is already resident there is nothing to do (exact
+    // comparison against a host copy; the O(T^2) dominance table alone is milliseconds of host time at T = 1000).
+    std::vector<unsigned char> blob;
+    auto put = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; blob.insert(blob.end(), b, b + n); };
+    int dims[4] = {NK, R, T, V};
+    put(dims, sizeof dims);
+    put(cat->keys, sizeof(ksched_keyinfo) * (size_t)NK);
+    unsigned char has_int = cat->key_int_values != nullptr, has_off = cat->offering_keys != nullptr;
+    put(&has_int, 1); put(&has_off, 1);
+    if (has_int) put(cat->key_int_values, sizeof(int64_t) * (size_t)NK * 64);
+    put(cat->types, sizeof(ksched_type_row) * (size_t)T);
+    put(cat->type_capacity, sizeof(int64_t) * (size_t)T * KSCHED_MAX_RES);
+    if (has_off) put(cat->offering_keys, sizeof(uint64_t) * (size_t)T * 64);
+    if (h->have_catalog && blob == h->catalog_blob) {
+      // same instance types: only the templates can differ (remaining provisioner limits move between solves, daemonset
+      // overhead with the daemonsets) - they are small, re-upload them when they changed
+      if (h->h_templates.size() != (size_t)V || std::memcmp(h->h_templates.data(), cat->templates, sizeof(ksched_template) * (size_t)V) != 0) {
+        CUDA_TRY(h, upload(h, h->d_templates, cat->templates, (size_t)V));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        h->cat.templates = h->d_templates.ptr;
+        h->h_templates.assign(cat->templates, cat->templates + V);
+      }
+      return KSCHED_OK;
+    }
+    h->catalog_blob.swap(blob);
+  }
   h->W64 = W64;
   // ---- bit-sliced tables, built on the host (amortised: instance types change rarely)
   std::vector<int16_t> valrow((size_t)NK * 64, -1), offrow(64, -1);

@@ -9,11 +9,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
 #include <tuple>
+#include <unordered_set>
 #include <set>
 #include <stdexcept>
 
@@ -169,6 +172,49 @@ std::string term_key(const PodAffinityTerm& t) {
   std::string s = t.topology_key + "|" + selector_key(t.selector) + "|";
   for (auto& n : t.namespaces) s += n + ",";
   return s;
+}
+
+// Structural equality of everything class_key reads (a SUFFICIENT condition for "same class": two pods whose containers
+// differ but sum to the same requests still share a class, they just take the keyed path below). Consecutive pods of a batch
+// usually come from one deployment, so the per-pod cost of interning is one such comparison instead of a key string.
+bool same_reqs(const std::vector<NodeSelectorRequirement>& a, const std::vector<NodeSelectorRequirement>& b) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); ++i) if (a[i].key != b[i].key || a[i].op != b[i].op || a[i].values != b[i].values) return false;
+  return true;
+}
+bool same_selector(const LabelSelector& a, const LabelSelector& b) {
+  return a.is_nil == b.is_nil && a.match_labels == b.match_labels && same_reqs(a.match_expressions, b.match_expressions);
+}
+bool same_term(const PodAffinityTerm& a, const PodAffinityTerm& b) {
+  return a.topology_key == b.topology_key && a.namespaces == b.namespaces && same_selector(a.selector, b.selector);
+}
+template <class T, class F>
+bool same_vec(const std::vector<T>& a, const std::vector<T>& b, F eq) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); ++i) if (!eq(a[i], b[i])) return false;
+  return true;
+}
+bool same_container(const Container& a, const Container& b) {
+  return a.requests == b.requests && a.limits == b.limits &&
+         same_vec(a.ports, b.ports, [](const HostPort& x, const HostPort& y) { return x.ip == y.ip && x.port == y.port && x.protocol == y.protocol; });
+}
+bool same_spec(const Pod& a, const Pod& b) {
+  auto wterm = [](const WeightedPodAffinityTerm& x, const WeightedPodAffinityTerm& y) { return x.weight == y.weight && same_term(x.term, y.term); };
+  return a.ns == b.ns && a.labels == b.labels && same_vec(a.containers, b.containers, same_container) &&
+         same_vec(a.init_containers, b.init_containers, same_container) && a.node_selector == b.node_selector &&
+         a.has_node_affinity == b.has_node_affinity && a.has_required_node_affinity == b.has_required_node_affinity &&
+         same_vec(a.required_node_terms, b.required_node_terms, same_reqs) &&
+         same_vec(a.preferred_node_terms, b.preferred_node_terms,
+                  [](const PreferredSchedulingTerm& x, const PreferredSchedulingTerm& y) { return x.weight == y.weight && same_reqs(x.preference, y.preference); }) &&
+         same_vec(a.pod_affinity_required, b.pod_affinity_required, same_term) && same_vec(a.pod_affinity_preferred, b.pod_affinity_preferred, wterm) &&
+         same_vec(a.pod_anti_affinity_required, b.pod_anti_affinity_required, same_term) &&
+         same_vec(a.pod_anti_affinity_preferred, b.pod_anti_affinity_preferred, wterm) &&
+         same_vec(a.topology_spread, b.topology_spread,
+                  [](const TopologySpreadConstraint& x, const TopologySpreadConstraint& y) {
+                    return x.max_skew == y.max_skew && x.topology_key == y.topology_key && x.schedule_anyway == y.schedule_anyway && same_selector(x.selector, y.selector);
+                  }) &&
+         same_vec(a.tolerations, b.tolerations,
+                  [](const Toleration& x, const Toleration& y) { return x.key == y.key && x.op == y.op && x.value == y.value && x.effect == y.effect; });
 }
 
 // Everything the scheduler can observe about a pod except its identity (uid / name / timestamp).
@@ -445,6 +491,14 @@ struct Group {
 }  // namespace
 
 std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candidates) {
+  static const bool prof = std::getenv("KSCHED_ENCODE_PROFILE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto phase = [&](const char* name) {
+    if (!prof) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[encode] %-28s %8.2f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   auto enc = std::make_unique<Encoded>();
   Encoded& E = *enc;
   E.problem_ref = &P;
@@ -466,8 +520,11 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
         for (auto& p : P.nodes[i].pods) if (reschedulable(p)) E.pods.push_back(&p);
   }
   const size_t NP = E.pods.size();
-  {
-    std::set<std::string> uids;
+  bool uids_ascending = true;  // strictly ascending UIDs (the usual case: one informer list) are unique and already ranked
+  for (size_t i = 1; i < NP && uids_ascending; ++i) uids_ascending = E.pods[i - 1]->uid < E.pods[i]->uid;
+  if (!uids_ascending) {
+    std::unordered_set<std::string> uids;
+    uids.reserve(NP * 2);
     for (auto* p : E.pods)
       if (!uids.insert(p->uid).second) throw std::runtime_error("pods must have unique UIDs: " + p->uid);
   }
@@ -485,6 +542,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   for (auto& pr : P.provisioners)
     for (auto& t : pr.taints) if (t.effect == "PreferNoSchedule") tolerate_pns = true;
 
+  phase("who takes part");
   // ------------------------------------------------------------------ pod specs: classes and relaxation chains
   struct Spec { Pod pod; ResourceList req; uint32_t next = KSCHED_NONE; };
   std::vector<Spec> specs;
@@ -508,9 +566,13 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     return id;
   };
   E.pod_class.resize(NP);
-  for (size_t i = 0; i < NP; ++i) E.pod_class[i] = intern(*E.pods[i]);
+  for (size_t i = 0; i < NP; ++i) {
+    if (i > 0 && same_spec(*E.pods[i], *E.pods[i - 1])) E.pod_class[i] = E.pod_class[i - 1];  // same deployment as the previous pod
+    else E.pod_class[i] = intern(*E.pods[i]);
+  }
   std::vector<Pod> daemons = P.daemonset_pods;
 
+  phase("pod classes");
   // ------------------------------------------------------------------ active keys + dictionary
   // pod-side keys: anything a pod / daemonset / topology group / node filter can put into a node's requirements
   std::set<std::string> pod_side;
@@ -608,6 +670,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   for (int k = 0; k < NK; ++k) B.key_meta[k] = KeyMeta{E.keys[k].int_mask, &E.key_int_values[(size_t)k * 64]};
   const int zone_key = B.key_of(kZone), ct_key = B.key_of(kCapacityType);
 
+  phase("keys + dictionary");
   // ------------------------------------------------------------------ resources
   {
     std::set<std::string> names;
@@ -623,6 +686,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     for (size_t i = 0; i < E.res_names.size(); ++i) B.res_id[E.res_names[i]] = (int)i;
   }
 
+  phase("resources");
   // ------------------------------------------------------------------ instance types (columns, price order)
   const int NT = (int)P.instance_types.size();
   E.type_words = (NT + 63) / 64;
@@ -696,6 +760,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   // but they do satisfy an absent one: keep them visible through a catch-all bit when the key is inactive.
   // (When zone/ct keys are inactive every offering maps to z=0/ct=0 above, which is exactly "key not constrained".)
 
+  phase("instance types");
   // ------------------------------------------------------------------ templates
   const int NV = (int)E.template_provisioner.size();
   E.templates.resize(NV);
@@ -737,6 +802,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
   E.template_bounds = tb;
 
+  phase("templates");
   // ------------------------------------------------------------------ daemonset overhead (scheduler.go:250-267)
   auto daemon_reqs = [&](const Pod& d, ksched_reqset& rs, ksched_bounds& bd) {
     Builder::Special sp;
@@ -760,6 +826,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     E.templates[v].daemon_res_present = B.fill_resources(total, E.templates[v].daemon_requests);
   }
 
+  phase("daemonset overhead");
   // ------------------------------------------------------------------ existing nodes (scheduler.go:221-248, existingnode.go:41-75)
   std::map<std::string, int> hostname_slot;  // hostname -> existing slot
   for (int si : state_nodes) {
@@ -815,6 +882,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
   const int NE = (int)E.existing.size();
 
+  phase("existing nodes");
   // ------------------------------------------------------------------ topology groups (topology.go)
   std::vector<Group> groups;
   std::map<std::string, size_t> group_of;          // hash -> index, non-inverse
@@ -882,8 +950,16 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
       if (B.compatible(rs, bd, f.first, f.second)) return true;
     return false;
   };
-  std::set<std::string> excluded;
-  for (auto* p : E.pods) excluded.insert(p->uid);
+  // pods of the batch are not counted as cluster pods (topology.go:66-70); only consulted for pods bound to nodes
+  std::unordered_set<std::string> excluded;
+  {
+    bool any_bound = false;
+    for (auto& n : P.nodes) any_bound = any_bound || !n.pods.empty();
+    if (any_bound) {
+      excluded.reserve(NP * 2);
+      for (auto* p : E.pods) excluded.insert(p->uid);
+    }
+  }
   auto new_group = [&](int type, const std::string& key, const Pod& p, std::set<std::string> nss, const LabelSelector& sel, int32_t skew) {
     Group g;
     g.type = type; g.key = key; g.max_skew = skew; g.namespaces = std::move(nss); g.selector = sel;
@@ -1035,6 +1111,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     }
   }
 
+  phase("topology groups");
   // ------------------------------------------------------------------ class rows
   const int NC = (int)specs.size();
   E.classes.resize(NC);
@@ -1134,17 +1211,23 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
       if (tolerates_all(B.taintsets[s], p.tolerations)) E.classes[c].tolerated_taintsets |= 1ull << s;
   }
 
+  phase("class rows");
   // ------------------------------------------------------------------ per-pod queue keys (queue.go:74-110)
   E.pod_timestamp.resize(NP);
   E.pod_uid_rank.resize(NP);
   {
-    std::vector<uint32_t> order(NP);
-    for (size_t i = 0; i < NP; ++i) order[i] = (uint32_t)i;
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return E.pods[a]->uid < E.pods[b]->uid; });
-    for (size_t r = 0; r < NP; ++r) E.pod_uid_rank[order[r]] = (uint32_t)r;
+    if (uids_ascending) {
+      for (size_t i = 0; i < NP; ++i) E.pod_uid_rank[i] = (uint32_t)i;
+    } else {
+      std::vector<uint32_t> order(NP);
+      for (size_t i = 0; i < NP; ++i) order[i] = (uint32_t)i;
+      std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return E.pods[a]->uid < E.pods[b]->uid; });
+      for (size_t r = 0; r < NP; ++r) E.pod_uid_rank[order[r]] = (uint32_t)r;
+    }
     for (size_t i = 0; i < NP; ++i) E.pod_timestamp[i] = E.pods[i]->creation_ts;
   }
 
+  phase("queue keys");
   // ------------------------------------------------------------------ wire up the flat structs
   ksched_catalog& cat = E.catalog;
   cat.n_keys = NK; cat.n_res = (int)E.res_names.size(); cat.n_types = NT; cat.n_templates = NV;

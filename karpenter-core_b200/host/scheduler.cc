@@ -14,6 +14,7 @@
 #include <set>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "encoder.h"
@@ -88,28 +89,56 @@ void decode(const Encoded& E, const ResultBuffers& B, Result& out) {
   out.existing_node_index = E.existing_state_index;
   out.existing_pods.assign(NE, {});
   out.new_nodes.assign((size_t)B.r.n_new_nodes, {});
-  // pods in Add order
-  std::vector<int32_t> order(P);
-  for (size_t i = 0; i < P; ++i) order[i] = (int32_t)i;
-  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return B.seq[a] < B.seq[b]; });
-  for (int32_t p : order) {
-    int32_t a = B.assign[p];
-    if (a < 0) continue;
-    if ((size_t)a < NE) out.existing_pods[a].push_back(p);
-    else out.new_nodes[(size_t)a - NE].pods.push_back(p);
+  // pods in Add order: place_seq is a permutation of 0..placed-1 over the placed pods
+  {
+    std::vector<int32_t> by_seq(P, -1);
+    for (size_t p = 0; p < P; ++p)
+      if (B.assign[p] >= 0 && B.seq[p] >= 0 && (size_t)B.seq[p] < P) by_seq[(size_t)B.seq[p]] = (int32_t)p;
+    for (size_t q = 0; q < P; ++q) {
+      const int32_t p = by_seq[q];
+      if (p < 0) continue;
+      const int32_t a = B.assign[p];
+      if ((size_t)a < NE) out.existing_pods[a].push_back(p);
+      else out.new_nodes[(size_t)a - NE].pods.push_back(p);
+    }
   }
+  // lo.Filter keeps the provider's input order: permute the surviving columns (price order) into an input-order bitset and
+  // read that out; requirement renderings are memoised per (key, masks) - nodes of one deployment share them
+  const size_t NT = E.type_input_index.size();
+  std::vector<uint64_t> in_order((NT + 63) / 64);
+  std::vector<std::unordered_map<uint64_t, std::string>> rendered(E.key_names.size());
   for (int n = 0; n < B.r.n_new_nodes; ++n) {
     const ksched_new_node& src = B.nodes[n];
     NewNodeResult& dst = out.new_nodes[n];
     dst.provisioner = src.template_index;
     const uint64_t* bits = &B.types[(size_t)n * E.type_words];
-    for (size_t c = 0; c < E.type_input_index.size(); ++c)
-      if ((bits[c / 64] >> (c % 64)) & 1) dst.instance_type_options.push_back(E.type_input_index[c]);
-    std::sort(dst.instance_type_options.begin(), dst.instance_type_options.end());  // lo.Filter keeps input order
+    std::fill(in_order.begin(), in_order.end(), 0);
+    size_t n_opts = 0;
+    for (size_t w = 0; w < E.type_words; ++w) {
+      uint64_t m = bits[w];
+      while (m) {
+        const size_t c = w * 64 + (size_t)__builtin_ctzll(m);
+        m &= m - 1;
+        if (c >= NT) continue;
+        const size_t t = (size_t)E.type_input_index[c];
+        in_order[t >> 6] |= 1ull << (t & 63);
+        ++n_opts;
+      }
+    }
+    dst.instance_type_options.reserve(n_opts);
+    for (size_t w = 0; w < in_order.size(); ++w) {
+      uint64_t m = in_order[w];
+      while (m) { dst.instance_type_options.push_back((int32_t)(w * 64 + (size_t)__builtin_ctzll(m))); m &= m - 1; }
+    }
     for (size_t r = 0; r < E.res_names.size(); ++r)
       if ((src.requests_present >> r) & 1) dst.requests[E.res_names[r]] = src.requests[r];
     for (size_t k = 0; k < E.key_names.size(); ++k)
-      if ((src.reqs.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1) dst.requirements[E.key_names[k]] = khost::render_requirement(E, src.reqs, (int)k);
+      if ((src.reqs.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1) {
+        const uint64_t memo_key = src.reqs.values[k] ^ (((src.reqs.meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1) << 63);  // <= 63 values per key
+        auto it = rendered[k].find(memo_key);
+        if (it == rendered[k].end()) it = rendered[k].emplace(memo_key, khost::render_requirement(E, src.reqs, (int)k)).first;
+        dst.requirements[E.key_names[k]] = it->second;
+      }
     // launch choice: column -> the provider's instance type, offering by its position in that type's Offerings list
     if ((size_t)n < B.launch.size() && B.launch[n].type_column >= 0 && E.problem_ref) {
       const ksched_launch_choice& lc = B.launch[n];
@@ -200,6 +229,40 @@ int kh_scheduler_solve(const Problem* P, const int* candidates, int ncand, Resul
     int rc = solve_encoded(*E, B, false);
     if (rc != KSCHED_OK) { out->error = g_err; return rc; }
     decode(*E, B, *out);
+    return KSCHED_OK;
+  } catch (const std::exception& e) {
+    out->error = e.what();
+    return fail(error_code(e), e.what());
+  }
+}
+
+// The same call with its host phases timed (bench.py's end-to-end leg): phases_us = [encode, catalog, solve, decode, total].
+// encode = NewScheduler's marshalling (string-level model -> flat structs); catalog = ksched_load_catalog (a no-op when the
+// byte-identical catalog is already resident); solve = ksched_solve (upload + kernels + download); decode = the
+// ([]*Node, []*ExistingNode) shape.
+int kh_scheduler_solve_timed(const Problem* P, const int* candidates, int ncand, Result* out, double* phases_us) {
+  *out = Result();
+  try {
+    using clk = std::chrono::steady_clock;
+    auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    const auto t0 = clk::now();
+    std::vector<int> c(candidates, candidates + ncand);
+    auto E = khost::encode(*P, c);
+    E->problem.count_nodes_visited = g_count_visited;
+    const auto t1 = clk::now();
+    int rc = ensure_handle();
+    if (rc != KSCHED_OK) return rc;
+    rc = ksched_load_catalog(g_handle, &E->catalog);
+    if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+    const auto t2 = clk::now();
+    ResultBuffers B;
+    B.prepare(*E, false);
+    rc = ksched_solve(g_handle, &E->problem, &B.r);
+    if (rc != KSCHED_OK) { out->error = ksched_last_error(g_handle); return fail(rc, out->error); }
+    const auto t3 = clk::now();
+    decode(*E, B, *out);
+    const auto t4 = clk::now();
+    if (phases_us) { phases_us[0] = us(t0, t1); phases_us[1] = us(t1, t2); phases_us[2] = us(t2, t3); phases_us[3] = us(t3, t4); phases_us[4] = us(t0, t4); }
     return KSCHED_OK;
   } catch (const std::exception& e) {
     out->error = e.what();
