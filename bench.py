@@ -358,8 +358,8 @@ def main():
                 "same_result_as_resident_run": e2e_same,
                 "solve_only": {"value": all_scheduled * args.steps / so_s, "unit": "pods/s", "ms_per_step": 1000 * so_s / args.steps,
                                "path": "ksched_solve(handle, problem*, result*) with host buffers (flat structs in and out)"}},
-        # own kernels per resident Solve: sort_keys, 2x gather_u64, gather_rows, feasibility, pack, finalize_options
-        "gpu_launches": 7 * args.steps,
+        # own kernels per resident Solve: sort_keys, 2x gather_u64, gather_rows, class_feasibility, feasibility, pack, finalize_options
+        "gpu_launches": 8 * args.steps,
         "roofline": {"kernel": "pack_kernel", "bound": "hbm", "achieved": pack_gbs, "peak": peak, "unit": "GB/s", "frac": pack_gbs / peak,
                      "traffic": ncu_traffic(f"pack_kernel_c{args.config}"), "peak_source": peak_src, "algorithmic_bytes": int(pack_bytes),
                      "us_per_launch": pack_avg_us,
@@ -368,7 +368,11 @@ def main():
         "roofline_feasibility": {"kernel": "feasibility_kernel", "bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak,
                                  "traffic": ncu_traffic(f"feasibility_kernel_c{args.config}"), "peak_source": peak_src, "algorithmic_bytes": int(k1_bytes),
                                  "us_per_launch": k1_avg, "us_min": k1_us[0],
-                                 "note": "bytes = P*256 + C*256 + P*C/8 (SURVEY 8d K1), cold L2, this workload's shape"},
+                                 "physical_bytes": int(d["pods"] * 32 + d["pods"] * d["templates"] * d["type_words"] * 8 + d["pods"] * 8),
+                                 "class_pass_us": rs.timings()["class_feasibility_us"],
+                                 "note": "bytes = P*256 + C*256 + P*C/8 (SURVEY 8d K1), cold L2, this workload's shape. Pods of one class share "
+                                         "their row: class_feasibility_kernel evaluates the n_classes distinct rows, this kernel streams the dense "
+                                         "matrix (physical: one 32-byte sector of every pod row + the matrix + the best vector)"},
         "clocks": clocks,
     }
     if rank == 0:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KSCHED_ABI_VERSION 2
+#define KSCHED_ABI_VERSION 3
 #define KSCHED_MAX_KEYS 16
 #define KSCHED_MAX_RES 8
 #define KSCHED_MAX_TEMPLATES 16
@@ -238,6 +238,7 @@ typedef struct ksched_timings {
   int32_t feasibility_launches, pack_launches, sort_launches;
   int32_t pad;
   int64_t h2d_bytes, d2h_bytes; /* host<->device bytes moved by the last ksched_solve (upload + download) */
+  double class_feasibility_us;  /* ksched_run_feasibility_only: the per-class row evaluations that precede the dense-matrix kernel */
 } ksched_timings;
 
 typedef struct ksched_handle ksched_handle;

@@ -168,12 +168,15 @@ constexpr int kK1Cache = 16;  // per-lane words of the previous row's result kep
 
 struct K1Params;
 
+// class_feasibility_kernel: the row evaluation, run over the n_classes DISTINCT pod rows (K1Params::rows = the class table):
+// pods of one class are indistinguishable to the scheduler, so their feasibility rows are identical and each is computed
+// once. feasibility_kernel (below) then materialises the dense pods x (template, instance type) matrix from them.
 // Shared-memory staging: the small tables every row evaluation walks with DEPENDENT loads (templates, key info, the
 // value->row maps, the sorted allocatable arrays of the Fits binary search) are copied once per CTA; the wide column
 // bitsets (valset / fitset / member / offset) stay in global memory and are read one coalesced word per lane.
 // Each warp owns a CONTIGUOUS chunk of the FFD-ordered pod-row matrix: consecutive rows are very often identical in
 // every field that matters to feasibility (same deployment), and then the previous result is written out again.
-__global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel() {
+__global__ void __launch_bounds__(kK1Threads, 1) class_feasibility_kernel() {
   extern __shared__ __align__(16) unsigned char k1_smem[];
 #ifdef KSCHED_PROFILE_K1
   long long t_start = clock64(), t_stage = 0, t_compute = 0, n_compute = 0;
@@ -320,3 +323,46 @@ __global__ void __launch_bounds__(kK1Threads, 1) feasibility_kernel() {
 #endif
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// K1 proper: the dense P x (templates x instance types) feasibility bitmask F and the per-pod best column, in FFD order.
+// Row j of F is the row of pod j's class (class_feasibility_kernel): this kernel is a pure stream - per 32 pod rows one
+// coalesced load of their class words (the `reserved` word of the 256-byte FFD rows K0 wrote), then 16-byte stores of the
+// class rows (read through L1: consecutive pods share a class, the n_classes x RW table stays cache-resident).
+// Algorithmic bytes: P*256 + C*256 + P*C/8; physical: the class word's 32-byte sector of every row + the
+// matrix + the best vector.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) feasibility_kernel(const uint64_t* __restrict__ rows, int n_pods, int n_classes, int RW,
+                                                          const uint32_t* __restrict__ Fclass, const unsigned long long* __restrict__ best_class,
+                                                          uint32_t* __restrict__ F, unsigned long long* __restrict__ best) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nblk = (n_pods + 31) >> 5;
+  const int Q = RW >> 2;  // 16-byte chunks per row (RW = templates x column words is a multiple of 4: W32 is even, see below)
+  for (int blk = warp; blk < nblk; blk += nwarps) {
+    const int j = (blk << 5) + lane;
+    uint32_t cls = 0;
+    if (j < n_pods) {
+      cls = (uint32_t)__ldg(rows + (size_t)j * KSCHED_ROW_WORDS + 31);  // ksched_pod_row::reserved = the row's class
+      if (cls >= (uint32_t)n_classes) cls = 0;
+      best[j] = __ldg(best_class + cls);
+    }
+    const int rows_here = min(32, n_pods - (blk << 5));
+    uint4* dst = reinterpret_cast<uint4*>(F + (size_t)(blk << 5) * RW);
+    const int total = rows_here * Q;
+    if ((RW & 3) == 0) {
+      for (int q0 = 0; q0 < total; q0 += 32) {  // uniform trip count: every lane takes part in the shuffle
+        const int q = q0 + lane, qc = q < total ? q : total - 1;
+        const int r = qc / Q, part = qc - r * Q;
+        const uint32_t c2 = __shfl_sync(0xffffffffu, cls, r);
+        if (q < total) dst[q] = __ldg(reinterpret_cast<const uint4*>(Fclass + (size_t)c2 * RW) + part);
+      }
+    } else {
+      for (int r = 0; r < rows_here; ++r) {
+        const uint32_t c2 = __shfl_sync(0xffffffffu, cls, r);
+        for (int w = lane; w < RW; w += 32) F[((size_t)(blk << 5) + r) * RW + w] = __ldg(Fclass + (size_t)c2 * RW + w);
+      }
+    }
+  }
+}

@@ -2,7 +2,7 @@
 //
 //  K0  sort_keys / gather_rows   FFD order of the queue (queue.go:35-110) and the dense, FFD-ordered
 //                                P x 256 B pod-row matrix the feasibility kernel streams.
-//  K1  feasibility_kernel        dense pods x (template, instance type) bitmask F, bit-sliced over columns:
+//  K1  class_feasibility_kernel + feasibility_kernel: dense pods x (template, instance type) bitmask F, bit-sliced over columns:
 //                                Requirements.Compatible/Intersects (requirements.go:123-206), fits /
 //                                hasOffering (node.go:143-159), Taints.Tolerates (taints.go:28) as AND/OR of
 //                                precomputed column bitsets; warp ballot/ffs gives the per-pod best column.
@@ -179,7 +179,8 @@ struct ksched_handle {
   DevBuf<ksched_reqset> d_filter_terms;
   DevBuf<int32_t> d_hostname_reqs, d_relax, d_assign, d_place_seq, d_last_len, d_nn_count, d_nn_tb, d_ov_node, d_perm_desc, d_grp_cnt,
       d_grp_cnt0, d_grp_host_row, d_grp_host_total, d_grp_host_total0;
-  DevBuf<uint32_t> d_F;
+  DevBuf<uint32_t> d_F, d_Fclass;
+  DevBuf<unsigned long long> d_best_class;
   DevBuf<unsigned long long> d_best;
   DevBuf<int64_t> d_ex_req, d_ex_req0, d_ex_avail, d_nn_req, d_remaining, d_alloc_rt;
   DevBuf<long long> d_ov_q, d_ov_bound, d_ov_bound2, d_fc_bound, d_fc_bound2;
@@ -252,6 +253,7 @@ int ksched_create(int device_ordinal, ksched_handle** out) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, pack_kernel);
     cudaFuncGetAttributes(&fa, feasibility_kernel);
+    cudaFuncGetAttributes(&fa, class_feasibility_kernel);
     cudaFuncGetAttributes(&fa, finalize_options_kernel);
     cudaFuncGetAttributes(&fa, gather_rows_kernel);
     cudaFuncGetAttributes(&fa, sort_keys_kernel);
@@ -632,13 +634,15 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
     }
     h->n_hostgroups = nh;
     const size_t stride = (size_t)NE + MAXN;
-    std::vector<uint16_t> host((size_t)std::max(nh, 1) * stride, 0);
+    // [hostname group][existing node | new node slot] counters: only the existing-node columns carry initial values, the
+    // rest of the (up to 40 MB) matrix is zeroed on the device instead of being built and shipped from the host
+    std::vector<uint16_t> host((size_t)std::max(nh, 1) * std::max(NE, 1), 0);
     for (int g = 0; g < NG; ++g) {
       if (host_row[g] < 0) continue;
       int total = pb->groups[g].extra_nonzero_domains;
       for (int e = 0; e < NE; ++e) {
         int32_t v = pb->group_existing_counts[(size_t)g * std::max(NE, 1) + e];
-        host[(size_t)host_row[g] * stride + e] = (uint16_t)std::min(v, 0xFFFF);
+        host[(size_t)host_row[g] * NE + e] = (uint16_t)std::min(v, 0xFFFF);
         if (v > 0) ++total;
       }
       host_total[g] = total;
@@ -668,7 +672,13 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
     CUDA_TRY(h, upload_vec(h, h->d_grp_host_total0, host_total));
     CUDA_TRY(h, upload_vec(h, h->d_grp_cnt0, cnt));
     CUDA_TRY(h, upload_vec(h, h->d_grp_registered0, registered));
-    CUDA_TRY(h, upload_vec(h, h->d_grp_host0, host));
+    CUDA_TRY(h, h->d_grp_host0.ensure((size_t)std::max(nh, 1) * stride));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_grp_host0.ptr, 0, (size_t)std::max(nh, 1) * stride * sizeof(uint16_t), h->stream));
+    if (NE > 0 && nh > 0) {
+      CUDA_TRY(h, cudaMemcpy2DAsync(h->d_grp_host0.ptr, stride * sizeof(uint16_t), host.data(), (size_t)NE * sizeof(uint16_t), (size_t)NE * sizeof(uint16_t),
+                                    (size_t)nh, cudaMemcpyHostToDevice, h->stream));
+      h->tm.h2d_bytes += (int64_t)nh * NE * 2;
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, h->d_grp_host_total.ensure(std::max(NG, 1)));
     CUDA_TRY(h, h->d_grp_cnt.ensure((size_t)std::max(NG, 1) * 64));
@@ -682,6 +692,8 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   CUDA_TRY(h, h->d_rows.ensure(p1 * KSCHED_ROW_WORDS));
   CUDA_TRY(h, h->d_F.ensure(p1 * V * W32));
   CUDA_TRY(h, h->d_best.ensure(p1));
+  CUDA_TRY(h, h->d_Fclass.ensure((size_t)std::max(NC, 1) * V * W32));
+  CUDA_TRY(h, h->d_best_class.ensure((size_t)std::max(NC, 1)));
   CUDA_TRY(h, h->d_relax.ensure(p1)); CUDA_TRY(h, h->d_assign.ensure(p1)); CUDA_TRY(h, h->d_place_seq.ensure(p1));
   CUDA_TRY(h, h->d_queue.ensure(p1 + 1)); CUDA_TRY(h, h->d_last_len.ensure(p1)); CUDA_TRY(h, h->d_last_epoch.ensure(p1));
   const size_t mn = (size_t)MAXN;
@@ -743,12 +755,13 @@ static int run_sort(ksched_handle* h) {
 }
 
 static void fill_k1(ksched_handle* h, K1Params& k1) {
+  // the row evaluation runs over the class table (every class once); feasibility_kernel replicates the rows per pod
   k1.cat = h->cat;
-  k1.rows = h->d_rows.ptr;
-  k1.n_pods = h->n_pods;
+  k1.rows = reinterpret_cast<const uint64_t*>(h->d_classes.ptr);
+  k1.n_pods = h->n_classes;
   k1.itype_sets = h->d_itype_sets.ptr;
-  k1.F = h->d_F.ptr;
-  k1.best = h->d_best.ptr;
+  k1.F = h->d_Fclass.ptr;
+  k1.best = h->d_best_class.ptr;
   const int W32 = h->cat.W32;
   if (h->world > 1) {
     ksched_shard_range(W32, h->rank, h->world, &k1.word_begin, &k1.word_end);
@@ -761,8 +774,9 @@ static void fill_k1(ksched_handle* h, K1Params& k1) {
 static std::mutex g_k1_mu;
 static cudaEvent_t g_k1_done[64] = {};
 
-static int run_feasibility(ksched_handle* h) {
-  if (h->n_pods == 0) return KSCHED_OK;
+// K1, class pass: every distinct pod row evaluated once (class_feasibility_kernel over the class table).
+static int run_class_feasibility(ksched_handle* h) {
+  if (h->n_pods == 0 || h->n_classes == 0) return KSCHED_OK;
   K1Params k1;
   fill_k1(h, k1);
   const DevCatalog& c = h->cat;
@@ -775,10 +789,9 @@ static int run_feasibility(ksched_handle* h) {
   const size_t table_bytes = (size_t)(h->n_valrows + 2 * c.n_keys + h->n_offrows + 1 + c.n_templates) * c.W32 * sizeof(uint32_t);
   k1.tables_in_smem = smem + table_bytes <= (size_t)(160 << 10) ? 1 : 0;
   if (k1.tables_in_smem) smem += table_bytes;
-  // one CTA per SM at most; every warp takes a contiguous chunk of >= 8 rows
+  // one warp per class row (a row evaluation is ~10k cycles of dependent work: no chunking)
   const int warps_per_block = kK1Threads / 32;
-  const int want_warps = std::max(1, (h->n_pods + 7) / 8);
-  const int blocks = std::max(1, std::min(148, (want_warps + warps_per_block - 1) / warps_per_block));
+  const int blocks = std::max(1, std::min(148 * 2, (h->n_classes + warps_per_block - 1) / warps_per_block));
   k1.dbg = nullptr;
 #ifdef KSCHED_PROFILE_K1
   CUDA_TRY(h, h->d_k1dbg.ensure(8));
@@ -793,8 +806,10 @@ static int run_feasibility(ksched_handle* h) {
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, done, 0));
     h->k1_host = k1;
     CUDA_TRY(h, cudaMemcpyToSymbolAsync(g_k1, &h->k1_host, sizeof(K1Params), 0, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaFuncSetAttribute(feasibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per function: under the launch lock
-    feasibility_kernel<<<blocks, kK1Threads, smem, h->stream>>>();
+    CUDA_TRY(h, cudaFuncSetAttribute(class_feasibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per function: under the launch lock
+    if (h->world > 1)  // column words of the other shards read as 0
+      CUDA_TRY(h, cudaMemsetAsync(h->d_Fclass.ptr, 0, (size_t)std::max(h->n_classes, 1) * c.n_templates * c.W32 * 4, h->stream));
+    class_feasibility_kernel<<<blocks, kK1Threads, smem, h->stream>>>();
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(done, h->stream));
   }
@@ -807,7 +822,19 @@ static int run_feasibility(ksched_handle* h) {
             blocks, dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[4] ? dbg[5] / dbg[4] : 0);
   }
 #endif
-  h->tm.feasibility_launches = 1;
+  return KSCHED_OK;
+}
+
+// K1 proper: the dense pods x (template, instance type) matrix and the per-pod best column, streamed from the class rows.
+static int run_feasibility(ksched_handle* h) {
+  if (h->n_pods == 0) return KSCHED_OK;
+  const int RW = h->cat.n_templates * h->cat.W32;
+  const int nblk = (h->n_pods + 31) / 32;
+  const int blocks = std::max(1, std::min(148 * 8, (nblk + 7) / 8));  // 8 warps per CTA, one 32-row block per warp and iteration
+  feasibility_kernel<<<blocks, 256, 0, h->stream>>>(h->d_rows.ptr, h->n_pods, h->n_classes, RW, h->d_Fclass.ptr, h->d_best_class.ptr, h->d_F.ptr,
+                                                    h->d_best.ptr);
+  CUDA_TRY(h, cudaGetLastError());
+  h->tm.feasibility_launches = 2;
   const long long C = (long long)h->cat.n_templates * h->cat.n_types;
   h->tm.feasibility_bytes = (long long)h->n_pods * 256 + C * 256 + (long long)h->n_pods * C / 8;
   return KSCHED_OK;
@@ -932,6 +959,7 @@ int ksched_run_resident(ksched_handle* h, int do_flush) {
   CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
   if ((rc = run_sort(h)) != KSCHED_OK) return rc;
   CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+  if ((rc = run_class_feasibility(h)) != KSCHED_OK) return rc;
   if ((rc = run_feasibility(h)) != KSCHED_OK) return rc;
   CUDA_TRY(h, cudaEventRecord(h->ev[2], h->stream));
   h->tm.allreduce_us = 0;
@@ -960,6 +988,8 @@ int ksched_run_feasibility_only(ksched_handle* h, int do_flush, float* elapsed_u
     CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)h->n_pods * 4, cudaMemcpyDeviceToDevice, h->stream));
     if ((rc = run_sort(h)) != KSCHED_OK) return rc;
   }
+  CUDA_TRY(h, cudaEventRecord(h->ev[7], h->stream));
+  if ((rc = run_class_feasibility(h)) != KSCHED_OK) return rc;  // n_classes row evaluations (timed on their own)
   if (do_flush && (rc = flush_l2(h)) != KSCHED_OK) return rc;
   CUDA_TRY(h, cudaEventRecord(h->ev[5], h->stream));
   if ((rc = run_feasibility(h)) != KSCHED_OK) return rc;
@@ -968,6 +998,7 @@ int ksched_run_feasibility_only(ksched_handle* h, int do_flush, float* elapsed_u
   CUDA_TRY(h, cudaGetLastError());
   if (elapsed_us) *elapsed_us = ev_us(h->ev[5], h->ev[6]);
   h->tm.feasibility_us = ev_us(h->ev[5], h->ev[6]);
+  h->tm.class_feasibility_us = ev_us(h->ev[7], h->ev[5]);  // includes the L2 flush when one was asked for
   return KSCHED_OK;
 }
 

@@ -114,7 +114,7 @@ void decode(const Encoded& E, const ResultBuffers& B, Result& out) {
     const uint64_t* bits = &B.types[(size_t)n * E.type_words];
     std::fill(in_order.begin(), in_order.end(), 0);
     size_t n_opts = 0;
-    for (size_t w = 0; w < E.type_words; ++w) {
+    for (size_t w = 0; w < (size_t)E.type_words; ++w) {
       uint64_t m = bits[w];
       while (m) {
         const size_t c = w * 64 + (size_t)__builtin_ctzll(m);

@@ -19,7 +19,7 @@ def test_library_exports_every_header_symbol(pkg):
     lib = pkg.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.ksched_abi_version() == int(re.search(r"#define\s+KSCHED_ABI_VERSION\s+(\d+)", header).group(1)) == 2
+    assert lib.ksched_abi_version() == int(re.search(r"#define\s+KSCHED_ABI_VERSION\s+(\d+)", header).group(1)) == 3
     assert lib.ksched_type_words(1000) == 16 and lib.ksched_type_words(1) == 1 and lib.ksched_type_words(65) == 2
 
 
