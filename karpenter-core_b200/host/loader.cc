@@ -194,6 +194,12 @@ Pod pod(const Value& e, size_t index) {
   p.is_daemonset = e.boolean("isDaemonSet");
   p.terminal = e.boolean("terminal");
   p.terminating = e.boolean("terminating");
+  if (const Value* vs = e.get("volumes"))
+    for (auto& v : vs->arr) p.volumes.push_back({v.s("driver"), v.s("pvc")});
+  if (e.has("deletionCost")) { p.has_deletion_cost = true; p.deletion_cost = e.d("deletionCost"); }
+  if (e.has("priority")) { p.has_priority = true; p.priority = (int32_t)e.i("priority"); }
+  p.do_not_evict = e.boolean("doNotEvict");
+  p.owned_by_node = e.boolean("ownedByNode");
   return p;
 }
 }  // namespace
@@ -233,6 +239,8 @@ Problem* problem_from_json(const char* text) {
         pr.has_limits = true;
         pr.limits = resources(l);
       }
+      pr.consolidation_enabled = e.boolean("consolidationEnabled");
+      if (e.has("ttlSecondsUntilExpired")) { pr.has_ttl_until_expired = true; pr.ttl_seconds_until_expired = e.i("ttlSecondsUntilExpired"); }
       if (const Value* its = e.get("instanceTypes"); its && its->kind == Value::Arr) {
         for (auto& x : its->arr) pr.instance_types.push_back((int32_t)x.num);
       } else {
@@ -260,6 +268,12 @@ Problem* problem_from_json(const char* text) {
       n.marked_for_deletion = e.boolean("markedForDeletion");
       n.candidate = e.boolean("candidate");
       n.disruption_cost = e.d("disruptionCost");
+      n.deleting = e.boolean("deleting");
+      n.nominated = e.boolean("nominated");
+      if (e.has("doNotConsolidate")) n.do_not_consolidate = e.s("doNotConsolidate") == "true" ? 1 : 2;
+      n.creation_ts = e.d("creationTimestamp");
+      if (const Value* vl = e.get("volumeLimits"); vl && !vl->is_null())
+        for (auto& kv : vl->obj) n.volume_limits[kv.first] = (int32_t)kv.second.num;
       P.nodes.push_back(std::move(n));
     }
   if (const Value* ps = root.get("pods")) {
@@ -273,6 +287,16 @@ Problem* problem_from_json(const char* text) {
       P.daemonset_pods.back().is_daemonset = true;
     }
   }
+  if (const Value* ps = root.get("pdbs"))
+    for (auto& e : ps->arr) {
+      PodDisruptionBudget b;
+      b.ns = e.s("namespace", "default");
+      b.selector = selector(e.get("selector"));
+      b.disruptions_allowed = (int32_t)e.i("disruptionsAllowed");
+      P.pdbs.push_back(std::move(b));
+    }
+  P.now_ts = root.d("now");
+  P.derive_candidates = root.boolean("deriveCandidates");
   P.simulation_mode = root.boolean("simulationMode");
   P.empty_topology = root.boolean("emptyTopology");
   return prob.release();

@@ -85,6 +85,12 @@ struct Container {
   std::vector<HostPort> ports;
 };
 
+// One volume of a pod as the host resolved it (volumeusage.go:133-190 does the API Gets: PVC -> storage class / bound PV ->
+// CSI driver name). driver "" = a non-CSI volume, which the reference does not track.
+struct PodVolume {
+  std::string driver, pvc_id;  // pvc_id = "<namespace>/<claim>" (or the generated ephemeral claim name)
+};
+
 struct Pod {
   std::string name, ns = "default", uid;
   int64_t creation_ts = 0;
@@ -105,6 +111,14 @@ struct Pod {
   std::string node_name;
   bool is_daemonset = false;
   bool terminal = false, terminating = false;
+  std::vector<PodVolume> volumes;           // Spec.Volumes that are PVC / ephemeral claims (existingnode.go:91-96)
+  // deprovisioning candidate ranking (deprovisioning/helpers.go:125-165,339-366)
+  bool has_deletion_cost = false;           // controller.kubernetes.io/pod-deletion-cost annotation parsed as a float
+  double deletion_cost = 0;
+  bool has_priority = false;                // Spec.Priority != nil
+  int32_t priority = 0;
+  bool do_not_evict = false;                // karpenter.sh/do-not-evict: "true"
+  bool owned_by_node = false;               // static / mirror pod (ownerReference v1 Node)
 };
 
 struct Offering {
@@ -129,6 +143,9 @@ struct Provisioner {
   std::vector<Taint> taints, startup_taints;
   bool has_limits = false;  // Spec.Limits != nil
   ResourceList limits;
+  bool consolidation_enabled = false;       // Spec.Consolidation.Enabled (consolidation.go:104-118)
+  bool has_ttl_until_expired = false;       // Spec.TTLSecondsUntilExpired != nil (helpers.go:275-287)
+  int64_t ttl_seconds_until_expired = 0;
   std::vector<int32_t> instance_types;  // indices into Problem.instance_types (GetInstanceTypes result)
 };
 
@@ -144,6 +161,19 @@ struct StateNode {
   // consolidation candidate data (deprovisioning/helpers.go:171-249)
   bool candidate = false;
   double disruption_cost = 0;
+  // raw inputs of candidateNodes / sortAndFilterCandidates (used when Problem.derive_candidates is set)
+  bool deleting = false;                    // DeletionTimestamp != nil (helpers.go:340)
+  bool nominated = false;                   // state.Node.Nominated()
+  int8_t do_not_consolidate = 0;            // karpenter.sh/do-not-consolidate annotation: 0 absent, 1 "true", 2 any other value
+  double creation_ts = 0;                   // seconds (node.CreationTimestamp)
+  std::map<std::string, int32_t> volume_limits;  // CSINode driver -> Allocatable.Count (state/cluster.go:292-303)
+};
+
+// policy/v1 PodDisruptionBudget as PDBLimits reads it (deprovisioning/pdblimits.go:34-80)
+struct PodDisruptionBudget {
+  std::string ns;
+  LabelSelector selector;
+  int32_t disruptions_allowed = 0;
 };
 
 // Derived, dictionary-independent facts about the cluster state that every encoding of the same Problem needs again
@@ -161,6 +191,9 @@ struct Problem {
   std::vector<StateNode> nodes;
   std::vector<Pod> pods;            // pending pods handed to Solve
   std::vector<Pod> daemonset_pods;  // daemonset template pods (getDaemonSetPods)
+  std::vector<PodDisruptionBudget> pdbs;
+  double now_ts = 0;                 // the clock candidateNodes reads (seconds)
+  bool derive_candidates = false;    // candidate / disruption_cost of every node come from rank_candidates, not from the fields
   bool simulation_mode = false;
   bool empty_topology = false;  // benchmark passes &scheduling.Topology{} (scheduling_benchmark_test.go:123)
 };

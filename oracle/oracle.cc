@@ -685,6 +685,30 @@ struct SchedNode {  // node.go:34-40
   bool max_alloc_valid = false;
 };
 
+// volumeusage.go:33-131. The API Gets of validate() (:133-190) happen on the host: a pod arrives with (driver, pvc id) pairs.
+struct VolumeUsage {
+  std::map<std::string, std::set<std::string>> volumes;  // driver -> mounted pvc ids
+  static std::map<std::string, std::set<std::string>> of(const Pod& pod) {
+    std::map<std::string, std::set<std::string>> v;
+    for (auto& pv : pod.volumes) if (!pv.driver.empty()) v[pv.driver].insert(pv.pvc_id);  // :180-183 non-CSI volumes are not tracked
+    return v;
+  }
+  // Validate :121-131 -> VolumeCount; Exceeds :101-112
+  bool exceeds(const Pod& pod, const std::map<std::string, int32_t>& limits) const {
+    auto u = volumes;
+    for (auto& kv : of(pod)) u[kv.first].insert(kv.second.begin(), kv.second.end());
+    for (auto& kv : u) {
+      auto l = limits.find(kv.first);
+      if (l == limits.end()) continue;
+      if ((int64_t)kv.second.size() > (int64_t)l->second) return true;
+    }
+    return false;
+  }
+  void add(const Pod& pod) {  // Add :91-98
+    for (auto& kv : of(pod)) volumes[kv.first].insert(kv.second.begin(), kv.second.end());
+  }
+};
+
 struct ExistingNode {  // existingnode.go:28-39
   int state_index;
   std::vector<int> pods;
@@ -692,6 +716,8 @@ struct ExistingNode {  // existingnode.go:28-39
   Requirements req;
   std::vector<Taint> taints;
   HostPortUsage ports;
+  VolumeUsage volumes;
+  std::map<std::string, int32_t> volume_limits;
   bool initialized;
 };
 
@@ -816,10 +842,11 @@ struct Scheduler {
     n.ports.add(pod);
     return true;
   }
-  bool existing_add(ExistingNode& n, int pi) {  // existingnode.go:77-130 (volume limits: host-side pre-filter, out of scope)
+  bool existing_add(ExistingNode& n, int pi) {  // existingnode.go:77-130
     Pod& pod = pods[pi];
     if (!tolerates(n.taints, pod)) return false;
     if (!n.ports.validate(pod)) return false;
+    if (n.volumes.exceeds(pod, n.volume_limits)) return false;  // :88-96
     ResourceList requests = merge(n.requests, requests_for_pod(pod));
     if (!fits(requests, n.available)) return false;
     Requirements node_req;
@@ -836,6 +863,7 @@ struct Scheduler {
     n.req = std::move(node_req);
     topology.Record(pod, n.req);
     n.ports.add(pod);
+    n.volumes.add(pod);
     return true;
   }
 
@@ -1007,6 +1035,8 @@ struct Scheduler {
       e.requests = rem_daemon;
       e.req = Requirements::FromLabels(n.labels);
       for (auto& p : n.pods) e.ports.add(p);
+      for (auto& p : n.pods) e.volumes.add(p);  // state.Node.VolumeUsage(): every pod bound to the node (state/cluster.go:340-347)
+      e.volume_limits = n.volume_limits;
       auto init_it = n.labels.find(kInitialized);
       e.initialized = init_it != n.labels.end() && init_it->second == "true";
       std::string hostname;
@@ -1152,35 +1182,111 @@ double worst_launch_price(const InstanceType& it, const std::map<std::string, st
 }
 }  // namespace
 
+// GetPodEvictionCost helpers.go:125-146
+static double clampd(double lo, double v, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+double pod_eviction_cost(const Pod& p) {
+  double cost = 1.0;
+  if (p.has_deletion_cost) cost += p.deletion_cost / 134217728.0;   // math.Pow(2, 27)
+  if (p.has_priority) cost += (double)p.priority / 33554432.0;      // math.Pow(2, 25)
+  return clampd(-10.0, cost, 10.0);
+}
+
+// candidateNodes (helpers.go:171-249) with consolidation.ShouldDeprovision (consolidation.go:104-118) as the filter, then
+// sortAndFilterCandidates (consolidation.go:85-103): canBeTerminated (helpers.go:339-366, PDBLimits pdblimits.go:55-68) and the
+// sort by disruption cost (R4: stable). Without Problem.derive_candidates the `candidate` / `disruption_cost` fields are inputs.
+void rank_candidates(const Problem& P, std::vector<int>* order, std::vector<double>* cost_out) {
+  struct C { int node; double cost; };
+  std::vector<C> cands;
+  for (size_t i = 0; i < P.nodes.size(); ++i) {
+    const StateNode& n = P.nodes[i];
+    if (!P.derive_candidates) {
+      if (n.candidate) cands.push_back({(int)i, n.disruption_cost});
+      continue;
+    }
+    const Provisioner* prov = nullptr;
+    auto pl = n.labels.find(kProvisionerName);
+    if (pl != n.labels.end())
+      for (auto& pr : P.provisioners) if (pr.name == pl->second) prov = &pr;
+    if (n.marked_for_deletion) continue;                    // :186-188
+    if (!prov) continue;                                    // :190-192
+    auto itn = n.labels.find(kInstanceType);                // :194-198 instance type must be one the provisioner offers
+    bool it_ok = false;
+    if (itn != n.labels.end())
+      for (int idx : prov->instance_types) if (P.instance_types[(size_t)idx].name == itn->second) it_ok = true;
+    if (!it_ok) continue;
+    if (!n.labels.count(kCapacityType) || !n.labels.count(kZone)) continue;  // :201-208
+    auto ini = n.labels.find(kInitialized);
+    if (ini == n.labels.end() || ini->second != "true") continue;            // :211-213
+    if (n.nominated) continue;                                               // :215-217
+    // ShouldDeprovision consolidation.go:104-118
+    if (n.do_not_consolidate != 0) { if (n.do_not_consolidate == 1) continue; }
+    else if (!prov->consolidation_enabled) continue;
+    double cost = 0.0;                                      // disruptionCost helpers.go:159-165
+    for (auto& p : n.pods) cost += pod_eviction_cost(p);
+    double remaining = 1.0;                                 // calculateLifetimeRemaining helpers.go:275-287
+    if (prov->has_ttl_until_expired) {
+      const double age = P.now_ts - n.creation_ts, total = (double)prov->ttl_seconds_until_expired;
+      remaining = clampd(0.0, (total - age) / total, 1.0);
+    }
+    cost *= remaining;
+    // canBeTerminated helpers.go:339-351
+    if (n.deleting) continue;
+    bool blocked = false;
+    for (auto& p : n.pods) {                                // CanEvictPods pdblimits.go:55-68
+      for (auto& b : P.pdbs)
+        if (b.ns == p.ns && !b.selector.is_nil && selector_matches_nonnil(b.selector, p.labels) && b.disruptions_allowed == 0) blocked = true;
+    }
+    for (auto& p : n.pods) {                                // PodsPreventEviction helpers.go:354-366
+      if (p.terminating || p.terminal || p.owned_by_node) continue;
+      if (p.do_not_evict) blocked = true;
+    }
+    if (blocked) continue;
+    cands.push_back({(int)i, cost});
+  }
+  std::stable_sort(cands.begin(), cands.end(), [](const C& a, const C& b) { return a.cost < b.cost; });
+  order->clear();
+  if (cost_out) cost_out->clear();
+  for (auto& c : cands) { order->push_back(c.node); if (cost_out) cost_out->push_back(c.cost); }
+}
+
 // The scheduler result keeps requirements only as canonical strings; for the price guard we need the
 // Requirements object of the single new node, so the simulation is re-run here with access to internals.
-void consolidate(const Problem& P, ConsolidationResult& out, int only_count) {
+// mode 0: firstNNodeConsolidationOption (multinodeconsolidation.go:74-114); only_count > 0: ONE computeConsolidation (+ the
+// multi-node caller's filterOutSameType) over that many cheapest candidates; mode 1: SingleNodeConsolidation.ComputeCommand
+// (singlenodeconsolidation.go:43-84, Validation taken as valid: it re-runs the same simulation after a TTL).
+static void consolidate_impl(const Problem& P, ConsolidationResult& out, int only_count, int mode, int single_only) {
   out = ConsolidationResult();
   try {
     std::vector<Candidate> cands;
-    for (size_t i = 0; i < P.nodes.size(); ++i) {
-      const StateNode& n = P.nodes[i];
-      if (!n.candidate) continue;
-      Candidate c;
-      c.node = (int)i;
-      c.cost = n.disruption_cost;
-      auto itn = n.labels.find(kInstanceType);
-      c.it = nullptr;
-      if (itn != n.labels.end())
-        for (auto& t : P.instance_types) if (t.name == itn->second) c.it = &t;
-      auto ct = n.labels.find(kCapacityType);
-      c.capacity_type = ct == n.labels.end() ? "" : ct->second;
-      auto z = n.labels.find(kZone);
-      c.zone = z == n.labels.end() ? "" : z->second;
-      cands.push_back(c);
+    {
+      std::vector<int> order;
+      std::vector<double> costs;
+      rank_candidates(P, &order, &costs);
+      for (size_t q = 0; q < order.size(); ++q) {
+        const StateNode& n = P.nodes[(size_t)order[q]];
+        Candidate c;
+        c.node = order[q];
+        c.cost = costs[q];
+        auto itn = n.labels.find(kInstanceType);
+        c.it = nullptr;
+        if (itn != n.labels.end())
+          for (auto& t : P.instance_types) if (t.name == itn->second) c.it = &t;
+        auto ct = n.labels.find(kCapacityType);
+        c.capacity_type = ct == n.labels.end() ? "" : ct->second;
+        auto z = n.labels.find(kZone);
+        c.zone = z == n.labels.end() ? "" : z->second;
+        cands.push_back(c);
+      }
     }
-    // sortAndFilterCandidates consolidation.go:100-103 (R4 stable)
-    std::stable_sort(cands.begin(), cands.end(), [](const Candidate& a, const Candidate& b) { return a.cost < b.cost; });
     for (auto& c : cands) out.candidate_order.push_back(c.node);
 
     struct Cmd { int action = 0; std::vector<int> options; };
-    auto compute = [&](int count) -> Cmd {  // consolidation.go:190-274 on candidates[0:count]
+    auto compute_set = [&](const std::vector<int>& which, bool multi) -> Cmd {  // consolidation.go:190-274 on the given candidates
       Cmd cmd;
+      const int count = (int)which.size();
+      std::vector<Candidate> sel;
+      for (int i : which) sel.push_back(cands[(size_t)i]);
+      const std::vector<Candidate>& cands = sel;  // the code below indexes the selected candidates 0..count-1
       std::vector<int> nodes;
       for (int i = 0; i < count; ++i) nodes.push_back(cands[i].node);
       std::vector<int> state_nodes;
@@ -1219,6 +1325,11 @@ void consolidate(const Problem& P, ConsolidationResult& out, int only_count) {
       if (all_spot && nn.req.Get(kCapacityType).Has("spot")) return cmd;
       Requirement ct = nn.req.Get(kCapacityType);
       if (ct.Has("spot") && ct.Has("on-demand")) nn.req.Add(Requirement::New(kCapacityType, Op::In, {"spot"}));
+      if (!multi) {  // single-node consolidation returns computeConsolidation's command as it is
+        cmd.action = 2;
+        for (auto* t : opts) cmd.options.push_back(t->index);
+        return cmd;
+      }
       // filterOutSameType multinodeconsolidation.go:132-165 (applied by the multi-node caller)
       std::set<std::string> existing_types;
       std::map<std::string, double> by_type;
@@ -1243,6 +1354,35 @@ void consolidate(const Problem& P, ConsolidationResult& out, int only_count) {
       for (auto* t : opts2) cmd.options.push_back(t->index);
       return cmd;
     };
+    auto compute = [&](int count) -> Cmd {
+      std::vector<int> which;
+      for (int i = 0; i < count; ++i) which.push_back(i);
+      return compute_set(which, true);
+    };
+    if (mode == 1) {
+      if (single_only >= 0) {  // one candidate's computeConsolidation (position in the cost order)
+        if (single_only >= (int)cands.size()) throw std::runtime_error("candidate out of range");
+        Cmd c = compute_set({single_only}, false);
+        out.action = c.action;
+        out.nodes_removed = (c.action == 1 || c.action == 2) ? 1 : 0;
+        out.replacement_options = c.options;
+        out.single_node = (c.action == 1 || c.action == 2) ? cands[(size_t)single_only].node : -1;
+        return;
+      }
+      for (size_t i = 0; i < cands.size(); ++i) {  // singlenodeconsolidation.go:54-77
+        Cmd c = compute_set({(int)i}, false);
+        out.probes.push_back((int)i);
+        out.probe_actions.push_back(c.action);
+        if (c.action == 1 || c.action == 2) {
+          out.action = c.action;
+          out.nodes_removed = 1;
+          out.replacement_options = c.options;
+          out.single_node = cands[i].node;
+          return;
+        }
+      }
+      return;
+    }
 
     if (only_count > 0) {  // one computeConsolidation over the `only_count` cheapest candidates (tests of the price guards)
       if (only_count > (int)cands.size()) throw std::runtime_error("probe size out of range");
@@ -1277,5 +1417,8 @@ void consolidate(const Problem& P, ConsolidationResult& out, int only_count) {
     out.error = e.what();
   }
 }
+
+void consolidate(const Problem& P, ConsolidationResult& out, int only_count) { consolidate_impl(P, out, only_count, 0, -1); }
+void consolidate_single(const Problem& P, ConsolidationResult& out, int only_candidate) { consolidate_impl(P, out, 0, 1, only_candidate); }
 
 }  // namespace oracle

@@ -27,10 +27,17 @@ struct ConsolidationResult {
   std::vector<int> candidate_order;      // node indices in disruption-cost order
   std::vector<int> probes, probe_actions;  // binary-search trace (prefix length, action)
   int simulations = 0;
+  int single_node = -1;   // consolidate_single: Problem.nodes index of the node the command removes
   std::string error;
 };
 // MultiNodeConsolidation.firstNNodeConsolidationOption (multinodeconsolidation.go:74-114)
 // only_count > 0: a single computeConsolidation over that many candidates instead of the search
 void consolidate(const kmodel::Problem& P, ConsolidationResult& out, int only_count = 0);
+// SingleNodeConsolidation.ComputeCommand (singlenodeconsolidation.go:43-84): candidates in disruption-cost order, the first one
+// whose computeConsolidation yields delete / replace wins. probes = positions tried. only_candidate >= 0: just that position.
+void consolidate_single(const kmodel::Problem& P, ConsolidationResult& out, int only_candidate = -1);
+// candidateNodes + sortAndFilterCandidates (helpers.go:171-249,339-366, consolidation.go:85-118, pdblimits.go:55-68)
+void rank_candidates(const kmodel::Problem& P, std::vector<int>* order, std::vector<double>* cost);
+double pod_eviction_cost(const kmodel::Pod& p);  // helpers.go:125-146
 
 }  // namespace oracle

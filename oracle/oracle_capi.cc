@@ -95,4 +95,25 @@ int oracle_consolidate(const kmodel::Problem* P, int* nodes_removed, int* simula
   put(r.error, err, err_cap);
   return r.error.empty() ? r.action : -1;
 }
+
+// single-node consolidation: returns the action; node = Problem.nodes index removed (-1 none); probes = positions tried
+int oracle_consolidate_single(const kmodel::Problem* P, int only_candidate, int* node, int* options, int options_cap, int* n_options,
+                              int* n_probes, char* err, int err_cap) {
+  ConsolidationResult r;
+  consolidate_single(*P, r, only_candidate);
+  *node = r.single_node;
+  *n_options = (int)r.replacement_options.size();
+  for (int i = 0; i < *n_options && i < options_cap; ++i) options[i] = r.replacement_options[i];
+  *n_probes = (int)r.probes.size();
+  put(r.error, err, err_cap);
+  return r.error.empty() ? r.action : -1;
+}
+// candidate ranking: order = Problem.nodes indices in disruption order, cost parallel; returns the number of candidates
+int oracle_rank_candidates(const kmodel::Problem* P, int* order, double* cost, int cap) {
+  std::vector<int> o;
+  std::vector<double> c;
+  rank_candidates(*P, &o, &c);
+  for (size_t i = 0; i < o.size() && (int)i < cap; ++i) { order[i] = o[i]; cost[i] = c[i]; }
+  return (int)o.size();
+}
 }
