@@ -13,8 +13,9 @@
  *  - label keys are dictionary ids; up to KSCHED_MAX_KEYS "mask keys", each with <= 63 distinct values,
  *    one bit per value. kubernetes.io/hostname and node.kubernetes.io/instance-type are NOT mask keys:
  *    a node's hostname is its slot index, an instance-type requirement is a bitset over types.
- *  - a requirement mirrors pkg/scheduling/requirement.go:36-42 exactly: {complement, values, >gt, <lt};
- *    `values` are the members (complement=0) or the excluded members (complement=1).
+ *  - a requirement mirrors pkg/scheduling/requirement.go:36-42: {complement, values}; `values` are the members
+ *    (complement=0) or the excluded members (complement=1). Gt/Lt bounds travel as excluded REGION bits
+ *    (ksched_key_regions below), so the device algebra is pure mask arithmetic.
  *  - resource quantities are int64 milli-units (k8s resource.Quantity, exact for whole milli values).
  *  - instance types ("columns") are supplied in ascending (cheapest available offering price, input
  *    index) order; type_input_index maps back to the caller's slice order (lo.Filter keeps input order,
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KSCHED_ABI_VERSION 3
+#define KSCHED_ABI_VERSION 4
 #define KSCHED_MAX_KEYS 16
 #define KSCHED_MAX_RES 8
 #define KSCHED_MAX_TEMPLATES 16
@@ -58,11 +59,37 @@ typedef struct ksched_reqset {
   uint64_t meta;
 } ksched_reqset; /* 136 bytes */
 
-/* Optional integer bounds (Gt/Lt, requirement.go:58-66) for one reqset; only read where meta has HASGT/HASLT. */
+/* Integer bounds (Gt/Lt, requirement.go:58-66) of one reqset in the HOST algebra (csrc/reqmask.cuh); only read where meta
+ * has HASGT/HASLT. Nothing that crosses the C-ABI carries them: see ksched_key_regions. */
 typedef struct ksched_bounds {
   int64_t gt[KSCHED_MAX_KEYS];
   int64_t lt[KSCHED_MAX_KEYS];
 } ksched_bounds;
+
+/*
+ * Region form of Gt/Lt — how bounded requirements cross the C-ABI and live on the device.
+ * For one key let t[0] < ... < t[m-1] be every threshold any Gt/Lt requirement of the problem names. They cut the integers
+ * that are NOT dictionary values into m+1 regions R0 = (-inf,t0), Ri = (t[i-1],t[i]), Rm = (t[m-1],+inf); region Ri is bit
+ * region_shift+i of the key's 64-bit value word, right above the real dictionary values. A complement requirement with bounds
+ * {excluded E, >gt, <lt} (requirement.go:36-42) is handed over as complement=1 with
+ *     values = E  |  every real dictionary value outside (gt,lt) (non-integers included)  |  every region outside (gt,lt)
+ * and the HASGT/HASLT meta bits clear. Then Intersection's max(gt)/min(lt)/"drop members outside the bounds"
+ * (requirement.go:120-143) is the plain union / and-not of the masks, "gt >= lt -> DoesNotExist" (:124-126) is "all regions
+ * excluded", Has(v) is the bit test, and the excluded set proper (for Operator(), :186-197) is
+ * values & above[low] & below[high] with low / high the number of excluded regions at either end.
+ * A key also gets region bits (m = 0: one region) when some instance type carries a complement requirement on it
+ * (NotIn / Exists / Gt / Lt): the region bits are what a complement node requirement and a complement type have in common.
+ * Keys with neither have region_mask 0 and nothing changes for them.
+ */
+#define KSCHED_MAX_THRESHOLDS 7
+typedef struct ksched_key_regions {
+  uint64_t region_mask;  /* n_thresholds+1 contiguous bits, or 0 */
+  int32_t region_shift;  /* bit of R0 */
+  int32_t n_thresholds;
+  int64_t thresholds[KSCHED_MAX_THRESHOLDS];   /* ascending */
+  uint64_t above[KSCHED_MAX_THRESHOLDS + 1];   /* above[i]: real values admitted when the i lowest regions are excluded (above[0] = all) */
+  uint64_t below[KSCHED_MAX_THRESHOLDS + 1];   /* below[j]: ... when the j highest regions are excluded (below[0] = all) */
+} ksched_key_regions;
 
 /*
  * 256-byte pod-class row. One row per class of pods that are indistinguishable to the scheduler
@@ -121,13 +148,14 @@ typedef struct ksched_keyinfo {
 
 typedef struct ksched_catalog {
   int32_t n_keys, n_res, n_types, n_templates;
-  const ksched_keyinfo* keys;      /* [n_keys] */
+  const ksched_keyinfo* keys;      /* [n_keys]; dict_mask = the REAL values (region bits are added by the library) */
+  const ksched_key_regions* key_regions; /* [n_keys] or NULL (no key has region bits) */
   const int64_t* key_int_values;   /* [n_keys][64] integer value of dictionary entry, where int_mask set; may be NULL */
   const ksched_type_row* types;    /* [n_types], price order */
-  const ksched_bounds* type_bounds; /* [n_types] or NULL */
+  const ksched_bounds* type_bounds; /* must be NULL: bounded requirements arrive in region form */
   const int64_t* type_capacity;    /* [n_types][KSCHED_MAX_RES] Capacity (limits bookkeeping, scheduler.go:273-309) */
   const ksched_template* templates; /* [n_templates], weight order (v1alpha5/provisioner.go:132) */
-  const ksched_bounds* template_bounds; /* [n_templates] or NULL */
+  const ksched_bounds* template_bounds; /* must be NULL (region form) */
   /* Launch choice (the step after the path: fake/cloudprovider.go:74-84 orders the surviving options by their cheapest
      compatible offering, cloudprovider/types.go:128-145 picks that offering). [n_types][64], slot = ct*16 + zone:
      (rank of the offering's price among all distinct prices of the catalog) << 16 | position in the type's Offerings
@@ -174,12 +202,12 @@ typedef struct ksched_class_topo {
 typedef struct ksched_problem {
   int32_t n_pods, n_classes, n_existing, n_groups;
   const ksched_pod_row* classes;     /* [n_classes] */
-  const ksched_bounds* class_bounds; /* [n_classes] or NULL */
+  const ksched_bounds* class_bounds; /* must be NULL (region form) */
   const uint32_t* pod_class;         /* [n_pods] initial class of every pod, caller order */
   const int64_t* pod_timestamp;      /* [n_pods] creationTimestamp seconds (queue.go:100) */
   const uint32_t* pod_uid_rank;      /* [n_pods] rank of the pod's UID in ascending string order (queue.go:108) */
   const ksched_existing_node* existing; /* [n_existing], caller order */
-  const ksched_bounds* existing_bounds; /* or NULL */
+  const ksched_bounds* existing_bounds; /* must be NULL (region form) */
   const ksched_topo_group* groups;   /* [n_groups] */
   const int32_t* group_domain_counts; /* [n_groups][64] initial per-domain counts of mask-key groups (countDomains) */
   const int32_t* group_existing_counts; /* [n_groups][n_existing] initial counts of hostname groups per existing node */

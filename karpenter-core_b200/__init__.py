@@ -393,7 +393,8 @@ class ResidentSolve:
         arr, n = _cand_array(list(candidates))
         self.enc = lib().kh_encode(problem.ptr, arr, n)
         if not self.enc:
-            raise KschedError(KSCHED_ERR_INVALID, lib().kh_scheduler_error().decode())
+            msg = lib().kh_scheduler_error().decode()
+            raise KschedError(KSCHED_ERR_UNSUPPORTED if msg.startswith("unsupported:") else KSCHED_ERR_INVALID, msg)
         d = (C.c_longlong * 10)()
         lib().kh_encoded_dims(self.enc, d)
         self.dims = dict(zip(["pods", "classes", "existing", "groups", "types", "templates", "keys", "resources", "type_words", "class_topo"], list(d)))

@@ -10,6 +10,7 @@ struct DevCatalog {
   int n_keys, n_res, n_types, n_templates, W32;
   const ksched_keyinfo* keys;        // [n_keys]
   const int64_t* key_int_values;     // [n_keys][64]
+  const ksched_key_regions* key_regions;  // [n_keys] or nullptr: region form of Gt/Lt (ksched.h); keys[k].dict_mask includes the region bits
   const ksched_template* templates;  // [n_templates]
   const ksched_type_row* types;      // [n_types]
   const int64_t* capacity;           // [n_types][8]
@@ -39,7 +40,7 @@ struct DevCatalog {
 };
 
 __device__ __forceinline__ KeyMeta key_meta(const DevCatalog& c, int k) {
-  return KeyMeta{c.keys[k].int_mask, c.key_int_values ? c.key_int_values + (size_t)k * 64 : nullptr};
+  return KeyMeta{c.keys[k].int_mask, c.key_int_values ? c.key_int_values + (size_t)k * 64 : nullptr, c.key_regions ? c.key_regions + k : nullptr};
 }
 
 // number of types with alloc_r < q  (lower bound)

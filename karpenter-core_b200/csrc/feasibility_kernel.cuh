@@ -91,7 +91,7 @@ __device__ __noinline__ unsigned long long k1_compute_row(int j, uint64_t word, 
         present = merged.present;
         if (present) {
           allowed = ksched::req_allowed(merged, c.keys[k].dict_mask, km);
-          neg = ksched::req_op_negative(merged);
+          neg = ksched::req_op_negative(merged, km);
         }
       }
       ok = ok && (__ballot_sync(0xffffffffu, !compat) == 0);

@@ -154,6 +154,7 @@ struct ksched_handle {
   int W64 = 0;
   DevBuf<ksched_keyinfo> d_keys;
   DevBuf<int64_t> d_key_int, d_capacity, d_alloc_sorted;
+  DevBuf<ksched_key_regions> d_key_regions;
   DevBuf<ksched_template> d_templates;
   DevBuf<ksched_type_row> d_types;
   DevBuf<float> d_price32;
@@ -279,15 +280,20 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   if (!h || !cat) return KSCHED_ERR_INVALID;
   if (cat->n_keys > KSCHED_MAX_KEYS || cat->n_res > KSCHED_MAX_RES || cat->n_templates > KSCHED_MAX_TEMPLATES || cat->n_templates < 1 ||
       cat->n_types < 0) { h->err = "catalog dimensions out of range"; return KSCHED_ERR_INVALID; }
-  if (cat->type_bounds) { h->err = "instance types with Gt/Lt requirements are not supported"; return KSCHED_ERR_UNSUPPORTED; }
-  // device code carries no Gt/Lt bounds at all (reqmask.cuh compiles them out): refuse any requirement set that has one
+  // Gt/Lt cross the ABI in region form (ksched_key_regions): a requirement set that still carries gt / lt is a caller bug
+  if (cat->type_bounds || cat->template_bounds) { h->err = "bounds arrays must be NULL: Gt/Lt requirements are passed in region form (ksched_key_regions)"; return KSCHED_ERR_INVALID; }
   for (int v = 0; v < cat->n_templates; ++v)
-    if (cat->template_bounds || (cat->templates[v].reqs.meta >> KSCHED_META_HASGT_SHIFT)) {
-      h->err = "provisioners with Gt/Lt requirements are not supported on the device path";
-      return KSCHED_ERR_UNSUPPORTED;
-    }
+    if (cat->templates[v].reqs.meta >> KSCHED_META_HASGT_SHIFT) { h->err = "template requirement with HASGT/HASLT set: pass Gt/Lt in region form"; return KSCHED_ERR_INVALID; }
   for (int t = 0; t < cat->n_types; ++t)
-    if (cat->types[t].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "instance types with Gt/Lt requirements are not supported"; return KSCHED_ERR_UNSUPPORTED; }
+    if (cat->types[t].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "instance-type requirement with HASGT/HASLT set: pass Gt/Lt in region form"; return KSCHED_ERR_INVALID; }
+  if (cat->key_regions)
+    for (int k = 0; k < cat->n_keys; ++k) {
+      const ksched_key_regions& g = cat->key_regions[k];
+      if (!g.region_mask) continue;
+      const uint64_t want = (g.n_thresholds + 1 >= 64 ? ~0ull : ((1ull << (g.n_thresholds + 1)) - 1)) << g.region_shift;
+      if (g.n_thresholds < 0 || g.n_thresholds > KSCHED_MAX_THRESHOLDS || g.region_shift < 0 || g.region_shift + g.n_thresholds + 1 > 63 ||
+          g.region_mask != want || (g.region_mask & cat->keys[k].dict_mask)) { h->err = "inconsistent ksched_key_regions"; return KSCHED_ERR_INVALID; }
+    }
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int T = cat->n_types, NK = cat->n_keys, V = cat->n_templates, R = cat->n_res;
   const int W64 = type_words64(T), W32 = W64 * 2;
@@ -299,8 +305,9 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
     int dims[4] = {NK, R, T, V};
     put(dims, sizeof dims);
     put(cat->keys, sizeof(ksched_keyinfo) * (size_t)NK);
-    unsigned char has_int = cat->key_int_values != nullptr, has_off = cat->offering_keys != nullptr;
-    put(&has_int, 1); put(&has_off, 1);
+    unsigned char has_int = cat->key_int_values != nullptr, has_off = cat->offering_keys != nullptr, has_reg = cat->key_regions != nullptr;
+    put(&has_int, 1); put(&has_off, 1); put(&has_reg, 1);
+    if (has_reg) put(cat->key_regions, sizeof(ksched_key_regions) * (size_t)NK);
     if (has_int) put(cat->key_int_values, sizeof(int64_t) * (size_t)NK * 64);
     put(cat->types, sizeof(ksched_type_row) * (size_t)T);
     put(cat->type_capacity, sizeof(int64_t) * (size_t)T * KSCHED_MAX_RES);
@@ -336,16 +343,20 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
     price32[t] = (float)row.min_price;
     const int w = t >> 5;
     const uint32_t bit = 1u << (t & 31);
-    if ((row.meta >> KSCHED_META_COMPLEMENT_SHIFT) & 0xFFFF || (row.meta >> KSCHED_META_HASGT_SHIFT)) {
-      h->err = "instance types with complement / bounded requirements are not supported";
-      return KSCHED_ERR_UNSUPPORTED;
-    }
     for (int k = 0; k < NK; ++k) {
       bool present = (row.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1;
       if (!present) { absent[(size_t)k * W32 + w] |= bit; continue; }
       type_relevant |= 1u << k;
       uint64_t v = row.values[k];
-      if (!v) { negempty[(size_t)k * W32 + w] |= bit; continue; }
+      if ((row.meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1) {
+        // complement requirement (NotIn / Exists / Gt / Lt, region form): the type admits every value and region it does not
+        // exclude; its operator is negative (NotIn) when it really excludes a value (requirement.go:186-197)
+        const uint64_t region_mask = cat->key_regions ? cat->key_regions[k].region_mask : 0;
+        if (!region_mask) { h->err = "instance type with a complement requirement on a key without region bits"; return KSCHED_ERR_INVALID; }
+        ksched::Req r{v, 0, 0, true, true, false, false};
+        if (ksched::req_excluded(r, KeyMeta{0, nullptr, cat->key_regions + k}) != 0) negempty[(size_t)k * W32 + w] |= bit;
+        v = ~v & (cat->keys[k].dict_mask | region_mask);
+      } else if (!v) { negempty[(size_t)k * W32 + w] |= bit; continue; }
       while (v) {
         int b = __builtin_ctzll(v);
         v &= v - 1;
@@ -389,7 +400,15 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
       }
     }
   }
-  CUDA_TRY(h, upload(h, h->d_keys, cat->keys, (size_t)NK));
+  {
+    // the device's dict_mask includes the region bits: "every admissible value" of a complement requirement then covers the
+    // regions a complement instance type shares with it (catalog.cuh: key_typeset_word walks the admitted bits)
+    std::vector<ksched_keyinfo> dev_keys(cat->keys, cat->keys + NK);
+    if (cat->key_regions) for (int k = 0; k < NK; ++k) dev_keys[k].dict_mask |= cat->key_regions[k].region_mask;
+    CUDA_TRY(h, upload_vec(h, h->d_keys, dev_keys));
+    if (cat->key_regions) CUDA_TRY(h, upload(h, h->d_key_regions, cat->key_regions, (size_t)NK));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // dev_keys is a stack vector
+  }
   if (cat->key_int_values) CUDA_TRY(h, upload(h, h->d_key_int, cat->key_int_values, (size_t)NK * 64));
   CUDA_TRY(h, upload(h, h->d_templates, cat->templates, (size_t)V));
   CUDA_TRY(h, upload(h, h->d_types, cat->types, (size_t)T));
@@ -428,6 +447,7 @@ int ksched_load_catalog(ksched_handle* h, const ksched_catalog* cat) {
   c.n_keys = NK; c.n_res = R; c.n_types = T; c.n_templates = V; c.W32 = W32;
   c.keys = h->d_keys.ptr;
   c.key_int_values = cat->key_int_values ? h->d_key_int.ptr : nullptr;
+  c.key_regions = cat->key_regions ? h->d_key_regions.ptr : nullptr;
   c.templates = h->d_templates.ptr;
   c.types = h->d_types.ptr;
   c.capacity = h->d_capacity.ptr;
@@ -545,13 +565,13 @@ int ksched_nccl_init(ksched_handle* h, const void* id128, int rank, int world) {
 int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   if (!h || !pb) return KSCHED_ERR_INVALID;
   if (!h->have_catalog) { h->err = "ksched_load_catalog must be called first"; return KSCHED_ERR_INVALID; }
-  if (pb->class_bounds || pb->existing_bounds) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+  if (pb->class_bounds || pb->existing_bounds) { h->err = "bounds arrays must be NULL: Gt/Lt requirements are passed in region form (ksched_key_regions)"; return KSCHED_ERR_INVALID; }
   for (int i = 0; i < pb->n_classes; ++i)
-    if (pb->classes[i].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+    if (pb->classes[i].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "requirement with HASGT/HASLT set: pass Gt/Lt in region form"; return KSCHED_ERR_INVALID; }
   for (int i = 0; i < pb->n_existing; ++i)
-    if (pb->existing[i].reqs.meta >> KSCHED_META_HASGT_SHIFT) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+    if (pb->existing[i].reqs.meta >> KSCHED_META_HASGT_SHIFT) { h->err = "requirement with HASGT/HASLT set: pass Gt/Lt in region form"; return KSCHED_ERR_INVALID; }
   for (int i = 0; i < pb->n_filter_terms; ++i)
-    if (pb->filter_terms[i].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "Gt/Lt requirements are not carried on the device path yet"; return KSCHED_ERR_UNSUPPORTED; }
+    if (pb->filter_terms[i].meta >> KSCHED_META_HASGT_SHIFT) { h->err = "requirement with HASGT/HASLT set: pass Gt/Lt in region form"; return KSCHED_ERR_INVALID; }
   CUDA_TRY(h, cudaSetDevice(h->device));
   h->tm.h2d_bytes = 0;
   const DevCatalog& c = h->cat;

@@ -26,6 +26,10 @@ struct Req {
 struct KeyMeta {
   uint64_t int_mask;          // dictionary entries that parse as integers
   const int64_t* int_values;  // [64] or nullptr when the key has no integer entries / no bounds in play
+  // Region form of Gt/Lt (what the DEVICE carries instead of gt / lt, see ksched_key_regions in ksched.h): a bounded
+  // complement requirement excludes the region bits outside (gt, lt) and the dictionary values outside it. nullptr: the
+  // key has no region bits (host algebra, and every key without thresholds / complement instance types).
+  const ksched_key_regions* regions;
 };
 
 KS_HD int popc64(uint64_t x) {
@@ -72,7 +76,7 @@ KS_HD void req_store(ksched_reqset& s, ksched_bounds* b, int k, const Req& r) {
 // dictionary entries inside (gt, lt): withinIntPtrs (requirement.go:227-243) as a mask
 KS_HD uint64_t within_mask(bool has_gt, int64_t gt, bool has_lt, int64_t lt, const KeyMeta& km) {
 #if defined(__CUDA_ARCH__)
-  // Device code never sees Gt/Lt: ksched_load_catalog / ksched_upload refuse every requirement set that carries a bound.
+  // Device code never sees gt / lt: the encoder hands every bounded requirement over in region form (ksched_key_regions).
   return ~0ull;
 #endif
   if (!has_gt && !has_lt) return ~0ull;
@@ -95,25 +99,89 @@ KS_HD uint64_t within_mask(bool has_gt, int64_t gt, bool has_lt, int64_t lt, con
 
 // Requirement.Len() == 0 (requirement.go:199-204): complement sets are never empty
 KS_HD bool req_len_zero(const Req& r) { return !r.complement && r.values == 0; }
-// Operator() in {NotIn, DoesNotExist} (requirement.go:186-197)
-KS_HD bool req_op_negative(const Req& r) { return r.complement ? (r.values != 0) : (r.values == 0); }
+
+// ---- region form (ksched_key_regions): number of excluded regions at the low / high end of a complement requirement
+KS_HD int region_low(uint64_t values, const ksched_key_regions& g) {
+  const uint64_t f = (values & g.region_mask) >> g.region_shift;
+  int n = 0;
+  while (n <= g.n_thresholds && ((f >> n) & 1)) ++n;
+  return n;
+}
+KS_HD int region_high(uint64_t values, const ksched_key_regions& g) {
+  const uint64_t f = (values & g.region_mask) >> g.region_shift;
+  int n = 0;
+  while (n <= g.n_thresholds && ((f >> (g.n_thresholds - n)) & 1)) ++n;
+  return n;
+}
+// The values a complement requirement really excludes (Requirement.values of requirement.go:36-42; Intersection keeps only
+// excluded values inside the bounds, :139-143): in region form `values` also holds everything the bounds cut away.
+KS_HD uint64_t req_excluded(const Req& r, const KeyMeta& km) {
+  if (!km.regions || !km.regions->region_mask) return r.values;
+  const ksched_key_regions& g = *km.regions;
+  return r.values & ~g.region_mask & g.above[region_low(r.values, g)] & g.below[region_high(r.values, g)];
+}
+// Operator() in {NotIn, DoesNotExist} (requirement.go:186-197); a complement set with bounds but no excluded value is Exists
+KS_HD bool req_op_negative(const Req& r, const KeyMeta& km) { return r.complement ? (req_excluded(r, km) != 0) : (r.values == 0); }
 // Len() == 1
 KS_HD bool req_len_one(const Req& r) { return !r.complement && popc64(r.values) == 1; }
 
-// Requirement.Intersection (requirement.go:117-150)
-KS_HD Req req_intersect(const Req& a, const Req& b, const KeyMeta& km) {
+// Host algebra -> region form for one requirement (the conversion the encoder applies at the C-ABI boundary). Returns false
+// when a bound is not one of the key's thresholds.
+inline bool req_to_region_form(const Req& r, const ksched_key_regions& g, uint64_t dict_mask, Req* out) {
+  *out = r;
+  if (!r.present || (!r.has_gt && !r.has_lt)) return true;
+  const int m = g.n_thresholds;
+  int low = 0, high = 0;
+  if (r.has_gt) { int i = 0; while (i < m && g.thresholds[i] != r.gt) ++i; if (i == m) return false; low = i + 1; }
+  if (r.has_lt) { int i = 0; while (i < m && g.thresholds[i] != r.lt) ++i; if (i == m) return false; high = m - i; }
+  uint64_t v = r.values;
+  for (int i = 0; i < low; ++i) v |= 1ull << (g.region_shift + i);
+  for (int i = 0; i < high; ++i) v |= 1ull << (g.region_shift + m - i);
+  v |= dict_mask & ~(g.above[low] & g.below[high]);
+  *out = Req{v, 0, 0, true, true, false, false};
+  return true;
+}
+// Fill a key's region tables from its thresholds (ascending, distinct) and its integer dictionary entries.
+inline void regions_build(ksched_key_regions* g, const int64_t* thresholds, int m, int n_dict_values, uint64_t dict_mask, const KeyMeta& km) {
+  *g = ksched_key_regions{};
+  g->region_shift = n_dict_values;
+  g->n_thresholds = m;
+  g->region_mask = ((1ull << (m + 1)) - 1) << n_dict_values;
+  for (int i = 0; i < m; ++i) g->thresholds[i] = thresholds[i];
+  for (int q = 0; q <= m; ++q) {
+    g->above[q] = q == 0 ? dict_mask : within_mask(true, g->thresholds[q - 1], false, 0, km) & dict_mask;
+    g->below[q] = q == 0 ? dict_mask : within_mask(false, 0, true, g->thresholds[m - q], km) & dict_mask;
+  }
+}
+
+// Requirement.Intersection (requirement.go:117-150) in REGION form: the bounds are excluded region bits, so max(gt) / min(lt) /
+// "drop members outside the bounds" are one OR / AND-NOT. This is the device's algebra; the host keeps {values, gt, lt} and the
+// encoder converts at the boundary (tests/test_region_form.py checks that the two commute).
+KS_HD Req req_intersect_regions(const Req& a, const Req& b, const KeyMeta& km) {
   Req r;
   r.present = true;
   r.complement = a.complement && b.complement;
-#if defined(__CUDA_ARCH__)
   r.has_gt = r.has_lt = false;
   r.gt = r.lt = 0;
-  if (a.complement && b.complement) r.values = a.values | b.values;
+  if (a.complement && b.complement) {
+    r.values = a.values | b.values;
+    // greaterThan >= lessThan -> DoesNotExist (requirement.go:124-126): no region is left between the bounds
+    if (km.regions && km.regions->region_mask && (r.values & km.regions->region_mask) == km.regions->region_mask) { r.complement = false; r.values = 0; }
+  }
   else if (a.complement && !b.complement) r.values = b.values & ~a.values;
   else if (!a.complement && b.complement) r.values = a.values & ~b.values;
   else r.values = a.values & b.values;
   return r;
+}
+
+// Requirement.Intersection (requirement.go:117-150)
+KS_HD Req req_intersect(const Req& a, const Req& b, const KeyMeta& km) {
+#if defined(__CUDA_ARCH__)
+  return req_intersect_regions(a, b, km);
 #endif
+  Req r;
+  r.present = true;
+  r.complement = a.complement && b.complement;
   r.has_gt = a.has_gt || b.has_gt;
   r.has_lt = a.has_lt || b.has_lt;
   r.gt = a.has_gt ? (b.has_gt ? (a.gt > b.gt ? a.gt : b.gt) : a.gt) : b.gt;
@@ -142,12 +210,12 @@ KS_HD bool key_intersects(const Req& existing, const Req& incoming, const KeyMet
   if (!existing.present || !incoming.present) return true;
   Req i = req_intersect(existing, incoming, km);
   if (!req_len_zero(i)) return true;
-  return req_op_negative(incoming) && req_op_negative(existing);
+  return req_op_negative(incoming, km) && req_op_negative(existing, km);
 }
 // One key of Requirements.Compatible (requirements.go:123-133), `node` is the receiver.
 KS_HD bool key_compatible(const Req& node, const Req& incoming, bool well_known, const KeyMeta& km) {
   if (!incoming.present) return true;
-  if (!well_known && !node.present && !req_op_negative(incoming)) return false;
+  if (!well_known && !node.present && !req_op_negative(incoming, km)) return false;
   return key_intersects(node, incoming, km);
 }
 // Requirements.Add for one key (requirements.go:87-94): incoming.Intersection(existing)

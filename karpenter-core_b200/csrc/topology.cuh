@@ -332,7 +332,7 @@ __device__ __noinline__ void build_type_ctx(const Touched& t, const long long* q
     KeyMeta km = key_meta(c, k);
     x.key[x.nkeys] = (int8_t)k;
     x.allowed[x.nkeys] = ksched::req_allowed(f, c.keys[k].dict_mask, km);
-    x.neg[x.nkeys] = ksched::req_op_negative(f);
+    x.neg[x.nkeys] = ksched::req_op_negative(f, km);
     ++x.nkeys;
   };
   if (fresh) {
@@ -590,7 +590,7 @@ __device__ __noinline__ void topo_record_entry(uint32_t e, const uint64_t* vals,
     if (!doit) continue;
     Req r = load_soa(vals, meta, stride, idx, x.key);
     uint64_t v = 0;
-    if (allv) v = r.present ? r.values : 0;  // domains.Values(): members, or the excluded set of a complement
+    if (allv) v = r.present ? (r.complement ? ksched::req_excluded(r, key_meta(c, x.key)) : r.values) : 0;  // domains.Values(): members, or the excluded set of a complement
     else if (r.present && ksched::req_len_one(r)) v = r.values;
     while (v) {
       int d = __ffsll((long long)v) - 1;

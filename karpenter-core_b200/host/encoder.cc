@@ -407,6 +407,20 @@ struct Builder {
     if (pod.has_required_node_affinity && !pod.required_node_terms.empty())
       add_selector_reqs(rs, b, pod.required_node_terms[0], sp);
   }
+  // Hand a requirement set over to the C-ABI: bounds become excluded regions + excluded out-of-range values (ksched.h:
+  // ksched_key_regions). Applied at the very end, after every host-side use of the exact {values, gt, lt} form.
+  void to_region_form(ksched_reqset& rs, const ksched_bounds& b) const {
+    if (!(rs.meta >> KSCHED_META_HASGT_SHIFT)) return;
+    for (int k = 0; k < (int)E.key_names.size(); ++k) {
+      Req r = ksched::req_load(rs, &b, k);
+      if (!r.present || (!r.has_gt && !r.has_lt)) continue;
+      if (E.key_regions.empty() || !E.key_regions[k].region_mask) throw std::runtime_error("internal: bounded requirement on a key without regions");
+      Req out;
+      if (!ksched::req_to_region_form(r, E.key_regions[k], E.keys[k].dict_mask, &out)) throw std::runtime_error("internal: bound that is not a threshold of its key");
+      ksched_bounds scratch{};
+      ksched::req_store(rs, &scratch, k, out);
+    }
+  }
   bool compatible(const ksched_reqset& node, const ksched_bounds& nb, const ksched_reqset& inc, const ksched_bounds& ib) const {
     for (int k = 0; k < (int)E.key_names.size(); ++k) {
       Req n = ksched::req_load(node, &nb, k), i = ksched::req_load(inc, &ib, k);
@@ -667,8 +681,43 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     ki.is_zone = E.key_names[k] == kZone;
     ki.is_capacity_type = E.key_names[k] == kCapacityType;
   }
-  for (int k = 0; k < NK; ++k) B.key_meta[k] = KeyMeta{E.keys[k].int_mask, &E.key_int_values[(size_t)k * 64]};
+  for (int k = 0; k < NK; ++k) B.key_meta[k] = KeyMeta{E.keys[k].int_mask, &E.key_int_values[(size_t)k * 64], nullptr};
   const int zone_key = B.key_of(kZone), ct_key = B.key_of(kCapacityType);
+  // Region form of Gt/Lt (ksched.h: ksched_key_regions). Every threshold any requirement of this problem names, per key; a
+  // key also gets one region when an instance type has a complement requirement on it.
+  {
+    std::vector<std::set<int64_t>> thr(NK);
+    std::vector<bool> type_complement(NK, false);
+    auto note_thr = [&](const std::vector<NodeSelectorRequirement>& rs, bool is_type) {
+      for (auto& r : rs) {
+        int k = B.key_of(r.key);
+        if (k < 0) continue;
+        if (r.op == Op::Gt || r.op == Op::Lt) { int64_t v = 0; if (!r.values.empty()) parse_int(r.values[0], &v); thr[k].insert(v); }
+        if (is_type && r.op != Op::In && r.op != Op::DoesNotExist) type_complement[k] = true;
+      }
+    };
+    auto note_pod_thr = [&](const Pod& p) {
+      for (auto& t : p.required_node_terms) note_thr(t, false);
+      for (auto& t : p.preferred_node_terms) note_thr(t.preference, false);
+    };
+    for (auto& sp : specs) note_pod_thr(sp.pod);
+    for (auto& d : daemons) note_pod_thr(d);
+    for (auto& it : P.instance_types) note_thr(it.requirements, true);
+    for (auto& pr : P.provisioners) note_thr(pr.requirements, false);
+    bool any = false;
+    for (int k = 0; k < NK; ++k) any = any || !thr[k].empty() || type_complement[k];
+    if (any) {
+      E.key_regions.assign(NK, ksched_key_regions{});
+      for (int k = 0; k < NK; ++k) {
+        if (thr[k].empty() && !type_complement[k]) continue;
+        const int m = (int)thr[k].size(), nd = (int)E.key_values[k].size();
+        if (m > KSCHED_MAX_THRESHOLDS) unsupported("label key " + E.key_names[k] + " has more than 7 distinct Gt/Lt thresholds");
+        if (nd + m + 1 > 63) unsupported("label key " + E.key_names[k] + " has too many values for its Gt/Lt regions");
+        std::vector<int64_t> ts(thr[k].begin(), thr[k].end());
+        ksched::regions_build(&E.key_regions[k], ts.data(), m, nd, E.keys[k].dict_mask, B.key_meta[k]);
+      }
+    }
+  }
 
   phase("keys + dictionary");
   // ------------------------------------------------------------------ resources
@@ -726,10 +775,9 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
         }
         int k = B.key_of(key);
         if (k < 0) continue;
-        if (r.op == Op::Gt || r.op == Op::Lt || r.op == Op::NotIn || r.op == Op::Exists)
-          unsupported("instance type " + it.name + " has a complement / bounded requirement on " + key);
         B.add_req(rs, bd, k, B.encode_req(k, r.op, r.values));
       }
+      B.to_region_form(rs, bd);
       std::memcpy(row.values, rs.values, sizeof row.values);
       row.meta = rs.meta;
       ResourceList overhead = merge(merge(it.kube_reserved, it.system_reserved), it.eviction_threshold);
@@ -1082,8 +1130,9 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     o.max_skew = G.max_skew;
     o.filter_begin = (uint32_t)E.filter_terms.size();
     for (auto& f : G.filter) {
-      if (f.first.meta >> KSCHED_META_HASGT_SHIFT) unsupported("Gt/Lt inside a topology node filter");
-      E.filter_terms.push_back(f.first);
+      ksched_reqset term = f.first;
+      B.to_region_form(term, f.second);
+      E.filter_terms.push_back(term);
     }
     o.filter_end = (uint32_t)E.filter_terms.size();
     if (G.key == kHostname) {
@@ -1237,12 +1286,12 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   cat.type_bounds = nullptr;
   cat.type_capacity = E.type_capacity.data();
   cat.templates = E.templates.data();
-  cat.template_bounds = E.any_template_bounds ? E.template_bounds.data() : nullptr;
+  cat.template_bounds = nullptr;
   cat.offering_keys = E.offering_keys.data();
   ksched_problem& pr = E.problem;
   pr.n_pods = (int)NP; pr.n_classes = NC; pr.n_existing = NE; pr.n_groups = NG;
   pr.classes = E.classes.data();
-  pr.class_bounds = E.any_class_bounds ? E.class_bounds.data() : nullptr;
+  pr.class_bounds = nullptr;
   pr.pod_class = E.pod_class.data();
   pr.pod_timestamp = E.pod_timestamp.data();
   pr.pod_uid_rank = E.pod_uid_rank.data();
@@ -1263,14 +1312,32 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   pr.max_new_nodes = (int)NP;
   pr.write_feasibility = 0;
   pr.count_nodes_visited = 0;  // the exact nodes_visited statistic is opt-in (kh_set_count_visited / tests): it turns the pack kernel's steady-state paths off
-  if (E.any_class_bounds || E.any_template_bounds)
-    unsupported("Gt/Lt requirements on pods / provisioners are not carried on the device path yet");
+  // Gt/Lt leave the host algebra here: templates and pod classes in region form (types and filter terms already are)
+  for (int v = 0; v < NV; ++v) B.to_region_form(E.templates[v].reqs, tb[v]);
+  for (int c = 0; c < NC; ++c) {
+    ksched_reqset rs{};
+    std::memcpy(rs.values, E.classes[c].values, sizeof rs.values);
+    rs.meta = E.classes[c].meta;
+    B.to_region_form(rs, E.class_bounds[c]);
+    std::memcpy(E.classes[c].values, rs.values, sizeof rs.values);
+    E.classes[c].meta = rs.meta;
+  }
+  cat.key_regions = E.key_regions.empty() ? nullptr : E.key_regions.data();
   return enc;
 }
 
 std::string render_requirement(const Encoded& E, const ksched_reqset& rs, int k) {
   static const ksched_bounds zero{};
   Req r = ksched::req_load(rs, &zero, k);
+  // results come back in region form (ksched.h: ksched_key_regions): recover the excluded set proper and the bounds
+  std::string bounds;
+  if (r.complement && !E.key_regions.empty() && E.key_regions[k].region_mask) {
+    const ksched_key_regions& g = E.key_regions[k];
+    const int low = ksched::region_low(r.values, g), high = ksched::region_high(r.values, g);
+    r.values = ksched::req_excluded(r, KeyMeta{0, nullptr, &g});
+    if (low > 0) bounds += " >" + std::to_string(g.thresholds[low - 1]);
+    if (high > 0) bounds += " <" + std::to_string(g.thresholds[g.n_thresholds - high]);
+  }
   const char* op;
   if (r.complement) op = r.values ? "NotIn" : "Exists";
   else op = r.values ? "In" : "DoesNotExist";
@@ -1278,7 +1345,7 @@ std::string render_requirement(const Encoded& E, const ksched_reqset& rs, int k)
   bool first = true;
   for (size_t b = 0; b < E.key_values[k].size(); ++b)
     if ((r.values >> b) & 1) { if (!first) s += " "; s += E.key_values[k][b]; first = false; }
-  return s + "]";
+  return s + "]" + bounds;
 }
 
 }  // namespace khost

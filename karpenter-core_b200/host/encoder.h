@@ -29,6 +29,7 @@ struct Encoded {
   // ---- backing storage of the flat structures
   std::vector<ksched_keyinfo> keys;
   std::vector<int64_t> key_int_values;
+  std::vector<ksched_key_regions> key_regions;        // [n_keys] or empty: region form of Gt/Lt (ksched.h)
   std::vector<ksched_type_row> types;
   std::vector<int64_t> type_capacity;
   std::vector<uint64_t> offering_keys;                // [n_types][64] launch-choice table (ksched_catalog.offering_keys)

@@ -435,7 +435,7 @@ Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int 
       for (size_t b = 0; b < E->key_values[k].size(); ++b) if (E->key_values[k][b] == "spot") spot = 1ull << b;
       ksched::Req in{spot, 0, 0, true, false, false, false};
       static const ksched_bounds zero{};
-      ksched::KeyMeta km{0, nullptr};
+      ksched::KeyMeta km{0, nullptr, nullptr};
       ksched_bounds tmp{};
       ksched::req_store(reqs, &tmp, (int)k, ksched::key_add(ksched::req_load(reqs, &zero, (int)k), in, km));
     }
@@ -641,7 +641,9 @@ extern "C" unsigned long long kh_encoded_digest(const Encoded* E) {
   for (bool b : E->existing_initialized) { unsigned char c = b; bytes(&c, 1); }
   vec(E->template_provisioner); vec(E->type_input_index);
   bytes(&E->type_words, sizeof E->type_words);
-  vec(E->keys); vec(E->key_int_values); vec(E->types); vec(E->type_capacity); vec(E->offering_keys); vec(E->price_by_rank);
+  vec(E->keys); vec(E->key_int_values);
+  if (!E->key_regions.empty()) vec(E->key_regions);  // absent for problems without Gt/Lt: their digests predate the region form
+  vec(E->types); vec(E->type_capacity); vec(E->offering_keys); vec(E->price_by_rank);
   vec(E->templates); vec(E->template_bounds); vec(E->classes); vec(E->class_bounds);
   unsigned char flags[2] = {(unsigned char)E->any_class_bounds, (unsigned char)E->any_template_bounds};
   bytes(flags, 2);
@@ -681,7 +683,7 @@ static ksched::Req spec_req(const char* op_c, const char* vals_c, const std::vec
 struct TestDict {
   std::vector<std::string> dict{"1", "2", "9", "A", "B"};
   int64_t ints[64] = {1, 2, 9};
-  ksched::KeyMeta km{0x7, ints};
+  ksched::KeyMeta km{0x7, ints, nullptr};
 };
 // out: [present, complement, values, has_gt, gt, has_lt, lt, len_zero, op_negative]
 void kh_mask_intersection(const char* aop, const char* avals, const char* bop, const char* bvals, long long* out) {
@@ -689,7 +691,7 @@ void kh_mask_intersection(const char* aop, const char* avals, const char* bop, c
   ksched::Req a = spec_req(aop, avals, d.dict), b = spec_req(bop, bvals, d.dict);
   ksched::Req r = ksched::req_intersect(a, b, d.km);
   out[0] = r.present; out[1] = r.complement; out[2] = (long long)r.values; out[3] = r.has_gt; out[4] = r.gt; out[5] = r.has_lt; out[6] = r.lt;
-  out[7] = ksched::req_len_zero(r); out[8] = ksched::req_op_negative(r);
+  out[7] = ksched::req_len_zero(r); out[8] = ksched::req_op_negative(r, d.km);
 }
 long long kh_mask_allowed(const char* aop, const char* avals) {
   TestDict d;
@@ -701,5 +703,69 @@ int kh_mask_compatible(const char* aop, const char* avals, int a_present, const 
   a.present = a_present;
   b.present = b_present;
   return ksched::key_compatible(a, b, well_known != 0, d.km) ? 1 : 0;
+}
+
+// Region form of Gt/Lt (ksched.h: ksched_key_regions) against the host algebra: random requirements over a dictionary with
+// integer and non-integer values and random thresholds; for every pair the region-form results must equal the converted
+// host results (Intersection, Len()==0, Operator negativity, Has over the dictionary, the excluded set, Compatible).
+// Returns the number of mismatches.
+int kh_region_selftest(unsigned seed, int iters) {
+  uint64_t st = seed * 0x9E3779B97F4A7C15ull + 12345;
+  auto rnd = [&](int n) { st = st * 6364136223846793005ull + 1442695040888963407ull; return (int)((st >> 33) % (uint64_t)n); };
+  const int64_t pool[8] = {0, 1, 2, 3, 5, 7, 9, 10};
+  int bad = 0;
+  for (int it = 0; it < iters; ++it) {
+    // dictionary: bits 0..3 integers 1,2,5,9; bits 4,5 non-integers
+    int64_t ints[64] = {1, 2, 5, 9};
+    const uint64_t dict = 0x3F;
+    ksched::KeyMeta hk{0xF, ints, nullptr};
+    std::set<int64_t> tset;
+    const int m = rnd(5);
+    while ((int)tset.size() < m) tset.insert(pool[rnd(8)]);
+    std::vector<int64_t> ts(tset.begin(), tset.end());
+    ksched_key_regions g;
+    ksched::regions_build(&g, ts.data(), m, 6, dict, hk);
+    ksched::KeyMeta rk{0xF, ints, &g};
+    auto atom = [&]() {
+      ksched::Req r{0, 0, 0, true, true, false, false};
+      const int op = rnd(m > 0 ? 6 : 4);
+      if (op == 0) { r.complement = false; r.values = (uint64_t)rnd(64); }
+      else if (op == 1) { r.values = (uint64_t)rnd(64); }
+      else if (op == 2) {}
+      else if (op == 3) { r.complement = false; }
+      else if (op == 4) { r.has_gt = true; r.gt = ts[(size_t)rnd(m)]; }
+      else { r.has_lt = true; r.lt = ts[(size_t)rnd(m)]; }
+      return r;
+    };
+    auto compound = [&]() { ksched::Req r = atom(); for (int i = rnd(3); i > 0; --i) r = ksched::req_intersect(atom(), r, hk); return r; };
+    const ksched::Req a = compound(), b = compound();
+    ksched::Req ra, rb;
+    if (!ksched::req_to_region_form(a, g, dict, &ra) || !ksched::req_to_region_form(b, g, dict, &rb)) { ++bad; continue; }
+    const ksched::Req h = ksched::req_intersect(a, b, hk), r = ksched::req_intersect_regions(ra, rb, rk);
+    ksched::Req want;
+    if (!ksched::req_to_region_form(h, g, dict, &want)) { ++bad; continue; }
+    bool ok = want.complement == r.complement && want.values == r.values;
+    ok = ok && ksched::req_len_zero(h) == ksched::req_len_zero(r);
+    ok = ok && ksched::req_op_negative(h, hk) == ksched::req_op_negative(r, rk);
+    ok = ok && ksched::req_op_negative(a, hk) == ksched::req_op_negative(ra, rk);
+    ok = ok && ksched::req_allowed(h, dict, hk) == (ksched::req_allowed(r, dict | g.region_mask, rk) & dict);
+    if (h.complement) ok = ok && ksched::req_excluded(r, rk) == h.values;
+    for (int wk = 0; wk < 2; ++wk)
+      for (int pa = 0; pa < 2; ++pa) {
+        ksched::Req na = a, nra = ra;
+        na.present = nra.present = pa != 0;
+        ok = ok && ksched::key_compatible(na, b, wk != 0, hk) ==
+                       [&] {  // key_compatible with the region-form intersection (what the device compiles)
+                         if (!rb.present) return true;
+                         if (!wk && !nra.present && !ksched::req_op_negative(rb, rk)) return false;
+                         if (!nra.present) return true;
+                         ksched::Req i = ksched::req_intersect_regions(nra, rb, rk);
+                         if (!ksched::req_len_zero(i)) return true;
+                         return ksched::req_op_negative(rb, rk) && ksched::req_op_negative(nra, rk);
+                       }();
+      }
+    if (!ok) ++bad;
+  }
+  return bad;
 }
 }

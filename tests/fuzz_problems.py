@@ -109,3 +109,54 @@ def random_problem(seed):
         daemons.append({"name": "ds", "uid": "ds", "requests": {"cpu": "100m", "memory": "64Mi"},
                         "tolerations": [{"operator": "Exists"}] if rng.random() < 0.5 else []})
     return fx.problem(pods, instance_types=its, provisioners=provisioners, nodes=nodes, daemonSetPods=daemons)
+
+
+def random_problem_with_bounds(seed):
+    """random_problem(seed) plus the requirement forms the device carries in region form (include/ksched.h: ksched_key_regions):
+    Gt / Lt on provisioners and pods (node affinity, required and preferred), NotIn / Exists / DoesNotExist / Gt / Lt requirements
+    on instance types. A separate random stream, so random_problem's corpus stays what it was."""
+    prob = random_problem(seed)
+    rng = random.Random(seed * 7919 + 13)
+    its = prob["instanceTypes"]
+    ints = sorted({int(r["values"][0]) for it in its for r in it["requirements"] if r["key"] == "integer"})
+    thresholds = [str(rng.choice(ints) + rng.choice([-1, 0, 0, 1])) for _ in range(rng.choice([1, 2, 3]))] if ints else ["1"]
+    def bound():
+        return {"key": "integer", "operator": rng.choice(["Gt", "Lt"]), "values": [rng.choice(thresholds)]}
+    for pr in prob["provisioners"]:
+        if rng.random() < 0.5:
+            pr.setdefault("requirements", []).append(bound())
+        if rng.random() < 0.15:
+            pr.setdefault("requirements", []).append({"key": "integer", "operator": "NotIn", "values": [str(rng.choice(ints or [1]))]})
+    for p in prob["pods"]:
+        r = rng.random()
+        if r < 0.25:
+            term = [bound()] + ([bound()] if rng.random() < 0.3 else [])
+            na = p.setdefault("nodeAffinity", {})
+            if "required" in na:
+                for t in na["required"]:
+                    t.extend(term)
+            else:
+                na["required"] = [term]
+        elif r < 0.35:
+            p.setdefault("nodeAffinity", {}).setdefault("preferred", []).append({"weight": rng.choice([1, 70]), "terms": [bound()]})
+        elif r < 0.42:
+            p.setdefault("nodeAffinity", {}).setdefault("required", [[]])[0].append(
+                {"key": "tier", "operator": rng.choice(["In", "NotIn", "Exists", "DoesNotExist"]), "values": [rng.choice(["gold", "silver"])]})
+    for it in its:
+        r = rng.random()
+        if r < 0.10:
+            it["requirements"].append({"key": "tier", "operator": "NotIn", "values": [rng.choice(["gold", "silver"])]})
+        elif r < 0.18:
+            it["requirements"].append({"key": "tier", "operator": "Exists", "values": []})
+        elif r < 0.26:
+            it["requirements"].append({"key": "tier", "operator": "In", "values": [rng.choice(["gold", "silver"])]})
+        elif r < 0.30:
+            it["requirements"].append({"key": "tier", "operator": "DoesNotExist", "values": []})
+        elif r < 0.34:
+            it["requirements"] = [q for q in it["requirements"] if q["key"] != "integer"] + [bound()]
+    for t in [q for p in prob["pods"] for q in p.get("nodeAffinity", {}).get("required", [])]:
+        for q in t:
+            if q["operator"] in ("Exists", "DoesNotExist"):
+                q["values"] = []
+    prob["wellKnownLabels"] = list(prob["wellKnownLabels"]) + (["tier"] if rng.random() < 0.5 else [])
+    return prob

@@ -1394,3 +1394,86 @@ def self_zone_affinity_prefers_the_in_flight_nodes_domain():
         for res in results:
             assert res["assign"] == [0] and res["newNodes"] == []
     return {"multi": [for_zone[z] for z in ZONES]}, check
+
+
+# ------------------------------------------------------------------ Gt / Lt requirements (scheduling/suite_test.go:213-230) and complement
+# requirements on instance types: carried on the device in region form (include/ksched.h: ksched_key_regions)
+def _launched_integer(prob, res, pod_index=0):
+    it = next(i for i in prob["instanceTypes"] if i["name"] == launched_type(prob, res, pod_index))
+    return next(r["values"][0] for r in it["requirements"] if r["key"] == "integer")
+
+
+@cpu_case("suite_test.go:213-221")
+def provisioner_requirement_gt():
+    prob = problem([pod()], provisioners=[provisioner(requirements=[{"key": "integer", "operator": "Gt", "values": ["8"]}])])
+
+    def check(res):
+        assert scheduled(res, 0)
+        assert _launched_integer(prob, res) == "16"
+    return prob, check
+
+
+@cpu_case("suite_test.go:222-230")
+def provisioner_requirement_lt():
+    prob = problem([pod()], provisioners=[provisioner(requirements=[{"key": "integer", "operator": "Lt", "values": ["8"]}])])
+
+    def check(res):
+        assert scheduled(res, 0)
+        assert _launched_integer(prob, res) == "2"
+    return prob, check
+
+
+@cpu_case("requirement.go:117-150 (Gt on the provisioner, Lt on the pod: the bounds meet on the node)")
+def pod_and_provisioner_bounds_intersect():
+    its = fx.fake_instance_types(12)
+    pr = provisioner(requirements=[{"key": "integer", "operator": "Gt", "values": ["3"]}])
+    lt = pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "integer", "operator": "Lt", "values": ["6"]}]]})
+    crossing = pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "integer", "operator": "Lt", "values": ["3"]}]]})
+    notin = pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "integer", "operator": "Lt", "values": ["6"]},
+                                                            {"key": "integer", "operator": "NotIn", "values": ["4"]}]]})
+    prob = {"multi": [problem([p], instance_types=its, provisioners=[pr]) for p in (lt, crossing, notin)]}
+
+    def check(results):
+        a, b, c = results
+        assert a["assign"][0] >= 0 and b["assign"][0] < 0 and c["assign"][0] >= 0
+        opts = lambda r: sorted(its[i]["name"] for i in r["newNodes"][0]["options"])
+        assert opts(a) == ["fake-it-3", "fake-it-4"]     # integer in (3, 6) = cpu 4, 5
+        assert opts(c) == ["fake-it-4"]                  # ... without 4
+        assert a["newNodes"][0]["requirements"]["integer"] == "Exists [] >3 <6"
+        assert c["newNodes"][0]["requirements"]["integer"] == "NotIn [4] >3 <6"
+    return prob, check
+
+
+@cpu_case("requirements.go:123-133 (a Gt requirement is Exists with bounds: not a negative operator)")
+def gt_on_an_undefined_custom_key_is_incompatible():
+    # "custom" is not well known and the provisioner does not define it: In / Exists / Gt / Lt are refused, NotIn / DoesNotExist pass
+    mk = lambda op, vals: pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "custom", "operator": op, "values": vals}]]})
+    return each_alone([mk("Gt", ["1"]), mk("Lt", ["9"]), mk("NotIn", ["x"]), mk("DoesNotExist", []), mk("Exists", [])],
+                      [False, False, True, True, False])
+
+
+@cpu_case("requirements.go:189-206 with cloudprovider/types.go:72-85 (instance types may carry NotIn / Exists / Gt / Lt requirements)")
+def instance_types_with_complement_requirements():
+    its = fx.fake_instance_types(6)
+    its[0]["requirements"].append({"key": "tier", "operator": "NotIn", "values": ["gold"]})
+    its[1]["requirements"].append({"key": "tier", "operator": "Exists", "values": []})
+    its[2]["requirements"].append({"key": "tier", "operator": "In", "values": ["gold"]})
+    its[3]["requirements"].append({"key": "tier", "operator": "DoesNotExist", "values": []})
+    its[4]["requirements"].append({"key": "tier", "operator": "Gt", "values": ["5"]})
+    # its[5]: no requirement on the key
+    mk = lambda op, vals: pod({"cpu": "100m"}, nodeAffinity={"required": [[{"key": "tier", "operator": op, "values": vals}]]})
+    cases = [("In", ["gold"]), ("In", ["silver"]), ("NotIn", ["gold"]), ("Exists", []), ("DoesNotExist", []), ("In", ["7"]), ("Lt", ["3"])]
+    prob = {"multi": [problem([mk(op, v)], instance_types=its, wellKnownLabels=fx.WELL_KNOWN_EXTRA + ["tier"]) for op, v in cases]}
+    want = [["fake-it-1", "fake-it-2", "fake-it-5"],                         # In gold: Exists, In gold, no requirement
+            ["fake-it-0", "fake-it-1", "fake-it-5"],                         # In silver: NotIn gold, Exists, none
+            ["fake-it-0", "fake-it-1", "fake-it-3", "fake-it-4", "fake-it-5"],  # NotIn gold: every complement, DoesNotExist (both negative), none
+            ["fake-it-0", "fake-it-1", "fake-it-2", "fake-it-4", "fake-it-5"],  # Exists
+            ["fake-it-0", "fake-it-3", "fake-it-5"],                         # DoesNotExist: NotIn (negative) and DoesNotExist, none
+            ["fake-it-0", "fake-it-1", "fake-it-4", "fake-it-5"],            # In 7: NotIn gold, Exists, Gt 5, none
+            ["fake-it-0", "fake-it-1", "fake-it-5"]]                         # Lt 3: complement types whose bounds do not cross (Gt 5 does)
+
+    def check(results):
+        for r, w in zip(results, want):
+            assert r["assign"][0] >= 0
+            assert sorted(its[i]["name"] for i in r["newNodes"][0]["options"]) == w
+    return prob, check

@@ -19,7 +19,7 @@ def test_library_exports_every_header_symbol(pkg):
     lib = pkg.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.ksched_abi_version() == int(re.search(r"#define\s+KSCHED_ABI_VERSION\s+(\d+)", header).group(1)) == 3
+    assert lib.ksched_abi_version() == int(re.search(r"#define\s+KSCHED_ABI_VERSION\s+(\d+)", header).group(1)) == 4
     assert lib.ksched_type_words(1000) == 16 and lib.ksched_type_words(1) == 1 and lib.ksched_type_words(65) == 2
 
 
@@ -69,16 +69,30 @@ def test_duplicate_uids_are_rejected(pkg, oracle):
 
 
 def test_unsupported_inputs_fail_loudly(pkg):
+    # what the encoding cannot express is refused, never approximated: more than 16 active label keys, more than 7 distinct
+    # Gt/Lt thresholds on one key, a key whose values + regions do not fit one 64-bit word
+    many = fx.pod({"cpu": "1"}, nodeSelector={f"custom-{i}": "x" for i in range(17)})
+    with pytest.raises(pkg.KschedError) as e:
+        pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem([many])))
+    assert "unsupported" in str(e.value)
+    thr = [fx.pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "integer", "operator": "Gt", "values": [str(i)]}]]}) for i in range(8)]
+    with pytest.raises(pkg.KschedError) as e:
+        pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem(thr)))
+    assert "unsupported" in str(e.value)
+    wide = fx.pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "team", "operator": "In", "values": [f"v{i}" for i in range(64)]}]]})
+    with pytest.raises(pkg.KschedError) as e:
+        pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem([wide])))
+    assert "unsupported" in str(e.value)
+
+
+def test_gt_lt_and_complement_instance_types_are_encoded(pkg):
+    """the encoder hands Gt/Lt over in region form (include/ksched.h: ksched_key_regions) instead of refusing them"""
     its = fx.default_instance_types()
     its[0]["requirements"].append({"key": "custom", "operator": "NotIn", "values": ["x"]})
-    pr = fx.provisioner(labels={"custom": "y"})
-    with pytest.raises(pkg.KschedError) as e:
-        pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem([fx.pod({"cpu": "1"})], instance_types=its, provisioners=[pr])))
-    assert "unsupported" in str(e.value)
-    gt = fx.pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "integer", "operator": "Gt", "values": ["2"]}]]})
-    with pytest.raises(pkg.KschedError) as e:
-        pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem([gt])))
-    assert "unsupported" in str(e.value)
+    pr = fx.provisioner(labels={"custom": "y"}, requirements=[{"key": "integer", "operator": "Gt", "values": ["1"]}])
+    gt = fx.pod({"cpu": "1"}, nodeAffinity={"required": [[{"key": "integer", "operator": "Lt", "values": ["20"]}]]})
+    rs = pkg.ResidentSolve(pkg.Problem.from_dict(fx.problem([gt], instance_types=its, provisioners=[pr])))
+    assert rs.dims["pods"] == 1
 
 
 def test_no_cpu_fallback(pkg):

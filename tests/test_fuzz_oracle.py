@@ -1,7 +1,7 @@
 """CPU: the oracle runs every fuzz problem without error and its result satisfies basic conservation invariants."""
 import pytest
 
-from fuzz_problems import random_problem
+from fuzz_problems import random_problem, random_problem_with_bounds
 
 
 @pytest.mark.parametrize("seed", range(40))
@@ -19,3 +19,16 @@ def test_oracle_invariants_on_random_problems(pkg, oracle, seed):
         assert n["options"], "a committed node always has at least one instance type left"
         assert n["requests"].get("pods", 0) >= 1000 * len(n["pods"])
     assert all(a < ne + len(r["newNodes"]) for a in r["assign"])
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_encoder_accepts_bounds_fuzz_and_oracle_runs(pkg, oracle, seed):
+    """Gt / Lt / complement-type problems: the oracle runs them and the product's encoder hands them over (region form) or refuses loudly"""
+    prob = random_problem_with_bounds(seed)
+    problem = pkg.Problem.from_dict(prob)
+    res = pkg.Result()
+    assert oracle.solve(problem, res) == 0, res.error
+    try:
+        pkg.ResidentSolve(problem)
+    except pkg.KschedError as e:
+        assert e.code == pkg.KSCHED_ERR_UNSUPPORTED, str(e)
