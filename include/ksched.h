@@ -175,6 +175,27 @@ typedef struct ksched_existing_node {
   uint64_t label_keys_other;          /* reserved */
 } ksched_existing_node;
 
+/*
+ * CSI volume limits of existing nodes (scheduling/volumeusage.go:33-131, checked by ExistingNode.Add, existingnode.go:88-96).
+ * The API Gets of VolumeUsage.validate (:133-190: claim -> storage class / bound volume -> CSI driver) are the caller's; what
+ * crosses the ABI is counting. Only drivers that some existing node limits matter (<= KSCHED_MAX_VOLUME_DRIVERS). A claim that
+ * exactly one pod of (batch + bound pods) mounts is counted (priv / used); a claim several pods share is a TRACKED id, one bit
+ * of a 64-bit mask, so that mounting it twice on a node counts once (volumes.union, :55-70). Pod p fits node e iff for every
+ * limited driver d:  used[d] + popcount((mounted | shared) & volume_driver_mask[d]) + priv[d] <= limit[d].
+ * A node that already exceeds a limit accepts nobody (Exceeds walks the node's own drivers too, :101-112): the caller marks it
+ * by an `available` vector no pod fits.
+ */
+#define KSCHED_MAX_VOLUME_DRIVERS 4
+typedef struct ksched_class_volumes {
+  uint64_t shared;                          /* tracked claims the pods of this class mount */
+  uint16_t priv[KSCHED_MAX_VOLUME_DRIVERS]; /* claims only this pod mounts, per limited driver */
+} ksched_class_volumes;
+typedef struct ksched_node_volumes {
+  uint64_t mounted;                         /* tracked claims already mounted on the node */
+  int32_t used[KSCHED_MAX_VOLUME_DRIVERS];  /* mounted claims that are not tracked ids, per driver */
+  int32_t limit[KSCHED_MAX_VOLUME_DRIVERS]; /* CSINode allocatable count, -1 = the node has no limit for the driver */
+} ksched_node_volumes;
+
 /* topology group: TopologyGroup, topologygroup.go:53-64 */
 typedef struct ksched_topo_group {
   uint8_t type;      /* 0 spread, 1 pod affinity, 2 pod anti-affinity */
@@ -223,6 +244,10 @@ typedef struct ksched_problem {
   int32_t max_new_nodes;              /* capacity for new nodes (<= n_pods) */
   int32_t write_feasibility;          /* also copy the dense feasibility bitmask back (result.feasibility) */
   int32_t count_nodes_visited;        /* keep the exact nodes_visited statistic (one extra pass over the in-flight nodes per pod) */
+  /* CSI volume limits; both NULL when no pod of the batch mounts a claim of a driver that some existing node limits */
+  const ksched_class_volumes* class_volumes;   /* [n_classes] */
+  const ksched_node_volumes* existing_volumes; /* [n_existing] */
+  uint64_t volume_driver_mask[KSCHED_MAX_VOLUME_DRIVERS]; /* tracked claim ids by driver */
 } ksched_problem;
 
 typedef struct ksched_new_node {

@@ -155,6 +155,11 @@ struct ksched_handle {
   DevBuf<ksched_keyinfo> d_keys;
   DevBuf<int64_t> d_key_int, d_capacity, d_alloc_sorted;
   DevBuf<ksched_key_regions> d_key_regions;
+  DevBuf<ksched_class_volumes> d_cls_vol;
+  DevBuf<int32_t> d_cls_cursor;
+  DevBuf<ksched_node_volumes> d_ex_vol, d_ex_vol0;
+  bool have_volumes = false;
+  uint64_t vol_mask[KSCHED_MAX_VOLUME_DRIVERS] = {};
   DevBuf<ksched_template> d_templates;
   DevBuf<ksched_type_row> d_types;
   DevBuf<float> d_price32;
@@ -632,6 +637,13 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
     CUDA_TRY(h, upload_vec(h, h->d_ex_vals0, vals));
     CUDA_TRY(h, upload_vec(h, h->d_ex_meta0, meta));
     CUDA_TRY(h, upload_vec(h, h->d_ex_hp0, hp));
+    h->have_volumes = pb->class_volumes != nullptr && pb->existing_volumes != nullptr && NE > 0;
+    if (h->have_volumes) {
+      CUDA_TRY(h, upload(h, h->d_cls_vol, pb->class_volumes, (size_t)NC));
+      CUDA_TRY(h, upload(h, h->d_ex_vol0, pb->existing_volumes, (size_t)NE));
+      CUDA_TRY(h, h->d_ex_vol.ensure((size_t)NE));
+      for (int d = 0; d < KSCHED_MAX_VOLUME_DRIVERS; ++d) h->vol_mask[d] = pb->volume_driver_mask[d];
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host vectors go out of scope
     size_t ne = (size_t)std::max(NE, 1);
     CUDA_TRY(h, h->d_ex_req.ensure(8 * ne));
@@ -870,6 +882,9 @@ static int reset_state(ksched_handle* h) {
   CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_meta.ptr, h->d_ex_meta0.ptr, (size_t)NE * 8, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_hp.ptr, h->d_ex_hp0.ptr, (size_t)NE * 8, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_ex_closed.ptr, 0, (size_t)NE, h->stream));
+  CUDA_TRY(h, h->d_cls_cursor.ensure((size_t)std::max(h->n_classes, 1)));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_cls_cursor.ptr, 0, (size_t)std::max(h->n_classes, 1) * 4, h->stream));
+  if (h->have_volumes) CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_vol.ptr, h->d_ex_vol0.ptr, (size_t)h->n_existing * sizeof(ksched_node_volumes), cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_cnt.ptr, h->d_grp_cnt0.ptr, (size_t)NG * 64 * 4, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_registered.ptr, h->d_grp_registered0.ptr, (size_t)NG * 8, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host_total.ptr, h->d_grp_host_total0.ptr, (size_t)NG * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -910,6 +925,9 @@ static int run_pack(ksched_handle* h) {
   s.ex_req = h->d_ex_req.ptr; s.ex_avail = h->d_ex_avail.ptr; s.ex_req_present = h->d_ex_req_present.ptr; s.ex_avail_present = h->d_ex_avail_present.ptr;
   s.ex_vals = h->d_ex_vals.ptr; s.ex_meta = h->d_ex_meta.ptr; s.ex_taintset = h->d_ex_taintset.ptr; s.ex_itype = h->d_ex_itype.ptr;
   s.ex_hp = h->d_ex_hp.ptr; s.ex_closed = h->d_ex_closed.ptr;
+  s.cls_cursor = h->d_cls_cursor.ptr;
+  s.cls_vol = h->have_volumes ? h->d_cls_vol.ptr : nullptr; s.ex_vol = h->have_volumes ? h->d_ex_vol.ptr : nullptr;
+  for (int d = 0; d < KSCHED_MAX_VOLUME_DRIVERS; ++d) s.vol_mask[d] = h->vol_mask[d];
   s.nn_tmpl = h->d_nn_tmpl.ptr; s.nn_count = h->d_nn_count.ptr; s.nn_tb = h->d_nn_tb.ptr; s.nn_req = h->d_nn_req.ptr;
   s.nn_req_present = h->d_nn_req_present.ptr;
   s.nn_vals = h->d_nn_vals.ptr; s.nn_meta = h->d_nn_meta.ptr; s.nn_opts = h->d_nn_opts.ptr; s.nn_hp = h->d_nn_hp.ptr;

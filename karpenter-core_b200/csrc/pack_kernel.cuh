@@ -164,6 +164,21 @@ __device__ __forceinline__ unsigned long long block_min_u64_db(unsigned long lon
   return warp_min_u64(r);
 }
 
+// two independent u32 minima with one barrier (double-buffered scratch, same protocol as block_min_u64_db)
+__device__ __forceinline__ void block_min2_u32_db(unsigned a, unsigned b, unsigned long long (*red)[32], int& parity, unsigned* ra, unsigned* rb) {
+  a = __reduce_min_sync(0xffffffffu, a);
+  b = __reduce_min_sync(0xffffffffu, b);
+  if (blockDim.x == 32) { *ra = a; *rb = b; return; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* buf = red[parity];
+  parity ^= 1;
+  if (lane == 0) buf[warp] = ((unsigned long long)a << 32) | b;
+  __syncthreads();
+  const unsigned long long r = lane < (int)(blockDim.x >> 5) ? buf[lane] : ~0ull;
+  *ra = __reduce_min_sync(0xffffffffu, (unsigned)(r >> 32));
+  *rb = __reduce_min_sync(0xffffffffu, (unsigned)r);
+}
+
 struct StepShared {
   int placed_closed;   // commit outcome: 1 = the accepting node became full and left the active set
   int path;            // fresh-node path
@@ -376,16 +391,35 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
     const bool simple = !has_topo && p_hpc == 0 && p_hpe == 0;  // the requirement verdict memo (HotSmem::absorbed/rejected) applies
 
     bool placed = false;
+    ksched_class_volumes p_vol{};
+    bool has_vol = false;
+    if (s.cls_vol) {
+      p_vol = s.cls_vol[cls];
+      has_vol = (p_vol.shared | p_vol.priv[0] | p_vol.priv[1] | p_vol.priv[2] | p_vol.priv[3]) != 0;
+    }
     GK_T(0)
     // ------------------------------------------------------------ 1) existing nodes in caller order (scheduler.go:176-180)
     if (NE > 0) {
-      unsigned long long mine = ~0ull;
+      // Every existing node below the class's cursor refuses this class for good: it is closed, its taints are not
+      // tolerated, a host port or a volume limit is taken, or the requests no longer fit - all of which only get worse as
+      // pods are added (existingnode.go:79-102). Rejections by requirements / topology can be lifted later and stop the cursor.
+      const int start = s.cls_cursor[cls];
+      unsigned mine = ~0u, soft = ~0u;  // first node this thread accepts / first node it did not refuse for good
       Touched t;
       t.n = 0;
-      for (int e = tid; e < NE; e += blockDim.x) {
+      for (int e = start + tid; e < NE; e += blockDim.x) {
         if (s.ex_closed[e]) continue;
         if (!((p_tol >> s.ex_taintset[e]) & 1)) continue;
         if (p_hpc && (s.ex_hp[e] & p_hpc)) continue;
+        if (has_vol) {  // volumeUsage.Validate(pod).Exceeds(volumeLimits) existingnode.go:88-96
+          const ksched_node_volumes nv = s.ex_vol[e];
+          const uint64_t all = nv.mounted | p_vol.shared;
+          bool over = false;
+#pragma unroll
+          for (int d = 0; d < KSCHED_MAX_VOLUME_DRIVERS; ++d)
+            over = over || (nv.limit[d] >= 0 && nv.used[d] + __popcll(all & s.vol_mask[d]) + (int)p_vol.priv[d] > nv.limit[d]);
+          if (over) continue;
+        }
         bool ok = true;  // Fits(requests, available) comes first (existingnode.go:98-102)
         const uint32_t qp = s.ex_req_present[e] | p_res;
         for (int r = 0; r < R && ok; ++r) {
@@ -395,20 +429,24 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
           ok = q <= a;
         }
         if (!ok) continue;
+        if (soft == ~0u) soft = (unsigned)e;
         if (p_itype != KSCHED_NONE) {
           const uint32_t it = s.ex_itype[e];
           bool allowed = it == KSCHED_NONE ? (s.itype_complement[p_itype] != 0) : ((s.itype_sets[(size_t)p_itype * W32 + (it >> 5)] >> (it & 31)) & 1);
           if (!allowed) continue;
         }
         if (!plain && !requirements_phase(s.ex_vals, s.ex_meta[e], NE, e, e, true, t)) continue;
-        mine = (unsigned long long)e;
+        mine = (unsigned)e;
         break;  // this thread's remaining nodes have larger indices
       }
-      const unsigned long long w = block_min_u64_db(mine, red, parity);
+      unsigned w32, soft_min;
+      block_min2_u32_db(mine, soft, red, parity, &w32, &soft_min);
+      if (tid == 0) s.cls_cursor[cls] = soft_min == ~0u ? NE : (int)soft_min;  // read again only after the next step's barriers
+      const unsigned long long w = w32 == ~0u ? ~0ull : (unsigned long long)w32;
       if (w != ~0ull) {
         const int e = (int)w;
         nodes_visited += e + 1;
-        if (mine == w) {  // the winning thread commits its own candidate
+        if (mine == w32) {  // the winning thread commits its own candidate
           uint64_t meta = s.ex_meta[e];
           if (!plain) {
             for (int i = 0; i < t.n; ++i) {
@@ -430,6 +468,13 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
           }
           s.ex_req_present[e] |= p_res;
           if (p_hpe) s.ex_hp[e] |= p_hpe;
+          if (has_vol) {  // volumeUsage.Add existingnode.go:128
+            ksched_node_volumes nv = s.ex_vol[e];
+            nv.mounted |= p_vol.shared;
+#pragma unroll
+            for (int d = 0; d < KSCHED_MAX_VOLUME_DRIVERS; ++d) nv.used[d] += (int)p_vol.priv[d];
+            s.ex_vol[e] = nv;
+          }
           s.ex_closed[e] = closed;
           s.assign[pod] = e;
           s.place_seq[pod] = seq;

@@ -54,6 +54,10 @@ struct PackState {
   const uint32_t* ex_itype;
   uint64_t* ex_hp;
   uint8_t* ex_closed;
+  int32_t* cls_cursor;                  // [n_classes] existing nodes below it refuse the class for good (pack_kernel.cuh, generic step 1)
+  const ksched_class_volumes* cls_vol;  // [n_classes] or nullptr: CSI volume limits (ksched.h)
+  ksched_node_volumes* ex_vol;          // [n_existing]
+  uint64_t vol_mask[KSCHED_MAX_VOLUME_DRIVERS];
   // new nodes (SoA, capacity max_new)
   uint8_t* nn_tmpl;
   int32_t* nn_count;

@@ -200,6 +200,7 @@ bool same_container(const Container& a, const Container& b) {
 }
 bool same_spec(const Pod& a, const Pod& b) {
   auto wterm = [](const WeightedPodAffinityTerm& x, const WeightedPodAffinityTerm& y) { return x.weight == y.weight && same_term(x.term, y.term); };
+  if (!a.volumes.empty() || !b.volumes.empty()) return false;  // claims are per pod: the keyed path decides (volume signature)
   return a.ns == b.ns && a.labels == b.labels && same_vec(a.containers, b.containers, same_container) &&
          same_vec(a.init_containers, b.init_containers, same_container) && a.node_selector == b.node_selector &&
          a.has_node_affinity == b.has_node_affinity && a.has_required_node_affinity == b.has_required_node_affinity &&
@@ -557,6 +558,52 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     for (auto& t : pr.taints) if (t.effect == "PreferNoSchedule") tolerate_pns = true;
 
   phase("who takes part");
+  // ------------------------------------------------------------------ CSI volume limits (ksched.h: ksched_class_volumes)
+  // Drivers some owned state node limits; claims by how many pods (batch + bound) mount them: one -> counted, several -> tracked id.
+  std::vector<std::string> vol_drivers;
+  std::map<std::pair<std::string, std::string>, int> vol_tracked;  // (driver, claim) -> bit
+  auto pod_claims = [&](const Pod& p) {  // VolumeUsage.validate's result: driver -> claim set, limited drivers only
+    std::map<std::string, std::set<std::string>> m;
+    for (auto& v : p.volumes)
+      if (!v.driver.empty() && std::find(vol_drivers.begin(), vol_drivers.end(), v.driver) != vol_drivers.end()) m[v.driver].insert(v.pvc_id);
+    return m;
+  };
+  {
+    std::set<std::string> drivers;
+    for (int si : state_nodes) for (auto& kv : P.nodes[si].volume_limits) drivers.insert(kv.first);
+    vol_drivers.assign(drivers.begin(), drivers.end());
+    if (vol_drivers.size() > KSCHED_MAX_VOLUME_DRIVERS) unsupported("more than 4 CSI drivers with node volume limits");
+    if (!vol_drivers.empty()) {
+      std::map<std::pair<std::string, std::string>, int> refs;
+      auto count = [&](const Pod& p) { for (auto& kv : pod_claims(p)) for (auto& c : kv.second) refs[{kv.first, c}]++; };
+      for (auto* p : E.pods) count(*p);
+      for (int si : state_nodes) for (auto& p : P.nodes[si].pods) count(p);
+      for (auto& kv : refs)
+        if (kv.second > 1) {
+          if (vol_tracked.size() >= 64) unsupported("more than 64 volume claims shared between pods");
+          const int bit = (int)vol_tracked.size();
+          vol_tracked[kv.first] = bit;
+        }
+    }
+  }
+  auto volume_signature = [&](const Pod& p, ksched_class_volumes* out) {
+    ksched_class_volumes cv{};
+    if (!vol_drivers.empty())
+      for (auto& kv : pod_claims(p)) {
+        const size_t d = (size_t)(std::find(vol_drivers.begin(), vol_drivers.end(), kv.first) - vol_drivers.begin());
+        for (auto& c : kv.second) {
+          auto t = vol_tracked.find({kv.first, c});
+          if (t != vol_tracked.end()) cv.shared |= 1ull << t->second;
+          else if (cv.priv[d] == 0xFFFF) unsupported("more than 65535 volume claims on one pod");
+          else cv.priv[d]++;
+        }
+      }
+    if (out) *out = cv;
+    char b[96];
+    std::snprintf(b, sizeof b, "|V=%llx:%u:%u:%u:%u", (unsigned long long)cv.shared, cv.priv[0], cv.priv[1], cv.priv[2], cv.priv[3]);
+    return (cv.shared | cv.priv[0] | cv.priv[1] | cv.priv[2] | cv.priv[3]) ? std::string(b) : std::string();
+  };
+
   // ------------------------------------------------------------------ pod specs: classes and relaxation chains
   struct Spec { Pod pod; ResourceList req; uint32_t next = KSCHED_NONE; };
   std::vector<Spec> specs;
@@ -564,6 +611,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   std::function<uint32_t(const Pod&)> intern = [&](const Pod& p) -> uint32_t {
     ResourceList req = pod_requests(p);
     std::string k = class_key(p, req);
+    if (!p.volumes.empty()) k += volume_signature(p, nullptr);
     auto it = spec_id.find(k);
     if (it != spec_id.end()) return it->second;
     uint32_t id = (uint32_t)specs.size();
@@ -919,6 +967,28 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     E.existing_state_index.push_back(si);
     auto ini = n.labels.find(kInitialized);
     E.existing_initialized.push_back(ini != n.labels.end() && ini->second == "true");
+    if (!vol_drivers.empty()) {  // state.Node.VolumeUsage() / VolumeLimits() (state/cluster.go:292-303,340-347)
+      ksched_node_volumes nv{};
+      std::map<std::string, std::set<std::string>> mounted;
+      for (auto& p : n.pods) for (auto& kv : pod_claims(p)) mounted[kv.first].insert(kv.second.begin(), kv.second.end());
+      bool over = false;
+      for (size_t d = 0; d < KSCHED_MAX_VOLUME_DRIVERS; ++d) {
+        nv.limit[d] = -1;
+        if (d >= vol_drivers.size()) continue;
+        auto l = n.volume_limits.find(vol_drivers[d]);
+        if (l != n.volume_limits.end()) nv.limit[d] = l->second;
+        int total = 0;
+        for (auto& c : mounted[vol_drivers[d]]) {
+          ++total;
+          auto t = vol_tracked.find({vol_drivers[d], c});
+          if (t != vol_tracked.end()) nv.mounted |= 1ull << t->second; else nv.used[d]++;
+        }
+        if (nv.limit[d] >= 0 && total > nv.limit[d]) over = true;
+      }
+      // a node already over a limit refuses every pod (VolumeCount.Exceeds walks the node's own drivers, volumeusage.go:101-112)
+      if (over) { e.available[2] = std::numeric_limits<int64_t>::min() / 4; e.available_present |= 1u << 2; }
+      E.existing_volumes.push_back(nv);
+    }
     E.existing.push_back(e);
     for (int v = 0; v < NV; ++v)  // scheduler.go:244-246
       if (P.provisioners[E.template_provisioner[v]].name == own->second && E.templates[v].has_limits) {
@@ -1250,6 +1320,16 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     }
     row.topo_end = (uint32_t)E.class_topo.size();
   }
+  if (!vol_drivers.empty()) {
+    E.class_volumes.resize(NC);
+    bool any = false;
+    for (int c = 0; c < NC; ++c) any = !volume_signature(specs[c].pod, &E.class_volumes[c]).empty() || any;
+    if (!any) E.class_volumes.clear();  // no pod of the batch mounts a limited claim: the kernels never look
+    for (auto& kv : vol_tracked) {
+      const size_t d = (size_t)(std::find(vol_drivers.begin(), vol_drivers.end(), kv.first.first) - vol_drivers.begin());
+      E.volume_driver_mask[d] |= 1ull << kv.second;
+    }
+  }
   // host-port conflict masks and tolerated taint sets need the complete entry / taint-set tables
   for (int c = 0; c < NC; ++c) {
     const Pod& p = specs[c].pod;
@@ -1311,6 +1391,11 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   pr.n_hostname_reqs = (int)E.hostname_reqs.size() / 2;
   pr.max_new_nodes = (int)NP;
   pr.write_feasibility = 0;
+  if (!E.class_volumes.empty() && NE > 0) {
+    pr.class_volumes = E.class_volumes.data();
+    pr.existing_volumes = E.existing_volumes.data();
+    for (int d = 0; d < KSCHED_MAX_VOLUME_DRIVERS; ++d) pr.volume_driver_mask[d] = E.volume_driver_mask[d];
+  }
   pr.count_nodes_visited = 0;  // the exact nodes_visited statistic is opt-in (kh_set_count_visited / tests): it turns the pack kernel's steady-state paths off
   // Gt/Lt leave the host algebra here: templates and pod classes in region form (types and filter terms already are)
   for (int v = 0; v < NV; ++v) B.to_region_form(E.templates[v].reqs, tb[v]);

@@ -51,6 +51,9 @@ struct Encoded {
   std::vector<uint64_t> itype_req_sets;
   std::vector<uint8_t> itype_req_complement;
   std::vector<int32_t> hostname_reqs;
+  std::vector<ksched_class_volumes> class_volumes;    // CSI volume limits (ksched.h); empty when no pod mounts a limited claim
+  std::vector<ksched_node_volumes> existing_volumes;
+  uint64_t volume_driver_mask[KSCHED_MAX_VOLUME_DRIVERS] = {};
 
   ksched_catalog catalog{};
   ksched_problem problem{};

@@ -649,6 +649,7 @@ extern "C" unsigned long long kh_encoded_digest(const Encoded* E) {
   bytes(flags, 2);
   vec(E->pod_class); vec(E->pod_timestamp); vec(E->pod_uid_rank); vec(E->existing); vec(E->groups); vec(E->group_domain_counts);
   vec(E->group_existing_counts); vec(E->class_topo); vec(E->filter_terms); vec(E->itype_req_sets); vec(E->itype_req_complement); vec(E->hostname_reqs);
+  if (!E->class_volumes.empty()) { vec(E->class_volumes); vec(E->existing_volumes); bytes(E->volume_driver_mask, sizeof E->volume_driver_mask); }
   const ksched_catalog& c = E->catalog;
   int cat[4] = {c.n_keys, c.n_res, c.n_types, c.n_templates};
   bytes(cat, sizeof cat);

@@ -159,4 +159,21 @@ def random_problem_with_bounds(seed):
             if q["operator"] in ("Exists", "DoesNotExist"):
                 q["values"] = []
     prob["wellKnownLabels"] = list(prob["wellKnownLabels"]) + (["tier"] if rng.random() < 0.5 else [])
+    # CSI volume limits (existingnode.go:88-96): limits on some nodes, private and shared claims on pending and bound pods
+    if prob.get("nodes") and rng.random() < 0.6:
+        drivers = ["ebs", "efs"]
+        def claims(owner):
+            out = []
+            for _ in range(rng.choice([0, 0, 1, 2, 3])):
+                d = rng.choice(drivers + [""])
+                out.append({"driver": d, "pvc": rng.choice([f"default/shared-{rng.randrange(4)}", f"default/{owner}-{len(out)}"])})
+            return out
+        for n in prob["nodes"]:
+            if rng.random() < 0.7:
+                n["volumeLimits"] = {d: rng.choice([0, 1, 2, 4]) for d in drivers if rng.random() < 0.7}
+            for bp in n["pods"]:
+                bp["volumes"] = claims(bp["name"])
+        for p in prob["pods"]:
+            if rng.random() < 0.5:
+                p["volumes"] = claims(p["name"])
     return prob

@@ -1477,3 +1477,62 @@ def instance_types_with_complement_requirements():
             assert r["assign"][0] >= 0
             assert sorted(its[i]["name"] for i in r["newNodes"][0]["options"]) == w
     return prob, check
+
+
+# ------------------------------------------------------------------ CSI volume limits of existing nodes (suite_test.go:1995-2240)
+def _volume_setup(claims_of, n_pods, limit=10):
+    big = fx.instance_type("instance-type", {"cpu": "1024", "pods": "1024"})
+    node = fx.state_node("node-0", "instance-type", allocatable={"cpu": "1000", "pods": "1000"},
+                         pods_=[pod({"cpu": "1"}, nodeName="node-0")], volumeLimits={"fake.csi.provider": limit})
+    ps = [pod({"cpu": "1"}, volumes=claims_of(i)) for i in range(n_pods)]
+    return problem(ps, instance_types=[big], provisioners=[provisioner(limits=None)], nodes=[node])
+
+
+@cpu_case("suite_test.go:1995-2057")
+def volume_limits_force_a_second_node():
+    prob = _volume_setup(lambda i: [{"driver": "fake.csi.provider", "pvc": f"default/my-claim-a-{i}"},
+                                    {"driver": "fake.csi.provider", "pvc": f"default/my-claim-b-{i}"}], 6)
+
+    def check(res):
+        assert all(a >= 0 for a in res["assign"])
+        assert sorted(res["assign"]).count(0) == 5      # the in-flight node takes 5 pods = 10 volumes
+        assert len(res["newNodes"]) == 1
+    return prob, check
+
+
+@cpu_case("suite_test.go:2058-2123")
+def one_shared_claim_fits_a_single_node():
+    prob = _volume_setup(lambda i: [{"driver": "fake.csi.provider", "pvc": "default/my-claim"}, {"driver": "fake.csi.provider", "pvc": "default/my-claim"}], 100)
+
+    def check(res):
+        assert res["assign"] == [0] * 100 and res["newNodes"] == []
+    return prob, check
+
+
+@cpu_case("suite_test.go:2124-2240 (claims without a CSI driver are not counted)")
+def non_csi_claims_are_not_counted():
+    prob = _volume_setup(lambda i: [{"driver": "", "pvc": f"default/nfs-{i}"}, {"driver": "", "pvc": f"default/static-{i}"}], 12)
+
+    def check(res):
+        assert res["assign"] == [0] * 12 and res["newNodes"] == []
+    return prob, check
+
+
+@cpu_case("volumeusage.go:101-131 (shared and private claims on one node; a node over its limit takes nobody)")
+def shared_and_private_claims_mix():
+    big = fx.instance_type("instance-type", {"cpu": "1024", "pods": "1024"})
+    bound = [pod({"cpu": "1"}, nodeName="node-0", volumes=[{"driver": "ebs", "pvc": "default/shared"}, {"driver": "ebs", "pvc": "default/b0"}])]
+    over = [pod({"cpu": "1"}, nodeName="node-1", volumes=[{"driver": "ebs", "pvc": f"default/o{i}"} for i in range(3)])]
+    nodes = [fx.state_node("node-0", "instance-type", allocatable={"cpu": "1000", "pods": "1000"}, pods_=bound, volumeLimits={"ebs": 4}),
+             fx.state_node("node-1", "instance-type", allocatable={"cpu": "1000", "pods": "1000"}, pods_=over, volumeLimits={"ebs": 2}),
+             fx.state_node("node-2", "instance-type", allocatable={"cpu": "1000", "pods": "1000"}, volumeLimits={"efs": 1})]
+    ps = [pod({"cpu": "3"}, volumes=[{"driver": "ebs", "pvc": "default/shared"}, {"driver": "ebs", "pvc": "default/p0"}]),   # node-0: 2 + 1 new = 3
+          pod({"cpu": "2"}, volumes=[{"driver": "ebs", "pvc": "default/shared"}, {"driver": "ebs", "pvc": "default/p1"}]),   # node-0: 4
+          pod({"cpu": "1"}, volumes=[{"driver": "ebs", "pvc": "default/shared"}, {"driver": "ebs", "pvc": "default/p2"}]),   # node-0 full, node-1 over its limit -> node-2 (no ebs limit)
+          pod({"cpu": "500m"}),                                                                                          # no volumes: node-0
+          pod({"cpu": "250m"}, volumes=[{"driver": "efs", "pvc": "default/e0"}, {"driver": "efs", "pvc": "default/e1"}])]     # efs limit 1 on node-2 -> node-0
+    prob = problem(ps, instance_types=[big], provisioners=[provisioner(limits=None)], nodes=nodes)
+
+    def check(res):
+        assert res["assign"] == [0, 0, 2, 0, 0]
+    return prob, check
