@@ -24,6 +24,7 @@
 #ifndef KSCHED_H
 #define KSCHED_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -284,6 +285,61 @@ typedef struct ksched_result {
   ksched_launch_choice* launch; /* [max_new_nodes] or NULL (needs ksched_catalog.offering_keys) */
 } ksched_result;
 
+/*
+ * Device-resident cluster snapshot for the consolidation simulator (deprovisioning/helpers.go:42-115, the state it reads:
+ * controllers/state/cluster.go:74-103, state/node.go:113-143). One consolidation pass simulates many candidate sets against the
+ * same cluster; the cluster crosses the ABI ONCE, as a superset problem:
+ *   existing = every owned, not-deleting node - the candidates too - with ALL its pods bound (available, host ports, volumes);
+ *   pods     = the pending pods first, then every reschedulable pod of every candidate node, node by node;
+ *   pod_node = the existing slot a pod is bound to (-1 = pending: part of every simulation).
+ * A simulation names the existing slots it removes: their pods form the batch, the slots accept nobody, the rest of the cluster
+ * is what the superset says. Topology groups are not supported on this path yet (n_groups must be 0): ksched_load_cluster answers
+ * KSCHED_ERR_UNSUPPORTED and the caller simulates through ksched_solve instead.
+ */
+typedef struct ksched_cluster {
+  const ksched_problem* problem;
+  const int32_t* pod_node; /* [problem->n_pods] */
+} ksched_cluster;
+
+typedef struct ksched_candidate_set {
+  const int32_t* nodes;     /* existing slots removed by this simulation (the candidates, helpers.go:52-68), distinct */
+  int32_t n_nodes;
+  int32_t pad;
+  const int64_t* remaining; /* [n_templates][KSCHED_MAX_RES] provisioner limits left with the removed nodes' capacity given back
+                               (scheduler.go:221-248 only subtracts the nodes that stay), or NULL = as in the catalog */
+} ksched_candidate_set;
+
+/* What computeConsolidation reads of one simulation (consolidation.go:190-274). */
+typedef struct ksched_sim_result {
+  int32_t n_pods;        /* size of the batch */
+  int32_t n_unscheduled;
+  int32_t n_new_nodes;
+  int32_t error;         /* 0, or a negative ksched error of this simulation (capacity overflow ...) */
+  ksched_new_node node0; /* the first new node, valid when n_new_nodes >= 1 */
+} ksched_sim_result;
+
+/*
+ * Candidate ranking for deprovisioning: disruption cost per node and the order consolidation tries the nodes in
+ * (deprovisioning/helpers.go:125-165,275-287 disruptionCost / GetPodEvictionCost / calculateLifetimeRemaining,
+ * consolidation.go:85-103 sortAndFilterCandidates). What needs strings or the API server stays with the caller and arrives as
+ * flags: node_eligible (candidateNodes' label / annotation filters, helpers.go:171-222, consolidation.go:104-118) and the
+ * "blocks eviction" pod flag (PDB with no disruptions left, do-not-evict: helpers.go:339-366, pdblimits.go:55-68).
+ */
+#define KSCHED_RANK_HAS_DELETION_COST 1
+#define KSCHED_RANK_HAS_PRIORITY 2
+#define KSCHED_RANK_BLOCKS_EVICTION 4
+typedef struct ksched_rank_input {
+  int32_t n_nodes, n_pods;
+  const int32_t* pod_offsets;      /* [n_nodes + 1] pods of node n = [pod_offsets[n], pod_offsets[n+1]), in the node's pod-list order */
+  const double* pod_deletion_cost; /* [n_pods] controller.kubernetes.io/pod-deletion-cost */
+  const int32_t* pod_priority;     /* [n_pods] Spec.Priority */
+  const uint8_t* pod_flags;        /* [n_pods] KSCHED_RANK_* */
+  const uint8_t* node_eligible;    /* [n_nodes] */
+  const double* node_age_seconds;  /* [n_nodes] clock.Since(node.CreationTimestamp) */
+  const double* node_ttl_seconds;  /* [n_nodes] provisioner.Spec.TTLSecondsUntilExpired, < 0 = nil */
+  const double* node_cost;         /* NULL, or [n_nodes] disruption costs computed elsewhere: only filter + order */
+} ksched_rank_input;
+
 typedef struct ksched_timings {
   double upload_us, sort_us, feasibility_us, pack_us, download_us, total_us, allreduce_us;
   int64_t feasibility_bytes; /* P*256 + C*256 + P*C/8 for the last solve */
@@ -315,6 +371,10 @@ int ksched_shard_range(int n_words32, int rank, int world, int* begin, int* end)
 /* NCCL: rank 0 calls ksched_nccl_unique_id, the host distributes the 128 bytes, every rank calls ksched_nccl_init. */
 int ksched_nccl_unique_id(void* out128);
 int ksched_nccl_init(ksched_handle* h, const void* id128, int rank, int world);
+/* One ncclAllGather of `bytes` bytes per rank on the handle's communicator (host buffers; recv holds world * bytes): the
+   exchange step of a sharded consolidation pass (each rank's simulation verdicts). Call ksched_set_shard(h, 0, 1) after
+   ksched_nccl_init when the communicator is only used for this (no column sharding of the feasibility matrix). */
+int ksched_allgather(ksched_handle* h, const void* send, size_t bytes, void* recv);
 
 /* Scheduler.Solve: host buffers in, host buffers out; stream-synchronised before returning. */
 int ksched_solve(ksched_handle* h, const ksched_problem* problem, ksched_result* result);
@@ -324,6 +384,15 @@ int ksched_upload(ksched_handle* h, const ksched_problem* problem);
 int ksched_run_resident(ksched_handle* h, int flush_l2);
 int ksched_download(ksched_handle* h, const ksched_problem* problem, ksched_result* result);
 int ksched_run_feasibility_only(ksched_handle* h, int flush_l2, float* elapsed_us);
+
+/* Consolidation simulator on a device-resident cluster snapshot: upload once, then any number of simulations. */
+int ksched_load_cluster(ksched_handle* h, const ksched_cluster* cluster);
+/* results[n_sets]; node0_types[n_sets][type_words] = surviving InstanceTypeOptions of each simulation's first new node.
+   The simulations run back to back on the handle's stream with one synchronisation at the end. */
+int ksched_simulate_batch(ksched_handle* h, const ksched_candidate_set* sets, int n_sets, ksched_sim_result* results, uint64_t* node0_types);
+
+/* order[0..*n_candidates) = node indices by ascending disruption cost (ties: input order), cost[i] = cost of order[i]. */
+int ksched_rank_candidates(ksched_handle* h, const ksched_rank_input* in, int32_t* order, double* cost, int32_t* n_candidates);
 
 int ksched_get_timings(const ksched_handle* h, ksched_timings* out);
 

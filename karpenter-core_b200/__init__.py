@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "ksched_abi_version", "ksched_device_count", "ksched_create", "ksched_destroy", "ksched_last_error",
     "ksched_type_words", "ksched_load_catalog", "ksched_set_shard", "ksched_shard_range", "ksched_nccl_unique_id", "ksched_nccl_init",
     "ksched_solve", "ksched_upload", "ksched_run_resident", "ksched_download", "ksched_run_feasibility_only",
-    "ksched_get_timings",
+    "ksched_get_timings", "ksched_load_cluster", "ksched_simulate_batch", "ksched_allgather", "ksched_rank_candidates",
 ]
 
 
@@ -116,6 +116,16 @@ def lib():
     L.kh_consolidate.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                  C.POINTER(C.c_int)]
     L.kh_consolidate_candidates.argtypes = [C.c_void_p]
+    L.kh_cluster_open.restype = C.c_void_p
+    L.kh_cluster_open.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.kh_cluster_close.argtypes = [C.c_void_p]
+    L.kh_cluster_probe_sets.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                        C.POINTER(C.c_int)]
+    L.kh_cluster_candidates.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    L.kh_consolidate_single.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    L.kh_allgather_i32.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+    L.kh_nccl_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.kh_rank_candidates.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int]
     L.kh_consolidate_probe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
     L.kh_mask_intersection.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_longlong)]
     L.kh_mask_allowed.restype = C.c_longlong
@@ -292,9 +302,79 @@ def simulate_scheduling(problem: Problem, nodes_to_delete):
     return Scheduler(problem).solve(candidates=nodes_to_delete)
 
 
+class ClusterSession:
+    """One consolidation pass over a cluster: the candidates ranked once, the cluster resident on the device once
+    (ksched_load_cluster), every computeConsolidation one entry of a ksched_simulate_batch call."""
+    OPTIONS_STRIDE = 2048
+
+    def __init__(self, problem: Problem):
+        self.problem = problem
+        res, n = C.c_int(), C.c_int()
+        self.ptr = lib().kh_cluster_open(problem.ptr, C.byref(res), C.byref(n))
+        if not self.ptr:
+            msg = lib().kh_scheduler_error().decode()
+            raise KschedError(KSCHED_ERR_NO_DEVICE if "no usable CUDA device" in msg else KSCHED_ERR_INVALID, msg)
+        self.resident = bool(res.value)
+        self.n_candidates = n.value
+
+    def candidate_nodes(self):
+        arr = (C.c_int * max(1, self.n_candidates))()
+        lib().kh_cluster_candidates(self.ptr, arr, self.n_candidates)
+        return list(arr[:self.n_candidates])
+
+    def probe_sets(self, sets, multi):
+        """computeConsolidation for every candidate set (positions in the disruption order) in one device batch ->
+        [(action, options)]"""
+        if not sets:
+            return []
+        flat = [i for s_ in sets for i in s_]
+        off = [0]
+        for s_ in sets:
+            off.append(off[-1] + len(s_))
+        stride = self.OPTIONS_STRIDE
+        actions = (C.c_int * len(sets))()
+        nopt = (C.c_int * len(sets))()
+        opts = (C.c_int * (stride * len(sets)))()
+        _check(lib().kh_cluster_probe_sets(self.ptr, (C.c_int * max(1, len(flat)))(*flat), (C.c_int * len(off))(*off), len(sets), int(multi), actions, opts, stride,
+                                           nopt))
+        return [(int(actions[q]), list(opts[q * stride:q * stride + min(nopt[q], stride)])) for q in range(len(sets))]
+
+    def close(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.kh_cluster_close(self.ptr)
+            self.ptr = None
+
+    __del__ = close
+
+
+def rank_candidates(problem: Problem, cap=65536):
+    """deprovisioning candidates in disruption order (device kernels: costs, lifetime scaling, order) -> (node indices, costs)"""
+    order = (C.c_int * cap)()
+    cost = (C.c_double * cap)()
+    n = lib().kh_rank_candidates(problem.ptr, order, cost, cap)
+    if n < 0:
+        _check(n)
+    return list(order[:n]), list(cost[:n])
+
+
+def nccl_allgather_i32(values, world):
+    """one ncclAllGather of `values` (ints) on the scheduler handle's communicator -> [per-rank list]"""
+    n = len(values)
+    send = (C.c_int * max(1, n))(*values)
+    recv = (C.c_int * max(1, n * world))()
+    _check(lib().kh_allgather_i32(send, n, recv))
+    return [list(recv[r * n:(r + 1) * n]) for r in range(world)]
+
+
 class MultiNodeConsolidation:
     def __init__(self, problem: Problem):
         self.problem = problem
+        self._session = None
+
+    def session(self):
+        if self._session is None:
+            self._session = ClusterSession(self.problem)
+        return self._session
 
     def first_n_node_consolidation_option(self):
         out4 = (C.c_int * 4)()
@@ -307,25 +387,19 @@ class MultiNodeConsolidation:
         return {"action": out4[0], "nodes_removed": out4[1], "simulations": out4[2], "options": list(opts[:out4[3]]),
                 "probes": list(probes[:npr.value]), "probe_actions": list(acts[:npr.value])}
 
-
     def candidates(self):
         return int(lib().kh_consolidate_candidates(self.problem.ptr))
 
     def probe(self, count):
-        """computeConsolidation over the `count` cheapest candidates (one simulateScheduling on this rank's GPU)."""
-        opts = (C.c_int * 8192)()
-        n = C.c_int()
-        rc = lib().kh_consolidate_probe(self.problem.ptr, int(count), opts, 8192, C.byref(n))
-        if rc < 0:
-            _check(rc)
-        return (int(rc), list(opts[:n.value]))
+        """computeConsolidation over the `count` cheapest candidates (one simulation on this rank's GPU, cluster resident)."""
+        return self.session().probe_sets([list(range(int(count)))], True)[0]
 
     def first_n_node_consolidation_option_sharded(self, rank=0, world=1, all_gather=None):
         """The same binary search with its probes sharded over ranks (consolidation probes are
         independent simulations). Each round evaluates, in parallel, every probe the sequential search could reach within
         the next log2(world+1) steps and then replays the sequential decisions on the gathered outcomes, so the command
         is identical to first_n_node_consolidation_option for any world size. `all_gather(obj) -> [obj per rank]`
-        (torch.distributed.all_gather_object wrapped by the caller); None = single process."""
+        (e.g. nccl_allgather_i32 on the verdicts; None = single process)."""
         n = self.candidates()
 
         def probe_many(counts):
@@ -339,6 +413,22 @@ class MultiNodeConsolidation:
 
         action, count, options, rounds, probes = speculative_binary_search(n, probe_many, world)
         return {"action": action, "nodes_removed": count, "options": options, "rounds": rounds, "probes": probes}
+
+
+class SingleNodeConsolidation:
+    """SingleNodeConsolidation.ComputeCommand (singlenodeconsolidation.go:43-84): the candidates in disruption order, the
+    first whose computeConsolidation yields delete / replace wins. The simulations are independent: a rank sweeps its share
+    `batch` simulations per device call."""
+
+    def __init__(self, problem: Problem):
+        self.problem = problem
+
+    def compute_command(self, first=0, last=-1, batch=64):
+        out4 = (C.c_int * 4)()
+        node = C.c_int()
+        opts = (C.c_int * 8192)()
+        _check(lib().kh_consolidate_single(self.problem.ptr, int(first), int(last), int(batch), out4, C.byref(node), opts, 8192))
+        return {"action": out4[0], "position": out4[1], "simulations": out4[2], "node": node.value, "options": list(opts[:out4[3]])}
 
 
 def speculation_frontier(lo, hi, width):

@@ -58,6 +58,7 @@ constexpr uint64_t kNoBest = ~0ull;
 }  // namespace
 
 #include "pack_kernel.cuh"
+#include "cluster.cuh"
 
 namespace {
 
@@ -157,6 +158,19 @@ struct ksched_handle {
   DevBuf<ksched_key_regions> d_key_regions;
   DevBuf<ksched_class_volumes> d_cls_vol;
   DevBuf<int32_t> d_cls_cursor;
+  // device-resident cluster snapshot (ksched_load_cluster)
+  bool have_cluster = false;
+  int sup_pods = 0, sup_pending = 0;
+  std::vector<int32_t> h_node_first, h_node_count;   // per existing slot: first superset pod bound to it, how many
+  DevBuf<int32_t> d_sup_pod_node, d_node_first, d_node_dst, d_set_nodes, d_pod_src;
+  DevBuf<uint32_t> d_sup_class, d_sup_uid, d_sim_types;
+  DevBuf<int64_t> d_sup_ts, d_sim_remaining;
+  DevBuf<uint8_t> d_in_set;
+  DevBuf<SimResultDev> d_sim_results;
+  DevBuf<uint8_t> d_gather_send, d_gather_recv;
+  DevBuf<int32_t> d_rk_off, d_rk_prio, d_rk_order, d_rk_n;
+  DevBuf<double> d_rk_dc, d_rk_age, d_rk_ttl, d_rk_cost_in, d_rk_cost, d_rk_cost_out;
+  DevBuf<uint8_t> d_rk_flags, d_rk_elig_in, d_rk_elig;
   DevBuf<ksched_node_volumes> d_ex_vol, d_ex_vol0;
   bool have_volumes = false;
   uint64_t vol_mask[KSCHED_MAX_VOLUME_DRIVERS] = {};
@@ -566,6 +580,24 @@ int ksched_nccl_init(ksched_handle* h, const void* id128, int rank, int world) {
   return KSCHED_OK;
 }
 
+// One ncclAllGather of `bytes` bytes per rank on the handle's communicator (consolidation: the verdicts of the simulations
+// each rank ran). Host buffers in and out; recv holds world * bytes.
+int ksched_allgather(ksched_handle* h, const void* send, size_t bytes, void* recv) {
+  if (!h || !send || !recv) return KSCHED_ERR_INVALID;
+  if (!h->comm) { h->err = "ksched_nccl_init must be called first"; return KSCHED_ERR_INVALID; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int world = 0;
+  if (ncclCommCount(h->comm, &world) != ncclSuccess) return KSCHED_ERR_NCCL;
+  CUDA_TRY(h, h->d_gather_send.ensure(std::max<size_t>(bytes, 1)));
+  CUDA_TRY(h, h->d_gather_recv.ensure(std::max<size_t>(bytes * (size_t)world, 1)));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_gather_send.ptr, send, bytes, cudaMemcpyHostToDevice, h->stream));
+  ncclResult_t r = ncclAllGather(h->d_gather_send.ptr, h->d_gather_recv.ptr, bytes, ncclUint8, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + ncclGetErrorString(r); return KSCHED_ERR_NCCL; }
+  CUDA_TRY(h, cudaMemcpyAsync(recv, h->d_gather_recv.ptr, bytes * (size_t)world, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return KSCHED_OK;
+}
+
 // ---- upload one problem (pods / nodes / topology) and keep pristine copies of everything the pack kernel mutates
 int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
   if (!h || !pb) return KSCHED_ERR_INVALID;
@@ -872,7 +904,7 @@ static int run_feasibility(ksched_handle* h) {
   return KSCHED_OK;
 }
 
-static int reset_state(ksched_handle* h) {
+static int reset_state(ksched_handle* h, const int64_t* d_remaining_src = nullptr) {
   const int P = h->n_pods, NE = std::max(h->n_existing, 1), NG = std::max(h->n_groups, 1);
   CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)P * 4, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_relax.ptr, 0, (size_t)std::max(P, 1) * 4, h->stream));
@@ -892,11 +924,15 @@ static int reset_state(ksched_handle* h) {
   CUDA_TRY(h, cudaMemsetAsync(h->d_grp_min_slot.ptr, 0, (size_t)NG * 4, h->stream));
   const size_t hs = (size_t)std::max(h->n_hostgroups, 1) * ((size_t)h->n_existing + h->max_new);
   CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host.ptr, h->d_grp_host0.ptr, hs * 2, cudaMemcpyDeviceToDevice, h->stream));
-  std::vector<int64_t> rem((size_t)h->cat.n_templates * KSCHED_MAX_RES);
-  for (int v = 0; v < h->cat.n_templates; ++v)
-    for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[(size_t)v * KSCHED_MAX_RES + r] = h->h_templates[v].remaining[r];
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, rem.data(), rem.size() * 8, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rem is a stack vector
+  if (d_remaining_src) {  // simulation on the cluster snapshot: limits with the removed nodes' capacity given back, already on the device
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, d_remaining_src, (size_t)h->cat.n_templates * KSCHED_MAX_RES * 8, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    std::vector<int64_t> rem((size_t)h->cat.n_templates * KSCHED_MAX_RES);
+    for (int v = 0; v < h->cat.n_templates; ++v)
+      for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[(size_t)v * KSCHED_MAX_RES + r] = h->h_templates[v].remaining[r];
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, rem.data(), rem.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rem is a stack vector
+  }
   CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 48 * sizeof(long long), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fc_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->d_fc_front_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
@@ -1040,14 +1076,8 @@ int ksched_run_feasibility_only(ksched_handle* h, int do_flush, float* elapsed_u
   return KSCHED_OK;
 }
 
-int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* res) {
-  if (!h || !pb || !res || !h->uploaded) return KSCHED_ERR_INVALID;
-  CUDA_TRY(h, cudaSetDevice(h->device));
-  const int P = h->n_pods, NE = h->n_existing, MAXN = h->max_new, W32 = h->cat.W32, W64 = h->W64, V = h->cat.n_templates;
-  long long counters[48];
-  CUDA_TRY(h, cudaMemcpyAsync(counters, h->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
 #ifdef KSCHED_PROFILE_PACK
+static void print_pack_profile(const long long* counters) {
   fprintf(stderr, "[pack profile] generic: topo=%lld existing=%lld eval=%lld commit=%lld fresh=%lld fail=%lld | fastblock=%lld genericcall=%lld | "
                   "n_generic=%lld inflight_placed=%lld fresh_steps=%lld failures=%lld paths[rej,cached,row,dyn,cachedempty]=%lld,%lld,%lld,%lld,%lld steps=%lld\n",
           counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[14], counters[15], counters[17], counters[18],
@@ -1057,6 +1087,18 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
   fprintf(stderr, "[pack profile] in-flight commit: winner+barrier=%lld record=%lld rest=%lld\n", counters[30], counters[31], counters[11]);
   fprintf(stderr, "[pack profile] class_run: calls=%lld pods=%lld bails=%lld ineligible=%lld cycles=%lld\n", counters[40], counters[41], counters[42], counters[43],
           counters[14]);
+}
+#endif
+
+int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* res) {
+  if (!h || !pb || !res || !h->uploaded) return KSCHED_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int P = h->n_pods, NE = h->n_existing, MAXN = h->max_new, W32 = h->cat.W32, W64 = h->W64, V = h->cat.n_templates;
+  long long counters[48];
+  CUDA_TRY(h, cudaMemcpyAsync(counters, h->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+#ifdef KSCHED_PROFILE_PACK
+  print_pack_profile(counters);
 #endif
   if (counters[4] != 0) {
     h->err = counters[4] == KSCHED_ERR_OVERFLOW ? "new-node capacity exceeded" : "a pod is constrained by more topology groups than the kernel supports";
@@ -1155,6 +1197,183 @@ int ksched_solve(ksched_handle* h, const ksched_problem* pb, ksched_result* res)
   h->tm.upload_us = std::chrono::duration<double, std::micro>(t1 - t0).count();
   h->tm.download_us = std::chrono::duration<double, std::micro>(t3 - t2).count();
   return rc;
+}
+
+// ---- consolidation simulator on a device-resident cluster snapshot (cluster.cuh)
+int ksched_load_cluster(ksched_handle* h, const ksched_cluster* cl) {
+  if (!h || !cl || !cl->problem || (!cl->pod_node && cl->problem->n_pods > 0)) return KSCHED_ERR_INVALID;
+  const ksched_problem* pb = cl->problem;
+  h->have_cluster = false;
+  if (pb->n_groups != 0) { h->err = "unsupported: topology groups on the cluster-snapshot path (simulate through ksched_solve)"; return KSCHED_ERR_UNSUPPORTED; }
+  const int P = pb->n_pods, NE = pb->n_existing;
+  // pods: the pending ones first, then node by node (every node's pods contiguous)
+  std::vector<int32_t> first((size_t)std::max(NE, 1), -1), count((size_t)std::max(NE, 1), 0);
+  int pending = 0;
+  for (int i = 0; i < P; ++i) {
+    const int nd = cl->pod_node[i];
+    if (nd >= NE) { h->err = "pod_node out of range"; return KSCHED_ERR_INVALID; }
+    if (nd < 0) { if (i != pending) { h->err = "pending pods must come first"; return KSCHED_ERR_INVALID; } ++pending; continue; }
+    if (first[nd] < 0) first[nd] = i;
+    else if (cl->pod_node[i - 1] != nd) { h->err = "the pods of one node must be contiguous"; return KSCHED_ERR_INVALID; }
+    ++count[nd];
+  }
+  int rc = ksched_upload(h, pb);  // the superset problem: buffers sized for the largest batch, existing-node state, class tables
+  if (rc != KSCHED_OK) return rc;
+  CUDA_TRY(h, upload(h, h->d_sup_pod_node, cl->pod_node, (size_t)P));
+  CUDA_TRY(h, upload(h, h->d_sup_class, pb->pod_class, (size_t)P));
+  CUDA_TRY(h, upload(h, h->d_sup_ts, pb->pod_timestamp, (size_t)P));
+  CUDA_TRY(h, upload(h, h->d_sup_uid, pb->pod_uid_rank, (size_t)P));
+  CUDA_TRY(h, upload_vec(h, h->d_node_first, first));
+  CUDA_TRY(h, h->d_node_dst.ensure((size_t)std::max(NE, 1)));
+  CUDA_TRY(h, h->d_in_set.ensure((size_t)std::max(NE, 1)));
+  CUDA_TRY(h, h->d_pod_src.ensure((size_t)std::max(P, 1)));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->h_node_first.swap(first);
+  h->h_node_count.swap(count);
+  h->sup_pods = P;
+  h->sup_pending = pending;
+  h->have_cluster = true;
+  return KSCHED_OK;
+}
+
+int ksched_simulate_batch(ksched_handle* h, const ksched_candidate_set* sets, int n_sets, ksched_sim_result* results, uint64_t* node0_types) {
+  if (!h || !sets || n_sets < 0 || (n_sets > 0 && !results)) return KSCHED_ERR_INVALID;
+  if (!h->have_cluster) { h->err = "ksched_load_cluster must be called first"; return KSCHED_ERR_INVALID; }
+  if (n_sets == 0) return KSCHED_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int NE = h->n_existing, V = h->cat.n_templates, W32 = h->cat.W32, W64 = h->W64;
+  // stage every set's node list, per-node batch offsets and limits in one upload each
+  std::vector<int32_t> all_nodes, all_dst((size_t)n_sets * std::max(NE, 1), 0), batch((size_t)n_sets, 0), node_off((size_t)n_sets + 1, 0);
+  std::vector<int64_t> all_rem((size_t)n_sets * V * KSCHED_MAX_RES, 0);
+  std::vector<uint8_t> seen((size_t)std::max(NE, 1), 0);
+  for (int q = 0; q < n_sets; ++q) {
+    const ksched_candidate_set& cs = sets[q];
+    if (cs.n_nodes < 0 || (cs.n_nodes > 0 && !cs.nodes)) { h->err = "bad candidate set"; return KSCHED_ERR_INVALID; }
+    std::vector<int32_t> nodes(cs.nodes, cs.nodes + cs.n_nodes);
+    std::sort(nodes.begin(), nodes.end());  // the batch lists the removed nodes' pods in slot order (the queue sorts them anyway, queue.go:35-110)
+    int pos = h->sup_pending;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      const int nd = nodes[i];
+      if (nd < 0 || nd >= NE || (i > 0 && nodes[i - 1] == nd)) { h->err = "candidate set: existing slot out of range or repeated"; return KSCHED_ERR_INVALID; }
+      all_dst[(size_t)q * NE + nd] = pos;
+      pos += h->h_node_count[(size_t)nd];
+    }
+    batch[(size_t)q] = pos;
+    all_nodes.insert(all_nodes.end(), nodes.begin(), nodes.end());
+    node_off[(size_t)q + 1] = (int32_t)all_nodes.size();
+    for (int v = 0; v < V; ++v)
+      for (int r = 0; r < KSCHED_MAX_RES; ++r)
+        all_rem[((size_t)q * V + v) * KSCHED_MAX_RES + r] = cs.remaining ? cs.remaining[(size_t)v * KSCHED_MAX_RES + r] : h->h_templates[(size_t)v].remaining[r];
+  }
+  (void)seen;
+  if (all_nodes.empty()) all_nodes.push_back(0);
+  CUDA_TRY(h, upload_vec(h, h->d_set_nodes, all_nodes));
+  CUDA_TRY(h, upload_vec(h, h->d_node_dst, all_dst));
+  CUDA_TRY(h, upload_vec(h, h->d_sim_remaining, all_rem));
+  CUDA_TRY(h, h->d_sim_results.ensure((size_t)n_sets));
+  CUDA_TRY(h, h->d_sim_types.ensure((size_t)n_sets * W32));
+  CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+  int rc = KSCHED_OK;
+  for (int q = 0; q < n_sets && rc == KSCHED_OK; ++q) {
+    const int n_nodes = node_off[(size_t)q + 1] - node_off[(size_t)q];
+    h->n_pods = batch[(size_t)q];
+    rc = reset_state(h, h->d_sim_remaining.ptr + (size_t)q * V * KSCHED_MAX_RES);
+    if (rc != KSCHED_OK) break;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_in_set.ptr, 0, (size_t)std::max(NE, 1), h->stream));
+    if (n_nodes > 0)
+      cluster_mark_kernel<<<(n_nodes + 255) / 256, 256, 0, h->stream>>>(h->d_set_nodes.ptr + node_off[(size_t)q], n_nodes, h->d_in_set.ptr, h->d_ex_closed.ptr);
+    if (h->sup_pods > 0)
+      cluster_select_kernel<<<(h->sup_pods + 255) / 256, 256, 0, h->stream>>>(h->sup_pods, h->d_sup_pod_node.ptr, h->d_in_set.ptr, h->d_node_dst.ptr + (size_t)q * NE,
+                                                                              h->d_node_first.ptr, h->sup_pending, h->d_sup_class.ptr, h->d_sup_ts.ptr, h->d_sup_uid.ptr,
+                                                                              h->d_pod_class0.ptr, h->d_ts.ptr, h->d_uid_rank.ptr, h->d_pod_src.ptr);
+    // the working copy of the pod classes (reset_state copied the previous batch's): refresh it from the new batch
+    if (h->n_pods > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)h->n_pods * 4, cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = run_sort(h)) != KSCHED_OK) break;
+    if ((rc = run_class_feasibility(h)) != KSCHED_OK) break;
+    if ((rc = run_feasibility(h)) != KSCHED_OK) break;
+    if ((rc = run_pack(h)) != KSCHED_OK) break;
+    cluster_collect_kernel<<<1, 64, 0, h->stream>>>(h->d_counters.ptr, h->n_pods, h->d_nn_tmpl.ptr, h->d_nn_count.ptr, h->d_nn_req.ptr, h->d_nn_req_present.ptr,
+                                                    h->d_nn_vals.ptr, h->d_nn_meta.ptr, h->d_nn_opts.ptr, h->max_new, W32, h->d_sim_results.ptr + q,
+                                                    h->d_sim_types.ptr + (size_t)q * W32);
+  }
+  h->n_pods = h->sup_pods;
+  if (rc != KSCHED_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[4], h->stream));
+#ifdef KSCHED_PROFILE_PACK
+  {
+    long long counters[48];
+    CUDA_TRY(h, cudaMemcpyAsync(counters, h->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    print_pack_profile(counters);  // the last simulation of the batch
+  }
+#endif
+  std::vector<SimResultDev> dev((size_t)n_sets);
+  std::vector<uint32_t> types((size_t)n_sets * W32);
+  CUDA_TRY(h, cudaMemcpyAsync(dev.data(), h->d_sim_results.ptr, dev.size() * sizeof(SimResultDev), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(types.data(), h->d_sim_types.ptr, types.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  h->tm.total_us = ev_us(h->ev[0], h->ev[4]);
+  for (int q = 0; q < n_sets; ++q) {
+    const SimResultDev& d = dev[(size_t)q];
+    ksched_sim_result& o = results[q];
+    std::memset(&o, 0, sizeof o);
+    o.n_pods = d.n_pods; o.n_unscheduled = d.n_unscheduled; o.n_new_nodes = d.n_new_nodes; o.error = d.error;
+    if (d.n_new_nodes >= 1) {
+      o.node0.template_index = d.template_index; o.node0.pod_count = d.pod_count; o.node0.requests_present = d.requests_present;
+      std::memcpy(o.node0.requests, d.requests, sizeof d.requests);
+      std::memcpy(o.node0.reqs.values, d.values, sizeof d.values);
+      o.node0.reqs.meta = d.meta;
+    }
+    if (node0_types) {
+      std::memset(node0_types + (size_t)q * W64, 0, (size_t)W64 * 8);
+      if (d.n_new_nodes >= 1) std::memcpy(node0_types + (size_t)q * W64, &types[(size_t)q * W32], (size_t)W32 * 4);
+    }
+  }
+  return KSCHED_OK;
+}
+
+int ksched_rank_candidates(ksched_handle* h, const ksched_rank_input* in, int32_t* order, double* cost, int32_t* n_candidates) {
+  if (!h || !in || !order || !cost || !n_candidates || in->n_nodes < 0 || in->n_pods < 0) return KSCHED_ERR_INVALID;
+  *n_candidates = 0;
+  const int N = in->n_nodes, NP = in->n_pods;
+  if (N == 0) return KSCHED_OK;
+  if (!in->node_eligible || (!in->node_cost && (!in->pod_offsets || !in->node_age_seconds || !in->node_ttl_seconds ||
+                                                (NP > 0 && (!in->pod_deletion_cost || !in->pod_priority || !in->pod_flags))))) return KSCHED_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, upload(h, h->d_rk_elig_in, in->node_eligible, (size_t)N));
+  if (in->node_cost) {
+    CUDA_TRY(h, upload(h, h->d_rk_cost_in, in->node_cost, (size_t)N));
+  } else {
+    CUDA_TRY(h, upload(h, h->d_rk_off, in->pod_offsets, (size_t)N + 1));
+    CUDA_TRY(h, upload(h, h->d_rk_age, in->node_age_seconds, (size_t)N));
+    CUDA_TRY(h, upload(h, h->d_rk_ttl, in->node_ttl_seconds, (size_t)N));
+    if (NP > 0) {
+      CUDA_TRY(h, upload(h, h->d_rk_dc, in->pod_deletion_cost, (size_t)NP));
+      CUDA_TRY(h, upload(h, h->d_rk_prio, in->pod_priority, (size_t)NP));
+      CUDA_TRY(h, upload(h, h->d_rk_flags, in->pod_flags, (size_t)NP));
+    }
+  }
+  CUDA_TRY(h, h->d_rk_cost.ensure((size_t)N));
+  CUDA_TRY(h, h->d_rk_cost_out.ensure((size_t)N));
+  CUDA_TRY(h, h->d_rk_elig.ensure((size_t)N));
+  CUDA_TRY(h, h->d_rk_order.ensure((size_t)N));
+  CUDA_TRY(h, h->d_rk_n.ensure(1));
+  const int blocks = (N + 255) / 256;
+  rank_cost_kernel<<<blocks, 256, 0, h->stream>>>(N, h->d_rk_off.ptr, h->d_rk_dc.ptr, h->d_rk_prio.ptr, h->d_rk_flags.ptr, h->d_rk_elig_in.ptr, h->d_rk_age.ptr,
+                                                  h->d_rk_ttl.ptr, in->node_cost ? h->d_rk_cost_in.ptr : nullptr, h->d_rk_cost.ptr, h->d_rk_elig.ptr);
+  rank_position_kernel<<<blocks, 256, 0, h->stream>>>(N, h->d_rk_cost.ptr, h->d_rk_elig.ptr, h->d_rk_order.ptr, h->d_rk_cost_out.ptr, h->d_rk_n.ptr);
+  CUDA_TRY(h, cudaGetLastError());
+  int32_t n = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&n, h->d_rk_n.ptr, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (n > 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(order, h->d_rk_order.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(cost, h->d_rk_cost_out.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  *n_candidates = n;
+  return KSCHED_OK;
 }
 
 int ksched_get_timings(const ksched_handle* h, ksched_timings* out) {

@@ -505,7 +505,7 @@ struct Group {
 
 }  // namespace
 
-std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candidates) {
+std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candidates, bool cluster_superset) {
   static const bool prof = std::getenv("KSCHED_ENCODE_PROFILE") != nullptr;
   auto t_last = std::chrono::steady_clock::now();
   auto phase = [&](const char* name) {
@@ -526,13 +526,25 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     std::set<int> cand(candidates.begin(), candidates.end());
     auto reschedulable = [](const Pod& p) { return !p.is_daemonset && !p.terminal && !p.terminating; };  // utils/node/node.go:30-50
     for (size_t i = 0; i < P.nodes.size(); ++i)
-      if (!cand.count((int)i) && !P.nodes[i].marked_for_deletion) state_nodes.push_back((int)i);
+      if ((cluster_superset || !cand.count((int)i)) && !P.nodes[i].marked_for_deletion) state_nodes.push_back((int)i);
     for (auto& p : P.pods) E.pods.push_back(&p);
-    for (int c : candidates)
-      for (auto& p : P.nodes.at(c).pods) if (reschedulable(p)) E.pods.push_back(&p);
-    for (size_t i = 0; i < P.nodes.size(); ++i)
-      if (!cand.count((int)i) && P.nodes[i].marked_for_deletion)
-        for (auto& p : P.nodes[i].pods) if (reschedulable(p)) E.pods.push_back(&p);
+    if (cluster_superset) {
+      // pending pods first (the pods of deleting nodes are pending in every simulation), then the candidates' pods node by node
+      for (size_t i = 0; i < P.nodes.size(); ++i)
+        if (!cand.count((int)i) && P.nodes[i].marked_for_deletion)
+          for (auto& p : P.nodes[i].pods) if (reschedulable(p)) E.pods.push_back(&p);
+      E.pod_node.assign(E.pods.size(), -1);
+      for (int c : candidates) {
+        if (P.nodes.at(c).marked_for_deletion) throw std::runtime_error("a candidate node is marked for deletion");
+        for (auto& p : P.nodes[c].pods) if (reschedulable(p)) { E.pods.push_back(&p); E.pod_node.push_back(-2 - c); }  // slot resolved below
+      }
+    } else {
+      for (int c : candidates)
+        for (auto& p : P.nodes.at(c).pods) if (reschedulable(p)) E.pods.push_back(&p);
+      for (size_t i = 0; i < P.nodes.size(); ++i)
+        if (!cand.count((int)i) && P.nodes[i].marked_for_deletion)
+          for (auto& p : P.nodes[i].pods) if (reschedulable(p)) E.pods.push_back(&p);
+    }
   }
   const size_t NP = E.pods.size();
   bool uids_ascending = true;  // strictly ascending UIDs (the usual case: one informer list) are unique and already ranked
@@ -990,12 +1002,29 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
       E.existing_volumes.push_back(nv);
     }
     E.existing.push_back(e);
+    int charged = -1;
+    int64_t charged_cap[KSCHED_MAX_RES] = {};
     for (int v = 0; v < NV; ++v)  // scheduler.go:244-246
       if (P.provisioners[E.template_provisioner[v]].name == own->second && E.templates[v].has_limits) {
         int64_t cap[KSCHED_MAX_RES];
         uint32_t present = B.fill_resources(n.capacity, cap);
         for (int r = 0; r < KSCHED_MAX_RES; ++r)
-          if ((E.templates[v].limit_present >> r) & 1 && (present >> r) & 1) E.templates[v].remaining[r] -= cap[r];
+          if ((E.templates[v].limit_present >> r) & 1 && (present >> r) & 1) { E.templates[v].remaining[r] -= cap[r]; charged_cap[r] = cap[r]; }
+        charged = v;
+      }
+    if (cluster_superset) {
+      E.existing_template.push_back(charged);
+      E.existing_capacity.insert(E.existing_capacity.end(), charged_cap, charged_cap + KSCHED_MAX_RES);
+    }
+  }
+  if (cluster_superset) {
+    std::map<int, int> slot_of_state;
+    for (size_t e = 0; e < E.existing_state_index.size(); ++e) slot_of_state[E.existing_state_index[e]] = (int)e;
+    for (auto& pn : E.pod_node)
+      if (pn <= -2) {
+        auto f = slot_of_state.find(-2 - pn);
+        if (f == slot_of_state.end()) throw std::runtime_error("a candidate node is not owned by a provisioner");
+        pn = f->second;
       }
   }
   const int NE = (int)E.existing.size();
@@ -1410,6 +1439,8 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   cat.key_regions = E.key_regions.empty() ? nullptr : E.key_regions.data();
   return enc;
 }
+
+bool label_selector_matches(const kmodel::LabelSelector& sel, const kmodel::Labels& labels) { return !sel.is_nil && selector_matches(sel, labels); }
 
 std::string render_requirement(const Encoded& E, const ksched_reqset& rs, int k) {
   static const ksched_bounds zero{};

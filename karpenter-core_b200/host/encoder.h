@@ -20,6 +20,9 @@ struct Encoded {
   // ---- which objects take part (provisioner.go:119-144 / deprovisioning/helpers.go:42-93)
   std::vector<const kmodel::Pod*> pods;               // Solve's pod list
   std::vector<int> existing_state_index;              // existing slot -> Problem.nodes index
+  std::vector<int32_t> pod_node;                      // cluster_superset: existing slot a batch pod is bound to, -1 = pending
+  std::vector<int64_t> existing_capacity;             // cluster_superset: [n_existing][KSCHED_MAX_RES] node capacity (limits bookkeeping)
+  std::vector<int32_t> existing_template;             // cluster_superset: template whose limits the node's capacity was charged to, or -1
   std::vector<bool> existing_initialized;
   std::vector<int> template_provisioner;              // template v -> Problem.provisioners index
   std::vector<int> type_input_index;                  // column -> Problem.instance_types index
@@ -60,7 +63,12 @@ struct Encoded {
 };
 
 // Throws std::runtime_error; messages starting with "unsupported:" map to KSCHED_ERR_UNSUPPORTED.
-std::unique_ptr<Encoded> encode(const kmodel::Problem& P, const std::vector<int>& candidates);
+// cluster_superset: the encoding ksched_load_cluster wants (ksched.h: ksched_cluster) - the candidates' pods form the batch as
+// usual but the candidate nodes STAY existing nodes, with all their pods bound; Encoded::pod_node says where each pod lives.
+std::unique_ptr<Encoded> encode(const kmodel::Problem& P, const std::vector<int>& candidates, bool cluster_superset = false);
+
+// metav1.LabelSelectorAsSelector(sel).Matches(labels); a nil selector matches nothing
+bool label_selector_matches(const kmodel::LabelSelector& sel, const kmodel::Labels& labels);
 
 // Render one requirement of a reqset the way the oracle's Requirement::Canonical() does ("In [a b]").
 std::string render_requirement(const Encoded& E, const ksched_reqset& rs, int key);

@@ -366,12 +366,83 @@ namespace {
 struct Cand { int node; const InstanceType* it; std::string ct, zone; double cost; };
 struct Cmd { int action = 0; std::vector<int> options; };
 
-std::vector<Cand> sorted_candidates(const Problem* P) {
-  std::vector<Cand> cands;
-  for (size_t i = 0; i < P->nodes.size(); ++i) {
+// candidateNodes + sortAndFilterCandidates (deprovisioning/helpers.go:171-249,339-366, consolidation.go:85-118). The string /
+// API-object side (labels, annotations, PDB selectors) is decided here; the disruption costs, their lifetime scaling and the
+// order come from the device (ksched_rank_candidates) - there is no host-side sort to fall back to.
+void rank_on_device(const Problem* P, std::vector<int>* order, std::vector<double>* cost) {
+  const size_t N = P->nodes.size();
+  order->clear();
+  cost->clear();
+  if (N == 0) return;
+  if (ensure_handle() != KSCHED_OK) throw std::runtime_error(g_err);
+  std::vector<uint8_t> eligible(N, 0), flags;
+  std::vector<int32_t> off(N + 1, 0), prio;
+  std::vector<double> dc, age(N, 0.0), ttl(N, -1.0), given(N, 0.0);
+  for (size_t i = 0; i < N; ++i) {
     const StateNode& n = P->nodes[i];
-    if (!n.candidate) continue;
-    Cand c{(int)i, nullptr, "", "", n.disruption_cost};
+    off[i] = (int32_t)flags.size();
+    if (!P->derive_candidates) {
+      eligible[i] = n.candidate ? 1 : 0;
+      given[i] = n.disruption_cost;
+      continue;
+    }
+    const Provisioner* prov = nullptr;
+    auto pl = n.labels.find("karpenter.sh/provisioner-name");
+    if (pl != n.labels.end())
+      for (auto& pr : P->provisioners) if (pr.name == pl->second) prov = &pr;
+    bool ok = !n.marked_for_deletion && prov != nullptr;                                  // helpers.go:186-192
+    if (ok) {
+      auto itn = n.labels.find("node.kubernetes.io/instance-type");                       // :194-198
+      bool it_ok = false;
+      if (itn != n.labels.end())
+        for (int idx : prov->instance_types) if (P->instance_types[(size_t)idx].name == itn->second) it_ok = true;
+      ok = it_ok;
+    }
+    ok = ok && n.labels.count("karpenter.sh/capacity-type") && n.labels.count("topology.kubernetes.io/zone");  // :201-208
+    if (ok) { auto ini = n.labels.find("karpenter.sh/initialized"); ok = ini != n.labels.end() && ini->second == "true"; }  // :211-213
+    ok = ok && !n.nominated;                                                              // :215-217
+    if (ok) ok = n.do_not_consolidate != 0 ? n.do_not_consolidate != 1 : prov->consolidation_enabled;  // consolidation.go:104-118
+    ok = ok && !n.deleting;                                                               // canBeTerminated helpers.go:340
+    eligible[i] = ok ? 1 : 0;
+    if (prov && prov->has_ttl_until_expired) { ttl[i] = (double)prov->ttl_seconds_until_expired; age[i] = P->now_ts - n.creation_ts; }
+    for (auto& p : n.pods) {
+      uint8_t f = 0;
+      if (p.has_deletion_cost) f |= KSCHED_RANK_HAS_DELETION_COST;
+      if (p.has_priority) f |= KSCHED_RANK_HAS_PRIORITY;
+      bool blocks = false;
+      for (auto& b : P->pdbs)                                                             // CanEvictPods pdblimits.go:55-68
+        if (b.ns == p.ns && b.disruptions_allowed == 0 && khost::label_selector_matches(b.selector, p.labels)) blocks = true;
+      if (!(p.terminating || p.terminal || p.owned_by_node) && p.do_not_evict) blocks = true;  // PodsPreventEviction helpers.go:354-366
+      if (blocks) f |= KSCHED_RANK_BLOCKS_EVICTION;
+      flags.push_back(f);
+      dc.push_back(p.deletion_cost);
+      prio.push_back(p.priority);
+    }
+  }
+  off[N] = (int32_t)flags.size();
+  ksched_rank_input in{};
+  in.n_nodes = (int32_t)N;
+  in.n_pods = (int32_t)flags.size();
+  in.pod_offsets = off.data(); in.pod_deletion_cost = dc.data(); in.pod_priority = prio.data(); in.pod_flags = flags.data();
+  in.node_eligible = eligible.data(); in.node_age_seconds = age.data(); in.node_ttl_seconds = ttl.data();
+  in.node_cost = P->derive_candidates ? nullptr : given.data();
+  std::vector<int32_t> ord(N);
+  std::vector<double> cst(N);
+  int32_t n = 0;
+  int rc = ksched_rank_candidates(g_handle, &in, ord.data(), cst.data(), &n);
+  if (rc != KSCHED_OK) throw std::runtime_error(ksched_last_error(g_handle));
+  order->assign(ord.begin(), ord.begin() + n);
+  cost->assign(cst.begin(), cst.begin() + n);
+}
+
+std::vector<Cand> sorted_candidates(const Problem* P) {
+  std::vector<int> order;
+  std::vector<double> cost;
+  rank_on_device(P, &order, &cost);
+  std::vector<Cand> cands;
+  for (size_t q = 0; q < order.size(); ++q) {
+    const StateNode& n = P->nodes[(size_t)order[q]];
+    Cand c{order[q], nullptr, "", "", cost[q]};
     auto itn = n.labels.find("node.kubernetes.io/instance-type");
     if (itn != n.labels.end())
       for (auto& t : P->instance_types) if (t.name == itn->second) c.it = &t;
@@ -381,58 +452,45 @@ std::vector<Cand> sorted_candidates(const Problem* P) {
     if (z != n.labels.end()) c.zone = z->second;
     cands.push_back(c);
   }
-  std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.cost < b.cost; });  // consolidation.go:100-103
   return cands;
 }
 
-// computeConsolidation (consolidation.go:190-274) + filterOutSameType (multinodeconsolidation.go:132-165) for the
-// first `count` candidates: one simulateScheduling = one ksched_solve.
-Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int count) {
+// computeConsolidation after the simulation (consolidation.go:206-274) + the multi-node caller's filterOutSameType
+// (multinodeconsolidation.go:132-165, `multi`): sel = the candidates being removed, node0 / bits = the single new node.
+Cmd finish_command(const Problem* P, const Encoded& E, const std::vector<Cand>& sel, bool all_scheduled, int n_new, const ksched_reqset& node0_reqs,
+                   const uint64_t* bits, bool multi) {
   Cmd cmd;
-  std::vector<int> nodes;
-  for (int i = 0; i < count; ++i) nodes.push_back(cands[i].node);
-  auto E = khost::encode(*P, nodes);
-  E->problem.count_nodes_visited = g_count_visited;
-  ResultBuffers B;
-  int rc = solve_encoded(*E, B, false);
-  if (rc != KSCHED_OK) throw std::runtime_error(g_err);
-  size_t scheduled = 0;
-  for (auto a : B.assign) if (a >= 0) ++scheduled;
-  // helpers.go:109-113 walks EVERY ExistingNode Solve returns (all owned nodes that are neither candidates nor marked for
-  // deletion) and gives up when one of them is not initialised - whether or not a pod landed on it
-  for (size_t e = 0; e < E->existing.size(); ++e)
-    if (!E->existing_initialized[e]) return cmd;
-  if (scheduled != E->pods.size()) return cmd;
-  if (B.r.n_new_nodes == 0) { cmd.action = 1; return cmd; }
-  if (B.r.n_new_nodes != 1) return cmd;
+  const int count = (int)sel.size();
+  if (!all_scheduled) return cmd;
+  if (n_new == 0) { cmd.action = 1; return cmd; }
+  if (n_new != 1) return cmd;
   double price = 0;  // getNodePrices consolidation.go:277-287
   for (int i = 0; i < count; ++i) {
-    const Cand& c = cands[i];
+    const Cand& c = sel[i];
     if (!c.it) throw std::runtime_error("candidate without a known instance type");
     bool ok = false;
     for (auto& o : c.it->offerings) if (o.capacity_type == c.ct && o.zone == c.zone) { price += o.price; ok = true; break; }
     if (!ok) throw std::runtime_error("unable to determine offering");
   }
-  ksched_reqset reqs = B.nodes[0].reqs;
+  ksched_reqset reqs = node0_reqs;
   std::vector<int> opts;
-  const uint64_t* bits = &B.types[0];
-  for (size_t c = 0; c < E->type_input_index.size(); ++c)
-    if ((bits[c / 64] >> (c % 64)) & 1) opts.push_back(E->type_input_index[c]);
+  for (size_t c = 0; c < E.type_input_index.size(); ++c)
+    if ((bits[c / 64] >> (c % 64)) & 1) opts.push_back(E.type_input_index[c]);
   std::sort(opts.begin(), opts.end());
   std::vector<int> kept;
-  for (int t : opts) if (worst_launch_price(*E, P->instance_types[t], reqs) < price) kept.push_back(t);  // filterByPrice
+  for (int t : opts) if (worst_launch_price(E, P->instance_types[t], reqs) < price) kept.push_back(t);  // filterByPrice
   if (kept.empty()) return cmd;
   bool all_spot = true;
-  for (int i = 0; i < count; ++i) if (cands[i].ct != "spot") all_spot = false;
-  if (all_spot && req_has(*E, reqs, "karpenter.sh/capacity-type", "spot")) return cmd;
+  for (int i = 0; i < count; ++i) if (sel[i].ct != "spot") all_spot = false;
+  if (all_spot && req_has(E, reqs, "karpenter.sh/capacity-type", "spot")) return cmd;
   bool spot_only = false;
-  if (req_has(*E, reqs, "karpenter.sh/capacity-type", "spot") && req_has(*E, reqs, "karpenter.sh/capacity-type", "on-demand")) {
+  if (req_has(E, reqs, "karpenter.sh/capacity-type", "spot") && req_has(E, reqs, "karpenter.sh/capacity-type", "on-demand")) {
     spot_only = true;
     // Requirements.Add(capacity-type In [spot]) (consolidation.go:262-265)
-    for (size_t k = 0; k < E->key_names.size(); ++k) {
-      if (E->key_names[k] != "karpenter.sh/capacity-type") continue;
+    for (size_t k = 0; k < E.key_names.size(); ++k) {
+      if (E.key_names[k] != "karpenter.sh/capacity-type") continue;
       uint64_t spot = 0;
-      for (size_t b = 0; b < E->key_values[k].size(); ++b) if (E->key_values[k][b] == "spot") spot = 1ull << b;
+      for (size_t b = 0; b < E.key_values[k].size(); ++b) if (E.key_values[k][b] == "spot") spot = 1ull << b;
       ksched::Req in{spot, 0, 0, true, false, false, false};
       static const ksched_bounds zero{};
       ksched::KeyMeta km{0, nullptr, nullptr};
@@ -440,10 +498,15 @@ Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int 
       ksched::req_store(reqs, &tmp, (int)k, ksched::key_add(ksched::req_load(reqs, &zero, (int)k), in, km));
     }
   }
+  if (!multi) {  // single-node consolidation takes computeConsolidation's command as it is (singlenodeconsolidation.go:56-76)
+    cmd.action = 2;
+    cmd.options = kept;
+    return cmd;
+  }
   std::set<std::string> existing_types;  // filterOutSameType
   std::map<std::string, double> by_type;
   for (int i = 0; i < count; ++i) {
-    const Cand& c = cands[i];
+    const Cand& c = sel[i];
     existing_types.insert(c.it->name);
     for (auto& o : c.it->offerings)
       if (o.capacity_type == c.ct && o.zone == c.zone) {
@@ -458,25 +521,179 @@ Cmd compute_consolidation(const Problem* P, const std::vector<Cand>& cands, int 
     if (existing_types.count(name) && by_type[name] < max_price) max_price = by_type[name];
   }
   std::vector<int> kept2;
-  for (int t : kept) if (worst_launch_price(*E, P->instance_types[t], reqs, spot_only) < max_price) kept2.push_back(t);
+  for (int t : kept) if (worst_launch_price(E, P->instance_types[t], reqs, spot_only) < max_price) kept2.push_back(t);
   if (kept2.empty()) return cmd;
   cmd.action = 2;
   cmd.options = kept2;
   return cmd;
 }
+
+// One simulateScheduling = one ksched_solve of a freshly encoded problem (the path for clusters the snapshot cannot hold).
+Cmd compute_consolidation_encoded(const Problem* P, const std::vector<Cand>& sel, bool multi) {
+  std::vector<int> nodes;
+  for (auto& c : sel) nodes.push_back(c.node);
+  auto E = khost::encode(*P, nodes);
+  E->problem.count_nodes_visited = g_count_visited;
+  ResultBuffers B;
+  int rc = solve_encoded(*E, B, false);
+  if (rc != KSCHED_OK) throw std::runtime_error(g_err);
+  size_t scheduled = 0;
+  for (auto a : B.assign) if (a >= 0) ++scheduled;
+  // helpers.go:109-113 walks EVERY ExistingNode Solve returns (all owned nodes that are neither candidates nor marked for
+  // deletion) and gives up when one of them is not initialised - whether or not a pod landed on it
+  for (size_t e = 0; e < E->existing.size(); ++e)
+    if (!E->existing_initialized[e]) return Cmd();
+  return finish_command(P, *E, sel, scheduled == E->pods.size(), B.r.n_new_nodes, B.nodes[0].reqs, &B.types[0], multi);
+}
+
+// The consolidation pass over one cluster: candidates ranked once, the cluster resident on the device once
+// (ksched_load_cluster), every computeConsolidation a ksched_simulate_batch entry. Clusters the snapshot cannot hold
+// (topology groups) are simulated one freshly encoded ksched_solve at a time - still on the GPU, never on the CPU.
+struct ClusterSession {
+  const Problem* P = nullptr;
+  std::vector<Cand> cands;            // disruption order
+  std::unique_ptr<Encoded> E;         // superset encoding (resident == true)
+  std::vector<int> slot_of_node;      // Problem.nodes index -> existing slot
+  bool resident = false;
+  int simulations = 0;
+
+  explicit ClusterSession(const Problem* p) : P(p), cands(sorted_candidates(p)) {
+    if (ensure_handle() != KSCHED_OK) throw std::runtime_error(g_err);
+    std::vector<int> nodes;
+    for (auto& c : cands) nodes.push_back(c.node);
+    auto sup = khost::encode(*P, nodes, true);
+    sup->problem.count_nodes_visited = 0;
+    int rc = ksched_load_catalog(g_handle, &sup->catalog);
+    if (rc != KSCHED_OK) throw std::runtime_error(ksched_last_error(g_handle));
+    ksched_cluster cl{&sup->problem, sup->pod_node.data()};
+    rc = ksched_load_cluster(g_handle, &cl);
+    if (rc == KSCHED_ERR_UNSUPPORTED) return;  // resident stays false
+    if (rc != KSCHED_OK) throw std::runtime_error(ksched_last_error(g_handle));
+    E = std::move(sup);
+    slot_of_node.assign(P->nodes.size(), -1);
+    for (size_t e = 0; e < E->existing_state_index.size(); ++e) slot_of_node[(size_t)E->existing_state_index[e]] = (int)e;
+    resident = true;
+  }
+
+  // computeConsolidation for every set (positions in the disruption order), one ksched_simulate_batch call
+  std::vector<Cmd> compute_many(const std::vector<std::vector<int>>& sets, bool multi) {
+    std::vector<Cmd> out(sets.size());
+    simulations += (int)sets.size();
+    if (!resident) {
+      for (size_t q = 0; q < sets.size(); ++q) {
+        std::vector<Cand> sel;
+        for (int i : sets[q]) sel.push_back(cands.at((size_t)i));
+        out[q] = compute_consolidation_encoded(P, sel, multi);
+      }
+      return out;
+    }
+    const size_t NE = E->existing.size(), V = E->templates.size();
+    std::vector<std::vector<int32_t>> slots(sets.size());
+    std::vector<std::vector<int64_t>> rem(sets.size());
+    std::vector<ksched_candidate_set> cs(sets.size());
+    std::vector<char> skip(sets.size(), 0);
+    std::vector<char> removed(NE);
+    for (size_t q = 0; q < sets.size(); ++q) {
+      std::fill(removed.begin(), removed.end(), 0);
+      rem[q].resize(V * KSCHED_MAX_RES);
+      for (size_t v = 0; v < V; ++v) for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[q][v * KSCHED_MAX_RES + r] = E->templates[v].remaining[r];
+      for (int i : sets[q]) {
+        const int e = slot_of_node.at((size_t)cands.at((size_t)i).node);
+        if (e < 0) throw std::runtime_error("candidate is not an existing node of the snapshot");
+        slots[q].push_back(e);
+        removed[(size_t)e] = 1;
+        const int v = E->existing_template[(size_t)e];  // scheduler.go:221-248 only charges the nodes that stay
+        if (v >= 0) for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[q][(size_t)v * KSCHED_MAX_RES + r] += E->existing_capacity[(size_t)e * KSCHED_MAX_RES + r];
+      }
+      // helpers.go:109-113: an uninitialised node among those that stay ends the simulation with "do nothing"
+      for (size_t e = 0; e < NE; ++e) if (!removed[e] && !E->existing_initialized[e]) skip[q] = 1;
+      cs[q] = ksched_candidate_set{slots[q].data(), (int32_t)slots[q].size(), 0, rem[q].data()};
+    }
+    std::vector<ksched_sim_result> res(sets.size());
+    std::vector<uint64_t> types(sets.size() * (size_t)E->type_words);
+    int rc = ksched_simulate_batch(g_handle, cs.data(), (int)cs.size(), res.data(), types.data());
+    if (rc != KSCHED_OK) throw std::runtime_error(ksched_last_error(g_handle));
+    for (size_t q = 0; q < sets.size(); ++q) {
+      if (skip[q]) continue;
+      if (res[q].error) throw std::runtime_error("simulation failed on the device");
+      std::vector<Cand> sel;
+      for (int i : sets[q]) sel.push_back(cands[(size_t)i]);
+      out[q] = finish_command(P, *E, sel, res[q].n_unscheduled == 0, res[q].n_new_nodes, res[q].node0.reqs, &types[q * (size_t)E->type_words], multi);
+    }
+    return out;
+  }
+  Cmd compute_prefix(int count) {
+    std::vector<int> set;
+    for (int i = 0; i < count; ++i) set.push_back(i);
+    return compute_many({set}, true)[0];
+  }
+};
 }  // namespace
 
 extern "C" {
-// number of consolidation candidates (nodes flagged `candidate`)
-int kh_consolidate_candidates(const Problem* P) { return (int)sorted_candidates(P).size(); }
+// number of consolidation candidates
+int kh_consolidate_candidates(const Problem* P) {
+  try { return (int)sorted_candidates(P).size(); } catch (const std::exception& e) { return fail(error_code(e), e.what()); }
+}
+// candidate ranking on the device: order = Problem.nodes indices by disruption cost, cost parallel; returns their number
+int kh_rank_candidates(const Problem* P, int* order, double* cost, int cap) {
+  try {
+    std::vector<int> o;
+    std::vector<double> c;
+    rank_on_device(P, &o, &c);
+    for (size_t i = 0; i < o.size() && (int)i < cap; ++i) { order[i] = o[i]; cost[i] = c[i]; }
+    return (int)o.size();
+  } catch (const std::exception& e) {
+    return fail(error_code(e), e.what());
+  }
+}
 
-// One probe of the search: computeConsolidation over the `count` cheapest-to-disrupt candidates.
+// A consolidation pass over one cluster (ClusterSession): open once, probe many times, close. The session keeps the
+// cluster resident on the device (ksched_load_cluster); `resident` tells whether the snapshot path took it.
+ClusterSession* kh_cluster_open(const Problem* P, int* resident, int* n_candidates) {
+  try {
+    auto* cs = new ClusterSession(P);
+    if (resident) *resident = cs->resident ? 1 : 0;
+    if (n_candidates) *n_candidates = (int)cs->cands.size();
+    return cs;
+  } catch (const std::exception& e) {
+    fail(error_code(e), e.what());
+    return nullptr;
+  }
+}
+void kh_cluster_close(ClusterSession* cs) { delete cs; }
+// computeConsolidation for n_sets candidate sets in ONE ksched_simulate_batch call. sets = positions in the disruption order,
+// set q = sets[set_off[q] .. set_off[q+1]); multi = apply the multi-node caller's filterOutSameType.
+// actions[q] = 0 / 1 / 2; options of set q are written to options[q * options_stride ...], n_options[q] of them.
+int kh_cluster_probe_sets(ClusterSession* cs, const int* sets, const int* set_off, int n_sets, int multi, int* actions, int* options, int options_stride,
+                          int* n_options) {
+  try {
+    std::vector<std::vector<int>> v((size_t)n_sets);
+    for (int q = 0; q < n_sets; ++q) v[(size_t)q].assign(sets + set_off[q], sets + set_off[q + 1]);
+    auto cmds = cs->compute_many(v, multi != 0);
+    for (int q = 0; q < n_sets; ++q) {
+      actions[q] = cmds[(size_t)q].action;
+      n_options[q] = (int)cmds[(size_t)q].options.size();
+      for (size_t i = 0; i < cmds[(size_t)q].options.size() && (int)i < options_stride; ++i) options[(size_t)q * options_stride + i] = cmds[(size_t)q].options[i];
+    }
+    return KSCHED_OK;
+  } catch (const std::exception& e) {
+    return fail(error_code(e), e.what());
+  }
+}
+// disruption order of the session's candidates (Problem.nodes indices)
+int kh_cluster_candidates(const ClusterSession* cs, int* nodes, int cap) {
+  for (size_t i = 0; i < cs->cands.size() && (int)i < cap; ++i) nodes[i] = cs->cands[i].node;
+  return (int)cs->cands.size();
+}
+
+// One probe of the multi-node search: computeConsolidation over the `count` cheapest-to-disrupt candidates.
 // Returns the action (0 nothing, 1 delete, 2 replace) or a negative error; options = surviving replacement types.
 int kh_consolidate_probe(const Problem* P, int count, int* options, int options_cap, int* n_options) {
   try {
-    auto cands = sorted_candidates(P);
-    if (count < 1 || count > (int)cands.size()) return fail(KSCHED_ERR_INVALID, "probe size out of range");
-    Cmd c = compute_consolidation(P, cands, count);
+    ClusterSession cs(P);
+    if (count < 1 || count > (int)cs.cands.size()) return fail(KSCHED_ERR_INVALID, "probe size out of range");
+    Cmd c = cs.compute_prefix(count);
     *n_options = (int)c.options.size();
     for (size_t i = 0; i < c.options.size() && (int)i < options_cap; ++i) options[i] = c.options[i];
     return c.action;
@@ -489,16 +706,16 @@ int kh_consolidate_probe(const Problem* P, int count, int* options, int options_
 // out ints: [action, nodes_removed, simulations, n_options]; options = instance type indices.
 int kh_consolidate(const Problem* P, int* out4, int* options, int options_cap, int* probes, int* probe_actions, int probes_cap, int* n_probes) {
   try {
-    auto cands = sorted_candidates(P);
+    ClusterSession cs(P);
     int sims = 0;
     out4[0] = out4[1] = out4[2] = out4[3] = 0;
     *n_probes = 0;
-    if (cands.size() < 2) return KSCHED_OK;
-    int mn = 1, mx = (int)cands.size() - 1, last_count = 0;
+    if (cs.cands.size() < 2) return KSCHED_OK;
+    int mn = 1, mx = (int)cs.cands.size() - 1, last_count = 0;
     Cmd last;
     while (mn <= mx) {
       int mid = (mn + mx) / 2;
-      Cmd c = compute_consolidation(P, cands, mid + 1);
+      Cmd c = cs.compute_prefix(mid + 1);
       ++sims;
       if (*n_probes < probes_cap) { probes[*n_probes] = mid + 1; probe_actions[*n_probes] = c.action; }
       ++*n_probes;
@@ -510,6 +727,58 @@ int kh_consolidate(const Problem* P, int* out4, int* options, int options_cap, i
     out4[2] = sims;
     out4[3] = (int)last.options.size();
     for (size_t i = 0; i < last.options.size() && (int)i < options_cap; ++i) options[i] = last.options[i];
+    return KSCHED_OK;
+  } catch (const std::exception& e) {
+    return fail(error_code(e), e.what());
+  }
+}
+
+// ncclAllGather of n ints per rank on the scheduler handle's communicator (kh_nccl_init first)
+int kh_allgather_i32(const int* send, int n, int* recv) {
+  int rc = ensure_handle();
+  if (rc != KSCHED_OK) return rc;
+  rc = ksched_allgather(g_handle, send, (size_t)n * sizeof(int), recv);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  return KSCHED_OK;
+}
+// communicator for the scheduler handle without column sharding (replicas / sharded consolidation)
+int kh_nccl_init(const void* id128, int rank, int world) {
+  int rc = ensure_handle();
+  if (rc != KSCHED_OK) return rc;
+  rc = ksched_nccl_init(g_handle, id128, rank, world);
+  if (rc == KSCHED_OK) rc = ksched_set_shard(g_handle, 0, 1);
+  if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
+  return KSCHED_OK;
+}
+
+// SingleNodeConsolidation.ComputeCommand (singlenodeconsolidation.go:43-84): the candidates in disruption order, the first
+// whose computeConsolidation yields delete / replace wins (Validation is taken as valid: it re-runs the same simulation
+// after a TTL). The independent simulations go to the device `batch` at a time (ksched_simulate_batch).
+// out4: [action, position of the winning candidate in the disruption order or -1, simulations, n_options]; *node = its
+// Problem.nodes index. first / last bound the positions tried (a rank's share of the sweep); last < 0 = all.
+int kh_consolidate_single(const Problem* P, int first, int last, int batch, int* out4, int* node, int* options, int options_cap) {
+  try {
+    ClusterSession cs(P);
+    out4[0] = 0; out4[1] = -1; out4[2] = 0; out4[3] = 0;
+    *node = -1;
+    const int n = (int)cs.cands.size();
+    if (last < 0 || last > n) last = n;
+    if (batch < 1) batch = 1;
+    for (int b = std::max(first, 0); b < last; b += batch) {
+      std::vector<std::vector<int>> sets;
+      for (int i = b; i < std::min(last, b + batch); ++i) sets.push_back({i});
+      auto cmds = cs.compute_many(sets, false);
+      out4[2] += (int)sets.size();
+      for (size_t q = 0; q < cmds.size(); ++q)
+        if (cmds[q].action == 1 || cmds[q].action == 2) {
+          out4[0] = cmds[q].action;
+          out4[1] = b + (int)q;
+          out4[3] = (int)cmds[q].options.size();
+          *node = cs.cands[(size_t)(b + (int)q)].node;
+          for (size_t i = 0; i < cmds[q].options.size() && (int)i < options_cap; ++i) options[i] = cmds[q].options[i];
+          return KSCHED_OK;
+        }
+    }
     return KSCHED_OK;
   } catch (const std::exception& e) {
     return fail(error_code(e), e.what());

@@ -16,5 +16,10 @@ for count in [int(x) for x in os.environ.get("KS_PROBES", "2501,1251,626,313,400
     out.append({"count": count, "action": r[0], "n_options": len(r[1]), "wall_ms": round(dt * 1e3, 2),
                 **{kk: round(v / 1e3, 3) for kk, v in tm.items() if kk.endswith("_us")}})
     print(json.dumps(out[-1]), flush=True)
+t0 = time.perf_counter(); sn = k.SingleNodeConsolidation(p).compute_command(batch=64); dt = time.perf_counter() - t0
+print(json.dumps({"single_node_s": round(dt, 3), **{kk: v for kk, v in sn.items() if kk != "options"}}), flush=True)
+cs = mnc.session()
+t0 = time.perf_counter(); sw = cs.probe_sets([[i] for i in range(min(512, cs.n_candidates))], False); dt = time.perf_counter() - t0
+print(json.dumps({"single_node_sweep_512_s": round(dt, 3), "hits": sum(1 for a, _ in sw if a)}), flush=True)
 t0 = time.perf_counter(); full = mnc.first_n_node_consolidation_option(); dt = time.perf_counter() - t0
 print(json.dumps({"search_s": round(dt, 3), **{kk: v for kk, v in full.items() if kk != "options"}, "n_options": len(full["options"])}), flush=True)

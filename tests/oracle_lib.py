@@ -25,6 +25,26 @@ class Oracle:
                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                            C.POINTER(C.c_int), C.c_char_p, C.c_int]
 
+        lib.oracle_consolidate_single.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
+                                                  C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        lib.oracle_rank_candidates.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int]
+
+    def consolidate_single(self, problem, only_candidate=-1):
+        """SingleNodeConsolidation.ComputeCommand -> {action, node, options, simulations}; only_candidate = one position"""
+        node, nopt, npr = C.c_int(), C.c_int(), C.c_int()
+        opts = (C.c_int * 8192)()
+        err = C.create_string_buffer(1024)
+        action = self.lib.oracle_consolidate_single(problem.ptr, int(only_candidate), C.byref(node), opts, 8192, C.byref(nopt), C.byref(npr), err, 1024)
+        if action < 0:
+            raise RuntimeError(err.value.decode())
+        return {"action": action, "node": node.value, "options": list(opts[:nopt.value]), "simulations": npr.value}
+
+    def rank_candidates(self, problem, cap=65536):
+        order = (C.c_int * cap)()
+        cost = (C.c_double * cap)()
+        n = self.lib.oracle_rank_candidates(problem.ptr, order, cost, cap)
+        return list(order[:n]), list(cost[:n])
+
     def _s(self, fn, *args):
         buf = C.create_string_buffer(4096)
         n = fn(*[a.encode() if isinstance(a, str) else a for a in args], buf, 4096)
