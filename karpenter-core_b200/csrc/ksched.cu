@@ -160,6 +160,7 @@ struct ksched_handle {
   DevBuf<int32_t> d_cls_cursor;
   // device-resident cluster snapshot (ksched_load_cluster)
   bool have_cluster = false;
+  int stop_new_nodes = 0;
   int sup_pods = 0, sup_pending = 0;
   std::vector<int32_t> h_node_first, h_node_count;   // per existing slot: first superset pod bound to it, how many
   DevBuf<int32_t> d_sup_pod_node, d_node_first, d_node_dst, d_set_nodes, d_pod_src;
@@ -974,6 +975,7 @@ static int run_pack(ksched_handle* h) {
   s.fd_cap = kFreshMemoSlots; s.fd_state = h->d_fd_state.ptr; s.fd_fc = h->d_fd_fc.ptr; s.fd_meta = h->d_fd_meta.ptr; s.fd_vals = h->d_fd_vals.ptr;
   s.fd_opts = h->d_fd_opts.ptr; s.fd_bound = h->d_fd_bound.ptr; s.fd_bound2 = h->d_fd_bound2.ptr; s.fd_dom = h->d_fd_dom.ptr;
   s.count_visited = h->count_visited;
+  s.stop_new_nodes = h->stop_new_nodes;
   s.grp_cnt = h->d_grp_cnt.ptr; s.grp_registered = h->d_grp_registered.ptr; s.grp_host = h->d_grp_host.ptr;
   s.grp_host_row = h->d_grp_host_row.ptr; s.grp_host_total = h->d_grp_host_total.ptr; s.remaining = h->d_remaining.ptr;
   s.grp_active = h->d_grp_active.ptr; s.grp_min_slot = h->d_grp_min_slot.ptr;
@@ -1274,6 +1276,9 @@ int ksched_simulate_batch(ksched_handle* h, const ksched_candidate_set* sets, in
   CUDA_TRY(h, h->d_sim_types.ensure((size_t)n_sets * W32));
   CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
   int rc = KSCHED_OK;
+  // nothing computeConsolidation can return depends on what happens after a second new node is opened
+  // (consolidation.go:214-224: len(newNodes) != 1 -> do nothing): the simulation stops there
+  h->stop_new_nodes = 2;
   for (int q = 0; q < n_sets && rc == KSCHED_OK; ++q) {
     const int n_nodes = node_off[(size_t)q + 1] - node_off[(size_t)q];
     h->n_pods = batch[(size_t)q];
@@ -1297,6 +1302,7 @@ int ksched_simulate_batch(ksched_handle* h, const ksched_candidate_set* sets, in
                                                     h->d_sim_types.ptr + (size_t)q * W32);
   }
   h->n_pods = h->sup_pods;
+  h->stop_new_nodes = 0;
   if (rc != KSCHED_OK) return rc;
   CUDA_TRY(h, cudaEventRecord(h->ev[4], h->stream));
 #ifdef KSCHED_PROFILE_PACK

@@ -323,6 +323,108 @@ struct LoopVars {
   uint32_t fresh_cls;
 };
 
+// ---- existing-node run ("water-fill") --------------------------------------------------------------------------------
+// A run of consecutive first-pass pods of ONE plain class (no requirement key, no topology relation, no host port, no
+// volume, no instance-type / hostname requirement) is placed on the existing nodes in one pass. First fit over existing
+// nodes in slice order (scheduler.go:176-180) sends identical pods to the first node that still fits one, until it does not:
+// node e takes K_e = min over requested resources of floor((available - requests) / request) of them, so the run is an
+// exclusive prefix sum of K over the nodes from the class's cursor on. Every effect of the sequential commits is reproduced
+// (requests, closed flag, assign, place_seq); what the existing nodes cannot take is left to the generic step.
+constexpr int kExRunMax = 1 << 20;
+__device__ __forceinline__ bool class_has_volumes(const PackState& s, unsigned cls) {
+  if (!s.cls_vol) return false;
+  const ksched_class_volumes v = s.cls_vol[cls];
+  return (v.shared | v.priv[0] | v.priv[1] | v.priv[2] | v.priv[3]) != 0;
+}
+struct ExRunIO { int qi, head, qlen, seq, parity, placed; long long add_calls; };
+__shared__ ExRunIO g_xio;
+__shared__ int g_xscan[2][8];
+__device__ __forceinline__ int block_scan_incl(int v, int* total, int& xpar) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  int* buf = g_xscan[xpar];
+  xpar ^= 1;
+  if (lane == 31) buf[warp] = x;
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) { const int t = buf[w]; if (w < warp) base += t; tot += t; }
+  *total = tot;
+  return x + base;
+}
+__device__ __noinline__ void existing_run(const PodRegs& first) {
+  KS_K2
+  const int tid = threadIdx.x, T = blockDim.x, NE = s.n_existing, R = c.n_res;
+  ExRunIO& io = g_xio;
+  const unsigned cls = (unsigned)first.cls64;
+  const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
+  const int qi = io.qi, seq0 = io.seq;
+  int parity = io.parity, xpar = 0;
+  __syncthreads();  // everybody has read g_xio
+  // run length: consecutive queue entries of this class
+  const int lim = min(s.n_pods - qi, kExRunMax);
+  unsigned long long stop = ~0ull;
+  for (int j = tid; j < lim; j += T)
+    if ((unsigned)ffd_rows[qi + j].reserved != cls) { stop = (unsigned long long)j; break; }
+  const unsigned long long st = block_min_u64_db(stop, g_red, parity);
+  const int m = st == ~0ull ? lim : (int)st;
+  int e0 = s.cls_cursor[cls], placed = 0, last_used = -1;
+  while (placed < m && e0 < NE) {
+    const int e = e0 + tid;
+    int k = 0;
+    if (e < NE && !s.ex_closed[e] && ((first.tol >> s.ex_taintset[e]) & 1)) {
+      long long K = m - placed;
+      const uint32_t qp = s.ex_req_present[e] | first.res, ap = s.ex_avail_present[e];
+      for (int r = 0; r < R && K > 0; ++r) {
+        if (!((qp >> r) & 1)) continue;
+        const long long a = ((ap >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
+        const long long q = s.ex_req[(size_t)r * NE + e];
+        const long long pr = (r < kHotRes && ((first.res >> r) & 1)) ? first.req[r] : 0;
+        if (q + pr > a) { K = 0; break; }  // Fits(requests + pod, available) fails for the very next pod (existingnode.go:98-102)
+        if (pr > 0) { const long long kk = (a - q) / pr; if (kk < K) K = kk; }
+      }
+      k = (int)K;
+    }
+    int total;
+    const int incl = block_scan_incl(k, &total, xpar);
+    const int excl = incl - k, want = m - placed;
+    const int take = excl < want ? min(k, want - excl) : 0;
+    if (take > 0) {
+      bool closed = false;
+      for (int r = 0; r < R; ++r) {
+        if (r < kHotRes && ((first.res >> r) & 1)) s.ex_req[(size_t)r * NE + e] += (long long)take * first.req[r];
+        const long long a = ((s.ex_avail_present[e] >> r) & 1) ? s.ex_avail[(size_t)r * NE + e] : 0;
+        if (s.min_req[r] > 0 && s.ex_req[(size_t)r * NE + e] + s.min_req[r] > a) closed = true;
+      }
+      s.ex_req_present[e] |= first.res;
+      s.ex_closed[e] = closed;
+      for (int j = 0; j < take; ++j) {
+        const uint32_t pod = s.order[qi + placed + excl + j];
+        s.assign[pod] = e;
+        s.place_seq[pod] = seq0 + placed + excl + j;
+      }
+    }
+    const unsigned long long lu = block_min_u64_db(take > 0 ? (unsigned long long)(0x7fffffff - e) : ~0ull, g_red, parity);  // max e that took pods
+    if (lu != ~0ull) last_used = 0x7fffffff - (int)lu;
+    placed += min(total, want);
+    if (placed < m) e0 += T;
+  }
+  if (tid == 0) {
+    // nodes passed over took nothing for a monotone reason (closed, taint, requests), nodes filled are full for this class
+    s.cls_cursor[cls] = placed < m ? NE : (last_used >= 0 ? last_used : s.cls_cursor[cls]);
+    const int qcap = s.n_pods + 1;
+    io.qi = qi + placed;
+    io.head = (io.head + placed) % qcap;
+    io.qlen -= placed;
+    io.seq = seq0 + placed;
+    io.add_calls += placed;
+    io.placed = placed;
+    io.parity = parity;
+  }
+  __syncthreads();
+}
+
 // One full Scheduler.add for one pod (existing nodes -> in-flight nodes -> new node -> relax/requeue). Every thread of
 // the CTA calls it together. Kept out of line: the steady-state path in pack_kernel must stay a few KB of code, because a
 // single resident CTA runs straight out of the instruction cache hierarchy (L0 ~6 KB, L1.5 32 KB).
@@ -1669,6 +1771,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
   // class-run bookkeeping: classes found ineligible are not tried again; a run that places nothing backs off
   uint32_t run_block_cls = KSCHED_NONE;
   int run_skip = 0, run_fail = 0;
+  uint32_t xrun_block_cls = KSCHED_NONE;  // existing-node run: class the existing nodes have no room left for
 
   for (int i = tid; i < s.n_pods; i += blockDim.x) {
     s.queue[i] = s.order[i];
@@ -1742,6 +1845,28 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
       }
       // status 1 / 2: the pod at qi takes the generic step
     }
+    // ---- existing-node run (see existing_run): identical plain pods take the existing nodes in one prefix-sum pass
+    if (NE > 0 && !s.count_visited && qi < s.n_pods && (unsigned)nxt.cls64 != xrun_block_cls &&
+        ((nxt.meta >> KSCHED_META_PRESENT_SHIFT) & 0xFFFF) == 0 && nxt.topo_begin == nxt.topo_end && nxt.itype == KSCHED_NONE &&
+        nxt.hostname == KSCHED_NONE && nxt.hpc == 0 && nxt.hpe == 0 && (nxt.res >> kHotRes) == 0 && !class_has_volumes(s, (unsigned)nxt.cls64)) {
+      __syncthreads();
+      if (tid == 0) { ExRunIO& io = g_xio; io.qi = qi; io.head = head; io.qlen = qlen; io.seq = seq; io.parity = parity; io.add_calls = add_calls; io.placed = 0; }
+      __syncthreads();
+      existing_run(nxt);
+      const ExRunIO& io = g_xio;
+      const int placed = io.placed;
+      qi = io.qi; head = io.head; qlen = io.qlen; seq = io.seq; parity = io.parity; add_calls = io.add_calls;
+      __syncthreads();  // g_xio is rewritten by the next run
+      if (placed == 0) xrun_block_cls = (unsigned)nxt.cls64;  // no existing node takes this class: the generic step does the rest of it
+      if (placed > 0) {
+        fresh_valid = 0;
+        if (qlen == 0) break;
+        if (qi < s.n_pods) nxt = load_pod_regs(ffd_rows + qi, s.order[qi]);
+        if ((unsigned)nxt.cls64 == (unsigned)ffd_rows[qi - 1].reserved) xrun_block_cls = (unsigned)nxt.cls64;  // the existing nodes are full for this class
+        continue;
+      }
+    }
+    if (s.stop_new_nodes > 0 && n_new >= s.stop_new_nodes) break;  // simulation: the verdict no longer depends on the rest (cluster.cuh)
     PodRegs cur;
     const bool first_pass = qi < s.n_pods;
     if (first_pass) {

@@ -100,6 +100,7 @@ struct PackState {
   long long* fd_bound;               // [fd_cap][4]
   long long* fd_bound2;
   uint8_t* fd_dom;
+  int stop_new_nodes;                // > 0: stop once this many new nodes are open (consolidation simulations, cluster.cuh)
   int count_visited;                 // keep the exact nodes_visited statistic (costs a pass over all in-flight nodes per pod)
   int alloc_in_smem;
   int run_off;                       // byte offset (after HotSmem) of the class-run loop's per-node arrays in dynamic shared memory

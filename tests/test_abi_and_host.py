@@ -59,6 +59,20 @@ def test_encoder_shapes(pkg, config, pods, types, nodes):
         assert d["groups"] > 0
 
 
+def test_library_exports_every_host_header_symbol(pkg):
+    """include/ksched_host.h: the string-level entry points a cgo shim binds when it lets the library encode"""
+    header = (ROOT / "include" / "ksched_host.h").read_text()
+    declared = set(re.findall(r"\b(kh_[a-z0-9_]+)\(", header))
+    assert len(declared) >= 25
+    lib = pkg.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    import subprocess
+    src = "#include \"ksched_host.h\"\nint main(void) { return 0; }\n"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"), "-x", "c", "-"], input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr     # both headers are plain C
+
+
 def test_duplicate_uids_are_rejected(pkg, oracle):
     prob = fx.problem([fx.pod({"cpu": "1"}, uid="same"), fx.pod({"cpu": "1"}, uid="same")])
     p = pkg.Problem.from_dict(prob)
