@@ -204,6 +204,115 @@ def secondary(pkg, config, steps=3):
     return out
 
 
+C5 = dict(nodes=5000, pods=50_000, types=1000, name="C5: multi-node consolidation, 5k existing nodes / 50k bound pods x 1k instance types")
+OPT_CAP = 1024  # instance-type options exchanged per verdict
+
+
+def c5_block(pkg, torch, dist, rank, world, steps):
+    """BASELINE config 5 as one consolidation pass per step: candidates ranked on the device, the cluster resident on every
+    rank's GPU (ksched_load_cluster), the multi-node binary search with its probes one per GPU (speculative frontier, SURVEY
+    8e) and a single-node sweep over the 512 cheapest candidates sharded by position. The only exchange is ONE ncclAllGather of
+    the verdicts per round on the scheduler handle's communicator. value = pods re-packed per second over every simulation
+    run; parity = command + probe trace equal to the committed oracle run (tests/golden/fullsize/c5.json)."""
+    problem = pkg.Problem.synth(5, C5["pods"], C5["types"], 42, C5["nodes"])
+    if world > 1:
+        import ctypes as C
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            assert pkg.lib().ksched_nccl_unique_id(buf) == 0
+            uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        pkg._check(pkg.lib().kh_nccl_init(raw, rank, world))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(mine, per_rank):
+        """{key: (action, options)} of every rank through one ncclAllGather of fixed-size int records"""
+        if world == 1:
+            return dict(mine)
+        rec = 3 + OPT_CAP
+        flat = []
+        for key, (action, options) in list(mine.items())[:per_rank]:
+            flat += [key, action, len(options)] + list(options[:OPT_CAP]) + [0] * (OPT_CAP - min(len(options), OPT_CAP))
+        flat += [-1] * (per_rank * rec - len(flat))
+        out = {}
+        for part in pkg.nccl_allgather_i32(flat, world):
+            for q in range(per_rank):
+                r = part[q * rec:(q + 1) * rec]
+                if r[0] >= 0:
+                    out[r[0]] = (r[1], r[3:3 + r[2]])
+        return out
+
+    stats = {"multi_s": 0.0, "single_s": 0.0, "rank_s": 0.0, "open_s": 0.0, "repacked": 0, "simulations": 0}
+    last = {}
+    for step in range(steps + 1):  # the first pass is the warm-up
+        barrier()
+        t0 = time.perf_counter()
+        order, cost = pkg.rank_candidates(problem)
+        t1 = time.perf_counter()
+        sess = pkg.ClusterSession(problem)
+        barrier()
+        t2 = time.perf_counter()
+        n = sess.n_candidates
+        evaluated = []
+
+        def probe_many(counts):
+            mine = {}
+            for i, c in enumerate(counts):
+                if i % world == rank:
+                    mine[c] = sess.probe_sets([list(range(c))], True)[0]
+            evaluated.extend(counts)
+            return gather(mine, (len(counts) + world - 1) // world)
+
+        action, removed, options, rounds, path = pkg.speculative_binary_search(n, probe_many, world)
+        barrier()
+        t3 = time.perf_counter()
+        sweep = min(512, n)
+        per = (sweep + world - 1) // world
+        lo, hi = min(sweep, rank * per), min(sweep, (rank + 1) * per)
+        hit = None
+        for b in range(lo, hi, 64):
+            res = sess.probe_sets([[i] for i in range(b, min(hi, b + 64))], False)
+            for q, (a, o) in enumerate(res):
+                if a and hit is None:
+                    hit = (b + q, a, o)
+            if hit:
+                break
+        hits = gather({hit[0]: (hit[1], hit[2])} if hit else {}, 1)
+        barrier()
+        t4 = time.perf_counter()
+        sess.close()
+        single = min(hits.items())[0:1] + min(hits.items())[1] if hits else None
+        if step == 0:
+            continue
+        stats["rank_s"] += t1 - t0; stats["open_s"] += t2 - t1; stats["multi_s"] += t3 - t2; stats["single_s"] += t4 - t3
+        stats["repacked"] += 10 * sum(evaluated)
+        stats["simulations"] += len(evaluated)
+        last = {"action": action, "nodes_removed": removed, "n_options": len(options), "rounds": rounds, "probes_on_path": path,
+                "single_node": {"position": single[0], "action": single[1], "n_options": len(single[2])} if single else None,
+                "candidates": n, "first_candidates": order[:4]}
+    out = {"workload": C5["name"], "nodes": C5["nodes"], "bound_pods": C5["pods"], "instance_types": C5["types"], "steps": steps, "warmup": 1,
+           "value": stats["repacked"] / stats["multi_s"], "unit": "pods re-packed/s (multi-node search, every simulation run)",
+           "multi_node_search_ms": 1000 * stats["multi_s"] / steps, "simulations_per_search": stats["simulations"] / steps,
+           "single_node_sweep_512_ms": 1000 * stats["single_s"] / steps, "rank_candidates_ms": 1000 * stats["rank_s"] / steps,
+           "load_cluster_ms": 1000 * stats["open_s"] / steps, "sharding": f"probes one per GPU over {world} GPU(s), one ncclAllGather of verdicts per round",
+           "result": last}
+    g = ROOT / "tests" / "golden" / "fullsize" / "c5.json"
+    if g.exists():
+        gold = json.loads(g.read_text())
+        m = gold["multi_node"]
+        seq = [c for c in m["probes"]]
+        out["parity_vs_oracle"] = bool(last["action"] == m["action"] and last["nodes_removed"] == m["nodes_removed"] and last["n_options"] == len(m["options"]) and
+                                       last["probes_on_path"] == seq)
+        out["oracle_seconds_same_search_1_core"] = gold["oracle_seconds_multi_node"]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,6 +323,7 @@ def main():
     ap.add_argument("--pods", type=int, default=0)
     ap.add_argument("--types", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs and the secondary configurations (profiling runs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the consolidation block (config_c5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -375,6 +485,9 @@ def main():
                                          "matrix (physical: one 32-byte sector of every pod row + the matrix + the best vector)"},
         "clocks": clocks,
     }
+    if not args.no_c5:
+        rs = None  # the handle now serves the consolidation pass
+        line["config_c5"] = c5_block(pkg, torch, dist, rank, world, 2)
     if rank == 0:
         if gold:
             details["parity_vs_oracle"] = bool(int(res.digest()) == gold["digest"])

@@ -61,3 +61,24 @@ def test_c3_c4_samples_match_oracle(pkg, oracle, cfg, pods, types, seed):
     oracle.solve(problem, want)
     assert np.array_equal(got.assign, want.assign)
     assert got.digest() == want.digest()
+
+
+def test_c5_full_size_matches_oracle_command_and_trace(pkg):
+    """BASELINE config 5 at full size (5 000 nodes, 50 000 bound pods, 1 000 types) against the committed oracle run
+    (tests/golden/fullsize/c5.json, ~7 minutes of CPU): the candidate order and costs (device ranking), the multi-node
+    command with the binary search's whole probe trace, and the single-node command."""
+    want = json.loads((GOLD / "c5.json").read_text())
+    problem = pkg.Problem.synth(5, want["pods"], want["types"], want["seed"], want["nodes"])
+    order, cost = pkg.rank_candidates(problem)
+    assert hashlib.sha256(np.asarray(order, dtype=np.int32).tobytes()).hexdigest() == want["candidate_order_sha256"]
+    assert hashlib.sha256(np.asarray(cost, dtype=np.float64).tobytes()).hexdigest() == want["candidate_cost_sha256"]
+    got = pkg.MultiNodeConsolidation(problem).first_n_node_consolidation_option()
+    m = want["multi_node"]
+    assert (got["action"], got["nodes_removed"], got["options"], got["probes"], got["probe_actions"]) == \
+           (m["action"], m["nodes_removed"], m["options"], m["probes"], m["probe_actions"])
+    one = pkg.SingleNodeConsolidation(problem).compute_command()
+    s1 = want["single_node"]
+    assert (one["action"], one["node"], one["options"]) == (s1["action"], s1["node"], s1["options"])
+    # the same search with its probes evaluated four per round (what four GPUs would do) replays the same decisions
+    wide = pkg.MultiNodeConsolidation(problem).first_n_node_consolidation_option_sharded(0, 1, None)
+    assert (wide["action"], wide["nodes_removed"], wide["options"]) == (m["action"], m["nodes_removed"], m["options"])
