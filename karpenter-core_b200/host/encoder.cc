@@ -19,6 +19,7 @@
 #include <unordered_set>
 #include <set>
 #include <stdexcept>
+#include <thread>
 
 #include "reqmask.cuh"
 
@@ -28,6 +29,23 @@ using ksched::KeyMeta;
 using ksched::Req;
 
 namespace {
+
+// Split [0, n) over the host's cores; fn(begin, end) must only write what it owns. Small inputs stay on the calling thread.
+template <class F>
+void parallel_ranges(size_t n, size_t min_per_thread, F fn) {
+  static const size_t env_threads = [] { const char* e = std::getenv("KSCHED_HOST_THREADS"); return e ? (size_t)std::max(1, std::atoi(e)) : (size_t)0; }();
+  size_t nt = env_threads ? env_threads : std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+  nt = std::min(nt, std::max<size_t>(1, n / std::max<size_t>(1, min_per_thread)));
+  if (nt <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; ++t) {
+    const size_t b = t * per, e = std::min(n, b + per);
+    if (b >= e) break;
+    th.emplace_back([=] { fn(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
 
 [[noreturn]] void unsupported(const std::string& what) { throw std::runtime_error("unsupported: " + what); }
 
@@ -640,9 +658,16 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     return id;
   };
   E.pod_class.resize(NP);
-  for (size_t i = 0; i < NP; ++i) {
-    if (i > 0 && same_spec(*E.pods[i], *E.pods[i - 1])) E.pod_class[i] = E.pod_class[i - 1];  // same deployment as the previous pod
-    else E.pod_class[i] = intern(*E.pods[i]);
+  {
+    // "same deployment as the previous pod" is a pure comparison of two pods: every pair at once, on all cores; only the
+    // class boundaries (a few hundred in a 100 000-pod batch) take the keyed path, in order
+    std::vector<uint8_t> same(NP, 0);
+    parallel_ranges(NP, 4096, [&](size_t b, size_t e) {
+      for (size_t i = std::max<size_t>(b, 1); i < e; ++i) same[i] = same_spec(*E.pods[i], *E.pods[i - 1]) ? 1 : 0;
+    });
+    phase("  same_spec pairs");
+    for (size_t i = 0; i < NP; ++i) E.pod_class[i] = same[i] ? E.pod_class[i - 1] : intern(*E.pods[i]);
+    phase("  intern boundaries");
   }
   std::vector<Pod> daemons = P.daemonset_pods;
 
@@ -1265,6 +1290,24 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   E.classes.resize(NC);
   E.class_bounds.resize(NC);
   std::map<std::string, uint32_t> itype_req_id;
+  // (class, group) relations: selector matches of every class against every group, on all cores (pure reads)
+  std::vector<uint8_t> rel((size_t)NC * std::max(NG, 1), 0);
+  parallel_ranges((size_t)NC, 16, [&](size_t cb, size_t ce) {
+    for (size_t c = cb; c < ce; ++c)
+      for (int g = 0; g < NG; ++g) {
+        const Group& G = groups[g];
+        const bool owns = G.owner_specs.count(c) > 0;
+        const bool sel = G.selects(specs[c].pod);
+        uint32_t flags = 0;
+        if (sel) flags |= KSCHED_TOPO_SELECTS;
+        if (!G.inverse && owns) flags |= KSCHED_TOPO_CONSTRAINS;
+        if (G.inverse && sel) flags |= KSCHED_TOPO_CONSTRAINS;  // Counts(): nil node filter always matches
+        if (!G.inverse && sel) flags |= KSCHED_TOPO_RECORDS;
+        if (G.inverse && owns) flags |= KSCHED_TOPO_RECORDS_INVERSE;
+        rel[c * NG + g] = (uint8_t)flags;
+      }
+  });
+  phase("  class relations");
   for (int c = 0; c < NC; ++c) {
     const Pod& p = specs[c].pod;
     ksched_pod_row& row = E.classes[c];
@@ -1336,15 +1379,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     // topology relations
     row.topo_begin = (uint32_t)E.class_topo.size();
     for (int g = 0; g < NG; ++g) {
-      const Group& G = groups[g];
-      bool owns = G.owner_specs.count((size_t)c) > 0;
-      bool sel = G.selects(p);
-      uint32_t flags = 0;
-      if (sel) flags |= KSCHED_TOPO_SELECTS;
-      if (!G.inverse && owns) flags |= KSCHED_TOPO_CONSTRAINS;
-      if (G.inverse && sel) flags |= KSCHED_TOPO_CONSTRAINS;  // Counts(): nil node filter always matches
-      if (!G.inverse && sel) flags |= KSCHED_TOPO_RECORDS;
-      if (G.inverse && owns) flags |= KSCHED_TOPO_RECORDS_INVERSE;
+      const uint32_t flags = rel[(size_t)c * NG + g];
       if (flags & ~KSCHED_TOPO_SELECTS) E.class_topo.push_back({(uint32_t)g, flags});
     }
     row.topo_end = (uint32_t)E.class_topo.size();

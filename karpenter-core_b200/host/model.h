@@ -203,6 +203,7 @@ struct NewNodeResult {
   int32_t provisioner = -1;                   // index into the weight-ordered provisioner list
   std::vector<int32_t> pods;                  // indices into Problem.pods, in Add order
   std::vector<int32_t> instance_type_options; // indices into Problem.instance_types, input order preserved
+  int32_t option_set = -1;                    // >= 0: the options are Result::option_sets[option_set] (nodes of one deployment share their set)
   ResourceList requests;
   // final requirement per key (hostname removed), rendered "key Op [v1 v2]" style for comparison
   std::map<std::string, std::string> requirements;
@@ -216,11 +217,17 @@ struct Result {
   std::vector<int32_t> assign;        // per pod: -1 unscheduled; [0,E) existing node idx; E+i new node i
   std::vector<int32_t> relax_level;   // per pod: number of successful Relax calls
   std::vector<NewNodeResult> new_nodes;
+  std::vector<std::vector<int32_t>> option_sets;  // distinct InstanceTypeOptions lists, shared by the nodes that name them
   std::vector<int32_t> existing_node_index;  // s.existingNodes[i] -> index into Problem.nodes
   std::vector<std::vector<int32_t>> existing_pods;  // per existing node: pods in Add order
   int64_t nodes_visited = 0;  // sum over Add attempts of candidate nodes examined (SURVEY 8d K2 bytes)
   int64_t add_calls = 0;      // number of Scheduler.add calls (queue pops)
   std::string error;
 };
+
+// InstanceTypeOptions of a new node: its own list, or the shared one it names
+inline const std::vector<int32_t>& node_options(const Result& r, const NewNodeResult& n) {
+  return n.option_set >= 0 ? r.option_sets[(size_t)n.option_set] : n.instance_type_options;
+}
 
 }  // namespace kmodel

@@ -63,11 +63,11 @@ void kh_result_new_node_info(const Result* r, int* out) {
   for (size_t i = 0; i < r->new_nodes.size(); ++i) {
     out[3 * i] = r->new_nodes[i].provisioner;
     out[3 * i + 1] = (int)r->new_nodes[i].pods.size();
-    out[3 * i + 2] = (int)r->new_nodes[i].instance_type_options.size();
+    out[3 * i + 2] = (int)kmodel::node_options(*r, r->new_nodes[i]).size();
   }
 }
 long long kh_result_new_node_options(const Result* r, long long i, int* out, long long cap) {
-  auto& v = r->new_nodes.at(i).instance_type_options;
+  auto& v = kmodel::node_options(*r, r->new_nodes.at(i));
   for (size_t k = 0; k < v.size() && (long long)k < cap; ++k) out[k] = v[k];
   return (long long)v.size();
 }
@@ -80,7 +80,7 @@ unsigned long long kh_result_digest(const Result* r) {
   for (auto& n : r->new_nodes) {
     h = fnv(h, &n.provisioner, 4);
     h = fnv(h, n.pods.data(), n.pods.size() * 4);
-    h = fnv(h, n.instance_type_options.data(), n.instance_type_options.size() * 4);
+    h = fnv(h, kmodel::node_options(*r, n).data(), kmodel::node_options(*r, n).size() * 4);
     for (auto& kv : n.requests) { h = fnv_str(h, kv.first); h = fnv(h, &kv.second, 8); }
     for (auto& kv : n.requirements) { h = fnv_str(h, kv.first); h = fnv_str(h, kv.second); }
   }
@@ -145,11 +145,12 @@ static long long result_json(const Result* r, char* buf, long long cap, bool bri
     auto& nn = r->new_nodes[n];
     o << (n ? "," : "") << "{\"provisioner\":" << nn.provisioner << ",\"pods\":[";
     for (size_t i = 0; i < nn.pods.size(); ++i) o << (i ? "," : "") << nn.pods[i];
+    const std::vector<int32_t>& nn_options = kmodel::node_options(*r, nn);
     if (brief) {
-      o << "],\"nOptions\":" << nn.instance_type_options.size() << ",\"requests\":{";
+      o << "],\"nOptions\":" << nn_options.size() << ",\"requests\":{";
     } else {
       o << "],\"options\":[";
-      for (size_t i = 0; i < nn.instance_type_options.size(); ++i) o << (i ? "," : "") << nn.instance_type_options[i];
+      for (size_t i = 0; i < nn_options.size(); ++i) o << (i ? "," : "") << nn_options[i];
       o << "],\"requests\":{";
     }
     bool first = true;

@@ -107,28 +107,40 @@ void decode(const Encoded& E, const ResultBuffers& B, Result& out) {
   const size_t NT = E.type_input_index.size();
   std::vector<uint64_t> in_order((NT + 63) / 64);
   std::vector<std::unordered_map<uint64_t, std::string>> rendered(E.key_names.size());
+  // nodes opened for one deployment end with the same option set: each distinct bitset is expanded once and shared
+  std::unordered_map<std::string, int32_t> set_of;
   for (int n = 0; n < B.r.n_new_nodes; ++n) {
     const ksched_new_node& src = B.nodes[n];
     NewNodeResult& dst = out.new_nodes[n];
     dst.provisioner = src.template_index;
     const uint64_t* bits = &B.types[(size_t)n * E.type_words];
-    std::fill(in_order.begin(), in_order.end(), 0);
-    size_t n_opts = 0;
-    for (size_t w = 0; w < (size_t)E.type_words; ++w) {
-      uint64_t m = bits[w];
-      while (m) {
-        const size_t c = w * 64 + (size_t)__builtin_ctzll(m);
-        m &= m - 1;
-        if (c >= NT) continue;
-        const size_t t = (size_t)E.type_input_index[c];
-        in_order[t >> 6] |= 1ull << (t & 63);
-        ++n_opts;
+    std::string key(reinterpret_cast<const char*>(bits), (size_t)E.type_words * 8);
+    auto found = set_of.find(key);
+    if (found != set_of.end()) {
+      dst.option_set = found->second;
+    } else {
+      std::fill(in_order.begin(), in_order.end(), 0);
+      size_t n_opts = 0;
+      for (size_t w = 0; w < (size_t)E.type_words; ++w) {
+        uint64_t m = bits[w];
+        while (m) {
+          const size_t c = w * 64 + (size_t)__builtin_ctzll(m);
+          m &= m - 1;
+          if (c >= NT) continue;
+          const size_t t = (size_t)E.type_input_index[c];
+          in_order[t >> 6] |= 1ull << (t & 63);
+          ++n_opts;
+        }
       }
-    }
-    dst.instance_type_options.reserve(n_opts);
-    for (size_t w = 0; w < in_order.size(); ++w) {
-      uint64_t m = in_order[w];
-      while (m) { dst.instance_type_options.push_back((int32_t)(w * 64 + (size_t)__builtin_ctzll(m))); m &= m - 1; }
+      std::vector<int32_t> opts;
+      opts.reserve(n_opts);
+      for (size_t w = 0; w < in_order.size(); ++w) {
+        uint64_t m = in_order[w];
+        while (m) { opts.push_back((int32_t)(w * 64 + (size_t)__builtin_ctzll(m))); m &= m - 1; }
+      }
+      dst.option_set = (int32_t)out.option_sets.size();
+      out.option_sets.push_back(std::move(opts));
+      set_of.emplace(std::move(key), dst.option_set);
     }
     for (size_t r = 0; r < E.res_names.size(); ++r)
       if ((src.requests_present >> r) & 1) dst.requests[E.res_names[r]] = src.requests[r];
@@ -868,7 +880,7 @@ extern "C" int kh_launch_table_selfcheck(const Problem* P, const Result* ref) {
       const uint32_t zmask = allowed(zone_key, nn.requirements, 0xFFFF), cmask = allowed(ct_key, nn.requirements, 0xF);
       uint64_t best = ~0ull, best_off = ksched::kNoOffering;
       int best_col = -1;
-      for (int ti : nn.instance_type_options) {
+      for (int ti : kmodel::node_options(*ref, nn)) {
         const int c = col_of[(size_t)ti];
         const uint64_t ok = ksched::offering_min_key(&E->offering_keys[(size_t)c * 64], zmask, cmask);
         if (ok == ksched::kNoOffering) continue;
