@@ -1,5 +1,6 @@
 /*
- * ksched_host — the string-level entry points of libksched.so: the host layer ABOVE the flat C-ABI of ksched.h.
+ * ksched_host — the string-level entry points: the host layer ABOVE the flat C-ABI of ksched.h. Link with -lksched -lkmodel
+ * (libkmodel.so: problems / results, no CUDA; libksched.so: everything that solves).
  *
  * ksched.h is what a Go encoder would bind (flat structs, no strings). This header is the other way to bind the library:
  * hand it the reference's objects as they are — pods, provisioners, instance types, state nodes as one JSON document

@@ -51,20 +51,20 @@ class Timings(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}
 
 
-_lib = None
+_model = None
+MODEL_LIB_PATH = Path(__file__).resolve().parent / "libkmodel.so"
 
 
-def lib():
-    """Load libksched.so (fails loudly when the extension was not built)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(there is no CPU fallback for the solver)")
-    L = C.CDLL(str(LIB_PATH))
+def model_lib():
+    """libkmodel.so: the string-level model (JSON loader, synthetic BASELINE configurations, result accessors). No CUDA and
+    no solver in it: the oracle's tests and the bench's reference arm load this library alone."""
+    global _model
+    if _model is not None:
+        return _model
+    if not MODEL_LIB_PATH.exists():
+        raise RuntimeError(f"{MODEL_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(str(MODEL_LIB_PATH))
     L.kh_last_error.restype = C.c_char_p
-    L.kh_scheduler_error.restype = C.c_char_p
     L.kh_problem_from_json.restype = C.c_void_p
     L.kh_problem_from_json.argtypes = [C.c_char_p]
     L.kh_problem_synth.restype = C.c_void_p
@@ -92,6 +92,23 @@ def lib():
     L.kh_result_to_json_brief.restype = C.c_longlong
     L.kh_result_to_json_brief.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     L.kh_problem_pod_summary.argtypes = [C.c_void_p, C.c_void_p]
+    _model = L
+    return L
+
+
+_lib = None
+
+
+def lib():
+    """Load libksched.so (fails loudly when the extension was not built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the solver)")
+    L = C.CDLL(str(LIB_PATH))
+    L.kh_scheduler_error.restype = C.c_char_p
     L.kh_encoded_digest.restype = C.c_ulonglong
     L.kh_encoded_digest.argtypes = [C.c_void_p]
     L.kh_launch_table_selfcheck.argtypes = [C.c_void_p, C.c_void_p]
@@ -165,33 +182,33 @@ class Problem:
 
     def __init__(self, ptr):
         if not ptr:
-            raise ValueError(lib().kh_last_error().decode())
+            raise ValueError(model_lib().kh_last_error().decode())
         self.ptr = ptr
 
     @classmethod
     def from_dict(cls, d):
-        return cls(lib().kh_problem_from_json(json.dumps(d).encode()))
+        return cls(model_lib().kh_problem_from_json(json.dumps(d).encode()))
 
     @classmethod
     def synth(cls, config, n_pods, n_types, seed=42, n_nodes=0):
         """BASELINE.json configurations C1..C5."""
-        return cls(lib().kh_problem_synth(config, n_pods, n_types, seed, n_nodes))
+        return cls(model_lib().kh_problem_synth(config, n_pods, n_types, seed, n_nodes))
 
     def pod_summary(self):
         """[n_pods][6] int64: cpu milli, memory milli, app label id, self anti-affinity on hostname, zone spread skew, hostname spread skew"""
         n = self.counts()["pods"]
         out = np.zeros((max(n, 1), 6), dtype=np.int64)
-        lib().kh_problem_pod_summary(self.ptr, out.ctypes.data_as(C.c_void_p))
+        model_lib().kh_problem_pod_summary(self.ptr, out.ctypes.data_as(C.c_void_p))
         return out[:n]
 
     def counts(self):
         out = (C.c_longlong * 6)()
-        lib().kh_problem_counts(self.ptr, out)
+        model_lib().kh_problem_counts(self.ptr, out)
         return dict(zip(["pods", "instance_types", "provisioners", "nodes", "daemonset_pods", "bound_pods"], list(out)))
 
     def __del__(self):
-        if getattr(self, "ptr", None) and _lib is not None:
-            _lib.kh_problem_free(self.ptr)
+        if getattr(self, "ptr", None) and _model is not None:
+            _model.kh_problem_free(self.ptr)
             self.ptr = None
 
 
@@ -199,66 +216,66 @@ class Result:
     """([]*Node, []*ExistingNode) of Scheduler.Solve as flat data."""
 
     def __init__(self):
-        self.ptr = lib().kh_result_new()
+        self.ptr = model_lib().kh_result_new()
 
     def __del__(self):
-        if getattr(self, "ptr", None) and _lib is not None:
-            _lib.kh_result_free(self.ptr)
+        if getattr(self, "ptr", None) and _model is not None:
+            _model.kh_result_free(self.ptr)
             self.ptr = None
 
     @property
     def error(self):
-        return lib().kh_result_error(self.ptr).decode()
+        return model_lib().kh_result_error(self.ptr).decode()
 
     @property
     def assign(self):
-        n = lib().kh_result_num_pods(self.ptr)
+        n = model_lib().kh_result_num_pods(self.ptr)
         out = np.empty(n, dtype=np.int32)
-        lib().kh_result_assign(self.ptr, out.ctypes.data)
+        model_lib().kh_result_assign(self.ptr, out.ctypes.data)
         return out
 
     @property
     def relax_level(self):
-        n = lib().kh_result_num_pods(self.ptr)
+        n = model_lib().kh_result_num_pods(self.ptr)
         out = np.empty(n, dtype=np.int32)
-        lib().kh_result_relax(self.ptr, out.ctypes.data)
+        model_lib().kh_result_relax(self.ptr, out.ctypes.data)
         return out
 
     @property
     def num_new_nodes(self):
-        return lib().kh_result_num_new_nodes(self.ptr)
+        return model_lib().kh_result_num_new_nodes(self.ptr)
 
     @property
     def num_existing(self):
-        return lib().kh_result_num_existing(self.ptr)
+        return model_lib().kh_result_num_existing(self.ptr)
 
     @property
     def nodes_visited(self):
-        return lib().kh_result_nodes_visited(self.ptr)
+        return model_lib().kh_result_nodes_visited(self.ptr)
 
     @property
     def add_calls(self):
-        return lib().kh_result_add_calls(self.ptr)
+        return model_lib().kh_result_add_calls(self.ptr)
 
     def new_node_info(self):
         """[n_new, 3] = (provisioner index in weight order, pod count, surviving instance-type options)"""
         n = self.num_new_nodes
         out = np.empty((n, 3), dtype=np.int32)
-        lib().kh_result_new_node_info(self.ptr, out.ctypes.data)
+        model_lib().kh_result_new_node_info(self.ptr, out.ctypes.data)
         return out
 
     def new_node_options(self, i):
         cap = 1 << 16
         out = np.empty(cap, dtype=np.int32)
-        n = lib().kh_result_new_node_options(self.ptr, i, out.ctypes.data, cap)
+        n = model_lib().kh_result_new_node_options(self.ptr, i, out.ctypes.data, cap)
         return out[:n].copy()
 
     def digest(self):
-        return lib().kh_result_digest(self.ptr)
+        return model_lib().kh_result_digest(self.ptr)
 
     def to_dict(self, brief=False):
         """brief: per-node instance-type lists replaced by their length (full-size problems)"""
-        fn = lib().kh_result_to_json_brief if brief else lib().kh_result_to_json
+        fn = model_lib().kh_result_to_json_brief if brief else model_lib().kh_result_to_json
         need = fn(self.ptr, None, 0)
         buf = C.create_string_buffer(need)
         fn(self.ptr, buf, need)

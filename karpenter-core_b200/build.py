@@ -1,6 +1,9 @@
 """In-tree build of the native pieces (no JIT cache: the built .so files travel to the GPU box).
 
-  csrc/ksched.cu + host/*.cc  ->  karpenter-core_b200/libksched.so   (C-ABI of include/ksched.h + host layer)
+  host/{loader,synth,result_io}.cc       ->  karpenter-core_b200/libkmodel.so   (string-level model: JSON loader, synthetic BASELINE
+                                             configurations, result accessors - no CUDA, no solver; the oracle's tests and the
+                                             bench's reference arm load this one alone)
+  csrc/ksched.cu + host/{encoder,scheduler}.cc  ->  karpenter-core_b200/libksched.so   (C-ABI of include/ksched.h + host layer)
 """
 import os
 import subprocess
@@ -12,7 +15,8 @@ ROOT = PKG.parent
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-HOST_SRCS = ["loader.cc", "synth.cc", "result_io.cc", "encoder.cc", "scheduler.cc"]
+MODEL_SRCS = ["loader.cc", "synth.cc", "result_io.cc"]
+HOST_SRCS = ["encoder.cc", "scheduler.cc"]
 CUDA_SRCS = ["ksched.cu"]
 
 
@@ -46,7 +50,19 @@ def build_product(force=False, verbose_ptxas=False):
     return out
 
 
+def build_model(force=False):
+    out = PKG / "libkmodel.so"
+    srcs = [PKG / "host" / s for s in MODEL_SRCS]
+    deps = srcs + list((PKG / "host").glob("*.h"))
+    if not force and not _newer(out, deps):
+        return out
+    # linked by nvcc's host toolchain like libksched.so (shared libstdc++): objects of one library are read by the other
+    _run([NVCC, *ARCH, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-Wall", "-I", PKG / "host", "-o", out, *srcs])
+    return out
+
+
 def build_all(force=False):
+    build_model(force)
     build_product(force)
 
 

@@ -37,7 +37,7 @@ def test_shard_ranges_partition_the_columns(pkg):
 
 
 def test_quantity_parser(pkg):
-    q = pkg.lib().kh_parse_quantity
+    q = pkg.model_lib().kh_parse_quantity
     assert q(b"100m") == 100 and q(b"1") == 1000 and q(b"1.8G") == 1_800_000_000_000 and q(b"4Gi") == 4 * 1024 ** 3 * 1000
     assert q(b"10Mi") == 10 * 1024 ** 2 * 1000 and q(b"2Ti") == 2 * 1024 ** 4 * 1000 and q(b"4.5") == 4500 and q(b"1m") == 1
     assert q(b"1u") == -2 ** 63  # sub-milli quantities are rejected, not rounded
@@ -64,9 +64,9 @@ def test_library_exports_every_host_header_symbol(pkg):
     header = (ROOT / "include" / "ksched_host.h").read_text()
     declared = set(re.findall(r"\b(kh_[a-z0-9_]+)\(", header))
     assert len(declared) >= 25
-    lib = pkg.lib()
+    lib, model = pkg.lib(), pkg.model_lib()   # link with -lksched -lkmodel
     for sym in declared:
-        assert hasattr(lib, sym), sym
+        assert hasattr(lib, sym) or hasattr(model, sym), sym
     import subprocess
     src = "#include \"ksched_host.h\"\nint main(void) { return 0; }\n"
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"), "-x", "c", "-"], input=src, text=True, capture_output=True)
@@ -117,6 +117,16 @@ def test_no_cpu_fallback(pkg):
     with pytest.raises(pkg.KschedError) as e:
         pkg.Scheduler(problem).solve()
     assert e.value.code == pkg.KSCHED_ERR_NO_DEVICE
+
+
+def test_model_library_has_no_solver_and_no_cuda():
+    """libkmodel.so (what the oracle's tests and the bench's reference arm load) is the string-level model only"""
+    import subprocess
+    so = ROOT / "karpenter-core_b200" / "libkmodel.so"
+    out = subprocess.run(["ldd", str(so)], capture_output=True, text=True).stdout
+    assert "cuda" not in out.lower() and "nccl" not in out.lower() and "ksched" not in out
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True).stdout
+    assert "ksched_solve" not in syms and "kh_scheduler_solve" not in syms and "kh_problem_from_json" in syms
 
 
 def test_product_does_not_link_or_import_the_oracle():
