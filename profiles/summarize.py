@@ -1,6 +1,6 @@
 """Turn the raw ncu outputs of one gpurun call (gpurun_out/) into the small summaries kept under profiles/.
 
-  python profiles/summarize.py r02        # reads gpurun_out/launches.csv, gpurun_out/r01_full.ncu-rep (if present)
+  python profiles/summarize.py r02        # reads gpurun_out/<tag>_launches.csv (or launches.csv), gpurun_out/<tag>_full.ncu-rep
 
 launch list  : ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \\
                python bench.py --steps 2 --warmup 3 --no-cpu-baseline
@@ -22,7 +22,9 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 
 def launch_shares():
-    src = OUT / "launches.csv"
+    src = OUT / f"{tag}_launches.csv"
+    if not src.exists():
+        src = OUT / "launches.csv"
     if not src.exists():
         return
     rows = [l for l in src.read_text().splitlines() if l.startswith('"')]
@@ -54,9 +56,12 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def full_capture():
-    rep = OUT / "r01_full.ncu-rep"
+    rep = OUT / f"{tag}_full.ncu-rep"
     if not rep.exists():
         return
+    suffix = "" if tag == "r01" else "_c4"  # round 2 on: the bench's workload is C4
+    old = ROOT / "profiles" / "traffic.json"
+    traffic_prev = json.loads(old.read_text()) if old.exists() else {}
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -70,14 +75,17 @@ def full_capture():
             if w in ix:
                 rec[w] = r[ix[w]] + " " + units[ix[w]]
         kernels.append(rec)
-        short = "pack_kernel" if "pack_kernel" in name else ("feasibility_kernel" if "feasibility_kernel" in name else name)
+        short = "pack_kernel" if "pack_kernel" in name else ("class_feasibility_kernel" if "class_feasibility" in name else
+                                                             ("feasibility_kernel" if "feasibility_kernel" in name else name.split("(")[0]))
+        short += suffix
         rd = float(r[ix["dram__bytes_read.sum"]].replace(",", "")) * scale.get(units[ix["dram__bytes_read.sum"]], 1.0)
         wr = float(r[ix["dram__bytes_write.sum"]].replace(",", "")) * scale.get(units[ix["dram__bytes_write.sum"]], 1.0)
         traffic[short] = rd + wr
     (ROOT / "profiles" / f"{tag}_ncu_full_summary.json").write_text(json.dumps({
-        "command": "ncu --set full --clock-control none --import-source on -k regex:feasibility_kernel|pack_kernel -s 6 -c 2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline",
+        "command": "ncu --set full --clock-control none --import-source on -k regex:feasibility_kernel|pack_kernel python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c5 (the step after the warm-ups)",
         "kernels": kernels}, indent=1) + "\n")
-    (ROOT / "profiles" / "traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
+    traffic_prev.update(traffic)
+    (ROOT / "profiles" / "traffic.json").write_text(json.dumps(traffic_prev, indent=1) + "\n")
 
 
 launch_shares()
