@@ -293,12 +293,30 @@ typedef struct ksched_result {
  *   pods     = the pending pods first, then every reschedulable pod of every candidate node, node by node;
  *   pod_node = the existing slot a pod is bound to (-1 = pending: part of every simulation).
  * A simulation names the existing slots it removes: their pods form the batch, the slots accept nobody, the rest of the cluster
- * is what the superset says. Topology groups are not supported on this path yet (n_groups must be 0): ksched_load_cluster answers
- * KSCHED_ERR_UNSUPPORTED and the caller simulates through ksched_solve instead.
+ * is what the superset says.
+ * Topology (problem->n_groups > 0): the superset's initial group counters count NO pod of the batch (topology.go:66-70); a pod
+ * that stays on its node in a simulation is counted again on the device from the tables below - countDomains
+ * (topology.go:231-276: namespace + selector per class, node label + TopologyNodeFilter per node) and the inverse
+ * anti-affinity groups of bound pods (topology.go:183-227). A cluster with groups but without these tables is refused with
+ * KSCHED_ERR_UNSUPPORTED.
  */
+#define KSCHED_COUNT_DOMAINS 0 /* a group in Topology.topologies counts the bound pod (countDomains) */
+#define KSCHED_COUNT_INVERSE 1 /* an inverse anti-affinity group the bound pod owns (updateInverseAffinities) */
+typedef struct ksched_count_rel {
+  uint32_t group;
+  uint8_t kind;   /* KSCHED_COUNT_* */
+  uint8_t times;  /* how many of the pod's terms hash to this group */
+  uint16_t pad;
+} ksched_count_rel;
 typedef struct ksched_cluster {
   const ksched_problem* problem;
   const int32_t* pod_node; /* [problem->n_pods] */
+  /* topology tables (all NULL when problem->n_groups == 0) */
+  const uint32_t* class_count_begin;      /* [n_classes + 1] ranges in class_count */
+  const ksched_count_rel* class_count;
+  const int8_t* node_domain;              /* [n_keys][n_existing] dictionary id of the node's label value, -1 = no such label */
+  const uint8_t* node_has_hostname_label; /* [n_existing] */
+  const uint32_t* group_filter_match;     /* [n_groups][(n_existing + 31) / 32] bit e: TopologyNodeFilter.Matches(node e) */
 } ksched_cluster;
 
 typedef struct ksched_candidate_set {

@@ -37,6 +37,42 @@ __global__ void cluster_select_kernel(int n_sup, const int32_t* __restrict__ pod
   out_src[dst] = i;
 }
 
+// Topology counters of one simulation = the superset's (no batch pod counted) + every candidate pod that STAYS on its node:
+// countDomains (topology.go:231-276) for the groups that count its class, and the inverse anti-affinity groups it owns
+// (topology.go:183-227). One thread per superset pod; the counters are plain integers, so the adds commute.
+__global__ void cluster_topology_kernel(int n_sup, const int32_t* __restrict__ pod_node, const uint8_t* __restrict__ in_set,
+                                        const uint32_t* __restrict__ sup_class, const uint32_t* __restrict__ cc_begin,
+                                        const ksched_count_rel* __restrict__ cc, const ksched_topo_group* __restrict__ groups,
+                                        const int8_t* __restrict__ node_dom, const uint8_t* __restrict__ node_hostlabel,
+                                        const uint32_t* __restrict__ filt, int filt_words, int n_existing, int hstride,
+                                        const int32_t* __restrict__ host_row, int32_t* grp_cnt, unsigned long long* grp_registered, uint16_t* grp_host,
+                                        int32_t* grp_host_total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sup) return;
+  const int e = pod_node[i];
+  if (e < 0 || in_set[e]) return;  // pending, or part of this simulation's batch
+  const uint32_t cls = sup_class[i];
+  for (uint32_t q = cc_begin[cls]; q < cc_begin[cls + 1]; ++q) {
+    const ksched_count_rel r = cc[q];
+    const ksched_topo_group G = groups[r.group];
+    if (r.kind == KSCHED_COUNT_DOMAINS && G.filter_begin != G.filter_end &&
+        !((filt[(size_t)r.group * filt_words + (e >> 5)] >> (e & 31)) & 1)) continue;      // TopologyNodeFilter.Matches(node)
+    if (G.key == KSCHED_KEY_HOSTNAME) {
+      if (r.kind == KSCHED_COUNT_INVERSE && !node_hostlabel[e]) continue;                 // node.Labels[key] must exist (topology.go:215)
+      const size_t idx = (size_t)host_row[r.group] * hstride + e;
+      unsigned* word = reinterpret_cast<unsigned*>(grp_host) + (idx >> 1);
+      const int shift = (int)(idx & 1) * 16;
+      const unsigned old = atomicAdd(word, (unsigned)r.times << shift);
+      if (((old >> shift) & 0xFFFFu) == 0) atomicAdd(&grp_host_total[r.group], 1);
+    } else {
+      const int d = node_dom[(size_t)G.key * n_existing + e];
+      if (d < 0) continue;
+      atomicAdd(&grp_cnt[(size_t)r.group * 64 + d], (int)r.times);
+      atomicOr(&grp_registered[r.group], 1ull << d);
+    }
+  }
+}
+
 // What computeConsolidation reads of a simulation (consolidation.go:190-274): how many pods landed, how many nodes were
 // opened and, for the price guards, the first new node in full.
 struct SimResultDev {

@@ -168,6 +168,12 @@ struct ksched_handle {
   DevBuf<int64_t> d_sup_ts, d_sim_remaining;
   DevBuf<uint8_t> d_in_set;
   DevBuf<SimResultDev> d_sim_results;
+  bool cluster_topology = false;
+  int filt_words = 0;
+  DevBuf<uint32_t> d_cc_begin, d_filt;
+  DevBuf<ksched_count_rel> d_cc;
+  DevBuf<int8_t> d_node_dom;
+  DevBuf<uint8_t> d_node_hostlabel;
   DevBuf<uint8_t> d_gather_send, d_gather_recv;
   DevBuf<int32_t> d_rk_off, d_rk_prio, d_rk_order, d_rk_n;
   DevBuf<double> d_rk_dc, d_rk_age, d_rk_ttl, d_rk_cost_in, d_rk_cost, d_rk_cost_out;
@@ -1206,7 +1212,11 @@ int ksched_load_cluster(ksched_handle* h, const ksched_cluster* cl) {
   if (!h || !cl || !cl->problem || (!cl->pod_node && cl->problem->n_pods > 0)) return KSCHED_ERR_INVALID;
   const ksched_problem* pb = cl->problem;
   h->have_cluster = false;
-  if (pb->n_groups != 0) { h->err = "unsupported: topology groups on the cluster-snapshot path (simulate through ksched_solve)"; return KSCHED_ERR_UNSUPPORTED; }
+  const bool topo = pb->n_groups != 0;
+  if (topo && (!cl->class_count_begin || !cl->node_domain || !cl->node_has_hostname_label || !cl->group_filter_match)) {
+    h->err = "unsupported: a cluster with topology groups needs the counting tables of ksched_cluster";
+    return KSCHED_ERR_UNSUPPORTED;
+  }
   const int P = pb->n_pods, NE = pb->n_existing;
   // pods: the pending ones first, then node by node (every node's pods contiguous)
   std::vector<int32_t> first((size_t)std::max(NE, 1), -1), count((size_t)std::max(NE, 1), 0);
@@ -1229,6 +1239,19 @@ int ksched_load_cluster(ksched_handle* h, const ksched_cluster* cl) {
   CUDA_TRY(h, h->d_node_dst.ensure((size_t)std::max(NE, 1)));
   CUDA_TRY(h, h->d_in_set.ensure((size_t)std::max(NE, 1)));
   CUDA_TRY(h, h->d_pod_src.ensure((size_t)std::max(P, 1)));
+  h->cluster_topology = topo;
+  if (topo) {
+    const int NC = pb->n_classes, NK = h->cat.n_keys;
+    h->filt_words = (NE + 31) / 32;
+    const uint32_t n_rel = cl->class_count_begin[NC];
+    for (uint32_t q = 0; q < n_rel; ++q)
+      if (cl->class_count[q].group >= (uint32_t)pb->n_groups) { h->err = "class_count group out of range"; return KSCHED_ERR_INVALID; }
+    CUDA_TRY(h, upload(h, h->d_cc_begin, cl->class_count_begin, (size_t)NC + 1));
+    CUDA_TRY(h, upload(h, h->d_cc, cl->class_count, (size_t)std::max<uint32_t>(n_rel, 1)));
+    CUDA_TRY(h, upload(h, h->d_node_dom, cl->node_domain, (size_t)std::max(NK, 1) * std::max(NE, 1)));
+    CUDA_TRY(h, upload(h, h->d_node_hostlabel, cl->node_has_hostname_label, (size_t)std::max(NE, 1)));
+    CUDA_TRY(h, upload(h, h->d_filt, cl->group_filter_match, (size_t)pb->n_groups * std::max(h->filt_words, 1)));
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->h_node_first.swap(first);
   h->h_node_count.swap(count);
@@ -1291,6 +1314,11 @@ int ksched_simulate_batch(ksched_handle* h, const ksched_candidate_set* sets, in
       cluster_select_kernel<<<(h->sup_pods + 255) / 256, 256, 0, h->stream>>>(h->sup_pods, h->d_sup_pod_node.ptr, h->d_in_set.ptr, h->d_node_dst.ptr + (size_t)q * NE,
                                                                               h->d_node_first.ptr, h->sup_pending, h->d_sup_class.ptr, h->d_sup_ts.ptr, h->d_sup_uid.ptr,
                                                                               h->d_pod_class0.ptr, h->d_ts.ptr, h->d_uid_rank.ptr, h->d_pod_src.ptr);
+    if (h->cluster_topology && h->sup_pods > 0)
+      cluster_topology_kernel<<<(h->sup_pods + 255) / 256, 256, 0, h->stream>>>(
+          h->sup_pods, h->d_sup_pod_node.ptr, h->d_in_set.ptr, h->d_sup_class.ptr, h->d_cc_begin.ptr, h->d_cc.ptr, h->d_groups.ptr, h->d_node_dom.ptr,
+          h->d_node_hostlabel.ptr, h->d_filt.ptr, h->filt_words, NE, NE + h->max_new, h->d_grp_host_row.ptr, h->d_grp_cnt.ptr,
+          reinterpret_cast<unsigned long long*>(h->d_grp_registered.ptr), h->d_grp_host.ptr, h->d_grp_host_total.ptr);
     // the working copy of the pod classes (reset_state copied the previous batch's): refresh it from the new batch
     if (h->n_pods > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)h->n_pods * 4, cudaMemcpyDeviceToDevice, h->stream));
     if ((rc = run_sort(h)) != KSCHED_OK) break;

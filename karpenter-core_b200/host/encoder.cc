@@ -1284,6 +1284,60 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     }
   }
 
+  if (cluster_superset && NG > 0) {
+    // What countDomains (topology.go:231-276) and updateInverseAffinities (:183-227) would add for a bound pod of each class,
+    // split into its class part (namespace, selector, owned inverse groups) and its node part (label value, node filter).
+    const int NCs = (int)specs.size();
+    E.class_count_begin.assign((size_t)NCs + 1, 0);
+    for (int c = 0; c < NCs; ++c) {
+      const Pod& p = specs[(size_t)c].pod;
+      E.class_count_begin[(size_t)c] = (uint32_t)E.class_count.size();
+      std::map<size_t, int> inverse_times;
+      for (auto& term : p.pod_anti_affinity_required) {
+        Group g = new_group(2, term.topology_key, p, namespace_list(p.ns, term.namespaces), term.selector, INT32_MAX);
+        g.inverse = true;
+        auto it = inverse_group_of.find(g.hash());
+        if (it != inverse_group_of.end()) inverse_times[it->second]++;
+      }
+      for (int g = 0; g < NG; ++g) {
+        const Group& G = groups[(size_t)g];
+        if (G.inverse) {
+          auto it = inverse_times.find((size_t)g);
+          if (it != inverse_times.end()) E.class_count.push_back({(uint32_t)g, KSCHED_COUNT_INVERSE, (uint8_t)std::min(it->second, 255), 0});
+        } else if (G.namespaces.count(p.ns) && (G.selector.is_nil || selector_matches(G.selector, p.labels))) {
+          E.class_count.push_back({(uint32_t)g, KSCHED_COUNT_DOMAINS, 1, 0});
+        }
+      }
+    }
+    E.class_count_begin[(size_t)NCs] = (uint32_t)E.class_count.size();
+    E.node_domain.assign((size_t)std::max(NK, 1) * std::max(NE, 1), -1);
+    E.node_has_hostname_label.assign((size_t)std::max(NE, 1), 0);
+    const int FW = (NE + 31) / 32;
+    E.group_filter_match.assign((size_t)NG * std::max(FW, 1), 0);
+    std::map<std::string, std::vector<char>> filter_memo;  // node labels without the hostname -> verdict per group
+    for (int e = 0; e < NE; ++e) {
+      const StateNode& n = P.nodes[(size_t)E.existing_state_index[(size_t)e]];
+      for (int k = 0; k < NK; ++k) {
+        auto l = n.labels.find(E.key_names[(size_t)k]);
+        if (l == n.labels.end()) continue;
+        auto v = B.value_id[(size_t)k].find(l->second);
+        if (v != B.value_id[(size_t)k].end()) E.node_domain[(size_t)k * NE + e] = (int8_t)v->second;
+      }
+      E.node_has_hostname_label[(size_t)e] = n.labels.count(kHostname) ? 1 : 0;
+      Labels sig = n.labels;
+      sig.erase(kHostname);
+      const std::string key = labels_key(sig);
+      auto memo = filter_memo.find(key);
+      if (memo == filter_memo.end()) {
+        std::vector<char> v((size_t)NG, 1);
+        for (int g = 0; g < NG; ++g) v[(size_t)g] = filter_matches_labels(groups[(size_t)g], n.labels) ? 1 : 0;
+        memo = filter_memo.emplace(key, std::move(v)).first;
+      }
+      for (int g = 0; g < NG; ++g)
+        if (memo->second[(size_t)g]) E.group_filter_match[(size_t)g * FW + (e >> 5)] |= 1u << (e & 31);
+    }
+  }
+
   phase("topology groups");
   // ------------------------------------------------------------------ class rows
   const int NC = (int)specs.size();

@@ -22,7 +22,13 @@ struct Encoded {
   std::vector<int> existing_state_index;              // existing slot -> Problem.nodes index
   std::vector<int32_t> pod_node;                      // cluster_superset: existing slot a batch pod is bound to, -1 = pending
   std::vector<int64_t> existing_capacity;             // cluster_superset: [n_existing][KSCHED_MAX_RES] node capacity (limits bookkeeping)
-  std::vector<int32_t> existing_template;             // cluster_superset: template whose limits the node's capacity was charged to, or -1
+  std::vector<int32_t> existing_template;
+  // cluster_superset with topology groups: what a bound pod that stays contributes to the counters (ksched.h: ksched_cluster)
+  std::vector<uint32_t> class_count_begin;
+  std::vector<ksched_count_rel> class_count;
+  std::vector<int8_t> node_domain;
+  std::vector<uint8_t> node_has_hostname_label;
+  std::vector<uint32_t> group_filter_match;             // cluster_superset: template whose limits the node's capacity was charged to, or -1
   std::vector<bool> existing_initialized;
   std::vector<int> template_provisioner;              // template v -> Problem.provisioners index
   std::vector<int> type_input_index;                  // column -> Problem.instance_types index

@@ -577,7 +577,16 @@ struct ClusterSession {
     sup->problem.count_nodes_visited = 0;
     int rc = ksched_load_catalog(g_handle, &sup->catalog);
     if (rc != KSCHED_OK) throw std::runtime_error(ksched_last_error(g_handle));
-    ksched_cluster cl{&sup->problem, sup->pod_node.data()};
+    ksched_cluster cl{};
+    cl.problem = &sup->problem;
+    cl.pod_node = sup->pod_node.data();
+    if (sup->problem.n_groups > 0) {
+      cl.class_count_begin = sup->class_count_begin.data();
+      cl.class_count = sup->class_count.data();
+      cl.node_domain = sup->node_domain.data();
+      cl.node_has_hostname_label = sup->node_has_hostname_label.data();
+      cl.group_filter_match = sup->group_filter_match.data();
+    }
     rc = ksched_load_cluster(g_handle, &cl);
     if (rc == KSCHED_ERR_UNSUPPORTED) return;  // resident stays false
     if (rc != KSCHED_OK) throw std::runtime_error(ksched_last_error(g_handle));

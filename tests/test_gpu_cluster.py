@@ -105,3 +105,59 @@ def test_snapshot_with_provisioner_limits_and_uninitialised_nodes(pkg, oracle):
     problem2 = pkg.Problem.from_dict(prob)
     cs2 = pkg.ClusterSession(problem2)
     assert cs2.probe_sets([[0], [0, 1]], True) == [oracle.consolidate_probe(problem2, 1), oracle.consolidate_probe(problem2, 2)]
+
+
+# ---------------------------------------------------------------- clusters WITH topology groups on the snapshot path
+from consolidation_answers import CASES as _CONS, CPU_ONLY_CASES as _CONS_LATE
+from fuzz_problems import random_problem
+
+
+@pytest.mark.parametrize("name,ref,build", _CONS + _CONS_LATE, ids=[c[0] for c in _CONS + _CONS_LATE])
+def test_consolidation_known_answers_run_on_the_snapshot(pkg, oracle, name, ref, build):
+    """every consolidation known answer (the topology-aware ones included, suite_test.go:1827-2030) is taken by the
+    device-resident cluster - no probe falls back to a re-encoded ksched_solve - and equals the oracle probe for probe"""
+    prob, _ = build()
+    problem = pkg.Problem.from_dict(prob)
+    cs = pkg.ClusterSession(problem)
+    assert cs.resident
+    sets = [list(range(c)) for c in range(1, cs.n_candidates + 1)]
+    if sets:
+        assert cs.probe_sets(sets, True) == [oracle.consolidate_probe(problem, len(s_)) for s_ in sets]
+
+
+def _candidate_cluster(seed):
+    """a fuzz problem (pending pods, bound pods with selectors / anti-affinity, spread constraints, several provisioners) whose
+    owned nodes are consolidation candidates"""
+    prob = random_problem(seed)
+    rng = random.Random(seed * 31 + 7)
+    offered = {(it["name"], o["capacityType"], o["zone"]) for it in prob["instanceTypes"] for o in it["offerings"]}
+    n = 0
+    for node in prob.get("nodes", []):
+        lab = node["labels"]
+        if lab.get(fx.PROVISIONER_NAME) and not node.get("markedForDeletion") and \
+                (lab.get(fx.INSTANCE_TYPE), lab.get(fx.CAPACITY_TYPE), lab.get(fx.ZONE)) in offered:  # getNodePrices needs the node's offering
+            node["candidate"] = True
+            node["disruptionCost"] = float(rng.choice([0, 1, 1, 2, 3]))
+            n += 1
+    return prob, n
+
+
+@pytest.mark.parametrize("seed", [s for s in range(400) if _candidate_cluster(s)[1] >= 2][:60])
+def test_snapshot_equals_oracle_on_random_clusters_with_topology(pkg, oracle, seed):
+    prob, n = _candidate_cluster(seed)
+    problem = pkg.Problem.from_dict(prob)
+    try:
+        cs = pkg.ClusterSession(problem)
+    except pkg.KschedError as e:
+        if e.code == pkg.KSCHED_ERR_UNSUPPORTED:
+            pytest.skip(f"refused loudly: {e}")
+        raise
+    assert cs.resident
+    order = cs.candidate_nodes()
+    prefixes = [list(range(c)) for c in range(1, len(order) + 1)]
+    singles = [[i] for i in range(len(order))]
+    for s_, g in zip(prefixes, cs.probe_sets(prefixes, True)):
+        assert g == oracle.consolidate_probe(problem, len(s_)), ("prefix", len(s_))
+    for s_, g in zip(singles, cs.probe_sets(singles, False)):
+        w = oracle.consolidate_single(problem, s_[0])
+        assert g == (w["action"], w["options"]), ("single", s_)
