@@ -67,7 +67,7 @@ int kh_scheduler_solve(const kh_problem* p, const int* candidates, int n_candida
 int kh_rank_candidates(const kh_problem* p, int* order, double* cost, int cap);
 
 /* ---- deprovisioning: the simulator. Open once per pass; every probe is one entry of a ksched_simulate_batch call against
- * the device-resident cluster (resident = 0: the cluster has topology groups and each probe is a freshly encoded
+ * the device-resident cluster (resident = 0: the snapshot refused the cluster and each probe is a freshly encoded
  * ksched_solve instead - same answers, slower). */
 kh_cluster* kh_cluster_open(const kh_problem* p, int* resident, int* n_candidates);
 void kh_cluster_close(kh_cluster* c);

@@ -997,6 +997,7 @@ static int run_pack(ksched_handle* h) {
   for (const ksched_template& tm : h->h_templates) if (tm.has_limits && tm.limit_present) s.any_limits = 1;
   s.use_warp_loop = getenv("KSCHED_WARPLOOP") ? 1 : 0;  // superseded by the class-run loop (kept for A/B timing: 18 ms vs 8 ms on C2 when both are on)
   s.use_class_run = getenv("KSCHED_NO_CLASSRUN") ? 0 : 1;
+  s.use_level_step = std::getenv("KSCHED_NO_LEVELSTEP") ? 0 : 1;
   // block size: the chain is latency-bound on ONE thread's commit; more warps only help when there are many candidate
   // nodes to examine per pod (existing nodes, large in-flight sets)
   int threads = h->n_existing >= 2048 ? kPackThreads : (h->n_existing >= 256 ? 256 : 128);

@@ -1109,6 +1109,57 @@ __device__ __noinline__ void warp_resident_loop(WarpIO* io) {
     if (__any_sync(0xffffffffu, ok && (qf == 2 || !(plain || absorbed == cls)))) break;
     const unsigned long long wkey = warp_min_u64(ok ? key : ~0ull);
     if (wkey == ~0ull) break;  // nobody accepts: a new node has to be opened
+    // ---- level step. The accepting nodes with the FEWEST pods (count L) take the next pods one each, in tie order: a node
+    // that accepts moves to the front of block L+1 (scheduler.go:183 re-sort), i.e. behind every node still in block L. With
+    // t identical pods ahead, the first t members of the block take them - t iterations of this loop in one.
+    const unsigned members = __ballot_sync(0xffffffffu, ok && (key >> 32) == (wkey >> 32));
+    if (s.use_level_step && (members & (members - 1)) && ncls == cur.cls64) {
+      const bool same = qi + lane < s.n_pods && (lane == 0 || ffd_rows[qi + lane].reserved == cur.cls64);
+      const unsigned sm = __ballot_sync(0xffffffffu, same);
+      const int run_len = sm == 0xffffffffu ? 32 : __ffs(~sm) - 1;
+      const int k = __popc(members);
+      const int t = k < run_len ? k : run_len;
+      if (t > 1) {
+        int rank = 0;
+        for (unsigned mm = members; mm; mm &= mm - 1) {
+          const unsigned long long k2 = __shfl_sync(0xffffffffu, key, __ffs(mm) - 1);
+          rank += k2 < key ? 1 : 0;
+        }
+        if (((members >> lane) & 1) && rank < t) {
+          const uint32_t pod = s.order[qi + rank];
+#pragma unroll
+          for (int r = 0; r < kHotRes; ++r) q[r] = nq[r];
+          const int count = (int)(wkey >> 32) + 1;
+          key = order_key(count, -(tick + 1 + rank));
+          if ((cur.res & 0xF) & ~((fl >> 1) & 0xF)) {
+            s.nn_req_present[node] |= cur.res;
+            fl |= (unsigned short)((cur.res & 0xF) << 1);
+          }
+          dirty = true;
+          rejected = KSCHED_NONE;
+          s.assign[pod] = NE + node;
+          s.place_seq[pod] = seq + rank;
+          if (node_closed(q, min_req, RH, b, b2, fl)) {  // the node leaves the active set
+            for (int r = 0; r < RH; ++r) s.nn_req[(size_t)r * MAXN + node] = q[r];
+            s.nn_count[node] = count;
+            s.nn_tb[node] = -(tick + 1 + rank);
+            live = false;
+            dirty = false;
+            key = ~0ull;
+          }
+        }
+        tick += t; seq += t; qi += t; add_calls += t;
+        head += t; if (head >= qcap) head -= qcap;
+        qlen -= t;
+        if (qi >= s.n_pods || qlen == 0) break;
+        if (run_len > t) { cur.pod = s.order[qi]; cur.row = ffd_rows + qi; }
+        else cur = load_pod_regs(ffd_rows + qi, s.order[qi]);
+        if (qi + 1 < s.n_pods) { npod = s.order[qi + 1]; ncls = ffd_rows[qi + 1].reserved; } else ncls = ~0ull;
+        if (lane == 0 && qi + 32 < s.n_pods) prefetch_l2(reinterpret_cast<const char*>(ffd_rows + qi + 32) + 128);
+        if (lane == 2 && qi + 96 < s.n_pods) prefetch_l2(s.order + qi + 96);
+        continue;
+      }
+    }
     if (ok && key == wkey) {
 #pragma unroll
       for (int r = 0; r < kHotRes; ++r) q[r] = nq[r];
