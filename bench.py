@@ -491,7 +491,8 @@ def main():
     if rank == 0:
         if gold:
             details["parity_vs_oracle"] = bool(int(res.digest()) == gold["digest"])
-            details["parity_source"] = "whole-result digest of the committed full-size oracle run (tests/golden/fullsize)"
+            details["parity_source"] = "whole-result digest of the committed full-size oracle run (tests/golden/fullsize); the oracle is the C++ " \
+                                       "restatement of the Go algorithm under canonical rules R1-R6 (DESIGN.md section 6), the Go reference itself cannot run here"
         if world == 1 and not args.no_cpu_baseline:
             import oracle_lib
             oracle = oracle_lib.load()

@@ -18,6 +18,15 @@ __global__ void sort_keys_kernel(int n, const ksched_pod_row* __restrict__ class
   k_tie[i] = ((uint64_t)(ts[i] + (1ll << 32)) << 30) | (uint64_t)uid_rank[i];
   idx[i] = (uint32_t)i;
 }
+// The same order from ONE packed key when it fits 64 bits: (rank of the class's (cpu, memory) pair among all classes,
+// timestamp - min timestamp, UID rank). cls_rank is built on the host at upload (classes are few).
+__global__ void sort_key1_kernel(int n, const uint32_t* __restrict__ cls_rank, const uint32_t* __restrict__ pod_class, const int64_t* __restrict__ ts,
+                                 const uint32_t* __restrict__ uid_rank, long long ts_min, int ts_bits, int uid_bits, uint64_t* key, uint32_t* idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  key[i] = ((uint64_t)cls_rank[pod_class[i]] << (ts_bits + uid_bits)) | ((uint64_t)(ts[i] - ts_min) << uid_bits) | (uint64_t)uid_rank[i];
+  idx[i] = (uint32_t)i;
+}
 __global__ void gather_u64_kernel(int n, const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t* dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[idx[i]];

@@ -230,6 +230,10 @@ struct ksched_handle {
   DevBuf<long long> d_counters, d_k1dbg;
   DevBuf<uint32_t> d_flush;
   size_t cub_tmp_bytes = 0;
+  // one-pass queue order (feasibility_kernel.cuh: sort_key1_kernel): total key bits, 0 = the three-key path
+  int sort1_bits = 0, sort1_ts_bits = 0, sort1_uid_bits = 0;
+  long long sort1_ts_min = 0;
+  DevBuf<uint32_t> d_cls_rank;
   int64_t min_req[KSCHED_MAX_RES] = {0};
   // sharding / nccl
   int rank = 0, world = 1;
@@ -645,6 +649,37 @@ int ksched_upload(ksched_handle* h, const ksched_problem* pb) {
     h->min_req[r] = (NC == 0 || mn == INT64_MAX || mn < 0) ? 0 : mn;
   }
   CUDA_TRY(h, upload(h, h->d_classes, pb->classes, (size_t)NC));
+  {
+    // queue.go:82-108 orders by cpu desc, memory desc, timestamp asc, UID asc. (cpu, memory) is a property of the class: rank
+    // the classes once here, and the whole order is one packed key when rank, timestamp span and UID rank fit 64 bits.
+    std::vector<uint32_t> by((size_t)NC), rank((size_t)std::max(NC, 1), 0);
+    for (int i = 0; i < NC; ++i) by[(size_t)i] = (uint32_t)i;
+    auto cpu = [&](uint32_t c) { return pb->classes[c].requests[0]; };
+    auto mem = [&](uint32_t c) { return pb->classes[c].requests[1]; };
+    std::sort(by.begin(), by.end(), [&](uint32_t a, uint32_t b) { return cpu(a) != cpu(b) ? cpu(a) > cpu(b) : mem(a) > mem(b); });
+    uint32_t r = 0;
+    for (int i = 0; i < NC; ++i) {
+      if (i > 0 && (cpu(by[(size_t)i]) != cpu(by[(size_t)i - 1]) || mem(by[(size_t)i]) != mem(by[(size_t)i - 1]))) ++r;
+      rank[by[(size_t)i]] = r;
+    }
+    auto bits = [](unsigned long long v) { int b = 0; while (v) { ++b; v >>= 1; } return std::max(b, 1); };
+    long long ts_min = 0, ts_max = 0;
+    uint32_t uid_max = 0;
+    for (int i = 0; i < P; ++i) {
+      const long long t = pb->pod_timestamp[i];
+      if (i == 0 || t < ts_min) ts_min = t;
+      if (i == 0 || t > ts_max) ts_max = t;
+      uid_max = std::max(uid_max, pb->pod_uid_rank[i]);
+    }
+    const unsigned long long span = (unsigned long long)(ts_max - ts_min);
+    h->sort1_ts_bits = bits(span);
+    h->sort1_uid_bits = bits(uid_max);
+    h->sort1_ts_min = ts_min;
+    const int total = bits(r) + h->sort1_ts_bits + h->sort1_uid_bits;
+    h->sort1_bits = (span < (1ull << 62) && total <= 64 && !std::getenv("KSCHED_SORT3")) ? total : 0;
+    CUDA_TRY(h, upload_vec(h, h->d_cls_rank, rank));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rank is a stack vector
+  }
   CUDA_TRY(h, upload(h, h->d_pod_class0, pb->pod_class, (size_t)P));
   CUDA_TRY(h, h->d_pod_class.ensure(P));
   CUDA_TRY(h, upload(h, h->d_ts, pb->pod_timestamp, (size_t)P));
@@ -805,6 +840,18 @@ static int run_sort(ksched_handle* h) {
   const int P = h->n_pods;
   if (P == 0) return KSCHED_OK;
   const int threads = 256, blocks = (P + threads - 1) / threads;
+  if (h->sort1_bits > 0) {  // one packed key, only its significant bits sorted
+    sort_key1_kernel<<<blocks, threads, 0, h->stream>>>(P, h->d_cls_rank.ptr, h->d_pod_class.ptr, h->d_ts.ptr, h->d_uid_rank.ptr, h->sort1_ts_min,
+                                                        h->sort1_ts_bits, h->sort1_uid_bits, h->d_k_tie.ptr, h->d_idx_tmp.ptr);
+    size_t tmp1 = h->cub_tmp_bytes;
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.ptr, tmp1, h->d_k_tie.ptr, h->d_k_tmp.ptr, h->d_idx_tmp.ptr, h->d_order.ptr, P, 0, h->sort1_bits,
+                                                h->stream));
+    const int gblocks1 = std::min((P + 7) / 8, 148 * 8);
+    gather_rows_kernel<<<gblocks1, 256, 0, h->stream>>>(P, h->d_classes.ptr, h->d_pod_class.ptr, h->d_order.ptr, h->d_rows.ptr);
+    h->tm.sort_launches = 3;
+    h->sorted = true;
+    return KSCHED_OK;
+  }
   sort_keys_kernel<<<blocks, threads, 0, h->stream>>>(P, h->d_classes.ptr, h->d_pod_class.ptr, h->d_ts.ptr, h->d_uid_rank.ptr, h->d_k_cpu.ptr,
                                                       h->d_k_mem.ptr, h->d_k_tie.ptr, h->d_order.ptr);
   // LSD over three 64-bit keys with a stable radix sort: tie-break key first, cpu last
@@ -911,39 +958,63 @@ static int run_feasibility(ksched_handle* h) {
   return KSCHED_OK;
 }
 
-static int reset_state(ksched_handle* h, const int64_t* d_remaining_src = nullptr) {
+// Every array a Solve mutates goes back to its pristine copy (or to zero) in ONE launch: a table of (dst, src, bytes)
+// segments passed by value. (Round 1 issued ~20 cudaMemcpyAsync / cudaMemsetAsync calls per Solve; a consolidation
+// simulation is so short that those launches were most of it.)
+struct ResetSeg { void* dst; const void* src; unsigned long long bytes; };
+struct ResetTable { int n; ResetSeg seg[30]; };
+__global__ void reset_kernel(ResetTable t) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (int q = 0; q < t.n; ++q) {
+    const ResetSeg sg = t.seg[q];
+    const size_t n16 = sg.bytes / 16;
+    uint4* d = static_cast<uint4*>(sg.dst);
+    const uint4* sv = static_cast<const uint4*>(sg.src);
+    for (size_t i = tid; i < n16; i += nth) d[i] = sv ? sv[i] : make_uint4(0, 0, 0, 0);
+    unsigned char* db = static_cast<unsigned char*>(sg.dst);
+    const unsigned char* sb = static_cast<const unsigned char*>(sg.src);
+    for (size_t i = n16 * 16 + tid; i < sg.bytes; i += nth) db[i] = sb ? sb[i] : 0;
+  }
+}
+
+static int reset_state(ksched_handle* h, const int64_t* d_remaining_src = nullptr, void* also_zero = nullptr, size_t also_zero_bytes = 0) {
   const int P = h->n_pods, NE = std::max(h->n_existing, 1), NG = std::max(h->n_groups, 1);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)P * 4, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_relax.ptr, 0, (size_t)std::max(P, 1) * 4, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_req.ptr, h->d_ex_req0.ptr, (size_t)8 * NE * 8, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_req_present.ptr, h->d_ex_req_present0.ptr, (size_t)NE * 4, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_vals.ptr, h->d_ex_vals0.ptr, (size_t)16 * NE * 8, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_meta.ptr, h->d_ex_meta0.ptr, (size_t)NE * 8, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_hp.ptr, h->d_ex_hp0.ptr, (size_t)NE * 8, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_ex_closed.ptr, 0, (size_t)NE, h->stream));
   CUDA_TRY(h, h->d_cls_cursor.ensure((size_t)std::max(h->n_classes, 1)));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_cls_cursor.ptr, 0, (size_t)std::max(h->n_classes, 1) * 4, h->stream));
-  if (h->have_volumes) CUDA_TRY(h, cudaMemcpyAsync(h->d_ex_vol.ptr, h->d_ex_vol0.ptr, (size_t)h->n_existing * sizeof(ksched_node_volumes), cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_cnt.ptr, h->d_grp_cnt0.ptr, (size_t)NG * 64 * 4, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_registered.ptr, h->d_grp_registered0.ptr, (size_t)NG * 8, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host_total.ptr, h->d_grp_host_total0.ptr, (size_t)NG * 4, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_active.ptr, h->d_grp_active0.ptr, (size_t)NG, cudaMemcpyDeviceToDevice, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_grp_min_slot.ptr, 0, (size_t)NG * 4, h->stream));
+  ResetTable t{};
+  auto add = [&](void* dst, const void* src, size_t bytes) { if (bytes) t.seg[t.n++] = ResetSeg{dst, src, (unsigned long long)bytes}; };
+  add(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)P * 4);
+  add(h->d_relax.ptr, nullptr, (size_t)std::max(P, 1) * 4);
+  add(h->d_ex_req.ptr, h->d_ex_req0.ptr, (size_t)8 * NE * 8);
+  add(h->d_ex_req_present.ptr, h->d_ex_req_present0.ptr, (size_t)NE * 4);
+  add(h->d_ex_vals.ptr, h->d_ex_vals0.ptr, (size_t)16 * NE * 8);
+  add(h->d_ex_meta.ptr, h->d_ex_meta0.ptr, (size_t)NE * 8);
+  add(h->d_ex_hp.ptr, h->d_ex_hp0.ptr, (size_t)NE * 8);
+  add(h->d_ex_closed.ptr, nullptr, (size_t)NE);
+  add(h->d_cls_cursor.ptr, nullptr, (size_t)std::max(h->n_classes, 1) * 4);
+  if (h->have_volumes) add(h->d_ex_vol.ptr, h->d_ex_vol0.ptr, (size_t)h->n_existing * sizeof(ksched_node_volumes));
+  add(h->d_grp_cnt.ptr, h->d_grp_cnt0.ptr, (size_t)NG * 64 * 4);
+  add(h->d_grp_registered.ptr, h->d_grp_registered0.ptr, (size_t)NG * 8);
+  add(h->d_grp_host_total.ptr, h->d_grp_host_total0.ptr, (size_t)NG * 4);
+  add(h->d_grp_active.ptr, h->d_grp_active0.ptr, (size_t)NG);
+  add(h->d_grp_min_slot.ptr, nullptr, (size_t)NG * 4);
   const size_t hs = (size_t)std::max(h->n_hostgroups, 1) * ((size_t)h->n_existing + h->max_new);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_grp_host.ptr, h->d_grp_host0.ptr, hs * 2, cudaMemcpyDeviceToDevice, h->stream));
-  if (d_remaining_src) {  // simulation on the cluster snapshot: limits with the removed nodes' capacity given back, already on the device
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, d_remaining_src, (size_t)h->cat.n_templates * KSCHED_MAX_RES * 8, cudaMemcpyDeviceToDevice, h->stream));
-  } else {
+  add(h->d_grp_host.ptr, h->d_grp_host0.ptr, hs * 2);
+  if (d_remaining_src)  // simulation on the cluster snapshot: limits with the removed nodes' capacity given back, already on the device
+    add(h->d_remaining.ptr, d_remaining_src, (size_t)h->cat.n_templates * KSCHED_MAX_RES * 8);
+  add(h->d_counters.ptr, nullptr, 48 * sizeof(long long));
+  add(h->d_fc_state.ptr, nullptr, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates);
+  add(h->d_fc_front_state.ptr, nullptr, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates);
+  add(h->d_fd_state.ptr, nullptr, (size_t)kFreshMemoSlots);
+  add(also_zero, nullptr, also_zero_bytes);
+  if (!d_remaining_src) {
     std::vector<int64_t> rem((size_t)h->cat.n_templates * KSCHED_MAX_RES);
     for (int v = 0; v < h->cat.n_templates; ++v)
       for (int r = 0; r < KSCHED_MAX_RES; ++r) rem[(size_t)v * KSCHED_MAX_RES + r] = h->h_templates[v].remaining[r];
     CUDA_TRY(h, cudaMemcpyAsync(h->d_remaining.ptr, rem.data(), rem.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // rem is a stack vector
   }
-  CUDA_TRY(h, cudaMemsetAsync(h->d_counters.ptr, 0, 48 * sizeof(long long), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_fc_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_fc_front_state.ptr, 0, (size_t)std::max(h->n_classes, 1) * h->cat.n_templates, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_fd_state.ptr, 0, (size_t)kFreshMemoSlots, h->stream));
+  reset_kernel<<<148 * 2, 256, 0, h->stream>>>(t);
+  CUDA_TRY(h, cudaGetLastError());
   return KSCHED_OK;
 }
 
@@ -1306,9 +1377,8 @@ int ksched_simulate_batch(ksched_handle* h, const ksched_candidate_set* sets, in
   for (int q = 0; q < n_sets && rc == KSCHED_OK; ++q) {
     const int n_nodes = node_off[(size_t)q + 1] - node_off[(size_t)q];
     h->n_pods = batch[(size_t)q];
-    rc = reset_state(h, h->d_sim_remaining.ptr + (size_t)q * V * KSCHED_MAX_RES);
+    rc = reset_state(h, h->d_sim_remaining.ptr + (size_t)q * V * KSCHED_MAX_RES, h->d_in_set.ptr, (size_t)std::max(NE, 1));
     if (rc != KSCHED_OK) break;
-    CUDA_TRY(h, cudaMemsetAsync(h->d_in_set.ptr, 0, (size_t)std::max(NE, 1), h->stream));
     if (n_nodes > 0)
       cluster_mark_kernel<<<(n_nodes + 255) / 256, 256, 0, h->stream>>>(h->d_set_nodes.ptr + node_off[(size_t)q], n_nodes, h->d_in_set.ptr, h->d_ex_closed.ptr);
     if (h->sup_pods > 0)
