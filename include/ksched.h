@@ -327,7 +327,9 @@ typedef struct ksched_candidate_set {
                                (scheduler.go:221-248 only subtracts the nodes that stay), or NULL = as in the catalog */
 } ksched_candidate_set;
 
-/* What computeConsolidation reads of one simulation (consolidation.go:190-274). */
+/* What computeConsolidation reads of one simulation (consolidation.go:190-274). A simulation stops as soon as a second new
+   node is opened - len(newNodes) != 1 means "do nothing" whatever the rest of the batch does (:214-224) - so n_new_nodes >= 2
+   comes with n_unscheduled > 0 for the pods that were never tried. */
 typedef struct ksched_sim_result {
   int32_t n_pods;        /* size of the batch */
   int32_t n_unscheduled;

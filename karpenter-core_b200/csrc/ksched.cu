@@ -1393,7 +1393,8 @@ int ksched_simulate_batch(ksched_handle* h, const ksched_candidate_set* sets, in
     // the working copy of the pod classes (reset_state copied the previous batch's): refresh it from the new batch
     if (h->n_pods > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_pod_class.ptr, h->d_pod_class0.ptr, (size_t)h->n_pods * 4, cudaMemcpyDeviceToDevice, h->stream));
     if ((rc = run_sort(h)) != KSCHED_OK) break;
-    if ((rc = run_class_feasibility(h)) != KSCHED_OK) break;
+    // the class rows of the feasibility matrix depend on the classes and the catalog only: once per batch
+    if (q == 0 && (rc = run_class_feasibility(h)) != KSCHED_OK) break;
     if ((rc = run_feasibility(h)) != KSCHED_OK) break;
     if ((rc = run_pack(h)) != KSCHED_OK) break;
     cluster_collect_kernel<<<1, 64, 0, h->stream>>>(h->d_counters.ptr, h->n_pods, h->d_nn_tmpl.ptr, h->d_nn_count.ptr, h->d_nn_req.ptr, h->d_nn_req_present.ptr,
