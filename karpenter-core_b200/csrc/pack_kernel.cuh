@@ -1280,6 +1280,9 @@ struct RunCtx {
   unsigned red_pay[2][32];
   uint32_t q_pod[2][kRunChunk], q_cls[2][kRunChunk];  // upcoming queue entries (pod, class), double-buffered
   int32_t q_node[2][kRunChunk];                        // where the entry was placed (ksched_result.assign)
+  int q_end[2];           // first staged entry of another class (or the chunk length), per buffer
+  int lv_cnt[2];          // level step: members appended to the tie list (double-buffered)
+  int lv_fill[2];         // fill step: pods the only eligible node takes
   RunVariant var[kRunVariants];
 };
 __shared__ RunCtx g_rc;
@@ -1358,10 +1361,13 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
   const int qi0 = io.qi, seq0 = io.seq;
   int qi = qi0, qlen = io.qlen, tick = io.tick, n_active = io.n_active, n_new = io.n_new, parity = io.parity;
   const int fresh_valid = io.fresh_valid && io.fresh_cls == cls, fresh_a = io.fresh_a;
+  const int CH = T < kRunChunk ? T : kRunChunk;  // queue entries staged at a time: one per thread
+  if (tid == 0) { rc.q_end[0] = CH; rc.q_end[1] = CH; rc.lv_cnt[0] = 0; rc.lv_cnt[1] = 0; }  // (nobody reads these outside class_run)
+  const bool new_cls = rc.cls != cls;  // read BEFORE the barrier: thread 0 rewrites rc.cls right after it (racecheck, round 2)
   __syncthreads();  // everybody has read g_rio; earlier readers of g_rc are done
 
   // ---- relation tables (once per class)
-  if (rc.cls != cls) {
+  if (new_cls) {
     if (tid == 0) {
       rc.cls = cls;
       rc.n_var = 0; rc.var_next = 0; rc.n_host = 0; rc.n_mask = 0;
@@ -1410,7 +1416,6 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
 
   // ---- queue staging: the next CH (pod, class) entries; the chunk after them is fetched into registers meanwhile
   const ksched_pod_row* ffd_rows = reinterpret_cast<const ksched_pod_row*>(s.rows);
-  const int CH = T < kRunChunk ? T : kRunChunk;  // one entry per thread
   int cb = qi, buf = 0;
   uint32_t nx_pod = 0, nx_cls = KSCHED_NONE;
   if (tid < CH) {
@@ -1418,6 +1423,8 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
     uint32_t pd = 0, pc = KSCHED_NONE;
     if (idx < s.n_pods) { pd = s.order[idx]; pc = (uint32_t)ffd_rows[idx].reserved; }
     rc.q_pod[0][tid] = pd; rc.q_cls[0][tid] = pc;
+    const unsigned mm = __ballot_sync(0xffffffffu, pc != cls);  // CH is a multiple of 32: whole warps
+    if (lane == 0 && mm) atomicMin(&rc.q_end[0], (tid & ~31) + __ffs(mm) - 1);
     const int idx2 = idx + CH;
     if (idx2 < s.n_pods) { nx_pod = s.order[idx2]; nx_cls = (uint32_t)ffd_rows[idx2].reserved; }
   }
@@ -1505,6 +1512,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
   const int m_bias0 = n_mask > 0 ? (int)rc.m_self[0] - rc.m_skew[0] : 0, m_bias1 = n_mask > 1 ? (int)rc.m_self[1] - rc.m_skew[1] : 0;
   const bool m_rec0 = n_mask > 0 && rc.m_rec[0], m_rec1 = n_mask > 1 && rc.m_rec[1];
   int status = 0;
+  const bool lvl = s.use_level_run && n_mask == 0;
+  uint32_t* lvt = zv;  // level step: tie-breaks of the level's members (the zone words are unused when n_mask == 0)
+  int lvp = 0;
 
   while (true) {
     int i = qi - cb;
@@ -1520,16 +1530,145 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       i = 0;
       if (tid < CH) {
         rc.q_pod[buf][tid] = nx_pod; rc.q_cls[buf][tid] = nx_cls;
+        const unsigned mm = __ballot_sync(0xffffffffu, nx_cls != cls);
+        if (lane == 0 && mm) atomicMin(&rc.q_end[buf], (tid & ~31) + __ffs(mm) - 1);
         const int idx2 = cb + CH + tid;
         nx_cls = KSCHED_NONE;
         if (idx2 < s.n_pods) { nx_pod = s.order[idx2]; nx_cls = (uint32_t)ffd_rows[idx2].reserved; }
       }
       __syncthreads();
+      if (tid == 0) rc.q_end[buf ^ 1] = CH;  // the consumed buffer: its next atomicMin comes after the next chunk's first barrier
     }
     if (rc.q_cls[buf][i] != cls) break;  // class change or end of the first pass
+    int adv = 1;       // pods this iteration consumes
+    int mode = 0;      // 0: per-pod argmin below; 1: placed by a level / fill step; 2: nobody accepts (fresh node)
+    int k_avail = 1;   // pods of the class that may be consumed now: staged, same class, still queued
+    if (lvl) {
+      // ---- classes without mask-key spread: a node's verdict depends on the node alone, so
+      //  * level step: the n accepting nodes with the fewest pods take the next n pods one each, in tie order (each leaves
+      //    for the block of count + 1, behind every node of the level);
+      //  * fill step: the only accepting node takes pods until it refuses (resources / hostname limits);
+      //  * a fresh node is filled the same way in the iteration that creates it.
+      k_avail = rc.q_end[buf] - i;
+      k_avail = k_avail < qlen ? k_avail : qlen;
+      unsigned cmin = 0xFFFFFFFFu;
+      int ne = 0;
+      bool slow = false;
+      for (int a = tid; a < n_active; a += T) {
+        const uint32_t rp = rpv[a];
+        if ((rp & 0xFFFF) != 0 && !(rp & kRpDead)) {  // tombstones have no room
+          const unsigned cn = (unsigned)(hs->key[a] >> 32);
+          cmin = cn < cmin ? cn : cmin;
+          ++ne;
+          slow = slow || (rp & 0xFFFF) == kRoomSlow;
+        }
+      }
+      const unsigned wc = __reduce_min_sync(0xffffffffu, cmin);
+      const unsigned wn = __reduce_add_sync(0xffffffffu, (unsigned)ne) | (__any_sync(0xffffffffu, slow) ? 0x80000000u : 0u);
+      if (lane == 0) rc.red_key[parity][warp] = ((unsigned long long)wc << 32) | wn;
+      __syncthreads();
+      const unsigned long long rr = lane < nwarps ? rc.red_key[parity][lane] : 0xFFFFFFFF00000000ull;
+      parity ^= 1;
+      const unsigned c_min = __reduce_min_sync(0xffffffffu, (unsigned)(rr >> 32));
+      const int n_el = (int)__reduce_add_sync(0xffffffffu, (unsigned)rr & 0x7FFFFFFFu);
+      const bool any_slow = __any_sync(0xffffffffu, ((unsigned)rr >> 31) != 0);
+      if (!any_slow) {
+        if (n_el == 0) mode = 2;
+        else {
+          mode = 1;
+          const int lp = lvp;
+          lvp ^= 1;
+          if (tid == 0) rc.lv_cnt[lp ^ 1] = 0;  // last read before this iteration's first barrier
+          // the level's members append their tie-breaks to the list (any order)
+          for (int base = 0; base < n_active; base += T) {
+            const int a = base + tid;
+            bool mem = false;
+            unsigned tie = 0;
+            if (a < n_active) {
+              const uint32_t rp = rpv[a];
+              const unsigned long long key = hs->key[a];
+              mem = (rp & 0xFFFF) != 0 && !(rp & kRpDead) && (unsigned)(key >> 32) == c_min;
+              tie = (unsigned)key;
+              if (mem && n_el == 1) {  // fill: how many pods this node takes before it refuses
+                int cap = (int)(rp & 0xFFFF);
+                for (int j = 0; j < n_host; ++j) {
+                  const int times = rc.h_times[j], lim = rc.h_lim[j];
+                  if (!times || lim >= 0x10000) continue;
+                  if (lim >= 0xFFF0) { cap = 1; continue; }  // saturating counters nearby: one pod at a time
+                  const int td = (lim - (int)hc[j * kTopoCap + a]) / times + 1;
+                  cap = td < cap ? td : cap;
+                }
+                rc.lv_fill[lp] = cap < k_avail ? cap : k_avail;
+              }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, mem);
+            if (bal) {
+              const int src = __ffs(bal) - 1;
+              int pos0 = 0;
+              if (lane == src) pos0 = atomicAdd(&rc.lv_cnt[lp], __popc(bal));
+              pos0 = __shfl_sync(0xffffffffu, pos0, src);
+              if (mem) lvt[pos0 + __popc(bal & ((1u << lane) - 1u))] = tie;
+            }
+          }
+          __syncthreads();
+          const int n_s = rc.lv_cnt[lp];
+          const int t_fill = n_el == 1 ? rc.lv_fill[lp] : 1;
+          const int k_lvl = n_el == 1 ? 1 : (n_s < k_avail ? n_s : k_avail);
+          adv = n_el == 1 ? t_fill : k_lvl;
+          for (int a = tid; a < n_active; a += T) {
+            const uint32_t rp = rpv[a];
+            const unsigned long long key = hs->key[a];
+            if (!((rp & 0xFFFF) != 0 && !(rp & kRpDead) && (unsigned)(key >> 32) == c_min)) continue;
+            const unsigned tie = (unsigned)key;
+            int rank = 0;
+            if (n_el != 1) {
+              int j = 0;
+              for (; j + 4 <= n_s; j += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(lvt + j);
+                rank += (v.x < tie) + (v.y < tie) + (v.z < tie) + (v.w < tie);
+              }
+              for (; j < n_s; ++j) rank += lvt[j] < tie;
+              if (rank >= k_lvl) continue;
+            }
+            // the owner commits: pods i + rank .. i + rank + t - 1 of the chunk
+            const int t = t_fill;
+            uint32_t rp2 = rp - (uint32_t)t + ((uint32_t)t << 16);
+            for (int j = 0; j < n_host; ++j) {  // Topology.Record, hostname groups
+              const int times = rc.h_times[j];
+              const int old = hc[j * kTopoCap + a];
+              const int now = old + t * times > 0xFFFF ? 0xFFFF : old + t * times;
+              if (times) hc[j * kTopoCap + a] = (uint16_t)now;
+              if (now > rc.h_lim[j]) rp2 |= kRpDead;
+            }
+            const int count = (int)c_min + t;
+            const int tb = -(tick + rank + t);
+            unsigned long long nkey = order_key(count, tb);
+            const int nd = NE + hs->node[a];
+            for (int e = 0; e < t; ++e) rc.q_node[buf][i + rank + e] = nd;
+            if ((rp2 & 0xFFFF) == 0) {  // the class no longer fits by resources: does anything? (node_closed)
+              const int placed = (rp2 >> 16) & 0x7FFF;
+              long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+              for (int r = 0; r < kHotRes; ++r) { nq[r] = hs->q[r][a] + placed * p_req[r]; cb1[r] = hs->bound[r][a]; cb2[r] = hs->bound2[r][a]; }
+              const unsigned short fl = (unsigned short)(hs->flags[a] | ((p_res & 0xF) << 1));
+              if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
+                nkey = ~0ull;
+                hs->nn_last[a] = ((unsigned long long)(unsigned)count << 32) | (unsigned)tb;
+                atomicAdd(&rc.tomb, 1);
+              }
+            }
+            hs->key[a] = nkey;
+            rpv[a] = rp2;
+          }
+          tick += adv;
+        }
+      }
+    }
     // node-independent half of nextDomainTopologySpread, one domain per lane: min count over the pod's domains, the
     // domains within max-skew (count + self - min <= maxSkew)
     uint32_t okm0 = 0, okm1 = 0;
+    int fd0 = 0, fd1 = 0;
+    if (mode == 0) {
     if (n_mask > 0) {
       const bool valid = (m_reg0 >> lane) & 1;  // registered domains have ids < kRunDom
       const int cn = rc.cnt[warp][0][lane & (kRunDom - 1)];
@@ -1591,7 +1730,6 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
     const unsigned rp_l = lane < nwarps ? rc.red_pay[parity][lane] : 0;
     parity ^= 1;
     const unsigned long long wkey = warp_min_u64(rk);
-    int fd0 = 0, fd1 = 0;
     if (wkey != ~0ull) {
       const unsigned src = __ballot_sync(0xffffffffu, rk == wkey);
       const unsigned wp = __shfl_sync(0xffffffffu, rp_l, __ffs(src) - 1);
@@ -1649,7 +1787,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         __syncwarp();
       }
       ++tick;
-    } else {
+    } else mode = 2;
+    }
+    if (mode == 2) {
       // ---- nobody accepts: NewNode + Add replayed from a variant (templates: the one the variant was created from)
       if (n_new >= MAXN || n_active >= kActCap || (topo && n_active >= kTopoCap) || rc.n_var == 0) { status = 1; break; }
       bool ok = true;
@@ -1669,6 +1809,19 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       if (vi < 0) { status = 1; break; }
       const RunVariant& v = rc.var[vi];
       const int n = n_new, a = n_active;
+      // fill step on the fresh node: the further pods of the class it takes while it is the only accepting node
+      int t_more = 0;
+      if (lvl && k_avail > 1 && !(v.rp & kRpDead) && (v.rp & 0xFFFF) != kRoomSlow) {
+        int cap = (int)(v.rp & 0xFFFF);
+        for (int j = 0; j < n_host; ++j) {
+          const int times = rc.h_times[j], lim = rc.h_lim[j];
+          if (!times || lim >= 0x10000) continue;
+          if (lim >= 0xFFF0) { cap = 0; continue; }
+          const int td = (lim - times) / times + 1;  // the count is `times` after the first pod
+          cap = td < cap ? td : cap;
+        }
+        t_more = cap < k_avail - 1 ? cap : k_avail - 1;
+      }
       for (int w = tid; w < W32; w += T) s.nn_opts[(size_t)w * MAXN + n] = v.opts[w];
       if (tid < c.n_keys) s.nn_vals[(size_t)tid * MAXN + n] = v.vals[tid];
       if (tid < KSCHED_MAX_RES) s.nn_req[(size_t)tid * MAXN + n] = v.q[tid];
@@ -1698,6 +1851,30 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         }
         if (n_mask > 0) zv[a] = (1u << fd0) | (3u << 16);
         if (n_mask > 1) zv[kTopoCap + a] = (1u << fd1) | (3u << 16);
+        if (t_more > 0) {  // pods i + 1 .. i + t_more (not dead, exact room: checked above)
+          uint32_t rp2 = v.rp - (uint32_t)t_more + ((uint32_t)t_more << 16);
+          for (int j = 0; j < n_host; ++j) {
+            const int times = rc.h_times[j];
+            const int now = times + t_more * times > 0xFFFF ? 0xFFFF : times + t_more * times;
+            if (times) hc[j * kTopoCap + a] = (uint16_t)now;
+            if (now > rc.h_lim[j]) rp2 |= kRpDead;
+          }
+          unsigned long long nkey = order_key(1 + t_more, -(tick + 1 + t_more));
+          if ((rp2 & 0xFFFF) == 0) {  // full for the class: closed for every class? (same test as the accept that fills a node)
+            long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+            for (int r = 0; r < kHotRes; ++r) { nq[r] = v.q[r] + t_more * p_req[r]; cb1[r] = v.b1[r]; cb2[r] = v.b2[r]; }
+            const unsigned short fl = (unsigned short)(v.fl | ((p_res & 0xF) << 1));
+            if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
+              nkey = ~0ull;
+              hs->nn_last[a] = ((unsigned long long)(unsigned)(1 + t_more) << 32) | (unsigned)(-(tick + 1 + t_more));
+              atomicAdd(&rc.tomb, 1);
+            }
+          }
+          hs->key[a] = nkey;
+          rpv[a] = rp2;
+          for (int e = 1; e <= t_more; ++e) rc.q_node[buf][i + e] = NE + n;
+        }
       }
       if (n_mask > 0) {
         if (lane == 0) {
@@ -1706,13 +1883,14 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         }
         __syncwarp();
       }
-      ++tick;
+      adv = 1 + t_more;
+      tick += adv;
       ++n_new;
       ++n_active;
     }
-    // ---- the pod is placed: pop it
-    ++qi;
-    --qlen;
+    // ---- the pods are placed: pop them
+    qi += adv;
+    qlen -= adv;
     if (qlen == 0) break;
   }
   __syncthreads();

@@ -108,6 +108,7 @@ struct PackState {
   int use_warp_loop;                 // register-resident warp loop enabled (KSCHED_NO_WARPLOOP=1 turns it off for A/B timing)
   int use_class_run;                 // class-run loop enabled (KSCHED_NO_CLASSRUN=1 turns it off for A/B timing)
   int use_level_step;                // level step of the warp loop enabled (KSCHED_NO_LEVELSTEP=1 turns it off for A/B timing)
+  int use_level_run;                 // class_run: level / fill steps for classes without mask-key spread (KSCHED_NO_LEVELRUN=1: off)
   // topology counters
   int32_t* grp_cnt;                  // [n_groups][64]
   uint64_t* grp_registered;          // [n_groups]
