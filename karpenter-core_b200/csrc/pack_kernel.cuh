@@ -321,6 +321,9 @@ struct LoopVars {
   // the step has just opened node slot fresh_a for a pod of class fresh_cls and the node is still open (class_run captures it)
   int fresh_valid, fresh_a;
   uint32_t fresh_cls;
+  // the step failed and depends on nothing but (class, placements so far, relaxations so far): no topology relation of
+  // any kind, no relaxation left. pack_kernel requeues the following pods of the class without evaluating them again.
+  int fail_memo;
 };
 
 // ---- existing-node run ("water-fill") --------------------------------------------------------------------------------
@@ -457,6 +460,7 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
 #endif
     const uint32_t pod = cur.pod, cls = (uint32_t)cur.cls64;
     L.fresh_valid = 0;
+    L.fail_memo = 0;
     const ksched_pod_row& row = g_row;
     const uint32_t p_res = cur.res;
     long long preq[kHotRes];
@@ -1042,6 +1046,7 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
       }
       ++qlen;
       if (nx != KSCHED_NONE) ++epoch;  // a successful relaxation resets the lastLen map
+      L.fail_memo = nx == KSCHED_NONE && !has_topo && !pt_nonempty;
       __syncthreads();
     }
   }
@@ -1515,6 +1520,13 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
   const bool lvl = s.use_level_run && n_mask == 0;
   uint32_t* lvt = zv;  // level step: tie-breaks of the level's members (the zone words are unused when n_mask == 0)
   int lvp = 0;
+#ifdef KSCHED_PROFILE_PACK
+  const long long cr_t0 = clock64();
+  int cr_it[4] = {0, 0, 0, 0};  // iterations: level, fill, fresh, per-pod argmin
+#define CR_IT(k) { ++cr_it[k]; }
+#else
+#define CR_IT(k)
+#endif
 
   while (true) {
     int i = qi - cb;
@@ -1615,6 +1627,7 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
           const int t_fill = n_el == 1 ? rc.lv_fill[lp] : 1;
           const int k_lvl = n_el == 1 ? 1 : (n_s < k_avail ? n_s : k_avail);
           adv = n_el == 1 ? t_fill : k_lvl;
+          CR_IT(n_el == 1 ? 1 : 0)
           for (int a = tid; a < n_active; a += T) {
             const uint32_t rp = rpv[a];
             const unsigned long long key = hs->key[a];
@@ -1669,6 +1682,7 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
     uint32_t okm0 = 0, okm1 = 0;
     int fd0 = 0, fd1 = 0;
     if (mode == 0) {
+    CR_IT(3)
     if (n_mask > 0) {
       const bool valid = (m_reg0 >> lane) & 1;  // registered domains have ids < kRunDom
       const int cn = rc.cnt[warp][0][lane & (kRunDom - 1)];
@@ -1808,73 +1822,79 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         if ((n_mask < 1 || rc.var[v2].dom[0] == fd0) && (n_mask < 2 || rc.var[v2].dom[1] == fd1)) vi = v2;
       if (vi < 0) { status = 1; break; }
       const RunVariant& v = rc.var[vi];
-      const int n = n_new, a = n_active;
-      // fill step on the fresh node: the further pods of the class it takes while it is the only accepting node
-      int t_more = 0;
-      if (lvl && k_avail > 1 && !(v.rp & kRpDead) && (v.rp & 0xFFFF) != kRoomSlow) {
-        int cap = (int)(v.rp & 0xFFFF);
-        for (int j = 0; j < n_host; ++j) {
-          const int times = rc.h_times[j], lim = rc.h_lim[j];
-          if (!times || lim >= 0x10000) continue;
-          if (lim >= 0xFFF0) { cap = 0; continue; }
-          const int td = (lim - times) / times + 1;  // the count is `times` after the first pod
-          cap = td < cap ? td : cap;
+      CR_IT(2)
+      // Fill step on the fresh node: it takes `cap` further pods of the class while it is the only accepting node and then
+      // refuses (room 0 or a hostname limit reached). With an exact cap the run needs F such nodes in a row, m = 1 + cap pods
+      // each: all of them are created in this iteration, one per thread (slot a belongs to thread a % T as everywhere).
+      int cap = 0, F = 1;
+      bool cap_exact = false;
+      if (lvl && (v.rp & 0xFFFF) != kRoomSlow) {
+        cap_exact = true;
+        if (!(v.rp & kRpDead)) {
+          cap = (int)(v.rp & 0xFFFF);
+          for (int j = 0; j < n_host; ++j) {
+            const int times = rc.h_times[j], lim = rc.h_lim[j];
+            if (!times || lim >= 0x10000) continue;
+            if (lim >= 0xFFF0) { cap = 0; cap_exact = false; continue; }  // saturating counters nearby: one pod at a time
+            const int td = (lim - times) / times + 1;  // the count is `times` after the first pod
+            cap = td < cap ? td : cap;
+          }
         }
-        t_more = cap < k_avail - 1 ? cap : k_avail - 1;
       }
-      for (int w = tid; w < W32; w += T) s.nn_opts[(size_t)w * MAXN + n] = v.opts[w];
-      if (tid < c.n_keys) s.nn_vals[(size_t)tid * MAXN + n] = v.vals[tid];
-      if (tid < KSCHED_MAX_RES) s.nn_req[(size_t)tid * MAXN + n] = v.q[tid];
-      if (tid == a % T) {  // the new slot's owner
-        hs->key[a] = order_key(1, tick + 1);
+      const int m = 1 + cap;
+      if (cap_exact) {
+        F = (k_avail + m - 1) / m;
+        if (F > MAXN - n_new) F = MAXN - n_new;
+        if (F > kActCap - n_active) F = kActCap - n_active;
+        if (topo && F > kTopoCap - n_active) F = kTopoCap - n_active;
+      }
+      const int K = k_avail < F * m ? k_avail : F * m;  // pods consumed (k_avail is 1 outside level mode: F = m = K = 1)
+      for (int idx = tid; idx < W32 * F; idx += T) { const int w = idx / F, j = idx - w * F; s.nn_opts[(size_t)w * MAXN + n_new + j] = v.opts[w]; }
+      for (int idx = tid; idx < c.n_keys * F; idx += T) { const int k = idx / F, j = idx - k * F; s.nn_vals[(size_t)k * MAXN + n_new + j] = v.vals[k]; }
+      for (int idx = tid; idx < KSCHED_MAX_RES * F; idx += T) { const int r = idx / F, j = idx - r * F; s.nn_req[(size_t)r * MAXN + n_new + j] = v.q[r]; }
+      for (int e = tid; e < K; e += T) rc.q_node[buf][i + e] = NE + n_new + e / m;
+      if (tid == 0)
+        for (int j = 0; j < n_host; ++j) if (rc.h_times[j]) rc.h_inc[j] = rc.h_inc[j] + F;
+      for (int j = (tid + T - n_active % T) % T; j < F; j += T) {  // the new slots this thread owns
+        const int a = n_active + j, n = n_new + j;
+        const int t = (K - j * m < m ? K - j * m : m) - 1;  // further pods on this node (the last one may get fewer)
+        const int tk = tick + j * m;                          // tick of its first pod
 #pragma unroll
         for (int r = 0; r < kHotRes; ++r) { hs->q[r][a] = v.q[r]; hs->bound[r][a] = v.b1[r]; hs->bound2[r][a] = v.b2[r]; }
         hs->node[a] = n;
         hs->flags[a] = v.fl;
         hs->absorbed[a] = simple ? cls : KSCHED_NONE;
         hs->rejected[a] = KSCHED_NONE;
-        rpv[a] = v.rp;
         s.nn_meta[n] = v.meta;
         s.nn_tmpl[n] = (uint8_t)(v.fl >> 8);
         s.nn_req_present[n] = v.qp;
         s.nn_hp[n] = 0;
         s.nn_count[n] = 1;
-        s.nn_tb[n] = tick + 1;
-        rc.q_node[buf][i] = NE + n;
-        for (int j = 0; j < n_host; ++j) {
-          const int times = rc.h_times[j];
-          hc[j * kTopoCap + a] = (uint16_t)times;
-          if (times) {
-            s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n] = (uint16_t)times;
-            rc.h_inc[j] = rc.h_inc[j] + 1;
-          }
-        }
+        s.nn_tb[n] = tk + 1;
         if (n_mask > 0) zv[a] = (1u << fd0) | (3u << 16);
         if (n_mask > 1) zv[kTopoCap + a] = (1u << fd1) | (3u << 16);
-        if (t_more > 0) {  // pods i + 1 .. i + t_more (not dead, exact room: checked above)
-          uint32_t rp2 = v.rp - (uint32_t)t_more + ((uint32_t)t_more << 16);
-          for (int j = 0; j < n_host; ++j) {
-            const int times = rc.h_times[j];
-            const int now = times + t_more * times > 0xFFFF ? 0xFFFF : times + t_more * times;
-            if (times) hc[j * kTopoCap + a] = (uint16_t)now;
-            if (now > rc.h_lim[j]) rp2 |= kRpDead;
-          }
-          unsigned long long nkey = order_key(1 + t_more, -(tick + 1 + t_more));
-          if ((rp2 & 0xFFFF) == 0) {  // full for the class: closed for every class? (same test as the accept that fills a node)
-            long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
-#pragma unroll
-            for (int r = 0; r < kHotRes; ++r) { nq[r] = v.q[r] + t_more * p_req[r]; cb1[r] = v.b1[r]; cb2[r] = v.b2[r]; }
-            const unsigned short fl = (unsigned short)(v.fl | ((p_res & 0xF) << 1));
-            if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
-              nkey = ~0ull;
-              hs->nn_last[a] = ((unsigned long long)(unsigned)(1 + t_more) << 32) | (unsigned)(-(tick + 1 + t_more));
-              atomicAdd(&rc.tomb, 1);
-            }
-          }
-          hs->key[a] = nkey;
-          rpv[a] = rp2;
-          for (int e = 1; e <= t_more; ++e) rc.q_node[buf][i + e] = NE + n;
+        uint32_t rp2 = t > 0 ? v.rp - (uint32_t)t + ((uint32_t)t << 16) : v.rp;
+        for (int jj = 0; jj < n_host; ++jj) {
+          const int times = rc.h_times[jj];
+          const int now = times + t * times > 0xFFFF ? 0xFFFF : times + t * times;
+          hc[jj * kTopoCap + a] = (uint16_t)now;
+          if (times) s.grp_host[(size_t)rc.h_row[jj] * hstride + NE + n] = (uint16_t)times;  // (the run's write-back stores the final count)
+          if (t > 0 && now > rc.h_lim[jj]) rp2 |= kRpDead;
         }
+        unsigned long long nkey = t > 0 ? order_key(1 + t, -(tk + 1 + t)) : order_key(1, tk + 1);
+        if (t > 0 && (rp2 & 0xFFFF) == 0) {  // full for the class: closed for every class? (same test as the accept that fills a node)
+          long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+          for (int r = 0; r < kHotRes; ++r) { nq[r] = v.q[r] + t * p_req[r]; cb1[r] = v.b1[r]; cb2[r] = v.b2[r]; }
+          const unsigned short fl = (unsigned short)(v.fl | ((p_res & 0xF) << 1));
+          if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
+            nkey = ~0ull;
+            hs->nn_last[a] = ((unsigned long long)(unsigned)(1 + t) << 32) | (unsigned)(-(tk + 1 + t));
+            atomicAdd(&rc.tomb, 1);
+          }
+        }
+        hs->key[a] = nkey;
+        rpv[a] = rp2;
       }
       if (n_mask > 0) {
         if (lane == 0) {
@@ -1883,10 +1903,10 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         }
         __syncwarp();
       }
-      adv = 1 + t_more;
-      tick += adv;
-      ++n_new;
-      ++n_active;
+      adv = K;
+      tick += K;
+      n_new += F;
+      n_active += F;
     }
     // ---- the pods are placed: pop them
     qi += adv;
@@ -1951,6 +1971,14 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
     }
     n_active -= rc.tomb;
   }
+#ifdef KSCHED_PROFILE_PACK
+  if (tid == 0) {
+    const int b = lvl ? 32 : 36;  // [cycles, pods, level+fill iterations, fresh iterations] ; per-pod iterations go to 44 / 45
+    s.counters[b] += clock64() - cr_t0; s.counters[b + 1] += placed_total; s.counters[b + 2] += cr_it[0] + cr_it[1]; s.counters[b + 3] += cr_it[2];
+    s.counters[lvl ? 44 : 45] += cr_it[3];
+    s.counters[46] += cr_it[1];
+  }
+#endif
   if (tid == 0) {
     const int qcap = s.n_pods + 1;
     io.qi = qi; io.head = (io.head + placed_total) % qcap; io.qlen = qlen; io.tick = tick; io.seq = seq0 + placed_total; io.n_active = n_active; io.n_new = n_new; io.parity = parity;
@@ -2001,6 +2029,9 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
   uint32_t run_block_cls = KSCHED_NONE;
   int run_skip = 0, run_fail = 0;
   uint32_t xrun_block_cls = KSCHED_NONE;  // existing-node run: class the existing nodes have no room left for
+  // failure memo: the class whose Scheduler.add has just failed, valid while nothing is placed (seq) or relaxed (epoch)
+  uint32_t fail_cls = KSCHED_NONE, fail_epoch = 0;
+  int fail_seq = 0;
 
   for (int i = tid; i < s.n_pods; i += blockDim.x) {
     s.queue[i] = s.order[i];
@@ -2020,6 +2051,37 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
   const bool fast_allowed = NE == 0 && !s.count_visited;
 
   while (qlen > 0) {
+    // ---- failure memo: pods at the head of the queue of the class that has just failed fail again (same class, same state:
+    // scheduler.go:117-123 pushes them back unchanged, queue.go:61-68) - requeued in one step, up to one per thread
+    if (fast_allowed && fail_cls != KSCHED_NONE && seq == fail_seq && epoch == fail_epoch) {
+      const int T = blockDim.x;
+      int lim = qlen < T ? qlen : T;
+      if (qi < s.n_pods && s.n_pods - qi < lim) lim = s.n_pods - qi;  // the first pass ends with its last pod
+      uint32_t pj = 0;
+      bool stop = true;
+      if (tid < lim) {
+        int pos = head + tid;
+        if (pos >= qcap) pos -= qcap;
+        pj = s.queue[pos];
+        stop = s.pod_class[pj] != fail_cls || (s.last_epoch[pj] == epoch && s.last_len[pj] == qlen);  // Pop() would stop here
+      }
+      unsigned first, unused;
+      block_min2_u32_db(stop ? (unsigned)tid : 0xFFFFFFFFu, 0u, g_red, parity, &first, &unused);
+      const int k = first < (unsigned)lim ? (int)first : lim;
+      if (k > 0) {
+        if (tid < k) {
+          s.queue[(head + qlen + tid) % qcap] = pj;  // (every read of the old entries happened before the barrier above)
+          s.last_len[pj] = qlen;
+          s.last_epoch[pj] = epoch;
+        }
+        if (qi < s.n_pods) qi += k;
+        head = (head + k) % qcap;
+        add_calls += k;
+        __syncthreads();
+        if (qi < s.n_pods) nxt = load_pod_regs(ffd_rows + qi, s.order[qi]);
+        continue;
+      }
+    }
     // ---- register-resident mode (see warp_resident_loop): entered when the next pod is plain and <= 32 nodes are open
     if (fast_allowed && s.use_warp_loop && !fresh_valid && qi < s.n_pods && n_active > 0 && n_active <= 32 && simple_pod_regs(nxt)) {
       __syncthreads();
@@ -2116,8 +2178,9 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_kernel() {
 #ifdef KSCHED_PROFILE_PACK
     if (tid == 0) s.counters[8 + 9] += 1;
 #endif
-    LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited, pt_class, row_class, 0, 0, KSCHED_NONE};
+    LoopVars L{head, qlen, n_new, n_active, tick, seq, parity, fatal, epoch, pt_nonempty, nodes_visited, pt_class, row_class, 0, 0, KSCHED_NONE, 0};
     generic_step(cur, first_pass, fpos_first, L);
+    if (L.fail_memo) { fail_cls = (unsigned)cur.cls64; fail_seq = L.seq; fail_epoch = L.epoch; } else fail_cls = KSCHED_NONE;
     head = L.head; qlen = L.qlen; n_new = L.n_new; n_active = L.n_active; tick = L.tick; seq = L.seq; parity = L.parity; fatal = L.fatal;
     epoch = L.epoch; pt_nonempty = L.pt_nonempty; nodes_visited = L.nodes_visited; pt_class = L.pt_class; row_class = L.row_class;
     fresh_valid = L.fresh_valid; fresh_a = L.fresh_a; fresh_cls = L.fresh_cls;
