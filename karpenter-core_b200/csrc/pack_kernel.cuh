@@ -1292,6 +1292,28 @@ struct RunCtx {
 };
 __shared__ RunCtx g_rc;
 
+// ---- mask run: the class-run loop for ONE spread relation over a mask key (zone spread), driven by warp 0 alone ----------
+// The accepting nodes are kept in lists, one per domain they are pinned to plus one for the nodes not pinned yet, and every
+// list in buckets by pod count: inside a bucket the reference's order is "nodes re-keyed in this run, newest first" (an
+// accepting node moves to the FRONT of the block of count + 1: a stack), then the nodes untouched so far by tie-break (sorted
+// once per run by counting inside the bucket), then (count 1) the nodes created in this run in creation order. A pod's
+// node is then the smallest head key over the lists of the admissible domains: ~60 warp instructions and no block barrier
+// per pod instead of a scan of every open node. Anything the lists cannot represent hands the run back to the per-pod loop.
+constexpr int kM1Dom = 8;             // domains with ids < kM1Dom; list kM1Dom holds the nodes that admit every registered domain
+constexpr int kM1Lists = kM1Dom + 1;
+constexpr int kM1Lv = 12;             // pod counts < kM1Lv
+constexpr uint16_t kM1None = 0xFFFF;
+struct M1Ctx {
+  uint16_t stk[kM1Lv][kM1Lists];      // bucket: re-keyed nodes, newest first (linked through nxt)
+  uint16_t ap[kM1Lv][kM1Lists];       // bucket: untouched nodes arr[ap .. ae) in tie order
+  uint16_t ae[kM1Lv][kM1Lists];
+  uint16_t fh[kM1Dom], ft[kM1Dom];    // nodes created in this run and pinned to the domain (count 1), creation order
+  int bcnt[kM1Lv * kM1Lists];         // build: members per bucket (bucket = list * kM1Lv + count)
+  int bad;                            // build: a node the lists cannot represent
+  int out_adv, out_reason, out_tick, out_n_new, out_n_active;
+};
+__shared__ M1Ctx g_m1;
+
 struct RunIO {
   int qi, head, qlen, tick, seq, n_active, n_new, parity;
   long long add_calls;
@@ -1518,6 +1540,12 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
   const bool m_rec0 = n_mask > 0 && rc.m_rec[0], m_rec1 = n_mask > 1 && rc.m_rec[1];
   int status = 0;
   const bool lvl = s.use_level_run && n_mask == 0;
+  // mask run (see M1Ctx): one mask-key spread relation, domains and counts small enough for the lists
+  M1Ctx& m1 = g_m1;
+  bool m1_ok = s.use_mask_run && n_mask == 1 && (m_reg0 >> kM1Dom) == 0;
+  bool m1_built = false;
+  uint16_t* m1_arr = reinterpret_cast<uint16_t*>(zv + kTopoCap);  // the second mask relation's plane is unused (n_mask == 1)
+  uint16_t* m1_nxt = m1_arr + kTopoCap;
   uint32_t* lvt = zv;  // level step: tie-breaks of the level's members (the zone words are unused when n_mask == 0)
   int lvp = 0;
 #ifdef KSCHED_PROFILE_PACK
@@ -1552,6 +1580,255 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       if (tid == 0) rc.q_end[buf ^ 1] = CH;  // the consumed buffer: its next atomicMin comes after the next chunk's first barrier
     }
     if (rc.q_cls[buf][i] != cls) break;  // class change or end of the first pass
+    if (m1_ok) {
+      if (!m1_built) {
+        // ---- build the lists (once per call; nothing of this call has been committed yet, so nn_last is free as scratch)
+        m1_built = true;
+        uint8_t* t_b = reinterpret_cast<uint8_t*>(hs->nn_last);              // bucket of slot a (0xFF: not a member)
+        uint16_t* t_pos = reinterpret_cast<uint16_t*>(t_b + kTopoCap);        // its arrival order inside the bucket
+        uint16_t* t_slot = t_pos + kTopoCap;                                  // members, bucket by bucket, unsorted
+        uint32_t* t_tie = reinterpret_cast<uint32_t*>(t_slot + kTopoCap);     // their tie-breaks
+        for (int b = tid; b < kM1Lv * kM1Lists; b += T) {
+          m1.bcnt[b] = 0;
+          (&m1.stk[0][0])[b] = kM1None;
+        }
+        if (tid < kM1Dom) { m1.fh[tid] = kM1None; m1.ft[tid] = kM1None; }
+        if (tid == 0) m1.bad = 0;
+        __syncthreads();
+        for (int a = tid; a < n_active; a += T) {
+          const uint32_t rp = rpv[a];
+          int b = 0xFF;
+          if ((rp & 0xFFFF) != 0 && !(rp & kRpDead)) {
+            const uint32_t z = zv[a], adm = z & 0xFFFF;
+            const unsigned cn = (unsigned)(hs->key[a] >> 32);
+            int list = -1;
+            if (adm && !(adm & (adm - 1)) && (z & (1u << 16))) {  // pinned to one domain
+              if (adm & m_reg0) list = __ffs(adm) - 1;             // (a domain that is not registered never admits a pod)
+            } else if ((adm & m_reg0) == m_reg0) list = kM1Dom;     // admits every registered domain
+            else if (adm & m_reg0) m1.bad = 1;                      // some of them: per-pod loop
+            if (list >= 0) {
+              if (cn >= (unsigned)kM1Lv) m1.bad = 1;
+              else { b = list * kM1Lv + (int)cn; t_pos[a] = (uint16_t)atomicAdd(&m1.bcnt[b], 1); }
+            }
+          }
+          t_b[a] = (uint8_t)b;
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the bucket sizes -> arr segments
+          int run = 0;
+          for (int b0 = 0; b0 < kM1Lv * kM1Lists; b0 += 32) {
+            const int b = b0 + lane;
+            const int v = b < kM1Lv * kM1Lists ? m1.bcnt[b] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (b < kM1Lv * kM1Lists) {
+              const int list = b / kM1Lv, lv = b - list * kM1Lv;
+              m1.ap[lv][list] = (uint16_t)(run + inc - v);
+              m1.ae[lv][list] = (uint16_t)(run + inc);
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
+          }
+        }
+        __syncthreads();
+        const bool bad = m1.bad != 0;
+        if (!bad) {
+          for (int a = tid; a < n_active; a += T) {
+            const int b = t_b[a];
+            if (b == 0xFF) continue;
+            const int list = b / kM1Lv, lv = b - list * kM1Lv;
+            const int j = m1.ap[lv][list] + t_pos[a];
+            t_slot[j] = (uint16_t)a;
+            t_tie[j] = (uint32_t)hs->key[a];
+          }
+        }
+        __syncthreads();
+        if (!bad) {
+          for (int a = tid; a < n_active; a += T) {
+            const int b = t_b[a];
+            if (b == 0xFF) continue;
+            const int list = b / kM1Lv, lv = b - list * kM1Lv;
+            const int p0 = m1.ap[lv][list], p1 = m1.ae[lv][list];
+            const uint32_t tie = (uint32_t)hs->key[a];
+            int rank = 0;
+            for (int j = p0; j < p1; ++j) rank += t_tie[j] < tie;
+            m1_arr[p0 + rank] = (uint16_t)a;
+          }
+        }
+        __syncthreads();
+        if (bad) m1_ok = false;
+      }
+    }
+    if (m1_ok) {
+      if (warp == 0) {
+        const int L = lane;
+        const unsigned FULL = 0xffffffffu;
+        int cnt_d = L < kM1Dom ? rc.cnt[0][0][L] : 0;
+        const bool valid = L < kM1Dom && ((m_reg0 >> L) & 1);
+        auto bucket_head = [&](int lv) -> int {  // first node of bucket (lv, L) in the reference's order, -1: empty
+          const uint16_t st = m1.stk[lv][L];
+          if (st != kM1None) return st;
+          const int p = m1.ap[lv][L];
+          if (p < m1.ae[lv][L]) return m1_arr[p];
+          if (lv == 1 && L < kM1Dom && m1.fh[L] != kM1None) return m1.fh[L];
+          return -1;
+        };
+        int lev = kM1Lv;
+        if (L < kM1Lists) { lev = 0; while (lev < kM1Lv && bucket_head(lev) < 0) ++lev; }
+        int li = i, ltick = tick, lnew = n_new, lact = n_active;
+        int i_end = rc.q_end[buf];
+        if (i + qlen < i_end) i_end = i + qlen;
+        int reason = 0;  // 0: the staged entries of the class are consumed; 1: the pod at li needs generic_step; 2: per-pod loop from li on
+        while (li < i_end) {
+          const int mn = __reduce_min_sync(FULL, valid ? cnt_d : INT32_MAX);
+          const bool allowed = valid && (long long)cnt_d + m_bias0 <= (long long)mn;
+          const unsigned okm = __ballot_sync(FULL, allowed);
+          int hslot = -1;
+          if (L < kM1Lists && lev < kM1Lv && (L < kM1Dom ? allowed : okm != 0)) hslot = bucket_head(lev);
+          const unsigned long long key = hslot >= 0 ? hs->key[hslot] : ~0ull;
+          const unsigned long long wkey = warp_min_u64(key);
+          if (wkey != ~0ull) {
+            const int wl = __ffs(__ballot_sync(FULL, key == wkey)) - 1;
+            const int a = __shfl_sync(FULL, hslot, wl);
+            const uint32_t rp = rpv[a];
+            if ((rp & 0xFFFF) == kRoomSlow) { reason = 1; break; }  // the winner needs the full evaluation
+            int d = wl;
+            const bool pin = wl == kM1Dom;
+            if (pin) {  // the placement pins the node's domain: fewest pods, lowest id among the admissible ones (run_pick)
+              const int mc = __reduce_min_sync(FULL, allowed ? cnt_d : INT32_MAX);
+              d = __ffs(__ballot_sync(FULL, allowed && cnt_d == mc)) - 1;
+              if (!((rc.m_neutral[0] >> d) & 1) || !((zv[a] & (1u << 17)) || rc.m_wk[0])) { reason = 1; break; }
+            }
+            if (L == wl) {  // pop the head of the winner's list
+              const uint16_t st = m1.stk[lev][L];
+              if (st != kM1None) m1.stk[lev][L] = m1_nxt[st];
+              else if (m1.ap[lev][L] < m1.ae[lev][L]) m1.ap[lev][L] = m1.ap[lev][L] + 1;
+              else { const uint16_t f = m1.fh[L]; m1.fh[L] = m1_nxt[f]; if (m1_nxt[f] == kM1None) m1.ft[L] = kM1None; }
+              while (lev < kM1Lv && bucket_head(lev) < 0) ++lev;
+            }
+            // ---- commit (the per-pod loop's commit, relation by relation on the first lanes)
+            const int c = (int)(wkey >> 32);
+            uint32_t rp2 = rp - 1 + (1u << 16);
+            bool dead_l = false;
+            if (L < n_host) {  // Topology.Record, hostname groups
+              const int times = rc.h_times[L];
+              const int old = hc[L * kTopoCap + a];
+              const int now = old + times > 0xFFFF ? 0xFFFF : old + times;
+              if (times) hc[L * kTopoCap + a] = (uint16_t)now;
+              dead_l = now > rc.h_lim[L];
+            }
+            if (__any_sync(FULL, dead_l)) rp2 |= kRpDead;
+            unsigned long long nkey = order_key(c + 1, -(ltick + 1));
+            if (L == 0) {
+              const int n = hs->node[a];
+              if (pin) {  // requirements.Add(In{d}) on the node
+                const int k = rc.m_key[0];
+                zv[a] = (1u << d) | (3u << 16);
+                s.nn_vals[(size_t)k * MAXN + n] = 1ull << d;
+                s.nn_meta[n] = (s.nn_meta[n] | (1ull << (KSCHED_META_PRESENT_SHIFT + k))) & ~(1ull << (KSCHED_META_COMPLEMENT_SHIFT + k));
+              }
+              rc.q_node[buf][li] = NE + n;
+              if ((rp2 & 0xFFFF) == 0) {  // the class no longer fits by resources: does anything? (node_closed)
+                const int placed = (rp2 >> 16) & 0x7FFF;
+                long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+                for (int r = 0; r < kHotRes; ++r) { nq[r] = hs->q[r][a] + placed * p_req[r]; cb1[r] = hs->bound[r][a]; cb2[r] = hs->bound2[r][a]; }
+                const unsigned short fl = (unsigned short)(hs->flags[a] | ((p_res & 0xF) << 1));
+                if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
+                  nkey = ~0ull;
+                  hs->nn_last[a] = ((unsigned long long)(unsigned)(c + 1) << 32) | (unsigned)(-(ltick + 1));
+                  rc.tomb = rc.tomb + 1;
+                }
+              }
+              hs->key[a] = nkey;
+              rpv[a] = rp2;
+            }
+            const bool surv = (rp2 & 0xFFFF) != 0 && !(rp2 & kRpDead);  // still accepts the class: front of the block of count + 1
+            if (surv) {
+              if (c + 1 >= kM1Lv) reason = 2;
+              else if (L == d) {
+                m1_nxt[a] = m1.stk[c + 1][L];
+                m1.stk[c + 1][L] = (uint16_t)a;
+                if (c + 1 < lev) lev = c + 1;
+              }
+            }
+            if (m_rec0 && L == d) ++cnt_d;
+            ++ltick;
+            ++li;
+            __syncwarp();
+            if (reason == 2) break;
+          } else {
+            // ---- nobody accepts: NewNode + Add replayed from the variant of the domain a fresh node gets
+            if (lnew >= MAXN || lact >= kActCap || lact >= kTopoCap || rc.n_var == 0) { reason = 1; break; }
+            bool ok = true;
+            for (int j = 0; j < n_host; ++j) ok = ok && rc.h_lim[j] >= 0;
+            const unsigned cand = rc.m_tallow[0] & okm;
+            if (!ok || !cand) { reason = 1; break; }
+            const bool in_c = (cand >> L) & 1;  // (cand is a subset of okm: lanes below kM1Dom)
+            const int mc = __reduce_min_sync(FULL, in_c ? cnt_d : INT32_MAX);
+            const int fd = __ffs(__ballot_sync(FULL, in_c && cnt_d == mc)) - 1;
+            int vi = -1;
+            for (int v2 = 0; v2 < rc.n_var && vi < 0; ++v2) if (rc.var[v2].dom[0] == fd) vi = v2;
+            if (vi < 0) { reason = 1; break; }
+            const RunVariant& v = rc.var[vi];
+            const int n = lnew, a = lact;
+            for (int w = L; w < W32; w += 32) s.nn_opts[(size_t)w * MAXN + n] = v.opts[w];
+            if (L < c.n_keys) s.nn_vals[(size_t)L * MAXN + n] = v.vals[L];
+            if (L < KSCHED_MAX_RES) s.nn_req[(size_t)L * MAXN + n] = v.q[L];
+            if (L < n_host) {
+              const int times = rc.h_times[L];
+              hc[L * kTopoCap + a] = (uint16_t)times;
+              if (times) {
+                s.grp_host[(size_t)rc.h_row[L] * hstride + NE + n] = (uint16_t)times;
+                rc.h_inc[L] = rc.h_inc[L] + 1;
+              }
+            }
+            if (L == 0) {
+              hs->key[a] = order_key(1, ltick + 1);
+#pragma unroll
+              for (int r = 0; r < kHotRes; ++r) { hs->q[r][a] = v.q[r]; hs->bound[r][a] = v.b1[r]; hs->bound2[r][a] = v.b2[r]; }
+              hs->node[a] = n;
+              hs->flags[a] = v.fl;
+              hs->absorbed[a] = simple ? cls : KSCHED_NONE;
+              hs->rejected[a] = KSCHED_NONE;
+              rpv[a] = v.rp;
+              s.nn_meta[n] = v.meta;
+              s.nn_tmpl[n] = (uint8_t)(v.fl >> 8);
+              s.nn_req_present[n] = v.qp;
+              s.nn_hp[n] = 0;
+              s.nn_count[n] = 1;
+              s.nn_tb[n] = ltick + 1;
+              rc.q_node[buf][li] = NE + n;
+              zv[a] = (1u << fd) | (3u << 16);
+            }
+            if (L == fd) {
+              if ((v.rp & 0xFFFF) != 0 && !(v.rp & kRpDead)) {  // accepts further pods: end of the block of count 1
+                m1_nxt[a] = kM1None;
+                if (m1.ft[L] == kM1None) m1.fh[L] = (uint16_t)a; else m1_nxt[m1.ft[L]] = (uint16_t)a;
+                m1.ft[L] = (uint16_t)a;
+                if (1 < lev) lev = 1;
+              }
+              if (m_rec0) ++cnt_d;
+            }
+            ++ltick; ++lnew; ++lact; ++li;
+            __syncwarp();
+          }
+        }
+        // every warp's copy of the spread counters follows (the per-pod loop and the write-back read them)
+        if (L < kM1Dom) for (int w = 0; w < nwarps; ++w) rc.cnt[w][0][L] = cnt_d;
+        if (L == 0) { m1.out_adv = li - i; m1.out_reason = reason; m1.out_tick = ltick; m1.out_n_new = lnew; m1.out_n_active = lact; }
+      }
+      __syncthreads();
+      const int m_adv = m1.out_adv, m_reason = m1.out_reason;
+      tick = m1.out_tick; n_new = m1.out_n_new; n_active = m1.out_n_active;
+      qi += m_adv;
+      qlen -= m_adv;
+      __syncthreads();  // out_* are rewritten by the next entry
+      if (m_reason == 1) { status = 1; break; }
+      if (qlen == 0) break;
+      if (m_reason == 2) m1_ok = false;
+      continue;
+    }
     int adv = 1;       // pods this iteration consumes
     int mode = 0;      // 0: per-pod argmin below; 1: placed by a level / fill step; 2: nobody accepts (fresh node)
     int k_avail = 1;   // pods of the class that may be consumed now: staged, same class, still queued
