@@ -1293,21 +1293,23 @@ struct RunCtx {
 __shared__ RunCtx g_rc;
 
 // ---- mask run: the class-run loop for ONE spread relation over a mask key (zone spread), driven by warp 0 alone ----------
-// The accepting nodes are kept in lists, one per domain they are pinned to plus one for the nodes not pinned yet, and every
-// list in buckets by pod count: inside a bucket the reference's order is "nodes re-keyed in this run, newest first" (an
-// accepting node moves to the FRONT of the block of count + 1: a stack), then the nodes untouched so far by tie-break (sorted
-// once per run by counting inside the bucket), then (count 1) the nodes created in this run in creation order. A pod's
-// node is then the smallest head key over the lists of the admissible domains: ~60 warp instructions and no block barrier
-// per pod instead of a scan of every open node. Anything the lists cannot represent hands the run back to the per-pod loop.
+// The accepting nodes are kept in singly linked lists in the reference's order (pod count, then tie-break), one per
+// domain they are pinned to plus one for the nodes not pinned yet; they are sorted once per run (buckets by list and count,
+// ranks by counting inside the bucket). An accepting node moves to the FRONT of the block of count + 1 of its domain's
+// list (its new tie-break is the smallest so far), a fresh node goes to the END of the block of count 1. Each lane keeps
+// the head of its list, the node after it and the tail of the head's bucket in registers, so a pod's node is the smallest
+// head key over the lists of the admissible domains: a few warp reductions, no block barrier and no shared-memory load on
+// the critical path instead of a scan of every open node. Anything the lists cannot represent hands the run back to the
+// per-pod loop.
 constexpr int kM1Dom = 8;             // domains with ids < kM1Dom; list kM1Dom holds the nodes that admit every registered domain
 constexpr int kM1Lists = kM1Dom + 1;
 constexpr int kM1Lv = 12;             // pod counts < kM1Lv
 constexpr uint16_t kM1None = 0xFFFF;
 struct M1Ctx {
-  uint16_t stk[kM1Lv][kM1Lists];      // bucket: re-keyed nodes, newest first (linked through nxt)
-  uint16_t ap[kM1Lv][kM1Lists];       // bucket: untouched nodes arr[ap .. ae) in tie order
+  uint16_t tl[kM1Lv][kM1Lists];       // last node of the bucket (kM1None: empty)
+  uint16_t head[kM1Lists];            // first node of the list (between two entries of the warp loop)
+  uint16_t ap[kM1Lv][kM1Lists];       // build: the bucket is arr[ap .. ae)
   uint16_t ae[kM1Lv][kM1Lists];
-  uint16_t fh[kM1Dom], ft[kM1Dom];    // nodes created in this run and pinned to the domain (count 1), creation order
   int bcnt[kM1Lv * kM1Lists];         // build: members per bucket (bucket = list * kM1Lv + count)
   int bad;                            // build: a node the lists cannot represent
   int out_adv, out_reason, out_tick, out_n_new, out_n_active;
@@ -1562,7 +1564,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       __syncthreads();  // the last commit's q_node entry is visible
       if (tid < CH) {
         const uint32_t pd = rc.q_pod[buf][tid];
-        s.assign[pd] = rc.q_node[buf][tid];
+        int nd = rc.q_node[buf][tid];
+        if (nd < -1) nd = NE + hs->node[-nd - 2];  // the mask run stores the slot
+        s.assign[pd] = nd;
         s.place_seq[pd] = seq0 + (cb - qi0) + tid;
       }
       buf ^= 1;
@@ -1580,6 +1584,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       if (tid == 0) rc.q_end[buf ^ 1] = CH;  // the consumed buffer: its next atomicMin comes after the next chunk's first barrier
     }
     if (rc.q_cls[buf][i] != cls) break;  // class change or end of the first pass
+#ifdef KSCHED_PROFILE_PACK
+    const long long m1_t0 = clock64();
+#endif
     if (m1_ok) {
       if (!m1_built) {
         // ---- build the lists (once per call; nothing of this call has been committed yet, so nn_last is free as scratch)
@@ -1588,11 +1595,7 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         uint16_t* t_pos = reinterpret_cast<uint16_t*>(t_b + kTopoCap);        // its arrival order inside the bucket
         uint16_t* t_slot = t_pos + kTopoCap;                                  // members, bucket by bucket, unsorted
         uint32_t* t_tie = reinterpret_cast<uint32_t*>(t_slot + kTopoCap);     // their tie-breaks
-        for (int b = tid; b < kM1Lv * kM1Lists; b += T) {
-          m1.bcnt[b] = 0;
-          (&m1.stk[0][0])[b] = kM1None;
-        }
-        if (tid < kM1Dom) { m1.fh[tid] = kM1None; m1.ft[tid] = kM1None; }
+        for (int b = tid; b < kM1Lv * kM1Lists; b += T) m1.bcnt[b] = 0;
         if (tid == 0) m1.bad = 0;
         __syncthreads();
         for (int a = tid; a < n_active; a += T) {
@@ -1653,28 +1656,108 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
             int rank = 0;
             for (int j = p0; j < p1; ++j) rank += t_tie[j] < tie;
             m1_arr[p0 + rank] = (uint16_t)a;
+            t_pos[a] = (uint16_t)(p0 + rank);
           }
         }
         __syncthreads();
+        if (!bad) {  // link every list (its buckets are contiguous in arr), tails and heads
+          for (int a = tid; a < n_active; a += T) {
+            const int b = t_b[a];
+            if (b == 0xFF) continue;
+            const int list = b / kM1Lv, gp = t_pos[a];
+            m1_nxt[a] = gp + 1 < (int)m1.ae[kM1Lv - 1][list] ? m1_arr[gp + 1] : kM1None;
+          }
+          for (int b = tid; b < kM1Lv * kM1Lists; b += T) {
+            const int list = b / kM1Lv, lv = b - list * kM1Lv;
+            m1.tl[lv][list] = m1.ae[lv][list] > m1.ap[lv][list] ? m1_arr[m1.ae[lv][list] - 1] : kM1None;
+          }
+          if (tid < kM1Lists) m1.head[tid] = m1.ae[kM1Lv - 1][tid] > m1.ap[0][tid] ? m1_arr[m1.ap[0][tid]] : kM1None;
+        }
+        __syncthreads();
         if (bad) m1_ok = false;
+#ifdef KSCHED_PROFILE_PACK
+        if (tid == 0) { s.counters[38] += clock64() - m1_t0; s.counters[47] += bad ? 1 : 0; }
+#endif
       }
     }
+#ifdef KSCHED_PROFILE_PACK
+    const long long m1_t1 = clock64();
+#endif
     if (m1_ok) {
       if (warp == 0) {
         const int L = lane;
         const unsigned FULL = 0xffffffffu;
         int cnt_d = L < kM1Dom ? rc.cnt[0][0][L] : 0;
         const bool valid = L < kM1Dom && ((m_reg0 >> L) & 1);
-        auto bucket_head = [&](int lv) -> int {  // first node of bucket (lv, L) in the reference's order, -1: empty
-          const uint16_t st = m1.stk[lv][L];
-          if (st != kM1None) return st;
-          const int p = m1.ap[lv][L];
-          if (p < m1.ae[lv][L]) return m1_arr[p];
-          if (lv == 1 && L < kM1Dom && m1.fh[L] != kM1None) return m1.fh[L];
-          return -1;
+        // this lane's list: head (slot, key, room word), the node after it, the tail of the head's bucket, the first node
+        // behind that bucket and its pod count
+        int h = -1, n1 = -1, tcur = -1, bn = -1, bnc = 0;
+        unsigned long long hk = ~0ull, nk = ~0ull;
+        uint32_t hr = 0, nr = 0;
+        auto nxt_of = [&](int sl) -> int { const uint16_t v = m1_nxt[sl]; return v == kM1None ? -1 : (int)v; };
+        auto level_state = [&]() {
+          if (h < 0) { tcur = -1; bn = -1; bnc = 0; return; }
+          tcur = m1.tl[(int)(hk >> 32)][L];
+          bn = nxt_of(tcur);
+          bnc = bn >= 0 ? (int)(hs->key[bn] >> 32) : 0;
         };
-        int lev = kM1Lv;
-        if (L < kM1Lists) { lev = 0; while (lev < kM1Lv && bucket_head(lev) < 0) ++lev; }
+        if (L < kM1Lists) {
+          h = m1.head[L] == kM1None ? -1 : (int)m1.head[L];
+          if (h >= 0) { hk = hs->key[h]; hr = rpv[h]; n1 = nxt_of(h); }
+          if (n1 >= 0) { nk = hs->key[n1]; nr = rpv[n1]; }
+          level_state();
+        }
+        // node a (key ak, room word ar) enters this lane's list at the FRONT of the block of count La
+        auto insert_front = [&](int a, int La, unsigned long long ak, uint32_t ar) {
+          const int hl = h >= 0 ? (int)(hk >> 32) : 0x7fffffff;
+          if (hl >= La) {  // nothing lies below: the new head
+            m1_nxt[a] = h >= 0 ? (uint16_t)h : kM1None;
+            if (hl > La) { m1.tl[La][L] = (uint16_t)a; tcur = a; bn = h; bnc = hl; }
+            n1 = h; nk = hk; nr = hr;
+            h = a; hk = ak; hr = ar;
+          } else if (bn < 0 || bnc >= La) {  // right behind the head's bucket
+            m1_nxt[a] = bn >= 0 ? (uint16_t)bn : kM1None;
+            m1_nxt[tcur] = (uint16_t)a;
+            if (bn < 0 || bnc > La) m1.tl[La][L] = (uint16_t)a;
+            if (tcur == h) { n1 = a; nk = ak; nr = ar; }
+            bn = a; bnc = La;
+          } else {  // behind the last bucket below La (the head's level is not the one)
+            int lv = La - 1;
+            while (m1.tl[lv][L] == kM1None) --lv;
+            const int pred = m1.tl[lv][L];
+            m1_nxt[a] = m1_nxt[pred];
+            m1_nxt[pred] = (uint16_t)a;
+            if (m1.tl[La][L] == kM1None) m1.tl[La][L] = (uint16_t)a;
+            if (pred == h) { n1 = a; nk = ak; nr = ar; }
+            if (pred == tcur) { bn = a; bnc = La; }
+          }
+        };
+        // a fresh node (count 1, the largest tie-break so far) enters at the END of the block of count 1
+        auto insert_back1 = [&](int a, unsigned long long ak, uint32_t ar) {
+          const int hl = h >= 0 ? (int)(hk >> 32) : 0x7fffffff;
+          if (hl > 1) {
+            m1_nxt[a] = h >= 0 ? (uint16_t)h : kM1None;
+            m1.tl[1][L] = (uint16_t)a;
+            tcur = a; bn = h; bnc = hl;
+            n1 = h; nk = hk; nr = hr;
+            h = a; hk = ak; hr = ar;
+          } else if (hl == 1) {
+            m1_nxt[a] = bn >= 0 ? (uint16_t)bn : kM1None;
+            m1_nxt[tcur] = (uint16_t)a;
+            m1.tl[1][L] = (uint16_t)a;
+            if (tcur == h) { n1 = a; nk = ak; nr = ar; }
+            tcur = a;
+          } else {  // nodes without pods in front (not produced by the scheduler, kept exact anyway)
+            int lv = 1;
+            while (m1.tl[lv][L] == kM1None) --lv;
+            const int pred = m1.tl[lv][L];
+            m1_nxt[a] = m1_nxt[pred];
+            m1_nxt[pred] = (uint16_t)a;
+            m1.tl[1][L] = (uint16_t)a;
+            if (pred == h) { n1 = a; nk = ak; nr = ar; }
+            if (pred == tcur) { bn = a; bnc = 1; }
+          }
+        };
         int li = i, ltick = tick, lnew = n_new, lact = n_active;
         int i_end = rc.q_end[buf];
         if (i + qlen < i_end) i_end = i + qlen;
@@ -1683,14 +1766,13 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
           const int mn = __reduce_min_sync(FULL, valid ? cnt_d : INT32_MAX);
           const bool allowed = valid && (long long)cnt_d + m_bias0 <= (long long)mn;
           const unsigned okm = __ballot_sync(FULL, allowed);
-          int hslot = -1;
-          if (L < kM1Lists && lev < kM1Lv && (L < kM1Dom ? allowed : okm != 0)) hslot = bucket_head(lev);
-          const unsigned long long key = hslot >= 0 ? hs->key[hslot] : ~0ull;
+          const bool cand_ok = L < kM1Lists && h >= 0 && (L < kM1Dom ? allowed : okm != 0);
+          const unsigned long long key = cand_ok ? hk : ~0ull;
           const unsigned long long wkey = warp_min_u64(key);
           if (wkey != ~0ull) {
             const int wl = __ffs(__ballot_sync(FULL, key == wkey)) - 1;
-            const int a = __shfl_sync(FULL, hslot, wl);
-            const uint32_t rp = rpv[a];
+            const int a = __shfl_sync(FULL, h, wl);
+            const uint32_t rp = __shfl_sync(FULL, hr, wl);
             if ((rp & 0xFFFF) == kRoomSlow) { reason = 1; break; }  // the winner needs the full evaluation
             int d = wl;
             const bool pin = wl == kM1Dom;
@@ -1699,15 +1781,20 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
               d = __ffs(__ballot_sync(FULL, allowed && cnt_d == mc)) - 1;
               if (!((rc.m_neutral[0] >> d) & 1) || !((zv[a] & (1u << 17)) || rc.m_wk[0])) { reason = 1; break; }
             }
-            if (L == wl) {  // pop the head of the winner's list
-              const uint16_t st = m1.stk[lev][L];
-              if (st != kM1None) m1.stk[lev][L] = m1_nxt[st];
-              else if (m1.ap[lev][L] < m1.ae[lev][L]) m1.ap[lev][L] = m1.ap[lev][L] + 1;
-              else { const uint16_t f = m1.fh[L]; m1.fh[L] = m1_nxt[f]; if (m1_nxt[f] == kM1None) m1.ft[L] = kM1None; }
-              while (lev < kM1Lv && bucket_head(lev) < 0) ++lev;
+            const int c = (int)(wkey >> 32);
+            if (L == wl) {  // pop: the node behind the head moves up, the one behind that is fetched (used at this list's next pop)
+              h = n1; hk = nk; hr = nr;
+              n1 = -1; nk = ~0ull; nr = 0;
+              if (h >= 0) {
+                n1 = nxt_of(h);
+                if (n1 >= 0) { nk = hs->key[n1]; nr = rpv[n1]; }
+              }
+              if (h < 0 || (int)(hk >> 32) != c) {  // the bucket of count c is exhausted
+                m1.tl[c][L] = kM1None;
+                level_state();
+              }
             }
             // ---- commit (the per-pod loop's commit, relation by relation on the first lanes)
-            const int c = (int)(wkey >> 32);
             uint32_t rp2 = rp - 1 + (1u << 16);
             bool dead_l = false;
             if (L < n_host) {  // Topology.Record, hostname groups
@@ -1717,17 +1804,17 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
               if (times) hc[L * kTopoCap + a] = (uint16_t)now;
               dead_l = now > rc.h_lim[L];
             }
-            if (__any_sync(FULL, dead_l)) rp2 |= kRpDead;
-            unsigned long long nkey = order_key(c + 1, -(ltick + 1));
+            if (n_host > 0 && __any_sync(FULL, dead_l)) rp2 |= kRpDead;
+            const unsigned long long nkey = order_key(c + 1, -(ltick + 1));
             if (L == 0) {
-              const int n = hs->node[a];
+              unsigned long long skey = nkey;
               if (pin) {  // requirements.Add(In{d}) on the node
-                const int k = rc.m_key[0];
+                const int n = hs->node[a], k = rc.m_key[0];
                 zv[a] = (1u << d) | (3u << 16);
                 s.nn_vals[(size_t)k * MAXN + n] = 1ull << d;
                 s.nn_meta[n] = (s.nn_meta[n] | (1ull << (KSCHED_META_PRESENT_SHIFT + k))) & ~(1ull << (KSCHED_META_COMPLEMENT_SHIFT + k));
               }
-              rc.q_node[buf][li] = NE + n;
+              rc.q_node[buf][li] = -(a + 2);  // the slot: translated to the node when the chunk is stored
               if ((rp2 & 0xFFFF) == 0) {  // the class no longer fits by resources: does anything? (node_closed)
                 const int placed = (rp2 >> 16) & 0x7FFF;
                 long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
@@ -1735,27 +1822,22 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
                 for (int r = 0; r < kHotRes; ++r) { nq[r] = hs->q[r][a] + placed * p_req[r]; cb1[r] = hs->bound[r][a]; cb2[r] = hs->bound2[r][a]; }
                 const unsigned short fl = (unsigned short)(hs->flags[a] | ((p_res & 0xF) << 1));
                 if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
-                  nkey = ~0ull;
+                  skey = ~0ull;
                   hs->nn_last[a] = ((unsigned long long)(unsigned)(c + 1) << 32) | (unsigned)(-(ltick + 1));
                   rc.tomb = rc.tomb + 1;
                 }
               }
-              hs->key[a] = nkey;
+              hs->key[a] = skey;
               rpv[a] = rp2;
             }
-            const bool surv = (rp2 & 0xFFFF) != 0 && !(rp2 & kRpDead);  // still accepts the class: front of the block of count + 1
-            if (surv) {
+            if ((rp2 & 0xFFFF) != 0 && !(rp2 & kRpDead)) {  // still accepts the class: front of the block of count + 1
               if (c + 1 >= kM1Lv) reason = 2;
-              else if (L == d) {
-                m1_nxt[a] = m1.stk[c + 1][L];
-                m1.stk[c + 1][L] = (uint16_t)a;
-                if (c + 1 < lev) lev = c + 1;
-              }
+              else if (L == d) insert_front(a, c + 1, nkey, rp2);
             }
             if (m_rec0 && L == d) ++cnt_d;
             ++ltick;
             ++li;
-            __syncwarp();
+            __syncwarp();  // lane 0's key / room words before a later pop fetches them
             if (reason == 2) break;
           } else {
             // ---- nobody accepts: NewNode + Add replayed from the variant of the domain a fresh node gets
@@ -1783,8 +1865,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
                 rc.h_inc[L] = rc.h_inc[L] + 1;
               }
             }
+            const unsigned long long fkey = order_key(1, ltick + 1);
             if (L == 0) {
-              hs->key[a] = order_key(1, ltick + 1);
+              hs->key[a] = fkey;
 #pragma unroll
               for (int r = 0; r < kHotRes; ++r) { hs->q[r][a] = v.q[r]; hs->bound[r][a] = v.b1[r]; hs->bound2[r][a] = v.b2[r]; }
               hs->node[a] = n;
@@ -1802,20 +1885,17 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
               zv[a] = (1u << fd) | (3u << 16);
             }
             if (L == fd) {
-              if ((v.rp & 0xFFFF) != 0 && !(v.rp & kRpDead)) {  // accepts further pods: end of the block of count 1
-                m1_nxt[a] = kM1None;
-                if (m1.ft[L] == kM1None) m1.fh[L] = (uint16_t)a; else m1_nxt[m1.ft[L]] = (uint16_t)a;
-                m1.ft[L] = (uint16_t)a;
-                if (1 < lev) lev = 1;
-              }
+              if ((v.rp & 0xFFFF) != 0 && !(v.rp & kRpDead)) insert_back1(a, fkey, v.rp);  // accepts further pods of the class
               if (m_rec0) ++cnt_d;
             }
             ++ltick; ++lnew; ++lact; ++li;
             __syncwarp();
           }
         }
+        __syncwarp();
         // every warp's copy of the spread counters follows (the per-pod loop and the write-back read them)
         if (L < kM1Dom) for (int w = 0; w < nwarps; ++w) rc.cnt[w][0][L] = cnt_d;
+        if (L < kM1Lists) m1.head[L] = h >= 0 ? (uint16_t)h : kM1None;
         if (L == 0) { m1.out_adv = li - i; m1.out_reason = reason; m1.out_tick = ltick; m1.out_n_new = lnew; m1.out_n_active = lact; }
       }
       __syncthreads();
@@ -1824,6 +1904,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       qi += m_adv;
       qlen -= m_adv;
       __syncthreads();  // out_* are rewritten by the next entry
+#ifdef KSCHED_PROFILE_PACK
+      if (tid == 0) { s.counters[6] += clock64() - m1_t1; s.counters[7] += m_adv; s.counters[16] += 1; }
+#endif
       if (m_reason == 1) { status = 1; break; }
       if (qlen == 0) break;
       if (m_reason == 2) m1_ok = false;
@@ -2195,7 +2278,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
   const int placed_total = qi - qi0;
   if (tid < CH && tid < qi - cb) {  // assignments of the partly consumed chunk
     const uint32_t pd = rc.q_pod[buf][tid];
-    s.assign[pd] = rc.q_node[buf][tid];
+    int nd = rc.q_node[buf][tid];
+    if (nd < -1) nd = NE + hs->node[-nd - 2];  // the mask run stores the slot
+    s.assign[pd] = nd;
     s.place_seq[pd] = seq0 + (cb - qi0) + tid;
   }
   for (int a = tid; a < n_active; a += T) {  // requests, order statistics, hostname counters of the nodes that took pods
