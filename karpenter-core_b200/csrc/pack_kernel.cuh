@@ -179,6 +179,81 @@ __device__ __forceinline__ void block_min2_u32_db(unsigned a, unsigned b, unsign
   *rb = __reduce_min_sync(0xffffffffu, (unsigned)r);
 }
 
+// compute_front with the whole CTA (same result, every thread calls it): the per-resource arg-max types are found by
+// probing each resource's descending order T positions at a time (block minimum of the first hit), the pair coverage test
+// runs one option word per thread. The serial version walks the orders and the words through dependent L2 loads - 30 000
+// cycles per fresh node of a new shape on the 1 000-type catalog (profiles/README.md, round 2).
+__shared__ unsigned g_front_pairs;
+__device__ __noinline__ void compute_front_block(const uint32_t* opts, int stride, int n, long long* b1, long long* b2, unsigned short* bits,
+                                                 unsigned long long (*red)[32], int& parity) {
+  KS_K2
+  const int R = c.n_res < kHotRes ? c.n_res : kHotRes;
+  const int T = c.n_types, tid = threadIdx.x, NT = blockDim.x, W32 = c.W32;
+  unsigned pos[kHotRes] = {~0u, ~0u, ~0u, ~0u};
+  for (int r = 0; r < R; ++r) {
+    const int32_t* perm = c.perm_desc + (size_t)r * T;
+    for (int i = tid; i < T; i += NT) {
+      const int t = perm[i];
+      if ((opts[(size_t)(t >> 5) * stride + n] >> (t & 31)) & 1) { pos[r] = (unsigned)i; break; }
+    }
+  }
+  unsigned pm[kHotRes];
+  block_min2_u32_db(pos[0], pos[1], red, parity, &pm[0], &pm[1]);
+  block_min2_u32_db(pos[2], pos[3], red, parity, &pm[2], &pm[3]);
+  if (tid == 0) g_front_pairs = ~0u;
+  int arg[kHotRes];
+  long long m1v[kHotRes];
+  for (int r = 0; r < kHotRes; ++r) {
+    arg[r] = (r < R && pm[r] != ~0u) ? c.perm_desc[(size_t)r * T + pm[r]] : -1;
+    m1v[r] = arg[r] >= 0 ? c.alloc_rt[(size_t)r * T + arg[r]] : INT64_MIN;
+  }
+  bool done = arg[0] < 0 || c.n_res > kHotRes;  // no option left / resources beyond the hot vectors: necessary test only
+  unsigned short fb = 0;
+  if (!done) {
+    bool dom0 = true;  // one option is maximal in every resource
+    for (int r = 0; r < R; ++r) dom0 = dom0 && c.alloc_rt[(size_t)r * T + arg[0]] >= m1v[r];
+    if (dom0) { fb = kFlExact; done = true; }
+  }
+  if (done) {
+    if (tid == 0) {
+      for (int r = 0; r < kHotRes; ++r) { b1[r] = m1v[r]; b2[r] = INT64_MIN; }
+      *bits = fb;
+    }
+    return;  // (uniform: every thread holds the same values)
+  }
+  int cand[kHotRes], nc = 0;
+  for (int r = 0; r < R; ++r) {
+    bool seen = false;
+    for (int i = 0; i < nc; ++i) seen = seen || cand[i] == arg[r];
+    if (!seen) cand[nc++] = arg[r];
+  }
+  unsigned pair_ok = 0;  // bit (i*4+j), i<j: every option is dominated by candidate i or j
+  for (int i = 0; i < nc; ++i) for (int j = i + 1; j < nc; ++j) pair_ok |= 1u << (i * 4 + j);
+  unsigned mine = pair_ok;
+  for (int w = tid; w < W32; w += NT) {
+    const uint32_t m = opts[(size_t)w * stride + n];
+    if (!m) continue;
+    uint32_t d[kHotRes];
+    for (int i = 0; i < nc; ++i) d[i] = c.domset[(size_t)cand[i] * W32 + w];
+    for (int i = 0; i < nc; ++i) for (int j = i + 1; j < nc; ++j)
+      if (m & ~(d[i] | d[j])) mine &= ~(1u << (i * 4 + j));
+  }
+  mine = __reduce_and_sync(0xffffffffu, mine);
+  __syncthreads();  // g_front_pairs initialised
+  if ((tid & 31) == 0) atomicAnd(&g_front_pairs, mine);
+  __syncthreads();
+  pair_ok &= g_front_pairs;
+  if (tid == 0) {
+    for (int r = 0; r < kHotRes; ++r) { b1[r] = m1v[r]; b2[r] = INT64_MIN; }
+    *bits = 0;
+    if (pair_ok) {
+      const int pi = (__ffs(pair_ok) - 1) / 4, pj = (__ffs(pair_ok) - 1) % 4;
+      for (int r = 0; r < R; ++r) { b1[r] = c.alloc_rt[(size_t)r * T + cand[pi]]; b2[r] = c.alloc_rt[(size_t)r * T + cand[pj]]; }
+      *bits = kFlExact | kFlTwo;
+    }
+  }
+}
+
 struct StepShared {
   int placed_closed;   // commit outcome: 1 = the accepting node became full and left the active set
   int path;            // fresh-node path
@@ -929,6 +1004,10 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
           }
         }
         GK_T(19)
+        // the Pareto front of a new option set, with every thread (the words were stored before the barrier above)
+        const bool front_memo_hit = path == kPathRow && !limits_active && s.fc_front_state[fc];
+        const bool front_fresh = path != kPathCached && path != kPathDynCached && !front_memo_hit;
+        if (front_fresh) compute_front_block(s.nn_opts, MAXN, n, sh.bound, sh.bound2, &sh.front_bits, red, parity);
         // ---- commit the new node (NewNode + Add, node.go:44-107) — one thread, everything else was written above
         __syncthreads();
         if (tid == 0) {
@@ -949,8 +1028,7 @@ __device__ __noinline__ void generic_step(const PodRegs& cur, bool first_pass, i
             } else if (path == kPathDynCached) {
               for (int r = 0; r < kHotRes; ++r) { sh.bound[r] = s.fd_bound[(size_t)fd_slot * kHotRes + r]; sh.bound2[r] = s.fd_bound2[(size_t)fd_slot * kHotRes + r]; }
               sh.front_bits = s.fd_dom[fd_slot];
-            } else {
-              compute_front(s.nn_opts, MAXN, n, sh.bound, sh.bound2, &sh.front_bits);
+            } else {  // (front_fresh: computed by the CTA above)
               if (front_memo) {
                 for (int r = 0; r < kHotRes; ++r) { s.fc_bound[fc * kHotRes + r] = sh.bound[r]; s.fc_bound2[fc * kHotRes + r] = sh.bound2[r]; }
                 s.fc_dom[fc] = (uint8_t)sh.front_bits;
@@ -1762,11 +1840,14 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         int i_end = rc.q_end[buf];
         if (i + qlen < i_end) i_end = i + qlen;
         int reason = 0;  // 0: the staged entries of the class are consumed; 1: the pod at li needs generic_step; 2: per-pod loop from li on
+        // count + self - min <= maxSkew as count - min <= slack in 32 bits: counts are pod counts (< 2^30), so a slack of 2^30
+        // or more admits every domain exactly like the 64-bit form of the per-pod loop
+        const int slack = m_bias0 < -(1 << 30) ? (1 << 30) : -m_bias0;
         while (li < i_end) {
           const int mn = __reduce_min_sync(FULL, valid ? cnt_d : INT32_MAX);
-          const bool allowed = valid && (long long)cnt_d + m_bias0 <= (long long)mn;
+          const bool allowed = valid && cnt_d - mn <= slack;
           const unsigned okm = __ballot_sync(FULL, allowed);
-          const bool cand_ok = L < kM1Lists && h >= 0 && (L < kM1Dom ? allowed : okm != 0);
+          const bool cand_ok = L < kM1Dom ? allowed : (L == kM1Dom && okm != 0);  // an empty list keeps hk = ~0
           const unsigned long long key = cand_ok ? hk : ~0ull;
           const unsigned long long wkey = warp_min_u64(key);
           if (wkey != ~0ull) {
