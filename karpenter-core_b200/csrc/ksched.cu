@@ -1227,6 +1227,7 @@ int ksched_download(ksched_handle* h, const ksched_problem* pb, ksched_result* r
       o.reqs.meta = meta[n];
       uint32_t* dst = reinterpret_cast<uint32_t*>(res->new_node_types + (size_t)n * W64);
       for (int w = 0; w < W32; ++w) dst[w] = opts[(size_t)w * n_new + n];
+      if (W32 & 1) dst[W32] = 0;  // the row is W64 64-bit words: the caller's buffer need not be cleared
     }
   }
   if (res->launch && n_new > 0) {

@@ -30,23 +30,6 @@ using ksched::Req;
 
 namespace {
 
-// Split [0, n) over the host's cores; fn(begin, end) must only write what it owns. Small inputs stay on the calling thread.
-template <class F>
-void parallel_ranges(size_t n, size_t min_per_thread, F fn) {
-  static const size_t env_threads = [] { const char* e = std::getenv("KSCHED_HOST_THREADS"); return e ? (size_t)std::max(1, std::atoi(e)) : (size_t)0; }();
-  size_t nt = env_threads ? env_threads : std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
-  nt = std::min(nt, std::max<size_t>(1, n / std::max<size_t>(1, min_per_thread)));
-  if (nt <= 1) { fn((size_t)0, n); return; }
-  std::vector<std::thread> th;
-  const size_t per = (n + nt - 1) / nt;
-  for (size_t t = 0; t < nt; ++t) {
-    const size_t b = t * per, e = std::min(n, b + per);
-    if (b >= e) break;
-    th.emplace_back([=] { fn(b, e); });
-  }
-  for (auto& x : th) x.join();
-}
-
 [[noreturn]] void unsupported(const std::string& what) { throw std::runtime_error("unsupported: " + what); }
 
 const char* kHostname = "kubernetes.io/hostname";
@@ -538,6 +521,14 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   Builder B(P, E);
   const ClusterFacts& facts = cluster_facts(P);
 
+  static const bool enc_trace = std::getenv("KSCHED_ENCODE_TRACE") != nullptr;
+  auto enc_t0 = std::chrono::steady_clock::now();
+  const char* enc_prev = "setup";
+  auto enc_mark = [&](const char* next) {
+    if (enc_trace) { auto t = std::chrono::steady_clock::now(); std::fprintf(stderr, "[encode] %-40s %8.3f ms\n", enc_prev, std::chrono::duration<double, std::milli>(t - enc_t0).count()); enc_t0 = t; }
+    enc_prev = next;
+  };
+  enc_mark("who takes part");
   // ------------------------------------------------------------------ who takes part
   std::vector<int> state_nodes;
   {
@@ -565,14 +556,9 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     }
   }
   const size_t NP = E.pods.size();
-  bool uids_ascending = true;  // strictly ascending UIDs (the usual case: one informer list) are unique and already ranked
-  for (size_t i = 1; i < NP && uids_ascending; ++i) uids_ascending = E.pods[i - 1]->uid < E.pods[i]->uid;
-  if (!uids_ascending) {
-    std::unordered_set<std::string> uids;
-    uids.reserve(NP * 2);
-    for (auto* p : E.pods)
-      if (!uids.insert(p->uid).second) throw std::runtime_error("pods must have unique UIDs: " + p->uid);
-  }
+  // strictly ascending UIDs (the usual case: one informer list) are unique and already ranked; found out in the pass below
+  // that visits every pod anyway
+  bool uids_ascending = true;
   if (P.provisioners.empty()) throw std::runtime_error("no provisioners found");
   if (P.provisioners.size() > KSCHED_MAX_TEMPLATES) unsupported("more than 16 provisioners");
 
@@ -588,6 +574,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     for (auto& t : pr.taints) if (t.effect == "PreferNoSchedule") tolerate_pns = true;
 
   phase("who takes part");
+  enc_mark("CSI volume limits");
   // ------------------------------------------------------------------ CSI volume limits (ksched.h: ksched_class_volumes)
   // Drivers some owned state node limits; claims by how many pods (batch + bound) mount them: one -> counted, several -> tracked id.
   std::vector<std::string> vol_drivers;
@@ -634,6 +621,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     return (cv.shared | cv.priv[0] | cv.priv[1] | cv.priv[2] | cv.priv[3]) ? std::string(b) : std::string();
   };
 
+  enc_mark("pod specs: classes and relaxation chains");
   // ------------------------------------------------------------------ pod specs: classes and relaxation chains
   struct Spec { Pod pod; ResourceList req; uint32_t next = KSCHED_NONE; };
   std::vector<Spec> specs;
@@ -661,10 +649,27 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   {
     // "same deployment as the previous pod" is a pure comparison of two pods: every pair at once, on all cores; only the
     // class boundaries (a few hundred in a 100 000-pod batch) take the keyed path, in order
-    std::vector<uint8_t> same(NP, 0);
+    std::vector<uint8_t> same(NP, 0), uid_order_broken((NP >> 12) + 2, 0);
+    E.pod_timestamp.resize(NP);
     parallel_ranges(NP, 4096, [&](size_t b, size_t e) {
-      for (size_t i = std::max<size_t>(b, 1); i < e; ++i) same[i] = same_spec(*E.pods[i], *E.pods[i - 1]) ? 1 : 0;
+      bool asc = true;
+      if (b == 0 && e > 0) E.pod_timestamp[0] = E.pods[0]->creation_ts;
+      for (size_t i = std::max<size_t>(b, 1); i < e; ++i) {
+        const Pod& p = *E.pods[i];
+        const Pod& q = *E.pods[i - 1];
+        same[i] = same_spec(p, q) ? 1 : 0;
+        asc = asc && q.uid < p.uid;
+        E.pod_timestamp[i] = p.creation_ts;  // queue.go:74-110 sorts by it (per-pod queue keys below)
+      }
+      if (!asc) uid_order_broken[b >> 12] = 1;  // (ranges start at multiples of >= 4096 pods or at 0: one flag each)
     });
+    for (uint8_t f : uid_order_broken) uids_ascending = uids_ascending && !f;
+    if (!uids_ascending) {
+      std::unordered_set<std::string> uids;
+      uids.reserve(NP * 2);
+      for (auto* p : E.pods)
+        if (!uids.insert(p->uid).second) throw std::runtime_error("pods must have unique UIDs: " + p->uid);
+    }
     phase("  same_spec pairs");
     for (size_t i = 0; i < NP; ++i) E.pod_class[i] = same[i] ? E.pod_class[i - 1] : intern(*E.pods[i]);
     phase("  intern boundaries");
@@ -672,6 +677,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   std::vector<Pod> daemons = P.daemonset_pods;
 
   phase("pod classes");
+  enc_mark("active keys + dictionary");
   // ------------------------------------------------------------------ active keys + dictionary
   // pod-side keys: anything a pod / daemonset / topology group / node filter can put into a node's requirements
   std::set<std::string> pod_side;
@@ -805,6 +811,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("keys + dictionary");
+  enc_mark("resources");
   // ------------------------------------------------------------------ resources
   {
     std::set<std::string> names;
@@ -821,6 +828,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("resources");
+  enc_mark("instance types");
   // ------------------------------------------------------------------ instance types (columns, price order)
   const int NT = (int)P.instance_types.size();
   E.type_words = (NT + 63) / 64;
@@ -894,6 +902,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   // (When zone/ct keys are inactive every offering maps to z=0/ct=0 above, which is exactly "key not constrained".)
 
   phase("instance types");
+  enc_mark("templates");
   // ------------------------------------------------------------------ templates
   const int NV = (int)E.template_provisioner.size();
   E.templates.resize(NV);
@@ -936,6 +945,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   E.template_bounds = tb;
 
   phase("templates");
+  enc_mark("daemonset overhead");
   // ------------------------------------------------------------------ daemonset overhead (scheduler.go:250-267)
   auto daemon_reqs = [&](const Pod& d, ksched_reqset& rs, ksched_bounds& bd) {
     Builder::Special sp;
@@ -960,6 +970,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("daemonset overhead");
+  enc_mark("existing nodes");
   // ------------------------------------------------------------------ existing nodes (scheduler.go:221-248, existingnode.go:41-75)
   std::map<std::string, int> hostname_slot;  // hostname -> existing slot
   for (int si : state_nodes) {
@@ -1055,6 +1066,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   const int NE = (int)E.existing.size();
 
   phase("existing nodes");
+  enc_mark("topology groups");
   // ------------------------------------------------------------------ topology groups (topology.go)
   std::vector<Group> groups;
   std::map<std::string, size_t> group_of;          // hash -> index, non-inverse
@@ -1339,6 +1351,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("topology groups");
+  enc_mark("class rows");
   // ------------------------------------------------------------------ class rows
   const int NC = (int)specs.size();
   E.classes.resize(NC);
@@ -1459,8 +1472,8 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("class rows");
+  enc_mark("per-pod queue keys");
   // ------------------------------------------------------------------ per-pod queue keys (queue.go:74-110)
-  E.pod_timestamp.resize(NP);
   E.pod_uid_rank.resize(NP);
   {
     if (uids_ascending) {
@@ -1471,10 +1484,10 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
       std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return E.pods[a]->uid < E.pods[b]->uid; });
       for (size_t r = 0; r < NP; ++r) E.pod_uid_rank[order[r]] = (uint32_t)r;
     }
-    for (size_t i = 0; i < NP; ++i) E.pod_timestamp[i] = E.pods[i]->creation_ts;
   }
 
   phase("queue keys");
+  enc_mark("wire up the flat structs");
   // ------------------------------------------------------------------ wire up the flat structs
   ksched_catalog& cat = E.catalog;
   cat.n_keys = NK; cat.n_res = (int)E.res_names.size(); cat.n_types = NT; cat.n_templates = NV;
@@ -1526,6 +1539,7 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     E.classes[c].meta = rs.meta;
   }
   cat.key_regions = E.key_regions.empty() ? nullptr : E.key_regions.data();
+  enc_mark("end");
   return enc;
 }
 

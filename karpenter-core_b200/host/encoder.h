@@ -2,15 +2,35 @@
 // include/ksched.h — what a cgo shim would do from the Go objects handed to
 // scheduling.NewScheduler (provisioner.go:237-296, scheduler.go:42-78).
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ksched.h"
 #include "model.h"
 
 namespace khost {
+
+// Split [0, n) over the host's cores; fn(begin, end) must only write what it owns. Small inputs stay on the calling thread.
+template <class F>
+void parallel_ranges(size_t n, size_t min_per_thread, F fn) {
+  static const size_t env_threads = [] { const char* e = std::getenv("KSCHED_HOST_THREADS"); return e ? (size_t)std::max(1, std::atoi(e)) : (size_t)0; }();
+  size_t nt = env_threads ? env_threads : std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+  nt = std::min(nt, std::max<size_t>(1, n / std::max<size_t>(1, min_per_thread)));
+  if (nt <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; ++t) {
+    const size_t b = t * per, e = std::min(n, b + per);
+    if (b >= e) break;
+    th.emplace_back([=] { fn(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
 
 struct Encoded {
   // ---- dictionary

@@ -53,13 +53,16 @@ struct ResultBuffers {
   std::vector<uint64_t> best;
   std::vector<ksched_launch_choice> launch;
   ksched_result r{};
+  // ksched_solve overwrites every per-pod entry and the rows of the nodes it reports (ksched_download), decode reads nothing
+  // else: the buffers are sized, not cleared - kh_scheduler_solve keeps one set per thread, so a 100 000-pod Solve does not
+  // fault in and zero ~35 MB per call.
   void prepare(const Encoded& E, bool want_feasibility) {
     const size_t P = E.pods.size(), N = (size_t)std::max(1, E.problem.max_new_nodes);
-    assign.assign(P, -1);
-    relax.assign(P, 0);
-    seq.assign(P, -1);
+    assign.resize(P);
+    relax.resize(P);
+    seq.resize(P);
     nodes.resize(N);
-    types.assign(N * E.type_words, 0);
+    types.resize(N * E.type_words);
     existing_reqs.resize(std::max<size_t>(1, E.existing.size()));
     std::memset(&r, 0, sizeof r);
     r.assign = assign.data();
@@ -68,8 +71,10 @@ struct ResultBuffers {
     r.new_nodes = nodes.data();
     r.new_node_types = types.data();
     r.existing_reqs = existing_reqs.data();
-    launch.assign(nodes.size(), ksched_launch_choice{-1, -1, 0, 0});
+    launch.resize(nodes.size());
     r.launch = launch.data();
+    r.feasibility = nullptr;
+    r.best_column = nullptr;
     if (want_feasibility) {
       feasibility.assign(P * E.templates.size() * E.type_words, 0);
       best.assign(P, 0);
@@ -79,49 +84,47 @@ struct ResultBuffers {
   }
 };
 
-// ksched_result -> the reference's ([]*Node, []*ExistingNode) shape (node.go:34-40, existingnode.go:28-39)
+// ksched_result -> the reference's ([]*Node, []*ExistingNode) shape (node.go:34-40, existingnode.go:28-39). The per-node part
+// (pods in Add order, requests, rendered requirements, launch choice) is independent node by node and runs on all host cores.
 void decode(const Encoded& E, const ResultBuffers& B, Result& out) {
-  const size_t P = E.pods.size(), NE = E.existing.size();
-  out.assign.assign(B.assign.begin(), B.assign.end());
-  out.relax_level.assign(B.relax.begin(), B.relax.end());
+  const size_t P = E.pods.size(), NE = E.existing.size(), NN = (size_t)B.r.n_new_nodes, NA = NE + NN;
+  out.assign.assign(B.assign.begin(), B.assign.begin() + (ptrdiff_t)P);
+  out.relax_level.assign(B.relax.begin(), B.relax.begin() + (ptrdiff_t)P);
   out.nodes_visited = B.r.nodes_visited;
   out.add_calls = B.r.add_calls;
   out.existing_node_index = E.existing_state_index;
   out.existing_pods.assign(NE, {});
-  out.new_nodes.assign((size_t)B.r.n_new_nodes, {});
-  // pods in Add order: place_seq is a permutation of 0..placed-1 over the placed pods
+  out.new_nodes.assign(NN, {});
+  // pods per node in Add order: place_seq is a permutation of 0..placed-1 over the placed pods. Counting sort by node, then
+  // each node orders its few pods by sequence number.
+  std::vector<uint32_t> start(NA + 1, 0);
+  for (size_t p = 0; p < P; ++p) {
+    const int32_t a = B.assign[p];
+    if (a >= 0 && (size_t)a < NA && B.seq[p] >= 0) ++start[(size_t)a + 1];
+  }
+  for (size_t a = 0; a < NA; ++a) start[a + 1] += start[a];
+  std::vector<std::pair<int32_t, int32_t>> by_node(start[NA]);  // (sequence, pod)
   {
-    std::vector<int32_t> by_seq(P, -1);
-    for (size_t p = 0; p < P; ++p)
-      if (B.assign[p] >= 0 && B.seq[p] >= 0 && (size_t)B.seq[p] < P) by_seq[(size_t)B.seq[p]] = (int32_t)p;
-    for (size_t q = 0; q < P; ++q) {
-      const int32_t p = by_seq[q];
-      if (p < 0) continue;
+    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    for (size_t p = 0; p < P; ++p) {
       const int32_t a = B.assign[p];
-      if ((size_t)a < NE) out.existing_pods[a].push_back(p);
-      else out.new_nodes[(size_t)a - NE].pods.push_back(p);
+      if (a >= 0 && (size_t)a < NA && B.seq[p] >= 0) by_node[fill[(size_t)a]++] = {B.seq[p], (int32_t)p};
     }
   }
-  // lo.Filter keeps the provider's input order: permute the surviving columns (price order) into an input-order bitset and
-  // read that out; requirement renderings are memoised per (key, masks) - nodes of one deployment share them
-  const size_t NT = E.type_input_index.size();
-  std::vector<uint64_t> in_order((NT + 63) / 64);
-  std::vector<std::unordered_map<uint64_t, std::string>> rendered(E.key_names.size());
-  // nodes opened for one deployment end with the same option set: each distinct bitset is expanded once and shared
-  std::unordered_map<std::string, int32_t> set_of;
-  for (int n = 0; n < B.r.n_new_nodes; ++n) {
-    const ksched_new_node& src = B.nodes[n];
-    NewNodeResult& dst = out.new_nodes[n];
-    dst.provisioner = src.template_index;
-    const uint64_t* bits = &B.types[(size_t)n * E.type_words];
-    std::string key(reinterpret_cast<const char*>(bits), (size_t)E.type_words * 8);
-    auto found = set_of.find(key);
-    if (found != set_of.end()) {
-      dst.option_set = found->second;
-    } else {
+  // distinct option bitsets: nodes opened for one deployment end with the same set, each is expanded once and shared.
+  // lo.Filter keeps the provider's input order: the surviving columns (price order) are permuted into an input-order bitset.
+  const size_t NT = E.type_input_index.size(), TW = (size_t)E.type_words;
+  {
+    std::unordered_map<std::string, int32_t> set_of;
+    std::vector<uint64_t> in_order((NT + 63) / 64);
+    for (size_t n = 0; n < NN; ++n) {
+      const uint64_t* bits = &B.types[n * TW];
+      std::string key(reinterpret_cast<const char*>(bits), TW * 8);
+      auto found = set_of.find(key);
+      if (found != set_of.end()) { out.new_nodes[n].option_set = found->second; continue; }
       std::fill(in_order.begin(), in_order.end(), 0);
       size_t n_opts = 0;
-      for (size_t w = 0; w < (size_t)E.type_words; ++w) {
+      for (size_t w = 0; w < TW; ++w) {
         uint64_t m = bits[w];
         while (m) {
           const size_t c = w * 64 + (size_t)__builtin_ctzll(m);
@@ -138,32 +141,48 @@ void decode(const Encoded& E, const ResultBuffers& B, Result& out) {
         uint64_t m = in_order[w];
         while (m) { opts.push_back((int32_t)(w * 64 + (size_t)__builtin_ctzll(m))); m &= m - 1; }
       }
-      dst.option_set = (int32_t)out.option_sets.size();
+      out.new_nodes[n].option_set = (int32_t)out.option_sets.size();
       out.option_sets.push_back(std::move(opts));
-      set_of.emplace(std::move(key), dst.option_set);
-    }
-    for (size_t r = 0; r < E.res_names.size(); ++r)
-      if ((src.requests_present >> r) & 1) dst.requests[E.res_names[r]] = src.requests[r];
-    for (size_t k = 0; k < E.key_names.size(); ++k)
-      if ((src.reqs.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1) {
-        const uint64_t memo_key = src.reqs.values[k] ^ (((src.reqs.meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1) << 63);  // <= 63 values per key
-        auto it = rendered[k].find(memo_key);
-        if (it == rendered[k].end()) it = rendered[k].emplace(memo_key, khost::render_requirement(E, src.reqs, (int)k)).first;
-        dst.requirements[E.key_names[k]] = it->second;
-      }
-    // launch choice: column -> the provider's instance type, offering by its position in that type's Offerings list
-    if ((size_t)n < B.launch.size() && B.launch[n].type_column >= 0 && E.problem_ref) {
-      const ksched_launch_choice& lc = B.launch[n];
-      const int ti = E.type_input_index[(size_t)lc.type_column];
-      const kmodel::InstanceType& it = E.problem_ref->instance_types[(size_t)ti];
-      dst.launch_type = ti;
-      if (lc.offering_index < it.offerings.size()) {
-        dst.launch_capacity_type = it.offerings[lc.offering_index].capacity_type;
-        dst.launch_zone = it.offerings[lc.offering_index].zone;
-      }
-      if (lc.price_rank < E.price_by_rank.size()) dst.launch_price = E.price_by_rank[lc.price_rank];
+      set_of.emplace(std::move(key), out.new_nodes[n].option_set);
     }
   }
+  khost::parallel_ranges(NA, 512, [&](size_t a0, size_t a1) {
+    // requirement renderings are memoised per (key, masks) - nodes of one deployment share them (one memo per worker)
+    std::vector<std::unordered_map<uint64_t, std::string>> rendered(E.key_names.size());
+    for (size_t a = a0; a < a1; ++a) {
+      auto first = by_node.begin() + start[a], last = by_node.begin() + start[a + 1];
+      std::sort(first, last);
+      std::vector<int32_t>& pods = a < NE ? out.existing_pods[a] : out.new_nodes[a - NE].pods;
+      pods.reserve((size_t)(last - first));
+      for (auto it = first; it != last; ++it) pods.push_back(it->second);
+      if (a < NE) continue;
+      const size_t n = a - NE;
+      const ksched_new_node& src = B.nodes[n];
+      NewNodeResult& dst = out.new_nodes[n];
+      dst.provisioner = src.template_index;
+      for (size_t r = 0; r < E.res_names.size(); ++r)
+        if ((src.requests_present >> r) & 1) dst.requests[E.res_names[r]] = src.requests[r];
+      for (size_t k = 0; k < E.key_names.size(); ++k)
+        if ((src.reqs.meta >> (KSCHED_META_PRESENT_SHIFT + k)) & 1) {
+          const uint64_t memo_key = src.reqs.values[k] ^ (((src.reqs.meta >> (KSCHED_META_COMPLEMENT_SHIFT + k)) & 1) << 63);  // <= 63 values per key
+          auto it = rendered[k].find(memo_key);
+          if (it == rendered[k].end()) it = rendered[k].emplace(memo_key, khost::render_requirement(E, src.reqs, (int)k)).first;
+          dst.requirements[E.key_names[k]] = it->second;
+        }
+      // launch choice: column -> the provider's instance type, offering by its position in that type's Offerings list
+      if (n < B.launch.size() && B.launch[n].type_column >= 0 && E.problem_ref) {
+        const ksched_launch_choice& lc = B.launch[n];
+        const int ti = E.type_input_index[(size_t)lc.type_column];
+        const kmodel::InstanceType& it = E.problem_ref->instance_types[(size_t)ti];
+        dst.launch_type = ti;
+        if (lc.offering_index < it.offerings.size()) {
+          dst.launch_capacity_type = it.offerings[lc.offering_index].capacity_type;
+          dst.launch_zone = it.offerings[lc.offering_index].zone;
+        }
+        if (lc.price_rank < E.price_by_rank.size()) dst.launch_price = E.price_by_rank[lc.price_rank];
+      }
+    }
+  });
 }
 
 int error_code(const std::exception& e) {
@@ -237,7 +256,7 @@ int kh_scheduler_solve(const Problem* P, const int* candidates, int ncand, Resul
     std::vector<int> c(candidates, candidates + ncand);
     auto E = khost::encode(*P, c);
     E->problem.count_nodes_visited = g_count_visited;
-    ResultBuffers B;
+    static thread_local ResultBuffers B;
     int rc = solve_encoded(*E, B, false);
     if (rc != KSCHED_OK) { out->error = g_err; return rc; }
     decode(*E, B, *out);
@@ -267,7 +286,7 @@ int kh_scheduler_solve_timed(const Problem* P, const int* candidates, int ncand,
     rc = ksched_load_catalog(g_handle, &E->catalog);
     if (rc != KSCHED_OK) return fail(rc, ksched_last_error(g_handle));
     const auto t2 = clk::now();
-    ResultBuffers B;
+    static thread_local ResultBuffers B;
     B.prepare(*E, false);
     rc = ksched_solve(g_handle, &E->problem, &B.r);
     if (rc != KSCHED_OK) { out->error = ksched_last_error(g_handle); return fail(rc, out->error); }
