@@ -1836,6 +1836,24 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
             if (pred == tcur) { bn = a; bnc = 1; }
           }
         };
+        // the head (pod count c) leaves this lane's list: the node behind it moves up, the one behind that is fetched (it is used
+        // at this list's next pop)
+        auto pop_head = [&](int c) {
+          h = n1; hk = nk; hr = nr;
+          n1 = -1; nk = ~0ull; nr = 0;
+          if (h >= 0) {
+            n1 = nxt_of(h);
+            if (n1 >= 0) { nk = hs->key[n1]; nr = rpv[n1]; }
+          }
+          if (h < 0 || (int)(hk >> 32) != c) {  // the bucket of count c is exhausted
+            m1.tl[c][L] = kM1None;
+            level_state();
+          }
+        };
+        // skew 1 with a self-matching selector: only the domains with the fewest pods admit a pod, so once every one of them has
+        // a pinned node at hand and the unpinned nodes come later in the order, the next pods go one to each of these domains,
+        // smallest head key first - a whole round is committed at once, every lane its own domain
+        const bool rounds = m_rec0 && m_bias0 == 0;
         int li = i, ltick = tick, lnew = n_new, lact = n_active;
         int i_end = rc.q_end[buf];
         if (i + qlen < i_end) i_end = i + qlen;
@@ -1850,6 +1868,79 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
           const bool cand_ok = L < kM1Dom ? allowed : (L == kM1Dom && okm != 0);  // an empty list keeps hk = ~0
           const unsigned long long key = cand_ok ? hk : ~0ull;
           const unsigned long long wkey = warp_min_u64(key);
+#ifdef KSCHED_PROFILE_PACK
+          {  // how often a whole round (one pod per admissible domain, all from pinned lists) could be placed at once
+            const unsigned have = __ballot_sync(FULL, L < kM1Dom && allowed && h >= 0);
+            const unsigned long long ukey = __shfl_sync(FULL, hk, kM1Dom);
+            unsigned long long mx = (L < kM1Dom && allowed && h >= 0) ? hk : 0ull;
+            for (int o = 16; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(FULL, mx, o); mx = t > mx ? t : mx; }
+            const int na = __popc(okm);
+            if (L == 0 && na > 1 && have == okm && ukey > mx && i_end - li >= na) s.counters[17] += 1;
+            if (L == 0) s.counters[18] += 1;
+            if (L == 0 && na > 1) s.counters[19] += 1;
+          }
+#endif
+          if (rounds && wkey != ~0ull) {
+            const int na = __popc(okm);
+            if (na > 1 && i_end - li >= na) {
+              const bool act = L < kM1Dom && allowed;
+              const unsigned have = __ballot_sync(FULL, act && h >= 0);
+              const bool bad_l = act && h >= 0 && ((hr & 0xFFFF) == kRoomSlow || (int)(hk >> 32) + 1 >= kM1Lv);
+              const unsigned long long ukey = __shfl_sync(FULL, hk, kM1Dom);
+              const unsigned hi = act ? (unsigned)(hk >> 32) : 0u;
+              const unsigned mhi = __reduce_max_sync(FULL, hi);
+              const unsigned mlo = __reduce_max_sync(FULL, (act && hi == mhi) ? (unsigned)hk : 0u);
+              const unsigned long long mx = ((unsigned long long)mhi << 32) | mlo;  // largest head key of the round
+              if (have == okm && !__any_sync(FULL, bad_l) && ukey > mx) {
+                int rank = 0;  // position of this lane's node in the round
+                for (unsigned m = okm; m; m &= m - 1) {
+                  const unsigned long long k2 = __shfl_sync(FULL, hk, __ffs(m) - 1);
+                  rank += k2 < hk;
+                }
+                bool closed_l = false;
+                if (act) {
+                  const int a = h;
+                  const uint32_t rp = hr;
+                  const int c = (int)(hk >> 32);
+                  const int mytick = ltick + rank;
+                  pop_head(c);
+                  uint32_t rp2 = rp - 1 + (1u << 16);
+                  for (int j = 0; j < n_host; ++j) {  // Topology.Record, hostname groups
+                    const int times = rc.h_times[j];
+                    const int old = hc[j * kTopoCap + a];
+                    const int now = old + times > 0xFFFF ? 0xFFFF : old + times;
+                    if (times) hc[j * kTopoCap + a] = (uint16_t)now;
+                    if (now > rc.h_lim[j]) rp2 |= kRpDead;
+                  }
+                  const unsigned long long nkey = order_key(c + 1, -(mytick + 1));
+                  unsigned long long skey = nkey;
+                  rc.q_node[buf][li + rank] = -(a + 2);
+                  if ((rp2 & 0xFFFF) == 0) {  // the class no longer fits by resources: does anything? (node_closed)
+                    const int placed = (rp2 >> 16) & 0x7FFF;
+                    long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+                    for (int r = 0; r < kHotRes; ++r) { nq[r] = hs->q[r][a] + placed * p_req[r]; cb1[r] = hs->bound[r][a]; cb2[r] = hs->bound2[r][a]; }
+                    const unsigned short fl = (unsigned short)(hs->flags[a] | ((p_res & 0xF) << 1));
+                    if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
+                      skey = ~0ull;
+                      hs->nn_last[a] = ((unsigned long long)(unsigned)(c + 1) << 32) | (unsigned)(-(mytick + 1));
+                      closed_l = true;
+                    }
+                  }
+                  hs->key[a] = skey;
+                  rpv[a] = rp2;
+                  if ((rp2 & 0xFFFF) != 0 && !(rp2 & kRpDead)) insert_front(a, c + 1, nkey, rp2);
+                  ++cnt_d;
+                }
+                const unsigned tb = __ballot_sync(FULL, closed_l);
+                if (L == 0 && tb) rc.tomb = rc.tomb + __popc(tb);
+                ltick += na;
+                li += na;
+                __syncwarp();
+                continue;
+              }
+            }
+          }
           if (wkey != ~0ull) {
             const int wl = __ffs(__ballot_sync(FULL, key == wkey)) - 1;
             const int a = __shfl_sync(FULL, h, wl);
@@ -1863,18 +1954,7 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
               if (!((rc.m_neutral[0] >> d) & 1) || !((zv[a] & (1u << 17)) || rc.m_wk[0])) { reason = 1; break; }
             }
             const int c = (int)(wkey >> 32);
-            if (L == wl) {  // pop: the node behind the head moves up, the one behind that is fetched (used at this list's next pop)
-              h = n1; hk = nk; hr = nr;
-              n1 = -1; nk = ~0ull; nr = 0;
-              if (h >= 0) {
-                n1 = nxt_of(h);
-                if (n1 >= 0) { nk = hs->key[n1]; nr = rpv[n1]; }
-              }
-              if (h < 0 || (int)(hk >> 32) != c) {  // the bucket of count c is exhausted
-                m1.tl[c][L] = kM1None;
-                level_state();
-              }
-            }
+            if (L == wl) pop_head(c);
             // ---- commit (the per-pod loop's commit, relation by relation on the first lanes)
             uint32_t rp2 = rp - 1 + (1u << 16);
             bool dead_l = false;
