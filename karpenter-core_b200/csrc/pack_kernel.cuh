@@ -1391,6 +1391,8 @@ struct M1Ctx {
   int bcnt[kM1Lv * kM1Lists];         // build: members per bucket (bucket = list * kM1Lv + count)
   int bad;                            // build: a node the lists cannot represent
   int out_adv, out_reason, out_tick, out_n_new, out_n_active;
+  int n_fresh;                        // nodes created by this entry of the warp loop: slot | variant << 16; their global
+  uint32_t fr[kRunChunk];             // state (option words, requirement values, requests, ...) is stored by the CTA afterwards
 };
 __shared__ M1Ctx g_m1;
 
@@ -1854,7 +1856,7 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         // a pinned node at hand and the unpinned nodes come later in the order, the next pods go one to each of these domains,
         // smallest head key first - a whole round is committed at once, every lane its own domain
         const bool rounds = m_rec0 && m_bias0 == 0;
-        int li = i, ltick = tick, lnew = n_new, lact = n_active;
+        int li = i, ltick = tick, lnew = n_new, lact = n_active, nfr = 0;
         int i_end = rc.q_end[buf];
         if (i + qlen < i_end) i_end = i + qlen;
         int reason = 0;  // 0: the staged entries of the class are consumed; 1: the pod at li needs generic_step; 2: per-pod loop from li on
@@ -1973,7 +1975,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
                 const int n = hs->node[a], k = rc.m_key[0];
                 zv[a] = (1u << d) | (3u << 16);
                 s.nn_vals[(size_t)k * MAXN + n] = 1ull << d;
-                s.nn_meta[n] = (s.nn_meta[n] | (1ull << (KSCHED_META_PRESENT_SHIFT + k))) & ~(1ull << (KSCHED_META_COMPLEMENT_SHIFT + k));
+                // two reductions instead of a read-modify-write: the load would stall the whole chain for an L2 round trip
+                atomicOr(reinterpret_cast<unsigned long long*>(&s.nn_meta[n]), 1ull << (KSCHED_META_PRESENT_SHIFT + k));
+                atomicAnd(reinterpret_cast<unsigned long long*>(&s.nn_meta[n]), ~(1ull << (KSCHED_META_COMPLEMENT_SHIFT + k)));
               }
               rc.q_node[buf][li] = -(a + 2);  // the slot: translated to the node when the chunk is stored
               if ((rp2 & 0xFFFF) == 0) {  // the class no longer fits by resources: does anything? (node_closed)
@@ -2015,9 +2019,6 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
             if (vi < 0) { reason = 1; break; }
             const RunVariant& v = rc.var[vi];
             const int n = lnew, a = lact;
-            for (int w = L; w < W32; w += 32) s.nn_opts[(size_t)w * MAXN + n] = v.opts[w];
-            if (L < c.n_keys) s.nn_vals[(size_t)L * MAXN + n] = v.vals[L];
-            if (L < KSCHED_MAX_RES) s.nn_req[(size_t)L * MAXN + n] = v.q[L];
             if (L < n_host) {
               const int times = rc.h_times[L];
               hc[L * kTopoCap + a] = (uint16_t)times;
@@ -2036,15 +2037,11 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
               hs->absorbed[a] = simple ? cls : KSCHED_NONE;
               hs->rejected[a] = KSCHED_NONE;
               rpv[a] = v.rp;
-              s.nn_meta[n] = v.meta;
-              s.nn_tmpl[n] = (uint8_t)(v.fl >> 8);
-              s.nn_req_present[n] = v.qp;
-              s.nn_hp[n] = 0;
-              s.nn_count[n] = 1;
-              s.nn_tb[n] = ltick + 1;
               rc.q_node[buf][li] = NE + n;
               zv[a] = (1u << fd) | (3u << 16);
+              m1.fr[nfr] = (uint32_t)a | ((uint32_t)vi << 16);  // nothing in this loop reads the node's global state
             }
+            ++nfr;
             if (L == fd) {
               if ((v.rp & 0xFFFF) != 0 && !(v.rp & kRpDead)) insert_back1(a, fkey, v.rp);  // accepts further pods of the class
               if (m_rec0) ++cnt_d;
@@ -2057,9 +2054,31 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
         // every warp's copy of the spread counters follows (the per-pod loop and the write-back read them)
         if (L < kM1Dom) for (int w = 0; w < nwarps; ++w) rc.cnt[w][0][L] = cnt_d;
         if (L < kM1Lists) m1.head[L] = h >= 0 ? (uint16_t)h : kM1None;
-        if (L == 0) { m1.out_adv = li - i; m1.out_reason = reason; m1.out_tick = ltick; m1.out_n_new = lnew; m1.out_n_active = lact; }
+        if (L == 0) { m1.out_adv = li - i; m1.out_reason = reason; m1.out_tick = ltick; m1.out_n_new = lnew; m1.out_n_active = lact; m1.n_fresh = nfr; }
       }
       __syncthreads();
+      {  // the global state of the nodes the warp loop created, 64 words per node across the CTA
+        const int nfr = m1.n_fresh;
+        for (int e = tid; e < nfr * 64; e += T) {
+          const uint32_t rec = m1.fr[e >> 6];
+          const int a = (int)(rec & 0xFFFF), w = e & 63;
+          const RunVariant& v = rc.var[rec >> 16];
+          const int n = hs->node[a];
+          if (w < W32) s.nn_opts[(size_t)w * MAXN + n] = v.opts[w];
+          if (w < c.n_keys) s.nn_vals[(size_t)w * MAXN + n] = v.vals[w];
+          if (w < KSCHED_MAX_RES) s.nn_req[(size_t)w * MAXN + n] = v.q[w];
+          if (w == 0) {
+            s.nn_meta[n] = v.meta;
+            s.nn_tmpl[n] = (uint8_t)(v.fl >> 8);
+            s.nn_req_present[n] = v.qp;
+            s.nn_hp[n] = 0;
+            if (((rpv[a] >> 16) & 0x7FFF) == 0) {  // no further pod so far: (1, creation tick); otherwise the run's write-back stores them
+              s.nn_count[n] = 1;
+              s.nn_tb[n] = (int)((unsigned)hs->key[a] ^ 0x80000000u);
+            }
+          }
+        }
+      }
       const int m_adv = m1.out_adv, m_reason = m1.out_reason;
       tick = m1.out_tick; n_new = m1.out_n_new; n_active = m1.out_n_active;
       qi += m_adv;
