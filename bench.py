@@ -330,6 +330,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and "KSCHED_HOST_THREADS" not in os.environ:
+        # the host encoder / decoder split their per-pod and per-node passes over the cores: N replicas share the box
+        os.environ["KSCHED_HOST_THREADS"] = str(max(2, min(16, (os.cpu_count() or 16) // world)))
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -453,8 +456,10 @@ def main():
                "parallelism": "1 Solve per GPU" + (f", {world} independent replicas (seed 42 + rank), no data-path collective" if world > 1 else ""),
                "phases_ms_per_step": {k[:-3]: v / args.steps / 1000 for k, v in phase.items()},
                "encode_host_ms": 1000 * encode_s, "catalog_load_ms": 1000 * catalog_s, "wall_ms_per_step": 1000 * wall / args.steps,
-               "library_kernels_per_step": "3x cub::DeviceRadixSort::SortPairs (not counted in gpu_launches)",
-               "limiter": "pack_kernel: one CTA, a sequential first-fit chain over the pods (DESIGN.md section 4)"}
+               "library_kernels_per_step": "1x cub::DeviceRadixSort::SortPairs over the packed key's significant bits (3 cub kernels, not counted in gpu_launches)",
+               "host_threads": os.environ.get("KSCHED_HOST_THREADS", "default (up to 16)"),
+               "limiter": "pack_kernel: one CTA, a sequential first-fit chain over the pods; closed-form steps (level / fill / bulk fresh nodes / "
+                          "rounds of the mask run) place several pods per iteration (DESIGN.md section 4)"}
     line = {
         "metric": "pods scheduled/sec (Scheduler.Solve)", "value": value, "unit": "pods/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -468,8 +473,9 @@ def main():
                 "same_result_as_resident_run": e2e_same,
                 "solve_only": {"value": all_scheduled * args.steps / so_s, "unit": "pods/s", "ms_per_step": 1000 * so_s / args.steps,
                                "path": "ksched_solve(handle, problem*, result*) with host buffers (flat structs in and out)"}},
-        # own kernels per resident Solve: sort_keys, 2x gather_u64, gather_rows, class_feasibility, feasibility, pack, finalize_options
-        "gpu_launches": 8 * args.steps,
+        # own kernels per resident Solve: reset_kernel, sort_key1, gather_rows, class_feasibility, feasibility, pack, finalize_options
+        # (profiles/r02b_launch_shares.txt)
+        "gpu_launches": 7 * args.steps,
         "roofline": {"kernel": "pack_kernel", "bound": "hbm", "achieved": pack_gbs, "peak": peak, "unit": "GB/s", "frac": pack_gbs / peak,
                      "traffic": ncu_traffic(f"pack_kernel_c{args.config}"), "peak_source": peak_src, "algorithmic_bytes": int(pack_bytes),
                      "us_per_launch": pack_avg_us,
