@@ -1882,25 +1882,38 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
             if (L == 0 && na > 1) s.counters[19] += 1;
           }
 #endif
-          if (rounds && wkey != ~0ull) {
+          if (rounds) {
             const int na = __popc(okm);
             if (na > 1 && i_end - li >= na) {
               const bool act = L < kM1Dom && allowed;
-              const unsigned have = __ballot_sync(FULL, act && h >= 0);
-              const bool bad_l = act && h >= 0 && ((hr & 0xFFFF) == kRoomSlow || (int)(hk >> 32) + 1 >= kM1Lv);
+              const bool hd = act && h >= 0;                       // this domain's pod goes to the head of its list
+              const unsigned hv = __ballot_sync(FULL, hd), fv = okm & ~hv;  // fv: domains that get a fresh node (no pinned node at hand)
+              const bool bad_l = hd && ((hr & 0xFFFF) == kRoomSlow || (int)(hk >> 32) + 1 >= kM1Lv);
               const unsigned long long ukey = __shfl_sync(FULL, hk, kM1Dom);
-              const unsigned hi = act ? (unsigned)(hk >> 32) : 0u;
+              const unsigned hi = hd ? (unsigned)(hk >> 32) : 0u;
               const unsigned mhi = __reduce_max_sync(FULL, hi);
-              const unsigned mlo = __reduce_max_sync(FULL, (act && hi == mhi) ? (unsigned)hk : 0u);
+              const unsigned mlo = __reduce_max_sync(FULL, (hd && hi == mhi) ? (unsigned)hk : 0u);
               const unsigned long long mx = ((unsigned long long)mhi << 32) | mlo;  // largest head key of the round
-              if (have == okm && !__any_sync(FULL, bad_l) && ukey > mx) {
+              // fresh nodes come last in a round, lowest domain id first (every admissible domain has the same count: run_pick
+              // takes the lowest id), and only when no unpinned node is left (it would be taken first)
+              int vi_l = -1;
+              const int nf = __popc(fv);
+              bool fresh_ok = true;
+              if (fv) {
+                const bool fl = act && h < 0;
+                if (fl) for (int v2 = 0; v2 < rc.n_var && vi_l < 0; ++v2) if (rc.var[v2].dom[0] == L) vi_l = v2;
+                fresh_ok = ukey == ~0ull && (fv & ~rc.m_tallow[0]) == 0 && !__any_sync(FULL, fl && vi_l < 0) && lnew + nf <= MAXN &&
+                           lact + nf <= kActCap && lact + nf <= kTopoCap;
+                for (int j = 0; j < n_host; ++j) fresh_ok = fresh_ok && rc.h_lim[j] >= 0;
+              }
+              if (fresh_ok && !__any_sync(FULL, bad_l) && (hv == 0 || ukey > mx)) {
                 int rank = 0;  // position of this lane's node in the round
-                for (unsigned m = okm; m; m &= m - 1) {
+                for (unsigned m = hv; m; m &= m - 1) {
                   const unsigned long long k2 = __shfl_sync(FULL, hk, __ffs(m) - 1);
                   rank += k2 < hk;
                 }
                 bool closed_l = false;
-                if (act) {
+                if (hd) {
                   const int a = h;
                   const uint32_t rp = hr;
                   const int c = (int)(hk >> 32);
@@ -1933,9 +1946,37 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
                   rpv[a] = rp2;
                   if ((rp2 & 0xFFFF) != 0 && !(rp2 & kRpDead)) insert_front(a, c + 1, nkey, rp2);
                   ++cnt_d;
+                } else if (act) {  // NewNode + Add replayed from the variant of this lane's domain
+                  const RunVariant& v = rc.var[vi_l];
+                  const int idx = __popc(fv & ((1u << L) - 1u));
+                  const int n = lnew + idx, a = lact + idx;
+                  const int mytick = ltick + __popc(hv) + idx;
+                  for (int j = 0; j < n_host; ++j) {
+                    const int times = rc.h_times[j];
+                    hc[j * kTopoCap + a] = (uint16_t)times;
+                    if (times) s.grp_host[(size_t)rc.h_row[j] * hstride + NE + n] = (uint16_t)times;
+                  }
+                  const unsigned long long fkey = order_key(1, mytick + 1);
+                  hs->key[a] = fkey;
+#pragma unroll
+                  for (int r = 0; r < kHotRes; ++r) { hs->q[r][a] = v.q[r]; hs->bound[r][a] = v.b1[r]; hs->bound2[r][a] = v.b2[r]; }
+                  hs->node[a] = n;
+                  hs->flags[a] = v.fl;
+                  hs->absorbed[a] = simple ? cls : KSCHED_NONE;
+                  hs->rejected[a] = KSCHED_NONE;
+                  rpv[a] = v.rp;
+                  rc.q_node[buf][li + __popc(hv) + idx] = NE + n;
+                  zv[a] = (1u << L) | (3u << 16);
+                  m1.fr[nfr + idx] = (uint32_t)a | ((uint32_t)vi_l << 16);
+                  if ((v.rp & 0xFFFF) != 0 && !(v.rp & kRpDead)) insert_back1(a, fkey, v.rp);
+                  ++cnt_d;
                 }
+                if (nf && L < n_host && rc.h_times[L]) rc.h_inc[L] = rc.h_inc[L] + nf;
                 const unsigned tb = __ballot_sync(FULL, closed_l);
                 if (L == 0 && tb) rc.tomb = rc.tomb + __popc(tb);
+                lnew += nf;
+                lact += nf;
+                nfr += nf;
                 ltick += na;
                 li += na;
                 __syncwarp();
