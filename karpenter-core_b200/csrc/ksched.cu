@@ -1071,6 +1071,7 @@ static int run_pack(ksched_handle* h) {
   s.use_level_step = std::getenv("KSCHED_NO_LEVELSTEP") ? 0 : 1;
   s.use_level_run = std::getenv("KSCHED_NO_LEVELRUN") ? 0 : 1;
   s.use_mask_run = std::getenv("KSCHED_NO_MASKRUN") ? 0 : 1;
+  s.use_level_warp = std::getenv("KSCHED_NO_LEVELWARP") ? 0 : 1;
   // block size: the chain is latency-bound on ONE thread's commit; more warps only help when there are many candidate
   // nodes to examine per pod (existing nodes, large in-flight sets)
   int threads = h->n_existing >= 2048 ? kPackThreads : (h->n_existing >= 256 ? 256 : 128);

@@ -2133,6 +2133,97 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       if (m_reason == 2) m1_ok = false;
       continue;
     }
+    if (lvl && n_active > 0 && n_active <= 32 && s.use_level_warp) {
+      // ---- at most 32 open nodes: the level / fill steps of the block below with ONE node per lane of warp 0 and no block
+      // barrier (slot a belongs to thread a, as in the block-wide form). Fresh nodes and winners that need the full evaluation
+      // go to the block-wide iteration below.
+      if (warp == 0) {
+        const unsigned FULL = 0xffffffffu;
+        const int a = lane;
+        const bool mine = a < n_active;
+        int li = i, ltick = tick, reason = 0;
+        int i_end = rc.q_end[buf];
+        if (i + qlen < i_end) i_end = i + qlen;
+        while (li < i_end) {
+          const uint32_t rp = mine ? rpv[a] : 0u;
+          const unsigned long long key = mine ? hs->key[a] : ~0ull;
+          const bool el = mine && (rp & 0xFFFF) != 0 && !(rp & kRpDead);
+          const unsigned elm = __ballot_sync(FULL, el);
+          if (!elm || __any_sync(FULL, el && (rp & 0xFFFF) == kRoomSlow)) { reason = 1; break; }
+          const unsigned cn = el ? (unsigned)(key >> 32) : 0xFFFFFFFFu;
+          const unsigned c_min = __reduce_min_sync(FULL, cn);
+          const bool mem = el && cn == c_min;
+          const unsigned memm = __ballot_sync(FULL, mem);
+          const int k_av = i_end - li;
+          int t = 1, rank = 0, adv_w;
+          if (!(elm & (elm - 1))) {  // fill: the only accepting node takes pods until it refuses
+            int cap = (int)(rp & 0xFFFF);
+            if (mem) {
+              for (int j = 0; j < n_host; ++j) {
+                const int times = rc.h_times[j], lim = rc.h_lim[j];
+                if (!times || lim >= 0x10000) continue;
+                if (lim >= 0xFFF0) { cap = 1; continue; }
+                const int td = (lim - (int)hc[j * kTopoCap + a]) / times + 1;
+                cap = td < cap ? td : cap;
+              }
+            }
+            t = __shfl_sync(FULL, cap, __ffs(memm) - 1);
+            t = t < k_av ? t : k_av;
+            adv_w = t;
+          } else {  // level: the accepting nodes with the fewest pods, one pod each in tie order
+            const unsigned tie = (unsigned)key;
+            for (unsigned m = memm; m; m &= m - 1) {
+              const unsigned tm = __shfl_sync(FULL, tie, __ffs(m) - 1);
+              rank += tm < tie;
+            }
+            const int n_s = __popc(memm);
+            adv_w = n_s < k_av ? n_s : k_av;
+          }
+          if (mem && rank < adv_w) {  // (fill: rank 0 < t)
+            uint32_t rp2 = rp - (uint32_t)t + ((uint32_t)t << 16);
+            for (int j = 0; j < n_host; ++j) {  // Topology.Record, hostname groups
+              const int times = rc.h_times[j];
+              const int old = hc[j * kTopoCap + a];
+              const int now = old + t * times > 0xFFFF ? 0xFFFF : old + t * times;
+              if (times) hc[j * kTopoCap + a] = (uint16_t)now;
+              if (now > rc.h_lim[j]) rp2 |= kRpDead;
+            }
+            const int count = (int)c_min + t;
+            const int tb = -(ltick + rank + t);
+            unsigned long long nkey = order_key(count, tb);
+            const int nd = NE + hs->node[a];
+            for (int e = 0; e < t; ++e) rc.q_node[buf][li + rank + e] = nd;
+            if ((rp2 & 0xFFFF) == 0) {  // the class no longer fits by resources: does anything? (node_closed)
+              const int placed = (rp2 >> 16) & 0x7FFF;
+              long long nq[kHotRes], cb1[kHotRes], cb2[kHotRes];
+#pragma unroll
+              for (int r = 0; r < kHotRes; ++r) { nq[r] = hs->q[r][a] + placed * p_req[r]; cb1[r] = hs->bound[r][a]; cb2[r] = hs->bound2[r][a]; }
+              const unsigned short fl = (unsigned short)(hs->flags[a] | ((p_res & 0xF) << 1));
+              if (node_closed(nq, min_req, RH, cb1, cb2, fl)) {
+                nkey = ~0ull;
+                hs->nn_last[a] = ((unsigned long long)(unsigned)count << 32) | (unsigned)tb;
+                atomicAdd(&rc.tomb, 1);
+              }
+            }
+            hs->key[a] = nkey;
+            rpv[a] = rp2;
+          }
+          ltick += adv_w;
+          li += adv_w;
+        }
+        if (lane == 0) { g_m1.out_adv = li - i; g_m1.out_reason = reason; g_m1.out_tick = ltick; }
+      }
+      __syncthreads();
+      const int w_adv = g_m1.out_adv, w_reason = g_m1.out_reason;
+      tick = g_m1.out_tick;
+      qi += w_adv;
+      qlen -= w_adv;
+      i += w_adv;
+      __syncthreads();  // out_* are rewritten by the next entry
+      if (qlen == 0) break;
+      if (w_reason == 0) continue;  // the staged entries of the class are consumed
+      // w_reason == 1: the pod at i takes the block-wide iteration (fresh nodes / full evaluation)
+    }
     int adv = 1;       // pods this iteration consumes
     int mode = 0;      // 0: per-pod argmin below; 1: placed by a level / fill step; 2: nobody accepts (fresh node)
     int k_avail = 1;   // pods of the class that may be consumed now: staged, same class, still queued

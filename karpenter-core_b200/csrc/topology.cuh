@@ -109,6 +109,7 @@ struct PackState {
   int use_class_run;                 // class-run loop enabled (KSCHED_NO_CLASSRUN=1 turns it off for A/B timing)
   int use_level_step;                // level step of the warp loop enabled (KSCHED_NO_LEVELSTEP=1 turns it off for A/B timing)
   int use_level_run;                 // class_run: level / fill steps for classes without mask-key spread (KSCHED_NO_LEVELRUN=1: off)
+  int use_level_warp;                // class_run: the level / fill steps on one warp while at most 32 nodes are open (KSCHED_NO_LEVELWARP=1: off)
   int use_mask_run;                  // class_run: list-driven warp loop for one mask-key spread relation (KSCHED_NO_MASKRUN=1: off)
   // topology counters
   int32_t* grp_cnt;                  // [n_groups][64]

@@ -1,6 +1,6 @@
 """Scratch driver (not a test): pack-kernel time per configuration with the class-run modes switched on and off
 (KSCHED_NO_LEVELRUN / KSCHED_NO_MASKRUN) and per block size, resident problem, L2 flushed.
-Usage: python tests/gpu_sweep_threads.py [configs, default 2,3,4] [threads, default 128]"""
+Usage: python tests/gpu_sweep_threads.py [configs, default 2,3,4] [threads, default 128] [final]"""
 import os, sys
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from conftest import load_pkg
@@ -13,10 +13,11 @@ for cfg in cfgs:
     p = k.Problem.synth(cfg, P, T, 42, 0)
     rs = k.ResidentSolve(p); rs.set_count_visited(False); rs.load()
     base = None
-    for off in ("KSCHED_NO_LEVELRUN,KSCHED_NO_MASKRUN", "KSCHED_NO_MASKRUN", ""):
+    modes = ("KSCHED_NO_LEVELWARP", "") if len(sys.argv) > 3 and sys.argv[3] == "final" else ("KSCHED_NO_LEVELRUN,KSCHED_NO_MASKRUN", "KSCHED_NO_MASKRUN", "KSCHED_NO_LEVELWARP", "")
+    for off in modes:
         for threads in threads_list:
             os.environ["KSCHED_PACK_THREADS"] = str(threads)
-            for v in ("KSCHED_NO_LEVELRUN", "KSCHED_NO_MASKRUN"):
+            for v in ("KSCHED_NO_LEVELRUN", "KSCHED_NO_MASKRUN", "KSCHED_NO_LEVELWARP"):
                 os.environ.pop(v, None)
             for v in off.split(","):
                 if v: os.environ[v] = "1"
