@@ -93,6 +93,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def mark(self):
+        """the timed region starts here: earlier samples (nvidia-smi needs a few hundred ms to start) are dropped"""
+        self.samples = []
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
@@ -383,11 +387,12 @@ def main():
         return float(tt.item())
 
     # ---- value: resident problem, kernels only
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi is up and sampling by the time the warm-ups are done
     for _ in range(args.warmup):
         rs.run(flush_l2=True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     phase = {"sort_us": 0.0, "feasibility_us": 0.0, "pack_us": 0.0, "allreduce_us": 0.0, "total_us": 0.0}
     wall0 = time.perf_counter()
     for _ in range(args.steps):
