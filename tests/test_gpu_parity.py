@@ -168,3 +168,31 @@ def test_consolidation_known_answers_match_oracle(pkg, oracle, name, ref, build)
         return got
 
     check(probe, search)
+
+
+CLASS_RUN_SWITCHES = ("KSCHED_NO_LEVELWARP", "KSCHED_NO_MASKRUN", "KSCHED_NO_LEVELRUN", "KSCHED_NO_CLASSRUN")
+
+
+@pytest.mark.parametrize("config,pods,types,seed", [(4, 6000, 1000, 7), (4, 2500, 1000, 3), (3, 5000, 1000, 7), (2, 3000, 500, 7), (2, 4000, 40, 9)])
+def test_class_run_modes_agree(pkg, monkeypatch, config, pods, types, seed):
+    """The closed-form steps of the class-run loop (level / fill steps and fresh nodes in bulk, their one-warp form, the mask
+    run with its rounds) are exact: with each of them switched off (KSCHED_NO_*: the per-pod loop or the generic step then
+    places the same pods one at a time) the whole result is the same, bit for bit (scheduler.go:174-219 is one pod at a
+    time; DESIGN.md section 4 says why several at once give the same answer)."""
+    problem = pkg.Problem.synth(config, pods, types, seed, 0)
+    rs = pkg.ResidentSolve(problem)
+    rs.set_count_visited(False)
+    rs.load()
+    digests = {}
+    for off in ("", "KSCHED_NO_LEVELWARP", "KSCHED_NO_MASKRUN", "KSCHED_NO_LEVELRUN,KSCHED_NO_MASKRUN", "KSCHED_NO_CLASSRUN"):
+        for v in CLASS_RUN_SWITCHES:
+            monkeypatch.delenv(v, raising=False)
+        for v in off.split(","):
+            if v:
+                monkeypatch.setenv(v, "1")
+        rs.run()
+        res = rs.download()
+        digests[off or "all on"] = (int(res.digest()), int(res.num_new_nodes), int((res.assign >= 0).sum()))
+    for v in CLASS_RUN_SWITCHES:
+        monkeypatch.delenv(v, raising=False)
+    assert len(set(digests.values())) == 1, digests
