@@ -16,6 +16,7 @@
 #include <functional>
 #include <limits>
 #include <tuple>
+#include <unordered_map>
 #include <unordered_set>
 #include <set>
 #include <stdexcept>
@@ -217,6 +218,41 @@ bool same_spec(const Pod& a, const Pod& b) {
                   }) &&
          same_vec(a.tolerations, b.tolerations,
                   [](const Toleration& x, const Toleration& y) { return x.key == y.key && x.op == y.op && x.value == y.value && x.effect == y.effect; });
+}
+
+// A hash of (a subset of) what same_spec compares: equal specs hash equally, so a pod that starts a new run of its batch
+// finds the class of an earlier run by hash + one same_spec against that class's first pod, without building the key string.
+uint64_t spec_hash(const Pod& p) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  auto mix = [&](uint64_t v) { h = (h ^ v) * 0x100000001b3ull; h ^= h >> 29; };
+  auto str = [&](const std::string& x) { mix(x.size()); for (unsigned char ch : x) h = (h ^ ch) * 0x100000001b3ull; };
+  auto labels = [&](const Labels& l) { mix(l.size()); for (auto& kv : l) { str(kv.first); str(kv.second); } };
+  auto resources = [&](const ResourceList& r) { mix(r.size()); for (auto& kv : r) { str(kv.first); mix((uint64_t)kv.second); } };
+  auto containers = [&](const std::vector<Container>& cs) {
+    mix(cs.size());
+    for (auto& c : cs) { resources(c.requests); resources(c.limits); mix(c.ports.size()); for (auto& hp : c.ports) mix((uint64_t)hp.port); }
+  };
+  str(p.ns);
+  labels(p.labels);
+  containers(p.containers);
+  containers(p.init_containers);
+  labels(p.node_selector);
+  mix((uint64_t)p.has_node_affinity * 2 + (uint64_t)p.has_required_node_affinity);
+  mix(p.required_node_terms.size());
+  for (auto& t : p.required_node_terms) { mix(t.size()); for (auto& r : t) { str(r.key); mix((uint64_t)r.op); mix(r.values.size()); } }
+  mix(p.preferred_node_terms.size());
+  for (auto& t : p.preferred_node_terms) mix((uint64_t)t.weight);
+  mix(p.pod_affinity_required.size());
+  for (auto& t : p.pod_affinity_required) str(t.topology_key);
+  mix(p.pod_affinity_preferred.size());
+  mix(p.pod_anti_affinity_required.size());
+  for (auto& t : p.pod_anti_affinity_required) str(t.topology_key);
+  mix(p.pod_anti_affinity_preferred.size());
+  mix(p.topology_spread.size());
+  for (auto& t : p.topology_spread) { mix((uint64_t)t.max_skew); str(t.topology_key); mix((uint64_t)t.schedule_anyway); }
+  mix(p.tolerations.size());
+  for (auto& t : p.tolerations) { str(t.key); str(t.effect); }
+  return h;
 }
 
 // Everything the scheduler can observe about a pod except its identity (uid / name / timestamp).
@@ -650,14 +686,16 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     // "same deployment as the previous pod" is a pure comparison of two pods: every pair at once, on all cores; only the
     // class boundaries (a few hundred in a 100 000-pod batch) take the keyed path, in order
     std::vector<uint8_t> same(NP, 0), uid_order_broken((NP >> 12) + 2, 0);
+    std::vector<uint64_t> run_hash(NP, 0);  // spec_hash of the pods that start a run
     E.pod_timestamp.resize(NP);
     parallel_ranges(NP, 4096, [&](size_t b, size_t e) {
       bool asc = true;
-      if (b == 0 && e > 0) E.pod_timestamp[0] = E.pods[0]->creation_ts;
+      if (b == 0 && e > 0) { E.pod_timestamp[0] = E.pods[0]->creation_ts; run_hash[0] = spec_hash(*E.pods[0]); }
       for (size_t i = std::max<size_t>(b, 1); i < e; ++i) {
         const Pod& p = *E.pods[i];
         const Pod& q = *E.pods[i - 1];
         same[i] = same_spec(p, q) ? 1 : 0;
+        if (!same[i]) run_hash[i] = spec_hash(p);
         asc = asc && q.uid < p.uid;
         E.pod_timestamp[i] = p.creation_ts;  // queue.go:74-110 sorts by it (per-pod queue keys below)
       }
@@ -671,7 +709,28 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
         if (!uids.insert(p->uid).second) throw std::runtime_error("pods must have unique UIDs: " + p->uid);
     }
     phase("  same_spec pairs");
-    for (size_t i = 0; i < NP; ++i) E.pod_class[i] = same[i] ? E.pod_class[i - 1] : intern(*E.pods[i]);
+    // a run's class: the class of an earlier run with the same spec (hash, then one same_spec against that class's first pod),
+    // else the keyed path (new classes, pods with volumes, pods whose containers differ but sum to the same requests)
+    std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
+    for (size_t i = 0; i < NP; ++i) {
+      if (same[i]) { E.pod_class[i] = E.pod_class[i - 1]; continue; }
+      const Pod& p = *E.pods[i];
+      uint32_t id = KSCHED_NONE;
+      if (p.volumes.empty()) {
+        auto it = by_hash.find(run_hash[i]);
+        if (it != by_hash.end())
+          for (uint32_t cid : it->second)
+            if (same_spec(p, specs[cid].pod)) { id = cid; break; }
+      }
+      if (id == KSCHED_NONE) {
+        id = intern(p);
+        if (p.volumes.empty()) {
+          auto& v = by_hash[run_hash[i]];
+          if (std::find(v.begin(), v.end(), id) == v.end()) v.push_back(id);
+        }
+      }
+      E.pod_class[i] = id;
+    }
     phase("  intern boundaries");
   }
   std::vector<Pod> daemons = P.daemonset_pods;
