@@ -557,14 +557,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   Builder B(P, E);
   const ClusterFacts& facts = cluster_facts(P);
 
-  static const bool enc_trace = std::getenv("KSCHED_ENCODE_TRACE") != nullptr;
-  auto enc_t0 = std::chrono::steady_clock::now();
-  const char* enc_prev = "setup";
-  auto enc_mark = [&](const char* next) {
-    if (enc_trace) { auto t = std::chrono::steady_clock::now(); std::fprintf(stderr, "[encode] %-40s %8.3f ms\n", enc_prev, std::chrono::duration<double, std::milli>(t - enc_t0).count()); enc_t0 = t; }
-    enc_prev = next;
-  };
-  enc_mark("who takes part");
   // ------------------------------------------------------------------ who takes part
   std::vector<int> state_nodes;
   {
@@ -610,7 +602,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     for (auto& t : pr.taints) if (t.effect == "PreferNoSchedule") tolerate_pns = true;
 
   phase("who takes part");
-  enc_mark("CSI volume limits");
   // ------------------------------------------------------------------ CSI volume limits (ksched.h: ksched_class_volumes)
   // Drivers some owned state node limits; claims by how many pods (batch + bound) mount them: one -> counted, several -> tracked id.
   std::vector<std::string> vol_drivers;
@@ -657,7 +648,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     return (cv.shared | cv.priv[0] | cv.priv[1] | cv.priv[2] | cv.priv[3]) ? std::string(b) : std::string();
   };
 
-  enc_mark("pod specs: classes and relaxation chains");
   // ------------------------------------------------------------------ pod specs: classes and relaxation chains
   struct Spec { Pod pod; ResourceList req; uint32_t next = KSCHED_NONE; };
   std::vector<Spec> specs;
@@ -736,7 +726,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   std::vector<Pod> daemons = P.daemonset_pods;
 
   phase("pod classes");
-  enc_mark("active keys + dictionary");
   // ------------------------------------------------------------------ active keys + dictionary
   // pod-side keys: anything a pod / daemonset / topology group / node filter can put into a node's requirements
   std::set<std::string> pod_side;
@@ -870,7 +859,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("keys + dictionary");
-  enc_mark("resources");
   // ------------------------------------------------------------------ resources
   {
     std::set<std::string> names;
@@ -887,7 +875,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("resources");
-  enc_mark("instance types");
   // ------------------------------------------------------------------ instance types (columns, price order)
   const int NT = (int)P.instance_types.size();
   E.type_words = (NT + 63) / 64;
@@ -961,7 +948,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   // (When zone/ct keys are inactive every offering maps to z=0/ct=0 above, which is exactly "key not constrained".)
 
   phase("instance types");
-  enc_mark("templates");
   // ------------------------------------------------------------------ templates
   const int NV = (int)E.template_provisioner.size();
   E.templates.resize(NV);
@@ -1004,7 +990,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   E.template_bounds = tb;
 
   phase("templates");
-  enc_mark("daemonset overhead");
   // ------------------------------------------------------------------ daemonset overhead (scheduler.go:250-267)
   auto daemon_reqs = [&](const Pod& d, ksched_reqset& rs, ksched_bounds& bd) {
     Builder::Special sp;
@@ -1029,7 +1014,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("daemonset overhead");
-  enc_mark("existing nodes");
   // ------------------------------------------------------------------ existing nodes (scheduler.go:221-248, existingnode.go:41-75)
   std::map<std::string, int> hostname_slot;  // hostname -> existing slot
   for (int si : state_nodes) {
@@ -1125,7 +1109,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   const int NE = (int)E.existing.size();
 
   phase("existing nodes");
-  enc_mark("topology groups");
   // ------------------------------------------------------------------ topology groups (topology.go)
   std::vector<Group> groups;
   std::map<std::string, size_t> group_of;          // hash -> index, non-inverse
@@ -1410,7 +1393,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("topology groups");
-  enc_mark("class rows");
   // ------------------------------------------------------------------ class rows
   const int NC = (int)specs.size();
   E.classes.resize(NC);
@@ -1531,7 +1513,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("class rows");
-  enc_mark("per-pod queue keys");
   // ------------------------------------------------------------------ per-pod queue keys (queue.go:74-110)
   E.pod_uid_rank.resize(NP);
   {
@@ -1546,7 +1527,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
   }
 
   phase("queue keys");
-  enc_mark("wire up the flat structs");
   // ------------------------------------------------------------------ wire up the flat structs
   ksched_catalog& cat = E.catalog;
   cat.n_keys = NK; cat.n_res = (int)E.res_names.size(); cat.n_types = NT; cat.n_templates = NV;
@@ -1598,7 +1578,6 @@ std::unique_ptr<Encoded> encode(const Problem& P, const std::vector<int>& candid
     E.classes[c].meta = rs.meta;
   }
   cat.key_regions = E.key_regions.empty() ? nullptr : E.key_regions.data();
-  enc_mark("end");
   return enc;
 }
 
