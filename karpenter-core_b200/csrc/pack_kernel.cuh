@@ -1589,9 +1589,9 @@ __device__ __noinline__ void class_run(const PodRegs& first_in) {
       for (int j = 0; j < kRunMask; ++j) same = same && (j >= n_mask || rc.var[i].dom[j] == dom[j]);
       if (same) ok = false;  // already known
     }
+    const int slot = rc.var_next;  // read BEFORE the barrier: thread 0 moves it while the others still copy (racecheck warning, round 2)
     __syncthreads();  // rc.n_var / var_next read by everybody before thread 0 moves them
     if (ok) {
-      const int slot = rc.var_next;
       RunVariant& v = rc.var[slot];
       for (int w = tid; w < W32; w += T) v.opts[w] = s.nn_opts[(size_t)w * MAXN + n];
       if (tid < KSCHED_MAX_KEYS) v.vals[tid] = tid < c.n_keys ? s.nn_vals[(size_t)tid * MAXN + n] : 0;
